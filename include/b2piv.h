@@ -1,0 +1,94 @@
+/* b2piv.h - C ABI of the B200-native LSPIV cross-correlation engine (libb2piv.so).
+ *
+ * Drop-in boundary for the ONE hot path of localdevices/pyorc: Frames.get_piv -> get_ffpiv -> ffpiv.  Every entry
+ * point cites the reference interface it replaces (paths relative to the pyorc tree @ be7d7c8, v0.9.9).
+ * Plain pointers and sizes only; no torch / numpy types; never throws; every call returns a status code and
+ * b2piv_last_error() explains a failure.  There is no CPU fallback anywhere behind this ABI.
+ *
+ * Conventions
+ *   frames      : [n_frames][height][width] row-major, dtype B2PIV_U8 or B2PIV_F32 (what pyorc hands to
+ *                 ffpiv.cross_corr as `frame_chunk.values`, pyorc/velocimetry/ffpiv.py:223,451)
+ *   windows     : flattened row-major, index r*n_cols + c (reshape at ffpiv.py:469-470)
+ *   u, v        : pixels / frame; u = column (x) shift, v = row (y, image-down) shift; no sign flip
+ *                 (ffpiv.py:325-326,418-419 scale them by res/dt only)
+ *   outputs     : float32, [n_frames-1][n_rows*n_cols]
+ */
+#ifndef B2PIV_H
+#define B2PIV_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2piv_engine b2piv_engine;
+
+enum { B2PIV_OK = 0, B2PIV_ERR_ARG = 1, B2PIV_ERR_CUDA = 2, B2PIV_ERR_UNSUPPORTED = 3, B2PIV_ERR_STATE = 4 };
+enum { B2PIV_U8 = 0, B2PIV_F32 = 1 };
+
+/* ABI version (major*100 + minor). */
+int b2piv_version(void);
+
+/* Engine bound to one CUDA device (one per thread and device; calls on one engine are serialised by the caller,
+ * exactly like the reference's single-threaded chunk loop, ffpiv.py:348,399). */
+int b2piv_create(b2piv_engine** out, int device);
+void b2piv_destroy(b2piv_engine* e);
+/* Message of the last failing call on `e` (or of the last failing b2piv_create when e == NULL). */
+const char* b2piv_last_error(const b2piv_engine* e);
+
+/* Numerical switches for the details that live in ffpiv rather than pyorc (see oracle/ffpiv_oracle.py):
+ *   "clip_normalized" (0/1), "border_nan" (0/1), "gauss_eps" (float), "copy_chunks" (H2D pipeline depth). */
+int b2piv_set_option(b2piv_engine* e, const char* name, double value);
+
+/* Plan = frame geometry + window geometry.  Replaces the geometry half of ffpiv.cross_corr and
+ * ffpiv.window.get_rect_coordinates (pyorc/api/frames.py:85-90): n_rows=(H-wy)/(wy-oy)+1, n_cols likewise.
+ * Supported windows: powers of two 16..128 per axis; search_area_size == window_size as pyorc
+ * always passes (frames.py:168). */
+int b2piv_plan(b2piv_engine* e, int height, int width, int win_y, int win_x, int ovl_y, int ovl_x, int dtype,
+               int* n_rows, int* n_cols);
+
+/* Per-time-step PIV on HOST buffers: the call behind `_get_uv_timestep` (ffpiv.py:446-474), i.e.
+ * cross_corr + nanmax + nanmean + u_v_displacement fused.  Copies frames H2D in chunks overlapped with compute,
+ * copies the four result fields back, synchronises.  signal_threshold < 0 means None (ffpiv.py:93-97). */
+int b2piv_pairs_host(b2piv_engine* e, const void* frames, int n_frames, float signal_threshold, float* u, float* v,
+                     float* corr_max, float* s2n);
+
+/* Same on DEVICE-resident frames (stream-ordered, no synchronisation): rows `pitch_bytes` apart, frames
+ * `frame_stride_bytes` apart.  Output pointers are device memory.  `cuda_stream` is a cudaStream_t (may be 0). */
+int b2piv_pairs_device(b2piv_engine* e, const void* d_frames, long long frame_stride_bytes, int pitch_bytes,
+                       int n_frames, float signal_threshold, float* d_u, float* d_v, float* d_corr_max, float* d_s2n,
+                       void* cuda_stream);
+
+/* Triage entry: the full correlation planes ffpiv.cross_corr returns (ffpiv.py:222-231), fftshifted, /N, clipped,
+ * float32 [n_frames-1][n_windows][wy][wx] on the host.  Not part of the fast path. */
+int b2piv_corr_planes_host(b2piv_engine* e, const void* frames, int n_frames, float signal_threshold, float* corr);
+
+/* Ensemble-correlation mode (`_get_ffpiv_mean`, ffpiv.py:182-376).
+ *   begin      : zero the per-window plane sums / valid counts (ffpiv.py:345)
+ *   add        : process_frame_chunk + accumulation (ffpiv.py:200-243, :359-365); returns the masked per-pair
+ *                corr_max and s2n [n_frames-1][n_windows] that aggregate_results averages on the host
+ *   finish     : count filter, mean plane, peak fit (ffpiv.py:280-282, :324); min_count = count_min * n_chunks
+ *   accum      : device pointers of the accumulators so ranks can all-reduce them (NCCL) before `finish`. */
+int b2piv_ens_begin(b2piv_engine* e);
+int b2piv_ens_add_host(b2piv_engine* e, const void* frames, int n_frames, float corr_min, float s2n_min,
+                       float signal_threshold, float* corr_max, float* s2n);
+int b2piv_ens_add_device(b2piv_engine* e, const void* d_frames, long long frame_stride_bytes, int pitch_bytes,
+                         int n_frames, float corr_min, float s2n_min, float signal_threshold, float* d_corr_max,
+                         float* d_s2n, void* cuda_stream);
+int b2piv_ens_accum(b2piv_engine* e, float** d_plane_sum, float** d_count, long long* n_plane_floats,
+                    long long* n_windows);
+int b2piv_ens_finish_host(b2piv_engine* e, float min_count, float* u, float* v, float* count);
+
+/* Page-locked host memory so H2D copies run at full PCIe rate without staging. */
+void* b2piv_host_alloc(size_t bytes);
+void b2piv_host_free(void* p);
+
+/* Introspection for bench.py: CUDA-event time (ms) spent in PIV kernels during the last *_host call, and the
+ * number of kernels this engine has launched since creation. */
+int b2piv_last_kernel_ms(const b2piv_engine* e, float* ms);
+long long b2piv_launch_count(const b2piv_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2PIV_H */

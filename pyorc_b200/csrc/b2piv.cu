@@ -1,0 +1,705 @@
+// b2piv.cu - kernels + C ABI (include/b2piv.h) of the B200-native LSPIV engine.  sm_100a only.
+//
+// Replaces the ffpiv/rocket-fft CPU path that pyorc/velocimetry/ffpiv.py calls (cross_corr, u_v_displacement)
+// with ONE fused kernel per frame-pair batch: window gather -> normalise -> packed complex 2-D FFT -> cross
+// spectrum -> inverse FFT -> fftshift,/N,clip -> max / mean / first-argmax -> 3-point Gaussian sub-pixel fit.
+#include "../../include/b2piv.h"
+#include "piv_core.cuh"
+
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace b2piv;
+
+// ------------------------------------------------------------------------------------------------------------
+// Kernels
+// ------------------------------------------------------------------------------------------------------------
+// Per-time-step: persistent CTAs stride over (frame pair, window pair) work items.
+template <class C>
+__global__ void __launch_bounds__(C::NT) piv_pairs_kernel(Params p, const float2* __restrict__ twx,
+                                                          const float2* __restrict__ twy, int n_items) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<C>& s = *reinterpret_cast<Smem<C>*>(smem_raw);
+    const int tid = threadIdx.x;
+    phase_init<C>(s, tid, twx, twy);
+    __syncthreads();
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const Item it = decode_item<C>(p, item);
+        phase_load<C>(s, tid, p, it);            __syncthreads();
+        phase_stats<C>(s, tid, p);               __syncthreads();
+        phase_center<C>(s, tid, p);              __syncthreads();
+        phase_stats_f32<C>(s, tid, p);
+        fft_pass<C, C::NWIN, 0, 0, 0>(s, tid);   __syncthreads();
+        fft_pass<C, C::NWIN, 0, 1, 0>(s, tid);   __syncthreads();
+        fft_pass<C, C::NWIN, 1, 0, 0>(s, tid);   __syncthreads();
+        fft_pass<C, C::NWIN, 1, 1, 0>(s, tid);   __syncthreads();
+        phase_cross<C>(s, tid);                  __syncthreads();
+        fft_pass<C, 1, 1, 1, 1>(s, tid);         __syncthreads();
+        fft_pass<C, 1, 1, 0, 1>(s, tid);         __syncthreads();
+        fft_pass<C, 1, 0, 1, 1>(s, tid);         __syncthreads();
+        fft_pass<C, 1, 0, 0, 1>(s, tid);         __syncthreads();
+        phase_reduce<C>(s, tid, p, it);          __syncthreads();
+        phase_peak<C>(s, tid, p, it);            __syncthreads();
+    }
+}
+
+// Ensemble accumulate: one CTA owns a window pair and walks over all frame pairs of the chunk; the masked
+// correlation planes are summed in REGISTERS and added to the HBM accumulator once per launch
+// (pyorc/velocimetry/ffpiv.py:200-243 thresholds, :361-363 accumulation).
+struct EnsParams {
+    float corr_min, s2n_min;
+    float* plane_sum;   // [n_windows][WY][WX] fftshifted coordinates
+    float* count;       // [n_windows]
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::NT) piv_ens_kernel(Params p, EnsParams ep, const float2* __restrict__ twx,
+                                                        const float2* __restrict__ twy, int n_witems) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<C>& s = *reinterpret_cast<Smem<C>*>(smem_raw);
+    const int tid = threadIdx.x;
+    constexpr int EPT = C::NPX / C::NT;
+    phase_init<C>(s, tid, twx, twy);
+    __syncthreads();
+    const int nw = p.n_rows * p.n_cols;
+    for (int wi = blockIdx.x; wi < n_witems; wi += gridDim.x) {
+        float acc[C::NWIN][EPT];
+        float cnt[C::NWIN];
+#pragma unroll
+        for (int w = 0; w < C::NWIN; ++w) {
+            cnt[w] = 0.f;
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) acc[w][k] = 0.f;
+        }
+        Item it = decode_item<C>(p, wi);  // pair 0 of this window item
+        for (int pr = 0; pr < p.n_pairs; ++pr) {
+            it.pair = pr;
+            phase_load<C>(s, tid, p, it);            __syncthreads();
+            phase_stats<C>(s, tid, p);               __syncthreads();
+            phase_center<C>(s, tid, p);              __syncthreads();
+            phase_stats_f32<C>(s, tid, p);
+            fft_pass<C, C::NWIN, 0, 0, 0>(s, tid);   __syncthreads();
+            fft_pass<C, C::NWIN, 0, 1, 0>(s, tid);   __syncthreads();
+            fft_pass<C, C::NWIN, 1, 0, 0>(s, tid);   __syncthreads();
+            fft_pass<C, C::NWIN, 1, 1, 0>(s, tid);   __syncthreads();
+            phase_cross<C>(s, tid);                  __syncthreads();
+            fft_pass<C, 1, 1, 1, 1>(s, tid);         __syncthreads();
+            fft_pass<C, 1, 1, 0, 1>(s, tid);         __syncthreads();
+            fft_pass<C, 1, 0, 1, 1>(s, tid);         __syncthreads();
+            fft_pass<C, 1, 0, 0, 1>(s, tid);         __syncthreads();
+            phase_reduce<C>(s, tid, p, it);          __syncthreads();
+#pragma unroll
+            for (int w = 0; w < C::NWIN; ++w) {
+                if (w == 1 && !it.valid1) continue;
+                const unsigned long long key = total_max_u64<C>(s, 2 * w + 0);
+                float cmax = __uint_as_float((unsigned)(key >> 32));
+                float s2n = cmax / (total_sum_f32<C>(s, 2 * w + 1) / (float)C::NPX);
+                bool ok = (cmax >= ep.corr_min) && (s2n >= ep.s2n_min) && isfinite(cmax);
+                if (p.keep && !p.keep[it.w[w]]) ok = false;   // NaN plane in the reference -> masked out
+                if (ok) {
+#pragma unroll
+                    for (int k = 0; k < EPT; ++k) {
+                        const int e = tid + k * C::NT;
+                        acc[w][k] += shifted_value<C>(s, w, e / C::WX, e % C::WX);
+                    }
+                    if (cmax > 1e-6f) cnt[w] += 1.f;
+                } else {
+                    cmax = 0.f; s2n = 0.f;
+                }
+                if (tid == 0) {
+                    const long long o = (long long)pr * nw + it.w[w];
+                    p.cmax[o] = cmax; p.s2n[o] = s2n;
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int w = 0; w < C::NWIN; ++w) {
+            if (w == 1 && !it.valid1) continue;
+            float* dst = ep.plane_sum + (long long)it.w[w] * C::NPX;
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) dst[tid + k * C::NT] += acc[w][k];
+            if (tid == 0) ep.count[it.w[w]] += cnt[w];
+        }
+    }
+}
+
+// Ensemble finish: count filter -> mean plane -> first-argmax + Gaussian (ffpiv.py:280-282, :324). One CTA/window.
+__global__ void __launch_bounds__(256) ens_finish_kernel(const float* __restrict__ plane_sum, const float* __restrict__ count,
+                                                         int wy, int wx, float min_count, int border_nan, float eps,
+                                                         float* __restrict__ u, float* __restrict__ v) {
+    __shared__ unsigned long long red[8];
+    const int w = blockIdx.x, tid = threadIdx.x;
+    const float cnt = count[w];
+    const float* pl = plane_sum + (long long)w * wy * wx;
+    const bool dead = !(cnt >= min_count);          // corr_sum[count < min] = nan
+    unsigned long long best = 0ull;
+    bool anynan = false;
+    for (int e = tid; e < wy * wx; e += 256) {
+        const float val = pl[e] / cnt;              // 0/0 -> NaN like np.divide
+        if (isnan(val)) anynan = true;
+        const unsigned long long key = ((unsigned long long)__float_as_uint(val < 0.f ? 0.f : val) << 32) |
+                                       (unsigned long long)(0xffffffffu - (unsigned)e);
+        if (!isnan(val)) best = key > best ? key : best;
+    }
+    anynan = __syncthreads_or(anynan);
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+    }
+    if ((tid & 31) == 0) red[tid >> 5] = best;
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 1; i < 8; ++i) best = red[i] > best ? red[i] : best;
+        float uu, vv;
+        if (dead || anynan) {
+            uu = vv = nanf("");
+        } else {
+            const int idx = (int)(0xffffffffu - (unsigned)(best & 0xffffffffull));
+            const int pi = idx / wx, pj = idx % wx;
+            if (pi == 0 || pi == wy - 1 || pj == 0 || pj == wx - 1) {
+                if (border_nan) uu = vv = nanf("");
+                else { uu = (float)(pj - wx / 2); vv = (float)(pi - wy / 2); }
+            } else {
+                const float lc = logf(pl[pi * wx + pj] / cnt + eps);
+                const float ll = logf(pl[(pi - 1) * wx + pj] / cnt + eps), lr = logf(pl[(pi + 1) * wx + pj] / cnt + eps);
+                const float ld = logf(pl[pi * wx + pj - 1] / cnt + eps), lu = logf(pl[pi * wx + pj + 1] / cnt + eps);
+                vv = ((float)pi + (ll - lr) / (2.f * ll - 4.f * lc + 2.f * lr)) - (float)(wy / 2);
+                uu = ((float)pj + (ld - lu) / (2.f * ld - 4.f * lc + 2.f * lu)) - (float)(wx / 2);
+            }
+        }
+        u[w] = uu; v[w] = vv;
+    }
+}
+
+// signal_threshold: fraction of non-zero pixels of a window over all frames of the call (ffpiv.py:93-97).
+__global__ void __launch_bounds__(256) signal_keep_kernel(const unsigned char* __restrict__ frames, long long frame_stride,
+                                                          int pitch, int is_f32, int n_frames, int n_cols, int wy, int wx,
+                                                          int sy, int sx, float thr, unsigned char* __restrict__ keep) {
+    __shared__ unsigned red[8];
+    const int w = blockIdx.x, tid = threadIdx.x;
+    const int r = w / n_cols, c = w % n_cols;
+    unsigned cnt = 0;
+    for (int f = 0; f < n_frames; ++f) {
+        const unsigned char* base = frames + f * frame_stride + (long long)(r * sy) * pitch;
+        for (int e = tid; e < wy * wx; e += 256) {
+            const int y = e / wx, x = c * sx + e % wx;
+            if (is_f32) cnt += (((const float*)(base + (long long)y * pitch))[x] != 0.f);
+            else        cnt += (base[(long long)y * pitch + x] != 0);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((tid & 31) == 0) red[tid >> 5] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned t = 0;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        const double score = (double)t / ((double)n_frames * wy * wx);
+        keep[w] = score >= (double)thr ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Engine
+// ------------------------------------------------------------------------------------------------------------
+struct b2piv_engine {
+    int device = 0;
+    std::string err;
+    // options
+    int clip_norm = 1, border_nan = 1, copy_chunks = 8;
+    float gauss_eps = 1e-7f;
+    // plan
+    bool planned = false;
+    int H = 0, W = 0, wy = 0, wx = 0, oy = 0, ox = 0, dtype = 0, n_rows = 0, n_cols = 0;
+    float2 *d_twx = nullptr, *d_twy = nullptr;
+    int sm_count = 0;
+    // streams / events
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+    std::vector<cudaEvent_t> ev_chunk;
+    // device workspace for *_host calls
+    unsigned char* d_frames = nullptr; size_t cap_frames = 0;
+    float* d_out = nullptr; size_t cap_out = 0;       // 4 result fields
+    float* d_planes = nullptr; size_t cap_planes = 0;
+    unsigned char* d_keep = nullptr; size_t cap_keep = 0;
+    // ensemble accumulators
+    float* d_ens_sum = nullptr; float* d_ens_cnt = nullptr; size_t cap_ens = 0; bool ens_open = false;
+    // stats
+    float last_kernel_ms = 0.f;
+    long long launches = 0;
+};
+
+static std::string g_create_err;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            e->err = std::string(#call) + ": " + cudaGetErrorString(_e);                           \
+            return B2PIV_ERR_CUDA;                                                                 \
+        }                                                                                          \
+    } while (0)
+
+static int fail(b2piv_engine* e, int code, const std::string& msg) {
+    e->err = msg;
+    return code;
+}
+
+template <class T>
+static int ensure(b2piv_engine* e, T** ptr, size_t* cap, size_t bytes) {
+    if (*cap >= bytes && *ptr) return B2PIV_OK;
+    if (*ptr) CK(cudaFree(*ptr));
+    *ptr = nullptr; *cap = 0;
+    CK(cudaMalloc((void**)ptr, bytes));
+    *cap = bytes;
+    return B2PIV_OK;
+}
+
+// ---- kernel dispatch over the compiled window configurations ------------------------------------------------
+template <class C>
+static int launch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
+    const int nw = p.n_rows * p.n_cols;
+    const int per_pair = (C::NWIN == 2) ? (nw + 1) / 2 : nw;
+    const long long n_items = (long long)per_pair * p.n_pairs;
+    if (n_items <= 0) return B2PIV_OK;
+    const size_t smem = sizeof(Smem<C>);
+    auto kern = piv_pairs_kernel<C>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::NT, smem));
+    if (occ < 1) return fail(e, B2PIV_ERR_CUDA, "kernel does not fit on an SM");
+    long long grid = (long long)occ * e->sm_count;
+    if (grid > n_items) grid = n_items;
+    kern<<<(unsigned)grid, C::NT, smem, st>>>(p, e->d_twx, e->d_twy, (int)n_items);
+    CK(cudaGetLastError());
+    e->launches++;
+    return B2PIV_OK;
+}
+
+template <class C>
+static int launch_ens(b2piv_engine* e, const Params& p, const EnsParams& ep, cudaStream_t st) {
+    const int nw = p.n_rows * p.n_cols;
+    const int n_witems = (C::NWIN == 2) ? (nw + 1) / 2 : nw;
+    if (p.n_pairs <= 0) return B2PIV_OK;
+    const size_t smem = sizeof(Smem<C>);
+    auto kern = piv_ens_kernel<C>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::NT, smem));
+    if (occ < 1) return fail(e, B2PIV_ERR_CUDA, "kernel does not fit on an SM");
+    long long grid = (long long)occ * e->sm_count;
+    if (grid > n_witems) grid = n_witems;
+    kern<<<(unsigned)grid, C::NT, smem, st>>>(p, ep, e->d_twx, e->d_twy, n_witems);
+    CK(cudaGetLastError());
+    e->launches++;
+    return B2PIV_OK;
+}
+
+// window shapes compiled in (NT threads; two windows per work item unless the planes do not fit in 227 KB)
+#define B2PIV_CONFIGS(X)      \
+    X(16, 16, 64, 2)          \
+    X(32, 32, 128, 2)         \
+    X(64, 64, 256, 2)         \
+    X(32, 64, 128, 2)         \
+    X(64, 32, 128, 2)         \
+    X(64, 128, 256, 2)        \
+    X(128, 64, 256, 2)        \
+    X(128, 128, 512, 1)
+
+static bool supported(int wy, int wx) {
+#define X(Y, XX, T, NW) if (wy == Y && wx == XX) return true;
+    B2PIV_CONFIGS(X)
+#undef X
+    return false;
+}
+
+static int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
+#define X(Y, XX, T, NW) if (e->wy == Y && e->wx == XX) return launch_pairs<Cfg<Y, XX, T, NW>>(e, p, st);
+    B2PIV_CONFIGS(X)
+#undef X
+    return fail(e, B2PIV_ERR_UNSUPPORTED, "window size not compiled in");
+}
+static int dispatch_ens(b2piv_engine* e, const Params& p, const EnsParams& ep, cudaStream_t st) {
+#define X(Y, XX, T, NW) if (e->wy == Y && e->wx == XX) return launch_ens<Cfg<Y, XX, T, NW>>(e, p, ep, st);
+    B2PIV_CONFIGS(X)
+#undef X
+    return fail(e, B2PIV_ERR_UNSUPPORTED, "window size not compiled in");
+}
+
+static Params base_params(const b2piv_engine* e, const void* d_frames, long long frame_stride, int pitch, int n_pairs) {
+    Params p;
+    memset(&p, 0, sizeof(p));
+    p.frames = d_frames; p.frame_stride = frame_stride; p.pitch = pitch; p.is_f32 = (e->dtype == B2PIV_F32);
+    p.n_rows = e->n_rows; p.n_cols = e->n_cols; p.sy = e->wy - e->oy; p.sx = e->wx - e->ox; p.n_pairs = n_pairs;
+    p.clip_norm = e->clip_norm; p.border_nan = e->border_nan; p.gauss_eps = e->gauss_eps;
+    return p;
+}
+
+static int make_keep(b2piv_engine* e, const void* d_frames, long long frame_stride, int pitch, int n_frames, float thr,
+                     cudaStream_t st) {
+    const int nw = e->n_rows * e->n_cols;
+    int rc = ensure(e, &e->d_keep, &e->cap_keep, (size_t)nw);
+    if (rc) return rc;
+    signal_keep_kernel<<<nw, 256, 0, st>>>((const unsigned char*)d_frames, frame_stride, pitch, e->dtype == B2PIV_F32, n_frames,
+                                           e->n_cols, e->wy, e->wx, e->wy - e->oy, e->wx - e->ox, thr, e->d_keep);
+    CK(cudaGetLastError());
+    e->launches++;
+    return B2PIV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int b2piv_version(void) { return 100; }
+
+const char* b2piv_last_error(const b2piv_engine* e) { return e ? e->err.c_str() : g_create_err.c_str(); }
+
+int b2piv_create(b2piv_engine** out, int device) {
+    if (!out) { g_create_err = "out is NULL"; return B2PIV_ERR_ARG; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n);
+    if (ce != cudaSuccess || n <= 0) {
+        g_create_err = std::string("no CUDA device available (") + cudaGetErrorString(ce) + "); b2piv has no CPU fallback";
+        return B2PIV_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { g_create_err = "device index out of range"; return B2PIV_ERR_ARG; }
+    cudaDeviceProp prop;
+    if ((ce = cudaSetDevice(device)) != cudaSuccess || (ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        g_create_err = std::string("cudaSetDevice: ") + cudaGetErrorString(ce);
+        return B2PIV_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        g_create_err = "b2piv is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+        return B2PIV_ERR_UNSUPPORTED;
+    }
+    b2piv_engine* e = new b2piv_engine();
+    e->device = device;
+    e->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&e->ev_k0) != cudaSuccess || cudaEventCreate(&e->ev_k1) != cudaSuccess) {
+        g_create_err = "stream/event creation failed";
+        delete e;
+        return B2PIV_ERR_CUDA;
+    }
+    *out = e;
+    return B2PIV_OK;
+}
+
+void b2piv_destroy(b2piv_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    cudaFree(e->d_twx); cudaFree(e->d_twy); cudaFree(e->d_frames); cudaFree(e->d_out); cudaFree(e->d_planes);
+    cudaFree(e->d_keep); cudaFree(e->d_ens_sum); cudaFree(e->d_ens_cnt);
+    for (auto ev : e->ev_chunk) cudaEventDestroy(ev);
+    if (e->ev_k0) cudaEventDestroy(e->ev_k0);
+    if (e->ev_k1) cudaEventDestroy(e->ev_k1);
+    if (e->s_copy) cudaStreamDestroy(e->s_copy);
+    if (e->s_comp) cudaStreamDestroy(e->s_comp);
+    delete e;
+}
+
+int b2piv_set_option(b2piv_engine* e, const char* name, double value) {
+    if (!e || !name) return B2PIV_ERR_ARG;
+    const std::string n(name);
+    if (n == "clip_normalized") e->clip_norm = value != 0.0;
+    else if (n == "border_nan") e->border_nan = value != 0.0;
+    else if (n == "gauss_eps") e->gauss_eps = (float)value;
+    else if (n == "copy_chunks") e->copy_chunks = value < 1 ? 1 : (int)value;
+    else return fail(e, B2PIV_ERR_ARG, "unknown option " + n);
+    return B2PIV_OK;
+}
+
+int b2piv_plan(b2piv_engine* e, int height, int width, int win_y, int win_x, int ovl_y, int ovl_x, int dtype,
+               int* n_rows, int* n_cols) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (dtype != B2PIV_U8 && dtype != B2PIV_F32) return fail(e, B2PIV_ERR_ARG, "dtype must be B2PIV_U8 or B2PIV_F32");
+    if (win_y <= 0 || win_x <= 0 || ovl_y < 0 || ovl_x < 0 || ovl_y >= win_y || ovl_x >= win_x)
+        return fail(e, B2PIV_ERR_ARG, "need 0 <= overlap < window_size");
+    if (height < win_y || width < win_x) return fail(e, B2PIV_ERR_ARG, "frame smaller than the interrogation window");
+    if (!supported(win_y, win_x))
+        return fail(e, B2PIV_ERR_UNSUPPORTED, "window " + std::to_string(win_y) + "x" + std::to_string(win_x) +
+                                                  " not supported (powers of two 16..128 per axis)");
+    CK(cudaSetDevice(e->device));
+    e->H = height; e->W = width; e->wy = win_y; e->wx = win_x; e->oy = ovl_y; e->ox = ovl_x; e->dtype = dtype;
+    e->n_rows = (height - win_y) / (win_y - ovl_y) + 1;
+    e->n_cols = (width - win_x) / (win_x - ovl_x) + 1;
+    // twiddle tables exp(-2 pi i j / N), computed in double
+    std::vector<float2> tx(win_x), ty(win_y);
+    for (int j = 0; j < win_x; ++j) tx[j] = make_float2((float)cos(2.0 * M_PI * j / win_x), (float)-sin(2.0 * M_PI * j / win_x));
+    for (int j = 0; j < win_y; ++j) ty[j] = make_float2((float)cos(2.0 * M_PI * j / win_y), (float)-sin(2.0 * M_PI * j / win_y));
+    if (e->d_twx) { CK(cudaFree(e->d_twx)); e->d_twx = nullptr; }
+    if (e->d_twy) { CK(cudaFree(e->d_twy)); e->d_twy = nullptr; }
+    CK(cudaMalloc((void**)&e->d_twx, sizeof(float2) * win_x));
+    CK(cudaMalloc((void**)&e->d_twy, sizeof(float2) * win_y));
+    CK(cudaMemcpy(e->d_twx, tx.data(), sizeof(float2) * win_x, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_twy, ty.data(), sizeof(float2) * win_y, cudaMemcpyHostToDevice));
+    e->planned = true;
+    e->ens_open = false;
+    if (n_rows) *n_rows = e->n_rows;
+    if (n_cols) *n_cols = e->n_cols;
+    return B2PIV_OK;
+}
+
+int b2piv_pairs_device(b2piv_engine* e, const void* d_frames, long long frame_stride_bytes, int pitch_bytes, int n_frames,
+                       float signal_threshold, float* d_u, float* d_v, float* d_corr_max, float* d_s2n, void* cuda_stream) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (!e->planned) return fail(e, B2PIV_ERR_STATE, "b2piv_plan has not been called");
+    if (!d_frames || !d_u || !d_v || !d_corr_max || !d_s2n) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
+    if (n_frames < 2) return fail(e, B2PIV_ERR_ARG, "need at least 2 frames (one pair)");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    Params p = base_params(e, d_frames, frame_stride_bytes, pitch_bytes, n_frames - 1);
+    if (signal_threshold >= 0.f) {
+        int rc = make_keep(e, d_frames, frame_stride_bytes, pitch_bytes, n_frames, signal_threshold, st);
+        if (rc) return rc;
+        p.keep = e->d_keep;
+    }
+    p.u = d_u; p.v = d_v; p.cmax = d_corr_max; p.s2n = d_s2n;
+    return dispatch_pairs(e, p, st);
+}
+
+}  // extern "C"
+
+// shared H2D pipeline: copy frames chunk-wise on s_copy, call `work(first_pair, n_pairs)` on s_comp per chunk
+template <class F>
+static int pipeline_host(b2piv_engine* e, const void* frames, int n_frames, bool pipelined, F&& work) {
+    const size_t esz = e->dtype == B2PIV_F32 ? 4 : 1;
+    const size_t fbytes = (size_t)e->H * e->W * esz;
+    int rc = ensure(e, &e->d_frames, &e->cap_frames, fbytes * n_frames);
+    if (rc) return rc;
+    const int n_pairs = n_frames - 1;
+    int chunks = pipelined ? e->copy_chunks : 1;
+    if (chunks > n_pairs) chunks = n_pairs;
+    while ((int)e->ev_chunk.size() < chunks) {
+        cudaEvent_t ev;
+        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        e->ev_chunk.push_back(ev);
+    }
+    const int per = (n_pairs + chunks - 1) / chunks;
+    CK(cudaEventRecord(e->ev_k0, e->s_comp));
+    int copied = 0;  // frames already enqueued for copy
+    for (int c = 0; c < chunks; ++c) {
+        const int p0 = c * per;
+        const int p1 = (p0 + per < n_pairs) ? p0 + per : n_pairs;
+        if (p0 >= p1) break;
+        const int need = p1 + 1;  // frames [0, p1] must be resident
+        if (need > copied) {
+            CK(cudaMemcpyAsync(e->d_frames + (size_t)copied * fbytes, (const unsigned char*)frames + (size_t)copied * fbytes,
+                               (size_t)(need - copied) * fbytes, cudaMemcpyHostToDevice, e->s_copy));
+            copied = need;
+        }
+        CK(cudaEventRecord(e->ev_chunk[c], e->s_copy));
+        CK(cudaStreamWaitEvent(e->s_comp, e->ev_chunk[c], 0));
+        rc = work(p0, p1 - p0);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(e->ev_k1, e->s_comp));
+    return B2PIV_OK;
+}
+
+extern "C" {
+
+int b2piv_pairs_host(b2piv_engine* e, const void* frames, int n_frames, float signal_threshold, float* u, float* v,
+                     float* corr_max, float* s2n) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (!e->planned) return fail(e, B2PIV_ERR_STATE, "b2piv_plan has not been called");
+    if (!frames || !u || !v || !corr_max || !s2n) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
+    if (n_frames < 2) return fail(e, B2PIV_ERR_ARG, "need at least 2 frames (one pair)");
+    CK(cudaSetDevice(e->device));
+    const size_t esz = e->dtype == B2PIV_F32 ? 4 : 1;
+    const int pitch = (int)(e->W * esz);
+    const long long fstride = (long long)e->H * pitch;
+    const size_t nw = (size_t)e->n_rows * e->n_cols, n_pairs = (size_t)n_frames - 1;
+    const size_t field = nw * n_pairs;
+    int rc = ensure(e, &e->d_out, &e->cap_out, field * 4 * sizeof(float));
+    if (rc) return rc;
+    const bool use_keep = signal_threshold >= 0.f;
+    bool keep_done = false;
+    rc = pipeline_host(e, frames, n_frames, !use_keep, [&](int p0, int np) -> int {
+        if (use_keep && !keep_done) {
+            int r2 = make_keep(e, e->d_frames, fstride, pitch, n_frames, signal_threshold, e->s_comp);
+            if (r2) return r2;
+            keep_done = true;
+        }
+        Params p = base_params(e, e->d_frames + (size_t)p0 * fstride, fstride, pitch, np);
+        p.keep = use_keep ? e->d_keep : nullptr;
+        p.u = e->d_out + 0 * field + (size_t)p0 * nw; p.v = e->d_out + 1 * field + (size_t)p0 * nw;
+        p.cmax = e->d_out + 2 * field + (size_t)p0 * nw; p.s2n = e->d_out + 3 * field + (size_t)p0 * nw;
+        return dispatch_pairs(e, p, e->s_comp);
+    });
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(u, e->d_out + 0 * field, field * sizeof(float), cudaMemcpyDeviceToHost, e->s_comp));
+    CK(cudaMemcpyAsync(v, e->d_out + 1 * field, field * sizeof(float), cudaMemcpyDeviceToHost, e->s_comp));
+    CK(cudaMemcpyAsync(corr_max, e->d_out + 2 * field, field * sizeof(float), cudaMemcpyDeviceToHost, e->s_comp));
+    CK(cudaMemcpyAsync(s2n, e->d_out + 3 * field, field * sizeof(float), cudaMemcpyDeviceToHost, e->s_comp));
+    CK(cudaStreamSynchronize(e->s_comp));
+    CK(cudaStreamSynchronize(e->s_copy));
+    CK(cudaEventElapsedTime(&e->last_kernel_ms, e->ev_k0, e->ev_k1));
+    return B2PIV_OK;
+}
+
+int b2piv_corr_planes_host(b2piv_engine* e, const void* frames, int n_frames, float signal_threshold, float* corr) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (!e->planned) return fail(e, B2PIV_ERR_STATE, "b2piv_plan has not been called");
+    if (!frames || !corr) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
+    if (n_frames < 2) return fail(e, B2PIV_ERR_ARG, "need at least 2 frames (one pair)");
+    CK(cudaSetDevice(e->device));
+    const size_t esz = e->dtype == B2PIV_F32 ? 4 : 1;
+    const int pitch = (int)(e->W * esz);
+    const long long fstride = (long long)e->H * pitch;
+    const size_t nw = (size_t)e->n_rows * e->n_cols, n_pairs = (size_t)n_frames - 1;
+    const size_t field = nw * n_pairs, pl = field * e->wy * e->wx;
+    int rc = ensure(e, &e->d_out, &e->cap_out, field * 4 * sizeof(float));
+    if (rc) return rc;
+    rc = ensure(e, &e->d_planes, &e->cap_planes, pl * sizeof(float));
+    if (rc) return rc;
+    const bool use_keep = signal_threshold >= 0.f;
+    rc = pipeline_host(e, frames, n_frames, false, [&](int p0, int np) -> int {
+        if (use_keep) {
+            int r2 = make_keep(e, e->d_frames, fstride, pitch, n_frames, signal_threshold, e->s_comp);
+            if (r2) return r2;
+        }
+        Params p = base_params(e, e->d_frames, fstride, pitch, np);
+        p.u = e->d_out; p.v = e->d_out + field; p.cmax = e->d_out + 2 * field; p.s2n = e->d_out + 3 * field;
+        p.planes = e->d_planes;
+        return dispatch_pairs(e, p, e->s_comp);
+    });
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(corr, e->d_planes, pl * sizeof(float), cudaMemcpyDeviceToHost, e->s_comp));
+    CK(cudaStreamSynchronize(e->s_comp));
+    CK(cudaStreamSynchronize(e->s_copy));
+    if (use_keep) {  // NaN planes for windows below the signal threshold, like ffpiv
+        std::vector<unsigned char> keep(nw);
+        CK(cudaMemcpy(keep.data(), e->d_keep, nw, cudaMemcpyDeviceToHost));
+        const size_t npx = (size_t)e->wy * e->wx;
+        for (size_t pr = 0; pr < n_pairs; ++pr)
+            for (size_t w = 0; w < nw; ++w)
+                if (!keep[w])
+                    for (size_t i = 0; i < npx; ++i) corr[(pr * nw + w) * npx + i] = nanf("");
+    }
+    return B2PIV_OK;
+}
+
+int b2piv_ens_begin(b2piv_engine* e) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (!e->planned) return fail(e, B2PIV_ERR_STATE, "b2piv_plan has not been called");
+    CK(cudaSetDevice(e->device));
+    const size_t nw = (size_t)e->n_rows * e->n_cols, npx = (size_t)e->wy * e->wx;
+    const size_t need = nw * npx * sizeof(float);
+    if (e->cap_ens < need) {
+        if (e->d_ens_sum) CK(cudaFree(e->d_ens_sum));
+        if (e->d_ens_cnt) CK(cudaFree(e->d_ens_cnt));
+        e->d_ens_sum = e->d_ens_cnt = nullptr; e->cap_ens = 0;
+        CK(cudaMalloc((void**)&e->d_ens_sum, need));
+        CK(cudaMalloc((void**)&e->d_ens_cnt, nw * sizeof(float)));
+        e->cap_ens = need;
+    }
+    CK(cudaMemsetAsync(e->d_ens_sum, 0, need, e->s_comp));
+    CK(cudaMemsetAsync(e->d_ens_cnt, 0, nw * sizeof(float), e->s_comp));
+    CK(cudaStreamSynchronize(e->s_comp));
+    e->ens_open = true;
+    return B2PIV_OK;
+}
+
+int b2piv_ens_add_device(b2piv_engine* e, const void* d_frames, long long frame_stride_bytes, int pitch_bytes, int n_frames,
+                         float corr_min, float s2n_min, float signal_threshold, float* d_corr_max, float* d_s2n,
+                         void* cuda_stream) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (!e->planned || !e->ens_open) return fail(e, B2PIV_ERR_STATE, "call b2piv_plan and b2piv_ens_begin first");
+    if (!d_frames || !d_corr_max || !d_s2n) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
+    if (n_frames < 2) return fail(e, B2PIV_ERR_ARG, "need at least 2 frames (one pair)");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    Params p = base_params(e, d_frames, frame_stride_bytes, pitch_bytes, n_frames - 1);
+    if (signal_threshold >= 0.f) {
+        int rc = make_keep(e, d_frames, frame_stride_bytes, pitch_bytes, n_frames, signal_threshold, st);
+        if (rc) return rc;
+        p.keep = e->d_keep;
+    }
+    p.cmax = d_corr_max; p.s2n = d_s2n;
+    EnsParams ep{corr_min, s2n_min, e->d_ens_sum, e->d_ens_cnt};
+    return dispatch_ens(e, p, ep, st);
+}
+
+int b2piv_ens_add_host(b2piv_engine* e, const void* frames, int n_frames, float corr_min, float s2n_min,
+                       float signal_threshold, float* corr_max, float* s2n) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (!e->planned || !e->ens_open) return fail(e, B2PIV_ERR_STATE, "call b2piv_plan and b2piv_ens_begin first");
+    if (!frames || !corr_max || !s2n) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
+    if (n_frames < 2) return fail(e, B2PIV_ERR_ARG, "need at least 2 frames (one pair)");
+    CK(cudaSetDevice(e->device));
+    const size_t esz = e->dtype == B2PIV_F32 ? 4 : 1;
+    const int pitch = (int)(e->W * esz);
+    const long long fstride = (long long)e->H * pitch;
+    const size_t nw = (size_t)e->n_rows * e->n_cols, field = nw * ((size_t)n_frames - 1);
+    int rc = ensure(e, &e->d_out, &e->cap_out, field * 4 * sizeof(float));
+    if (rc) return rc;
+    rc = pipeline_host(e, frames, n_frames, false, [&](int, int) -> int {
+        return b2piv_ens_add_device(e, e->d_frames, fstride, pitch, n_frames, corr_min, s2n_min, signal_threshold,
+                                    e->d_out, e->d_out + field, e->s_comp);
+    });
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(corr_max, e->d_out, field * sizeof(float), cudaMemcpyDeviceToHost, e->s_comp));
+    CK(cudaMemcpyAsync(s2n, e->d_out + field, field * sizeof(float), cudaMemcpyDeviceToHost, e->s_comp));
+    CK(cudaStreamSynchronize(e->s_comp));
+    CK(cudaStreamSynchronize(e->s_copy));
+    CK(cudaEventElapsedTime(&e->last_kernel_ms, e->ev_k0, e->ev_k1));
+    return B2PIV_OK;
+}
+
+int b2piv_ens_accum(b2piv_engine* e, float** d_plane_sum, float** d_count, long long* n_plane_floats, long long* n_windows) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (!e->planned || !e->ens_open) return fail(e, B2PIV_ERR_STATE, "call b2piv_plan and b2piv_ens_begin first");
+    const long long nw = (long long)e->n_rows * e->n_cols;
+    if (d_plane_sum) *d_plane_sum = e->d_ens_sum;
+    if (d_count) *d_count = e->d_ens_cnt;
+    if (n_plane_floats) *n_plane_floats = nw * e->wy * e->wx;
+    if (n_windows) *n_windows = nw;
+    return B2PIV_OK;
+}
+
+int b2piv_ens_finish_host(b2piv_engine* e, float min_count, float* u, float* v, float* count) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (!e->planned || !e->ens_open) return fail(e, B2PIV_ERR_STATE, "call b2piv_plan and b2piv_ens_begin first");
+    if (!u || !v) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
+    CK(cudaSetDevice(e->device));
+    const size_t nw = (size_t)e->n_rows * e->n_cols;
+    int rc = ensure(e, &e->d_out, &e->cap_out, nw * 4 * sizeof(float));
+    if (rc) return rc;
+    ens_finish_kernel<<<(unsigned)nw, 256, 0, e->s_comp>>>(e->d_ens_sum, e->d_ens_cnt, e->wy, e->wx, min_count, e->border_nan,
+                                                           e->gauss_eps, e->d_out, e->d_out + nw);
+    CK(cudaGetLastError());
+    e->launches++;
+    CK(cudaMemcpyAsync(u, e->d_out, nw * sizeof(float), cudaMemcpyDeviceToHost, e->s_comp));
+    CK(cudaMemcpyAsync(v, e->d_out + nw, nw * sizeof(float), cudaMemcpyDeviceToHost, e->s_comp));
+    if (count) CK(cudaMemcpyAsync(count, e->d_ens_cnt, nw * sizeof(float), cudaMemcpyDeviceToHost, e->s_comp));
+    CK(cudaStreamSynchronize(e->s_comp));
+    return B2PIV_OK;
+}
+
+void* b2piv_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void b2piv_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int b2piv_last_kernel_ms(const b2piv_engine* e, float* ms) {
+    if (!e || !ms) return B2PIV_ERR_ARG;
+    *ms = e->last_kernel_ms;
+    return B2PIV_OK;
+}
+long long b2piv_launch_count(const b2piv_engine* e) { return e ? e->launches : 0; }
+
+}  // extern "C"

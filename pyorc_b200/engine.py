@@ -1,0 +1,332 @@
+"""ctypes binding of ``libb2piv.so`` (C ABI in ``include/b2piv.h``) - the B200 LSPIV engine.
+
+This is the host side of the drop-in boundary for pyorc's ``_get_uv_timestep`` / ``_get_ffpiv_mean``
+(pyorc/velocimetry/ffpiv.py:446-474, :182-376): numpy (host) or torch-CUDA (device) frame stacks in, the four
+result fields out.  There is NO CPU fallback: without the CUDA library or without a B200 every call raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libb2piv.so")
+_lib = None
+
+B2PIV_U8, B2PIV_F32 = 0, 1
+_ERR = {1: ValueError, 2: RuntimeError, 3: NotImplementedError, 4: RuntimeError}
+
+# every symbol include/b2piv.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = (
+    "b2piv_version",
+    "b2piv_create",
+    "b2piv_destroy",
+    "b2piv_last_error",
+    "b2piv_set_option",
+    "b2piv_plan",
+    "b2piv_pairs_host",
+    "b2piv_pairs_device",
+    "b2piv_corr_planes_host",
+    "b2piv_ens_begin",
+    "b2piv_ens_add_host",
+    "b2piv_ens_add_device",
+    "b2piv_ens_accum",
+    "b2piv_ens_finish_host",
+    "b2piv_host_alloc",
+    "b2piv_host_free",
+    "b2piv_last_kernel_ms",
+    "b2piv_launch_count",
+)
+
+
+def load_library(path: Optional[str] = None):
+    """Load ``libb2piv.so`` and declare the prototypes.  Raises if the library has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or _LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(pyorc_b200 has no CPU fallback)"
+        )
+    lib = ctypes.CDLL(path)
+    vp, ci, cf, cll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
+    fp = ctypes.POINTER(ctypes.c_float)
+    lib.b2piv_version.restype = ci
+    lib.b2piv_create.argtypes = [ctypes.POINTER(vp), ci]
+    lib.b2piv_destroy.argtypes = [vp]
+    lib.b2piv_destroy.restype = None
+    lib.b2piv_last_error.argtypes = [vp]
+    lib.b2piv_last_error.restype = ctypes.c_char_p
+    lib.b2piv_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_double]
+    lib.b2piv_plan.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    lib.b2piv_pairs_host.argtypes = [vp, vp, ci, cf, vp, vp, vp, vp]
+    lib.b2piv_pairs_device.argtypes = [vp, vp, cll, ci, ci, cf, vp, vp, vp, vp, vp]
+    lib.b2piv_corr_planes_host.argtypes = [vp, vp, ci, cf, vp]
+    lib.b2piv_ens_begin.argtypes = [vp]
+    lib.b2piv_ens_add_host.argtypes = [vp, vp, ci, cf, cf, cf, vp, vp]
+    lib.b2piv_ens_add_device.argtypes = [vp, vp, cll, ci, ci, cf, cf, cf, vp, vp, vp]
+    lib.b2piv_ens_accum.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(cll), ctypes.POINTER(cll)]
+    lib.b2piv_ens_finish_host.argtypes = [vp, cf, vp, vp, vp]
+    lib.b2piv_host_alloc.argtypes = [ctypes.c_size_t]
+    lib.b2piv_host_alloc.restype = vp
+    lib.b2piv_host_free.argtypes = [vp]
+    lib.b2piv_host_free.restype = None
+    lib.b2piv_last_kernel_ms.argtypes = [vp, fp]
+    lib.b2piv_launch_count.argtypes = [vp]
+    lib.b2piv_launch_count.restype = cll
+    for name in ABI_SYMBOLS:
+        getattr(lib, name)
+    if path == _LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+class _CudaView:
+    """Expose a raw device pointer through ``__cuda_array_interface__`` (so torch can wrap it without a copy)."""
+
+    def __init__(self, ptr: int, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class Engine:
+    """One PIV engine bound to one CUDA device (mirrors the role of ffpiv's ``engine=`` back-ends)."""
+
+    def __init__(self, device: int = 0, clip_normalized: Optional[bool] = None, border_nan: Optional[bool] = None,
+                 gauss_eps: Optional[float] = None):
+        self._lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self._lib.b2piv_create(ctypes.byref(h), int(device))
+        if rc != 0:
+            msg = self._lib.b2piv_last_error(None).decode()
+            raise _ERR.get(rc, RuntimeError)(f"b2piv_create failed: {msg}")
+        self._h = h
+        self.device = int(device)
+        self._plan = None
+        self._pinned = []
+        if clip_normalized is not None:
+            self.set_option("clip_normalized", float(bool(clip_normalized)))
+        if border_nan is not None:
+            self.set_option("border_nan", float(bool(border_nan)))
+        if gauss_eps is not None:
+            self.set_option("gauss_eps", float(gauss_eps))
+
+    # ---- plumbing -------------------------------------------------------------------------------------------
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self._lib.b2piv_last_error(self._h).decode()
+            raise _ERR.get(rc, RuntimeError)(f"{what}: {msg}")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            for p in self._pinned:
+                self._lib.b2piv_host_free(p)
+            self._pinned = []
+            self._lib.b2piv_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_option(self, name: str, value: float):
+        self._check(self._lib.b2piv_set_option(self._h, name.encode(), float(value)), "b2piv_set_option")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.b2piv_launch_count(self._h))
+
+    @property
+    def last_kernel_ms(self) -> float:
+        ms = ctypes.c_float()
+        self._check(self._lib.b2piv_last_kernel_ms(self._h, ctypes.byref(ms)), "b2piv_last_kernel_ms")
+        return float(ms.value)
+
+    def pinned_empty(self, shape, dtype=np.uint8) -> np.ndarray:
+        """A page-locked numpy array (freed with the engine) - H2D at full PCIe rate."""
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        p = self._lib.b2piv_host_alloc(max(nbytes, 1))
+        if not p:
+            raise MemoryError("cudaHostAlloc failed")
+        self._pinned.append(p)
+        buf = (ctypes.c_ubyte * max(nbytes, 1)).from_address(p)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    # ---- plan -----------------------------------------------------------------------------------------------
+    def plan(self, dim_size: Tuple[int, int], window_size: Tuple[int, int], overlap: Tuple[int, int], dtype) -> Tuple[int, int]:
+        """Fix frame and window geometry; returns ``(n_rows, n_cols)``."""
+        dt = np.dtype(dtype) if not isinstance(dtype, int) else None
+        if dt is not None:
+            if dt == np.uint8:
+                code = B2PIV_U8
+            elif dt == np.float32:
+                code = B2PIV_F32
+            else:
+                raise TypeError(f"frames must be uint8 or float32, got {dt}")
+        else:
+            code = dtype
+        key = (tuple(dim_size), tuple(window_size), tuple(overlap), code)
+        if self._plan and self._plan[0] == key:
+            return self._plan[1]
+        nr, nc = ctypes.c_int(), ctypes.c_int()
+        self._check(
+            self._lib.b2piv_plan(self._h, int(dim_size[0]), int(dim_size[1]), int(window_size[0]), int(window_size[1]),
+                                 int(overlap[0]), int(overlap[1]), code, ctypes.byref(nr), ctypes.byref(nc)),
+            "b2piv_plan",
+        )
+        self._plan = (key, (nr.value, nc.value))
+        return self._plan[1]
+
+    def _prep(self, frames, window_size, overlap):
+        """Validate a frame stack, (re)plan, return (frames, n, n_rows, n_cols, is_torch)."""
+        if _is_torch(frames):
+            import torch
+
+            if not frames.is_cuda:
+                raise TypeError("torch frames must live on the engine's CUDA device (pass numpy for host data)")
+            if frames.dim() != 3:
+                raise ValueError("frames must be [n, H, W]")
+            if frames.dtype not in (torch.uint8, torch.float32):
+                raise TypeError("frames must be uint8 or float32")
+            if frames.stride(2) != 1:
+                frames = frames.contiguous()
+            dt = np.uint8 if frames.dtype == torch.uint8 else np.float32
+            n, H, W = frames.shape
+            nr, nc = self.plan((H, W), window_size, overlap, dt)
+            return frames, n, nr, nc, True
+        frames = np.asarray(frames)
+        if frames.ndim != 3:
+            raise ValueError("frames must be [n, H, W]")
+        if frames.dtype not in (np.uint8, np.float32):
+            # the reference accepts any real dtype and promotes to float64; the engine computes in float32
+            frames = frames.astype(np.float32)
+        frames = np.ascontiguousarray(frames)
+        n, H, W = frames.shape
+        nr, nc = self.plan((H, W), window_size, overlap, frames.dtype)
+        return frames, n, nr, nc, False
+
+    # ---- per-time-step ----------------------------------------------------------------------------------------
+    def pairs(self, frames, window_size, overlap, signal_threshold: Optional[float] = None, stream=None):
+        """``u, v, corr_max, s2n`` for every consecutive frame pair, each ``[n-1, n_rows, n_cols]`` float32.
+
+        numpy in -> numpy out (H2D/D2H inside, synchronous); torch CUDA tensor in -> torch CUDA tensors out
+        (stream-ordered on ``stream`` or torch's current stream, no synchronisation)."""
+        frames, n, nr, nc, on_dev = self._prep(frames, window_size, overlap)
+        if n < 2:
+            raise ValueError("need at least 2 frames (one frame pair)")
+        thr = -1.0 if signal_threshold is None else float(signal_threshold)
+        if on_dev:
+            import torch
+
+            if frames.device.index != self.device:
+                raise ValueError(f"frames are on cuda:{frames.device.index}, engine on cuda:{self.device}")
+            out = torch.empty((4, n - 1, nr, nc), dtype=torch.float32, device=frames.device)
+            st = stream if stream is not None else torch.cuda.current_stream(frames.device).cuda_stream
+            es = frames.element_size()
+            self._check(
+                self._lib.b2piv_pairs_device(self._h, frames.data_ptr(), frames.stride(0) * es, frames.stride(1) * es, n, thr,
+                                             out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), st),
+                "b2piv_pairs_device",
+            )
+            return out[0], out[1], out[2], out[3]
+        outs = [np.empty((n - 1, nr, nc), dtype=np.float32) for _ in range(4)]
+        self._check(
+            self._lib.b2piv_pairs_host(self._h, frames.ctypes.data, n, thr, *[o.ctypes.data for o in outs]),
+            "b2piv_pairs_host",
+        )
+        return tuple(outs)
+
+    def corr_planes(self, frames, window_size, overlap, signal_threshold: Optional[float] = None) -> np.ndarray:
+        """Full correlation planes ``[n-1, n_windows, wy, wx]`` float32 as ``ffpiv.cross_corr`` returns them
+        (triage / parity only - the fast path never materialises them)."""
+        frames, n, nr, nc, on_dev = self._prep(frames, window_size, overlap)
+        if on_dev:
+            frames = frames.cpu().numpy()
+        if n < 2:
+            raise ValueError("need at least 2 frames (one frame pair)")
+        thr = -1.0 if signal_threshold is None else float(signal_threshold)
+        corr = np.empty((n - 1, nr * nc, window_size[0], window_size[1]), dtype=np.float32)
+        self._check(self._lib.b2piv_corr_planes_host(self._h, frames.ctypes.data, n, thr, corr.ctypes.data), "b2piv_corr_planes_host")
+        return corr
+
+    # ---- ensemble ---------------------------------------------------------------------------------------------
+    def ens_begin(self, dim_size, window_size, overlap, dtype):
+        nr, nc = self.plan(dim_size, window_size, overlap, dtype)
+        self._check(self._lib.b2piv_ens_begin(self._h), "b2piv_ens_begin")
+        return nr, nc
+
+    def ens_add(self, frames, window_size, overlap, corr_min=0.2, s2n_min=3.0, signal_threshold=None, stream=None):
+        """Accumulate one chunk; returns masked per-pair ``corr_max, s2n`` ``[n-1, n_windows]``."""
+        frames, n, nr, nc, on_dev = self._prep(frames, window_size, overlap)
+        if n < 2:
+            raise ValueError("need at least 2 frames (one frame pair)")
+        thr = -1.0 if signal_threshold is None else float(signal_threshold)
+        if on_dev:
+            import torch
+
+            out = torch.empty((2, n - 1, nr * nc), dtype=torch.float32, device=frames.device)
+            st = stream if stream is not None else torch.cuda.current_stream(frames.device).cuda_stream
+            es = frames.element_size()
+            self._check(
+                self._lib.b2piv_ens_add_device(self._h, frames.data_ptr(), frames.stride(0) * es, frames.stride(1) * es, n,
+                                               float(corr_min), float(s2n_min), thr, out[0].data_ptr(), out[1].data_ptr(), st),
+                "b2piv_ens_add_device",
+            )
+            return out[0], out[1]
+        cm = np.empty((n - 1, nr * nc), dtype=np.float32)
+        sn = np.empty((n - 1, nr * nc), dtype=np.float32)
+        self._check(
+            self._lib.b2piv_ens_add_host(self._h, frames.ctypes.data, n, float(corr_min), float(s2n_min), thr, cm.ctypes.data, sn.ctypes.data),
+            "b2piv_ens_add_host",
+        )
+        return cm, sn
+
+    def ens_accumulators(self):
+        """torch views of the device accumulators ``(plane_sum [n_windows, wy, wx], count [n_windows])`` so that
+        ranks can ``all_reduce`` them before :meth:`ens_finish`."""
+        import torch
+
+        ps, pc = ctypes.c_void_p(), ctypes.c_void_p()
+        nf, nw = ctypes.c_longlong(), ctypes.c_longlong()
+        self._check(self._lib.b2piv_ens_accum(self._h, ctypes.byref(ps), ctypes.byref(pc), ctypes.byref(nf), ctypes.byref(nw)), "b2piv_ens_accum")
+        dev = torch.device("cuda", self.device)
+        plane = torch.as_tensor(_CudaView(ps.value, (nf.value,)), device=dev)
+        count = torch.as_tensor(_CudaView(pc.value, (nw.value,)), device=dev)
+        return plane.view(nw.value, -1), count
+
+    def ens_finish(self, min_count: float):
+        """Count filter + mean plane + peak fit; returns ``u, v, count`` each ``[n_windows]``."""
+        nr, nc = self._plan[1]
+        u = np.empty(nr * nc, dtype=np.float32)
+        v = np.empty(nr * nc, dtype=np.float32)
+        cnt = np.empty(nr * nc, dtype=np.float32)
+        self._check(self._lib.b2piv_ens_finish_host(self._h, float(min_count), u.ctypes.data, v.ctypes.data, cnt.ctypes.data), "b2piv_ens_finish_host")
+        return u, v, cnt
+
+
+_default_engines = {}
+
+
+def get_engine(device: int = 0) -> Engine:
+    """Process-wide engine per device (created on first use)."""
+    if device not in _default_engines:
+        _default_engines[device] = Engine(device)
+    return _default_engines[device]

@@ -1,0 +1,104 @@
+"""Frame-pair sharding across the GPUs of one box (one process per GPU, ``torch.distributed``).
+
+Per-time-step PIV is embarrassingly parallel over frame pairs (pyorc/velocimetry/ffpiv.py:399-440: chunks only share
+a 1-frame halo, :140), so rank *r* of *R* owns the contiguous pair range ``[r*P/R, (r+1)*P/R)`` and frames
+``[start, end]`` inclusive.  The only collectives are the broadcast of the pair-range table and the gather of the
+16 B/window results (NCCL on GPUs; the same code runs over gloo for CPU tests with an injected compute function).
+Ensemble mode all-reduces the plane sums / counts before the peak fit.
+"""
+
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+
+
+def shard_pairs(n_pairs: int, world_size: int, rank: Optional[int] = None):
+    """Contiguous, balanced pair ranges.  Returns the ``[world_size, 2]`` (start, stop) table or one row."""
+    if n_pairs < 0 or world_size < 1:
+        raise ValueError("n_pairs >= 0 and world_size >= 1 required")
+    base, rem = divmod(n_pairs, world_size)
+    starts = [r * base + min(r, rem) for r in range(world_size)]
+    table = np.array([[s, s + base + (1 if r < rem else 0)] for r, s in enumerate(starts)], dtype=np.int64)
+    return table if rank is None else tuple(int(v) for v in table[rank])
+
+
+def frame_range(pair_range: Tuple[int, int]) -> Tuple[int, int]:
+    """Frames (inclusive halo) a pair range needs: pairs [a, b) -> frames [a, b] i.e. slice a : b+1."""
+    a, b = pair_range
+    return a, (b + 1 if b > a else a)
+
+
+def scatter_pair_table(n_pairs: int, group=None, device=None):
+    """Rank 0 computes the pair-range table and broadcasts it (the 'scatter of the frame-pair index list')."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    t = torch.zeros((world, 2), dtype=torch.int64, device=device)
+    if rank == 0:
+        t.copy_(torch.from_numpy(shard_pairs(n_pairs, world)))
+    dist.broadcast(t, src=0, group=group)
+    return t.cpu().numpy()
+
+
+def gather_fields(local, n_pairs_total: int, table: np.ndarray, group=None):
+    """All-gather per-rank result stacks ``[4, pairs_r, rows, cols]`` into ``[4, n_pairs_total, rows, cols]``
+    (ragged shards are padded to the largest shard for the collective, then trimmed)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    counts = (table[:, 1] - table[:, 0]).astype(int)
+    pmax = int(counts.max()) if len(counts) else 0
+    nf, _, rows, cols = local.shape
+    pad = torch.zeros((nf, pmax, rows, cols), dtype=local.dtype, device=local.device)
+    pad[:, : local.shape[1]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    out = torch.empty((nf, n_pairs_total, rows, cols), dtype=local.dtype, device=local.device)
+    for r in range(world):
+        a, b = int(table[r, 0]), int(table[r, 1])
+        out[:, a:b] = bufs[r][:, : b - a]
+    return out
+
+
+def piv_pairs_sharded(frames_for_rank: Callable[[int, int], object], n_pairs_total: int,
+                      compute: Callable[[object], Tuple], group=None, device=None):
+    """Distributed per-time-step PIV.
+
+    ``frames_for_rank(f0, f1)`` returns this rank's frames ``[f0, f1)`` (device tensor or ndarray);
+    ``compute(frames)`` returns ``(u, v, corr_max, s2n)`` stacks ``[pairs, rows, cols]`` (the engine's ``pairs``).
+    Returns the gathered ``[4, n_pairs_total, rows, cols]`` tensor on every rank.
+    """
+    import torch
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group)
+    table = scatter_pair_table(n_pairs_total, group=group, device=device)
+    a, b = int(table[rank, 0]), int(table[rank, 1])
+    f0, f1 = frame_range((a, b))
+    if b > a:
+        res = compute(frames_for_rank(f0, f1))
+        local = torch.stack([torch.as_tensor(r) for r in res]).to(device if device is not None else "cpu")
+    else:
+        local = None
+    # shapes must agree across ranks even when a rank has no pair: share (rows, cols)
+    shp = torch.zeros(2, dtype=torch.int64, device=device)
+    if local is not None:
+        shp[0], shp[1] = local.shape[2], local.shape[3]
+    dist.all_reduce(shp, op=dist.ReduceOp.MAX, group=group)
+    if local is None:
+        local = torch.zeros((4, 0, int(shp[0]), int(shp[1])), dtype=torch.float32, device=device)
+    return gather_fields(local.float(), n_pairs_total, table, group=group)
+
+
+def allreduce_ensemble(engine, group=None):
+    """Sum the ensemble accumulators (plane sums + valid counts) over ranks before ``ens_finish``."""
+    import torch.distributed as dist
+
+    plane, count = engine.ens_accumulators()
+    dist.all_reduce(plane, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
+    return plane, count

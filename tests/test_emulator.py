@@ -1,0 +1,55 @@
+"""CPU: the CUDA kernel's barrier-delimited phases, compiled for the host (tests/emul), against the oracle.
+Checks the FFT factorisation, digit-swapped spectrum order, cross-spectrum packing, fftshift indexing, first-argmax
+and Gaussian fit without a GPU.  The emulator is test infrastructure only."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import ffpiv_oracle as O
+from pyorc_b200 import synth
+
+
+@pytest.fixture(scope="module")
+def emul():
+    import __graft_entry__ as g
+
+    lib = ctypes.CDLL(g.build_emulator())
+
+    def run(imgs, ws, ov, nwin=2, clip=1, border_nan=1):
+        imgs = np.ascontiguousarray(imgs)
+        n, H, W = imgs.shape
+        nr, nc = O.get_array_shape((H, W), ws, ov)
+        outs = [np.full((n - 1, nr, nc), -7, np.float32) for _ in range(4)]
+        planes = np.zeros((n - 1, nr * nc, ws[0], ws[1]), np.float32)
+        rc = lib.b2piv_emul_pairs(
+            imgs.ctypes.data_as(ctypes.c_void_p), n, H, W, int(imgs.dtype == np.float32), ws[0], ws[1], ov[0], ov[1], nwin, clip,
+            border_nan, ctypes.c_float(1e-7), None, *[o.ctypes.data_as(ctypes.c_void_p) for o in outs], planes.ctypes.data_as(ctypes.c_void_p),
+        )
+        assert rc == 0
+        return outs, planes
+
+    return run
+
+
+@pytest.mark.parametrize(
+    "ws,ov,shape",
+    [((64, 64), (32, 32), (2, 140, 200)), ((32, 32), (24, 24), (3, 70, 90)), ((16, 16), (8, 8), (2, 50, 60)),
+     ((32, 64), (16, 32), (2, 70, 140)), ((64, 32), (32, 16), (2, 140, 70)), ((128, 128), (64, 64), (2, 130, 200))],
+)
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32])
+@pytest.mark.parametrize("clip", [1, 0])
+def test_phases_match_oracle(emul, ws, ov, shape, dtype, clip):
+    O.CLIP_NORMALIZED = bool(clip)
+    imgs = synth.particle_frames(*shape, dtype=dtype)
+    nr, nc = O.get_array_shape(shape[1:], ws, ov)
+    _, _, corr = O.cross_corr(imgs, ws, ov)
+    u, v, c, s = O.uv_timestep(imgs, nc, nr, ws, ov)
+    for nwin in (2, 1):
+        (eu, ev, ec, es), pl = emul(imgs, ws, ov, nwin=nwin, clip=clip)
+        assert np.abs(pl - corr).max() < 2e-6
+        assert np.array_equal(np.isnan(eu), np.isnan(u))
+        ok = np.isfinite(u)
+        assert np.abs(eu[ok] - u[ok]).max() < 1e-3 and np.abs(ev[ok] - v[ok]).max() < 1e-3
+        assert np.abs(ec - c).max() < 2e-6
+        assert np.nanmax(np.abs(es - s) / np.abs(s)) < 1e-5

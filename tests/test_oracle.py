@@ -1,0 +1,131 @@
+"""CPU: the float64 oracle itself - analytic known answers and the reference-side semantics it must follow."""
+import numpy as np
+import pytest
+
+from oracle import ffpiv_oracle as O
+from pyorc_b200 import synth, window
+
+
+def blob_image(H, W, rng, n=None, sigma=1.6):
+    n = n or int(0.03 * H * W)
+    px, py, amp = rng.uniform(0, W, n), rng.uniform(0, H, n), rng.uniform(100, 255, n)
+    return px, py, amp
+
+
+def render(px, py, amp, H, W, sigma=1.6):
+    yy, xx = np.mgrid[0:H, 0:W]
+    img = np.zeros((H, W))
+    for x, y, a in zip(px, py, amp):
+        # periodic rendering so that a circular shift is exact
+        dx = np.minimum(np.abs(xx - x), W - np.abs(xx - x))
+        dy = np.minimum(np.abs(yy - y), H - np.abs(yy - y))
+        img += a * np.exp(-(dx**2 + dy**2) / (2 * sigma**2))
+    return img
+
+
+@pytest.mark.parametrize("clip", [True, False])
+@pytest.mark.parametrize("shift", [(2.3, 3.6), (-1.7, 3.3), (0.0, 0.0), (4.5, -5.25)])
+def test_known_subpixel_shift_single_window(clip, shift):
+    """One 64x64 periodic window, frame B = frame A shifted by (dy, dx): +u = right, +v = down."""
+    O.CLIP_NORMALIZED = clip
+    rng = np.random.default_rng(3)
+    px, py, amp = blob_image(64, 64, rng, n=60)
+    a = render(px, py, amp, 64, 64)
+    b = render(px + shift[1], py + shift[0], amp, 64, 64)
+    imgs = np.stack([a, b]).astype(np.float32)
+    u, v, c, s = O.uv_timestep(imgs, 1, 1, (64, 64), (32, 32))
+    assert abs(u[0, 0, 0] - shift[1]) < 0.05 and abs(v[0, 0, 0] - shift[0]) < 0.05
+    assert 0.6 < c[0, 0, 0] <= 1.0 and s[0, 0, 0] > 3
+
+
+def test_zero_signal_window_gives_zero_plane_and_nan_s2n():
+    imgs = np.zeros((2, 64, 64), np.uint8)
+    _, _, corr = O.cross_corr(imgs, (64, 64), (32, 32))
+    assert corr.dtype == np.float32 and corr.shape == (1, 1, 64, 64) and not corr.any()
+    u, v, c, s = O.uv_timestep(imgs, 1, 1, (64, 64), (32, 32))
+    assert c[0, 0, 0] == 0 and np.isnan(s[0, 0, 0])
+    assert np.isnan(u[0, 0, 0]) and np.isnan(v[0, 0, 0])  # argmax 0 -> border -> BORDER_RULE
+
+
+def test_argmax_first_occurrence_and_border_rules():
+    plane = np.zeros((1, 1, 8, 8), np.float32)
+    plane[0, 0, 3, 4] = 0.5
+    plane[0, 0, 5, 2] = 0.5  # tie: row-major first wins -> (3, 4)
+    plane[0, 0, 2, 4] = plane[0, 0, 4, 4] = 0.25
+    plane[0, 0, 3, 3] = plane[0, 0, 3, 5] = 0.25
+    u, v = O.u_v_displacement(plane, 1, 1)
+    assert u[0, 0, 0] == pytest.approx(0.0, abs=1e-6) and v[0, 0, 0] == pytest.approx(-1.0, abs=1e-6)
+    edge = np.zeros((1, 1, 8, 8), np.float32)
+    edge[0, 0, 0, 5] = 1.0
+    old = O.BORDER_RULE
+    try:
+        O.BORDER_RULE = "nan"
+        u, v = O.u_v_displacement(edge, 1, 1)
+        assert np.isnan(u).all() and np.isnan(v).all()
+        O.BORDER_RULE = "integer"
+        u, v = O.u_v_displacement(edge, 1, 1)
+        assert u[0, 0, 0] == 1 and v[0, 0, 0] == -4
+    finally:
+        O.BORDER_RULE = old
+
+
+def test_corr_is_float32_in_unit_interval_and_centre_is_zero_shift():
+    O.CLIP_NORMALIZED = True
+    imgs = synth.particle_frames(2, 96, 128, dtype=np.uint8)
+    same = np.stack([imgs[0], imgs[0]])
+    x, y, corr = O.cross_corr(same, (32, 32), (16, 16))
+    assert corr.dtype == np.float32 and corr.min() >= 0 and corr.max() <= 1
+    idx = corr.reshape(corr.shape[0], corr.shape[1], -1).argmax(-1)
+    assert (idx == 16 * 32 + 16).all()  # auto-correlation peaks at (wy//2, wx//2)
+    assert np.array_equal(x, window.get_rect_coordinates((96, 128), (32, 32), (16, 16))[0])
+    assert np.array_equal(y, window.get_rect_coordinates((96, 128), (32, 32), (16, 16))[1])
+
+
+def test_window_geometry_against_survey_table():
+    """SURVEY.md §8(a) sizes (OpenPIV field-shape rule)."""
+    assert O.get_array_shape((475, 371), (32, 32), (16, 16)) == (28, 22)
+    assert O.get_array_shape((1080, 1920), (64, 64), (32, 32)) == (32, 59)
+    assert O.get_array_shape((1080, 1920), (32, 32), (24, 24)) == (132, 237)
+    assert O.get_array_shape((2160, 3840), (64, 64), (32, 32)) == (66, 119)
+    assert O.get_array_shape((4320, 7680), (128, 128), (64, 64)) == (66, 119)
+    for dims, ws, ov in [((475, 371), (10, 10), (5, 5)), ((1080, 1920), (64, 64), (32, 32)), ((200, 333), (26, 26), (12, 12))]:
+        assert window.get_array_shape(dims, ws, ov) == O.get_array_shape(dims, ws, ov)
+        for a, b in zip(window.get_rect_coordinates(dims, ws, ov), O.get_rect_coordinates(dims, ws, ov)):
+            assert a.dtype == np.int64 and np.array_equal(a, b)
+    assert window.round_to_even((25, 25)) == (26, 26) == O.round_to_even((25, 25))
+    assert window.round_to_even((10, 64.0)) == (10, 64)
+
+
+def test_subwindows_layout_row_major():
+    img = np.arange(2 * 40 * 50).reshape(2, 40, 50)
+    st = O.subwindows(img, (16, 16), (8, 8))
+    nr, nc = O.get_array_shape((40, 50), (16, 16), (8, 8))
+    assert st.shape == (2, nr * nc, 16, 16)
+    r, c = 2, 3
+    assert np.array_equal(st[1, r * nc + c], img[1, r * 8 : r * 8 + 16, c * 8 : c * 8 + 16])
+
+
+def test_signal_threshold_masks_planes_with_nan():
+    imgs = synth.particle_frames(3, 96, 128, dtype=np.uint8)
+    imgs[:, :40, :60] = 0
+    _, _, corr = O.cross_corr(imgs, (32, 32), (16, 16), signal_threshold=0.5)
+    nr, nc = O.get_array_shape((96, 128), (32, 32), (16, 16))
+    assert np.isnan(corr[:, 0]).all() and np.isfinite(corr[:, nr * nc - 1]).all()
+    u, v, c, s = O.uv_timestep(imgs, nc, nr, (32, 32), (16, 16), signal_threshold=0.5)
+    assert np.isnan(c[:, 0, 0]).all() and np.isnan(u[:, 0, 0]).all()
+
+
+def test_ensemble_matches_manual_average():
+    """Ensemble restatement (ffpiv.py:200-376): with thresholds at 0 the mean plane is the plain average."""
+    O.CLIP_NORMALIZED = True
+    imgs = synth.particle_frames(5, 96, 128, dtype=np.uint8)
+    ws, ov = (32, 32), (16, 16)
+    nr, nc = O.get_array_shape(imgs.shape[-2:], ws, ov)
+    ens = O.Ensemble(nr, nc, ws, ov, corr_min=0.0, s2n_min=0.0, count_min=0.0)
+    ens.add_chunk(imgs[:3])
+    ens.add_chunk(imgs[2:])
+    u, v, cm, sn = ens.finalize()
+    _, _, corr = O.cross_corr(imgs, ws, ov)
+    u2, v2 = O.u_v_displacement(corr.mean(axis=0, keepdims=True), nr, nc)
+    assert np.allclose(u, u2, atol=1e-4, equal_nan=True) and np.allclose(v, v2, atol=1e-4, equal_nan=True)
+    assert cm.shape == (1, nr, nc) and sn.shape == (1, nr, nc)

@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py - interrogation windows / s of the fused LSPIV engine (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): synthetic 1080p, 100 frame pairs, 64x64 windows, 50 % overlap, single pass,
+uint8 frames.  A "step" is one pass of the hot path over that batch (188 800 windows) on every GPU (weak scaling:
+each rank owns its own 100-pair shard, frame pairs shard with no data-path collective; for N > 1 the 16 B/window
+results are all-gathered over NCCL inside the timed region).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N ...            # the reference's CPU path (oracle port, host cores)
+
+Prints ONE JSON line (rank 0).  `value` = windows/s with frames resident in HBM; `e2e` = the same metric through
+the host API (pinned host frames, H2D + D2H inside the timed region); `roofline` = algorithmic HBM bytes of the
+fused kernel against the measured copy bandwidth; `cpu_baseline` = the oracle port on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "interrogation windows/sec at 64x64, 50% overlap"
+H, W = 1080, 1920
+WS, OV = (64, 64), (32, 32)
+N_PAIRS = 100
+WORKLOAD = "synthetic 1080p, 100 frame pairs, 64x64 windows 50% overlap, single-pass, 1xB200 (per GPU)"
+# compulsory HBM traffic and FFT flops per window
+B_ALG = 2 * (WS[0] - OV[0]) * (WS[1] - OV[1]) * 1 + 16                      # 2064 B (uint8)
+F_ALG = 3 * 2.5 * (WS[0] * WS[1]) * np.log2(WS[0] * WS[1]) + 6 * WS[0] * (WS[1] // 2 + 1)  # 381 312 flop
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nme, val in zip(names, r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference(frames_np, workers):
+    """The reference's CPU path (oracle port: float64 pocketfft, all passes over memory pyorc makes) on `frames_np`."""
+    from oracle import ffpiv_oracle as O
+
+    t0 = time.perf_counter()
+    u, v, c, s = O.cpu_reference_pairs(frames_np, WS, OV, workers=workers)
+    dt = time.perf_counter() - t0
+    return (u, v, c, s), dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: time the CPU path on the box's host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from pyorc_b200 import synth
+
+    cores = os.cpu_count() or 1
+    sample_pairs = args.cpu_pairs
+    frames = synth.particle_frames(sample_pairs + 1, H, W, dtype=np.uint8)
+    nwin = sample_pairs * 32 * 59
+    cpu_reference(frames[:2], cores)  # warm-up (imports, pocketfft plans)
+    ts = []
+    for _ in range(args.steps):
+        _, dt = cpu_reference(frames, cores)
+        ts.append(dt)
+    total = float(np.sum(ts))
+    val = nwin * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "windows/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frame": [H, W], "window": list(WS), "overlap": list(OV), "input_dtype": "uint8",
+                   "sample": f"{sample_pairs} frame pairs of the workload per step ({nwin} windows)"},
+        "cpu_baseline": {"value": val, "unit": "windows/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample_pairs} of the 100 frame pairs per step; restated ffpiv CPU path (upstream ffpiv/rocket-fft unavailable offline), float64 pocketfft, one thread per frame pair on {cores} cores"},
+        "e2e": {"value": val, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-pairs", type=int, default=0, help="frame pairs of the workload the CPU baseline times (0: min(max(4, cores), 16))")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.cpu_pairs <= 0:
+        args.cpu_pairs = min(max(4, os.cpu_count() or 1), 16)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+
+    from pyorc_b200 import parallel, synth
+    from pyorc_b200.engine import Engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = Engine(local_rank)
+    n_frames = N_PAIRS + 1
+    frames = synth.particle_frames_torch(n_frames, H, W, dev, dtype="uint8", seed=synth.SEED + rank)
+    nr, nc = eng.plan((H, W), WS, OV, np.uint8)
+    nwin_rank = N_PAIRS * nr * nc
+    table = parallel.shard_pairs(N_PAIRS * world, world)
+
+    def step_device():
+        res = eng.pairs(frames, WS, OV)
+        if world > 1:
+            return parallel.gather_fields(torch.stack(res), N_PAIRS * world, table)
+        return res
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput (value) ---------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    sync_all()
+    launches0 = eng.launch_count
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    sync_all()
+    ms_total = e0.elapsed_time(e1)
+    launches = eng.launch_count - launches0
+    # kernel-only average launch duration (same stream, no gather) for the roofline
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    k0.record()
+    for _ in range(args.steps):
+        eng.pairs(frames, WS, OV)
+    k1.record()
+    torch.cuda.synchronize(dev)
+    ms_kernel = k0.elapsed_time(k1) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = nwin_rank * world / (ms_step * 1e-3)
+
+    # ---- end to end through the host API (pinned host frames -> H2D -> kernel -> D2H) ---------------------------
+    host = eng.pinned_empty((n_frames, H, W), np.uint8)
+    host[...] = frames.cpu().numpy()
+    for _ in range(2):
+        eng.pairs(host, WS, OV)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        hu, hv, hc, hs = eng.pairs(host, WS, OV)   # synchronous: returns after the D2H of the four fields
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = nwin_rank * world * args.steps / e2e_s
+    h2d = int(host.nbytes)
+    d2h = int(4 * hu.nbytes)
+
+    if rank != 0:
+        eng.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant (only) kernel -----------------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    achieved = B_ALG * nwin_rank / (ms_kernel * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "piv_pairs_kernel<64,64>", "ms_per_launch": ms_kernel, "alg_bytes_per_window": B_ALG,
+                "windows_per_launch": nwin_rank, "peak_source": peak_src,
+                "note": "fused kernel is fp32-issue/shared-memory bound by construction (SURVEY.md §8d); see fp32"}
+    prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    fp32 = {"achieved": F_ALG * nwin_rank / (ms_kernel * 1e-3) / 1e12, "unit": "TFLOP/s", "alg_flop_per_window": F_ALG,
+            "peak_nominal": 148 * 128 * 2 * 1.965e9 / 1e12}
+    fp32["frac_of_nominal"] = fp32["achieved"] / fp32["peak_nominal"]
+
+    # ---- CPU baseline (oracle port) on a bounded sample + parity of the GPU result on that sample ---------------
+    cpu = None
+    rmse = None
+    if world == 1:
+        cores = os.cpu_count() or 1
+        sample = host[: args.cpu_pairs + 1]
+        (u, v, c, s), dt = cpu_reference(sample, cores)
+        nw_s = args.cpu_pairs * nr * nc
+        cpu = {"value": nw_s / dt, "unit": "windows/s", "cores": cores, "kind": "port",
+               "sample": f"first {args.cpu_pairs} of the 100 frame pairs ({nw_s} windows); restated ffpiv CPU path "
+                         f"(float64 pocketfft, one thread per frame pair on {cores} cores); upstream ffpiv/rocket-fft not installable offline"}
+        ok = np.isfinite(u) & np.isfinite(hu[: args.cpu_pairs])
+        rmse = {"u_px": float(np.sqrt(np.mean((hu[: args.cpu_pairs][ok] - u[ok]) ** 2))),
+                "v_px": float(np.sqrt(np.mean((hv[: args.cpu_pairs][ok] - v[ok]) ** 2))),
+                "windows": int(ok.sum()), "nan_mask_equal": bool(np.array_equal(np.isnan(u), np.isnan(hu[: args.cpu_pairs])))}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frame": [H, W], "pairs_per_gpu": N_PAIRS, "window": list(WS), "overlap": list(OV),
+                   "input_dtype": "uint8", "windows_per_step": nwin_rank * world,
+                   "l2": f"inputs {frames.numel() / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)",
+                   "parallelism": f"frame-pair shard x{world}"},
+        "roofline": roofline, "fp32": fp32, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                "ms_per_step": 1e3 * e2e_s / args.steps, "api": "pyorc_b200.engine.Engine.pairs(numpy pinned)"},
+        "gpu_launches": int(launches), "clocks": clocks, "rmse_vs_oracle": rmse,
+    }
+    print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -319,9 +319,30 @@ class Ensemble:
 # --------------------------------------------------------------------------------------------------------------
 # Timed CPU baseline: same passes over memory as pyorc performs, pocketfft threaded over the window batch.
 # --------------------------------------------------------------------------------------------------------------
+def _pair_job(args):
+    a, b, window_size, overlap, n_rows, n_cols = args
+    wa = subwindows(a[None], window_size, overlap)[0]
+    wb = subwindows(b[None], window_size, overlap)[0]
+    corr = ncc(wa, wb, workers=1).astype(np.float32)[None]
+    with warnings.catch_warnings(), np.errstate(all="ignore"):
+        warnings.simplefilter("ignore", category=RuntimeWarning)
+        corr_max = np.nanmax(corr, axis=(-1, -2))
+        s2n = corr_max / np.nanmean(corr, axis=(-1, -2))
+    u, v = u_v_displacement(corr, n_rows, n_cols)
+    return u[0], v[0], corr_max.reshape(n_rows, n_cols).astype(np.float32), s2n.reshape(n_rows, n_cols).astype(np.float32)
+
+
 def cpu_reference_pairs(imgs, window_size, overlap, workers=None):
-    """The reference's per-time-step CPU path on ``imgs`` (all host cores via pocketfft ``workers``): gather ->
-    normalise -> rfft2.conj.irfft2 -> fftshift,/N,clip -> f32 corr -> nanmax, nanmean -> argmax + Gaussian."""
+    """The reference's per-time-step CPU path on ``imgs`` using all host cores the way ffpiv's numba engine does
+    (``prange`` over frame pairs): one thread per frame pair (numpy and pocketfft release the GIL), each doing
+    gather -> normalise -> rfft2.conj.irfft2 -> fftshift,/N,clip -> f32 corr -> nanmax, nanmean -> argmax + Gaussian,
+    i.e. the same passes over memory pyorc performs (ffpiv.py:446-474)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    imgs = np.asarray(imgs)
     workers = workers or os.cpu_count() or 1
-    n_rows, n_cols = get_array_shape(np.asarray(imgs).shape[-2:], window_size, overlap)
-    return uv_timestep(imgs, n_cols, n_rows, window_size, overlap, workers=workers)
+    n_rows, n_cols = get_array_shape(imgs.shape[-2:], window_size, overlap)
+    jobs = [(imgs[k], imgs[k + 1], tuple(window_size), tuple(overlap), n_rows, n_cols) for k in range(imgs.shape[0] - 1)]
+    with ThreadPoolExecutor(max_workers=max(1, min(workers, len(jobs)))) as ex:
+        res = list(ex.map(_pair_job, jobs))
+    return tuple(np.stack([r[i] for r in res]) for i in range(4))

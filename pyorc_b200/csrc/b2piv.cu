@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(C::NT) piv_ens_kernel(Params p, EnsParams ep, 
                 const unsigned long long key = total_max_u64<C>(s, 2 * w + 0);
                 float cmax = __uint_as_float((unsigned)(key >> 32));
                 float s2n = cmax / (total_sum_f32<C>(s, 2 * w + 1) / (float)C::NPX);
-                bool ok = (cmax >= ep.corr_min) && (s2n >= ep.s2n_min) && isfinite(cmax);
+                bool ok = (cmax >= ep.corr_min) && (s2n >= ep.s2n_min) && isfinite(cmax) && (s.scale[w] != 0.f);
                 if (p.keep && !p.keep[it.w[w]]) ok = false;   // NaN plane in the reference -> masked out
                 if (ok) {
 #pragma unroll

@@ -456,9 +456,12 @@ B2_HD void phase_reduce(Smem<C>& s, int tid, const Params& p, const Item& it) {
     for (int w = 0; w < C::NWIN; ++w) {
         unsigned long long best = 0ull;
         float sum = 0.f;
+        // a window with zero variance in either frame has an exactly-zero plane in the reference; the packed
+        // inverse FFT would otherwise leave ~1e-10 rounding cross-talk from its partner window there
+        const bool dead = (s.scale[w] == 0.f);
         for (int e = tid; e < C::NPX; e += C::NT) {
             const int i = e / C::WX, j = e % C::WX;
-            const float v = shifted_value<C>(s, w, i, j);
+            const float v = dead ? 0.f : shifted_value<C>(s, w, i, j);
             sum += v;
             union { float f; unsigned u; } cv; cv.f = v;
             const unsigned long long key = ((unsigned long long)cv.u << 32) | (unsigned long long)(0xffffffffu - (unsigned)e);

@@ -25,6 +25,9 @@ def run(H, W, ws, ov, n_frames, reps=5, dtype="uint8"):
     e.close()
 
 if __name__ == "__main__":
+    if "--single" in sys.argv:
+        run(1080, 1920, (64, 64), (32, 32), 21, reps=2)
+        sys.exit(0)
     run(1080, 1920, (64, 64), (32, 32), 101)
     run(1080, 1920, (64, 64), (32, 32), 101, dtype="float32")
     run(1080, 1920, (32, 32), (16, 16), 41)

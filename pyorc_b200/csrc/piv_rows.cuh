@@ -1,0 +1,457 @@
+// piv_rows.cuh - "row-per-thread" fused LSPIV kernel for square 32x32 / 64x64 uint8 windows (sm_100a).
+//
+// Work unit = one PAIR of adjacent interrogation windows (w0, w1) followed through a run of consecutive frames.
+// Per frame the two windows of THAT frame are packed as z = w0 + i*w1 and transformed by ONE complex 2-D FFT whose
+// two spectra (A0, A1) are kept ("parked") in shared memory; the cross spectra against the previous frame's parked
+// spectra, R_w = conj(A_w,prev) * A_w,new, are packed as G = R_0 + i*R_1 and ONE inverse complex FFT returns both
+// correlation planes.  Every window of every frame is therefore forward-transformed once (the reference transforms
+// it twice, as `b` of pair k and `a` of pair k+1): 1.0 complex FFT per window and pair instead of 1.5.
+//
+// A group of W threads owns the unit: thread t holds row t (then column c(t)) of the plane in REGISTERS - W complex
+// values - and runs whole W-point FFTs there with compile-time twiddles (zero index arithmetic); the only shared
+// memory traffic is the source tile (TMA, 64B/32B swizzle), two transposes per frame and the parked half-spectra.
+//   TMA tile -> rows in regs -> row FFT -> transpose -> column FFT -> [shuffle with the -kx partner lane]
+//   -> cross spectra + park -> inverse column FFT -> transpose -> inverse row FFT -> clip/max/sum -> peak fit.
+//
+// Replaces: ffpiv.cross_corr + nanmax/nanmean + ffpiv.u_v_displacement (pyorc/velocimetry/ffpiv.py:446-474).
+// The phases are __host__ __device__ and barrier-delimited like piv_core.cuh so tests/emul can run them on the CPU.
+#pragma once
+#include "piv_core.cuh"
+#include "twiddle128.h"
+
+namespace b2piv {
+
+// ------------------------------------------------------------------------------------------------------------
+// W-point in-register FFT, natural order in -> natural order out, compile-time twiddles.
+// ------------------------------------------------------------------------------------------------------------
+template <int W, int INV>
+B2_HD void fft_reg(float2* v) {
+    constexpr int A = Factor<W>::R1, B = Factor<W>::R2;  // n = B*n1 + n2, k = k1 + A*k2
+#pragma unroll
+    for (int n2 = 0; n2 < B; ++n2) {
+        float2 t[A];
+#pragma unroll
+        for (int i = 0; i < A; ++i) t[i] = v[B * i + n2];
+        RegDFT<A, INV>::run(t);
+#pragma unroll
+        for (int k1 = 0; k1 < A; ++k1) {
+            const int e = (n2 * k1) * (128 / W);
+            if (n2 * k1 == 0) {
+                v[B * k1 + n2] = t[k1];
+            } else {
+                const float c = cos128(e), sn = sin128(e);
+                const float2 a = t[k1];
+                v[B * k1 + n2] = INV ? make_float2(a.x * c - a.y * sn, a.y * c + a.x * sn)
+                                     : make_float2(a.x * c + a.y * sn, a.y * c - a.x * sn);
+            }
+        }
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < A; ++k1) RegDFT<B, INV>::run(v + B * k1);
+    float2 o[W];
+#pragma unroll
+    for (int k1 = 0; k1 < A; ++k1)
+#pragma unroll
+        for (int k2 = 0; k2 < B; ++k2) o[k1 + A * k2] = v[B * k1 + k2];
+#pragma unroll
+    for (int i = 0; i < W; ++i) v[i] = o[i];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Configuration / shared memory / parameters
+// ------------------------------------------------------------------------------------------------------------
+template <int W_>
+struct RCfg {
+    static constexpr int W = W_;
+    static constexpr int NT = W;              // one thread per row
+    static constexpr int NWARP = W / 32;
+    static constexpr int P = W + 1;           // transpose-plane pitch in float2 (odd: conflict-free both ways)
+    static constexpr int HS = W / 2 + 1;      // ky = 0 .. W/2 computed directly, the rest by Hermitian symmetry
+    static constexpr int NPX = W * W;
+    static constexpr int TILE = 2 * W * W;    // bytes: two windows of one frame, uint8
+};
+
+template <class R>
+struct RSmem {
+    alignas(1024) unsigned char tile[R::TILE];   // TMA destination: [window][row][W bytes], 64B/32B swizzled
+    float2 X[R::W * R::P];                       // transpose plane (also reused for the 3 neighbour rows)
+    float2 park[2][R::HS][R::NT];                // previous frame: scaled spectra A0, A1 at (ky <= W/2, own column)
+    unsigned red[R::NWARP][8];                   // block reductions (integer moments, float bits)
+    unsigned long long redk[R::NWARP][2];
+    unsigned long long mbar;                     // TMA completion barrier
+};
+
+struct RParams {
+    const unsigned char* frames;   // only used by the host emulator (device reads through the tensor map)
+    long long frame_stride;
+    int pitch;
+    int n_rows, n_cols, sy, sx;
+    int n_pairs;                   // frame pairs in this launch (frames = n_pairs + 1)
+    int run_len;                   // frame pairs per work unit
+    int n_units;                   // = n_wpairs * ceil(n_pairs / run_len)
+    int clip_norm, border_nan;
+    float gauss_eps;
+    const unsigned char* keep;
+    float *u, *v, *cmax, *s2n;
+    float* planes;
+};
+
+// Column owned by a thread in the column phases, chosen so that the -kx partner sits in the SAME warp at lane^16
+// (kx = 0 and W/2 are their own partners): warp w, lane l<16 -> column 16w+l ; lane 16+l -> (W-(16w+l)) % W,
+// except (w=0,l=0) -> W/2.
+template <int W>
+B2_HD int column_of(int tid) {
+    const int w = tid >> 5, l = tid & 31;
+    if (l < 16) return 16 * w + l;
+    const int m = 16 * w + (l - 16);
+    return m == 0 ? W / 2 : (W - m) % W;
+}
+template <int W>
+B2_HD int partner_lane_of(int tid) {
+    const int c = column_of<W>(tid);
+    const int l = tid & 31;
+    return (c == 0 || c == W / 2) ? l : (l ^ 16);
+}
+
+// swizzled byte offset of 16-byte chunk j of row r of window w in the tile (TMA SWIZZLE_64B / SWIZZLE_32B)
+template <int W>
+B2_HD int tile_chunk_offset(int w, int r, int j) {
+    const int x = (W == 64) ? ((r >> 1) & 3) : ((r >> 2) & 1);
+    return w * W * W + r * W + ((j ^ x) << 4);
+}
+
+// Per-thread register state that lives across the phases of one frame (and, for alpha/dead, across frames).
+template <class R>
+struct RRegs {
+    float2 v[R::W];
+    unsigned px[2][R::W / 4];     // packed source row of window 0 / 1
+    float half_alpha_prev[2];     // 0.5 / std of the previous frame's windows (0: dead)
+    float half_alpha_new[2];
+    float mean_new[2];
+    float rowmax[2], rowsum[2];
+    int pi[2], pj[2];
+    float cmaxv[2], sumv[2];
+    float2 r0, r1;                // host emulator only: cross spectra of the current ky step
+};
+
+struct RUnit {
+    int w[2];
+    int valid1;
+    int f0, f1;   // frames f0..f1 inclusive; pairs f0..f1-1
+    int x0[2], y0[2];
+};
+
+B2_HD RUnit decode_unit(const RParams& p, int unit) {
+    const int nw = p.n_rows * p.n_cols;
+    const int n_wp = (nw + 1) / 2;
+    RUnit u;
+    const int wp = unit % n_wp, chunk = unit / n_wp;
+    u.w[0] = 2 * wp;
+    u.valid1 = (2 * wp + 1 < nw);
+    u.w[1] = u.valid1 ? 2 * wp + 1 : 2 * wp;
+    u.f0 = chunk * p.run_len;
+    u.f1 = u.f0 + p.run_len < p.n_pairs ? u.f0 + p.run_len : p.n_pairs;
+    for (int k = 0; k < 2; ++k) {
+        u.y0[k] = (u.w[k] / p.n_cols) * p.sy;
+        u.x0[k] = (u.w[k] % p.n_cols) * p.sx;
+    }
+    return u;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// P1: rows from the tile into registers + integer moments (exact) -> red[warp][0..3] = S0, Q0, S1, Q1
+// ------------------------------------------------------------------------------------------------------------
+B2_HD unsigned dp4a_u(unsigned a, unsigned b, unsigned c) {
+#ifdef __CUDA_ARCH__
+    return __dp4a(a, b, c);
+#else
+    for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 0xff) * ((b >> (8 * i)) & 0xff);
+    return c;
+#endif
+}
+
+template <class R>
+B2_HD void rows_p1(RSmem<R>& s, RRegs<R>& r, int tid) {
+    constexpr int W = R::W;
+    unsigned S[2] = {0, 0}, Q[2] = {0, 0};
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+#pragma unroll
+        for (int j = 0; j < W / 16; ++j) {
+            const uint4 q = *reinterpret_cast<const uint4*>(s.tile + tile_chunk_offset<W>(w, tid, j));
+            r.px[w][4 * j + 0] = q.x; r.px[w][4 * j + 1] = q.y; r.px[w][4 * j + 2] = q.z; r.px[w][4 * j + 3] = q.w;
+        }
+#pragma unroll
+        for (int k = 0; k < W / 4; ++k) {
+            S[w] = dp4a_u(r.px[w][k], 0x01010101u, S[w]);
+            Q[w] = dp4a_u(r.px[w][k], r.px[w][k], Q[w]);
+        }
+    }
+    unsigned vals[4] = {S[0], Q[0], S[1], Q[1]};
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vals[k] += __shfl_xor_sync(0xffffffffu, vals[k], o);
+    }
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s.red[tid >> 5][k] = vals[k];
+    }
+#else
+    for (int k = 0; k < 4; ++k) s.red[tid >> 5][k] += vals[k];
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// P2: statistics -> mean, 0.5/std ; convert + centre (+clip) ; forward row FFT ; transposed store into X
+// ------------------------------------------------------------------------------------------------------------
+template <class R>
+B2_HD void rows_p2(RSmem<R>& s, RRegs<R>& r, int tid, int clip_norm) {
+    constexpr int W = R::W;
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        unsigned long long S = 0, Q = 0;
+#pragma unroll
+        for (int k = 0; k < R::NWARP; ++k) { S += s.red[k][2 * w]; Q += s.red[k][2 * w + 1]; }
+        const unsigned long long m2 = (unsigned long long)R::NPX * Q - S * S;   // N^2 * variance, exact
+        r.mean_new[w] = (float)S * (1.0f / (float)R::NPX);
+        // 0.5 / std = 0.5 * N / sqrt(N*Q - S^2)
+        r.half_alpha_new[w] = m2 ? 0.5f * (float)R::NPX * (1.0f / sqrtf((float)m2)) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < W / 4; ++k) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            float a0 = (float)((r.px[0][k] >> (8 * b)) & 0xffu) - r.mean_new[0];
+            float a1 = (float)((r.px[1][k] >> (8 * b)) & 0xffu) - r.mean_new[1];
+            if (clip_norm) { a0 = a0 < 0.f ? 0.f : a0; a1 = a1 < 0.f ? 0.f : a1; }
+            r.v[4 * k + b] = make_float2(a0, a1);
+        }
+    }
+    fft_reg<W, 0>(r.v);
+#pragma unroll
+    for (int k = 0; k < W; ++k) s.X[tid * R::P + k] = r.v[k];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// P3a: column from X, forward column FFT  -> r.v[ky] = Z(ky, col)
+// ------------------------------------------------------------------------------------------------------------
+template <class R>
+B2_HD void rows_p3a(RSmem<R>& s, RRegs<R>& r, int tid) {
+    constexpr int W = R::W;
+    const int c = column_of<W>(tid);
+#pragma unroll
+    for (int y = 0; y < W; ++y) r.v[y] = s.X[y * R::P + c];
+    fft_reg<W, 0>(r.v);
+}
+
+// First frame of a run: park the scaled spectra only.
+//   A0 = (z + conj zn) * (0.5/std0),  A1 = -i (z - conj zn) * (0.5/std1),  parked value = A / N^2
+// `zn` = Z(-ky, -kx) comes from the partner lane (register index (W-ky)%W).
+B2_HD void separate(float2 z, float2 zn, float b0, float b1, float2& a0, float2& a1) {
+    a0 = make_float2((z.x + zn.x) * b0, (z.y - zn.y) * b0);
+    a1 = make_float2((z.y + zn.y) * b1, (zn.x - z.x) * b1);
+}
+
+// One ky step (ky in [0, W/2]) of the cross phase, part A: needs partner's Z(kn) = `pz`.
+// Computes R0, R1 at (ky, own column), parks the new spectra, writes G(ky) into v[ky].
+template <class R>
+B2_HD void cross_step_a(RSmem<R>& s, RRegs<R>& r, int tid, int ky, float2 pz, bool have_prev, float2& r0, float2& r1) {
+    constexpr float INVN2 = 1.0f / ((float)R::NPX * (float)R::NPX);
+    float2 a0, a1;
+    separate(r.v[ky], pz, r.half_alpha_new[0], r.half_alpha_new[1], a0, a1);
+    if (have_prev) {
+        const float2 p0 = s.park[0][ky][tid], p1 = s.park[1][ky][tid];
+        r0 = make_float2(p0.x * a0.x + p0.y * a0.y, p0.x * a0.y - p0.y * a0.x);   // conj(p0) * a0
+        r1 = make_float2(p1.x * a1.x + p1.y * a1.y, p1.x * a1.y - p1.y * a1.x);
+    }
+    s.park[0][ky][tid] = make_float2(a0.x * INVN2, a0.y * INVN2);
+    s.park[1][ky][tid] = make_float2(a1.x * INVN2, a1.y * INVN2);
+    if (have_prev) r.v[ky] = make_float2(r0.x - r1.y, r0.y + r1.x);               // G = R0 + i R1
+}
+// part B: partner's (R0, R1) at (ky, -col) give G(-ky, col) = conj(R0) + i conj(R1)
+template <class R>
+B2_HD void cross_step_b(RRegs<R>& r, int ky, float2 q0, float2 q1) {
+    constexpr int W = R::W;
+    if (ky != 0 && ky != W / 2) r.v[W - ky] = make_float2(q0.x + q1.y, q1.x - q0.y);
+}
+
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ float2 shfl2(float2 a, int src) {
+    return make_float2(__shfl_sync(0xffffffffu, a.x, src), __shfl_sync(0xffffffffu, a.y, src));
+}
+// device: the whole cross phase for one thread
+template <class R>
+__device__ __forceinline__ void rows_p3b_device(RSmem<R>& s, RRegs<R>& r, int tid, bool have_prev) {
+    constexpr int W = R::W;
+    const int pl = partner_lane_of<W>(tid);
+#pragma unroll
+    for (int ky = 0; ky <= W / 2; ++ky) {
+        const float2 pz = shfl2(r.v[(W - ky) % W], pl);
+        float2 r0 = make_float2(0.f, 0.f), r1 = make_float2(0.f, 0.f);
+        cross_step_a<R>(s, r, tid, ky, pz, have_prev, r0, r1);
+        if (have_prev && ky != 0 && ky != W / 2) {
+            const float2 q0 = shfl2(r0, pl), q1 = shfl2(r1, pl);
+            cross_step_b<R>(r, ky, q0, q1);
+        }
+    }
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------------------
+// P4: inverse column FFT, store column into X.   P5: row from X, inverse row FFT, per-row max / sum.
+// ------------------------------------------------------------------------------------------------------------
+template <class R>
+B2_HD void rows_p4(RSmem<R>& s, RRegs<R>& r, int tid) {
+    constexpr int W = R::W;
+    fft_reg<W, 1>(r.v);
+    const int c = column_of<W>(tid);
+#pragma unroll
+    for (int y = 0; y < W; ++y) s.X[y * R::P + c] = r.v[y];
+}
+
+template <class R>
+B2_HD void rows_p5(RSmem<R>& s, RRegs<R>& r, int tid, bool dead0, bool dead1) {
+    constexpr int W = R::W;
+#pragma unroll
+    for (int x = 0; x < W; ++x) r.v[x] = s.X[tid * R::P + x];
+    fft_reg<W, 1>(r.v);
+    float m0 = 0.f, m1 = 0.f, s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int x = 0; x < W; ++x) {
+        float a = dead0 ? 0.f : clip01(r.v[x].x), b = dead1 ? 0.f : clip01(r.v[x].y);
+        r.v[x] = make_float2(a, b);
+        m0 = a > m0 ? a : m0; m1 = b > m1 ? b : m1;
+        s0 += a; s1 += b;
+    }
+    r.rowmax[0] = m0; r.rowmax[1] = m1; r.rowsum[0] = s0; r.rowsum[1] = s1;
+#ifdef __CUDA_ARCH__
+    float vm0 = m0, vm1 = m1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        vm0 = fmaxf(vm0, __shfl_xor_sync(0xffffffffu, vm0, o));
+        vm1 = fmaxf(vm1, __shfl_xor_sync(0xffffffffu, vm1, o));
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if ((tid & 31) == 0) {
+        s.red[tid >> 5][4] = __float_as_uint(vm0); s.red[tid >> 5][5] = __float_as_uint(vm1);
+        s.red[tid >> 5][6] = __float_as_uint(s0);  s.red[tid >> 5][7] = __float_as_uint(s1);
+    }
+#else
+    union { float f; unsigned u; } a;
+    const int wp = tid >> 5;
+    a.u = s.red[wp][4]; a.f = a.f > m0 ? a.f : m0; s.red[wp][4] = a.u;
+    a.u = s.red[wp][5]; a.f = a.f > m1 ? a.f : m1; s.red[wp][5] = a.u;
+    a.u = s.red[wp][6]; a.f += s0; s.red[wp][6] = a.u;
+    a.u = s.red[wp][7]; a.f += s1; s.red[wp][7] = a.u;
+#endif
+}
+
+B2_HD float bits_f(unsigned u) { union { float f; unsigned u; } a; a.u = u; return a.f; }
+
+// P6: block max / sum known; rows holding the max search their FIRST matching column in fftshifted order and
+// deposit key = shifted flat index (min wins).
+template <class R>
+B2_HD void rows_p6(RSmem<R>& s, RRegs<R>& r, int tid) {
+    constexpr int W = R::W;
+    const int si = (tid + W / 2) % W;   // fftshifted row index of this thread's row
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        float M = 0.f, S = 0.f;
+#pragma unroll
+        for (int k = 0; k < R::NWARP; ++k) { M = fmaxf(M, bits_f(s.red[k][4 + w])); S += bits_f(s.red[k][6 + w]); }
+        r.cmaxv[w] = M; r.sumv[w] = S;
+        unsigned long long key = ~0ull;
+        if (r.rowmax[w] == M) {
+            int first = W;
+            // shifted column j = (x + W/2) % W ; scan j descending so the smallest j survives
+#pragma unroll
+            for (int j = W - 1; j >= 0; --j) {
+                const int x = (j + W / 2) % W;
+                const float val = w == 0 ? r.v[x].x : r.v[x].y;
+                first = (val == M) ? j : first;
+            }
+            key = (unsigned long long)(si * W + first);
+        }
+#ifdef __CUDA_ARCH__
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other < key ? other : key;
+        }
+        if ((tid & 31) == 0) s.redk[tid >> 5][w] = key;
+#else
+        if (key < s.redk[tid >> 5][w]) s.redk[tid >> 5][w] = key;
+#endif
+    }
+}
+
+// P7: peak position known; the three rows around each peak are dumped (into X, free by now) for the Gaussian fit.
+template <class R>
+B2_HD void rows_p7(RSmem<R>& s, RRegs<R>& r, int tid) {
+    constexpr int W = R::W;
+    const int si = (tid + W / 2) % W;
+    float* nb = reinterpret_cast<float*>(s.X);   // [w][3][W]
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        unsigned long long key = ~0ull;
+#pragma unroll
+        for (int k = 0; k < R::NWARP; ++k) key = s.redk[k][w] < key ? s.redk[k][w] : key;
+        const int idx = (int)key;
+        r.pi[w] = idx / W; r.pj[w] = idx % W;
+        const int d = si - r.pi[w];
+        if (d >= -1 && d <= 1) {
+#pragma unroll
+            for (int x = 0; x < W; ++x) nb[(w * 3 + (d + 1)) * W + (x + W / 2) % W] = w == 0 ? r.v[x].x : r.v[x].y;
+        }
+    }
+}
+
+// P8: Gaussian fit + outputs by thread w (pyorc/velocimetry/ffpiv.py:465-466 + ffpiv.u_v_displacement).
+template <class R>
+B2_HD void rows_p8(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p, const RUnit& un, int pair) {
+    constexpr int W = R::W;
+    if (tid >= 2) return;
+    const int w = tid;
+    if (w == 1 && !un.valid1) return;
+    const float* nb = reinterpret_cast<const float*>(s.X) + w * 3 * W;
+    const int pi = r.pi[w], pj = r.pj[w];
+    const float cmax = r.cmaxv[w];
+    const float mean = r.sumv[w] / (float)R::NPX;
+    float uu, vv;
+    if (pi == 0 || pi == W - 1 || pj == 0 || pj == W - 1) {
+        if (p.border_nan) { uu = nanf(""); vv = nanf(""); }
+        else { uu = (float)(pj - W / 2); vv = (float)(pi - W / 2); }
+    } else {
+        const float eps = p.gauss_eps;
+        const float lc = logf(cmax + eps);
+        const float ll = logf(nb[0 * W + pj] + eps), lr = logf(nb[2 * W + pj] + eps);
+        const float ld = logf(nb[1 * W + pj - 1] + eps), lu = logf(nb[1 * W + pj + 1] + eps);
+        vv = ((float)pi + (ll - lr) / (2.f * ll - 4.f * lc + 2.f * lr)) - (float)(W / 2);
+        uu = ((float)pj + (ld - lu) / (2.f * ld - 4.f * lc + 2.f * lu)) - (float)(W / 2);
+    }
+    float oc = cmax, os = cmax / mean;
+    if (p.keep && !p.keep[un.w[w]]) { uu = vv = oc = os = nanf(""); }
+    const long long o = (long long)pair * p.n_rows * p.n_cols + un.w[w];
+    p.u[o] = uu; p.v[o] = vv; p.cmax[o] = oc; p.s2n[o] = os;
+}
+
+// optional triage dump of the full planes (fftshifted, clipped) - every thread writes its row
+template <class R>
+B2_HD void rows_dump_planes(RRegs<R>& r, int tid, const RParams& p, const RUnit& un, int pair) {
+    constexpr int W = R::W;
+    if (!p.planes) return;
+    const int si = (tid + W / 2) % W;
+    const long long nw = (long long)p.n_rows * p.n_cols;
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        if (w == 1 && !un.valid1) continue;
+        float* dst = p.planes + (((long long)pair * nw + un.w[w]) * W + si) * W;
+#pragma unroll
+        for (int x = 0; x < W; ++x) dst[(x + W / 2) % W] = w == 0 ? r.v[x].x : r.v[x].y;
+    }
+}
+
+}  // namespace b2piv

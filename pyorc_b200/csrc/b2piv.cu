@@ -5,6 +5,9 @@
 // spectrum -> inverse FFT -> fftshift,/N,clip -> max / mean / first-argmax -> 3-point Gaussian sub-pixel fit.
 #include "../../include/b2piv.h"
 #include "piv_core.cuh"
+#include "piv_rows.cuh"
+
+#include <cuda.h>   // CUtensorMap (types only; the encoder is resolved at run time, libcuda is not linked)
 
 #include <cuda_runtime.h>
 #include <cmath>
@@ -44,6 +47,99 @@ __global__ void __launch_bounds__(C::NT) piv_pairs_kernel(Params p, const float2
         fft_pass<C, 1, 0, 0, 1>(s, tid);         __syncthreads();
         phase_reduce<C>(s, tid, p, it);          __syncthreads();
         phase_peak<C>(s, tid, p, it);            __syncthreads();
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Row-per-thread kernel (piv_rows.cuh): TMA-staged uint8 tiles, register-resident W-point FFTs, forward spectra
+// shared between consecutive frame pairs.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, unsigned long long* bar, int x, int y, int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((unsigned long long)map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+        : "memory");
+}
+
+template <class R>
+__global__ void __launch_bounds__(R::NT) piv_rows_kernel(const __grid_constant__ CUtensorMap tmap, RParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    // the swizzled TMA tile needs a 1024-byte aligned base: align by hand (launch adds 1 KB of slack)
+    unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    RSmem<R>& s = *reinterpret_cast<RSmem<R>*>(base);
+    constexpr int W = R::W;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&s.mbar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+    RRegs<R> r;
+    for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
+        const RUnit un = decode_unit(p, unit);
+        if (tid == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(&s.mbar, R::TILE);
+            tma_load_3d(s.tile, &tmap, &s.mbar, un.x0[0], un.y0[0], un.f0);
+            tma_load_3d(s.tile + W * W, &tmap, &s.mbar, un.x0[1], un.y0[1], un.f0);
+        }
+        for (int f = un.f0; f <= un.f1; ++f) {
+            const bool have_prev = f > un.f0;
+            while (!mbar_try_wait(&s.mbar, parity)) {}
+            parity ^= 1u;
+            rows_p1<R>(s, r, tid);
+            __syncthreads();  // A: integer moments visible, tile fully consumed
+            if (tid == 0 && f < un.f1) {
+                fence_proxy_async();
+                mbar_expect_tx(&s.mbar, R::TILE);
+                tma_load_3d(s.tile, &tmap, &s.mbar, un.x0[0], un.y0[0], f + 1);
+                tma_load_3d(s.tile + W * W, &tmap, &s.mbar, un.x0[1], un.y0[1], f + 1);
+            }
+            rows_p2<R>(s, r, tid, p.clip_norm);
+            __syncthreads();  // B: row spectra in X
+            rows_p3a<R>(s, r, tid);
+            rows_p3b_device<R>(s, r, tid, have_prev);
+            if (have_prev) {
+                const bool dead0 = (r.half_alpha_prev[0] == 0.f) || (r.half_alpha_new[0] == 0.f);
+                const bool dead1 = (r.half_alpha_prev[1] == 0.f) || (r.half_alpha_new[1] == 0.f);
+                __syncthreads();  // C: every thread has read its column of X
+                rows_p4<R>(s, r, tid);
+                __syncthreads();  // D
+                rows_p5<R>(s, r, tid, dead0, dead1);
+                __syncthreads();  // E1: block max / sum
+                rows_p6<R>(s, r, tid);
+                __syncthreads();  // E2: first-argmax key
+                rows_dump_planes<R>(r, tid, p, un, f - 1);
+                rows_p7<R>(s, r, tid);
+                __syncthreads();  // F: neighbour rows dumped
+                rows_p8<R>(s, r, tid, p, un, f - 1);
+            }
+            r.half_alpha_prev[0] = r.half_alpha_new[0];
+            r.half_alpha_prev[1] = r.half_alpha_new[1];
+        }
+        __syncthreads();  // unit boundary: threads 0/1 may still read the neighbour rows (X) in rows_p8
     }
 }
 
@@ -211,6 +307,9 @@ struct b2piv_engine {
     std::string err;
     // options
     int clip_norm = 1, border_nan = 1, copy_chunks = 8;
+    int variant = 0;    // 0: auto, 1: generic shared-memory kernel, 2: row-per-thread TMA kernel (error if ineligible)
+    int run_len = 0;    // frame pairs per work unit of the rows kernel (0: auto)
+    int last_variant = 0;
     float gauss_eps = 1e-7f;
     // plan
     bool planned = false;
@@ -317,7 +416,87 @@ static bool supported(int wy, int wx) {
     return false;
 }
 
+
+// ---- row-per-thread kernel: tensor map + launch ---------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)ptr;
+    }
+    return fn;
+}
+
+static bool rows_eligible(const b2piv_engine* e, const void* d_frames, long long frame_stride, int pitch) {
+    if (e->dtype != B2PIV_U8 || e->wy != e->wx || (e->wy != 64 && e->wy != 32)) return false;
+    if ((pitch & 15) || (frame_stride & 15) || (((uintptr_t)d_frames) & 15)) return false;
+    return get_encode_tiled() != nullptr;
+}
+
+template <class R>
+static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st) {
+    constexpr int W = R::W;
+    const int n_frames = gp.n_pairs + 1;
+    CUtensorMap tmap;
+    const cuuint64_t dims[3] = {(cuuint64_t)e->W, (cuuint64_t)e->H, (cuuint64_t)n_frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)gp.pitch, (cuuint64_t)gp.frame_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)W, (cuuint32_t)W, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult cr = get_encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(gp.frames), dims, strides, box, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, W == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(e, B2PIV_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)cr));
+    RParams p;
+    memset(&p, 0, sizeof(p));
+    p.frames = (const unsigned char*)gp.frames; p.frame_stride = gp.frame_stride; p.pitch = gp.pitch;
+    p.n_rows = gp.n_rows; p.n_cols = gp.n_cols; p.sy = gp.sy; p.sx = gp.sx; p.n_pairs = gp.n_pairs;
+    p.clip_norm = gp.clip_norm; p.border_nan = gp.border_nan; p.gauss_eps = gp.gauss_eps; p.keep = gp.keep;
+    p.u = gp.u; p.v = gp.v; p.cmax = gp.cmax; p.s2n = gp.s2n; p.planes = gp.planes;
+    const size_t smem = sizeof(RSmem<R>) + 1024;
+    auto kern = piv_rows_kernel<R>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, R::NT, smem));
+    if (occ < 1) return fail(e, B2PIV_ERR_CUDA, "rows kernel does not fit on an SM");
+    const long long resident = (long long)occ * e->sm_count;
+    const int nw = gp.n_rows * gp.n_cols, n_wp = (nw + 1) / 2;
+    int run = e->run_len;
+    if (run <= 0) {  // aim for >= 8 waves of work units; every unit start costs one extra forward transform
+        long long chunks = (8 * resident + n_wp - 1) / n_wp;
+        if (chunks < 1) chunks = 1;
+        run = (int)((gp.n_pairs + chunks - 1) / chunks);
+        if (run < 8) run = 8;
+    }
+    if (run > gp.n_pairs) run = gp.n_pairs;
+    p.run_len = run;
+    const long long n_units = (long long)n_wp * ((gp.n_pairs + run - 1) / run);
+    p.n_units = (int)n_units;
+    long long grid = resident < n_units ? resident : n_units;
+    kern<<<(unsigned)grid, R::NT, smem, st>>>(tmap, p);
+    CK(cudaGetLastError());
+    e->launches++;
+    return B2PIV_OK;
+}
+
 static int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
+    if (p.n_pairs <= 0) return B2PIV_OK;
+    const bool can_rows = rows_eligible(e, p.frames, p.frame_stride, p.pitch);
+    if (e->variant == 2 && !can_rows)
+        return fail(e, B2PIV_ERR_UNSUPPORTED, "rows kernel needs uint8 frames, a square 32/64 window and 16-byte aligned base/pitch");
+    if (can_rows && e->variant != 1) {
+        e->last_variant = 2;
+        if (e->wy == 64) return launch_rows<RCfg<64>>(e, p, st);
+        return launch_rows<RCfg<32>>(e, p, st);
+    }
+    e->last_variant = 1;
 #define X(Y, XX, T, NW) if (e->wy == Y && e->wx == XX) return launch_pairs<Cfg<Y, XX, T, NW>>(e, p, st);
     B2PIV_CONFIGS(X)
 #undef X
@@ -414,6 +593,8 @@ int b2piv_set_option(b2piv_engine* e, const char* name, double value) {
     else if (n == "border_nan") e->border_nan = value != 0.0;
     else if (n == "gauss_eps") e->gauss_eps = (float)value;
     else if (n == "copy_chunks") e->copy_chunks = value < 1 ? 1 : (int)value;
+    else if (n == "kernel_variant") e->variant = (int)value;
+    else if (n == "run_len") e->run_len = value < 0 ? 0 : (int)value;
     else return fail(e, B2PIV_ERR_ARG, "unknown option " + n);
     return B2PIV_OK;
 }

@@ -170,6 +170,15 @@ B2_HD unsigned dp4a_u(unsigned a, unsigned b, unsigned c) {
 #endif
 }
 
+// byte b of a packed word as float without the (slow) I2F pipe: 0x4B0000bb is 8388608 + bb exactly
+B2_HD float byte_to_float(unsigned word, int b) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u + (unsigned)b)) - 8388608.0f;
+#else
+    return (float)((word >> (8 * b)) & 0xffu);
+#endif
+}
+
 template <class R>
 B2_HD void rows_p1(RSmem<R>& s, RRegs<R>& r, int tid) {
     constexpr int W = R::W;
@@ -223,9 +232,9 @@ B2_HD void rows_p2(RSmem<R>& s, RRegs<R>& r, int tid, int clip_norm) {
     for (int k = 0; k < W / 4; ++k) {
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            float a0 = (float)((r.px[0][k] >> (8 * b)) & 0xffu) - r.mean_new[0];
-            float a1 = (float)((r.px[1][k] >> (8 * b)) & 0xffu) - r.mean_new[1];
-            if (clip_norm) { a0 = a0 < 0.f ? 0.f : a0; a1 = a1 < 0.f ? 0.f : a1; }
+            float a0 = byte_to_float(r.px[0][k], b) - r.mean_new[0];
+            float a1 = byte_to_float(r.px[1][k], b) - r.mean_new[1];
+            if (clip_norm) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
             r.v[4 * k + b] = make_float2(a0, a1);
         }
     }
@@ -277,7 +286,7 @@ B2_HD void cross_step_b(RRegs<R>& r, int ky, float2 q0, float2 q1) {
     if (ky != 0 && ky != W / 2) r.v[W - ky] = make_float2(q0.x + q1.y, q1.x - q0.y);
 }
 
-#ifdef __CUDA_ARCH__
+#ifdef __CUDACC__
 __device__ __forceinline__ float2 shfl2(float2 a, int src) {
     return make_float2(__shfl_sync(0xffffffffu, a.x, src), __shfl_sync(0xffffffffu, a.y, src));
 }
@@ -320,9 +329,10 @@ B2_HD void rows_p5(RSmem<R>& s, RRegs<R>& r, int tid, bool dead0, bool dead1) {
     float m0 = 0.f, m1 = 0.f, s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int x = 0; x < W; ++x) {
-        float a = dead0 ? 0.f : clip01(r.v[x].x), b = dead1 ? 0.f : clip01(r.v[x].y);
+        // clip to [0, 1] (inputs are uint8, no NaNs can occur, so fmin/fmax are exact here)
+        float a = dead0 ? 0.f : fminf(fmaxf(r.v[x].x, 0.f), 1.f), b = dead1 ? 0.f : fminf(fmaxf(r.v[x].y, 0.f), 1.f);
         r.v[x] = make_float2(a, b);
-        m0 = a > m0 ? a : m0; m1 = b > m1 ? b : m1;
+        m0 = fmaxf(a, m0); m1 = fmaxf(b, m1);
         s0 += a; s1 += b;
     }
     r.rowmax[0] = m0; r.rowmax[1] = m1; r.rowsum[0] = s0; r.rowsum[1] = s1;
@@ -417,9 +427,10 @@ B2_HD void rows_p8(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p, const RU
     const int w = tid;
     if (w == 1 && !un.valid1) return;
     const float* nb = reinterpret_cast<const float*>(s.X) + w * 3 * W;
-    const int pi = r.pi[w], pj = r.pj[w];
-    const float cmax = r.cmaxv[w];
-    const float mean = r.sumv[w] / (float)R::NPX;
+    // selects, not r.x[w]: a dynamic index would demote the whole register struct to local memory
+    const int pi = w == 0 ? r.pi[0] : r.pi[1], pj = w == 0 ? r.pj[0] : r.pj[1];
+    const float cmax = w == 0 ? r.cmaxv[0] : r.cmaxv[1];
+    const float mean = (w == 0 ? r.sumv[0] : r.sumv[1]) / (float)R::NPX;
     float uu, vv;
     if (pi == 0 || pi == W - 1 || pj == 0 || pj == W - 1) {
         if (p.border_nan) { uu = nanf(""); vv = nanf(""); }
@@ -433,8 +444,9 @@ B2_HD void rows_p8(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p, const RU
         uu = ((float)pj + (ld - lu) / (2.f * ld - 4.f * lc + 2.f * lu)) - (float)(W / 2);
     }
     float oc = cmax, os = cmax / mean;
-    if (p.keep && !p.keep[un.w[w]]) { uu = vv = oc = os = nanf(""); }
-    const long long o = (long long)pair * p.n_rows * p.n_cols + un.w[w];
+    const int widx = w == 0 ? un.w[0] : un.w[1];
+    if (p.keep && !p.keep[widx]) { uu = vv = oc = os = nanf(""); }
+    const long long o = (long long)pair * p.n_rows * p.n_cols + widx;
     p.u[o] = uu; p.v[o] = vv; p.cmax[o] = oc; p.s2n[o] = os;
 }
 

@@ -1,6 +1,7 @@
 // TEST-ONLY host emulator: runs the kernel's barrier-delimited phases (pyorc_b200/csrc/piv_core.cuh) on the CPU,
 // "thread by thread, phase by phase", to validate index mathematics without a GPU.  Never loaded by pyorc_b200.
 #include "../../pyorc_b200/csrc/piv_core.cuh"
+#include "../../pyorc_b200/csrc/piv_rows.cuh"
 #include <vector>
 #include <cstring>
 #include <cmath>
@@ -60,5 +61,85 @@ extern "C" int b2piv_emul_pairs(const void* frames, int n_frames, int H, int W, 
     p.u = u; p.v = v; p.cmax = cmax; p.s2n = s2n; p.planes = planes;
 #define CASE(Y, X, T) if (wy == Y && wx == X) return nwin == 2 ? run<Cfg<Y, X, T, 2>>(p) : run<Cfg<Y, X, T, 1>>(p);
     CASE(16, 16, 64) CASE(32, 32, 128) CASE(64, 64, 256) CASE(128, 128, 256) CASE(32, 64, 128) CASE(64, 32, 128)
+    return -1;
+}
+
+
+// ---- row-per-thread kernel (piv_rows.cuh): lock-step emulation of the W threads of one group ---------------------
+template <class R>
+static int run_rows(RParams p) {
+    constexpr int W = R::W;
+    RSmem<R>* sp = new RSmem<R>();
+    RSmem<R>& s = *sp;
+    std::vector<RRegs<R>> regs(W), snap(W);
+    for (int unit = 0; unit < p.n_units; ++unit) {
+        const RUnit un = decode_unit(p, unit);
+        for (int f = un.f0; f <= un.f1; ++f) {
+            const bool have_prev = f > un.f0;
+            // "TMA": fill the swizzled tile from frame f
+            for (int w = 0; w < 2; ++w)
+                for (int row = 0; row < W; ++row)
+                    for (int j = 0; j < W / 16; ++j)
+                        memcpy(s.tile + tile_chunk_offset<W>(w, row, j),
+                               p.frames + (long long)f * p.frame_stride + (long long)(un.y0[w] + row) * p.pitch + un.x0[w] + 16 * j, 16);
+            memset(s.red, 0, sizeof(s.red));
+            for (int t = 0; t < W; ++t) rows_p1<R>(s, regs[t], t);
+            for (int t = 0; t < W; ++t) rows_p2<R>(s, regs[t], t, p.clip_norm);
+            for (int t = 0; t < W; ++t) rows_p3a<R>(s, regs[t], t);
+            snap = regs;
+            for (int ky = 0; ky <= W / 2; ++ky) {
+                for (int t = 0; t < W; ++t) {
+                    const int pt = (t & ~31) | partner_lane_of<W>(t);
+                    regs[t].r0 = regs[t].r1 = make_float2(0.f, 0.f);
+                    cross_step_a<R>(s, regs[t], t, ky, snap[pt].v[(W - ky) % W], have_prev, regs[t].r0, regs[t].r1);
+                }
+                if (have_prev && ky != 0 && ky != W / 2) {
+                    std::vector<float2> q0(W), q1(W);
+                    for (int t = 0; t < W; ++t) { q0[t] = regs[t].r0; q1[t] = regs[t].r1; }
+                    for (int t = 0; t < W; ++t) {
+                        const int pt = (t & ~31) | partner_lane_of<W>(t);
+                        cross_step_b<R>(regs[t], ky, q0[pt], q1[pt]);
+                    }
+                }
+            }
+            if (have_prev) {
+                for (int t = 0; t < W; ++t) rows_p4<R>(s, regs[t], t);
+                for (int k = 0; k < R::NWARP; ++k) for (int q = 4; q < 8; ++q) s.red[k][q] = 0;
+                for (int t = 0; t < W; ++t) {
+                    const bool d0 = regs[t].half_alpha_prev[0] == 0.f || regs[t].half_alpha_new[0] == 0.f;
+                    const bool d1 = regs[t].half_alpha_prev[1] == 0.f || regs[t].half_alpha_new[1] == 0.f;
+                    rows_p5<R>(s, regs[t], t, d0, d1);
+                }
+                for (int k = 0; k < R::NWARP; ++k) s.redk[k][0] = s.redk[k][1] = ~0ull;
+                for (int t = 0; t < W; ++t) rows_p6<R>(s, regs[t], t);
+                for (int t = 0; t < W; ++t) rows_dump_planes<R>(regs[t], t, p, un, f - 1);
+                for (int t = 0; t < W; ++t) rows_p7<R>(s, regs[t], t);
+                for (int t = 0; t < W; ++t) rows_p8<R>(s, regs[t], t, p, un, f - 1);
+            }
+            for (int t = 0; t < W; ++t) {
+                regs[t].half_alpha_prev[0] = regs[t].half_alpha_new[0];
+                regs[t].half_alpha_prev[1] = regs[t].half_alpha_new[1];
+            }
+        }
+    }
+    delete sp;
+    return 0;
+}
+
+extern "C" int b2piv_emul_rows(const unsigned char* frames, int n_frames, int H, int W, int win, int ovl, int run_len, int clip_norm,
+                               int border_nan, float eps, const unsigned char* keep, float* u, float* v, float* cmax, float* s2n,
+                               float* planes) {
+    RParams p;
+    memset(&p, 0, sizeof(p));
+    p.frames = frames; p.pitch = W; p.frame_stride = (long long)H * W;
+    p.n_rows = (H - win) / (win - ovl) + 1; p.n_cols = (W - win) / (win - ovl) + 1;
+    p.sy = p.sx = win - ovl; p.n_pairs = n_frames - 1;
+    p.run_len = run_len > 0 && run_len < p.n_pairs ? run_len : p.n_pairs;
+    const int nw = p.n_rows * p.n_cols;
+    p.n_units = ((nw + 1) / 2) * ((p.n_pairs + p.run_len - 1) / p.run_len);
+    p.clip_norm = clip_norm; p.border_nan = border_nan; p.gauss_eps = eps; p.keep = keep;
+    p.u = u; p.v = v; p.cmax = cmax; p.s2n = s2n; p.planes = planes;
+    if (win == 64) return run_rows<RCfg<64>>(p);
+    if (win == 32) return run_rows<RCfg<32>>(p);
     return -1;
 }

@@ -53,3 +53,49 @@ def test_phases_match_oracle(emul, ws, ov, shape, dtype, clip):
         assert np.abs(eu[ok] - u[ok]).max() < 1e-3 and np.abs(ev[ok] - v[ok]).max() < 1e-3
         assert np.abs(ec - c).max() < 2e-6
         assert np.nanmax(np.abs(es - s) / np.abs(s)) < 1e-5
+
+
+@pytest.fixture(scope="module")
+def emul_rows():
+    import __graft_entry__ as g
+
+    lib = ctypes.CDLL(g.build_emulator())
+
+    def run(imgs, win, ovl, run_len=0, clip=1, border_nan=1):
+        imgs = np.ascontiguousarray(imgs)
+        n, H, W = imgs.shape
+        nr, nc = O.get_array_shape((H, W), (win, win), (ovl, ovl))
+        outs = [np.full((n - 1, nr, nc), -7, np.float32) for _ in range(4)]
+        planes = np.zeros((n - 1, nr * nc, win, win), np.float32)
+        rc = lib.b2piv_emul_rows(
+            imgs.ctypes.data_as(ctypes.c_void_p), n, H, W, win, ovl, run_len, clip, border_nan, ctypes.c_float(1e-7), None,
+            *[o.ctypes.data_as(ctypes.c_void_p) for o in outs], planes.ctypes.data_as(ctypes.c_void_p),
+        )
+        assert rc == 0
+        return outs, planes
+
+    return run
+
+
+@pytest.mark.parametrize(
+    "win,ovl,shape,run_len",
+    [(64, 32, (4, 200, 304), 0), (64, 32, (5, 136, 208), 2), (32, 16, (4, 100, 160), 0), (32, 24, (4, 80, 96), 3), (64, 48, (3, 140, 160), 1)],
+)
+@pytest.mark.parametrize("clip", [1, 0])
+def test_rows_phases_match_oracle(emul_rows, win, ovl, shape, run_len, clip):
+    """Row-per-thread kernel phases (piv_rows.cuh): swizzled tile reads, register FFTs, partner-lane Hermitian split,
+    forward-spectrum sharing across consecutive pairs, first-argmax, dead windows."""
+    O.CLIP_NORMALIZED = bool(clip)
+    imgs = synth.particle_frames(*shape, dtype=np.uint8)
+    imgs[:, :40, :50] = 0
+    ws, ov = (win, win), (ovl, ovl)
+    nr, nc = O.get_array_shape(shape[1:], ws, ov)
+    _, _, corr = O.cross_corr(imgs, ws, ov)
+    u, v, c, s = O.uv_timestep(imgs, nc, nr, ws, ov)
+    (eu, ev, ec, es), pl = emul_rows(imgs, win, ovl, run_len, clip)
+    assert np.abs(pl - corr).max() < 2e-6
+    assert np.array_equal(np.isnan(eu), np.isnan(u)) and np.array_equal(np.isnan(es), np.isnan(s))
+    ok = np.isfinite(u)
+    assert np.abs(eu[ok] - u[ok]).max() < 1e-3 and np.abs(ev[ok] - v[ok]).max() < 1e-3
+    assert np.abs(ec - c).max() < 2e-6
+    assert np.nanmax(np.abs(es - s) / np.abs(s)) < 1e-5

@@ -23,9 +23,11 @@ def engine():
     e.close()
 
 
-def compare(engine, imgs, ws, ov, clip, check_planes=True, signal_threshold=None):
+def compare(engine, imgs, ws, ov, clip, check_planes=True, signal_threshold=None, variant=0, run_len=0):
     O.CLIP_NORMALIZED = bool(clip)
     engine.set_option("clip_normalized", float(clip))
+    engine.set_option("kernel_variant", float(variant))   # 0 auto, 1 generic smem kernel, 2 row-per-thread TMA kernel
+    engine.set_option("run_len", float(run_len))
     nr, nc = O.get_array_shape(imgs.shape[-2:], ws, ov)
     u, v, c, s = O.uv_timestep(imgs, nc, nr, ws, ov, signal_threshold=signal_threshold)
     gu, gv, gc, gs = engine.pairs(imgs, ws, ov, signal_threshold=signal_threshold)
@@ -74,6 +76,48 @@ def test_pairs_match_oracle(engine, ws, ov, shape, dtype, clip):
     compare(engine, imgs, ws, ov, clip)
 
 
+ROWS_CASES = [
+    ((64, 64), (32, 32), (4, 270, 400), 0),
+    ((64, 64), (32, 32), (6, 200, 304), 2),    # runs of 2 pairs: unit boundaries inside the stack
+    ((64, 64), (48, 48), (3, 150, 176), 1),
+    ((32, 32), (16, 16), (5, 150, 208), 0),
+    ((32, 32), (24, 24), (4, 100, 144), 3),
+    ((64, 64), (32, 32), (3, 64 * 2 + 7, 64 * 3 + 16), 0),   # 3 x 5 windows: odd count -> last unit has one window
+]
+
+
+@pytest.mark.parametrize("ws,ov,shape,run_len", ROWS_CASES)
+@pytest.mark.parametrize("clip", [1, 0])
+def test_rows_kernel_matches_oracle(engine, ws, ov, shape, run_len, clip):
+    """The row-per-thread TMA kernel (forced), including forward-spectrum sharing across consecutive pairs."""
+    imgs = synth.particle_frames(*shape, dtype=np.uint8)
+    imgs[:, :40, :50] = 0
+    compare(engine, imgs, ws, ov, clip, variant=2, run_len=run_len)
+
+
+def test_rows_and_generic_kernels_agree(engine):
+    imgs = synth.particle_frames(5, 270, 400, dtype=np.uint8)
+    engine.set_option("clip_normalized", 1.0)
+    engine.set_option("run_len", 0.0)
+    engine.set_option("kernel_variant", 1.0)
+    a = engine.pairs(imgs, (64, 64), (32, 32))
+    engine.set_option("kernel_variant", 2.0)
+    b = engine.pairs(imgs, (64, 64), (32, 32))
+    engine.set_option("kernel_variant", 0.0)
+    for x, y in zip(a, b):
+        assert np.array_equal(np.isnan(x), np.isnan(y))
+        assert np.nanmax(np.abs(x - y) / (1 + np.abs(x))) < 2e-5
+
+
+def test_rows_kernel_refuses_unaligned_pitch(engine):
+    imgs = synth.particle_frames(3, 150, 203, dtype=np.uint8)   # pitch 203 B: TMA needs 16-byte strides
+    engine.set_option("kernel_variant", 2.0)
+    with pytest.raises(NotImplementedError):
+        engine.pairs(imgs, (64, 64), (32, 32))
+    engine.set_option("kernel_variant", 0.0)
+    compare(engine, imgs, (64, 64), (32, 32), 1)   # auto falls back to the generic kernel
+
+
 def test_odd_window_count_and_ragged_edges(engine):
     # 3 x 5 windows (odd count -> last work item holds a single window); frame not a multiple of the stride
     imgs = synth.particle_frames(3, 64 * 2 + 7, 64 * 3 + 13, dtype=np.uint8)
@@ -98,6 +142,8 @@ def test_signal_threshold(engine):
 def test_device_resident_path(engine):
     import torch
 
+    engine.set_option("kernel_variant", 0.0)
+    engine.set_option("run_len", 0.0)
     imgs = synth.particle_frames(4, 270, 400, dtype=np.uint8)
     engine.set_option("clip_normalized", 1.0)
     hu, hv, hc, hs = engine.pairs(imgs, (64, 64), (32, 32))

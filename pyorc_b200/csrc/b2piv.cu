@@ -82,14 +82,18 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 
-template <class R>
-__global__ void __launch_bounds__(R::NT) piv_rows_kernel(const __grid_constant__ CUtensorMap tmap, RParams p) {
+// G groups of W threads share one CTA and run in LOCKSTEP (CTA-wide barriers): the loop body is ~180 KB of
+// straight-line code, far beyond the instruction caches, so all warps of an SM must stream the SAME instructions
+// (ncu on the one-group-per-CTA version: 30 % of issue slots lost to `no_instructions`).
+template <class R, int G>
+__global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constant__ CUtensorMap tmap, RParams p) {
     extern __shared__ unsigned char smem_dyn[];
-    // the swizzled TMA tile needs a 1024-byte aligned base: align by hand (launch adds 1 KB of slack)
+    // the swizzled TMA tiles need 1024-byte aligned bases: align by hand (launch adds 1 KB of slack)
     unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-    RSmem<R>& s = *reinterpret_cast<RSmem<R>*>(base);
     constexpr int W = R::W;
-    const int tid = threadIdx.x;
+    const int g = threadIdx.x / R::NT;     // group within the CTA
+    const int tid = threadIdx.x % R::NT;   // thread within the group (= row / column slot)
+    RSmem<R>& s = reinterpret_cast<RSmem<R>*>(base)[g];
     if (tid == 0) {
         mbar_init(&s.mbar, 1);
         fence_mbar_init();
@@ -97,49 +101,85 @@ __global__ void __launch_bounds__(R::NT) piv_rows_kernel(const __grid_constant__
     __syncthreads();
     uint32_t parity = 0;
     RRegs<R> r;
-    for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
-        const RUnit un = decode_unit(p, unit);
-        if (tid == 0) {
+    for (long long ubase = (long long)blockIdx.x * G; ubase < p.n_units; ubase += (long long)gridDim.x * G) {
+        int maxn = 0;  // frames of the longest unit of this round (uniform over the CTA)
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            if (ubase + j < p.n_units) {
+                const RUnit t = decode_unit(p, (int)(ubase + j));
+                maxn = max(maxn, t.f1 - t.f0 + 1);
+            }
+        }
+        const bool has_unit = (ubase + g) < p.n_units;
+        const RUnit un = decode_unit(p, has_unit ? (int)(ubase + g) : 0);
+        const int nfr = has_unit ? un.f1 - un.f0 + 1 : 0;
+        if (has_unit && tid == 0) {
             fence_proxy_async();
             mbar_expect_tx(&s.mbar, R::TILE);
             tma_load_3d(s.tile, &tmap, &s.mbar, un.x0[0], un.y0[0], un.f0);
             tma_load_3d(s.tile + W * W, &tmap, &s.mbar, un.x0[1], un.y0[1], un.f0);
         }
-        for (int f = un.f0; f <= un.f1; ++f) {
-            const bool have_prev = f > un.f0;
-            while (!mbar_try_wait(&s.mbar, parity)) {}
-            parity ^= 1u;
-            rows_p1<R>(s, r, tid);
-            __syncthreads();  // A: integer moments visible, tile fully consumed
-            if (tid == 0 && f < un.f1) {
-                fence_proxy_async();
-                mbar_expect_tx(&s.mbar, R::TILE);
-                tma_load_3d(s.tile, &tmap, &s.mbar, un.x0[0], un.y0[0], f + 1);
-                tma_load_3d(s.tile + W * W, &tmap, &s.mbar, un.x0[1], un.y0[1], f + 1);
+        for (int k = 0; k < maxn; ++k) {
+            const bool active = k < nfr;
+            const bool have_prev = k > 0;
+            const int f = un.f0 + k;
+            const int n_stage = have_prev ? 4 : 2;
+            // Four 1-D FFT passes per frame (rows, columns, columns, rows) share ONE copy of the unrolled W-point
+            // FFT: the inverse passes run the forward code on conj(G) (IFFT(G) = conj(FFT(conj G))).  Keeping the
+            // stage loop rolled cuts the loop body from ~170 KB to ~110 KB of instructions.
+#pragma unroll 1
+            for (int st = 0; st < n_stage; ++st) {
+                if (st == 0) {
+                    if (active) {
+                        while (!mbar_try_wait(&s.mbar, parity)) {}
+                        parity ^= 1u;
+                        rows_p1<R>(s, r, tid);
+                    }
+                    __syncthreads();  // A: integer moments visible, tile fully consumed
+                    if (active) {
+                        if (tid == 0 && k + 1 < nfr) {
+                            fence_proxy_async();
+                            mbar_expect_tx(&s.mbar, R::TILE);
+                            tma_load_3d(s.tile, &tmap, &s.mbar, un.x0[0], un.y0[0], f + 1);
+                            tma_load_3d(s.tile + W * W, &tmap, &s.mbar, un.x0[1], un.y0[1], f + 1);
+                        }
+                        rows_p2_pre<R>(s, r, tid, p.clip_norm);
+                    }
+                } else if (st == 1) {
+                    __syncthreads();  // B: row spectra in X
+                    if (active) rows_p3a<R>(s, r, tid);
+                } else if (st == 3) {
+                    __syncthreads();  // D: column results in X
+                    if (active) rows_p5_pre<R>(s, r, tid);
+                }
+                if (active) fft_reg<W, 0>(r.v);
+                if (st == 0) {
+                    if (active) rows_p2_post<R>(s, r, tid);
+                } else if (st == 1) {
+                    if (active) rows_p3b_device<R>(s, r, tid, have_prev);
+                } else if (st == 2) {
+                    __syncthreads();  // C: every thread has read its column of X
+                    if (active) rows_p4_post<R>(s, r, tid);
+                }
             }
-            rows_p2<R>(s, r, tid, p.clip_norm);
-            __syncthreads();  // B: row spectra in X
-            rows_p3a<R>(s, r, tid);
-            rows_p3b_device<R>(s, r, tid, have_prev);
             if (have_prev) {
                 const bool dead0 = (r.half_alpha_prev[0] == 0.f) || (r.half_alpha_new[0] == 0.f);
                 const bool dead1 = (r.half_alpha_prev[1] == 0.f) || (r.half_alpha_new[1] == 0.f);
-                __syncthreads();  // C: every thread has read its column of X
-                rows_p4<R>(s, r, tid);
-                __syncthreads();  // D
-                rows_p5<R>(s, r, tid, dead0, dead1);
+                if (active) rows_p5_post<R>(s, r, tid, dead0, dead1);
                 __syncthreads();  // E1: block max / sum
-                rows_p6<R>(s, r, tid);
+                if (active) rows_p6<R>(s, r, tid);
                 __syncthreads();  // E2: first-argmax key
-                rows_dump_planes<R>(r, tid, p, un, f - 1);
-                rows_p7<R>(s, r, tid);
+                if (active) {
+                    rows_dump_planes<R>(r, tid, p, un, f - 1);
+                    rows_p7<R>(s, r, tid);
+                }
                 __syncthreads();  // F: neighbour rows dumped
-                rows_p8<R>(s, r, tid, p, un, f - 1);
+                if (active) rows_p8<R>(s, r, tid, p, un, f - 1);
             }
             r.half_alpha_prev[0] = r.half_alpha_new[0];
             r.half_alpha_prev[1] = r.half_alpha_new[1];
         }
-        __syncthreads();  // unit boundary: threads 0/1 may still read the neighbour rows (X) in rows_p8
+        __syncthreads();  // round boundary: threads 0/1 may still read the neighbour rows (X) in rows_p8
     }
 }
 
@@ -438,10 +478,13 @@ static PFN_encodeTiled get_encode_tiled() {
 static bool rows_eligible(const b2piv_engine* e, const void* d_frames, long long frame_stride, int pitch) {
     if (e->dtype != B2PIV_U8 || e->wy != e->wx || (e->wy != 64 && e->wy != 32)) return false;
     if ((pitch & 15) || (frame_stride & 15) || (((uintptr_t)d_frames) & 15)) return false;
+    // every TMA box must start on a 16-byte boundary in global memory: the window stride along x has to be a
+    // multiple of 16 pixels (32x32 at 75 % overlap has stride 8 and takes the generic kernel)
+    if ((e->wx - e->ox) & 15) return false;
     return get_encode_tiled() != nullptr;
 }
 
-template <class R>
+template <class R, int G>
 static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st) {
     constexpr int W = R::W;
     const int n_frames = gp.n_pairs + 1;
@@ -460,13 +503,13 @@ static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st) {
     p.n_rows = gp.n_rows; p.n_cols = gp.n_cols; p.sy = gp.sy; p.sx = gp.sx; p.n_pairs = gp.n_pairs;
     p.clip_norm = gp.clip_norm; p.border_nan = gp.border_nan; p.gauss_eps = gp.gauss_eps; p.keep = gp.keep;
     p.u = gp.u; p.v = gp.v; p.cmax = gp.cmax; p.s2n = gp.s2n; p.planes = gp.planes;
-    const size_t smem = sizeof(RSmem<R>) + 1024;
-    auto kern = piv_rows_kernel<R>;
+    const size_t smem = sizeof(RSmem<R>) * G + 1024;
+    auto kern = piv_rows_kernel<R, G>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, R::NT, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, R::NT * G, smem));
     if (occ < 1) return fail(e, B2PIV_ERR_CUDA, "rows kernel does not fit on an SM");
-    const long long resident = (long long)occ * e->sm_count;
+    const long long resident = (long long)occ * e->sm_count * G;   // resident work units
     const int nw = gp.n_rows * gp.n_cols, n_wp = (nw + 1) / 2;
     int run = e->run_len;
     if (run <= 0) {  // aim for >= 8 waves of work units; every unit start costs one extra forward transform
@@ -479,8 +522,9 @@ static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st) {
     p.run_len = run;
     const long long n_units = (long long)n_wp * ((gp.n_pairs + run - 1) / run);
     p.n_units = (int)n_units;
-    long long grid = resident < n_units ? resident : n_units;
-    kern<<<(unsigned)grid, R::NT, smem, st>>>(tmap, p);
+    long long grid = (n_units + G - 1) / G;
+    if (grid > (long long)occ * e->sm_count) grid = (long long)occ * e->sm_count;
+    kern<<<(unsigned)grid, R::NT * G, smem, st>>>(tmap, p);
     CK(cudaGetLastError());
     e->launches++;
     return B2PIV_OK;
@@ -490,11 +534,11 @@ static int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
     if (p.n_pairs <= 0) return B2PIV_OK;
     const bool can_rows = rows_eligible(e, p.frames, p.frame_stride, p.pitch);
     if (e->variant == 2 && !can_rows)
-        return fail(e, B2PIV_ERR_UNSUPPORTED, "rows kernel needs uint8 frames, a square 32/64 window and 16-byte aligned base/pitch");
+        return fail(e, B2PIV_ERR_UNSUPPORTED, "rows kernel needs uint8 frames, a square 32/64 window, 16-byte aligned base/pitch and an x stride that is a multiple of 16");
     if (can_rows && e->variant != 1) {
         e->last_variant = 2;
-        if (e->wy == 64) return launch_rows<RCfg<64>>(e, p, st);
-        return launch_rows<RCfg<32>>(e, p, st);
+        if (e->wy == 64) return launch_rows<RCfg<64>, 3>(e, p, st);
+        return launch_rows<RCfg<32>, 11>(e, p, st);
     }
     e->last_variant = 1;
 #define X(Y, XX, T, NW) if (e->wy == Y && e->wx == XX) return launch_pairs<Cfg<Y, XX, T, NW>>(e, p, st);

@@ -216,7 +216,7 @@ B2_HD void rows_p1(RSmem<R>& s, RRegs<R>& r, int tid) {
 // P2: statistics -> mean, 0.5/std ; convert + centre (+clip) ; forward row FFT ; transposed store into X
 // ------------------------------------------------------------------------------------------------------------
 template <class R>
-B2_HD void rows_p2(RSmem<R>& s, RRegs<R>& r, int tid, int clip_norm) {
+B2_HD void rows_p2_pre(RSmem<R>& s, RRegs<R>& r, int tid, int clip_norm) {
     constexpr int W = R::W;
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
@@ -238,13 +238,15 @@ B2_HD void rows_p2(RSmem<R>& s, RRegs<R>& r, int tid, int clip_norm) {
             r.v[4 * k + b] = make_float2(a0, a1);
         }
     }
-    fft_reg<W, 0>(r.v);
+}
+template <class R>
+B2_HD void rows_p2_post(RSmem<R>& s, RRegs<R>& r, int tid) {
 #pragma unroll
-    for (int k = 0; k < W; ++k) s.X[tid * R::P + k] = r.v[k];
+    for (int k = 0; k < R::W; ++k) s.X[tid * R::P + k] = r.v[k];
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// P3a: column from X, forward column FFT  -> r.v[ky] = Z(ky, col)
+// P3a: column from X (the forward column FFT follows)  -> r.v[ky] = Z(ky, col)
 // ------------------------------------------------------------------------------------------------------------
 template <class R>
 B2_HD void rows_p3a(RSmem<R>& s, RRegs<R>& r, int tid) {
@@ -252,7 +254,6 @@ B2_HD void rows_p3a(RSmem<R>& s, RRegs<R>& r, int tid) {
     const int c = column_of<W>(tid);
 #pragma unroll
     for (int y = 0; y < W; ++y) r.v[y] = s.X[y * R::P + c];
-    fft_reg<W, 0>(r.v);
 }
 
 // First frame of a run: park the scaled spectra only.
@@ -277,13 +278,13 @@ B2_HD void cross_step_a(RSmem<R>& s, RRegs<R>& r, int tid, int ky, float2 pz, bo
     }
     s.park[0][ky][tid] = make_float2(a0.x * INVN2, a0.y * INVN2);
     s.park[1][ky][tid] = make_float2(a1.x * INVN2, a1.y * INVN2);
-    if (have_prev) r.v[ky] = make_float2(r0.x - r1.y, r0.y + r1.x);               // G = R0 + i R1
+    if (have_prev) r.v[ky] = make_float2(r0.x - r1.y, -(r0.y + r1.x));            // conj(G), G = R0 + i R1
 }
-// part B: partner's (R0, R1) at (ky, -col) give G(-ky, col) = conj(R0) + i conj(R1)
+// part B: partner's (R0, R1) at (ky, -col) give G(-ky, col) = conj(R0) + i conj(R1); stored conjugated
 template <class R>
 B2_HD void cross_step_b(RRegs<R>& r, int ky, float2 q0, float2 q1) {
     constexpr int W = R::W;
-    if (ky != 0 && ky != W / 2) r.v[W - ky] = make_float2(q0.x + q1.y, q1.x - q0.y);
+    if (ky != 0 && ky != W / 2) r.v[W - ky] = make_float2(q0.x + q1.y, q0.y - q1.x);   // conj of G(-ky)
 }
 
 #ifdef __CUDACC__
@@ -309,28 +310,32 @@ __device__ __forceinline__ void rows_p3b_device(RSmem<R>& s, RRegs<R>& r, int ti
 #endif
 
 // ------------------------------------------------------------------------------------------------------------
-// P4: inverse column FFT, store column into X.   P5: row from X, inverse row FFT, per-row max / sum.
+// P4: (forward FFT of conj G along columns, then) store column into X.
+// P5: row from X, (forward FFT along the row, then) conjugate, clip, per-row max / sum.
 // ------------------------------------------------------------------------------------------------------------
 template <class R>
-B2_HD void rows_p4(RSmem<R>& s, RRegs<R>& r, int tid) {
+B2_HD void rows_p4_post(RSmem<R>& s, RRegs<R>& r, int tid) {
     constexpr int W = R::W;
-    fft_reg<W, 1>(r.v);
     const int c = column_of<W>(tid);
 #pragma unroll
     for (int y = 0; y < W; ++y) s.X[y * R::P + c] = r.v[y];
 }
 
 template <class R>
-B2_HD void rows_p5(RSmem<R>& s, RRegs<R>& r, int tid, bool dead0, bool dead1) {
-    constexpr int W = R::W;
+B2_HD void rows_p5_pre(RSmem<R>& s, RRegs<R>& r, int tid) {
 #pragma unroll
-    for (int x = 0; x < W; ++x) r.v[x] = s.X[tid * R::P + x];
-    fft_reg<W, 1>(r.v);
+    for (int x = 0; x < R::W; ++x) r.v[x] = s.X[tid * R::P + x];
+}
+
+// r.v holds FFT2(conj G) = conj(planes): plane 0 = Re, plane 1 = -Im.
+template <class R>
+B2_HD void rows_p5_post(RSmem<R>& s, RRegs<R>& r, int tid, bool dead0, bool dead1) {
+    constexpr int W = R::W;
     float m0 = 0.f, m1 = 0.f, s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int x = 0; x < W; ++x) {
         // clip to [0, 1] (inputs are uint8, no NaNs can occur, so fmin/fmax are exact here)
-        float a = dead0 ? 0.f : fminf(fmaxf(r.v[x].x, 0.f), 1.f), b = dead1 ? 0.f : fminf(fmaxf(r.v[x].y, 0.f), 1.f);
+        float a = dead0 ? 0.f : fminf(fmaxf(r.v[x].x, 0.f), 1.f), b = dead1 ? 0.f : fminf(fmaxf(-r.v[x].y, 0.f), 1.f);
         r.v[x] = make_float2(a, b);
         m0 = fmaxf(a, m0); m1 = fmaxf(b, m1);
         s0 += a; s1 += b;

@@ -84,8 +84,8 @@ static int run_rows(RParams p) {
                                p.frames + (long long)f * p.frame_stride + (long long)(un.y0[w] + row) * p.pitch + un.x0[w] + 16 * j, 16);
             memset(s.red, 0, sizeof(s.red));
             for (int t = 0; t < W; ++t) rows_p1<R>(s, regs[t], t);
-            for (int t = 0; t < W; ++t) rows_p2<R>(s, regs[t], t, p.clip_norm);
-            for (int t = 0; t < W; ++t) rows_p3a<R>(s, regs[t], t);
+            for (int t = 0; t < W; ++t) { rows_p2_pre<R>(s, regs[t], t, p.clip_norm); fft_reg<W, 0>(regs[t].v); rows_p2_post<R>(s, regs[t], t); }
+            for (int t = 0; t < W; ++t) { rows_p3a<R>(s, regs[t], t); fft_reg<W, 0>(regs[t].v); }
             snap = regs;
             for (int ky = 0; ky <= W / 2; ++ky) {
                 for (int t = 0; t < W; ++t) {
@@ -103,12 +103,12 @@ static int run_rows(RParams p) {
                 }
             }
             if (have_prev) {
-                for (int t = 0; t < W; ++t) rows_p4<R>(s, regs[t], t);
+                for (int t = 0; t < W; ++t) { fft_reg<W, 0>(regs[t].v); rows_p4_post<R>(s, regs[t], t); }
                 for (int k = 0; k < R::NWARP; ++k) for (int q = 4; q < 8; ++q) s.red[k][q] = 0;
                 for (int t = 0; t < W; ++t) {
                     const bool d0 = regs[t].half_alpha_prev[0] == 0.f || regs[t].half_alpha_new[0] == 0.f;
                     const bool d1 = regs[t].half_alpha_prev[1] == 0.f || regs[t].half_alpha_new[1] == 0.f;
-                    rows_p5<R>(s, regs[t], t, d0, d1);
+                    rows_p5_pre<R>(s, regs[t], t); fft_reg<W, 0>(regs[t].v); rows_p5_post<R>(s, regs[t], t, d0, d1);
                 }
                 for (int k = 0; k < R::NWARP; ++k) s.redk[k][0] = s.redk[k][1] = ~0ull;
                 for (int t = 0; t < W; ++t) rows_p6<R>(s, regs[t], t);

@@ -81,7 +81,8 @@ ROWS_CASES = [
     ((64, 64), (32, 32), (6, 200, 304), 2),    # runs of 2 pairs: unit boundaries inside the stack
     ((64, 64), (48, 48), (3, 150, 176), 1),
     ((32, 32), (16, 16), (5, 150, 208), 0),
-    ((32, 32), (24, 24), (4, 100, 144), 3),
+    ((32, 32), (0, 0), (4, 100, 144), 3),      # no overlap: stride 32
+    ((64, 64), (16, 16), (3, 200, 256), 0),    # stride 48
     ((64, 64), (32, 32), (3, 64 * 2 + 7, 64 * 3 + 16), 0),   # 3 x 5 windows: odd count -> last unit has one window
 ]
 
@@ -107,6 +108,15 @@ def test_rows_and_generic_kernels_agree(engine):
     for x, y in zip(a, b):
         assert np.array_equal(np.isnan(x), np.isnan(y))
         assert np.nanmax(np.abs(x - y) / (1 + np.abs(x))) < 2e-5
+
+
+def test_rows_kernel_refuses_stride_not_multiple_of_16(engine):
+    imgs = synth.particle_frames(3, 100, 144, dtype=np.uint8)
+    engine.set_option("kernel_variant", 2.0)
+    with pytest.raises(NotImplementedError):
+        engine.pairs(imgs, (32, 32), (24, 24))            # stride 8: TMA boxes would start off a 16-byte boundary
+    engine.set_option("kernel_variant", 0.0)
+    compare(engine, imgs, (32, 32), (24, 24), 0)        # auto: generic kernel
 
 
 def test_rows_kernel_refuses_unaligned_pitch(engine):

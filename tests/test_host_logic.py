@@ -1,0 +1,147 @@
+"""CPU: host-side logic of the binding (chunking with 1-frame halo, unit conversion, Dataset layout, errors) with the
+engine replaced by an oracle-backed fake - the arithmetic itself is covered by the -m gpu parity tests."""
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import ffpiv_oracle as O
+from pyorc_b200 import _xr, frames as b2frames, synth, velocimetry, window
+
+
+class FakeEngine:
+    """Test double with the Engine interface, computing with the oracle (never used by the product)."""
+
+    def __init__(self):
+        self.calls = []
+
+    def pairs(self, imgs, ws, ov, signal_threshold=None, stream=None):
+        self.calls.append(np.asarray(imgs).shape[0])
+        nr, nc = O.get_array_shape(np.asarray(imgs).shape[-2:], ws, ov)
+        u, v, c, s = O.uv_timestep(np.asarray(imgs), nc, nr, ws, ov, signal_threshold=signal_threshold)
+        return u.astype(np.float32), v.astype(np.float32), c, s
+
+    def ens_begin(self, dim_size, ws, ov, dtype):
+        nr, nc = O.get_array_shape(dim_size, ws, ov)
+        self._ens = None
+        self._shape = (nr, nc)
+        return nr, nc
+
+    def ens_add(self, imgs, ws, ov, corr_min=0.2, s2n_min=3.0, signal_threshold=None, stream=None):
+        if self._ens is None:
+            self._ens = O.Ensemble(*self._shape, ws, ov, corr_min, s2n_min, 0.0, signal_threshold)
+        self._ens.add_chunk(np.asarray(imgs))
+        return self._ens.corr_chunks[-1].copy(), self._ens.s2n_chunks[-1].copy()
+
+    def ens_finish(self, min_count):
+        e = self._ens
+        cnt = np.asarray(e.corr_count).reshape(-1).astype(np.float32)
+        corr_sum = np.array(e.corr_sum, dtype=np.float32, copy=True)
+        with np.errstate(all="ignore"):
+            corr_sum[:, cnt < min_count] = np.nan
+            mean = corr_sum / cnt[None, :, None, None]
+        u, v = O.u_v_displacement(mean, *self._shape)
+        return u.reshape(-1).astype(np.float32), v.reshape(-1).astype(np.float32), cnt
+
+
+@pytest.fixture()
+def fake(monkeypatch):
+    fe = FakeEngine()
+    monkeypatch.setattr(velocimetry, "get_engine", lambda device=0: fe)
+    monkeypatch.setattr(window, "available_memory", lambda: 64e9)
+    O.CLIP_NORMALIZED = True
+    return fe
+
+
+def make_frames(n=7, H=100, W=140, fps=30.0):
+    imgs = synth.particle_frames(n, H, W, dtype=np.uint8)
+    t = np.arange(n) / fps
+    res = 0.01
+    y = np.flipud(np.linspace(res / 2, res * (H - 0.5), H))
+    x = np.linspace(res / 2, res * (W - 0.5), W)
+    return _xr.DataArray(imgs, ("time", "y", "x"), {"time": t, "y": y, "x": x}, attrs={"camera_config": "{}"}), res
+
+
+def test_get_piv_matches_reference_semantics(fake):
+    da, res = make_frames()
+    ds = b2frames.get_piv(da, window_size=32, engine="b200", resolution=res)
+    nr, nc = O.get_array_shape((100, 140), (32, 32), (16, 16))
+    assert ds["v_x"].values.shape == (6, nr, nc) and ds["v_x"].values.dtype == np.float32
+    u, v, c, s = O.uv_timestep(da.values, nc, nr, (32, 32), (16, 16))
+    dt = 1 / 30.0
+    assert np.allclose(ds["v_x"].values, (u * res / dt).astype(np.float32), equal_nan=True, rtol=1e-6)
+    assert np.allclose(ds["v_y"].values, (v * res / dt).astype(np.float32), equal_nan=True, rtol=1e-6)
+    assert np.array_equal(ds["corr"].values, c) and np.array_equal(ds["s2n"].values, s, equal_nan=True)
+    # coordinates: integer window centres index the frame axes (helpers.get_axes)
+    cols, rows = window.get_rect_coordinates((100, 140), (32, 32), (16, 16))
+    assert np.array_equal(ds.coords["x"], da.coords["x"][cols]) and np.array_equal(ds.coords["y"], da.coords["y"][rows])
+    assert np.array_equal(ds.coords["time"], da.coords["time"][1:])
+    assert ds.attrs == da.attrs
+
+
+def test_default_overlap_and_rounding(fake):
+    da, res = make_frames(n=3)
+    ds = b2frames.get_piv(da, window_size=31, engine="b200", resolution=res)   # -> window 32, overlap int(round(31)/2) = 15
+    nr, nc = O.get_array_shape((100, 140), (32, 32), (15, 15))
+    assert ds["v_x"].values.shape == (2, nr, nc)
+
+
+def test_unknown_engine_raises_like_reference(fake):
+    da, res = make_frames(n=3)
+    with pytest.raises(ValueError, match="Selected PIV engine numba does not exist."):
+        b2frames.get_piv(da, window_size=32, engine="numba", resolution=res)
+
+
+def test_chunks_share_one_frame_halo(fake):
+    da, res = make_frames(n=11)
+    nr, nc = O.get_array_shape((100, 140), (32, 32), (16, 16))
+    y, x = np.arange(nr), np.arange(nc)
+    whole = velocimetry.get_b2piv(da, y, x, np.full(10, 1 / 30), (32, 32), (16, 16), (32, 32), res, res, chunksize=100)
+    fake.calls.clear()
+    parts = velocimetry.get_b2piv(da, y, x, np.full(10, 1 / 30), (32, 32), (16, 16), (32, 32), res, res, chunksize=4)
+    assert fake.calls == [4, 5, 4]            # frames [0:4], [3:8], [7:11]  (ffpiv.py:140)
+    for k in ("v_x", "v_y", "corr", "s2n"):
+        assert np.array_equal(whole[k].values, parts[k].values, equal_nan=True)
+    assert np.array_equal(parts.coords["time"], da.coords["time"][1:])
+
+
+def test_chunksize_errors_and_warning(fake, monkeypatch):
+    da, res = make_frames(n=6)
+    nr, nc = O.get_array_shape((100, 140), (32, 32), (16, 16))
+    y, x = np.arange(nr), np.arange(nc)
+    with pytest.raises(OverflowError):
+        velocimetry.get_b2piv(da, y, x, np.full(5, 1 / 30), (32, 32), (16, 16), (32, 32), res, res, chunksize=1)
+    monkeypatch.setattr(window, "available_memory", lambda: 1e5)   # tiny "device" -> chunksize floor 5 + warning
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        ds = velocimetry.get_b2piv(da, y, x, np.full(5, 1 / 30), (32, 32), (16, 16), (32, 32), res, res)
+    assert any("Memory availability is poor" in str(m.message) for m in w)
+    assert ds["v_x"].values.shape[0] == 5
+    with pytest.raises(ValueError):
+        velocimetry.get_b2piv(da, y[:-1], x, np.full(5, 1 / 30), (32, 32), (16, 16), (32, 32), res, res)
+    with pytest.raises(NotImplementedError):
+        velocimetry.get_b2piv(da, y, x, np.full(5, 1 / 30), (32, 32), (16, 16), (64, 64), res, res)
+
+
+def test_ensemble_mode_plumbing(fake):
+    da, res = make_frames(n=9)
+    nr, nc = O.get_array_shape((100, 140), (32, 32), (16, 16))
+    y, x = np.arange(nr), np.arange(nc)
+    ds = velocimetry.get_b2piv(da, y, x, np.full(8, 1 / 30), (32, 32), (16, 16), (32, 32), res, res, chunksize=5,
+                               ensemble_corr=True, corr_min=0.0, s2n_min=0.0, count_min=0.0)
+    ens = O.Ensemble(nr, nc, (32, 32), (16, 16), 0.0, 0.0, 0.0)
+    ens.add_chunk(da.values[0:5])
+    ens.add_chunk(da.values[4:9])
+    u, v, cm, sn = ens.finalize()
+    assert ds["v_x"].values.shape == (1, nr, nc)
+    assert np.allclose(ds["v_x"].values, (u * res * 30).astype(np.float32), equal_nan=True, rtol=1e-5)
+    assert np.allclose(ds["corr"].values, cm, equal_nan=True) and np.allclose(ds["s2n"].values, sn, equal_nan=True)
+    assert len(ds.coords["time"]) == 1
+
+
+def test_window_memory_model():
+    assert window.required_memory(101, (1080, 1920), (64, 64), (32, 32)) > 101 * 1080 * 1920
+    with pytest.raises(ValueError):
+        window.get_axis_shape(100, 16, 16)
+    with pytest.raises(NotImplementedError):
+        window.get_rect_coordinates((100, 100), (32, 32), (16, 16), search_area_size=(64, 64))

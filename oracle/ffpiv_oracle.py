@@ -18,8 +18,12 @@ algorithm (ffpiv's numba engine, which follows OpenPIV's ``fft_correlate_images`
 * ``uv_timestep``         <- pyorc/velocimetry/ffpiv.py:446-474 (nanmax / nanmean / s2n, verbatim semantics)
 * ``Ensemble``            <- pyorc/velocimetry/ffpiv.py:200-243, :245-288, :290-338, :345-376
 
-PARITY PIN STATUS: see DESIGN.md "Oracle pin".  The switches below mark every detail that pyorc's source does
-not determine (they live in ffpiv); each has one documented default.
+PARITY PIN STATUS: PINNED against the reference's own golden vectors.  tests/golden/make_ngwerere_golden.py runs
+the reference's Python (imported from /root/reference) up to the ffpiv call and this oracle then reproduces both
+pinned ``v_x`` vectors of pyorc's tests/test_frames.py:139-153 (window 10, per-time-step and ensemble mode) to
+< 2e-8 m/s (the pins are printed with 8 digits) - tests/test_golden.py.  ``v_y``, ``corr`` and ``s2n`` are not
+value-checked by any reference test.  The switches below mark the details that pyorc's source does not determine
+(they live in ffpiv); CLIP_NORMALIZED is decided by the pin, GAUSS_EPS and BORDER_RULE are not observable in it.
 
 All FFTs are pocketfft (numpy.fft / scipy.fft) in float64 - the same algorithm family rocket-fft binds.
 """
@@ -43,8 +47,10 @@ except Exception:  # pragma: no cover
 # --------------------------------------------------------------------------------------------------------------
 # Details that live in ffpiv (not determinable from pyorc's source).  One documented default each.
 # --------------------------------------------------------------------------------------------------------------
-#: OpenPIV-style ``normalize_intensity`` clips the zero-mean/unit-std window at 0 (``np.clip(w, 0, w.max())``).
-CLIP_NORMALIZED = True
+#: OpenPIV's ``normalize_intensity`` clips the zero-mean/unit-std window at 0 (``np.clip(w, 0, w.max())``); ffpiv
+#: does NOT: only the un-clipped variant reproduces pyorc's golden vectors (tests/test_frames.py:142-143) - to
+#: 2e-8 in both modes, see tests/test_golden.py - the clipped one is off by 25 %.  PINNED.
+CLIP_NORMALIZED = False
 #: epsilon added to the five correlation samples before the logs of the Gaussian fit.
 GAUSS_EPS = 1e-7
 #: what a correlation peak on the plane border yields: "nan" (no sub-pixel fit possible -> NaN displacement)

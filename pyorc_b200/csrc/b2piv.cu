@@ -346,7 +346,7 @@ struct b2piv_engine {
     int device = 0;
     std::string err;
     // options
-    int clip_norm = 1, border_nan = 1, copy_chunks = 8;
+    int clip_norm = 0, border_nan = 1, copy_chunks = 8;   // clip_norm = 0 is what ffpiv does (pinned, tests/test_golden.py)
     int variant = 0;    // 0: auto, 1: generic shared-memory kernel, 2: row-per-thread TMA kernel (error if ineligible)
     int run_len = 0;    // frame pairs per work unit of the rows kernel (0: auto)
     int last_variant = 0;

@@ -6,6 +6,7 @@
 #include "../../include/b2piv.h"
 #include "piv_core.cuh"
 #include "piv_rows.cuh"
+#include "piv_direct.cuh"
 
 #include <cuda.h>   // CUtensorMap (types only; the encoder is resolved at run time, libcuda is not linked)
 
@@ -264,6 +265,69 @@ __global__ void __launch_bounds__(C::NT) piv_ens_kernel(Params p, EnsParams ep, 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Any-size windows (piv_direct.cuh): direct circular cross-correlation, one CTA per (pair, window).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DNT) piv_direct_kernel(Params p, int wy, int wx, long long n_items) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DView s = direct_view(smem_raw, wy, wx);
+    const int tid = threadIdx.x;
+    const int nw = p.n_rows * p.n_cols;
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int pair = (int)(item / nw), widx = (int)(item % nw);
+        direct_load(s, tid, p, pair, widx);            __syncthreads();
+        direct_center(s, tid, p);                      __syncthreads();
+        direct_correlate(s, tid, p, pair, widx);       __syncthreads();
+        direct_peak(s, tid, p, pair, widx);            __syncthreads();
+    }
+}
+
+// ensemble variant: CTA owns a window, walks the frame pairs, masked planes summed in registers
+__global__ void __launch_bounds__(DNT) piv_direct_ens_kernel(Params p, EnsParams ep, int wy, int wx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DView s = direct_view(smem_raw, wy, wx);
+    const int tid = threadIdx.x;
+    const int nw = p.n_rows * p.n_cols, npx = wy * wx;
+    constexpr int EPT = 16;   // 64*64 / 256
+    for (int widx = blockIdx.x; widx < nw; widx += gridDim.x) {
+        float acc[EPT];
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) acc[k] = 0.f;
+        float cnt = 0.f;
+        for (int pr = 0; pr < p.n_pairs; ++pr) {
+            direct_load(s, tid, p, pr, widx);          __syncthreads();
+            direct_center(s, tid, p);                  __syncthreads();
+            Params q = p; q.planes = nullptr;
+            direct_correlate(s, tid, q, pr, widx);     __syncthreads();
+            const unsigned long long key = d_tot_max(s, 4);
+            float cmax = __uint_as_float((unsigned)(key >> 32));
+            float s2n = cmax / (d_tot_sum(s, 5) / (float)npx);
+            bool ok = (cmax >= ep.corr_min) && (s2n >= ep.s2n_min) && isfinite(cmax);
+            if (p.keep && !p.keep[widx]) ok = false;
+            if (ok) {
+#pragma unroll
+                for (int k = 0; k < EPT; ++k) {
+                    const int e = tid + k * DNT;
+                    if (e < npx) acc[k] += s.plane[e];
+                }
+                if (cmax > 1e-6f) cnt += 1.f;
+            } else {
+                cmax = 0.f; s2n = 0.f;
+            }
+            if (tid == 0) { p.cmax[(long long)pr * nw + widx] = cmax; p.s2n[(long long)pr * nw + widx] = s2n; }
+            __syncthreads();
+        }
+        float* dst = ep.plane_sum + (long long)widx * npx;
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int e = tid + k * DNT;
+            if (e < npx) dst[e] += acc[k];
+        }
+        if (tid == 0) ep.count[widx] += cnt;
+    }
+}
+
 // Ensemble finish: count filter -> mean plane -> first-argmax + Gaussian (ffpiv.py:280-282, :324). One CTA/window.
 __global__ void __launch_bounds__(256) ens_finish_kernel(const float* __restrict__ plane_sum, const float* __restrict__ count,
                                                          int wy, int wx, float min_count, int border_nan, float eps,
@@ -347,7 +411,8 @@ struct b2piv_engine {
     std::string err;
     // options
     int clip_norm = 0, border_nan = 1, copy_chunks = 8;   // clip_norm = 0 is what ffpiv does (pinned, tests/test_golden.py)
-    int variant = 0;    // 0: auto, 1: generic shared-memory kernel, 2: row-per-thread TMA kernel (error if ineligible)
+    int variant = 0;    // 0: auto, 1: generic shared-memory FFT kernel, 2: row-per-thread TMA kernel (error if
+                        // ineligible), 3: direct any-size kernel
     int run_len = 0;    // frame pairs per work unit of the rows kernel (0: auto)
     int last_variant = 0;
     float gauss_eps = 1e-7f;
@@ -449,11 +514,43 @@ static int launch_ens(b2piv_engine* e, const Params& p, const EnsParams& ep, cud
     X(128, 64, 256, 2)        \
     X(128, 128, 512, 1)
 
-static bool supported(int wy, int wx) {
+static bool fft_config(int wy, int wx) {
 #define X(Y, XX, T, NW) if (wy == Y && wx == XX) return true;
     B2PIV_CONFIGS(X)
 #undef X
     return false;
+}
+static bool supported(int wy, int wx) { return fft_config(wy, wx) || (wy >= 4 && wx >= 4 && wy <= 64 && wx <= 64); }
+
+static int launch_direct(b2piv_engine* e, const Params& p, cudaStream_t st) {
+    const long long n_items = (long long)p.n_rows * p.n_cols * p.n_pairs;
+    if (n_items <= 0) return B2PIV_OK;
+    const size_t smem = direct_smem_bytes(e->wy, e->wx);
+    CK(cudaFuncSetAttribute(piv_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, piv_direct_kernel, DNT, smem));
+    if (occ < 1) return fail(e, B2PIV_ERR_CUDA, "direct kernel does not fit on an SM");
+    long long grid = (long long)occ * e->sm_count;
+    if (grid > n_items) grid = n_items;
+    piv_direct_kernel<<<(unsigned)grid, DNT, smem, st>>>(p, e->wy, e->wx, n_items);
+    CK(cudaGetLastError());
+    e->launches++;
+    return B2PIV_OK;
+}
+static int launch_direct_ens(b2piv_engine* e, const Params& p, const EnsParams& ep, cudaStream_t st) {
+    const int nw = p.n_rows * p.n_cols;
+    if (p.n_pairs <= 0) return B2PIV_OK;
+    const size_t smem = direct_smem_bytes(e->wy, e->wx);
+    CK(cudaFuncSetAttribute(piv_direct_ens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, piv_direct_ens_kernel, DNT, smem));
+    if (occ < 1) return fail(e, B2PIV_ERR_CUDA, "direct kernel does not fit on an SM");
+    long long grid = (long long)occ * e->sm_count;
+    if (grid > nw) grid = nw;
+    piv_direct_ens_kernel<<<(unsigned)grid, DNT, smem, st>>>(p, ep, e->wy, e->wx);
+    CK(cudaGetLastError());
+    e->launches++;
+    return B2PIV_OK;
 }
 
 
@@ -540,6 +637,10 @@ static int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
         if (e->wy == 64) return launch_rows<RCfg<64>, 3>(e, p, st);
         return launch_rows<RCfg<32>, 11>(e, p, st);
     }
+    if (!fft_config(e->wy, e->wx) || (e->variant == 3 && e->wy <= 64 && e->wx <= 64)) {
+        e->last_variant = 3;
+        return launch_direct(e, p, st);
+    }
     e->last_variant = 1;
 #define X(Y, XX, T, NW) if (e->wy == Y && e->wx == XX) return launch_pairs<Cfg<Y, XX, T, NW>>(e, p, st);
     B2PIV_CONFIGS(X)
@@ -547,6 +648,7 @@ static int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
     return fail(e, B2PIV_ERR_UNSUPPORTED, "window size not compiled in");
 }
 static int dispatch_ens(b2piv_engine* e, const Params& p, const EnsParams& ep, cudaStream_t st) {
+    if (!fft_config(e->wy, e->wx) || (e->variant == 3 && e->wy <= 64 && e->wx <= 64)) return launch_direct_ens(e, p, ep, st);
 #define X(Y, XX, T, NW) if (e->wy == Y && e->wx == XX) return launch_ens<Cfg<Y, XX, T, NW>>(e, p, ep, st);
     B2PIV_CONFIGS(X)
 #undef X
@@ -652,7 +754,7 @@ int b2piv_plan(b2piv_engine* e, int height, int width, int win_y, int win_x, int
     if (height < win_y || width < win_x) return fail(e, B2PIV_ERR_ARG, "frame smaller than the interrogation window");
     if (!supported(win_y, win_x))
         return fail(e, B2PIV_ERR_UNSUPPORTED, "window " + std::to_string(win_y) + "x" + std::to_string(win_x) +
-                                                  " not supported (powers of two 16..128 per axis)");
+                                                  " not supported (any size 4..64 per axis, or 64x128 / 128x64 / 128x128)");
     CK(cudaSetDevice(e->device));
     e->H = height; e->W = width; e->wy = win_y; e->wx = win_x; e->oy = ovl_y; e->ox = ovl_x; e->dtype = dtype;
     e->n_rows = (height - win_y) / (win_y - ovl_y) + 1;

@@ -2,6 +2,7 @@
 // "thread by thread, phase by phase", to validate index mathematics without a GPU.  Never loaded by pyorc_b200.
 #include "../../pyorc_b200/csrc/piv_core.cuh"
 #include "../../pyorc_b200/csrc/piv_rows.cuh"
+#include "../../pyorc_b200/csrc/piv_direct.cuh"
 #include <vector>
 #include <cstring>
 #include <cmath>
@@ -142,4 +143,29 @@ extern "C" int b2piv_emul_rows(const unsigned char* frames, int n_frames, int H,
     if (win == 64) return run_rows<RCfg<64>>(p);
     if (win == 32) return run_rows<RCfg<32>>(p);
     return -1;
+}
+
+
+// ---- direct any-size kernel (piv_direct.cuh) -------------------------------------------------------------------------
+extern "C" int b2piv_emul_direct(const void* frames, int n_frames, int H, int W, int is_f32, int wy, int wx, int oy, int ox,
+                                 int clip_norm, int border_nan, float eps, float* u, float* v, float* cmax, float* s2n, float* planes) {
+    Params p;
+    memset(&p, 0, sizeof(p));
+    p.frames = frames; p.pitch = W * (is_f32 ? 4 : 1); p.frame_stride = (long long)H * p.pitch; p.is_f32 = is_f32;
+    p.n_rows = (H - wy) / (wy - oy) + 1; p.n_cols = (W - wx) / (wx - ox) + 1;
+    p.sy = wy - oy; p.sx = wx - ox; p.n_pairs = n_frames - 1;
+    p.clip_norm = clip_norm; p.border_nan = border_nan; p.gauss_eps = eps;
+    p.u = u; p.v = v; p.cmax = cmax; p.s2n = s2n; p.planes = planes;
+    std::vector<unsigned char> mem(direct_smem_bytes(wy, wx) + 64);
+    DView s = direct_view(mem.data(), wy, wx);
+    const int nw = p.n_rows * p.n_cols;
+    for (int pair = 0; pair < p.n_pairs; ++pair)
+        for (int w = 0; w < nw; ++w) {
+            memset(s.red, 0, 64 * sizeof(unsigned long long));
+            for (int t = 0; t < DNT; ++t) direct_load(s, t, p, pair, w);
+            for (int t = 0; t < DNT; ++t) direct_center(s, t, p);
+            for (int t = 0; t < DNT; ++t) direct_correlate(s, t, p, pair, w);
+            for (int t = 0; t < DNT; ++t) direct_peak(s, t, p, pair, w);
+        }
+    return 0;
 }

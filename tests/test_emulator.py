@@ -99,3 +99,60 @@ def test_rows_phases_match_oracle(emul_rows, win, ovl, shape, run_len, clip):
     assert np.abs(eu[ok] - u[ok]).max() < 1e-3 and np.abs(ev[ok] - v[ok]).max() < 1e-3
     assert np.abs(ec - c).max() < 2e-6
     assert np.nanmax(np.abs(es - s) / np.abs(s)) < 1e-5
+
+
+@pytest.fixture(scope="module")
+def emul_direct():
+    import __graft_entry__ as g
+
+    lib = ctypes.CDLL(g.build_emulator())
+
+    def run(imgs, ws, ov, clip=0, border_nan=1):
+        imgs = np.ascontiguousarray(imgs)
+        n, H, W = imgs.shape
+        nr, nc = O.get_array_shape((H, W), ws, ov)
+        outs = [np.full((n - 1, nr, nc), -7, np.float32) for _ in range(4)]
+        planes = np.zeros((n - 1, nr * nc, ws[0], ws[1]), np.float32)
+        rc = lib.b2piv_emul_direct(
+            imgs.ctypes.data_as(ctypes.c_void_p), n, H, W, int(imgs.dtype == np.float32), ws[0], ws[1], ov[0], ov[1], clip, border_nan,
+            ctypes.c_float(1e-7), *[o.ctypes.data_as(ctypes.c_void_p) for o in outs], planes.ctypes.data_as(ctypes.c_void_p),
+        )
+        assert rc == 0
+        return outs, planes
+
+    return run
+
+
+@pytest.mark.parametrize("ws,ov,shape", [((10, 10), (5, 5), (3, 60, 70)), ((26, 26), (12, 12), (2, 80, 100)), ((20, 14), (10, 7), (2, 70, 60)),
+                                         ((9, 11), (4, 5), (2, 40, 50)), ((32, 32), (16, 16), (2, 70, 90))])
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32])
+def test_direct_phases_match_oracle(emul_direct, ws, ov, shape, dtype):
+    """Any-size direct-correlation kernel (pyorc's non power-of-two windows: 10, 20, 26, ...)."""
+    O.CLIP_NORMALIZED = False
+    imgs = synth.particle_frames(*shape, dtype=dtype)
+    imgs[:, :12, :12] = 0
+    nr, nc = O.get_array_shape(shape[1:], ws, ov)
+    _, _, corr = O.cross_corr(imgs, ws, ov)
+    u, v, c, s = O.uv_timestep(imgs, nc, nr, ws, ov)
+    (eu, ev, ec, es), pl = emul_direct(imgs, ws, ov)
+    assert np.abs(pl - corr).max() < 2e-6
+    assert np.array_equal(np.isnan(eu), np.isnan(u)) and np.array_equal(np.isnan(es), np.isnan(s))
+    ok = np.isfinite(u)
+    assert np.abs(eu[ok] - u[ok]).max() < 1e-3 and np.abs(ev[ok] - v[ok]).max() < 1e-3
+    assert np.abs(ec - c).max() < 2e-6
+
+
+def test_direct_phases_reproduce_reference_golden(emul_direct):
+    """The kernel code path itself (on the CPU) against pyorc's pinned v_x vector (tests/test_frames.py:143)."""
+    import os
+
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ngwerere_proj.npz"))
+    frames, t, res, pin = d["frames"], d["time_s"], float(d["resolution"]), d["pinned_vx_timestep"]
+    (eu, ev, ec, es), _ = emul_direct(frames, (10, 10), (5, 5))
+    vx = (eu * res / np.diff(t)[:, None, None]).astype(np.float32)
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", category=RuntimeWarning)
+        got = np.nanmean(vx, axis=0).flatten()[-4:]
+    assert np.allclose(got, pin, rtol=0, atol=2e-6), (got, pin)

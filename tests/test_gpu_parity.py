@@ -128,6 +128,25 @@ def test_rows_kernel_refuses_unaligned_pitch(engine):
     compare(engine, imgs, (64, 64), (32, 32), 1)   # auto falls back to the generic kernel
 
 
+DIRECT_CASES = [
+    ((10, 10), (5, 5), (3, 100, 120)),      # pyorc's golden-test window
+    ((26, 26), (12, 12), (3, 150, 180)),    # camera-config window 25 -> 26, overlap int(25/2)
+    ((20, 14), (10, 7), (2, 90, 80)),
+    ((50, 50), (25, 25), (2, 160, 210)),
+    ((9, 11), (4, 5), (2, 50, 60)),         # odd sizes (never produced by pyorc, allowed by the ABI)
+    ((64, 64), (32, 32), (2, 140, 200)),    # power of two through the direct kernel (variant 3)
+]
+
+
+@pytest.mark.parametrize("ws,ov,shape", DIRECT_CASES)
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32])
+def test_direct_kernel_any_window_size(engine, ws, ov, shape, dtype):
+    imgs = synth.particle_frames(*shape, dtype=dtype)
+    imgs[:, :20, :20] = 0
+    compare(engine, imgs, ws, ov, 0, variant=3)
+    engine.set_option("kernel_variant", 0.0)
+
+
 def test_odd_window_count_and_ragged_edges(engine):
     # 3 x 5 windows (odd count -> last work item holds a single window); frame not a multiple of the stride
     imgs = synth.particle_frames(3, 64 * 2 + 7, 64 * 3 + 13, dtype=np.uint8)
@@ -172,3 +191,47 @@ def test_errors(engine):
         engine.pairs(imgs[:1], (64, 64), (32, 32))
     with pytest.raises(ValueError):
         engine.pairs(imgs, (128, 128), (64, 64))  # frame smaller than window
+
+
+ENS_CASES = [
+    ((64, 64), (32, 32), (6, 200, 304), 0.3, 2.0),
+    ((32, 32), (16, 16), (6, 100, 160), 0.2, 3.0),
+    ((10, 10), (5, 5), (5, 60, 80), 0.0, 0.0),
+    ((26, 26), (12, 12), (5, 90, 120), 0.2, 1.5),
+    ((128, 128), (64, 64), (4, 300, 420), 0.2, 3.0),
+]
+
+
+@pytest.mark.parametrize("ws,ov,shape,corr_min,s2n_min", ENS_CASES)
+def test_ensemble_mode_matches_oracle(engine, ws, ov, shape, corr_min, s2n_min):
+    """Ensemble correlation (pyorc/velocimetry/ffpiv.py:182-376): thresholds + plane sums on the device, two chunks."""
+    O.CLIP_NORMALIZED = False
+    engine.set_option("clip_normalized", 0.0)
+    engine.set_option("kernel_variant", 0.0)
+    imgs = synth.particle_frames(*shape, dtype=np.uint8)
+    imgs[:, : ws[0], : ws[1]] = 0                      # one dead window
+    imgs[2] = synth.particle_frames(1, shape[1], shape[2], dtype=np.uint8, seed=7)[0]   # a decorrelated frame -> masked pairs
+    nr, nc = O.get_array_shape(shape[1:], ws, ov)
+    half = shape[0] // 2 + 1
+    chunks = [imgs[:half], imgs[half - 1 :]]
+    ens = O.Ensemble(nr, nc, ws, ov, corr_min=corr_min, s2n_min=s2n_min, count_min=0.2)
+    engine.ens_begin(shape[1:], ws, ov, np.uint8)
+    got_c, got_s = [], []
+    for ch in chunks:
+        ens.add_chunk(ch)
+        c, s_ = engine.ens_add(ch, ws, ov, corr_min=corr_min, s2n_min=s2n_min)
+        got_c.append(c); got_s.append(s_)
+    for a, b in zip(got_c, ens.corr_chunks):
+        assert np.array_equal(a == 0, b == 0), "mask of rejected pairs differs"
+        assert np.abs(a - b).max() <= 5e-6
+    for a, b in zip(got_s, ens.s2n_chunks):
+        assert np.abs(a - b).max() <= 2e-5 * max(1.0, np.abs(b).max())
+    u, v, cm, sn = ens.finalize()
+    gu, gv, cnt = engine.ens_finish(0.2 * len(chunks))
+    assert np.array_equal(cnt, np.asarray(ens.corr_count).reshape(-1))
+    u, v = u.reshape(-1), v.reshape(-1)
+    assert np.array_equal(np.isnan(gu), np.isnan(u))
+    ok = np.isfinite(u)
+    same = (np.abs(np.round(gu[ok]) - np.round(u[ok])) + np.abs(np.round(gv[ok]) - np.round(v[ok]))) < 0.5
+    assert same.mean() >= 0.99
+    assert np.abs(gu[ok][same] - u[ok][same]).max() <= 2e-3 and np.abs(gv[ok][same] - v[ok][same]).max() <= 2e-3

@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
         if (has_unit && tid == 0) {
             fence_proxy_async();
             mbar_expect_tx(&s.mbar, R::TILE);
-            tma_load_3d(s.tile, &tmap, &s.mbar, un.x0[0], un.y0[0], un.f0);
-            tma_load_3d(s.tile + W * W, &tmap, &s.mbar, un.x0[1], un.y0[1], un.f0);
+            tma_load_3d(s.tile(), &tmap, &s.mbar, un.x0[0], un.y0[0], un.f0);
+            tma_load_3d(s.tile() + W * W, &tmap, &s.mbar, un.x0[1], un.y0[1], un.f0);
         }
         for (int k = 0; k < maxn; ++k) {
             const bool active = k < nfr;
@@ -136,38 +136,31 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
                         parity ^= 1u;
                         rows_p1<R>(s, r, tid);
                     }
-                    __syncthreads();  // A: integer moments visible, tile fully consumed
-                    if (active) {
-                        if (tid == 0 && k + 1 < nfr) {
-                            fence_proxy_async();
-                            mbar_expect_tx(&s.mbar, R::TILE);
-                            tma_load_3d(s.tile, &tmap, &s.mbar, un.x0[0], un.y0[0], f + 1);
-                            tma_load_3d(s.tile + W * W, &tmap, &s.mbar, un.x0[1], un.y0[1], f + 1);
-                        }
-                        rows_p2_pre<R>(s, r, tid, p.clip_norm);
-                    }
-                } else if (st == 1) {
-                    __syncthreads();  // B: row spectra in X
-                    if (active) rows_p3a<R>(s, r, tid);
+                    __syncthreads();  // A: integer moments visible, tile (aliased on X) fully consumed
+                    if (active) rows_p2_pre<R>(s, r, tid, p.clip_norm);
                 } else if (st == 3) {
-                    __syncthreads();  // D: column results in X
-                    if (active) rows_p5_pre<R>(s, r, tid);
+                    transpose_inv_device<R>(s, r, tid, active);   // columns -> rows
                 }
                 if (active) fft_reg<W, 0>(r.v);
                 if (st == 0) {
-                    if (active) rows_p2_post<R>(s, r, tid);
+                    transpose_fwd_device<R>(s, r, tid, active);   // row spectra -> columns
                 } else if (st == 1) {
                     if (active) rows_p3b_device<R>(s, r, tid, have_prev);
-                } else if (st == 2) {
-                    __syncthreads();  // C: every thread has read its column of X
-                    if (active) rows_p4_post<R>(s, r, tid);
                 }
             }
             if (have_prev) {
                 const bool dead0 = (r.half_alpha_prev[0] == 0.f) || (r.half_alpha_new[0] == 0.f);
                 const bool dead1 = (r.half_alpha_prev[1] == 0.f) || (r.half_alpha_new[1] == 0.f);
                 if (active) rows_p5_post<R>(s, r, tid, dead0, dead1);
-                __syncthreads();  // E1: block max / sum
+            }
+            __syncthreads();  // E1: block max / sum; X (and the tile aliased on it) is free again
+            if (active && tid == 0 && k + 1 < nfr) {
+                fence_proxy_async();
+                mbar_expect_tx(&s.mbar, R::TILE);
+                tma_load_3d(s.tile(), &tmap, &s.mbar, un.x0[0], un.y0[0], f + 1);
+                tma_load_3d(s.tile() + W * W, &tmap, &s.mbar, un.x0[1], un.y0[1], f + 1);
+            }
+            if (have_prev) {
                 if (active) rows_p6<R>(s, r, tid);
                 __syncthreads();  // E2: first-argmax key
                 if (active) {
@@ -180,7 +173,7 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
             r.half_alpha_prev[0] = r.half_alpha_new[0];
             r.half_alpha_prev[1] = r.half_alpha_new[1];
         }
-        __syncthreads();  // round boundary: threads 0/1 may still read the neighbour rows (X) in rows_p8
+        __syncthreads();  // round boundary: the next round's first TMA overwrites X
     }
 }
 
@@ -414,6 +407,7 @@ struct b2piv_engine {
     int variant = 0;    // 0: auto, 1: generic shared-memory FFT kernel, 2: row-per-thread TMA kernel (error if
                         // ineligible), 3: direct any-size kernel
     int run_len = 0;    // frame pairs per work unit of the rows kernel (0: auto)
+    int groups = 0;     // window-pair groups per CTA of the rows kernel (0: default)
     int last_variant = 0;
     float gauss_eps = 1e-7f;
     // plan
@@ -634,8 +628,15 @@ static int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
         return fail(e, B2PIV_ERR_UNSUPPORTED, "rows kernel needs uint8 frames, a square 32/64 window, 16-byte aligned base/pitch and an x stride that is a multiple of 16");
     if (can_rows && e->variant != 1) {
         e->last_variant = 2;
-        if (e->wy == 64) return launch_rows<RCfg<64>, 3>(e, p, st);
-        return launch_rows<RCfg<32>, 11>(e, p, st);
+        // groups per CTA (lockstep width): 64x64 -> 4 groups = 8 warps per SM, 32x32 -> 12 groups = 12 warps per SM
+        if (e->wy == 64) {
+            if (e->groups == 1) return launch_rows<RCfg<64>, 1>(e, p, st);
+            if (e->groups == 2) return launch_rows<RCfg<64>, 2>(e, p, st);
+            return launch_rows<RCfg<64>, 4>(e, p, st);
+        }
+        if (e->groups == 1) return launch_rows<RCfg<32>, 1>(e, p, st);
+        if (e->groups == 2 || e->groups == 4) return launch_rows<RCfg<32>, 4>(e, p, st);
+        return launch_rows<RCfg<32>, 12>(e, p, st);
     }
     if (!fft_config(e->wy, e->wx) || (e->variant == 3 && e->wy <= 64 && e->wx <= 64)) {
         e->last_variant = 3;
@@ -741,6 +742,7 @@ int b2piv_set_option(b2piv_engine* e, const char* name, double value) {
     else if (n == "copy_chunks") e->copy_chunks = value < 1 ? 1 : (int)value;
     else if (n == "kernel_variant") e->variant = (int)value;
     else if (n == "run_len") e->run_len = value < 0 ? 0 : (int)value;
+    else if (n == "groups") e->groups = value < 0 ? 0 : (int)value;
     else return fail(e, B2PIV_ERR_ARG, "unknown option " + n);
     return B2PIV_OK;
 }

@@ -69,17 +69,28 @@ struct RCfg {
     static constexpr int HS = W / 2 + 1;      // ky = 0 .. W/2 computed directly, the rest by Hermitian symmetry
     static constexpr int NPX = W * W;
     static constexpr int TILE = 2 * W * W;    // bytes: two windows of one frame, uint8
+    // Transposes move 32x32 blocks: block b (pitch 33 float2) is READ by warp b.  A 64x64 transpose first moves the
+    // two off-diagonal blocks (one CTA barrier), then the diagonal ones (warp-synchronous), reusing the same two
+    // blocks - half a plane - so a group needs ~52 KB of shared memory and FOUR groups (8 warps, two per
+    // scheduler) fit on an SM.
+    static constexpr int BP = 33;                 // block pitch in float2
+    static constexpr int XBLK = 32 * BP;          // float2 per block
 };
 
 template <class R>
 struct RSmem {
-    alignas(1024) unsigned char tile[R::TILE];   // TMA destination: [window][row][W bytes], 64B/32B swizzled
-    float2 X[R::W * R::P];                       // transpose plane (also reused for the 3 neighbour rows)
+    // transpose plane; the TMA tile ([window][row][W bytes], 64B/32B swizzled) is ALIASED onto its start: the tile is
+    // consumed into registers before the first transpose of a frame and refilled after the last one
+    alignas(1024) float2 X[R::NWARP][R::XBLK];
+    float nb[2][3][R::W];                        // the three plane rows around each peak (Gaussian fit)
     float2 park[2][R::HS][R::NT];                // previous frame: scaled spectra A0, A1 at (ky <= W/2, own column)
     unsigned red[R::NWARP][8];                   // block reductions (integer moments, float bits)
     unsigned long long redk[R::NWARP][2];
     unsigned long long mbar;                     // TMA completion barrier
+    B2_HD unsigned char* tile() { return reinterpret_cast<unsigned char*>(X); }
 };
+static_assert(sizeof(float2) * RCfg<64>::NWARP * RCfg<64>::XBLK >= RCfg<64>::TILE, "tile must fit in the transpose blocks");
+static_assert(sizeof(float2) * RCfg<32>::NWARP * RCfg<32>::XBLK >= RCfg<32>::TILE, "tile must fit in the transpose blocks");
 
 struct RParams {
     const unsigned char* frames;   // only used by the host emulator (device reads through the tensor map)
@@ -100,7 +111,7 @@ struct RParams {
 // (kx = 0 and W/2 are their own partners): warp w, lane l<16 -> column 16w+l ; lane 16+l -> (W-(16w+l)) % W,
 // except (w=0,l=0) -> W/2.
 template <int W>
-B2_HD int column_of(int tid) {
+B2_HD constexpr int column_of(int tid) {
     const int w = tid >> 5, l = tid & 31;
     if (l < 16) return 16 * w + l;
     const int m = 16 * w + (l - 16);
@@ -187,7 +198,7 @@ B2_HD void rows_p1(RSmem<R>& s, RRegs<R>& r, int tid) {
     for (int w = 0; w < 2; ++w) {
 #pragma unroll
         for (int j = 0; j < W / 16; ++j) {
-            const uint4 q = *reinterpret_cast<const uint4*>(s.tile + tile_chunk_offset<W>(w, tid, j));
+            const uint4 q = *reinterpret_cast<const uint4*>(s.tile() + tile_chunk_offset<W>(w, tid, j));
             r.px[w][4 * j + 0] = q.x; r.px[w][4 * j + 1] = q.y; r.px[w][4 * j + 2] = q.z; r.px[w][4 * j + 3] = q.w;
         }
 #pragma unroll
@@ -239,22 +250,109 @@ B2_HD void rows_p2_pre(RSmem<R>& s, RRegs<R>& r, int tid, int clip_norm) {
         }
     }
 }
-template <class R>
-B2_HD void rows_p2_post(RSmem<R>& s, RRegs<R>& r, int tid) {
+// ---- forward transpose (thread = row  ->  thread = column), 32x32 blocks, see RCfg ----------------------------
+// WQ = warp of this thread (compile time so that every register index stays static).
+// "other": the values of my row that belong to columns owned by the OTHER warp go to block (1-WQ); after a CTA barrier I
+// read, from block WQ, the other warp's rows at my column.  "own": same inside the warp (warp-synchronous).
+// All four primitives work IN PLACE on r.v with static register indices (SET / HALF are compile-time):
+//   forward : a thread sends the entries of its row that belong to the columns of warp SET, v[column_of(32*SET+sl)],
+//             and later refills exactly those registers with rows 32*SRC .. 32*SRC+31 of its own column.  Either warp
+//             ends with v[column_of(y)] = entry y, which tr_unpermute() turns into natural order.
+//   inverse : a thread sends v[32*HALF + rr] (its column at the rows of warp HALF) and refills those registers with
+//             its own row at the columns of the sending warp: v[i] = entry kx = column_of(i) in the end.
+template <class R, int SET>
+B2_HD void tr_fwd_store_set(float2* blk, const RRegs<R>& r, int lane) {
 #pragma unroll
-    for (int k = 0; k < R::W; ++k) s.X[tid * R::P + k] = r.v[k];
+    for (int sl = 0; sl < 32; ++sl) blk[lane * R::BP + sl] = r.v[column_of<R::W>(32 * SET + sl)];
+}
+template <class R, int SET>
+B2_HD void tr_fwd_load_set(const float2* blk, RRegs<R>& r, int lane) {
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) r.v[column_of<R::W>(32 * SET + rr)] = blk[rr * R::BP + lane];
+}
+template <class R, int HALF>
+B2_HD void tr_inv_store_half(float2* blk, const RRegs<R>& r, int lane) {
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) blk[rr * R::BP + lane] = r.v[32 * HALF + rr];
+}
+template <class R, int HALF>
+B2_HD void tr_inv_load_half(const float2* blk, RRegs<R>& r, int lane) {
+#pragma unroll
+    for (int sl = 0; sl < 32; ++sl) r.v[32 * HALF + sl] = blk[lane * R::BP + sl];
+}
+// v[column_of(n)] = entry n  ->  v[n] = entry n      (FWD: after the forward transpose)
+// v[i] = entry column_of(i)  ->  v[n] = entry n      (!FWD: after the inverse transpose)
+template <class R, bool FWD>
+B2_HD void tr_unpermute(RRegs<R>& r) {
+    constexpr int W = R::W;
+    float2 t[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        if (FWD) t[i] = r.v[column_of<W>(i)];
+        else     t[column_of<W>(i)] = r.v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) r.v[i] = t[i];
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// P3a: column from X (the forward column FFT follows)  -> r.v[ky] = Z(ky, col)
-// ------------------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+// Device-side transposes for one thread.  Block b of X is read by warp b.  The warp-dependent branches only swap the
+// order of the two halves; the CTA barriers sit outside them.
 template <class R>
-B2_HD void rows_p3a(RSmem<R>& s, RRegs<R>& r, int tid) {
-    constexpr int W = R::W;
-    const int c = column_of<W>(tid);
-#pragma unroll
-    for (int y = 0; y < W; ++y) r.v[y] = s.X[y * R::P + c];
+__device__ __forceinline__ void transpose_fwd_device(RSmem<R>& s, RRegs<R>& r, int tid, bool active) {
+    const int lane = tid & 31, wq = tid >> 5;
+    if constexpr (R::NWARP == 2) {
+        if (active) { if (wq == 0) tr_fwd_store_set<R, 1>(s.X[1], r, lane); else tr_fwd_store_set<R, 0>(s.X[0], r, lane); }
+        __syncthreads();
+        if (wq == 0) {
+            if (active) tr_fwd_load_set<R, 1>(s.X[0], r, lane);      // rows 32..63 of my column
+            __syncwarp();
+            if (active) tr_fwd_store_set<R, 0>(s.X[0], r, lane);
+            __syncwarp();
+            if (active) tr_fwd_load_set<R, 0>(s.X[0], r, lane);      // rows 0..31
+        } else {
+            if (active) tr_fwd_load_set<R, 0>(s.X[1], r, lane);      // rows 0..31 of my column
+            __syncwarp();
+            if (active) tr_fwd_store_set<R, 1>(s.X[1], r, lane);
+            __syncwarp();
+            if (active) tr_fwd_load_set<R, 1>(s.X[1], r, lane);      // rows 32..63
+        }
+    } else {
+        if (active) tr_fwd_store_set<R, 0>(s.X[0], r, lane);
+        __syncwarp();
+        if (active) tr_fwd_load_set<R, 0>(s.X[0], r, lane);
+    }
+    if (active) tr_unpermute<R, true>(r);
 }
+template <class R>
+__device__ __forceinline__ void transpose_inv_device(RSmem<R>& s, RRegs<R>& r, int tid, bool active) {
+    const int lane = tid & 31, wq = tid >> 5;
+    if constexpr (R::NWARP == 2) {
+        __syncthreads();  // the other warp may still be reading its block (forward transpose)
+        if (active) { if (wq == 0) tr_inv_store_half<R, 1>(s.X[1], r, lane); else tr_inv_store_half<R, 0>(s.X[0], r, lane); }
+        __syncthreads();
+        if (wq == 0) {
+            if (active) tr_inv_load_half<R, 1>(s.X[0], r, lane);     // my row at the columns of warp 1
+            __syncwarp();
+            if (active) tr_inv_store_half<R, 0>(s.X[0], r, lane);
+            __syncwarp();
+            if (active) tr_inv_load_half<R, 0>(s.X[0], r, lane);
+        } else {
+            if (active) tr_inv_load_half<R, 0>(s.X[1], r, lane);     // my row at the columns of warp 0
+            __syncwarp();
+            if (active) tr_inv_store_half<R, 1>(s.X[1], r, lane);
+            __syncwarp();
+            if (active) tr_inv_load_half<R, 1>(s.X[1], r, lane);
+        }
+    } else {
+        __syncwarp();
+        if (active) tr_inv_store_half<R, 0>(s.X[0], r, lane);
+        __syncwarp();
+        if (active) tr_inv_load_half<R, 0>(s.X[0], r, lane);
+    }
+    if (active) tr_unpermute<R, false>(r);
+}
+#endif
 
 // First frame of a run: park the scaled spectra only.
 //   A0 = (z + conj zn) * (0.5/std0),  A1 = -i (z - conj zn) * (0.5/std1),  parked value = A / N^2
@@ -313,20 +411,6 @@ __device__ __forceinline__ void rows_p3b_device(RSmem<R>& s, RRegs<R>& r, int ti
 // P4: (forward FFT of conj G along columns, then) store column into X.
 // P5: row from X, (forward FFT along the row, then) conjugate, clip, per-row max / sum.
 // ------------------------------------------------------------------------------------------------------------
-template <class R>
-B2_HD void rows_p4_post(RSmem<R>& s, RRegs<R>& r, int tid) {
-    constexpr int W = R::W;
-    const int c = column_of<W>(tid);
-#pragma unroll
-    for (int y = 0; y < W; ++y) s.X[y * R::P + c] = r.v[y];
-}
-
-template <class R>
-B2_HD void rows_p5_pre(RSmem<R>& s, RRegs<R>& r, int tid) {
-#pragma unroll
-    for (int x = 0; x < R::W; ++x) r.v[x] = s.X[tid * R::P + x];
-}
-
 // r.v holds FFT2(conj G) = conj(planes): plane 0 = Re, plane 1 = -Im.
 template <class R>
 B2_HD void rows_p5_post(RSmem<R>& s, RRegs<R>& r, int tid, bool dead0, bool dead1) {
@@ -403,12 +487,12 @@ B2_HD void rows_p6(RSmem<R>& s, RRegs<R>& r, int tid) {
     }
 }
 
-// P7: peak position known; the three rows around each peak are dumped (into X, free by now) for the Gaussian fit.
+// P7: peak position known; the three rows around each peak are dumped for the Gaussian fit.
 template <class R>
 B2_HD void rows_p7(RSmem<R>& s, RRegs<R>& r, int tid) {
     constexpr int W = R::W;
     const int si = (tid + W / 2) % W;
-    float* nb = reinterpret_cast<float*>(s.X);   // [w][3][W]
+    float* nb = &s.nb[0][0][0];   // [w][3][W]
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
         unsigned long long key = ~0ull;
@@ -431,7 +515,7 @@ B2_HD void rows_p8(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p, const RU
     if (tid >= 2) return;
     const int w = tid;
     if (w == 1 && !un.valid1) return;
-    const float* nb = reinterpret_cast<const float*>(s.X) + w * 3 * W;
+    const float* nb = &s.nb[0][0][0] + w * 3 * W;
     // selects, not r.x[w]: a dynamic index would demote the whole register struct to local memory
     const int pi = w == 0 ? r.pi[0] : r.pi[1], pj = w == 0 ? r.pj[0] : r.pj[1];
     const float cmax = w == 0 ? r.cmaxv[0] : r.cmaxv[1];

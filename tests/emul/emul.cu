@@ -67,6 +67,31 @@ extern "C" int b2piv_emul_pairs(const void* frames, int n_frames, int H, int W, 
 
 
 // ---- row-per-thread kernel (piv_rows.cuh): lock-step emulation of the W threads of one group ---------------------
+// lock-step emulation of transpose_fwd_device / transpose_inv_device (sub-phases separated where the device has a
+// CTA barrier or a __syncwarp)
+template <class R, bool FWD>
+static void emul_transpose(RSmem<R>& s, std::vector<RRegs<R>>& regs) {
+    constexpr int W = R::W;
+    // op(t, set_or_half, block): store / load
+    auto store = [&](int t, int k, int blk) {
+        const int lane = t & 31;
+        if (FWD) { if (k == 0) tr_fwd_store_set<R, 0>(s.X[blk], regs[t], lane); else tr_fwd_store_set<R, (R::NWARP == 2 ? 1 : 0)>(s.X[blk], regs[t], lane); }
+        else     { if (k == 0) tr_inv_store_half<R, 0>(s.X[blk], regs[t], lane); else tr_inv_store_half<R, (R::NWARP == 2 ? 1 : 0)>(s.X[blk], regs[t], lane); }
+    };
+    auto load = [&](int t, int k, int blk) {
+        const int lane = t & 31;
+        if (FWD) { if (k == 0) tr_fwd_load_set<R, 0>(s.X[blk], regs[t], lane); else tr_fwd_load_set<R, (R::NWARP == 2 ? 1 : 0)>(s.X[blk], regs[t], lane); }
+        else     { if (k == 0) tr_inv_load_half<R, 0>(s.X[blk], regs[t], lane); else tr_inv_load_half<R, (R::NWARP == 2 ? 1 : 0)>(s.X[blk], regs[t], lane); }
+    };
+    if (R::NWARP == 2) {
+        for (int t = 0; t < W; ++t) { const int wq = t >> 5; store(t, 1 - wq, 1 - wq); }   // other warp's set -> its block
+        for (int t = 0; t < W; ++t) { const int wq = t >> 5; load(t, 1 - wq, wq); }        // from my block
+    }
+    for (int t = 0; t < W; ++t) { const int wq = t >> 5; store(t, wq, wq); }
+    for (int t = 0; t < W; ++t) { const int wq = t >> 5; load(t, wq, wq); }
+    for (int t = 0; t < W; ++t) tr_unpermute<R, FWD>(regs[t]);
+}
+
 template <class R>
 static int run_rows(RParams p) {
     constexpr int W = R::W;
@@ -81,12 +106,13 @@ static int run_rows(RParams p) {
             for (int w = 0; w < 2; ++w)
                 for (int row = 0; row < W; ++row)
                     for (int j = 0; j < W / 16; ++j)
-                        memcpy(s.tile + tile_chunk_offset<W>(w, row, j),
+                        memcpy(s.tile() + tile_chunk_offset<W>(w, row, j),
                                p.frames + (long long)f * p.frame_stride + (long long)(un.y0[w] + row) * p.pitch + un.x0[w] + 16 * j, 16);
             memset(s.red, 0, sizeof(s.red));
             for (int t = 0; t < W; ++t) rows_p1<R>(s, regs[t], t);
-            for (int t = 0; t < W; ++t) { rows_p2_pre<R>(s, regs[t], t, p.clip_norm); fft_reg<W, 0>(regs[t].v); rows_p2_post<R>(s, regs[t], t); }
-            for (int t = 0; t < W; ++t) { rows_p3a<R>(s, regs[t], t); fft_reg<W, 0>(regs[t].v); }
+            for (int t = 0; t < W; ++t) { rows_p2_pre<R>(s, regs[t], t, p.clip_norm); fft_reg<W, 0>(regs[t].v); }
+            emul_transpose<R, true>(s, regs);
+            for (int t = 0; t < W; ++t) fft_reg<W, 0>(regs[t].v);
             snap = regs;
             for (int ky = 0; ky <= W / 2; ++ky) {
                 for (int t = 0; t < W; ++t) {
@@ -104,12 +130,14 @@ static int run_rows(RParams p) {
                 }
             }
             if (have_prev) {
-                for (int t = 0; t < W; ++t) { fft_reg<W, 0>(regs[t].v); rows_p4_post<R>(s, regs[t], t); }
+                for (int t = 0; t < W; ++t) fft_reg<W, 0>(regs[t].v);
+                emul_transpose<R, false>(s, regs);
                 for (int k = 0; k < R::NWARP; ++k) for (int q = 4; q < 8; ++q) s.red[k][q] = 0;
                 for (int t = 0; t < W; ++t) {
                     const bool d0 = regs[t].half_alpha_prev[0] == 0.f || regs[t].half_alpha_new[0] == 0.f;
                     const bool d1 = regs[t].half_alpha_prev[1] == 0.f || regs[t].half_alpha_new[1] == 0.f;
-                    rows_p5_pre<R>(s, regs[t], t); fft_reg<W, 0>(regs[t].v); rows_p5_post<R>(s, regs[t], t, d0, d1);
+                    fft_reg<W, 0>(regs[t].v);
+                    rows_p5_post<R>(s, regs[t], t, d0, d1);
                 }
                 for (int k = 0; k < R::NWARP; ++k) s.redk[k][0] = s.redk[k][1] = ~0ull;
                 for (int t = 0; t < W; ++t) rows_p6<R>(s, regs[t], t);

@@ -83,10 +83,14 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 
-// G groups of W threads share one CTA and run in LOCKSTEP (CTA-wide barriers): the loop body is ~180 KB of
-// straight-line code, far beyond the instruction caches, so all warps of an SM must stream the SAME instructions
-// (ncu on the one-group-per-CTA version: 30 % of issue slots lost to `no_instructions`).
-template <class R, int G>
+// G groups of W threads share one CTA and run in LOCKSTEP (CTA-wide barriers): the loop body is >100 KB of
+// straight-line code, far beyond the instruction caches, so the warps of an SM should stream the SAME instructions
+// (ncu on a one-group-per-CTA version: 30 % of issue slots lost to `no_instructions`).
+// ROLLED: the four 1-D FFT passes of a frame share one copy of the unrolled FFT (smaller code, but the register
+// layout must be canonical at the loop head, which costs MOVs); otherwise four specialised copies.
+// Compute phases run unconditionally (an inactive group - only at the tail of the grid - works on garbage and never
+// stores results); only TMA traffic and global stores are predicated, so no shuffle sits in a divergent region.
+template <class R, int G, bool ROLLED>
 __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constant__ CUtensorMap tmap, RParams p) {
     extern __shared__ unsigned char smem_dyn[];
     // the swizzled TMA tiles need 1024-byte aligned bases: align by hand (launch adds 1 KB of slack)
@@ -102,6 +106,7 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
     __syncthreads();
     uint32_t parity = 0;
     RRegs<R> r;
+    r.half_alpha_prev[0] = r.half_alpha_prev[1] = 0.f;
     for (long long ubase = (long long)blockIdx.x * G; ubase < p.n_units; ubase += (long long)gridDim.x * G) {
         int maxn = 0;  // frames of the longest unit of this round (uniform over the CTA)
 #pragma unroll
@@ -124,35 +129,36 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
             const bool active = k < nfr;
             const bool have_prev = k > 0;
             const int f = un.f0 + k;
-            const int n_stage = have_prev ? 4 : 2;
-            // Four 1-D FFT passes per frame (rows, columns, columns, rows) share ONE copy of the unrolled W-point
-            // FFT: the inverse passes run the forward code on conj(G) (IFFT(G) = conj(FFT(conj G))).  Keeping the
-            // stage loop rolled cuts the loop body from ~170 KB to ~110 KB of instructions.
+            if (active) {
+                while (!mbar_try_wait(&s.mbar, parity)) {}
+                parity ^= 1u;
+            }
+            rows_p1<R>(s, r, tid);
+            __syncthreads();  // A: integer moments visible, tile (aliased on X) fully consumed
+            rows_p2_pre<R>(s, r, tid, p.clip_norm);
+            // The first frame of a unit has no previous spectra: it still runs the whole pipeline (on whatever the
+            // park buffer holds) and simply stores no result - one wasted inverse transform per ~26 frames buys a loop
+            // body without data-dependent branches, so no shuffle needs convergence bookkeeping.
+            if (ROLLED) {
 #pragma unroll 1
-            for (int st = 0; st < n_stage; ++st) {
-                if (st == 0) {
-                    if (active) {
-                        while (!mbar_try_wait(&s.mbar, parity)) {}
-                        parity ^= 1u;
-                        rows_p1<R>(s, r, tid);
-                    }
-                    __syncthreads();  // A: integer moments visible, tile (aliased on X) fully consumed
-                    if (active) rows_p2_pre<R>(s, r, tid, p.clip_norm);
-                } else if (st == 3) {
-                    transpose_inv_device<R>(s, r, tid, active);   // columns -> rows
+                for (int st = 0; st < 4; ++st) {
+                    if (st == 3) transpose_inv_device<R>(s, r, tid, true);      // columns -> rows
+                    fft_reg<W, 0>(r.v);
+                    if (st == 0) transpose_fwd_device<R>(s, r, tid, true);      // row spectra -> columns
+                    else if (st == 1) rows_p3b_device<R>(s, r, tid, true);
                 }
-                if (active) fft_reg<W, 0>(r.v);
-                if (st == 0) {
-                    transpose_fwd_device<R>(s, r, tid, active);   // row spectra -> columns
-                } else if (st == 1) {
-                    if (active) rows_p3b_device<R>(s, r, tid, have_prev);
-                }
+            } else {
+                fft_reg<W, 0>(r.v);
+                transpose_fwd_device<R>(s, r, tid, true);
+                fft_reg<W, 0>(r.v);
+                rows_p3b_device<R>(s, r, tid, true);
+                fft_reg<W, 0>(r.v);
+                transpose_inv_device<R>(s, r, tid, true);
+                fft_reg<W, 0>(r.v);
             }
-            if (have_prev) {
-                const bool dead0 = (r.half_alpha_prev[0] == 0.f) || (r.half_alpha_new[0] == 0.f);
-                const bool dead1 = (r.half_alpha_prev[1] == 0.f) || (r.half_alpha_new[1] == 0.f);
-                if (active) rows_p5_post<R>(s, r, tid, dead0, dead1);
-            }
+            const bool dead0 = (r.half_alpha_prev[0] == 0.f) || (r.half_alpha_new[0] == 0.f);
+            const bool dead1 = (r.half_alpha_prev[1] == 0.f) || (r.half_alpha_new[1] == 0.f);
+            rows_p5_post<R>(s, r, tid, dead0, dead1);
             __syncthreads();  // E1: block max / sum; X (and the tile aliased on it) is free again
             if (active && tid == 0 && k + 1 < nfr) {
                 fence_proxy_async();
@@ -160,16 +166,12 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
                 tma_load_3d(s.tile(), &tmap, &s.mbar, un.x0[0], un.y0[0], f + 1);
                 tma_load_3d(s.tile() + W * W, &tmap, &s.mbar, un.x0[1], un.y0[1], f + 1);
             }
-            if (have_prev) {
-                if (active) rows_p6<R>(s, r, tid);
-                __syncthreads();  // E2: first-argmax key
-                if (active) {
-                    rows_dump_planes<R>(r, tid, p, un, f - 1);
-                    rows_p7<R>(s, r, tid);
-                }
-                __syncthreads();  // F: neighbour rows dumped
-                if (active) rows_p8<R>(s, r, tid, p, un, f - 1);
-            }
+            rows_p6<R>(s, r, tid);
+            __syncthreads();  // E2: first-argmax key
+            if (active && have_prev) rows_dump_planes<R>(r, tid, p, un, f - 1);
+            rows_p7<R>(s, r, tid);
+            __syncthreads();  // F: neighbour rows dumped
+            if (active && have_prev) rows_p8<R>(s, r, tid, p, un, f - 1);
             r.half_alpha_prev[0] = r.half_alpha_new[0];
             r.half_alpha_prev[1] = r.half_alpha_new[1];
         }
@@ -408,6 +410,7 @@ struct b2piv_engine {
                         // ineligible), 3: direct any-size kernel
     int run_len = 0;    // frame pairs per work unit of the rows kernel (0: auto)
     int groups = 0;     // window-pair groups per CTA of the rows kernel (0: default)
+    int rolled = 0;     // rows kernel: 1 = one shared FFT body (rolled stage loop), 0 = four specialised copies
     int last_variant = 0;
     float gauss_eps = 1e-7f;
     // plan
@@ -575,7 +578,7 @@ static bool rows_eligible(const b2piv_engine* e, const void* d_frames, long long
     return get_encode_tiled() != nullptr;
 }
 
-template <class R, int G>
+template <class R, int G, bool ROLLED>
 static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st) {
     constexpr int W = R::W;
     const int n_frames = gp.n_pairs + 1;
@@ -595,7 +598,7 @@ static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st) {
     p.clip_norm = gp.clip_norm; p.border_nan = gp.border_nan; p.gauss_eps = gp.gauss_eps; p.keep = gp.keep;
     p.u = gp.u; p.v = gp.v; p.cmax = gp.cmax; p.s2n = gp.s2n; p.planes = gp.planes;
     const size_t smem = sizeof(RSmem<R>) * G + 1024;
-    auto kern = piv_rows_kernel<R, G>;
+    auto kern = piv_rows_kernel<R, G, ROLLED>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, R::NT * G, smem));
@@ -628,15 +631,16 @@ static int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
         return fail(e, B2PIV_ERR_UNSUPPORTED, "rows kernel needs uint8 frames, a square 32/64 window, 16-byte aligned base/pitch and an x stride that is a multiple of 16");
     if (can_rows && e->variant != 1) {
         e->last_variant = 2;
-        // groups per CTA (lockstep width): 64x64 -> 4 groups = 8 warps per SM, 32x32 -> 12 groups = 12 warps per SM
+        // groups per CTA (lockstep width) and rolled / unrolled stage loop
+        const bool rolled = e->rolled != 0;
         if (e->wy == 64) {
-            if (e->groups == 1) return launch_rows<RCfg<64>, 1>(e, p, st);
-            if (e->groups == 2) return launch_rows<RCfg<64>, 2>(e, p, st);
-            return launch_rows<RCfg<64>, 4>(e, p, st);
+            if (e->groups == 1) return rolled ? launch_rows<RCfg<64>, 1, true>(e, p, st) : launch_rows<RCfg<64>, 1, false>(e, p, st);
+            if (e->groups == 2) return rolled ? launch_rows<RCfg<64>, 2, true>(e, p, st) : launch_rows<RCfg<64>, 2, false>(e, p, st);
+            return rolled ? launch_rows<RCfg<64>, 4, true>(e, p, st) : launch_rows<RCfg<64>, 4, false>(e, p, st);
         }
-        if (e->groups == 1) return launch_rows<RCfg<32>, 1>(e, p, st);
-        if (e->groups == 2 || e->groups == 4) return launch_rows<RCfg<32>, 4>(e, p, st);
-        return launch_rows<RCfg<32>, 12>(e, p, st);
+        if (e->groups == 1) return rolled ? launch_rows<RCfg<32>, 1, true>(e, p, st) : launch_rows<RCfg<32>, 1, false>(e, p, st);
+        if (e->groups == 12) return rolled ? launch_rows<RCfg<32>, 12, true>(e, p, st) : launch_rows<RCfg<32>, 12, false>(e, p, st);
+        return rolled ? launch_rows<RCfg<32>, 4, true>(e, p, st) : launch_rows<RCfg<32>, 4, false>(e, p, st);
     }
     if (!fft_config(e->wy, e->wx) || (e->variant == 3 && e->wy <= 64 && e->wx <= 64)) {
         e->last_variant = 3;
@@ -743,6 +747,7 @@ int b2piv_set_option(b2piv_engine* e, const char* name, double value) {
     else if (n == "kernel_variant") e->variant = (int)value;
     else if (n == "run_len") e->run_len = value < 0 ? 0 : (int)value;
     else if (n == "groups") e->groups = value < 0 ? 0 : (int)value;
+    else if (n == "rolled") e->rolled = value != 0.0;
     else return fail(e, B2PIV_ERR_ARG, "unknown option " + n);
     return B2PIV_OK;
 }

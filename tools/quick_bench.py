@@ -5,12 +5,13 @@ import numpy as np, torch
 from pyorc_b200.engine import Engine
 from pyorc_b200 import synth
 
-def run(H, W, ws, ov, n_frames, reps=5, dtype="uint8", variant=0, run_len=0, groups=0):
+def run(H, W, ws, ov, n_frames, reps=5, dtype="uint8", variant=0, run_len=0, groups=0, rolled=0):
     dev = torch.device("cuda", 0)
     e = Engine(0)
     e.set_option("kernel_variant", variant)
     e.set_option("run_len", run_len)
     e.set_option("groups", groups)
+    e.set_option("rolled", rolled)
     fr = synth.particle_frames_torch(n_frames, H, W, dev, dtype=dtype)
     torch.cuda.synchronize()
     for _ in range(3):
@@ -24,22 +25,25 @@ def run(H, W, ws, ov, n_frames, reps=5, dtype="uint8", variant=0, run_len=0, gro
     nr, nc = out[0].shape[1:]
     nwin = (n_frames - 1) * nr * nc
     t = float(np.median(ts))
-    print(f"variant {variant} run_len {run_len} groups {groups} {H}x{W} win {ws} ov {ov} {dtype}: {nwin} windows in {t:.3f} ms -> {nwin / t / 1e3:.2f} Mwin/s  (u mean {float(torch.nanmean(out[0])):.3f} v mean {float(torch.nanmean(out[1])):.3f})", flush=True)
+    print(f"variant {variant} run_len {run_len} groups {groups} rolled {rolled} {H}x{W} win {ws} ov {ov} {dtype}: {nwin} windows in {t:.3f} ms -> {nwin / t / 1e3:.2f} Mwin/s  (u mean {float(torch.nanmean(out[0])):.3f} v mean {float(torch.nanmean(out[1])):.3f})", flush=True)
     e.close()
 
 if __name__ == "__main__":
     if "--single" in sys.argv:
-        run(1080, 1920, (64, 64), (32, 32), 21, reps=2, variant=int(os.environ.get("B2_VARIANT", "0")), groups=int(os.environ.get("B2_GROUPS", "0")))
+        run(1080, 1920, (64, 64), (32, 32), 21, reps=2, variant=int(os.environ.get("B2_VARIANT", "0")), groups=int(os.environ.get("B2_GROUPS", "0")), rolled=int(os.environ.get("B2_ROLLED", "0")))
         sys.exit(0)
     if "--variants" in sys.argv:
         run(1080, 1920, (64, 64), (32, 32), 101, variant=1)
-        for g in (1, 2, 4):
-            for rl in (0, 25):
-                run(1080, 1920, (64, 64), (32, 32), 101, variant=2, run_len=rl, groups=g)
+        for rolled in (0, 1):
+            for g in (1, 2, 4):
+                run(1080, 1920, (64, 64), (32, 32), 101, variant=2, groups=g, rolled=rolled)
+        run(1080, 1920, (64, 64), (32, 32), 101, variant=2, groups=4, rolled=0, run_len=50)
+        run(1080, 1920, (64, 64), (32, 32), 101, variant=2, groups=1, rolled=0, run_len=50)
         run(2160, 3840, (64, 64), (32, 32), 41, variant=2)
         run(1080, 1920, (32, 32), (16, 16), 41, variant=1)
-        for g in (1, 4, 12):
-            run(1080, 1920, (32, 32), (16, 16), 41, variant=2, groups=g)
+        for rolled in (0, 1):
+            for g in (1, 4, 12):
+                run(1080, 1920, (32, 32), (16, 16), 41, variant=2, groups=g, rolled=rolled)
         run(1080, 1920, (32, 32), (24, 24), 11, variant=0)
         run(1080, 1920, (10, 10), (5, 5), 5, variant=0)
         run(1080, 1920, (26, 26), (12, 12), 5, variant=0)

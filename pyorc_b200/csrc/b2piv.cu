@@ -631,12 +631,14 @@ static int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
         return fail(e, B2PIV_ERR_UNSUPPORTED, "rows kernel needs uint8 frames, a square 32/64 window, 16-byte aligned base/pitch and an x stride that is a multiple of 16");
     if (can_rows && e->variant != 1) {
         e->last_variant = 2;
-        // groups per CTA (lockstep width) and rolled / unrolled stage loop
+        // groups per CTA (lockstep width) and rolled / unrolled stage loop.  Measured on B200 (profiles/r01): 64x64 is
+        // fastest with one group per CTA (four 64-thread CTAs per SM) and four specialised FFT copies, 32x32 with four
+        // single-warp groups per CTA.
         const bool rolled = e->rolled != 0;
         if (e->wy == 64) {
-            if (e->groups == 1) return rolled ? launch_rows<RCfg<64>, 1, true>(e, p, st) : launch_rows<RCfg<64>, 1, false>(e, p, st);
+            if (e->groups == 4) return rolled ? launch_rows<RCfg<64>, 4, true>(e, p, st) : launch_rows<RCfg<64>, 4, false>(e, p, st);
             if (e->groups == 2) return rolled ? launch_rows<RCfg<64>, 2, true>(e, p, st) : launch_rows<RCfg<64>, 2, false>(e, p, st);
-            return rolled ? launch_rows<RCfg<64>, 4, true>(e, p, st) : launch_rows<RCfg<64>, 4, false>(e, p, st);
+            return rolled ? launch_rows<RCfg<64>, 1, true>(e, p, st) : launch_rows<RCfg<64>, 1, false>(e, p, st);
         }
         if (e->groups == 1) return rolled ? launch_rows<RCfg<32>, 1, true>(e, p, st) : launch_rows<RCfg<32>, 1, false>(e, p, st);
         if (e->groups == 12) return rolled ? launch_rows<RCfg<32>, 12, true>(e, p, st) : launch_rows<RCfg<32>, 12, false>(e, p, st);

@@ -186,8 +186,9 @@ def test_device_resident_path(engine):
 
 def test_errors(engine):
     imgs = synth.particle_frames(2, 100, 100, dtype=np.uint8)
+    big = synth.particle_frames(2, 200, 200, dtype=np.uint8)
     with pytest.raises(NotImplementedError):
-        engine.pairs(imgs, (48, 48), (24, 24))
+        engine.pairs(big, (96, 96), (48, 48))          # > 64 and not one of the compiled FFT shapes
     with pytest.raises(ValueError):
         engine.pairs(imgs[:1], (64, 64), (32, 32))
     with pytest.raises(ValueError):

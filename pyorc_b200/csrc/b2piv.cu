@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(C::NT) piv_pairs_kernel(Params p, const float2
         phase_stats<C>(s, tid, p);               __syncthreads();
         phase_center<C>(s, tid, p);              __syncthreads();
         phase_stats_f32<C>(s, tid, p);
+        if (p.ny * p.nx != C::NPX) { phase_embed<C>(s, tid, p); __syncthreads(); }
         fft_pass<C, C::NWIN, 0, 0, 0>(s, tid);   __syncthreads();
         fft_pass<C, C::NWIN, 0, 1, 0>(s, tid);   __syncthreads();
         fft_pass<C, C::NWIN, 1, 0, 0>(s, tid);   __syncthreads();
@@ -86,11 +87,11 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 // G groups of W threads share one CTA and run in LOCKSTEP (CTA-wide barriers): the loop body is >100 KB of
 // straight-line code, far beyond the instruction caches, so the warps of an SM should stream the SAME instructions
 // (ncu on a one-group-per-CTA version: 30 % of issue slots lost to `no_instructions`).
-// ROLLED: the four 1-D FFT passes of a frame share one copy of the unrolled FFT (smaller code, but the register
-// layout must be canonical at the loop head, which costs MOVs); otherwise four specialised copies.
+// ROLLED: the four 1-D FFT passes of a frame share one copy of the unrolled FFT; otherwise two copies (one
+// "FFT, transpose, FFT" block executed twice).
 // Compute phases run unconditionally (an inactive group - only at the tail of the grid - works on garbage and never
 // stores results); only TMA traffic and global stores are predicated, so no shuffle sits in a divergent region.
-template <class R, int G, bool ROLLED>
+template <class R, int G, bool ROLLED, bool ALIGNED>
 __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constant__ CUtensorMap tmap, RParams p) {
     extern __shared__ unsigned char smem_dyn[];
     // the swizzled TMA tiles need 1024-byte aligned bases: align by hand (launch adds 1 KB of slack)
@@ -119,11 +120,15 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
         const bool has_unit = (ubase + g) < p.n_units;
         const RUnit un = decode_unit(p, has_unit ? (int)(ubase + g) : 0);
         const int nfr = has_unit ? un.f1 - un.f0 + 1 : 0;
+        constexpr int TILE_BYTES = ALIGNED ? R::TILE : R::TILE_U;
+        constexpr int WIN_BYTES = TILE_BYTES / 2;
+        const int xa0 = ALIGNED ? un.x0[0] : (un.x0[0] & ~15), xa1 = ALIGNED ? un.x0[1] : (un.x0[1] & ~15);
+        const int xoff0 = un.x0[0] - xa0, xoff1 = un.x0[1] - xa1;
         if (has_unit && tid == 0) {
             fence_proxy_async();
-            mbar_expect_tx(&s.mbar, R::TILE);
-            tma_load_3d(s.tile(), &tmap, &s.mbar, un.x0[0], un.y0[0], un.f0);
-            tma_load_3d(s.tile() + W * W, &tmap, &s.mbar, un.x0[1], un.y0[1], un.f0);
+            mbar_expect_tx(&s.mbar, TILE_BYTES);
+            tma_load_3d(s.tile(), &tmap, &s.mbar, xa0, un.y0[0], un.f0);
+            tma_load_3d(s.tile() + WIN_BYTES, &tmap, &s.mbar, xa1, un.y0[1], un.f0);
         }
         for (int k = 0; k < maxn; ++k) {
             const bool active = k < nfr;
@@ -133,28 +138,29 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
                 while (!mbar_try_wait(&s.mbar, parity)) {}
                 parity ^= 1u;
             }
-            rows_p1<R>(s, r, tid);
+            rows_p1<R, ALIGNED>(s, r, tid, xoff0, xoff1);
             __syncthreads();  // A: integer moments visible, tile (aliased on X) fully consumed
             rows_p2_pre<R>(s, r, tid, p.clip_norm);
             // The first frame of a unit has no previous spectra: it still runs the whole pipeline (on whatever the
             // park buffer holds) and simply stores no result - one wasted inverse transform per ~26 frames buys a loop
             // body without data-dependent branches, so no shuffle needs convergence bookkeeping.
+            // FFT(rows) T FFT(cols) | cross | FFT(cols) T FFT(rows): the transpose T is its own inverse and leaves the
+            // registers in natural order, so the sequence is two identical halves (or four identical FFTs).
             if (ROLLED) {
 #pragma unroll 1
                 for (int st = 0; st < 4; ++st) {
-                    if (st == 3) transpose_inv_device<R>(s, r, tid, true);      // columns -> rows
                     fft_reg<W, 0>(r.v);
-                    if (st == 0) transpose_fwd_device<R>(s, r, tid, true);      // row spectra -> columns
+                    if ((st & 1) == 0) transpose_device<R>(s, r, tid, st != 0);
                     else if (st == 1) rows_p3b_device<R>(s, r, tid, true);
                 }
             } else {
-                fft_reg<W, 0>(r.v);
-                transpose_fwd_device<R>(s, r, tid, true);
-                fft_reg<W, 0>(r.v);
-                rows_p3b_device<R>(s, r, tid, true);
-                fft_reg<W, 0>(r.v);
-                transpose_inv_device<R>(s, r, tid, true);
-                fft_reg<W, 0>(r.v);
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    fft_reg<W, 0>(r.v);
+                    transpose_device<R>(s, r, tid, half != 0);
+                    fft_reg<W, 0>(r.v);
+                    if (half == 0) rows_p3b_device<R>(s, r, tid, true);
+                }
             }
             const bool dead0 = (r.half_alpha_prev[0] == 0.f) || (r.half_alpha_new[0] == 0.f);
             const bool dead1 = (r.half_alpha_prev[1] == 0.f) || (r.half_alpha_new[1] == 0.f);
@@ -162,9 +168,9 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
             __syncthreads();  // E1: block max / sum; X (and the tile aliased on it) is free again
             if (active && tid == 0 && k + 1 < nfr) {
                 fence_proxy_async();
-                mbar_expect_tx(&s.mbar, R::TILE);
-                tma_load_3d(s.tile(), &tmap, &s.mbar, un.x0[0], un.y0[0], f + 1);
-                tma_load_3d(s.tile() + W * W, &tmap, &s.mbar, un.x0[1], un.y0[1], f + 1);
+                mbar_expect_tx(&s.mbar, TILE_BYTES);
+                tma_load_3d(s.tile(), &tmap, &s.mbar, xa0, un.y0[0], f + 1);
+                tma_load_3d(s.tile() + WIN_BYTES, &tmap, &s.mbar, xa1, un.y0[1], f + 1);
             }
             rows_p6<R>(s, r, tid);
             __syncthreads();  // E2: first-argmax key
@@ -214,6 +220,7 @@ __global__ void __launch_bounds__(C::NT) piv_ens_kernel(Params p, EnsParams ep, 
             phase_stats<C>(s, tid, p);               __syncthreads();
             phase_center<C>(s, tid, p);              __syncthreads();
             phase_stats_f32<C>(s, tid, p);
+            if (p.ny * p.nx != C::NPX) { phase_embed<C>(s, tid, p); __syncthreads(); }
             fft_pass<C, C::NWIN, 0, 0, 0>(s, tid);   __syncthreads();
             fft_pass<C, C::NWIN, 0, 1, 0>(s, tid);   __syncthreads();
             fft_pass<C, C::NWIN, 1, 0, 0>(s, tid);   __syncthreads();
@@ -229,14 +236,14 @@ __global__ void __launch_bounds__(C::NT) piv_ens_kernel(Params p, EnsParams ep, 
                 if (w == 1 && !it.valid1) continue;
                 const unsigned long long key = total_max_u64<C>(s, 2 * w + 0);
                 float cmax = __uint_as_float((unsigned)(key >> 32));
-                float s2n = cmax / (total_sum_f32<C>(s, 2 * w + 1) / (float)C::NPX);
+                float s2n = cmax / (total_sum_f32<C>(s, 2 * w + 1) / (float)(p.ny * p.nx));
                 bool ok = (cmax >= ep.corr_min) && (s2n >= ep.s2n_min) && isfinite(cmax) && (s.scale[w] != 0.f);
                 if (p.keep && !p.keep[it.w[w]]) ok = false;   // NaN plane in the reference -> masked out
                 if (ok) {
 #pragma unroll
                     for (int k = 0; k < EPT; ++k) {
                         const int e = tid + k * C::NT;
-                        acc[w][k] += shifted_value<C>(s, w, e / C::WX, e % C::WX);
+                        if (e < p.ny * p.nx) acc[w][k] += shifted_value<C>(s, w, e / p.nx, e % p.nx, p.ny, p.nx);
                     }
                     if (cmax > 1e-6f) cnt[w] += 1.f;
                 } else {
@@ -252,9 +259,10 @@ __global__ void __launch_bounds__(C::NT) piv_ens_kernel(Params p, EnsParams ep, 
 #pragma unroll
         for (int w = 0; w < C::NWIN; ++w) {
             if (w == 1 && !it.valid1) continue;
-            float* dst = ep.plane_sum + (long long)it.w[w] * C::NPX;
+            float* dst = ep.plane_sum + (long long)it.w[w] * (p.ny * p.nx);
 #pragma unroll
-            for (int k = 0; k < EPT; ++k) dst[tid + k * C::NT] += acc[w][k];
+            for (int k = 0; k < EPT; ++k)
+                if (tid + k * C::NT < p.ny * p.nx) dst[tid + k * C::NT] += acc[w][k];
             if (tid == 0) ep.count[it.w[w]] += cnt[w];
         }
     }
@@ -572,23 +580,24 @@ static PFN_encodeTiled get_encode_tiled() {
 static bool rows_eligible(const b2piv_engine* e, const void* d_frames, long long frame_stride, int pitch) {
     if (e->dtype != B2PIV_U8 || e->wy != e->wx || (e->wy != 64 && e->wy != 32)) return false;
     if ((pitch & 15) || (frame_stride & 15) || (((uintptr_t)d_frames) & 15)) return false;
-    // every TMA box must start on a 16-byte boundary in global memory: the window stride along x has to be a
-    // multiple of 16 pixels (32x32 at 75 % overlap has stride 8 and takes the generic kernel)
-    if ((e->wx - e->ox) & 15) return false;
+    // every TMA box must start on a 16-byte boundary in global memory: x strides that are a multiple of 16 use exact
+    // swizzled boxes, multiples of 4 (32x32 at 75 % overlap: stride 8) a 16-byte wider box read at an offset
+    if ((e->wx - e->ox) & 3) return false;
     return get_encode_tiled() != nullptr;
 }
 
-template <class R, int G, bool ROLLED>
+template <class R, int G, bool ROLLED, bool ALIGNED>
 static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st) {
     constexpr int W = R::W;
     const int n_frames = gp.n_pairs + 1;
     CUtensorMap tmap;
     const cuuint64_t dims[3] = {(cuuint64_t)e->W, (cuuint64_t)e->H, (cuuint64_t)n_frames};
     const cuuint64_t strides[2] = {(cuuint64_t)gp.pitch, (cuuint64_t)gp.frame_stride};
-    const cuuint32_t box[3] = {(cuuint32_t)W, (cuuint32_t)W, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)(ALIGNED ? W : R::WB), (cuuint32_t)W, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult cr = get_encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(gp.frames), dims, strides, box, estr,
-                                           CU_TENSOR_MAP_INTERLEAVE_NONE, W == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                           !ALIGNED ? CU_TENSOR_MAP_SWIZZLE_NONE : (W == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
                                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(e, B2PIV_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)cr));
     RParams p;
@@ -598,7 +607,7 @@ static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st) {
     p.clip_norm = gp.clip_norm; p.border_nan = gp.border_nan; p.gauss_eps = gp.gauss_eps; p.keep = gp.keep;
     p.u = gp.u; p.v = gp.v; p.cmax = gp.cmax; p.s2n = gp.s2n; p.planes = gp.planes;
     const size_t smem = sizeof(RSmem<R>) * G + 1024;
-    auto kern = piv_rows_kernel<R, G, ROLLED>;
+    auto kern = piv_rows_kernel<R, G, ROLLED, ALIGNED>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, R::NT * G, smem));
@@ -624,39 +633,62 @@ static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st) {
     return B2PIV_OK;
 }
 
+// FFT plane for a window size that is not itself a compiled FFT shape: smallest power of two >= 2n per axis (exact
+// circular correlation by padding, piv_core.cuh phase_embed); squared up when the rectangular shape is not compiled.
+static int pad_pow2(int n) { int w = 16; while (w < 2 * n) w <<= 1; return w; }
+static void plane_shape(const b2piv_engine* e, int* py, int* px) {
+    if (fft_config(e->wy, e->wx)) { *py = e->wy; *px = e->wx; return; }
+    int a = pad_pow2(e->wy), b = pad_pow2(e->wx);
+    if (!fft_config(a, b)) a = b = (a > b ? a : b);
+    *py = a; *px = b;
+}
+
 static int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
     if (p.n_pairs <= 0) return B2PIV_OK;
     const bool can_rows = rows_eligible(e, p.frames, p.frame_stride, p.pitch);
     if (e->variant == 2 && !can_rows)
-        return fail(e, B2PIV_ERR_UNSUPPORTED, "rows kernel needs uint8 frames, a square 32/64 window, 16-byte aligned base/pitch and an x stride that is a multiple of 16");
+        return fail(e, B2PIV_ERR_UNSUPPORTED, "rows kernel needs uint8 frames, a square 32/64 window, 16-byte aligned base/pitch and an x stride that is a multiple of 4");
     if (can_rows && e->variant != 1) {
         e->last_variant = 2;
         // groups per CTA (lockstep width) and rolled / unrolled stage loop.  Measured on B200 (profiles/r01): 64x64 is
         // fastest with one group per CTA (four 64-thread CTAs per SM) and four specialised FFT copies, 32x32 with four
         // single-warp groups per CTA.
         const bool rolled = e->rolled != 0;
+        const bool aligned = ((e->wx - e->ox) & 15) == 0;
+#define ROWS_LAUNCH(RC, GG)                                                                                           \
+    return aligned ? (rolled ? launch_rows<RC, GG, true, true>(e, p, st) : launch_rows<RC, GG, false, true>(e, p, st))    \
+                   : (rolled ? launch_rows<RC, GG, true, false>(e, p, st) : launch_rows<RC, GG, false, false>(e, p, st))
         if (e->wy == 64) {
-            if (e->groups == 4) return rolled ? launch_rows<RCfg<64>, 4, true>(e, p, st) : launch_rows<RCfg<64>, 4, false>(e, p, st);
-            if (e->groups == 2) return rolled ? launch_rows<RCfg<64>, 2, true>(e, p, st) : launch_rows<RCfg<64>, 2, false>(e, p, st);
-            return rolled ? launch_rows<RCfg<64>, 1, true>(e, p, st) : launch_rows<RCfg<64>, 1, false>(e, p, st);
+            if (e->groups == 4) { ROWS_LAUNCH(RCfg<64>, 4); }
+            if (e->groups == 2) { ROWS_LAUNCH(RCfg<64>, 2); }
+            ROWS_LAUNCH(RCfg<64>, 1);
         }
-        if (e->groups == 1) return rolled ? launch_rows<RCfg<32>, 1, true>(e, p, st) : launch_rows<RCfg<32>, 1, false>(e, p, st);
-        if (e->groups == 12) return rolled ? launch_rows<RCfg<32>, 12, true>(e, p, st) : launch_rows<RCfg<32>, 12, false>(e, p, st);
-        return rolled ? launch_rows<RCfg<32>, 4, true>(e, p, st) : launch_rows<RCfg<32>, 4, false>(e, p, st);
+        if (e->groups == 1) { ROWS_LAUNCH(RCfg<32>, 1); }
+        if (e->groups == 12) { ROWS_LAUNCH(RCfg<32>, 12); }
+        ROWS_LAUNCH(RCfg<32>, 4);
+#undef ROWS_LAUNCH
     }
-    if (!fft_config(e->wy, e->wx) || (e->variant == 3 && e->wy <= 64 && e->wx <= 64)) {
+    // sizes that are not a compiled FFT shape: tiny windows are cheapest by direct correlation, the rest run padded
+    // through the FFT kernel; variant 3 forces the direct kernel
+    const bool tiny = !fft_config(e->wy, e->wx) && e->wy * e->wx <= 144;
+    if ((e->variant == 3 || tiny) && e->wy <= 64 && e->wx <= 64) {
         e->last_variant = 3;
         return launch_direct(e, p, st);
     }
     e->last_variant = 1;
-#define X(Y, XX, T, NW) if (e->wy == Y && e->wx == XX) return launch_pairs<Cfg<Y, XX, T, NW>>(e, p, st);
+    int py, px;
+    plane_shape(e, &py, &px);
+#define X(Y, XX, T, NW) if (py == Y && px == XX) return launch_pairs<Cfg<Y, XX, T, NW>>(e, p, st);
     B2PIV_CONFIGS(X)
 #undef X
     return fail(e, B2PIV_ERR_UNSUPPORTED, "window size not compiled in");
 }
 static int dispatch_ens(b2piv_engine* e, const Params& p, const EnsParams& ep, cudaStream_t st) {
-    if (!fft_config(e->wy, e->wx) || (e->variant == 3 && e->wy <= 64 && e->wx <= 64)) return launch_direct_ens(e, p, ep, st);
-#define X(Y, XX, T, NW) if (e->wy == Y && e->wx == XX) return launch_ens<Cfg<Y, XX, T, NW>>(e, p, ep, st);
+    const bool tiny = !fft_config(e->wy, e->wx) && e->wy * e->wx <= 144;
+    if ((e->variant == 3 || tiny) && e->wy <= 64 && e->wx <= 64) return launch_direct_ens(e, p, ep, st);
+    int py, px;
+    plane_shape(e, &py, &px);
+#define X(Y, XX, T, NW) if (py == Y && px == XX) return launch_ens<Cfg<Y, XX, T, NW>>(e, p, ep, st);
     B2PIV_CONFIGS(X)
 #undef X
     return fail(e, B2PIV_ERR_UNSUPPORTED, "window size not compiled in");
@@ -667,6 +699,7 @@ static Params base_params(const b2piv_engine* e, const void* d_frames, long long
     memset(&p, 0, sizeof(p));
     p.frames = d_frames; p.frame_stride = frame_stride; p.pitch = pitch; p.is_f32 = (e->dtype == B2PIV_F32);
     p.n_rows = e->n_rows; p.n_cols = e->n_cols; p.sy = e->wy - e->oy; p.sx = e->wx - e->ox; p.n_pairs = n_pairs;
+    p.ny = e->wy; p.nx = e->wx;
     p.clip_norm = e->clip_norm; p.border_nan = e->border_nan; p.gauss_eps = e->gauss_eps;
     return p;
 }
@@ -768,16 +801,18 @@ int b2piv_plan(b2piv_engine* e, int height, int width, int win_y, int win_x, int
     e->H = height; e->W = width; e->wy = win_y; e->wx = win_x; e->oy = ovl_y; e->ox = ovl_x; e->dtype = dtype;
     e->n_rows = (height - win_y) / (win_y - ovl_y) + 1;
     e->n_cols = (width - win_x) / (win_x - ovl_x) + 1;
-    // twiddle tables exp(-2 pi i j / N), computed in double
-    std::vector<float2> tx(win_x), ty(win_y);
-    for (int j = 0; j < win_x; ++j) tx[j] = make_float2((float)cos(2.0 * M_PI * j / win_x), (float)-sin(2.0 * M_PI * j / win_x));
-    for (int j = 0; j < win_y; ++j) ty[j] = make_float2((float)cos(2.0 * M_PI * j / win_y), (float)-sin(2.0 * M_PI * j / win_y));
+    // twiddle tables exp(-2 pi i j / N) for the FFT plane (= the window, or its padded power-of-two plane), in double
+    int py = win_y, px = win_x;
+    plane_shape(e, &py, &px);
+    std::vector<float2> tx(px), ty(py);
+    for (int j = 0; j < px; ++j) tx[j] = make_float2((float)cos(2.0 * M_PI * j / px), (float)-sin(2.0 * M_PI * j / px));
+    for (int j = 0; j < py; ++j) ty[j] = make_float2((float)cos(2.0 * M_PI * j / py), (float)-sin(2.0 * M_PI * j / py));
     if (e->d_twx) { CK(cudaFree(e->d_twx)); e->d_twx = nullptr; }
     if (e->d_twy) { CK(cudaFree(e->d_twy)); e->d_twy = nullptr; }
-    CK(cudaMalloc((void**)&e->d_twx, sizeof(float2) * win_x));
-    CK(cudaMalloc((void**)&e->d_twy, sizeof(float2) * win_y));
-    CK(cudaMemcpy(e->d_twx, tx.data(), sizeof(float2) * win_x, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(e->d_twy, ty.data(), sizeof(float2) * win_y, cudaMemcpyHostToDevice));
+    CK(cudaMalloc((void**)&e->d_twx, sizeof(float2) * px));
+    CK(cudaMalloc((void**)&e->d_twy, sizeof(float2) * py));
+    CK(cudaMemcpy(e->d_twx, tx.data(), sizeof(float2) * px, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_twy, ty.data(), sizeof(float2) * py, cudaMemcpyHostToDevice));
     e->planned = true;
     e->ens_open = false;
     if (n_rows) *n_rows = e->n_rows;

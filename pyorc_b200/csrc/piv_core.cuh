@@ -133,6 +133,8 @@ struct Params {
     int n_rows, n_cols;       // PIV field shape
     int sy, sx;               // window stride (w - overlap) in pixels
     int n_pairs;              // frame pairs in this launch
+    int ny, nx;               // true window size; equal to the FFT plane (WY, WX) or, for sizes that are not a power
+                              // of two, at most half of it ("padded mode", see phase_embed)
     int clip_norm;            // 1: clip normalised windows at 0 (OpenPIV normalize_intensity)
     int border_nan;           // 1: border peak -> NaN displacement, 0: integer peak
     float gauss_eps;          // epsilon added before logs
@@ -260,8 +262,8 @@ B2_HD void phase_load(Smem<C>& s, int tid, const Params& p, const Item& it) {
         const int x0 = c * p.sx;
         unsigned long long sa = 0, sb = 0, qa = 0, qb = 0;
         float fa = 0.f, fb = 0.f;
-        for (int e = tid; e < C::NPX; e += C::NT) {
-            const int y = e / C::WX, x = e % C::WX;
+        for (int e = tid; e < p.ny * p.nx; e += C::NT) {
+            const int y = e / p.nx, x = e % p.nx;
             float a, b;
             if (!p.is_f32) {
                 const unsigned char* ra = base + off + (long long)y * p.pitch + x0 + x;
@@ -295,7 +297,7 @@ B2_HD void phase_stats(Smem<C>& s, int tid, const Params& p) {
     if (tid < C::NWIN) {
         const int w = tid;
         if (!p.is_f32) {
-            const double n = (double)C::NPX;
+            const double n = (double)(p.ny * p.nx);
             const double sa = (double)total_sum_u64<C>(s, 4 * w + 0), qa = (double)total_sum_u64<C>(s, 4 * w + 1);
             const double sb = (double)total_sum_u64<C>(s, 4 * w + 2), qb = (double)total_sum_u64<C>(s, 4 * w + 3);
             const double va = (qa - sa * sa / n) / n, vb = (qb - sb * sb / n) / n;  // population variance
@@ -303,10 +305,11 @@ B2_HD void phase_stats(Smem<C>& s, int tid, const Params& p) {
             s.mean[2 * w + 1] = (float)(sb / n);
             s.isum[2 * w + 0] = (float)sa;
             s.isum[2 * w + 1] = (float)sb;
-            s.scale[w] = (va > 0.0 && vb > 0.0) ? (float)(1.0 / (n * n * sqrt(va) * sqrt(vb))) : 0.f;
+            // unnormalised inverse FFT of size NPX returns NPX * sum(a b); the reference divides the sum by n
+            s.scale[w] = (va > 0.0 && vb > 0.0) ? (float)(1.0 / ((double)C::NPX * n * sqrt(va) * sqrt(vb))) : 0.f;
         } else {
-            s.mean[2 * w + 0] = total_sum_f32<C>(s, 4 * w + 0) / (float)C::NPX;
-            s.mean[2 * w + 1] = total_sum_f32<C>(s, 4 * w + 2) / (float)C::NPX;
+            s.mean[2 * w + 0] = total_sum_f32<C>(s, 4 * w + 0) / (float)(p.ny * p.nx);
+            s.mean[2 * w + 1] = total_sum_f32<C>(s, 4 * w + 2) / (float)(p.ny * p.nx);
         }
     }
 }
@@ -319,10 +322,11 @@ B2_HD void phase_center(Smem<C>& s, int tid, const Params& p) {
         const float ma = s.mean[2 * w], mb = s.mean[2 * w + 1];
         const float ia = s.isum[2 * w], ib = s.isum[2 * w + 1];
         float qa = 0.f, qb = 0.f;
-        for (int e = tid; e < C::NPX; e += C::NT) {
-            const int y = e / C::WX, x = e % C::WX;
+        const bool exact_n = (p.ny * p.nx == C::NPX);
+        for (int e = tid; e < p.ny * p.nx; e += C::NT) {
+            const int y = e / p.nx, x = e % p.nx;
             float2 z = s.plane[w][y * C::P + x];
-            if (!p.is_f32) {  // exact: (N*x - S) is an integer below 2^24, 1/N is a power of two
+            if (!p.is_f32 && exact_n) {  // exact: (N*x - S) is an integer below 2^24, 1/N is a power of two
                 z.x = (z.x * (float)C::NPX - ia) * (1.0f / (float)C::NPX);
                 z.y = (z.y * (float)C::NPX - ib) * (1.0f / (float)C::NPX);
             } else { z.x -= ma; z.y -= mb; }
@@ -336,14 +340,32 @@ B2_HD void phase_center(Smem<C>& s, int tid, const Params& p) {
         }
     }
 }
+// PHASE 3c (padded mode only, ny*nx < NPX): windows whose size is not a power of two run through the power-of-two
+// FFT as an EXACT circular correlation of period (ny, nx): frame k's window is zero-padded, frame k+1's window is
+// tiled periodically over [0, 2ny) x [0, 2nx) (zero beyond), so  sum_x a'(x) b'(x + s)  for 0 <= s < n never wraps in
+// the (>= 2n)-point plane.  In-region values are rewritten unchanged, so concurrent readers are safe.
+template <class C>
+B2_HD void phase_embed(Smem<C>& s, int tid, const Params& p) {
+    if (p.ny * p.nx == C::NPX) return;
+#pragma unroll
+    for (int w = 0; w < C::NWIN; ++w) {
+        for (int e = tid; e < C::NPX; e += C::NT) {
+            const int y = e / C::WX, x = e % C::WX;
+            const float a = (y < p.ny && x < p.nx) ? s.plane[w][y * C::P + x].x : 0.f;
+            const float b = (y < 2 * p.ny && x < 2 * p.nx) ? s.plane[w][(y % p.ny) * C::P + (x % p.nx)].y : 0.f;
+            s.plane[w][y * C::P + x] = make_float2(a, b);
+        }
+    }
+}
+
 // PHASE 3b (f32 only): scale from centred second moments.
 template <class C>
 B2_HD void phase_stats_f32(Smem<C>& s, int tid, const Params& p) {
     if (p.is_f32 && tid < C::NWIN) {
         const int w = tid;
-        const double n = (double)C::NPX;
+        const double n = (double)(p.ny * p.nx);
         const double va = (double)total_sum_f32<C>(s, 4 * w + 1) / n, vb = (double)total_sum_f32<C>(s, 4 * w + 3) / n;
-        s.scale[w] = (va > 0.0 && vb > 0.0) ? (float)(1.0 / (n * n * sqrt(va) * sqrt(vb))) : 0.f;
+        s.scale[w] = (va > 0.0 && vb > 0.0) ? (float)(1.0 / ((double)C::NPX * n * sqrt(va) * sqrt(vb))) : 0.f;
     }
 }
 
@@ -444,8 +466,8 @@ B2_HD void phase_cross(Smem<C>& s, int tid) {
 B2_HD float clip01(float v) { return v < 0.f ? 0.f : (v > 1.f ? 1.f : v); }
 
 template <class C>
-B2_HD float shifted_value(const Smem<C>& s, int w, int i, int j) {  // plane index in fftshifted coordinates
-    const int sy = (i + C::WY / 2) % C::WY, sx = (j + C::WX / 2) % C::WX;
+B2_HD float shifted_value(const Smem<C>& s, int w, int i, int j, int ny = C::WY, int nx = C::WX) {  // fftshifted coordinates
+    const int sy = (i + ny - ny / 2) % ny, sx = (j + nx - nx / 2) % nx;
     const float2 z = s.plane[0][sy * C::P + sx];
     return clip01(w == 0 ? z.x : z.y);
 }
@@ -459,16 +481,16 @@ B2_HD void phase_reduce(Smem<C>& s, int tid, const Params& p, const Item& it) {
         // a window with zero variance in either frame has an exactly-zero plane in the reference; the packed
         // inverse FFT would otherwise leave ~1e-10 rounding cross-talk from its partner window there
         const bool dead = (s.scale[w] == 0.f);
-        for (int e = tid; e < C::NPX; e += C::NT) {
-            const int i = e / C::WX, j = e % C::WX;
-            const float v = dead ? 0.f : shifted_value<C>(s, w, i, j);
+        for (int e = tid; e < p.ny * p.nx; e += C::NT) {
+            const int i = e / p.nx, j = e % p.nx;
+            const float v = dead ? 0.f : shifted_value<C>(s, w, i, j, p.ny, p.nx);
             sum += v;
             union { float f; unsigned u; } cv; cv.f = v;
             const unsigned long long key = ((unsigned long long)cv.u << 32) | (unsigned long long)(0xffffffffu - (unsigned)e);
             best = key > best ? key : best;
             if (p.planes && (w == 0 || it.valid1)) {
                 const long long nw = (long long)p.n_rows * p.n_cols;
-                p.planes[(((long long)it.pair * nw + it.w[w]) * C::WY + i) * C::WX + j] = v;
+                p.planes[(((long long)it.pair * nw + it.w[w]) * p.ny + i) * p.nx + j] = v;
             }
         }
         deposit_max_u64<C>(s, tid, 2 * w + 0, best);
@@ -490,22 +512,23 @@ B2_HD void phase_peak(Smem<C>& s, int tid, const Params& p, const Item& it) {
     union { float f; unsigned u; } cv; cv.u = (unsigned)(key >> 32);
     const float cmax = cv.f;
     const int idx = (int)(0xffffffffu - (unsigned)(key & 0xffffffffull));
-    const int pi = idx / C::WX, pj = idx % C::WX;
-    const float mean = sum / (float)C::NPX;
+    const int ny = p.ny, nx = p.nx;
+    const int pi = idx / nx, pj = idx % nx;
+    const float mean = sum / (float)(ny * nx);
     float uu, vv;
-    const bool border = (pi == 0) || (pi == C::WY - 1) || (pj == 0) || (pj == C::WX - 1);
+    const bool border = (pi == 0) || (pi == ny - 1) || (pj == 0) || (pj == nx - 1);
     if (border) {
         if (p.border_nan) { uu = nanf(""); vv = nanf(""); }
-        else { uu = (float)(pj - C::WX / 2); vv = (float)(pi - C::WY / 2); }
+        else { uu = (float)(pj - nx / 2); vv = (float)(pi - ny / 2); }
     } else {
         const float eps = p.gauss_eps;
         const float lc = logf(cmax + eps);
-        const float ll = logf(shifted_value<C>(s, w, pi - 1, pj) + eps), lr = logf(shifted_value<C>(s, w, pi + 1, pj) + eps);
-        const float ld = logf(shifted_value<C>(s, w, pi, pj - 1) + eps), lu = logf(shifted_value<C>(s, w, pi, pj + 1) + eps);
+        const float ll = logf(shifted_value<C>(s, w, pi - 1, pj, ny, nx) + eps), lr = logf(shifted_value<C>(s, w, pi + 1, pj, ny, nx) + eps);
+        const float ld = logf(shifted_value<C>(s, w, pi, pj - 1, ny, nx) + eps), lu = logf(shifted_value<C>(s, w, pi, pj + 1, ny, nx) + eps);
         const float di = (ll - lr) / (2.f * ll - 4.f * lc + 2.f * lr);
         const float dj = (ld - lu) / (2.f * ld - 4.f * lc + 2.f * lu);
-        vv = ((float)pi + di) - (float)(C::WY / 2);
-        uu = ((float)pj + dj) - (float)(C::WX / 2);
+        vv = ((float)pi + di) - (float)(ny / 2);
+        uu = ((float)pj + dj) - (float)(nx / 2);
     }
     float o_c = cmax, o_s = cmax / mean;
     if (p.keep && !p.keep[it.w[w]]) { uu = vv = o_c = o_s = nanf(""); }

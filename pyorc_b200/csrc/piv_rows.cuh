@@ -68,7 +68,11 @@ struct RCfg {
     static constexpr int P = W + 1;           // transpose-plane pitch in float2 (odd: conflict-free both ways)
     static constexpr int HS = W / 2 + 1;      // ky = 0 .. W/2 computed directly, the rest by Hermitian symmetry
     static constexpr int NPX = W * W;
-    static constexpr int TILE = 2 * W * W;    // bytes: two windows of one frame, uint8
+    static constexpr int TILE = 2 * W * W;    // bytes: two windows of one frame, uint8 (16-byte aligned window starts)
+    // window starts that are only 4-byte aligned (e.g. 32x32 at 75 % overlap: stride 8): the TMA box starts at the
+    // 16-byte boundary below and is 16 bytes wider, rows are read at a per-window byte offset, no swizzle
+    static constexpr int WB = W + 16;
+    static constexpr int TILE_U = 2 * W * WB;
     // Transposes move 32x32 blocks: block b (pitch 33 float2) is READ by warp b.  A 64x64 transpose first moves the
     // two off-diagonal blocks (one CTA barrier), then the diagonal ones (warp-synchronous), reusing the same two
     // blocks - half a plane - so a group needs ~52 KB of shared memory and FOUR groups (8 warps, two per
@@ -89,8 +93,8 @@ struct RSmem {
     unsigned long long mbar;                     // TMA completion barrier
     B2_HD unsigned char* tile() { return reinterpret_cast<unsigned char*>(X); }
 };
-static_assert(sizeof(float2) * RCfg<64>::NWARP * RCfg<64>::XBLK >= RCfg<64>::TILE, "tile must fit in the transpose blocks");
-static_assert(sizeof(float2) * RCfg<32>::NWARP * RCfg<32>::XBLK >= RCfg<32>::TILE, "tile must fit in the transpose blocks");
+static_assert(sizeof(float2) * RCfg<64>::NWARP * RCfg<64>::XBLK >= RCfg<64>::TILE_U, "tile must fit in the transpose blocks");
+static_assert(sizeof(float2) * RCfg<32>::NWARP * RCfg<32>::XBLK >= RCfg<32>::TILE_U, "tile must fit in the transpose blocks");
 
 struct RParams {
     const unsigned char* frames;   // only used by the host emulator (device reads through the tensor map)
@@ -107,7 +111,7 @@ struct RParams {
     float* planes;
 };
 
-// Column owned by a thread in the column phases, chosen so that the -kx partner sits in the SAME warp at lane^16
+// Line (row before / column after the transpose) owned by a thread, chosen so that the -kx partner sits in the SAME warp at lane^16
 // (kx = 0 and W/2 are their own partners): warp w, lane l<16 -> column 16w+l ; lane 16+l -> (W-(16w+l)) % W,
 // except (w=0,l=0) -> W/2.
 template <int W>
@@ -190,16 +194,22 @@ B2_HD float byte_to_float(unsigned word, int b) {
 #endif
 }
 
-template <class R>
-B2_HD void rows_p1(RSmem<R>& s, RRegs<R>& r, int tid) {
+template <class R, bool ALIGNED = true>
+B2_HD void rows_p1(RSmem<R>& s, RRegs<R>& r, int tid, int xoff0 = 0, int xoff1 = 0) {
     constexpr int W = R::W;
     unsigned S[2] = {0, 0}, Q[2] = {0, 0};
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
+        if (ALIGNED) {
 #pragma unroll
-        for (int j = 0; j < W / 16; ++j) {
-            const uint4 q = *reinterpret_cast<const uint4*>(s.tile() + tile_chunk_offset<W>(w, tid, j));
-            r.px[w][4 * j + 0] = q.x; r.px[w][4 * j + 1] = q.y; r.px[w][4 * j + 2] = q.z; r.px[w][4 * j + 3] = q.w;
+            for (int j = 0; j < W / 16; ++j) {
+                const uint4 q = *reinterpret_cast<const uint4*>(s.tile() + tile_chunk_offset<W>(w, column_of<W>(tid), j));
+                r.px[w][4 * j + 0] = q.x; r.px[w][4 * j + 1] = q.y; r.px[w][4 * j + 2] = q.z; r.px[w][4 * j + 3] = q.w;
+            }
+        } else {
+            const unsigned char* row = s.tile() + (w * W + column_of<W>(tid)) * R::WB + (w == 0 ? xoff0 : xoff1);
+#pragma unroll
+            for (int k = 0; k < W / 4; ++k) r.px[w][k] = *reinterpret_cast<const unsigned*>(row + 4 * k);
         }
 #pragma unroll
         for (int k = 0; k < W / 4; ++k) {
@@ -254,103 +264,51 @@ B2_HD void rows_p2_pre(RSmem<R>& s, RRegs<R>& r, int tid, int clip_norm) {
 // WQ = warp of this thread (compile time so that every register index stays static).
 // "other": the values of my row that belong to columns owned by the OTHER warp go to block (1-WQ); after a CTA barrier I
 // read, from block WQ, the other warp's rows at my column.  "own": same inside the warp (warp-synchronous).
-// All four primitives work IN PLACE on r.v with static register indices (SET / HALF are compile-time):
-//   forward : a thread sends the entries of its row that belong to the columns of warp SET, v[column_of(32*SET+sl)],
-//             and later refills exactly those registers with rows 32*SRC .. 32*SRC+31 of its own column.  Either warp
-//             ends with v[column_of(y)] = entry y, which tr_unpermute() turns into natural order.
-//   inverse : a thread sends v[32*HALF + rr] (its column at the rows of warp HALF) and refills those registers with
-//             its own row at the columns of the sending warp: v[i] = entry kx = column_of(i) in the end.
+// Thread t owns LINE sigma(t) = column_of(t) in both orientations (row sigma(t) before the transpose, column sigma(t)
+// after it), so the transpose is one symmetric, in-place operation T with static register indices: thread t sends
+// v[sigma(u)] to thread u and stores what u sends into the same register, v[sigma(u)] = M(sigma(u), sigma(t)) - natural
+// order again.  T is its own inverse, so the forward (rows -> columns) and inverse (columns -> rows) transposes are the
+// same code.  SET selects the 32 partner threads of warp SET (compile time).
 template <class R, int SET>
-B2_HD void tr_fwd_store_set(float2* blk, const RRegs<R>& r, int lane) {
+B2_HD void tr_store_set(float2* blk, const RRegs<R>& r, int lane) {
 #pragma unroll
     for (int sl = 0; sl < 32; ++sl) blk[lane * R::BP + sl] = r.v[column_of<R::W>(32 * SET + sl)];
 }
 template <class R, int SET>
-B2_HD void tr_fwd_load_set(const float2* blk, RRegs<R>& r, int lane) {
+B2_HD void tr_load_set(const float2* blk, RRegs<R>& r, int lane) {
 #pragma unroll
     for (int rr = 0; rr < 32; ++rr) r.v[column_of<R::W>(32 * SET + rr)] = blk[rr * R::BP + lane];
 }
-template <class R, int HALF>
-B2_HD void tr_inv_store_half(float2* blk, const RRegs<R>& r, int lane) {
-#pragma unroll
-    for (int rr = 0; rr < 32; ++rr) blk[rr * R::BP + lane] = r.v[32 * HALF + rr];
-}
-template <class R, int HALF>
-B2_HD void tr_inv_load_half(const float2* blk, RRegs<R>& r, int lane) {
-#pragma unroll
-    for (int sl = 0; sl < 32; ++sl) r.v[32 * HALF + sl] = blk[lane * R::BP + sl];
-}
-// v[column_of(n)] = entry n  ->  v[n] = entry n      (FWD: after the forward transpose)
-// v[i] = entry column_of(i)  ->  v[n] = entry n      (!FWD: after the inverse transpose)
-template <class R, bool FWD>
-B2_HD void tr_unpermute(RRegs<R>& r) {
-    constexpr int W = R::W;
-    float2 t[W];
-#pragma unroll
-    for (int i = 0; i < W; ++i) {
-        if (FWD) t[i] = r.v[column_of<W>(i)];
-        else     t[column_of<W>(i)] = r.v[i];
-    }
-#pragma unroll
-    for (int i = 0; i < W; ++i) r.v[i] = t[i];
-}
 
 #ifdef __CUDACC__
-// Device-side transposes for one thread.  Block b of X is read by warp b.  The warp-dependent branches only swap the
-// order of the two halves; the CTA barriers sit outside them.
+// Device-side transpose for one thread.  Block b of X is read by warp b; the off-diagonal 32x32 blocks need one CTA
+// barrier, the diagonal ones are warp-synchronous.  `pre_barrier`: the other warp may still be reading its block.
 template <class R>
-__device__ __forceinline__ void transpose_fwd_device(RSmem<R>& s, RRegs<R>& r, int tid, bool active) {
+__device__ __forceinline__ void transpose_device(RSmem<R>& s, RRegs<R>& r, int tid, bool pre_barrier) {
     const int lane = tid & 31, wq = tid >> 5;
     if constexpr (R::NWARP == 2) {
-        if (active) { if (wq == 0) tr_fwd_store_set<R, 1>(s.X[1], r, lane); else tr_fwd_store_set<R, 0>(s.X[0], r, lane); }
+        if (pre_barrier) __syncthreads();
+        if (wq == 0) tr_store_set<R, 1>(s.X[1], r, lane); else tr_store_set<R, 0>(s.X[0], r, lane);
         __syncthreads();
         if (wq == 0) {
-            if (active) tr_fwd_load_set<R, 1>(s.X[0], r, lane);      // rows 32..63 of my column
+            tr_load_set<R, 1>(s.X[0], r, lane);
             __syncwarp();
-            if (active) tr_fwd_store_set<R, 0>(s.X[0], r, lane);
+            tr_store_set<R, 0>(s.X[0], r, lane);
             __syncwarp();
-            if (active) tr_fwd_load_set<R, 0>(s.X[0], r, lane);      // rows 0..31
+            tr_load_set<R, 0>(s.X[0], r, lane);
         } else {
-            if (active) tr_fwd_load_set<R, 0>(s.X[1], r, lane);      // rows 0..31 of my column
+            tr_load_set<R, 0>(s.X[1], r, lane);
             __syncwarp();
-            if (active) tr_fwd_store_set<R, 1>(s.X[1], r, lane);
+            tr_store_set<R, 1>(s.X[1], r, lane);
             __syncwarp();
-            if (active) tr_fwd_load_set<R, 1>(s.X[1], r, lane);      // rows 32..63
-        }
-    } else {
-        if (active) tr_fwd_store_set<R, 0>(s.X[0], r, lane);
-        __syncwarp();
-        if (active) tr_fwd_load_set<R, 0>(s.X[0], r, lane);
-    }
-    if (active) tr_unpermute<R, true>(r);
-}
-template <class R>
-__device__ __forceinline__ void transpose_inv_device(RSmem<R>& s, RRegs<R>& r, int tid, bool active) {
-    const int lane = tid & 31, wq = tid >> 5;
-    if constexpr (R::NWARP == 2) {
-        __syncthreads();  // the other warp may still be reading its block (forward transpose)
-        if (active) { if (wq == 0) tr_inv_store_half<R, 1>(s.X[1], r, lane); else tr_inv_store_half<R, 0>(s.X[0], r, lane); }
-        __syncthreads();
-        if (wq == 0) {
-            if (active) tr_inv_load_half<R, 1>(s.X[0], r, lane);     // my row at the columns of warp 1
-            __syncwarp();
-            if (active) tr_inv_store_half<R, 0>(s.X[0], r, lane);
-            __syncwarp();
-            if (active) tr_inv_load_half<R, 0>(s.X[0], r, lane);
-        } else {
-            if (active) tr_inv_load_half<R, 0>(s.X[1], r, lane);     // my row at the columns of warp 0
-            __syncwarp();
-            if (active) tr_inv_store_half<R, 1>(s.X[1], r, lane);
-            __syncwarp();
-            if (active) tr_inv_load_half<R, 1>(s.X[1], r, lane);
+            tr_load_set<R, 1>(s.X[1], r, lane);
         }
     } else {
         __syncwarp();
-        if (active) tr_inv_store_half<R, 0>(s.X[0], r, lane);
+        tr_store_set<R, 0>(s.X[0], r, lane);
         __syncwarp();
-        if (active) tr_inv_load_half<R, 0>(s.X[0], r, lane);
+        tr_load_set<R, 0>(s.X[0], r, lane);
     }
-    if (active) tr_unpermute<R, false>(r);
 }
 #endif
 
@@ -455,7 +413,7 @@ B2_HD float bits_f(unsigned u) { union { float f; unsigned u; } a; a.u = u; retu
 template <class R>
 B2_HD void rows_p6(RSmem<R>& s, RRegs<R>& r, int tid) {
     constexpr int W = R::W;
-    const int si = (tid + W / 2) % W;   // fftshifted row index of this thread's row
+    const int si = (column_of<W>(tid) + W / 2) % W;   // fftshifted index of this thread's row
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
         float M = 0.f, S = 0.f;
@@ -491,7 +449,7 @@ B2_HD void rows_p6(RSmem<R>& s, RRegs<R>& r, int tid) {
 template <class R>
 B2_HD void rows_p7(RSmem<R>& s, RRegs<R>& r, int tid) {
     constexpr int W = R::W;
-    const int si = (tid + W / 2) % W;
+    const int si = (column_of<W>(tid) + W / 2) % W;
     float* nb = &s.nb[0][0][0];   // [w][3][W]
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
@@ -544,7 +502,7 @@ template <class R>
 B2_HD void rows_dump_planes(RRegs<R>& r, int tid, const RParams& p, const RUnit& un, int pair) {
     constexpr int W = R::W;
     if (!p.planes) return;
-    const int si = (tid + W / 2) % W;
+    const int si = (column_of<W>(tid) + W / 2) % W;
     const long long nw = (long long)p.n_rows * p.n_cols;
 #pragma unroll
     for (int w = 0; w < 2; ++w) {

@@ -29,6 +29,7 @@ static int run(Params p) {
         ALL(phase_stats<C>(s, tid, p));
         zero_red(s); ALL(phase_center<C>(s, tid, p));
         ALL(phase_stats_f32<C>(s, tid, p));
+        ALL(phase_embed<C>(s, tid, p));
         ALL((fft_pass<C, C::NWIN, 0, 0, 0>(s, tid)));
         ALL((fft_pass<C, C::NWIN, 0, 1, 0>(s, tid)));
         ALL((fft_pass<C, C::NWIN, 1, 0, 0>(s, tid)));
@@ -60,6 +61,12 @@ extern "C" int b2piv_emul_pairs(const void* frames, int n_frames, int H, int W, 
     p.n_pairs = n_frames - 1;
     p.clip_norm = clip_norm; p.border_nan = border_nan; p.gauss_eps = eps; p.keep = keep;
     p.u = u; p.v = v; p.cmax = cmax; p.s2n = s2n; p.planes = planes;
+    p.ny = wy; p.nx = wx;
+    {   // non power-of-two windows: padded plane, same rule as b2piv.cu plane_shape()
+        auto pow2ok = [](int n) { return n == 16 || n == 32 || n == 64 || n == 128; };
+        auto pad = [](int n) { int w = 16; while (w < 2 * n) w <<= 1; return w; };
+        if (!(pow2ok(wy) && pow2ok(wx))) { int a = pad(wy), b = pad(wx); if (a != b && !((a == 32 && b == 64) || (a == 64 && b == 32))) a = b = (a > b ? a : b); wy = a; wx = b; }
+    }
 #define CASE(Y, X, T) if (wy == Y && wx == X) return nwin == 2 ? run<Cfg<Y, X, T, 2>>(p) : run<Cfg<Y, X, T, 1>>(p);
     CASE(16, 16, 64) CASE(32, 32, 128) CASE(64, 64, 256) CASE(128, 128, 256) CASE(32, 64, 128) CASE(64, 32, 128)
     return -1;
@@ -67,29 +74,24 @@ extern "C" int b2piv_emul_pairs(const void* frames, int n_frames, int H, int W, 
 
 
 // ---- row-per-thread kernel (piv_rows.cuh): lock-step emulation of the W threads of one group ---------------------
-// lock-step emulation of transpose_fwd_device / transpose_inv_device (sub-phases separated where the device has a
-// CTA barrier or a __syncwarp)
+// lock-step emulation of transpose_device (sub-phases separated where the device has a CTA barrier or a __syncwarp)
 template <class R, bool FWD>
 static void emul_transpose(RSmem<R>& s, std::vector<RRegs<R>>& regs) {
     constexpr int W = R::W;
-    // op(t, set_or_half, block): store / load
     auto store = [&](int t, int k, int blk) {
         const int lane = t & 31;
-        if (FWD) { if (k == 0) tr_fwd_store_set<R, 0>(s.X[blk], regs[t], lane); else tr_fwd_store_set<R, (R::NWARP == 2 ? 1 : 0)>(s.X[blk], regs[t], lane); }
-        else     { if (k == 0) tr_inv_store_half<R, 0>(s.X[blk], regs[t], lane); else tr_inv_store_half<R, (R::NWARP == 2 ? 1 : 0)>(s.X[blk], regs[t], lane); }
+        if (k == 0) tr_store_set<R, 0>(s.X[blk], regs[t], lane); else tr_store_set<R, (R::NWARP == 2 ? 1 : 0)>(s.X[blk], regs[t], lane);
     };
     auto load = [&](int t, int k, int blk) {
         const int lane = t & 31;
-        if (FWD) { if (k == 0) tr_fwd_load_set<R, 0>(s.X[blk], regs[t], lane); else tr_fwd_load_set<R, (R::NWARP == 2 ? 1 : 0)>(s.X[blk], regs[t], lane); }
-        else     { if (k == 0) tr_inv_load_half<R, 0>(s.X[blk], regs[t], lane); else tr_inv_load_half<R, (R::NWARP == 2 ? 1 : 0)>(s.X[blk], regs[t], lane); }
+        if (k == 0) tr_load_set<R, 0>(s.X[blk], regs[t], lane); else tr_load_set<R, (R::NWARP == 2 ? 1 : 0)>(s.X[blk], regs[t], lane);
     };
     if (R::NWARP == 2) {
-        for (int t = 0; t < W; ++t) { const int wq = t >> 5; store(t, 1 - wq, 1 - wq); }   // other warp's set -> its block
-        for (int t = 0; t < W; ++t) { const int wq = t >> 5; load(t, 1 - wq, wq); }        // from my block
+        for (int t = 0; t < W; ++t) { const int wq = t >> 5; store(t, 1 - wq, 1 - wq); }
+        for (int t = 0; t < W; ++t) { const int wq = t >> 5; load(t, 1 - wq, wq); }
     }
     for (int t = 0; t < W; ++t) { const int wq = t >> 5; store(t, wq, wq); }
     for (int t = 0; t < W; ++t) { const int wq = t >> 5; load(t, wq, wq); }
-    for (int t = 0; t < W; ++t) tr_unpermute<R, FWD>(regs[t]);
 }
 
 template <class R>
@@ -102,14 +104,26 @@ static int run_rows(RParams p) {
         const RUnit un = decode_unit(p, unit);
         for (int f = un.f0; f <= un.f1; ++f) {
             const bool have_prev = f > un.f0;
-            // "TMA": fill the swizzled tile from frame f
-            for (int w = 0; w < 2; ++w)
-                for (int row = 0; row < W; ++row)
-                    for (int j = 0; j < W / 16; ++j)
-                        memcpy(s.tile() + tile_chunk_offset<W>(w, row, j),
-                               p.frames + (long long)f * p.frame_stride + (long long)(un.y0[w] + row) * p.pitch + un.x0[w] + 16 * j, 16);
+            // "TMA": fill the tile from frame f (swizzled exact boxes, or 16-byte wider boxes from the boundary below)
+            const bool aligned = (p.sx % 16) == 0;
+            int xoff[2] = {0, 0};
+            for (int w = 0; w < 2; ++w) {
+                if (aligned) {
+                    for (int row = 0; row < W; ++row)
+                        for (int j = 0; j < W / 16; ++j)
+                            memcpy(s.tile() + tile_chunk_offset<W>(w, row, j),
+                                   p.frames + (long long)f * p.frame_stride + (long long)(un.y0[w] + row) * p.pitch + un.x0[w] + 16 * j, 16);
+                } else {
+                    const int xa = un.x0[w] & ~15;
+                    xoff[w] = un.x0[w] - xa;
+                    for (int row = 0; row < W; ++row)
+                        for (int b = 0; b < R::WB; ++b)
+                            s.tile()[(w * W + row) * R::WB + b] =
+                                (xa + b < p.pitch) ? p.frames[(long long)f * p.frame_stride + (long long)(un.y0[w] + row) * p.pitch + xa + b] : 0;
+                }
+            }
             memset(s.red, 0, sizeof(s.red));
-            for (int t = 0; t < W; ++t) rows_p1<R>(s, regs[t], t);
+            for (int t = 0; t < W; ++t) { if (aligned) rows_p1<R, true>(s, regs[t], t); else rows_p1<R, false>(s, regs[t], t, xoff[0], xoff[1]); }
             for (int t = 0; t < W; ++t) { rows_p2_pre<R>(s, regs[t], t, p.clip_norm); fft_reg<W, 0>(regs[t].v); }
             emul_transpose<R, true>(s, regs);
             for (int t = 0; t < W; ++t) fft_reg<W, 0>(regs[t].v);

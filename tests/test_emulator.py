@@ -79,7 +79,8 @@ def emul_rows():
 
 @pytest.mark.parametrize(
     "win,ovl,shape,run_len",
-    [(64, 32, (4, 200, 304), 0), (64, 32, (5, 136, 208), 2), (32, 16, (4, 100, 160), 0), (32, 24, (4, 80, 96), 3), (64, 48, (3, 140, 160), 1)],
+    [(64, 32, (4, 200, 304), 0), (64, 32, (5, 136, 208), 2), (32, 16, (4, 100, 160), 0), (32, 24, (4, 80, 96), 3), (64, 48, (3, 140, 160), 1),
+     (64, 40, (3, 140, 176), 0), (32, 20, (3, 80, 112), 2)],   # strides 24 / 12: window starts only 8- / 4-byte aligned
 )
 @pytest.mark.parametrize("clip", [1, 0])
 def test_rows_phases_match_oracle(emul_rows, win, ovl, shape, run_len, clip):
@@ -156,3 +157,24 @@ def test_direct_phases_reproduce_reference_golden(emul_direct):
         warnings.simplefilter("ignore", category=RuntimeWarning)
         got = np.nanmean(vx, axis=0).flatten()[-4:]
     assert np.allclose(got, pin, rtol=0, atol=2e-6), (got, pin)
+
+
+@pytest.mark.parametrize("ws,ov,shape", [((26, 26), (12, 12), (2, 80, 100)), ((20, 14), (10, 7), (2, 70, 60)), ((50, 50), (25, 25), (2, 110, 130)),
+                                         ((10, 10), (5, 5), (2, 40, 50)), ((24, 40), (12, 20), (2, 80, 120))])
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32])
+def test_padded_fft_phases_match_oracle(emul, ws, ov, shape, dtype):
+    """Windows that are not a power of two run EXACTLY through the power-of-two FFT kernel: zero-padded a, periodically
+    tiled b, plane >= 2n (piv_core.cuh phase_embed)."""
+    O.CLIP_NORMALIZED = False
+    imgs = synth.particle_frames(*shape, dtype=dtype)
+    imgs[:, :12, :12] = 0
+    nr, nc = O.get_array_shape(shape[1:], ws, ov)
+    _, _, corr = O.cross_corr(imgs, ws, ov)
+    u, v, c, s = O.uv_timestep(imgs, nc, nr, ws, ov)
+    for nwin in (2, 1):
+        (eu, ev, ec, es), pl = emul(imgs, ws, ov, nwin=nwin, clip=0)
+        assert np.abs(pl - corr).max() < 3e-6
+        assert np.array_equal(np.isnan(eu), np.isnan(u)) and np.array_equal(np.isnan(es), np.isnan(s))
+        ok = np.isfinite(u)
+        assert np.abs(eu[ok] - u[ok]).max() < 1e-3 and np.abs(ev[ok] - v[ok]).max() < 1e-3
+        assert np.abs(ec - c).max() < 3e-6

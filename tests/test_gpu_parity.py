@@ -148,6 +148,24 @@ def test_direct_kernel_any_window_size(engine, ws, ov, shape, dtype):
     engine.set_option("kernel_variant", 0.0)
 
 
+PADDED_CASES = [
+    ((26, 26), (12, 12), (3, 150, 180)),    # -> 64x64 plane
+    ((20, 14), (10, 7), (2, 90, 80)),       # -> 64x32 plane
+    ((50, 50), (25, 25), (2, 160, 210)),    # -> 128x128 plane
+    ((24, 40), (12, 20), (2, 100, 160)),    # -> 64x128 plane
+    ((14, 14), (7, 7), (3, 80, 90)),        # -> 32x32 plane
+]
+
+
+@pytest.mark.parametrize("ws,ov,shape", PADDED_CASES)
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32])
+def test_padded_fft_kernel_non_power_of_two_windows(engine, ws, ov, shape, dtype):
+    """pyorc's usual windows (26 from a camera-config 25, 20, 50 ...) through the power-of-two FFT kernel, exactly."""
+    imgs = synth.particle_frames(*shape, dtype=dtype)
+    imgs[:, :20, :20] = 0
+    compare(engine, imgs, ws, ov, 0, variant=0)
+
+
 def test_odd_window_count_and_ragged_edges(engine):
     # 3 x 5 windows (odd count -> last work item holds a single window); frame not a multiple of the stride
     imgs = synth.particle_frames(3, 64 * 2 + 7, 64 * 3 + 13, dtype=np.uint8)
@@ -189,6 +207,8 @@ def test_errors(engine):
     big = synth.particle_frames(2, 200, 200, dtype=np.uint8)
     with pytest.raises(NotImplementedError):
         engine.pairs(big, (96, 96), (48, 48))          # > 64 and not one of the compiled FFT shapes
+    with pytest.raises(NotImplementedError):
+        engine.pairs(big, (70, 70), (35, 35))
     with pytest.raises(ValueError):
         engine.pairs(imgs[:1], (64, 64), (32, 32))
     with pytest.raises(ValueError):
@@ -214,6 +234,22 @@ def test_ensemble_mode_matches_oracle(engine, ws, ov, shape, corr_min, s2n_min):
     imgs[:, : ws[0], : ws[1]] = 0                      # one dead window
     imgs[2] = synth.particle_frames(1, shape[1], shape[2], dtype=np.uint8, seed=7)[0]   # a decorrelated frame -> masked pairs
     nr, nc = O.get_array_shape(shape[1:], ws, ov)
+    # move each threshold into the widest gap of the actual per-pair metrics near its nominal value, so that no pair
+    # sits within rounding distance of a threshold (fp32 engine vs float64 oracle would then mask differently)
+    _, _, c_all, s_all = O.uv_timestep(imgs, nc, nr, ws, ov)
+
+    def gap_threshold(vals, nominal):
+        if nominal <= 0:
+            return 0.0
+        v = np.sort(vals[np.isfinite(vals)])
+        v = v[(v > 0.5 * nominal) & (v < 2.0 * nominal)]
+        if v.size < 2:
+            return float(nominal)
+        k = int(np.argmax(np.diff(v)))
+        return float(0.5 * (v[k] + v[k + 1]))
+
+    corr_min = gap_threshold(c_all.ravel(), corr_min)
+    s2n_min = gap_threshold(s_all.ravel(), s2n_min)
     half = shape[0] // 2 + 1
     chunks = [imgs[:half], imgs[half - 1 :]]
     ens = O.Ensemble(nr, nc, ws, ov, corr_min=corr_min, s2n_min=s2n_min, count_min=0.2)

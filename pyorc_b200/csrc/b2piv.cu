@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(C::NT) piv_pairs_kernel(Params p, const float2
         phase_stats<C>(s, tid, p);               __syncthreads();
         phase_center<C>(s, tid, p);              __syncthreads();
         phase_stats_f32<C>(s, tid, p);
-        if (p.ny * p.nx != C::NPX) { phase_embed<C>(s, tid, p); __syncthreads(); }
+        if (C::PADDED) { phase_embed<C>(s, tid, p); __syncthreads(); }
         fft_pass<C, C::NWIN, 0, 0, 0>(s, tid);   __syncthreads();
         fft_pass<C, C::NWIN, 0, 1, 0>(s, tid);   __syncthreads();
         fft_pass<C, C::NWIN, 1, 0, 0>(s, tid);   __syncthreads();
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(C::NT) piv_ens_kernel(Params p, EnsParams ep, 
             phase_stats<C>(s, tid, p);               __syncthreads();
             phase_center<C>(s, tid, p);              __syncthreads();
             phase_stats_f32<C>(s, tid, p);
-            if (p.ny * p.nx != C::NPX) { phase_embed<C>(s, tid, p); __syncthreads(); }
+            if (C::PADDED) { phase_embed<C>(s, tid, p); __syncthreads(); }
             fft_pass<C, C::NWIN, 0, 0, 0>(s, tid);   __syncthreads();
             fft_pass<C, C::NWIN, 0, 1, 0>(s, tid);   __syncthreads();
             fft_pass<C, C::NWIN, 1, 0, 0>(s, tid);   __syncthreads();
@@ -236,14 +236,14 @@ __global__ void __launch_bounds__(C::NT) piv_ens_kernel(Params p, EnsParams ep, 
                 if (w == 1 && !it.valid1) continue;
                 const unsigned long long key = total_max_u64<C>(s, 2 * w + 0);
                 float cmax = __uint_as_float((unsigned)(key >> 32));
-                float s2n = cmax / (total_sum_f32<C>(s, 2 * w + 1) / (float)(p.ny * p.nx));
+                float s2n = cmax / (total_sum_f32<C>(s, 2 * w + 1) / (float)(win_ny<C>(p) * win_nx<C>(p)));
                 bool ok = (cmax >= ep.corr_min) && (s2n >= ep.s2n_min) && isfinite(cmax) && (s.scale[w] != 0.f);
                 if (p.keep && !p.keep[it.w[w]]) ok = false;   // NaN plane in the reference -> masked out
                 if (ok) {
 #pragma unroll
                     for (int k = 0; k < EPT; ++k) {
                         const int e = tid + k * C::NT;
-                        if (e < p.ny * p.nx) acc[w][k] += shifted_value<C>(s, w, e / p.nx, e % p.nx, p.ny, p.nx);
+                        if (e < win_ny<C>(p) * win_nx<C>(p)) acc[w][k] += shifted_value<C>(s, w, e / win_nx<C>(p), e % win_nx<C>(p), win_ny<C>(p), win_nx<C>(p));
                     }
                     if (cmax > 1e-6f) cnt[w] += 1.f;
                 } else {
@@ -259,10 +259,10 @@ __global__ void __launch_bounds__(C::NT) piv_ens_kernel(Params p, EnsParams ep, 
 #pragma unroll
         for (int w = 0; w < C::NWIN; ++w) {
             if (w == 1 && !it.valid1) continue;
-            float* dst = ep.plane_sum + (long long)it.w[w] * (p.ny * p.nx);
+            float* dst = ep.plane_sum + (long long)it.w[w] * (win_ny<C>(p) * win_nx<C>(p));
 #pragma unroll
             for (int k = 0; k < EPT; ++k)
-                if (tid + k * C::NT < p.ny * p.nx) dst[tid + k * C::NT] += acc[w][k];
+                if (tid + k * C::NT < win_ny<C>(p) * win_nx<C>(p)) dst[tid + k * C::NT] += acc[w][k];
             if (tid == 0) ep.count[it.w[w]] += cnt[w];
         }
     }
@@ -436,7 +436,7 @@ struct b2piv_engine {
     float* d_planes = nullptr; size_t cap_planes = 0;
     unsigned char* d_keep = nullptr; size_t cap_keep = 0;
     // ensemble accumulators
-    float* d_ens_sum = nullptr; float* d_ens_cnt = nullptr; size_t cap_ens = 0; bool ens_open = false;
+    float* d_ens_sum = nullptr; float* d_ens_cnt = nullptr; size_t cap_ens = 0, cap_ens_windows = 0; bool ens_open = false;
     // stats
     float last_kernel_ms = 0.f;
     long long launches = 0;
@@ -678,7 +678,8 @@ static int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
     e->last_variant = 1;
     int py, px;
     plane_shape(e, &py, &px);
-#define X(Y, XX, T, NW) if (py == Y && px == XX) return launch_pairs<Cfg<Y, XX, T, NW>>(e, p, st);
+    const bool padded = !(py == e->wy && px == e->wx);
+#define X(Y, XX, T, NW) if (py == Y && px == XX) return padded ? launch_pairs<Cfg<Y, XX, T, NW, true>>(e, p, st) : launch_pairs<Cfg<Y, XX, T, NW, false>>(e, p, st);
     B2PIV_CONFIGS(X)
 #undef X
     return fail(e, B2PIV_ERR_UNSUPPORTED, "window size not compiled in");
@@ -688,7 +689,8 @@ static int dispatch_ens(b2piv_engine* e, const Params& p, const EnsParams& ep, c
     if ((e->variant == 3 || tiny) && e->wy <= 64 && e->wx <= 64) return launch_direct_ens(e, p, ep, st);
     int py, px;
     plane_shape(e, &py, &px);
-#define X(Y, XX, T, NW) if (py == Y && px == XX) return launch_ens<Cfg<Y, XX, T, NW>>(e, p, ep, st);
+    const bool padded = !(py == e->wy && px == e->wx);
+#define X(Y, XX, T, NW) if (py == Y && px == XX) return padded ? launch_ens<Cfg<Y, XX, T, NW, true>>(e, p, ep, st) : launch_ens<Cfg<Y, XX, T, NW, false>>(e, p, ep, st);
     B2PIV_CONFIGS(X)
 #undef X
     return fail(e, B2PIV_ERR_UNSUPPORTED, "window size not compiled in");
@@ -966,13 +968,14 @@ int b2piv_ens_begin(b2piv_engine* e) {
     CK(cudaSetDevice(e->device));
     const size_t nw = (size_t)e->n_rows * e->n_cols, npx = (size_t)e->wy * e->wx;
     const size_t need = nw * npx * sizeof(float);
-    if (e->cap_ens < need) {
+    if (e->cap_ens < need || e->cap_ens_windows < nw) {
         if (e->d_ens_sum) CK(cudaFree(e->d_ens_sum));
         if (e->d_ens_cnt) CK(cudaFree(e->d_ens_cnt));
-        e->d_ens_sum = e->d_ens_cnt = nullptr; e->cap_ens = 0;
+        e->d_ens_sum = e->d_ens_cnt = nullptr; e->cap_ens = 0; e->cap_ens_windows = 0;
         CK(cudaMalloc((void**)&e->d_ens_sum, need));
         CK(cudaMalloc((void**)&e->d_ens_cnt, nw * sizeof(float)));
         e->cap_ens = need;
+        e->cap_ens_windows = nw;
     }
     CK(cudaMemsetAsync(e->d_ens_sum, 0, need, e->s_comp));
     CK(cudaMemsetAsync(e->d_ens_cnt, 0, nw * sizeof(float), e->s_comp));

@@ -99,9 +99,12 @@ template <int N>
 B2_HD int negpos(int p) { return pos_of_freq<N>((N - freq_of_pos<N>(p)) % N); }
 
 // Kernel-wide compile-time configuration.
-template <int WY_, int WX_, int NT_, int NWIN_>
+template <int WY_, int WX_, int NT_, int NWIN_, bool PADDED_ = false>
 struct Cfg {
     static constexpr int WY = WY_, WX = WX_, NT = NT_, NWIN = NWIN_;  // NWIN windows per work item (1 or 2)
+    // PADDED: the true window (Params::ny, nx - run time) is at most half the FFT plane; otherwise it IS the plane and
+    // every loop bound / divisor below is a compile-time constant
+    static constexpr bool PADDED = PADDED_;
     static constexpr int NPX = WY * WX;
     static constexpr int P = WX + 1;          // plane pitch in float2 (odd -> conflict-free row & column walks)
     static constexpr int PLANE = WY * P;      // float2 per plane
@@ -110,6 +113,8 @@ struct Cfg {
     static constexpr int R1Y = Factor<WY>::R1, R2Y = Factor<WY>::R2;
     static constexpr int NRED = 8;            // reduction slots per warp
 };
+
+struct Params;
 
 // Shared-memory image of one CTA.  (On the host emulator this is a plain heap object.)
 template <class C>
@@ -142,6 +147,9 @@ struct Params {
     float* u; float* v; float* cmax; float* s2n;   // [n_pairs][n_rows*n_cols]
     float* planes;            // optional debug dump [n_pairs][n_windows][WY][WX] (fftshifted, clipped), or nullptr
 };
+
+template <class C> B2_HD int win_ny(const Params& p) { return C::PADDED ? p.ny : C::WY; }
+template <class C> B2_HD int win_nx(const Params& p) { return C::PADDED ? p.nx : C::WX; }
 
 // ------------------------------------------------------------------------------------------------------------
 // Block reduction helpers.  deposit(): each thread contributes v to slot; after a barrier total() sums warps.
@@ -262,8 +270,8 @@ B2_HD void phase_load(Smem<C>& s, int tid, const Params& p, const Item& it) {
         const int x0 = c * p.sx;
         unsigned long long sa = 0, sb = 0, qa = 0, qb = 0;
         float fa = 0.f, fb = 0.f;
-        for (int e = tid; e < p.ny * p.nx; e += C::NT) {
-            const int y = e / p.nx, x = e % p.nx;
+        for (int e = tid; e < win_ny<C>(p) * win_nx<C>(p); e += C::NT) {
+            const int y = e / win_nx<C>(p), x = e % win_nx<C>(p);
             float a, b;
             if (!p.is_f32) {
                 const unsigned char* ra = base + off + (long long)y * p.pitch + x0 + x;
@@ -297,7 +305,7 @@ B2_HD void phase_stats(Smem<C>& s, int tid, const Params& p) {
     if (tid < C::NWIN) {
         const int w = tid;
         if (!p.is_f32) {
-            const double n = (double)(p.ny * p.nx);
+            const double n = (double)(win_ny<C>(p) * win_nx<C>(p));
             const double sa = (double)total_sum_u64<C>(s, 4 * w + 0), qa = (double)total_sum_u64<C>(s, 4 * w + 1);
             const double sb = (double)total_sum_u64<C>(s, 4 * w + 2), qb = (double)total_sum_u64<C>(s, 4 * w + 3);
             const double va = (qa - sa * sa / n) / n, vb = (qb - sb * sb / n) / n;  // population variance
@@ -308,8 +316,8 @@ B2_HD void phase_stats(Smem<C>& s, int tid, const Params& p) {
             // unnormalised inverse FFT of size NPX returns NPX * sum(a b); the reference divides the sum by n
             s.scale[w] = (va > 0.0 && vb > 0.0) ? (float)(1.0 / ((double)C::NPX * n * sqrt(va) * sqrt(vb))) : 0.f;
         } else {
-            s.mean[2 * w + 0] = total_sum_f32<C>(s, 4 * w + 0) / (float)(p.ny * p.nx);
-            s.mean[2 * w + 1] = total_sum_f32<C>(s, 4 * w + 2) / (float)(p.ny * p.nx);
+            s.mean[2 * w + 0] = total_sum_f32<C>(s, 4 * w + 0) / (float)(win_ny<C>(p) * win_nx<C>(p));
+            s.mean[2 * w + 1] = total_sum_f32<C>(s, 4 * w + 2) / (float)(win_ny<C>(p) * win_nx<C>(p));
         }
     }
 }
@@ -322,9 +330,9 @@ B2_HD void phase_center(Smem<C>& s, int tid, const Params& p) {
         const float ma = s.mean[2 * w], mb = s.mean[2 * w + 1];
         const float ia = s.isum[2 * w], ib = s.isum[2 * w + 1];
         float qa = 0.f, qb = 0.f;
-        const bool exact_n = (p.ny * p.nx == C::NPX);
-        for (int e = tid; e < p.ny * p.nx; e += C::NT) {
-            const int y = e / p.nx, x = e % p.nx;
+        const bool exact_n = !C::PADDED;
+        for (int e = tid; e < win_ny<C>(p) * win_nx<C>(p); e += C::NT) {
+            const int y = e / win_nx<C>(p), x = e % win_nx<C>(p);
             float2 z = s.plane[w][y * C::P + x];
             if (!p.is_f32 && exact_n) {  // exact: (N*x - S) is an integer below 2^24, 1/N is a power of two
                 z.x = (z.x * (float)C::NPX - ia) * (1.0f / (float)C::NPX);
@@ -346,7 +354,7 @@ B2_HD void phase_center(Smem<C>& s, int tid, const Params& p) {
 // the (>= 2n)-point plane.  In-region values are rewritten unchanged, so concurrent readers are safe.
 template <class C>
 B2_HD void phase_embed(Smem<C>& s, int tid, const Params& p) {
-    if (p.ny * p.nx == C::NPX) return;
+    if (!C::PADDED) return;
 #pragma unroll
     for (int w = 0; w < C::NWIN; ++w) {
         for (int e = tid; e < C::NPX; e += C::NT) {
@@ -363,7 +371,7 @@ template <class C>
 B2_HD void phase_stats_f32(Smem<C>& s, int tid, const Params& p) {
     if (p.is_f32 && tid < C::NWIN) {
         const int w = tid;
-        const double n = (double)(p.ny * p.nx);
+        const double n = (double)(win_ny<C>(p) * win_nx<C>(p));
         const double va = (double)total_sum_f32<C>(s, 4 * w + 1) / n, vb = (double)total_sum_f32<C>(s, 4 * w + 3) / n;
         s.scale[w] = (va > 0.0 && vb > 0.0) ? (float)(1.0 / ((double)C::NPX * n * sqrt(va) * sqrt(vb))) : 0.f;
     }
@@ -481,16 +489,17 @@ B2_HD void phase_reduce(Smem<C>& s, int tid, const Params& p, const Item& it) {
         // a window with zero variance in either frame has an exactly-zero plane in the reference; the packed
         // inverse FFT would otherwise leave ~1e-10 rounding cross-talk from its partner window there
         const bool dead = (s.scale[w] == 0.f);
-        for (int e = tid; e < p.ny * p.nx; e += C::NT) {
-            const int i = e / p.nx, j = e % p.nx;
-            const float v = dead ? 0.f : shifted_value<C>(s, w, i, j, p.ny, p.nx);
+        const int ny = win_ny<C>(p), nx = win_nx<C>(p);
+        for (int e = tid; e < ny * nx; e += C::NT) {
+            const int i = e / nx, j = e % nx;
+            const float v = dead ? 0.f : shifted_value<C>(s, w, i, j, ny, nx);
             sum += v;
             union { float f; unsigned u; } cv; cv.f = v;
             const unsigned long long key = ((unsigned long long)cv.u << 32) | (unsigned long long)(0xffffffffu - (unsigned)e);
             best = key > best ? key : best;
             if (p.planes && (w == 0 || it.valid1)) {
                 const long long nw = (long long)p.n_rows * p.n_cols;
-                p.planes[(((long long)it.pair * nw + it.w[w]) * p.ny + i) * p.nx + j] = v;
+                p.planes[(((long long)it.pair * nw + it.w[w]) * ny + i) * nx + j] = v;
             }
         }
         deposit_max_u64<C>(s, tid, 2 * w + 0, best);
@@ -512,7 +521,7 @@ B2_HD void phase_peak(Smem<C>& s, int tid, const Params& p, const Item& it) {
     union { float f; unsigned u; } cv; cv.u = (unsigned)(key >> 32);
     const float cmax = cv.f;
     const int idx = (int)(0xffffffffu - (unsigned)(key & 0xffffffffull));
-    const int ny = p.ny, nx = p.nx;
+    const int ny = win_ny<C>(p), nx = win_nx<C>(p);
     const int pi = idx / nx, pj = idx % nx;
     const float mean = sum / (float)(ny * nx);
     float uu, vv;

@@ -67,8 +67,9 @@ extern "C" int b2piv_emul_pairs(const void* frames, int n_frames, int H, int W, 
         auto pad = [](int n) { int w = 16; while (w < 2 * n) w <<= 1; return w; };
         if (!(pow2ok(wy) && pow2ok(wx))) { int a = pad(wy), b = pad(wx); if (a != b && !((a == 32 && b == 64) || (a == 64 && b == 32))) a = b = (a > b ? a : b); wy = a; wx = b; }
     }
-#define CASE(Y, X, T) if (wy == Y && wx == X) return nwin == 2 ? run<Cfg<Y, X, T, 2>>(p) : run<Cfg<Y, X, T, 1>>(p);
-    CASE(16, 16, 64) CASE(32, 32, 128) CASE(64, 64, 256) CASE(128, 128, 256) CASE(32, 64, 128) CASE(64, 32, 128)
+    const bool padded = !(wy == p.ny && wx == p.nx);
+#define CASE(Y, X, T) if (wy == Y && wx == X) return padded ? (nwin == 2 ? run<Cfg<Y, X, T, 2, true>>(p) : run<Cfg<Y, X, T, 1, true>>(p)) : (nwin == 2 ? run<Cfg<Y, X, T, 2, false>>(p) : run<Cfg<Y, X, T, 1, false>>(p));
+    CASE(16, 16, 64) CASE(32, 32, 128) CASE(64, 64, 256) CASE(128, 128, 256) CASE(32, 64, 128) CASE(64, 32, 128) CASE(64, 128, 256)
     return -1;
 }
 

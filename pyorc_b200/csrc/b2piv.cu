@@ -418,7 +418,7 @@ struct b2piv_engine {
                         // ineligible), 3: direct any-size kernel
     int run_len = 0;    // frame pairs per work unit of the rows kernel (0: auto)
     int groups = 0;     // window-pair groups per CTA of the rows kernel (0: default)
-    int rolled = 0;     // rows kernel: 1 = one shared FFT body (rolled stage loop), 0 = four specialised copies
+    int rolled = -1;    // rows kernel: 1 = one shared FFT body (rolled stage loop), 0 = two copies, -1 = default per size
     int last_variant = 0;
     float gauss_eps = 1e-7f;
     // plan
@@ -653,7 +653,7 @@ static int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
         // groups per CTA (lockstep width) and rolled / unrolled stage loop.  Measured on B200 (profiles/r01): 64x64 is
         // fastest with one group per CTA (four 64-thread CTAs per SM) and four specialised FFT copies, 32x32 with four
         // single-warp groups per CTA.
-        const bool rolled = e->rolled != 0;
+        const bool rolled = e->rolled < 0 ? (e->wy == 64) : (e->rolled != 0);   // measured best: 64 rolled, 32 unrolled
         const bool aligned = ((e->wx - e->ox) & 15) == 0;
 #define ROWS_LAUNCH(RC, GG)                                                                                           \
     return aligned ? (rolled ? launch_rows<RC, GG, true, true>(e, p, st) : launch_rows<RC, GG, false, true>(e, p, st))    \
@@ -784,7 +784,7 @@ int b2piv_set_option(b2piv_engine* e, const char* name, double value) {
     else if (n == "kernel_variant") e->variant = (int)value;
     else if (n == "run_len") e->run_len = value < 0 ? 0 : (int)value;
     else if (n == "groups") e->groups = value < 0 ? 0 : (int)value;
-    else if (n == "rolled") e->rolled = value != 0.0;
+    else if (n == "rolled") e->rolled = value < 0 ? -1 : (value != 0.0);
     else return fail(e, B2PIV_ERR_ARG, "unknown option " + n);
     return B2PIV_OK;
 }

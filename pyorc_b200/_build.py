@@ -8,7 +8,9 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "b2piv.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "piv_core.cuh"), os.path.join(HERE, "..", "include", "b2piv.h")]
+DEPS = [os.path.join(HERE, "csrc", f) for f in sorted(os.listdir(os.path.join(HERE, "csrc")))] + [
+    os.path.join(HERE, "..", "include", "b2piv.h")
+]
 LIB = os.path.join(HERE, "libb2piv.so")
 
 NVCC_FLAGS = [

@@ -144,6 +144,7 @@ struct RRegs {
     float half_alpha_new[2];
     float mean_new[2];
     float rowmax[2], rowsum[2];
+    bool dead[2];                 // window w has zero variance in the previous or the current frame
     int pi[2], pj[2];
     float cmaxv[2], sumv[2];
     float2 r0, r1;                // host emulator only: cross spectra of the current ky step
@@ -185,13 +186,11 @@ B2_HD unsigned dp4a_u(unsigned a, unsigned b, unsigned c) {
 #endif
 }
 
-// byte b of a packed word as float without the (slow) I2F pipe: 0x4B0000bb is 8388608 + bb exactly
+// byte b of a packed word as float
 B2_HD float byte_to_float(unsigned word, int b) {
-#ifdef __CUDA_ARCH__
-    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u + (unsigned)b)) - 8388608.0f;
-#else
+    // one I2F with a byte selector: a single issue slot on the (otherwise idle) conversion pipe, cheaper here than the
+    // PRMT + FADD "magic number" sequence which costs two slots of the busy FMA/ALU pipes
     return (float)((word >> (8 * b)) & 0xffu);
-#endif
 }
 
 template <class R, bool ALIGNED = true>
@@ -336,11 +335,14 @@ B2_HD void cross_step_a(RSmem<R>& s, RRegs<R>& r, int tid, int ky, float2 pz, bo
     s.park[1][ky][tid] = make_float2(a1.x * INVN2, a1.y * INVN2);
     if (have_prev) r.v[ky] = make_float2(r0.x - r1.y, -(r0.y + r1.x));            // conj(G), G = R0 + i R1
 }
-// part B: partner's (R0, R1) at (ky, -col) give G(-ky, col) = conj(R0) + i conj(R1); stored conjugated
+// part B: the partner's (R0, R1) at (ky, -col) give G(-ky, col) = conj(R0) + i conj(R1), stored conjugated:
+// conj(G(-ky, col)) = (R0.x + R1.y, R0.y - R1.x).  The SENDER forms that value (cross_mirror) so only one complex number
+// crosses the warp per step.
+B2_HD float2 cross_mirror(float2 r0, float2 r1) { return make_float2(r0.x + r1.y, r0.y - r1.x); }
 template <class R>
-B2_HD void cross_step_b(RRegs<R>& r, int ky, float2 q0, float2 q1) {
+B2_HD void cross_step_b(RRegs<R>& r, int ky, float2 q) {
     constexpr int W = R::W;
-    if (ky != 0 && ky != W / 2) r.v[W - ky] = make_float2(q0.x + q1.y, q0.y - q1.x);   // conj of G(-ky)
+    if (ky != 0 && ky != W / 2) r.v[W - ky] = q;
 }
 
 #ifdef __CUDACC__
@@ -357,10 +359,7 @@ __device__ __forceinline__ void rows_p3b_device(RSmem<R>& s, RRegs<R>& r, int ti
         const float2 pz = shfl2(r.v[(W - ky) % W], pl);
         float2 r0 = make_float2(0.f, 0.f), r1 = make_float2(0.f, 0.f);
         cross_step_a<R>(s, r, tid, ky, pz, have_prev, r0, r1);
-        if (have_prev && ky != 0 && ky != W / 2) {
-            const float2 q0 = shfl2(r0, pl), q1 = shfl2(r1, pl);
-            cross_step_b<R>(r, ky, q0, q1);
-        }
+        if (have_prev && ky != 0 && ky != W / 2) cross_step_b<R>(r, ky, shfl2(cross_mirror(r0, r1), pl));
     }
 }
 #endif
@@ -377,11 +376,16 @@ B2_HD void rows_p5_post(RSmem<R>& s, RRegs<R>& r, int tid, bool dead0, bool dead
 #pragma unroll
     for (int x = 0; x < W; ++x) {
         // clip to [0, 1] (inputs are uint8, no NaNs can occur, so fmin/fmax are exact here)
-        float a = dead0 ? 0.f : fminf(fmaxf(r.v[x].x, 0.f), 1.f), b = dead1 ? 0.f : fminf(fmaxf(-r.v[x].y, 0.f), 1.f);
+        const float a = fminf(fmaxf(r.v[x].x, 0.f), 1.f), b = fminf(fmaxf(-r.v[x].y, 0.f), 1.f);
         r.v[x] = make_float2(a, b);
         m0 = fmaxf(a, m0); m1 = fmaxf(b, m1);
         s0 += a; s1 += b;
     }
+    // a window with zero variance has an exactly-zero plane in the reference (the packed inverse FFT leaves ~1e-10
+    // cross-talk from its partner window): force max = sum = 0 here, first-argmax 0 in rows_p6, zeros in the dumps
+    if (dead0) { m0 = 0.f; s0 = 0.f; }
+    if (dead1) { m1 = 0.f; s1 = 0.f; }
+    r.dead[0] = dead0; r.dead[1] = dead1;
     r.rowmax[0] = m0; r.rowmax[1] = m1; r.rowsum[0] = s0; r.rowsum[1] = s1;
 #ifdef __CUDA_ARCH__
     float vm0 = m0, vm1 = m1;
@@ -430,6 +434,7 @@ B2_HD void rows_p6(RSmem<R>& s, RRegs<R>& r, int tid) {
                 const float val = w == 0 ? r.v[x].x : r.v[x].y;
                 first = (val == M) ? j : first;
             }
+            if (r.dead[w]) first = 0;   // all-zero plane: every element is the maximum
             key = (unsigned long long)(si * W + first);
         }
 #ifdef __CUDA_ARCH__
@@ -461,7 +466,7 @@ B2_HD void rows_p7(RSmem<R>& s, RRegs<R>& r, int tid) {
         const int d = si - r.pi[w];
         if (d >= -1 && d <= 1) {
 #pragma unroll
-            for (int x = 0; x < W; ++x) nb[(w * 3 + (d + 1)) * W + (x + W / 2) % W] = w == 0 ? r.v[x].x : r.v[x].y;
+            for (int x = 0; x < W; ++x) nb[(w * 3 + (d + 1)) * W + (x + W / 2) % W] = r.dead[w] ? 0.f : (w == 0 ? r.v[x].x : r.v[x].y);
         }
     }
 }
@@ -509,7 +514,7 @@ B2_HD void rows_dump_planes(RRegs<R>& r, int tid, const RParams& p, const RUnit&
         if (w == 1 && !un.valid1) continue;
         float* dst = p.planes + (((long long)pair * nw + un.w[w]) * W + si) * W;
 #pragma unroll
-        for (int x = 0; x < W; ++x) dst[(x + W / 2) % W] = w == 0 ? r.v[x].x : r.v[x].y;
+        for (int x = 0; x < W; ++x) dst[(x + W / 2) % W] = r.dead[w] ? 0.f : (w == 0 ? r.v[x].x : r.v[x].y);
     }
 }
 

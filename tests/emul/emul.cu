@@ -136,11 +136,11 @@ static int run_rows(RParams p) {
                     cross_step_a<R>(s, regs[t], t, ky, snap[pt].v[(W - ky) % W], have_prev, regs[t].r0, regs[t].r1);
                 }
                 if (have_prev && ky != 0 && ky != W / 2) {
-                    std::vector<float2> q0(W), q1(W);
-                    for (int t = 0; t < W; ++t) { q0[t] = regs[t].r0; q1[t] = regs[t].r1; }
+                    std::vector<float2> q(W);
+                    for (int t = 0; t < W; ++t) q[t] = cross_mirror(regs[t].r0, regs[t].r1);
                     for (int t = 0; t < W; ++t) {
                         const int pt = (t & ~31) | partner_lane_of<W>(t);
-                        cross_step_b<R>(regs[t], ky, q0[pt], q1[pt]);
+                        cross_step_b<R>(regs[t], ky, q[pt]);
                     }
                 }
             }

@@ -81,6 +81,11 @@ int b2piv_ens_accum(b2piv_engine* e, float** d_plane_sum, float** d_count, long 
                     long long* n_windows);
 int b2piv_ens_finish_host(b2piv_engine* e, float min_count, float* u, float* v, float* count);
 
+/* Sub-pixel peak of arbitrary correlation planes [n_planes][wy][wx] (host): first-occurrence argmax + 3-point
+ * Gaussian fit minus the plane centre - the standalone `ffpiv.u_v_displacement` (pyorc/velocimetry/ffpiv.py:324,471),
+ * for callers that build their own planes (e.g. a mean plane).  u = column shift, v = row shift, [n_planes]. */
+int b2piv_peaks_host(b2piv_engine* e, const float* corr, long long n_planes, int wy, int wx, float* u, float* v);
+
 /* Page-locked host memory so H2D copies run at full PCIe rate without staging. */
 void* b2piv_host_alloc(size_t bytes);
 void b2piv_host_free(void* p);

@@ -1060,6 +1060,31 @@ int b2piv_ens_finish_host(b2piv_engine* e, float min_count, float* u, float* v, 
     return B2PIV_OK;
 }
 
+int b2piv_peaks_host(b2piv_engine* e, const float* corr, long long n_planes, int wy, int wx, float* u, float* v) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (!corr || !u || !v) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
+    if (n_planes < 0 || wy < 3 || wx < 3) return fail(e, B2PIV_ERR_ARG, "need n_planes >= 0 and planes of at least 3x3");
+    if (n_planes == 0) return B2PIV_OK;
+    CK(cudaSetDevice(e->device));
+    const size_t npx = (size_t)wy * wx;
+    int rc = ensure(e, &e->d_planes, &e->cap_planes, (size_t)n_planes * npx * sizeof(float));
+    if (rc) return rc;
+    rc = ensure(e, &e->d_out, &e->cap_out, (size_t)n_planes * 3 * sizeof(float));
+    if (rc) return rc;
+    float* d_one = e->d_out + 2 * n_planes;   // per-plane divisor 1 (the kernel divides the plane by its count)
+    std::vector<float> ones((size_t)n_planes, 1.0f);
+    CK(cudaMemcpyAsync(e->d_planes, corr, (size_t)n_planes * npx * sizeof(float), cudaMemcpyHostToDevice, e->s_comp));
+    CK(cudaMemcpyAsync(d_one, ones.data(), (size_t)n_planes * sizeof(float), cudaMemcpyHostToDevice, e->s_comp));
+    ens_finish_kernel<<<(unsigned)n_planes, 256, 0, e->s_comp>>>(e->d_planes, d_one, wy, wx, 0.f, e->border_nan, e->gauss_eps, e->d_out,
+                                                                  e->d_out + n_planes);
+    CK(cudaGetLastError());
+    e->launches++;
+    CK(cudaMemcpyAsync(u, e->d_out, (size_t)n_planes * sizeof(float), cudaMemcpyDeviceToHost, e->s_comp));
+    CK(cudaMemcpyAsync(v, e->d_out + n_planes, (size_t)n_planes * sizeof(float), cudaMemcpyDeviceToHost, e->s_comp));
+    CK(cudaStreamSynchronize(e->s_comp));
+    return B2PIV_OK;
+}
+
 void* b2piv_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;

@@ -36,6 +36,7 @@ ABI_SYMBOLS = (
     "b2piv_ens_add_device",
     "b2piv_ens_accum",
     "b2piv_ens_finish_host",
+    "b2piv_peaks_host",
     "b2piv_host_alloc",
     "b2piv_host_free",
     "b2piv_last_kernel_ms",
@@ -73,6 +74,7 @@ def load_library(path: Optional[str] = None):
     lib.b2piv_ens_add_device.argtypes = [vp, vp, cll, ci, ci, cf, cf, cf, vp, vp, vp]
     lib.b2piv_ens_accum.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(cll), ctypes.POINTER(cll)]
     lib.b2piv_ens_finish_host.argtypes = [vp, cf, vp, vp, vp]
+    lib.b2piv_peaks_host.argtypes = [vp, vp, cll, ci, ci, vp, vp]
     lib.b2piv_host_alloc.argtypes = [ctypes.c_size_t]
     lib.b2piv_host_alloc.restype = vp
     lib.b2piv_host_free.argtypes = [vp]
@@ -266,6 +268,20 @@ class Engine:
         corr = np.empty((n - 1, nr * nc, window_size[0], window_size[1]), dtype=np.float32)
         self._check(self._lib.b2piv_corr_planes_host(self._h, frames.ctypes.data, n, thr, corr.ctypes.data), "b2piv_corr_planes_host")
         return corr
+
+    def peaks(self, corr) -> Tuple[np.ndarray, np.ndarray]:
+        """``u, v`` (pixels, shape ``corr.shape[:-2]``) of arbitrary correlation planes ``[..., wy, wx]``: first-occurrence
+        argmax + 3-point Gaussian fit minus the centre - ``ffpiv.u_v_displacement`` without the reshape."""
+        corr = np.ascontiguousarray(corr, dtype=np.float32)
+        if corr.ndim < 2:
+            raise ValueError("corr must be [..., wy, wx]")
+        lead = corr.shape[:-2]
+        n = int(np.prod(lead)) if lead else 1
+        u = np.empty(n, dtype=np.float32)
+        v = np.empty(n, dtype=np.float32)
+        self._check(self._lib.b2piv_peaks_host(self._h, corr.ctypes.data, n, corr.shape[-2], corr.shape[-1], u.ctypes.data, v.ctypes.data),
+                    "b2piv_peaks_host")
+        return u.reshape(lead), v.reshape(lead)
 
     # ---- ensemble ---------------------------------------------------------------------------------------------
     def ens_begin(self, dim_size, window_size, overlap, dtype):

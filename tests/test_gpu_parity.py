@@ -284,3 +284,26 @@ def test_ensemble_mode_matches_oracle(engine, ws, ov, shape, corr_min, s2n_min):
     same = (np.abs(np.round(gu[ok]) - np.round(u[ok])) + np.abs(np.round(gv[ok]) - np.round(v[ok]))) < 0.5
     assert same.mean() >= 0.99
     assert np.abs(gu[ok][same] - u[ok][same]).max() <= 2e-3 and np.abs(gv[ok][same] - v[ok][same]).max() <= 2e-3
+
+
+def test_ffpiv_api_cross_corr_and_u_v_displacement(engine):
+    """ffpiv's own two-call form (cross_corr -> planes -> u_v_displacement) on the GPU, against the oracle's."""
+    from pyorc_b200 import ffpiv_api
+
+    O.CLIP_NORMALIZED = False
+    engine.set_option("clip_normalized", 0.0)
+    engine.set_option("kernel_variant", 0.0)
+    imgs = synth.particle_frames(3, 150, 210, dtype=np.uint8)
+    imgs[:, :40, :40] = 0
+    ws, ov = (32, 32), (16, 16)
+    nr, nc = O.get_array_shape(imgs.shape[-2:], ws, ov)
+    x, y, corr = ffpiv_api.cross_corr(imgs, window_size=ws, overlap=ov, search_area_size=ws, normalize=False, verbose=False)
+    ox, oy, ocorr = O.cross_corr(imgs, ws, ov)
+    assert np.array_equal(x, ox) and np.array_equal(y, oy) and corr.dtype == np.float32
+    assert np.nanmax(np.abs(corr - ocorr)) <= 5e-6
+    u, v = ffpiv_api.u_v_displacement(ocorr, nr, nc)          # same planes in -> isolates the peak-fit kernel
+    ou, ov_ = O.u_v_displacement(ocorr, nr, nc)
+    assert u.shape == ou.shape == (2, nr, nc)
+    assert np.array_equal(np.isnan(u), np.isnan(ou))
+    ok = np.isfinite(ou)
+    assert np.abs(u[ok] - ou[ok]).max() <= 1e-4 and np.abs(v[ok] - ov_[ok]).max() <= 1e-4

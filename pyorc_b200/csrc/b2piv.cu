@@ -91,7 +91,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 // "FFT, transpose, FFT" block executed twice).
 // Compute phases run unconditionally (an inactive group - only at the tail of the grid - works on garbage and never
 // stores results); only TMA traffic and global stores are predicated, so no shuffle sits in a divergent region.
-template <class R, int G, bool ROLLED, bool ALIGNED>
+template <class R, int G, bool ROLLED, bool ALIGNED, bool F32>
 __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constant__ CUtensorMap tmap, RParams p) {
     extern __shared__ unsigned char smem_dyn[];
     // the swizzled TMA tiles need 1024-byte aligned bases: align by hand (launch adds 1 KB of slack)
@@ -124,12 +124,26 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
         constexpr int WIN_BYTES = TILE_BYTES / 2;
         const int xa0 = ALIGNED ? un.x0[0] : (un.x0[0] & ~15), xa1 = ALIGNED ? un.x0[1] : (un.x0[1] & ~15);
         const int xoff0 = un.x0[0] - xa0, xoff1 = un.x0[1] - xa1;
-        if (has_unit && tid == 0) {
+        // TMA of the tile(s) a frame starts with: both uint8 windows, or (float32) window 0 - plus window 1 when both
+        // fit the buffer; `issue_f32` loads the W/32 swizzled 128-byte-wide boxes of one float32 window
+        auto issue_f32 = [&](int w, int frame, int toff) {
+#pragma unroll
+            for (int h = 0; h < W / 32; ++h)
+                tma_load_3d(s.tile() + toff + h * R::FBOX, &tmap, &s.mbar, un.x0[w] + 32 * h, un.y0[w], frame);
+        };
+        auto issue_frame_start = [&](int frame) {
             fence_proxy_async();
-            mbar_expect_tx(&s.mbar, TILE_BYTES);
-            tma_load_3d(s.tile(), &tmap, &s.mbar, xa0, un.y0[0], un.f0);
-            tma_load_3d(s.tile() + WIN_BYTES, &tmap, &s.mbar, xa1, un.y0[1], un.f0);
-        }
+            if constexpr (!F32) {
+                mbar_expect_tx(&s.mbar, TILE_BYTES);
+                tma_load_3d(s.tile(), &tmap, &s.mbar, xa0, un.y0[0], frame);
+                tma_load_3d(s.tile() + WIN_BYTES, &tmap, &s.mbar, xa1, un.y0[1], frame);
+            } else {
+                mbar_expect_tx(&s.mbar, R::F_PHASES == 2 ? R::FWIN : 2 * R::FWIN);
+                issue_f32(0, frame, 0);
+                if (R::F_PHASES == 1) issue_f32(1, frame, R::FWIN);
+            }
+        };
+        if (has_unit && tid == 0) issue_frame_start(un.f0);
         for (int k = 0; k < maxn; ++k) {
             const bool active = k < nfr;
             const bool have_prev = k > 0;
@@ -138,9 +152,35 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
                 while (!mbar_try_wait(&s.mbar, parity)) {}
                 parity ^= 1u;
             }
-            rows_p1<R, ALIGNED>(s, r, tid, xoff0, xoff1);
-            __syncthreads();  // A: integer moments visible, tile (aliased on X) fully consumed
-            rows_p2_pre<R>(s, r, tid, p.clip_norm);
+            if constexpr (!F32) {
+                rows_p1<R, ALIGNED>(s, r, tid, xoff0, xoff1);
+                __syncthreads();  // A: integer moments visible, tile (aliased on X) fully consumed
+                rows_p2_pre<R>(s, r, tid, p.clip_norm);
+            } else {
+                rows_f1<R>(s, r, tid, 0, 0);
+                if (R::F_PHASES == 1) rows_f1<R>(s, r, tid, 1, R::FWIN);
+                __syncthreads();  // A: tile consumed, row sums visible
+                if (R::F_PHASES == 2) {
+                    if (active && tid == 0) {   // window 1 of this frame into the same buffer
+                        fence_proxy_async();
+                        mbar_expect_tx(&s.mbar, R::FWIN);
+                        issue_f32(1, f, 0);
+                    }
+                    rows_f2<R>(s, r, tid, 0);   // overlaps the TMA round trip
+                    if (active) {
+                        while (!mbar_try_wait(&s.mbar, parity)) {}
+                        parity ^= 1u;
+                    }
+                    rows_f1<R>(s, r, tid, 1, 0);
+                    __syncthreads();  // A2: tile consumed again
+                    rows_f2<R>(s, r, tid, 1);
+                } else {
+                    rows_f2<R>(s, r, tid, 0);
+                    rows_f2<R>(s, r, tid, 1);
+                }
+                __syncthreads();  // A3: centred second moments visible
+                rows_f3<R>(s, r, tid, p.clip_norm);
+            }
             // The first frame of a unit has no previous spectra: it still runs the whole pipeline (on whatever the
             // park buffer holds) and simply stores no result - one wasted inverse transform per ~26 frames buys a loop
             // body without data-dependent branches, so no shuffle needs convergence bookkeeping.
@@ -166,12 +206,7 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
             const bool dead1 = (r.half_alpha_prev[1] == 0.f) || (r.half_alpha_new[1] == 0.f);
             rows_p5_post<R>(s, r, tid, dead0, dead1);
             __syncthreads();  // E1: block max / sum; X (and the tile aliased on it) is free again
-            if (active && tid == 0 && k + 1 < nfr) {
-                fence_proxy_async();
-                mbar_expect_tx(&s.mbar, TILE_BYTES);
-                tma_load_3d(s.tile(), &tmap, &s.mbar, xa0, un.y0[0], f + 1);
-                tma_load_3d(s.tile() + WIN_BYTES, &tmap, &s.mbar, xa1, un.y0[1], f + 1);
-            }
+            if (active && tid == 0 && k + 1 < nfr) issue_frame_start(f + 1);
             rows_p6<R>(s, r, tid);
             __syncthreads();  // E2: first-argmax key
             if (active && have_prev) rows_dump_planes<R>(r, tid, p, un, f - 1);
@@ -578,7 +613,7 @@ static PFN_encodeTiled get_encode_tiled() {
 }
 
 static bool rows_eligible(const b2piv_engine* e, const void* d_frames, long long frame_stride, int pitch) {
-    if (e->dtype != B2PIV_U8 || e->wy != e->wx || (e->wy != 64 && e->wy != 32)) return false;
+    if (e->wy != e->wx || (e->wy != 64 && e->wy != 32)) return false;   // uint8 and float32 frames both qualify
     if ((pitch & 15) || (frame_stride & 15) || (((uintptr_t)d_frames) & 15)) return false;
     // every TMA box must start on a 16-byte boundary in global memory: x strides that are a multiple of 16 use exact
     // swizzled boxes, multiples of 4 (32x32 at 75 % overlap: stride 8) a 16-byte wider box read at an offset
@@ -586,18 +621,19 @@ static bool rows_eligible(const b2piv_engine* e, const void* d_frames, long long
     return get_encode_tiled() != nullptr;
 }
 
-template <class R, int G, bool ROLLED, bool ALIGNED>
+template <class R, int G, bool ROLLED, bool ALIGNED, bool F32>
 static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st) {
     constexpr int W = R::W;
     const int n_frames = gp.n_pairs + 1;
     CUtensorMap tmap;
     const cuuint64_t dims[3] = {(cuuint64_t)e->W, (cuuint64_t)e->H, (cuuint64_t)n_frames};
     const cuuint64_t strides[2] = {(cuuint64_t)gp.pitch, (cuuint64_t)gp.frame_stride};
-    const cuuint32_t box[3] = {(cuuint32_t)(ALIGNED ? W : R::WB), (cuuint32_t)W, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)(F32 ? 32 : (ALIGNED ? W : R::WB)), (cuuint32_t)W, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult cr = get_encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(gp.frames), dims, strides, box, estr,
-                                           CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                           !ALIGNED ? CU_TENSOR_MAP_SWIZZLE_NONE : (W == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
+    const CUtensorMapSwizzle swz = F32 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                       : (!ALIGNED ? CU_TENSOR_MAP_SWIZZLE_NONE : (W == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B));
+    const CUresult cr = get_encode_tiled()(&tmap, F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
+                                           const_cast<void*>(gp.frames), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(e, B2PIV_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)cr));
     RParams p;
@@ -607,7 +643,7 @@ static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st) {
     p.clip_norm = gp.clip_norm; p.border_nan = gp.border_nan; p.gauss_eps = gp.gauss_eps; p.keep = gp.keep;
     p.u = gp.u; p.v = gp.v; p.cmax = gp.cmax; p.s2n = gp.s2n; p.planes = gp.planes;
     const size_t smem = sizeof(RSmem<R>) * G + 1024;
-    auto kern = piv_rows_kernel<R, G, ROLLED, ALIGNED>;
+    auto kern = piv_rows_kernel<R, G, ROLLED, ALIGNED, F32>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, R::NT * G, smem));
@@ -647,26 +683,27 @@ static int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
     if (p.n_pairs <= 0) return B2PIV_OK;
     const bool can_rows = rows_eligible(e, p.frames, p.frame_stride, p.pitch);
     if (e->variant == 2 && !can_rows)
-        return fail(e, B2PIV_ERR_UNSUPPORTED, "rows kernel needs uint8 frames, a square 32/64 window, 16-byte aligned base/pitch and an x stride that is a multiple of 4");
+        return fail(e, B2PIV_ERR_UNSUPPORTED, "rows kernel needs a square 32/64 window, 16-byte aligned base/pitch and an x stride that is a multiple of 4");
     if (can_rows && e->variant != 1) {
         e->last_variant = 2;
         // groups per CTA (lockstep width) and rolled / unrolled stage loop.  Measured on B200 (profiles/r01): 64x64 is
         // fastest with one group per CTA (four 64-thread CTAs per SM) and four specialised FFT copies, 32x32 with four
         // single-warp groups per CTA.
-        const bool rolled = e->rolled < 0 ? (e->wy == 64) : (e->rolled != 0);   // measured best: 64 rolled, 32 unrolled
+        // Compiled variants (measured on B200, profiles/r01/quick_sweeps.log): 64x64 is fastest with one group per CTA
+        // (four 64-thread CTAs per SM) and one shared FFT body, 32x32 with four single-warp groups and two FFT copies.
+        // `groups` / `rolled` select the alternatives kept for A/B runs.
         const bool aligned = ((e->wx - e->ox) & 15) == 0;
-#define ROWS_LAUNCH(RC, GG)                                                                                           \
-    return aligned ? (rolled ? launch_rows<RC, GG, true, true>(e, p, st) : launch_rows<RC, GG, false, true>(e, p, st))    \
-                   : (rolled ? launch_rows<RC, GG, true, false>(e, p, st) : launch_rows<RC, GG, false, false>(e, p, st))
-        if (e->wy == 64) {
-            if (e->groups == 4) { ROWS_LAUNCH(RCfg<64>, 4); }
-            if (e->groups == 2) { ROWS_LAUNCH(RCfg<64>, 2); }
-            ROWS_LAUNCH(RCfg<64>, 1);
+        if (e->dtype == B2PIV_F32) {
+            if (e->wy == 64) return launch_rows<RCfg<64>, 1, true, true, true>(e, p, st);
+            return launch_rows<RCfg<32>, 4, false, true, true>(e, p, st);
         }
-        if (e->groups == 1) { ROWS_LAUNCH(RCfg<32>, 1); }
-        if (e->groups == 12) { ROWS_LAUNCH(RCfg<32>, 12); }
-        ROWS_LAUNCH(RCfg<32>, 4);
-#undef ROWS_LAUNCH
+        if (e->wy == 64) {
+            if (e->groups == 4) return aligned ? launch_rows<RCfg<64>, 4, false, true, false>(e, p, st) : launch_rows<RCfg<64>, 4, false, false, false>(e, p, st);
+            if (e->rolled == 0) return aligned ? launch_rows<RCfg<64>, 1, false, true, false>(e, p, st) : launch_rows<RCfg<64>, 1, false, false, false>(e, p, st);
+            return aligned ? launch_rows<RCfg<64>, 1, true, true, false>(e, p, st) : launch_rows<RCfg<64>, 1, true, false, false>(e, p, st);
+        }
+        if (e->groups == 1) return aligned ? launch_rows<RCfg<32>, 1, false, true, false>(e, p, st) : launch_rows<RCfg<32>, 1, false, false, false>(e, p, st);
+        return aligned ? launch_rows<RCfg<32>, 4, false, true, false>(e, p, st) : launch_rows<RCfg<32>, 4, false, false, false>(e, p, st);
     }
     // sizes that are not a compiled FFT shape: tiny windows are cheapest by direct correlation, the rest run padded
     // through the FFT kernel; variant 3 forces the direct kernel

@@ -73,6 +73,11 @@ struct RCfg {
     // 16-byte boundary below and is 16 bytes wider, rows are read at a per-window byte offset, no swizzle
     static constexpr int WB = W + 16;
     static constexpr int TILE_U = 2 * W * WB;
+    // float32 frames: [W rows][128 B] boxes (32 floats, SWIZZLE_128B), W/32 boxes per window; a 64x64 window (16 KB)
+    // fills the transpose buffer, so its two windows arrive one after the other, a 32x32 pair (8 KB) together
+    static constexpr int FBOX = W * 128;                 // bytes per box
+    static constexpr int FWIN = (W / 32) * FBOX;         // bytes per window
+    static constexpr int F_PHASES = (W == 64) ? 2 : 1;   // TMA round trips per frame
     // Transposes move 32x32 blocks: block b (pitch 33 float2) is READ by warp b.  A 64x64 transpose first moves the
     // two off-diagonal blocks (one CTA barrier), then the diagonal ones (warp-synchronous), reusing the same two
     // blocks - half a plane - so a group needs ~52 KB of shared memory and FOUR groups (8 warps, two per
@@ -94,6 +99,8 @@ struct RSmem {
     B2_HD unsigned char* tile() { return reinterpret_cast<unsigned char*>(X); }
 };
 static_assert(sizeof(float2) * RCfg<64>::NWARP * RCfg<64>::XBLK >= RCfg<64>::TILE_U, "tile must fit in the transpose blocks");
+static_assert(sizeof(float2) * RCfg<64>::NWARP * RCfg<64>::XBLK >= RCfg<64>::FWIN, "float tile must fit in the transpose blocks");
+static_assert(sizeof(float2) * RCfg<32>::NWARP * RCfg<32>::XBLK >= 2 * RCfg<32>::FWIN, "float tiles must fit in the transpose blocks");
 static_assert(sizeof(float2) * RCfg<32>::NWARP * RCfg<32>::XBLK >= RCfg<32>::TILE_U, "tile must fit in the transpose blocks");
 
 struct RParams {
@@ -186,6 +193,8 @@ B2_HD unsigned dp4a_u(unsigned a, unsigned b, unsigned c) {
 #endif
 }
 
+B2_HD float bits_f32(unsigned u) { union { float f; unsigned u; } a; a.u = u; return a.f; }
+
 // byte b of a packed word as float
 B2_HD float byte_to_float(unsigned word, int b) {
     // one I2F with a byte selector: a single issue slot on the (otherwise idle) conversion pipe, cheaper here than the
@@ -230,6 +239,73 @@ B2_HD void rows_p1(RSmem<R>& s, RRegs<R>& r, int tid, int xoff0 = 0, int xoff1 =
 #else
     for (int k = 0; k < 4; ++k) s.red[tid >> 5][k] += vals[k];
 #endif
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// float32 frames.  F1(w): row of window w from its tile (at byte offset `toff`) into component w of r.v + row sum
+// (-> red[warp][2w]);  F2(w): mean from the block sum, centre, centred second moment (-> red[warp][2w+1]);
+// F3: 0.5/std of both windows, optional clip.  Two-pass moments like numpy's float path.
+// ------------------------------------------------------------------------------------------------------------
+B2_HD void red_put_f32(unsigned* cell, float v, int tid) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) *cell = __float_as_uint(v);
+#else
+    union { float f; unsigned u; } a;
+    a.u = *cell; a.f += v; *cell = a.u;
+#endif
+}
+template <class R>
+B2_HD void rows_f1(RSmem<R>& s, RRegs<R>& r, int tid, int w, int toff) {
+    constexpr int W = R::W;
+    const int row = column_of<W>(tid);
+    float sum = 0.f;
+#pragma unroll
+    for (int h = 0; h < W / 32; ++h) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 q = *reinterpret_cast<const float4*>(s.tile() + toff + h * R::FBOX + row * 128 + ((j ^ (row & 7)) << 4));
+            const float vals[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int x = 32 * h + 4 * j + k;
+                if (w == 0) r.v[x].x = vals[k]; else r.v[x].y = vals[k];
+                sum += vals[k];
+            }
+        }
+    }
+    red_put_f32(&s.red[tid >> 5][2 * w], sum, tid);
+}
+template <class R>
+B2_HD void rows_f2(RSmem<R>& s, RRegs<R>& r, int tid, int w) {
+    constexpr int W = R::W;
+    float S = 0.f;
+#pragma unroll
+    for (int k = 0; k < R::NWARP; ++k) S += bits_f32(s.red[k][2 * w]);
+    const float mean = S * (1.0f / (float)R::NPX);
+    float q = 0.f;
+#pragma unroll
+    for (int x = 0; x < W; ++x) {
+        if (w == 0) { r.v[x].x -= mean; q = fmaf(r.v[x].x, r.v[x].x, q); }
+        else        { r.v[x].y -= mean; q = fmaf(r.v[x].y, r.v[x].y, q); }
+    }
+    red_put_f32(&s.red[tid >> 5][2 * w + 1], q, tid);
+}
+template <class R>
+B2_HD void rows_f3(RSmem<R>& s, RRegs<R>& r, int tid, int clip_norm) {
+    constexpr int W = R::W;
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        float Q = 0.f;
+#pragma unroll
+        for (int k = 0; k < R::NWARP; ++k) Q += bits_f32(s.red[k][2 * w + 1]);
+        r.half_alpha_new[w] = Q > 0.f ? 0.5f * sqrtf((float)R::NPX) * (1.0f / sqrtf(Q)) : 0.f;   // 0.5 / sqrt(Q/N)
+    }
+    if (clip_norm) {
+#pragma unroll
+        for (int x = 0; x < W; ++x) r.v[x] = make_float2(fmaxf(r.v[x].x, 0.f), fmaxf(r.v[x].y, 0.f));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -95,7 +95,7 @@ static void emul_transpose(RSmem<R>& s, std::vector<RRegs<R>>& regs) {
     for (int t = 0; t < W; ++t) { const int wq = t >> 5; load(t, wq, wq); }
 }
 
-template <class R>
+template <class R, bool F32>
 static int run_rows(RParams p) {
     constexpr int W = R::W;
     RSmem<R>* sp = new RSmem<R>();
@@ -105,6 +105,7 @@ static int run_rows(RParams p) {
         const RUnit un = decode_unit(p, unit);
         for (int f = un.f0; f <= un.f1; ++f) {
             const bool have_prev = f > un.f0;
+            if (!F32) {
             // "TMA": fill the tile from frame f (swizzled exact boxes, or 16-byte wider boxes from the boundary below)
             const bool aligned = (p.sx % 16) == 0;
             int xoff[2] = {0, 0};
@@ -125,7 +126,32 @@ static int run_rows(RParams p) {
             }
             memset(s.red, 0, sizeof(s.red));
             for (int t = 0; t < W; ++t) { if (aligned) rows_p1<R, true>(s, regs[t], t); else rows_p1<R, false>(s, regs[t], t, xoff[0], xoff[1]); }
-            for (int t = 0; t < W; ++t) { rows_p2_pre<R>(s, regs[t], t, p.clip_norm); fft_reg<W, 0>(regs[t].v); }
+            for (int t = 0; t < W; ++t) rows_p2_pre<R>(s, regs[t], t, p.clip_norm);
+            } else {
+                // float32: 128-byte-wide boxes, SWIZZLE_128B; one window per TMA phase for 64x64, both for 32x32
+                auto fill = [&](int w, int toff) {
+                    for (int h = 0; h < W / 32; ++h)
+                        for (int row = 0; row < W; ++row)
+                            for (int j = 0; j < 8; ++j)
+                                memcpy(s.tile() + toff + h * R::FBOX + row * 128 + ((j ^ (row & 7)) << 4),
+                                       p.frames + (long long)f * p.frame_stride + (long long)(un.y0[w] + row) * p.pitch + 4 * (un.x0[w] + 32 * h + 4 * j), 16);
+                };
+                memset(s.red, 0, sizeof(s.red));
+                fill(0, 0);
+                if (R::F_PHASES == 1) fill(1, R::FWIN);
+                for (int t = 0; t < W; ++t) { rows_f1<R>(s, regs[t], t, 0, 0); if (R::F_PHASES == 1) rows_f1<R>(s, regs[t], t, 1, R::FWIN); }
+                if (R::F_PHASES == 2) {
+                    for (int t = 0; t < W; ++t) rows_f2<R>(s, regs[t], t, 0);
+                    fill(1, 0);
+                    for (int t = 0; t < W; ++t) rows_f1<R>(s, regs[t], t, 1, 0);
+                    for (int t = 0; t < W; ++t) rows_f2<R>(s, regs[t], t, 1);
+                } else {
+                    for (int t = 0; t < W; ++t) { rows_f2<R>(s, regs[t], t, 0); }
+                    for (int t = 0; t < W; ++t) { rows_f2<R>(s, regs[t], t, 1); }
+                }
+                for (int t = 0; t < W; ++t) rows_f3<R>(s, regs[t], t, p.clip_norm);
+            }
+            for (int t = 0; t < W; ++t) fft_reg<W, 0>(regs[t].v);
             emul_transpose<R, true>(s, regs);
             for (int t = 0; t < W; ++t) fft_reg<W, 0>(regs[t].v);
             snap = regs;
@@ -170,12 +196,11 @@ static int run_rows(RParams p) {
     return 0;
 }
 
-extern "C" int b2piv_emul_rows(const unsigned char* frames, int n_frames, int H, int W, int win, int ovl, int run_len, int clip_norm,
-                               int border_nan, float eps, const unsigned char* keep, float* u, float* v, float* cmax, float* s2n,
-                               float* planes) {
+static int emul_rows_any(const unsigned char* frames, int is_f32, int n_frames, int H, int W, int win, int ovl, int run_len, int clip_norm,
+                         int border_nan, float eps, const unsigned char* keep, float* u, float* v, float* cmax, float* s2n, float* planes) {
     RParams p;
     memset(&p, 0, sizeof(p));
-    p.frames = frames; p.pitch = W; p.frame_stride = (long long)H * W;
+    p.frames = frames; p.pitch = W * (is_f32 ? 4 : 1); p.frame_stride = (long long)H * p.pitch;
     p.n_rows = (H - win) / (win - ovl) + 1; p.n_cols = (W - win) / (win - ovl) + 1;
     p.sy = p.sx = win - ovl; p.n_pairs = n_frames - 1;
     p.run_len = run_len > 0 && run_len < p.n_pairs ? run_len : p.n_pairs;
@@ -183,9 +208,20 @@ extern "C" int b2piv_emul_rows(const unsigned char* frames, int n_frames, int H,
     p.n_units = ((nw + 1) / 2) * ((p.n_pairs + p.run_len - 1) / p.run_len);
     p.clip_norm = clip_norm; p.border_nan = border_nan; p.gauss_eps = eps; p.keep = keep;
     p.u = u; p.v = v; p.cmax = cmax; p.s2n = s2n; p.planes = planes;
-    if (win == 64) return run_rows<RCfg<64>>(p);
-    if (win == 32) return run_rows<RCfg<32>>(p);
+    if (win == 64) return is_f32 ? run_rows<RCfg<64>, true>(p) : run_rows<RCfg<64>, false>(p);
+    if (win == 32) return is_f32 ? run_rows<RCfg<32>, true>(p) : run_rows<RCfg<32>, false>(p);
     return -1;
+}
+extern "C" int b2piv_emul_rows(const unsigned char* frames, int n_frames, int H, int W, int win, int ovl, int run_len, int clip_norm,
+                               int border_nan, float eps, const unsigned char* keep, float* u, float* v, float* cmax, float* s2n,
+                               float* planes) {
+    return emul_rows_any(frames, 0, n_frames, H, W, win, ovl, run_len, clip_norm, border_nan, eps, keep, u, v, cmax, s2n, planes);
+}
+extern "C" int b2piv_emul_rows_f32(const float* frames, int n_frames, int H, int W, int win, int ovl, int run_len, int clip_norm,
+                                   int border_nan, float eps, const unsigned char* keep, float* u, float* v, float* cmax, float* s2n,
+                                   float* planes) {
+    return emul_rows_any((const unsigned char*)frames, 1, n_frames, H, W, win, ovl, run_len, clip_norm, border_nan, eps, keep, u, v, cmax,
+                         s2n, planes);
 }
 
 

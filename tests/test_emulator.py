@@ -67,7 +67,8 @@ def emul_rows():
         nr, nc = O.get_array_shape((H, W), (win, win), (ovl, ovl))
         outs = [np.full((n - 1, nr, nc), -7, np.float32) for _ in range(4)]
         planes = np.zeros((n - 1, nr * nc, win, win), np.float32)
-        rc = lib.b2piv_emul_rows(
+        fn = lib.b2piv_emul_rows_f32 if imgs.dtype == np.float32 else lib.b2piv_emul_rows
+        rc = fn(
             imgs.ctypes.data_as(ctypes.c_void_p), n, H, W, win, ovl, run_len, clip, border_nan, ctypes.c_float(1e-7), None,
             *[o.ctypes.data_as(ctypes.c_void_p) for o in outs], planes.ctypes.data_as(ctypes.c_void_p),
         )
@@ -178,3 +179,23 @@ def test_padded_fft_phases_match_oracle(emul, ws, ov, shape, dtype):
         ok = np.isfinite(u)
         assert np.abs(eu[ok] - u[ok]).max() < 1e-3 and np.abs(ev[ok] - v[ok]).max() < 1e-3
         assert np.abs(ec - c).max() < 3e-6
+
+
+@pytest.mark.parametrize("win,ovl,shape,run_len", [(64, 32, (4, 200, 304), 0), (32, 16, (4, 100, 160), 2), (64, 44, (3, 140, 164), 0), (32, 20, (3, 80, 112), 0)])
+def test_rows_phases_float32_frames(emul_rows, win, ovl, shape, run_len):
+    """float32 frames through the row-per-thread kernel: 128-byte swizzled boxes, two-pass moments, one window per TMA
+    phase for 64x64."""
+    O.CLIP_NORMALIZED = False
+    imgs = synth.particle_frames(*shape, dtype=np.float32)
+    imgs[:, :40, :52] = 0
+    imgs[1:] -= 0.25 * imgs[:-1]           # time_diff-like frames with negative values
+    ws, ov = (win, win), (ovl, ovl)
+    nr, nc = O.get_array_shape(shape[1:], ws, ov)
+    _, _, corr = O.cross_corr(imgs, ws, ov)
+    u, v, c, s = O.uv_timestep(imgs, nc, nr, ws, ov)
+    (eu, ev, ec, es), pl = emul_rows(imgs, win, ovl, run_len, 0)
+    assert np.abs(pl - corr).max() < 3e-6
+    assert np.array_equal(np.isnan(eu), np.isnan(u)) and np.array_equal(np.isnan(es), np.isnan(s))
+    ok = np.isfinite(u)
+    assert np.abs(eu[ok] - u[ok]).max() < 1e-3 and np.abs(ev[ok] - v[ok]).max() < 1e-3
+    assert np.abs(ec - c).max() < 3e-6

@@ -307,3 +307,14 @@ def test_ffpiv_api_cross_corr_and_u_v_displacement(engine):
     assert np.array_equal(np.isnan(u), np.isnan(ou))
     ok = np.isfinite(ou)
     assert np.abs(u[ok] - ou[ok]).max() <= 1e-4 and np.abs(v[ok] - ov_[ok]).max() <= 1e-4
+
+
+@pytest.mark.parametrize("ws,ov,shape,run_len", [((64, 64), (32, 32), (4, 270, 400), 0), ((32, 32), (16, 16), (5, 150, 208), 2),
+                                                 ((64, 64), (44, 44), (3, 160, 204), 0), ((32, 32), (24, 24), (3, 100, 144), 0)])
+def test_rows_kernel_float32_frames(engine, ws, ov, shape, run_len):
+    """float32 frames (pyorc's time_diff / smooth / edge_detect output) through the row-per-thread TMA kernel."""
+    imgs = synth.particle_frames(*shape, dtype=np.float32)
+    imgs[:, :40, :52] = 0
+    imgs[1:] -= 0.25 * imgs[:-1]
+    compare(engine, imgs, ws, ov, 0, variant=2, run_len=run_len)
+    engine.set_option("kernel_variant", 0.0)

@@ -45,6 +45,9 @@ if __name__ == "__main__":
             for g in (1, 4, 12):
                 run(1080, 1920, (32, 32), (16, 16), 41, variant=2, groups=g, rolled=rolled)
         run(1080, 1920, (32, 32), (24, 24), 11, variant=0)
+        run(1080, 1920, (64, 64), (32, 32), 51, variant=0, dtype="float32")
+        run(1080, 1920, (64, 64), (32, 32), 51, variant=1, dtype="float32")
+        run(1080, 1920, (32, 32), (16, 16), 41, variant=0, dtype="float32")
         run(1080, 1920, (10, 10), (5, 5), 5, variant=0)
         run(1080, 1920, (26, 26), (12, 12), 5, variant=0)
         run(1080, 1920, (50, 50), (25, 25), 3, variant=0)

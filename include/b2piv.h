@@ -86,6 +86,23 @@ int b2piv_ens_finish_host(b2piv_engine* e, float min_count, float* u, float* v, 
  * for callers that build their own planes (e.g. a mean plane).  u = column shift, v = row shift, [n_planes]. */
 int b2piv_peaks_host(b2piv_engine* e, const float* corr, long long n_planes, int wy, int wx, float* u, float* v);
 
+/* ---- Frame pre-processing on the device (the step before the path) --------------------------------
+ * Contiguous [n_frames][height][width] device buffers, dtype B2PIV_U8 or B2PIV_F32, stream-ordered.
+ *   normalize : pyorc Frames.normalize (pyorc/api/frames.py:279-306) -> uint8 [n][H][W]; the temporal mean uses every
+ *               `time_interval`-th frame (= round(n_frames / samples), frames.py:297)
+ *   time_diff : Frames.time_diff (frames.py:403-430) -> float32 [n-1][H][W]
+ *   minmax    : Frames.minmax (frames.py:343-361), element-wise clamp, same dtype out
+ *   gauss     : ksize1 == 0: Frames.smooth (frames.py:432-466, cv2.GaussianBlur(k2,k2,0));
+ *               ksize1 > 0: Frames.edge_detect (frames.py:308-341): blur(ksize2) - blur(ksize1); float32 out */
+int b2piv_pre_normalize_device(b2piv_engine* e, const void* d_frames, int dtype, int n_frames, int height, int width,
+                               int time_interval, unsigned char* d_out, void* cuda_stream);
+int b2piv_pre_time_diff_device(b2piv_engine* e, const void* d_frames, int dtype, int n_frames, int height, int width,
+                               float thres, int absolute, float* d_out, void* cuda_stream);
+int b2piv_pre_minmax_device(b2piv_engine* e, const void* d_in, int dtype, long long count, float lo, float hi, void* d_out,
+                            void* cuda_stream);
+int b2piv_pre_gauss_device(b2piv_engine* e, const void* d_frames, int dtype, int n_frames, int height, int width, int ksize1,
+                           int ksize2, float* d_out, void* cuda_stream);
+
 /* Page-locked host memory so H2D copies run at full PCIe rate without staging. */
 void* b2piv_host_alloc(size_t bytes);
 void b2piv_host_free(void* p);

@@ -7,6 +7,7 @@
 #include "piv_core.cuh"
 #include "piv_rows.cuh"
 #include "piv_direct.cuh"
+#include "preproc.cuh"
 
 #include <cuda.h>   // CUtensorMap (types only; the encoder is resolved at run time, libcuda is not linked)
 
@@ -471,6 +472,8 @@ struct b2piv_engine {
     float* d_planes = nullptr; size_t cap_planes = 0;
     unsigned char* d_keep = nullptr; size_t cap_keep = 0;
     // ensemble accumulators
+    float* d_pre_mean = nullptr; size_t cap_pre_mean = 0;   // pre-processing workspaces
+    unsigned* d_pre_mm = nullptr; size_t cap_pre_mm = 0;
     float* d_ens_sum = nullptr; float* d_ens_cnt = nullptr; size_t cap_ens = 0, cap_ens_windows = 0; bool ens_open = false;
     // stats
     float last_kernel_ms = 0.f;
@@ -802,7 +805,7 @@ void b2piv_destroy(b2piv_engine* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     cudaFree(e->d_twx); cudaFree(e->d_twy); cudaFree(e->d_frames); cudaFree(e->d_out); cudaFree(e->d_planes);
-    cudaFree(e->d_keep); cudaFree(e->d_ens_sum); cudaFree(e->d_ens_cnt);
+    cudaFree(e->d_keep); cudaFree(e->d_ens_sum); cudaFree(e->d_ens_cnt); cudaFree(e->d_pre_mean); cudaFree(e->d_pre_mm);
     for (auto ev : e->ev_chunk) cudaEventDestroy(ev);
     if (e->ev_k0) cudaEventDestroy(e->ev_k0);
     if (e->ev_k1) cudaEventDestroy(e->ev_k1);
@@ -1119,6 +1122,130 @@ int b2piv_peaks_host(b2piv_engine* e, const float* corr, long long n_planes, int
     CK(cudaMemcpyAsync(u, e->d_out, (size_t)n_planes * sizeof(float), cudaMemcpyDeviceToHost, e->s_comp));
     CK(cudaMemcpyAsync(v, e->d_out + n_planes, (size_t)n_planes * sizeof(float), cudaMemcpyDeviceToHost, e->s_comp));
     CK(cudaStreamSynchronize(e->s_comp));
+    return B2PIV_OK;
+}
+
+// ---- frame pre-processing on the device (kernels in preproc.cuh) -------------------------------------
+static int pre_grid(const b2piv_engine* e, long long n) {
+    long long g = (n + 255) / 256, cap = (long long)e->sm_count * 8;
+    return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+int b2piv_pre_normalize_device(b2piv_engine* e, const void* d_frames, int dtype, int n_frames, int height, int width, int time_interval,
+                               unsigned char* d_out, void* cuda_stream) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (!d_frames || !d_out) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
+    if (dtype != B2PIV_U8 && dtype != B2PIV_F32) return fail(e, B2PIV_ERR_ARG, "dtype must be B2PIV_U8 or B2PIV_F32");
+    if (n_frames < 1 || height < 1 || width < 1) return fail(e, B2PIV_ERR_ARG, "bad shape");
+    if (time_interval < 1) return fail(e, B2PIV_ERR_ARG, "time_interval must be >= 1 (too few frames for the requested samples)");
+    const int step_py = time_interval;
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const long long fe = (long long)height * width;
+    int rc = ensure(e, &e->d_pre_mean, &e->cap_pre_mean, (size_t)fe * sizeof(float));
+    if (rc) return rc;
+    rc = ensure(e, &e->d_pre_mm, &e->cap_pre_mm, (size_t)n_frames * 2 * sizeof(unsigned));
+    if (rc) return rc;
+    std::vector<unsigned> init((size_t)n_frames * 2);
+    for (int f = 0; f < n_frames; ++f) { init[2 * f] = 0xffffffffu; init[2 * f + 1] = 0u; }
+    CK(cudaMemcpyAsync(e->d_pre_mm, init.data(), init.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));   // `init` is a host temporary
+    const dim3 g1(pre_grid(e, fe)), g2(pre_grid(e, fe) / 4 + 1, n_frames);
+    if (dtype == B2PIV_U8) {
+        pre_mean_kernel<unsigned char><<<g1, 256, 0, st>>>((const unsigned char*)d_frames, fe, n_frames, step_py, e->d_pre_mean);
+        pre_minmax_kernel<unsigned char><<<g2, 256, 0, st>>>((const unsigned char*)d_frames, e->d_pre_mean, fe, e->d_pre_mm);
+        pre_normalize_kernel<unsigned char><<<g2, 256, 0, st>>>((const unsigned char*)d_frames, e->d_pre_mean, e->d_pre_mm, fe, d_out);
+    } else {
+        pre_mean_kernel<float><<<g1, 256, 0, st>>>((const float*)d_frames, fe, n_frames, step_py, e->d_pre_mean);
+        pre_minmax_kernel<float><<<g2, 256, 0, st>>>((const float*)d_frames, e->d_pre_mean, fe, e->d_pre_mm);
+        pre_normalize_kernel<float><<<g2, 256, 0, st>>>((const float*)d_frames, e->d_pre_mean, e->d_pre_mm, fe, d_out);
+    }
+    CK(cudaGetLastError());
+    e->launches += 3;
+    return B2PIV_OK;
+}
+
+int b2piv_pre_time_diff_device(b2piv_engine* e, const void* d_frames, int dtype, int n_frames, int height, int width, float thres,
+                               int absolute, float* d_out, void* cuda_stream) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (!d_frames || !d_out) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
+    if (dtype != B2PIV_U8 && dtype != B2PIV_F32) return fail(e, B2PIV_ERR_ARG, "dtype must be B2PIV_U8 or B2PIV_F32");
+    if (n_frames < 2) return fail(e, B2PIV_ERR_ARG, "need at least 2 frames");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const long long fe = (long long)height * width, n_out = fe * (n_frames - 1);
+    if (dtype == B2PIV_U8)
+        pre_time_diff_kernel<unsigned char><<<pre_grid(e, n_out), 256, 0, st>>>((const unsigned char*)d_frames, fe, n_out, thres, absolute, d_out);
+    else
+        pre_time_diff_kernel<float><<<pre_grid(e, n_out), 256, 0, st>>>((const float*)d_frames, fe, n_out, thres, absolute, d_out);
+    CK(cudaGetLastError());
+    e->launches++;
+    return B2PIV_OK;
+}
+
+int b2piv_pre_minmax_device(b2piv_engine* e, const void* d_in, int dtype, long long count, float lo, float hi, void* d_out,
+                            void* cuda_stream) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (!d_in || !d_out) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
+    if (dtype != B2PIV_U8 && dtype != B2PIV_F32) return fail(e, B2PIV_ERR_ARG, "dtype must be B2PIV_U8 or B2PIV_F32");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (dtype == B2PIV_U8) {
+        const float l = lo < 0.f ? 0.f : lo, h = hi > 255.f ? 255.f : hi;
+        pre_clamp_kernel<unsigned char><<<pre_grid(e, count), 256, 0, st>>>((const unsigned char*)d_in, count, l, h, (unsigned char*)d_out);
+    } else {
+        pre_clamp_kernel<float><<<pre_grid(e, count), 256, 0, st>>>((const float*)d_in, count, lo, hi, (float*)d_out);
+    }
+    CK(cudaGetLastError());
+    e->launches++;
+    return B2PIV_OK;
+}
+
+// OpenCV's getGaussianKernel(ksize, sigma <= 0, CV_32F): fixed dyadic tables up to 9 taps, exp(-x^2 / 2 sigma^2) normalised
+// with sigma = 0.3 * ((ksize - 1) / 2 - 1) + 0.8 beyond (checked against cv2 in tests/test_preprocess.py)
+static bool gauss_taps(int ksize, float* k) {
+    if (ksize < 1 || ksize > 2 * GB_MAXR + 1 || (ksize & 1) == 0) return false;
+    static const float t1[] = {1.f}, t3[] = {0.25f, 0.5f, 0.25f}, t5[] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f},
+                       t7[] = {0.03125f, 0.109375f, 0.21875f, 0.28125f, 0.21875f, 0.109375f, 0.03125f},
+                       t9[] = {4 / 256.f, 13 / 256.f, 30 / 256.f, 51 / 256.f, 60 / 256.f, 51 / 256.f, 30 / 256.f, 13 / 256.f, 4 / 256.f};
+    const float* tab = ksize == 1 ? t1 : ksize == 3 ? t3 : ksize == 5 ? t5 : ksize == 7 ? t7 : ksize == 9 ? t9 : nullptr;
+    if (tab) { for (int i = 0; i < ksize; ++i) k[i] = tab[i]; return true; }
+    const double sigma = 0.3 * ((ksize - 1) * 0.5 - 1.0) + 0.8;
+    double sum = 0.0;
+    std::vector<double> g(ksize);
+    for (int i = 0; i < ksize; ++i) { const double x = i - (ksize - 1) * 0.5; g[i] = exp(-x * x / (2.0 * sigma * sigma)); sum += g[i]; }
+    for (int i = 0; i < ksize; ++i) k[i] = (float)(g[i] / sum);
+    return true;
+}
+
+int b2piv_pre_gauss_device(b2piv_engine* e, const void* d_frames, int dtype, int n_frames, int height, int width, int ksize1, int ksize2,
+                           float* d_out, void* cuda_stream) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (!d_frames || !d_out) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
+    if (dtype != B2PIV_U8 && dtype != B2PIV_F32) return fail(e, B2PIV_ERR_ARG, "dtype must be B2PIV_U8 or B2PIV_F32");
+    GaussTaps taps;
+    memset(&taps, 0, sizeof(taps));
+    if (!gauss_taps(ksize2, taps.k2)) return fail(e, B2PIV_ERR_ARG, "kernel size must be odd and between 1 and 31");
+    taps.r2 = ksize2 / 2;
+    taps.r1 = -1;
+    if (ksize1 > 0) {
+        if (!gauss_taps(ksize1, taps.k1)) return fail(e, B2PIV_ERR_ARG, "kernel size must be odd and between 1 and 31");
+        taps.r1 = ksize1 / 2;
+    }
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int R = taps.r2 > taps.r1 ? taps.r2 : taps.r1;
+    const size_t smem = ((size_t)(GB_TY + 2 * R) * (GB_TX + 2 * R) + 2 * (size_t)(GB_TY + 2 * R) * GB_TX) * sizeof(float);
+    const dim3 grid((width + GB_TX - 1) / GB_TX, (height + GB_TY - 1) / GB_TY, n_frames), block(GB_TX, GB_TY);
+    if (dtype == B2PIV_U8) {
+        CK(cudaFuncSetAttribute(pre_gauss_kernel<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pre_gauss_kernel<unsigned char><<<grid, block, smem, st>>>((const unsigned char*)d_frames, height, width, taps, d_out);
+    } else {
+        CK(cudaFuncSetAttribute(pre_gauss_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pre_gauss_kernel<float><<<grid, block, smem, st>>>((const float*)d_frames, height, width, taps, d_out);
+    }
+    CK(cudaGetLastError());
+    e->launches++;
     return B2PIV_OK;
 }
 

@@ -354,14 +354,15 @@ B2_HD void phase_center(Smem<C>& s, int tid, const Params& p) {
 // the (>= 2n)-point plane.  In-region values are rewritten unchanged, so concurrent readers are safe.
 template <class C>
 B2_HD void phase_embed(Smem<C>& s, int tid, const Params& p) {
-    if (!C::PADDED) return;
+    if (C::PADDED) {
 #pragma unroll
-    for (int w = 0; w < C::NWIN; ++w) {
-        for (int e = tid; e < C::NPX; e += C::NT) {
-            const int y = e / C::WX, x = e % C::WX;
-            const float a = (y < p.ny && x < p.nx) ? s.plane[w][y * C::P + x].x : 0.f;
-            const float b = (y < 2 * p.ny && x < 2 * p.nx) ? s.plane[w][(y % p.ny) * C::P + (x % p.nx)].y : 0.f;
-            s.plane[w][y * C::P + x] = make_float2(a, b);
+        for (int w = 0; w < C::NWIN; ++w) {
+            for (int e = tid; e < C::NPX; e += C::NT) {
+                const int y = e / C::WX, x = e % C::WX;
+                const float a = (y < p.ny && x < p.nx) ? s.plane[w][y * C::P + x].x : 0.f;
+                const float b = (y < 2 * p.ny && x < 2 * p.nx) ? s.plane[w][(y % p.ny) * C::P + (x % p.nx)].y : 0.f;
+                s.plane[w][y * C::P + x] = make_float2(a, b);
+            }
         }
     }
 }

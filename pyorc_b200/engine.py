@@ -37,6 +37,10 @@ ABI_SYMBOLS = (
     "b2piv_ens_accum",
     "b2piv_ens_finish_host",
     "b2piv_peaks_host",
+    "b2piv_pre_normalize_device",
+    "b2piv_pre_time_diff_device",
+    "b2piv_pre_minmax_device",
+    "b2piv_pre_gauss_device",
     "b2piv_host_alloc",
     "b2piv_host_free",
     "b2piv_last_kernel_ms",
@@ -75,6 +79,10 @@ def load_library(path: Optional[str] = None):
     lib.b2piv_ens_accum.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(cll), ctypes.POINTER(cll)]
     lib.b2piv_ens_finish_host.argtypes = [vp, cf, vp, vp, vp]
     lib.b2piv_peaks_host.argtypes = [vp, vp, cll, ci, ci, vp, vp]
+    lib.b2piv_pre_normalize_device.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp]
+    lib.b2piv_pre_time_diff_device.argtypes = [vp, vp, ci, ci, ci, ci, cf, ci, vp, vp]
+    lib.b2piv_pre_minmax_device.argtypes = [vp, vp, ci, cll, cf, cf, vp, vp]
+    lib.b2piv_pre_gauss_device.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp, vp]
     lib.b2piv_host_alloc.argtypes = [ctypes.c_size_t]
     lib.b2piv_host_alloc.restype = vp
     lib.b2piv_host_free.argtypes = [vp]

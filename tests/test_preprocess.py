@@ -1,0 +1,95 @@
+"""Pre-processing filters: the GPU kernels against the numpy/OpenCV restatement of pyorc's own filter
+expressions.  normalize / minmax / time_diff are bit-exact (same IEEE float32 operation order); the Gaussian filters
+agree with cv2.GaussianBlur to float32 rounding."""
+import numpy as np
+import pytest
+
+from oracle import preprocess_oracle as P
+from pyorc_b200 import synth
+
+
+def test_oracle_gaussian_kernel_rule_matches_opencv():
+    """The tap rule restated in b2piv.cu (gauss_taps): dyadic tables up to 9 taps, sigma = 0.3*((k-1)/2-1)+0.8 beyond."""
+    import cv2
+
+    tabs = {1: [1.0], 3: [0.25, 0.5, 0.25], 5: [0.0625, 0.25, 0.375, 0.25, 0.0625],
+            7: [0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125],
+            9: [4 / 256, 13 / 256, 30 / 256, 51 / 256, 60 / 256, 51 / 256, 30 / 256, 13 / 256, 4 / 256]}
+    for k, t in tabs.items():
+        assert np.array_equal(cv2.getGaussianKernel(k, 0, cv2.CV_32F).ravel(), np.float32(t))
+    for k in (11, 13, 21, 31):
+        sigma = 0.3 * ((k - 1) * 0.5 - 1) + 0.8
+        x = np.arange(k) - (k - 1) / 2
+        g = np.exp(-x**2 / (2 * sigma**2))
+        assert np.abs(cv2.getGaussianKernel(k, 0, cv2.CV_32F).ravel() - g / g.sum()).max() < 1e-7
+
+
+def test_oracle_normalize_properties():
+    fr = synth.particle_frames(30, 40, 50, dtype=np.uint8)
+    out = P.normalize(fr, samples=15)
+    assert out.dtype == np.uint8 and out.shape == fr.shape
+    assert (out.reshape(30, -1).max(axis=1) == 255).all() and (out.reshape(30, -1).min(axis=1) == 0).all()
+    with pytest.raises(AssertionError):
+        P.normalize(fr[:5], samples=15)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32])
+def test_gpu_normalize_minmax_timediff_bit_exact(dtype):
+    from pyorc_b200 import preprocess as G
+
+    fr = synth.particle_frames(31, 120, 200, dtype=dtype)
+    fr[7] = fr[7, 0, 0]                                   # a flat frame: 0/0 -> uint8 0
+    if dtype == np.uint8:
+        assert np.array_equal(G.normalize(fr, samples=15), P.normalize(fr, samples=15))
+        assert np.array_equal(G.normalize(fr, samples=4), P.normalize(fr, samples=4))
+    else:
+        a, b = G.normalize(fr, samples=15), P.normalize(fr, samples=15)     # float mean: summation order differs by an ulp
+        assert (np.abs(a.astype(int) - b.astype(int)) <= 1).all() and (a != b).mean() < 1e-3
+    assert np.array_equal(G.minmax(fr, min=20, max=180), P.minmax(fr, min=20, max=180))
+    assert np.array_equal(G.minmax(fr, max=100), P.minmax(fr, max=100))
+    for thres, ab in ((0.0, False), (5.0, False), (2.0, True)):
+        assert np.array_equal(G.time_diff(fr, thres=thres, abs=ab), P.time_diff(fr, thres=thres, abs=ab))
+    with pytest.raises(AssertionError):
+        G.normalize(fr[:5], samples=15)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32])
+def test_gpu_gaussian_filters_match_opencv(dtype):
+    from pyorc_b200 import preprocess as G
+
+    fr = synth.particle_frames(3, 97, 131, dtype=dtype)   # odd sizes: partial tiles + reflect-101 borders
+    for wdw in (1, 2, 3, 5):
+        ref = P.smooth(fr, wdw)
+        got = G.smooth(fr, wdw)
+        assert got.dtype == np.float32 and np.abs(got - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+    for w1, w2 in ((1, 2), (2, 4), (1, 7)):
+        ref = P.edge_detect(fr, w1, w2)
+        got = G.edge_detect(fr, w1, w2)
+        assert np.abs(got - ref).max() <= 2e-4 * 255
+
+
+@pytest.mark.gpu
+def test_gpu_pipeline_stays_on_device_and_feeds_piv():
+    """normalize -> get_piv without leaving the device, against oracle filters + oracle PIV."""
+    import torch
+
+    from oracle import ffpiv_oracle as O
+    from pyorc_b200 import preprocess as G
+    from pyorc_b200.engine import get_engine
+
+    O.CLIP_NORMALIZED = False
+    fr = synth.particle_frames(16, 200, 304, dtype=np.uint8)
+    d = torch.from_numpy(fr).cuda()
+    dn = G.normalize(d, samples=15)
+    assert dn.is_cuda and dn.dtype == torch.uint8
+    eng = get_engine(0)
+    eng.set_option("clip_normalized", 0.0)
+    eng.set_option("kernel_variant", 0.0)
+    u, v, c, s = eng.pairs(dn, (64, 64), (32, 32))
+    ref_frames = P.normalize(fr, samples=15)
+    nr, nc = O.get_array_shape(fr.shape[1:], (64, 64), (32, 32))
+    ou, ov, oc, os_ = O.uv_timestep(ref_frames, nc, nr, (64, 64), (32, 32))
+    ok = np.isfinite(ou)
+    assert np.abs(u.cpu().numpy()[ok] - ou[ok]).max() <= 2e-3 and np.abs(c.cpu().numpy() - oc).max() <= 5e-6

@@ -103,6 +103,24 @@ int b2piv_pre_minmax_device(b2piv_engine* e, const void* d_in, int dtype, long l
 int b2piv_pre_gauss_device(b2piv_engine* e, const void* d_frames, int dtype, int n_frames, int height, int width, int ksize1,
                            int ksize2, float* d_out, void* cuda_stream);
 
+/* ---- Orthoprojection with index maps ----------------------------------------------------------------
+ * Replaces pyorc.project.img_to_ortho + _group_average (pyorc/project.py:19-53, :123-157) behind project_numpy
+ * (project.py:160-230).  The maps are the arrays CameraConfig.map_idx_img_ortho / map_mean_idx_img_ortho return
+ * (pyorc/api/cameraconfig.py:739-860), as int64:
+ *   nearest : out[idx_ortho[i]] = img[idx_img[i]], i < n_nearest (idx_ortho as POSITIONS, i.e. np.flatnonzero of the
+ *             reference's boolean mask)
+ *   mean    : out[uidx[g]] = float32 mean of img[src_idx[i]] over the samples with norm_idx[i] == g (accumulated in
+ *             ascending i like the reference); n_samples / n_groups may be 0 (reducer != "mean")
+ * Target pixels covered by neither map are 0.  `plan` merges the maps once per camera configuration; `device` projects
+ * contiguous [n_frames][height][width] frames to [n_frames][out_height][out_width], stream-ordered.  out_dtype is the
+ * input dtype (uint8: truncation, what Frames.project returns via output_dtypes=[da.dtype]) or B2PIV_F32 (the float
+ * means img_to_ortho itself returns). */
+int b2piv_project_plan(b2piv_engine* e, int height, int width, int out_height, int out_width, const long long* idx_img,
+                       const long long* idx_ortho, long long n_nearest, const long long* src_idx, const long long* norm_idx,
+                       long long n_samples, const long long* uidx, long long n_groups);
+int b2piv_project_device(b2piv_engine* e, const void* d_frames, int dtype, int n_frames, void* d_out, int out_dtype,
+                         void* cuda_stream);
+
 /* Page-locked host memory so H2D copies run at full PCIe rate without staging. */
 void* b2piv_host_alloc(size_t bytes);
 void b2piv_host_free(void* p);

@@ -8,6 +8,7 @@
 #include "piv_rows.cuh"
 #include "piv_direct.cuh"
 #include "preproc.cuh"
+#include "project.cuh"
 
 #include <cuda.h>   // CUtensorMap (types only; the encoder is resolved at run time, libcuda is not linked)
 
@@ -474,6 +475,10 @@ struct b2piv_engine {
     // ensemble accumulators
     float* d_pre_mean = nullptr; size_t cap_pre_mean = 0;   // pre-processing workspaces
     unsigned* d_pre_mm = nullptr; size_t cap_pre_mm = 0;
+    // orthoprojection plan (CSR gather lists, project.cuh)
+    int* d_proj_off = nullptr; size_t cap_proj_off = 0;
+    int* d_proj_src = nullptr; size_t cap_proj_src = 0;
+    int proj_h = 0, proj_w = 0, proj_out_h = 0, proj_out_w = 0; long long proj_samples = 0;
     float* d_ens_sum = nullptr; float* d_ens_cnt = nullptr; size_t cap_ens = 0, cap_ens_windows = 0; bool ens_open = false;
     // stats
     float last_kernel_ms = 0.f;
@@ -806,6 +811,7 @@ void b2piv_destroy(b2piv_engine* e) {
     cudaDeviceSynchronize();
     cudaFree(e->d_twx); cudaFree(e->d_twy); cudaFree(e->d_frames); cudaFree(e->d_out); cudaFree(e->d_planes);
     cudaFree(e->d_keep); cudaFree(e->d_ens_sum); cudaFree(e->d_ens_cnt); cudaFree(e->d_pre_mean); cudaFree(e->d_pre_mm);
+    cudaFree(e->d_proj_off); cudaFree(e->d_proj_src);
     for (auto ev : e->ev_chunk) cudaEventDestroy(ev);
     if (e->ev_k0) cudaEventDestroy(e->ev_k0);
     if (e->ev_k1) cudaEventDestroy(e->ev_k1);
@@ -1127,7 +1133,7 @@ int b2piv_peaks_host(b2piv_engine* e, const float* corr, long long n_planes, int
 
 // ---- frame pre-processing on the device (kernels in preproc.cuh) -------------------------------------
 static int pre_grid(const b2piv_engine* e, long long n) {
-    long long g = (n + 255) / 256, cap = (long long)e->sm_count * 8;
+    long long g = (n + 4095) / 4096, cap = (long long)e->sm_count * 8;   // 16 elements per thread and iteration
     return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
@@ -1146,11 +1152,9 @@ int b2piv_pre_normalize_device(b2piv_engine* e, const void* d_frames, int dtype,
     if (rc) return rc;
     rc = ensure(e, &e->d_pre_mm, &e->cap_pre_mm, (size_t)n_frames * 2 * sizeof(unsigned));
     if (rc) return rc;
-    std::vector<unsigned> init((size_t)n_frames * 2);
-    for (int f = 0; f < n_frames; ++f) { init[2 * f] = 0xffffffffu; init[2 * f + 1] = 0u; }
-    CK(cudaMemcpyAsync(e->d_pre_mm, init.data(), init.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));   // `init` is a host temporary
-    const dim3 g1(pre_grid(e, fe)), g2(pre_grid(e, fe) / 4 + 1, n_frames);
+    CK(cudaMemsetAsync(e->d_pre_mm, 0xff, (size_t)n_frames * sizeof(unsigned), st));
+    CK(cudaMemsetAsync(e->d_pre_mm + n_frames, 0x00, (size_t)n_frames * sizeof(unsigned), st));
+    const dim3 g1((unsigned)((fe / 4 + 255) / 256 < e->sm_count * 8 ? (fe / 4 + 255) / 256 : e->sm_count * 8)), g2(pre_grid(e, fe), n_frames);
     if (dtype == B2PIV_U8) {
         pre_mean_kernel<unsigned char><<<g1, 256, 0, st>>>((const unsigned char*)d_frames, fe, n_frames, step_py, e->d_pre_mean);
         pre_minmax_kernel<unsigned char><<<g2, 256, 0, st>>>((const unsigned char*)d_frames, e->d_pre_mean, fe, e->d_pre_mm);
@@ -1244,6 +1248,94 @@ int b2piv_pre_gauss_device(b2piv_engine* e, const void* d_frames, int dtype, int
         CK(cudaFuncSetAttribute(pre_gauss_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         pre_gauss_kernel<float><<<grid, block, smem, st>>>((const float*)d_frames, height, width, taps, d_out);
     }
+    CK(cudaGetLastError());
+    e->launches++;
+    return B2PIV_OK;
+}
+
+// ---- orthoprojection with index maps (kernel in project.cuh) -----------------------------------------
+// Merges the reference's two maps (nearest: out[idx_ortho[i]] = img[idx_img[i]], project.py:147-149; mean: group g =
+// samples i with norm_idx[i] == g, written to out[uidx[g]], project.py:150-154) into one CSR list per target pixel.
+// Later assignments win exactly as in the reference's sequential fancy-index stores.
+int b2piv_project_plan(b2piv_engine* e, int height, int width, int out_height, int out_width, const long long* idx_img,
+                       const long long* idx_ortho, long long n_nearest, const long long* src_idx, const long long* norm_idx,
+                       long long n_samples, const long long* uidx, long long n_groups) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (height < 1 || width < 1 || out_height < 1 || out_width < 1) return fail(e, B2PIV_ERR_ARG, "bad shape");
+    if (n_nearest < 0 || n_samples < 0 || n_groups < 0) return fail(e, B2PIV_ERR_ARG, "negative count");
+    if ((n_nearest && (!idx_img || !idx_ortho)) || (n_samples && (!src_idx || !norm_idx)) || (n_groups && !uidx))
+        return fail(e, B2PIV_ERR_ARG, "NULL index map");
+    const long long n_in = (long long)height * width, n_out = (long long)out_height * out_width;
+    if (n_in >= (1ll << 31) || n_out >= (1ll << 31) || n_nearest + n_samples >= (1ll << 31))
+        return fail(e, B2PIV_ERR_UNSUPPORTED, "index maps beyond 2^31 entries");
+    std::vector<int> nn((size_t)n_out, -1), grp((size_t)n_out, -1);
+    for (long long i = 0; i < n_nearest; ++i) {
+        if (idx_img[i] < 0 || idx_img[i] >= n_in) return fail(e, B2PIV_ERR_ARG, "idx_img out of range");
+        if (idx_ortho[i] < 0 || idx_ortho[i] >= n_out) return fail(e, B2PIV_ERR_ARG, "idx_ortho out of range");
+        nn[(size_t)idx_ortho[i]] = (int)idx_img[i];
+    }
+    for (long long g = 0; g < n_groups; ++g) {
+        if (uidx[g] < 0 || uidx[g] >= n_out) return fail(e, B2PIV_ERR_ARG, "uidx out of range");
+        grp[(size_t)uidx[g]] = (int)g;
+    }
+    std::vector<int> gcount((size_t)n_groups + 1, 0);
+    for (long long i = 0; i < n_samples; ++i) {
+        if (src_idx[i] < 0 || src_idx[i] >= n_in) return fail(e, B2PIV_ERR_ARG, "src_idx out of range");
+        if (norm_idx[i] < 0 || norm_idx[i] >= n_groups) return fail(e, B2PIV_ERR_ARG, "norm_idx out of range");
+        gcount[(size_t)norm_idx[i]]++;
+    }
+    for (long long g = 0; g < n_groups; ++g)
+        if (gcount[(size_t)g] == 0) return fail(e, B2PIV_ERR_ARG, "empty group in norm_idx (the reference would divide 0 by 0)");
+    // stable counting sort of the samples by group keeps the reference's accumulation order (ascending i)
+    std::vector<int> gstart((size_t)n_groups + 1, 0);
+    for (long long g = 0; g < n_groups; ++g) gstart[(size_t)g + 1] = gstart[(size_t)g] + gcount[(size_t)g];
+    std::vector<int> gsrc((size_t)n_samples), gpos(gstart.begin(), gstart.end());
+    for (long long i = 0; i < n_samples; ++i) gsrc[(size_t)gpos[(size_t)norm_idx[i]]++] = (int)src_idx[i];
+    std::vector<int> off((size_t)n_out + 1), src;
+    src.reserve((size_t)(n_nearest + n_samples));
+    for (long long j = 0; j < n_out; ++j) {
+        off[(size_t)j] = (int)src.size();
+        const int g = grp[(size_t)j];
+        if (g >= 0) src.insert(src.end(), gsrc.begin() + gstart[(size_t)g], gsrc.begin() + gstart[(size_t)g + 1]);
+        else if (nn[(size_t)j] >= 0) src.push_back(nn[(size_t)j]);
+    }
+    off[(size_t)n_out] = (int)src.size();
+    CK(cudaSetDevice(e->device));
+    int rc = ensure(e, &e->d_proj_off, &e->cap_proj_off, off.size() * sizeof(int));
+    if (rc) return rc;
+    rc = ensure(e, &e->d_proj_src, &e->cap_proj_src, (src.size() + 1) * sizeof(int));
+    if (rc) return rc;
+    CK(cudaMemcpy(e->d_proj_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (!src.empty()) CK(cudaMemcpy(e->d_proj_src, src.data(), src.size() * sizeof(int), cudaMemcpyHostToDevice));
+    e->proj_h = height; e->proj_w = width; e->proj_out_h = out_height; e->proj_out_w = out_width;
+    e->proj_samples = (long long)src.size();
+    return B2PIV_OK;
+}
+
+}  // extern "C"
+template <typename TI, typename TO>
+static void launch_project(const b2piv_engine* e, const void* d_frames, int n_frames, void* d_out, cudaStream_t st) {
+    constexpr int FR = 4;
+    const int n_out = e->proj_out_h * e->proj_out_w;
+    const dim3 grid((n_out + 255) / 256, (n_frames + FR - 1) / FR);
+    proj_gather_kernel<TI, TO, FR><<<grid, 256, 0, st>>>((const TI*)d_frames, (long long)e->proj_h * e->proj_w, n_frames, e->d_proj_off,
+                                                         e->d_proj_src, n_out, (TO*)d_out);
+}
+extern "C" {
+
+int b2piv_project_device(b2piv_engine* e, const void* d_frames, int dtype, int n_frames, void* d_out, int out_dtype, void* cuda_stream) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (!e->d_proj_off) return fail(e, B2PIV_ERR_STATE, "b2piv_project_plan has not been called");
+    if (!d_frames || !d_out) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
+    if (dtype != B2PIV_U8 && dtype != B2PIV_F32) return fail(e, B2PIV_ERR_ARG, "dtype must be B2PIV_U8 or B2PIV_F32");
+    if (out_dtype != B2PIV_F32 && out_dtype != dtype) return fail(e, B2PIV_ERR_ARG, "out_dtype must be the input dtype or B2PIV_F32");
+    if (n_frames < 1) return fail(e, B2PIV_ERR_ARG, "need at least 1 frame");
+    if ((n_frames + 3) / 4 > 65535) return fail(e, B2PIV_ERR_UNSUPPORTED, "more than 262140 frames per call");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (dtype == B2PIV_U8 && out_dtype == B2PIV_U8) launch_project<unsigned char, unsigned char>(e, d_frames, n_frames, d_out, st);
+    else if (dtype == B2PIV_U8) launch_project<unsigned char, float>(e, d_frames, n_frames, d_out, st);
+    else launch_project<float, float>(e, d_frames, n_frames, d_out, st);
     CK(cudaGetLastError());
     e->launches++;
     return B2PIV_OK;

@@ -14,34 +14,30 @@
 
 namespace b2piv {
 
-// 16 consecutive elements per thread and iteration (one 16-byte load for uint8, four for float32): every kernel below
-// is a pure stream, so the only things that matter are wide coalesced accesses and enough of them in flight.
-template <typename T> struct Vec16;
-template <> struct Vec16<unsigned char> {
+// Four consecutive elements per thread and access (one 4-byte load for uint8, one 16-byte load for float32, so that a
+// warp instruction always covers one contiguous 128- / 512-byte span on BOTH sides of a mixed uint8 / float32 kernel),
+// PRE_U independent accesses in flight per thread: every kernel below is a pure stream, so the only things that
+// matter are coalescing and enough bytes in flight (a first version with 16 elements = 64 contiguous float bytes per
+// thread ran at a quarter of this: lanes 64 B apart use half of each 32-byte sector per instruction).
+constexpr int PRE_U = 4;
+template <typename T> struct Vec4;
+template <> struct Vec4<unsigned char> {
     static __device__ __forceinline__ void load(const unsigned char* p, float* v) {
-        const uint4 q = *reinterpret_cast<const uint4*>(p);
-        const unsigned w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = (float)((w[i >> 2] >> (8 * (i & 3))) & 0xffu);
+        const uchar4 q = *reinterpret_cast<const uchar4*>(p);
+        v[0] = (float)q.x; v[1] = (float)q.y; v[2] = (float)q.z; v[3] = (float)q.w;
     }
     static __device__ __forceinline__ void store(unsigned char* p, const float* v) {   // values already in [0, 255]
-        unsigned w[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int i = 0; i < 16; ++i) w[i >> 2] |= ((unsigned)(int)v[i] & 0xffu) << (8 * (i & 3));
-        *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uchar4*>(p) = make_uchar4((unsigned char)(int)v[0], (unsigned char)(int)v[1], (unsigned char)(int)v[2],
+                                                    (unsigned char)(int)v[3]);
     }
 };
-template <> struct Vec16<float> {
+template <> struct Vec4<float> {
     static __device__ __forceinline__ void load(const float* p, float* v) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 q = reinterpret_cast<const float4*>(p)[j];
-            v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
-        }
+        const float4 q = *reinterpret_cast<const float4*>(p);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
     }
     static __device__ __forceinline__ void store(float* p, const float* v) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(p)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     }
 };
 __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -55,21 +51,29 @@ __global__ void __launch_bounds__(256) pre_mean_kernel(const T* __restrict__ fra
     const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int cnt = 0;
     for (int f = 0; f < n_frames; f += step) ++cnt;
-    const long long nv = (aligned16(frames) && aligned16(mean) && frame_elems % 16 == 0) ? frame_elems : 0;
-    for (long long i = t0 * 16; i < nv; i += stride * 16) {
-        double acc[16];
+    const long long nv = (aligned16(frames) && aligned16(mean) && frame_elems % 4 == 0) ? frame_elems : 0;
+    for (long long i = t0 * 4; i < nv; i += stride * 4) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        int f = 0;
+        for (; f + (PRE_U - 1) * step < n_frames; f += PRE_U * step) {
+            float a[PRE_U][4];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) acc[k] = 0.0;
-        for (int f = 0; f < n_frames; f += step) {
-            float a[16];
-            Vec16<T>::load(frames + (long long)f * frame_elems + i, a);
+            for (int u = 0; u < PRE_U; ++u) Vec4<T>::load(frames + (long long)(f + u * step) * frame_elems + i, a[u]);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) acc[k] += (double)a[k];
+            for (int u = 0; u < PRE_U; ++u)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[k] += (double)a[u][k];
         }
-        float m[16];
+        for (; f < n_frames; f += step) {
+            float a[4];
+            Vec4<T>::load(frames + (long long)f * frame_elems + i, a);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) m[k] = (float)(acc[k] / (double)cnt);
-        Vec16<float>::store(mean + i, m);
+            for (int k = 0; k < 4; ++k) acc[k] += (double)a[k];
+        }
+        float m[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m[k] = (float)(acc[k] / (double)cnt);
+        Vec4<float>::store(mean + i, m);
     }
     for (long long i = nv + t0; i < frame_elems; i += stride) {
         double acc = 0.0;
@@ -87,7 +91,8 @@ __device__ __forceinline__ float ord2f(unsigned o) {
     return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
 }
 
-// K2: per-frame min / max of (float32(frame) - mean); minmax[2f] = ordered min, [2f+1] = ordered max
+// K2: per-frame min / max of (float32(frame) - mean); minmax[f] = ordered min, minmax[n_frames + f] = ordered max
+// (so that two cudaMemsetAsync calls initialise them: 0xff.. for the minima, 0 for the maxima)
 template <typename T>
 __global__ void __launch_bounds__(256) pre_minmax_kernel(const T* __restrict__ frames, const float* __restrict__ mean, long long frame_elems,
                                                          unsigned* __restrict__ minmax) {
@@ -95,14 +100,21 @@ __global__ void __launch_bounds__(256) pre_minmax_kernel(const T* __restrict__ f
     const T* fr = frames + (long long)f * frame_elems;
     float mn = INFINITY, mx = -INFINITY;
     const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool vec = aligned16(fr) && aligned16(mean) && (frame_elems % 16 == 0);
+    const bool vec = aligned16(fr) && aligned16(mean) && (frame_elems % 4 == 0);
     if (vec) {
-        for (long long i = t0 * 16; i < frame_elems; i += stride * 16) {
-            float a[16], m[16];
-            Vec16<T>::load(fr + i, a);
-            Vec16<float>::load(mean + i, m);
+        for (long long i = t0 * 4; i < frame_elems; i += stride * 4 * PRE_U) {
+            float a[PRE_U][4], m[PRE_U][4];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) { const float d = __fsub_rn(a[k], m[k]); mn = fminf(mn, d); mx = fmaxf(mx, d); }
+            for (int u = 0; u < PRE_U; ++u) {
+                const long long ii = i + u * stride * 4;
+                if (ii < frame_elems) { Vec4<T>::load(fr + ii, a[u]); Vec4<float>::load(mean + ii, m[u]); }
+            }
+#pragma unroll
+            for (int u = 0; u < PRE_U; ++u)
+                if (i + u * stride * 4 < frame_elems) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { const float d = __fsub_rn(a[u][k], m[u][k]); mn = fminf(mn, d); mx = fmaxf(mx, d); }
+                }
         }
     } else {
         for (long long i = t0; i < frame_elems; i += stride) {
@@ -115,9 +127,14 @@ __global__ void __launch_bounds__(256) pre_minmax_kernel(const T* __restrict__ f
         mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicMin(&minmax[2 * f], f2ord(mn));
-        atomicMax(&minmax[2 * f + 1], f2ord(mx));
+    __shared__ float smn[8], smx[8];
+    if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) { mn = fminf(mn, smn[w]); mx = fmaxf(mx, smx[w]); }
+        atomicMin(&minmax[f], f2ord(mn));                 // layout [min of every frame | max of every frame]
+        atomicMax(&minmax[gridDim.y + f], f2ord(mx));
     }
 }
 
@@ -129,21 +146,30 @@ __global__ void __launch_bounds__(256) pre_normalize_kernel(const T* __restrict_
     const int f = blockIdx.y;
     const T* fr = frames + (long long)f * frame_elems;
     unsigned char* o = out + (long long)f * frame_elems;
-    const float mn = ord2f(minmax[2 * f]), mx = ord2f(minmax[2 * f + 1]);
+    const float mn = ord2f(minmax[f]), mx = ord2f(minmax[gridDim.y + f]);
     const float range = __fsub_rn(mx, mn);
     const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool vec = aligned16(fr) && aligned16(mean) && aligned16(o) && (frame_elems % 16 == 0);
+    const bool vec = aligned16(fr) && aligned16(mean) && aligned16(o) && (frame_elems % 4 == 0);
     if (vec) {
-        for (long long i = t0 * 16; i < frame_elems; i += stride * 16) {
-            float a[16], m[16];
-            Vec16<T>::load(fr + i, a);
-            Vec16<float>::load(mean + i, m);
+        for (long long i = t0 * 4; i < frame_elems; i += stride * 4 * PRE_U) {
+            float a[PRE_U][4], m[PRE_U][4];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const float v = __fmul_rn(__fdiv_rn(__fsub_rn(__fsub_rn(a[k], m[k]), mn), range), 255.0f);
-                a[k] = (v >= 0.f && v < 256.f) ? v : 0.f;
+            for (int u = 0; u < PRE_U; ++u) {
+                const long long ii = i + u * stride * 4;
+                if (ii < frame_elems) { Vec4<T>::load(fr + ii, a[u]); Vec4<float>::load(mean + ii, m[u]); }
             }
-            Vec16<unsigned char>::store(o + i, a);
+#pragma unroll
+            for (int u = 0; u < PRE_U; ++u) {
+                const long long ii = i + u * stride * 4;
+                if (ii < frame_elems) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float v = __fmul_rn(__fdiv_rn(__fsub_rn(__fsub_rn(a[u][k], m[u][k]), mn), range), 255.0f);
+                        a[u][k] = (v >= 0.f && v < 256.f) ? v : 0.f;   // NaN (flat frame) -> 0
+                    }
+                    Vec4<unsigned char>::store(o + ii, a[u]);
+                }
+            }
         }
     } else {
         for (long long i = t0; i < frame_elems; i += stride) {
@@ -159,24 +185,33 @@ template <typename T>
 __global__ void __launch_bounds__(256) pre_time_diff_kernel(const T* __restrict__ frames, long long frame_elems, long long n_out, float thres,
                                                             int absolute, float* __restrict__ out) {
     const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool vec = aligned16(frames) && aligned16(out) && (frame_elems % 16 == 0);
+    const bool vec = aligned16(frames) && aligned16(out) && (frame_elems % 4 == 0);
     if (vec) {
-        for (long long i = t0 * 16; i < n_out; i += stride * 16) {
-            float a[16], b[16];
-            Vec16<T>::load(frames + i, a);
-            Vec16<T>::load(frames + i + frame_elems, b);
+        for (long long i = t0 * 4; i < n_out; i += stride * 4 * PRE_U) {
+            float a[PRE_U][4], b[PRE_U][4];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const float d = __fsub_rn(b[k], a[k]);
-                float v = d > thres ? d : 0.f;
-                a[k] = absolute ? fabsf(v) : v;
+            for (int u = 0; u < PRE_U; ++u) {
+                const long long ii = i + u * stride * 4;
+                if (ii < n_out) { Vec4<T>::load(frames + ii, a[u]); Vec4<T>::load(frames + ii + frame_elems, b[u]); }
             }
-            Vec16<float>::store(out + i, a);
+#pragma unroll
+            for (int u = 0; u < PRE_U; ++u) {
+                const long long ii = i + u * stride * 4;
+                if (ii < n_out) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float d = __fsub_rn(b[u][k], a[u][k]);
+                        const float v = d > thres ? d : 0.f;   // where(diff > thres) ... fillna(0.0); NaN compares false -> 0
+                        a[u][k] = absolute ? fabsf(v) : v;
+                    }
+                    Vec4<float>::store(out + ii, a[u]);
+                }
+            }
         }
     } else {
         for (long long i = t0; i < n_out; i += stride) {
             const float d = __fsub_rn((float)frames[i + frame_elems], (float)frames[i]);
-            float v = d > thres ? d : 0.f;     // where(diff > thres) ... fillna(0.0); NaN compares false -> 0
+            float v = d > thres ? d : 0.f;
             if (absolute) v = fabsf(v);
             out[i] = v;
         }
@@ -185,17 +220,27 @@ __global__ void __launch_bounds__(256) pre_time_diff_kernel(const T* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(256) pre_clamp_kernel(const T* __restrict__ in, long long n, float lo, float hi, T* __restrict__ out) {
     const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long nv = (aligned16(in) && aligned16(out)) ? (n / 16) * 16 : 0;
-    for (long long i = t0 * 16; i < nv; i += stride * 16) {
-        float a[16];
-        Vec16<T>::load(in + i, a);
+    const long long nv = (aligned16(in) && aligned16(out)) ? (n / 4) * 4 : 0;
+    for (long long i = t0 * 4; i < nv; i += stride * 4 * PRE_U) {
+        float a[PRE_U][4];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) a[k] = fmaxf(fminf(a[k], hi), lo);
-        Vec16<T>::store(out + i, a);
+        for (int u = 0; u < PRE_U; ++u) {
+            const long long ii = i + u * stride * 4;
+            if (ii < nv) Vec4<T>::load(in + ii, a[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < PRE_U; ++u) {
+            const long long ii = i + u * stride * 4;
+            if (ii < nv) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) a[u][k] = fmaxf(fminf(a[u][k], hi), lo);   // np.maximum(np.minimum(x, max), min)
+                Vec4<T>::store(out + ii, a[u]);
+            }
+        }
     }
     for (long long i = nv + t0; i < n; i += stride) {
         const float x = (float)in[i];
-        out[i] = (T)fmaxf(fminf(x, hi), lo);   // np.maximum(np.minimum(x, max), min)
+        out[i] = (T)fmaxf(fminf(x, hi), lo);
     }
 }
 

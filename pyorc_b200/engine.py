@@ -41,6 +41,8 @@ ABI_SYMBOLS = (
     "b2piv_pre_time_diff_device",
     "b2piv_pre_minmax_device",
     "b2piv_pre_gauss_device",
+    "b2piv_project_plan",
+    "b2piv_project_device",
     "b2piv_host_alloc",
     "b2piv_host_free",
     "b2piv_last_kernel_ms",
@@ -83,6 +85,8 @@ def load_library(path: Optional[str] = None):
     lib.b2piv_pre_time_diff_device.argtypes = [vp, vp, ci, ci, ci, ci, cf, ci, vp, vp]
     lib.b2piv_pre_minmax_device.argtypes = [vp, vp, ci, cll, cf, cf, vp, vp]
     lib.b2piv_pre_gauss_device.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp, vp]
+    lib.b2piv_project_plan.argtypes = [vp, ci, ci, ci, ci, vp, vp, cll, vp, vp, cll, vp, cll]
+    lib.b2piv_project_device.argtypes = [vp, vp, ci, ci, vp, ci, vp]
     lib.b2piv_host_alloc.argtypes = [ctypes.c_size_t]
     lib.b2piv_host_alloc.restype = vp
     lib.b2piv_host_free.argtypes = [vp]

@@ -23,6 +23,7 @@ import numpy as np
 
 REF = "/root/reference"
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ngwerere_proj.npz")
+OUT_MAPS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ngwerere_maps.npz")
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -210,6 +211,27 @@ def main():
         source="pyorc @ be7d7c8 tests/test_frames.py:139-153; generated by tests/golden/make_ngwerere_golden.py",
     )
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
+    # ---- second fixture: the index maps themselves + the raw frame 0, so that the orthoprojection can be
+    # checked against the reference's own img_to_ortho output.  Maps are delta-coded int32 (np.cumsum restores them); the
+    # raw frame is cropped to the bounding box of every referenced source pixel (the rest is never read).
+    allsrc = np.concatenate([idx_img, src_idx])
+    r, c = allsrc // cc.width, allsrc % cc.width
+    r0, r1, c0, c1 = int(r.min()), int(r.max()) + 1, int(c.min()), int(c.max()) + 1
+
+    def delta(a):
+        return np.diff(np.asarray(a, dtype=np.int64), prepend=0).astype(np.int32)
+
+    ref0 = project.img_to_ortho(imgs[0], x, y, idx_img, idx_ortho, src_idx, uidx, norm_idx)   # float64 holding float32 means
+    assert np.array_equal(ref0.astype(np.float32).astype(np.float64), ref0)
+    assert np.array_equal(np.nan_to_num(ref0, nan=0.0).astype(np.uint8), proj[0])
+    np.savez_compressed(
+        OUT_MAPS, img_shape=np.array([cc.height, cc.width]), ortho_shape=np.array(shape), crop=np.array([r0, r1, c0, c1]),
+        raw0_crop=imgs[0][r0:r1, c0:c1], d_idx_img=delta(idx_img), idx_ortho_bits=np.packbits(idx_ortho), n_ortho=idx_ortho.size,
+        d_src_idx=delta(src_idx), d_uidx=delta(uidx), d_norm_idx=delta(norm_idx), ref0_f32=ref0.astype(np.float32),
+        source="pyorc @ be7d7c8 CameraConfig.map_idx_img_ortho / map_mean_idx_img_ortho / project.img_to_ortho on "
+               "examples/ngwerere frame 0; generated by tests/golden/make_ngwerere_golden.py",
+    )
+    print("wrote", OUT_MAPS, os.path.getsize(OUT_MAPS), "bytes; nearest", idx_img.size, "samples", src_idx.size, "groups", uidx.size)
 
 
 if __name__ == "__main__":

@@ -34,11 +34,12 @@ def test_oracle_normalize_properties():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(120, 200), (121, 203)])     # vector path / scalar path (frame size not a multiple of 4)
 @pytest.mark.parametrize("dtype", [np.uint8, np.float32])
-def test_gpu_normalize_minmax_timediff_bit_exact(dtype):
+def test_gpu_normalize_minmax_timediff_bit_exact(dtype, shape):
     from pyorc_b200 import preprocess as G
 
-    fr = synth.particle_frames(31, 120, 200, dtype=dtype)
+    fr = synth.particle_frames(31, shape[0], shape[1], dtype=dtype)
     fr[7] = fr[7, 0, 0]                                   # a flat frame: 0/0 -> uint8 0
     if dtype == np.uint8:
         assert np.array_equal(G.normalize(fr, samples=15), P.normalize(fr, samples=15))

@@ -1154,15 +1154,17 @@ int b2piv_pre_normalize_device(b2piv_engine* e, const void* d_frames, int dtype,
     if (rc) return rc;
     CK(cudaMemsetAsync(e->d_pre_mm, 0xff, (size_t)n_frames * sizeof(unsigned), st));
     CK(cudaMemsetAsync(e->d_pre_mm + n_frames, 0x00, (size_t)n_frames * sizeof(unsigned), st));
-    const dim3 g1((unsigned)((fe / 4 + 255) / 256 < e->sm_count * 8 ? (fe / 4 + 255) / 256 : e->sm_count * 8)), g2(pre_grid(e, fe), n_frames);
+    long long gx = (fe / 4 + 255) / 256;   // 4 pixels per thread and grid-stride iteration
+    gx = gx < 1 ? 1 : (gx > (long long)e->sm_count * 8 ? (long long)e->sm_count * 8 : gx);
+    const dim3 g1((unsigned)gx), g2((unsigned)gx, (n_frames + PRE_FPB - 1) / PRE_FPB);
     if (dtype == B2PIV_U8) {
         pre_mean_kernel<unsigned char><<<g1, 256, 0, st>>>((const unsigned char*)d_frames, fe, n_frames, step_py, e->d_pre_mean);
-        pre_minmax_kernel<unsigned char><<<g2, 256, 0, st>>>((const unsigned char*)d_frames, e->d_pre_mean, fe, e->d_pre_mm);
-        pre_normalize_kernel<unsigned char><<<g2, 256, 0, st>>>((const unsigned char*)d_frames, e->d_pre_mean, e->d_pre_mm, fe, d_out);
+        pre_minmax_kernel<unsigned char><<<g2, 256, 0, st>>>((const unsigned char*)d_frames, e->d_pre_mean, fe, n_frames, e->d_pre_mm);
+        pre_normalize_kernel<unsigned char><<<g2, 256, 0, st>>>((const unsigned char*)d_frames, e->d_pre_mean, e->d_pre_mm, fe, n_frames, d_out);
     } else {
         pre_mean_kernel<float><<<g1, 256, 0, st>>>((const float*)d_frames, fe, n_frames, step_py, e->d_pre_mean);
-        pre_minmax_kernel<float><<<g2, 256, 0, st>>>((const float*)d_frames, e->d_pre_mean, fe, e->d_pre_mm);
-        pre_normalize_kernel<float><<<g2, 256, 0, st>>>((const float*)d_frames, e->d_pre_mean, e->d_pre_mm, fe, d_out);
+        pre_minmax_kernel<float><<<g2, 256, 0, st>>>((const float*)d_frames, e->d_pre_mean, fe, n_frames, e->d_pre_mm);
+        pre_normalize_kernel<float><<<g2, 256, 0, st>>>((const float*)d_frames, e->d_pre_mean, e->d_pre_mm, fe, n_frames, d_out);
     }
     CK(cudaGetLastError());
     e->launches += 3;
@@ -1238,15 +1240,30 @@ int b2piv_pre_gauss_device(b2piv_engine* e, const void* d_frames, int dtype, int
     }
     CK(cudaSetDevice(e->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    const int R = taps.r2 > taps.r1 ? taps.r2 : taps.r1;
-    const size_t smem = ((size_t)(GB_TY + 2 * R) * (GB_TX + 2 * R) + 2 * (size_t)(GB_TY + 2 * R) * GB_TX) * sizeof(float);
-    const dim3 grid((width + GB_TX - 1) / GB_TX, (height + GB_TY - 1) / GB_TY, n_frames), block(GB_TX, GB_TY);
-    if (dtype == B2PIV_U8) {
-        CK(cudaFuncSetAttribute(pre_gauss_kernel<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        pre_gauss_kernel<unsigned char><<<grid, block, smem, st>>>((const unsigned char*)d_frames, height, width, taps, d_out);
-    } else {
-        CK(cudaFuncSetAttribute(pre_gauss_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        pre_gauss_kernel<float><<<grid, block, smem, st>>>((const float*)d_frames, height, width, taps, d_out);
+    const dim3 sgrid((width + GS_BW - 1) / GS_BW, (height + GS_SH - 1) / GS_SH, n_frames);
+    const int rmax = taps.r2 > taps.r1 ? taps.r2 : taps.r1;
+    bool fast = height > rmax && width > rmax && sgrid.y <= 65535 && sgrid.z <= 65535;   // one reflection suffices
+    if (fast) {
+#define B2_GAUSS_CASE(A, B)                                                                                                      \
+    if (taps.r1 == (A) && taps.r2 == (B)) {                                                                                      \
+        if (dtype == B2PIV_U8) pre_gauss_strip_kernel<unsigned char, A, B><<<sgrid, GS_BW, 0, st>>>((const unsigned char*)d_frames, height, width, taps, d_out); \
+        else pre_gauss_strip_kernel<float, A, B><<<sgrid, GS_BW, 0, st>>>((const float*)d_frames, height, width, taps, d_out);   \
+    } else
+        B2_GAUSS_CASE(-1, 1) B2_GAUSS_CASE(-1, 2) B2_GAUSS_CASE(-1, 3) B2_GAUSS_CASE(1, 2) B2_GAUSS_CASE(1, 3) B2_GAUSS_CASE(2, 4)
+        fast = false;
+#undef B2_GAUSS_CASE
+    }
+    if (!fast) {
+        const int R = taps.r2 > taps.r1 ? taps.r2 : taps.r1;
+        const size_t smem = ((size_t)(GB_TY + 2 * R) * (GB_TX + 2 * R) + 2 * (size_t)(GB_TY + 2 * R) * GB_TX) * sizeof(float);
+        const dim3 grid((width + GB_TX - 1) / GB_TX, (height + GB_TY - 1) / GB_TY, n_frames), block(GB_TX, GB_TY);
+        if (dtype == B2PIV_U8) {
+            CK(cudaFuncSetAttribute(pre_gauss_kernel<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            pre_gauss_kernel<unsigned char><<<grid, block, smem, st>>>((const unsigned char*)d_frames, height, width, taps, d_out);
+        } else {
+            CK(cudaFuncSetAttribute(pre_gauss_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            pre_gauss_kernel<float><<<grid, block, smem, st>>>((const float*)d_frames, height, width, taps, d_out);
+        }
     }
     CK(cudaGetLastError());
     e->launches++;

@@ -92,90 +92,109 @@ __device__ __forceinline__ float ord2f(unsigned o) {
 }
 
 // K2: per-frame min / max of (float32(frame) - mean); minmax[f] = ordered min, minmax[n_frames + f] = ordered max
-// (so that two cudaMemsetAsync calls initialise them: 0xff.. for the minima, 0 for the maxima)
+// (so that two cudaMemsetAsync calls initialise them: 0xff.. for the minima, 0 for the maxima).
+// A block covers PRE_FPB consecutive frames (blockIdx.y) so that the float32 mean - 4x the bytes of a uint8 frame - is
+// loaded once per PRE_FPB frames instead of once per frame (per-frame blocks ran at the L2 rate of the mean, 1.5 TB/s).
+constexpr int PRE_FPB = 8;
 template <typename T>
 __global__ void __launch_bounds__(256) pre_minmax_kernel(const T* __restrict__ frames, const float* __restrict__ mean, long long frame_elems,
-                                                         unsigned* __restrict__ minmax) {
-    const int f = blockIdx.y;
-    const T* fr = frames + (long long)f * frame_elems;
-    float mn = INFINITY, mx = -INFINITY;
+                                                         int n_frames, unsigned* __restrict__ minmax) {
+    const int f0 = blockIdx.y * PRE_FPB;
+    const int nf = n_frames - f0 < PRE_FPB ? n_frames - f0 : PRE_FPB;
+    const T* fr = frames + (long long)f0 * frame_elems;
+    float mn[PRE_FPB], mx[PRE_FPB];
+#pragma unroll
+    for (int k = 0; k < PRE_FPB; ++k) { mn[k] = INFINITY; mx[k] = -INFINITY; }
     const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool vec = aligned16(fr) && aligned16(mean) && (frame_elems % 4 == 0);
+    const bool vec = aligned16(frames) && aligned16(mean) && (frame_elems % 4 == 0);
     if (vec) {
-        for (long long i = t0 * 4; i < frame_elems; i += stride * 4 * PRE_U) {
-            float a[PRE_U][4], m[PRE_U][4];
+        for (long long i = t0 * 4; i < frame_elems; i += stride * 4) {
+            float m[4], a[PRE_FPB][4];
+            Vec4<float>::load(mean + i, m);
 #pragma unroll
-            for (int u = 0; u < PRE_U; ++u) {
-                const long long ii = i + u * stride * 4;
-                if (ii < frame_elems) { Vec4<T>::load(fr + ii, a[u]); Vec4<float>::load(mean + ii, m[u]); }
-            }
+            for (int k = 0; k < PRE_FPB; ++k)
+                if (k < nf) Vec4<T>::load(fr + (long long)k * frame_elems + i, a[k]);
 #pragma unroll
-            for (int u = 0; u < PRE_U; ++u)
-                if (i + u * stride * 4 < frame_elems) {
+            for (int k = 0; k < PRE_FPB; ++k)
+                if (k < nf) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) { const float d = __fsub_rn(a[u][k], m[u][k]); mn = fminf(mn, d); mx = fmaxf(mx, d); }
+                    for (int j = 0; j < 4; ++j) { const float d = __fsub_rn(a[k][j], m[j]); mn[k] = fminf(mn[k], d); mx[k] = fmaxf(mx[k], d); }
                 }
         }
     } else {
         for (long long i = t0; i < frame_elems; i += stride) {
-            const float d = __fsub_rn((float)fr[i], mean[i]);
-            mn = fminf(mn, d); mx = fmaxf(mx, d);
+            const float m = mean[i];
+#pragma unroll
+            for (int k = 0; k < PRE_FPB; ++k)
+                if (k < nf) { const float d = __fsub_rn((float)fr[(long long)k * frame_elems + i], m); mn[k] = fminf(mn[k], d); mx[k] = fmaxf(mx[k], d); }
         }
     }
+    __shared__ float smn[8][PRE_FPB], smx[8][PRE_FPB];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    for (int k = 0; k < PRE_FPB; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+        if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5][k] = mn[k]; smx[threadIdx.x >> 5][k] = mx[k]; }
     }
-    __shared__ float smn[8], smx[8];
-    if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < nf) {
+        float a = smn[0][threadIdx.x], b = smx[0][threadIdx.x];
 #pragma unroll
-        for (int w = 1; w < 8; ++w) { mn = fminf(mn, smn[w]); mx = fmaxf(mx, smx[w]); }
-        atomicMin(&minmax[f], f2ord(mn));                 // layout [min of every frame | max of every frame]
-        atomicMax(&minmax[gridDim.y + f], f2ord(mx));
+        for (int w = 1; w < 8; ++w) { a = fminf(a, smn[w][threadIdx.x]); b = fmaxf(b, smx[w][threadIdx.x]); }
+        atomicMin(&minmax[f0 + threadIdx.x], f2ord(a));
+        atomicMax(&minmax[n_frames + f0 + threadIdx.x], f2ord(b));
     }
 }
 
 // K3: ((d - min) / (max - min) * 255).astype(uint8) with numpy's float32 operation order (no contraction)
 template <typename T>
 __global__ void __launch_bounds__(256) pre_normalize_kernel(const T* __restrict__ frames, const float* __restrict__ mean,
-                                                            const unsigned* __restrict__ minmax, long long frame_elems,
+                                                            const unsigned* __restrict__ minmax, long long frame_elems, int n_frames,
                                                             unsigned char* __restrict__ out) {
-    const int f = blockIdx.y;
-    const T* fr = frames + (long long)f * frame_elems;
-    unsigned char* o = out + (long long)f * frame_elems;
-    const float mn = ord2f(minmax[f]), mx = ord2f(minmax[gridDim.y + f]);
-    const float range = __fsub_rn(mx, mn);
+    const int f0 = blockIdx.y * PRE_FPB;
+    const int nf = n_frames - f0 < PRE_FPB ? n_frames - f0 : PRE_FPB;
+    const T* fr = frames + (long long)f0 * frame_elems;
+    unsigned char* o = out + (long long)f0 * frame_elems;
+    float mn[PRE_FPB], range[PRE_FPB];
+#pragma unroll
+    for (int k = 0; k < PRE_FPB; ++k) {
+        const int f = k < nf ? f0 + k : f0;
+        mn[k] = ord2f(minmax[f]);
+        range[k] = __fsub_rn(ord2f(minmax[n_frames + f]), mn[k]);
+    }
     const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool vec = aligned16(fr) && aligned16(mean) && aligned16(o) && (frame_elems % 4 == 0);
+    const bool vec = aligned16(frames) && aligned16(mean) && aligned16(out) && (frame_elems % 4 == 0);
     if (vec) {
-        for (long long i = t0 * 4; i < frame_elems; i += stride * 4 * PRE_U) {
-            float a[PRE_U][4], m[PRE_U][4];
+        for (long long i = t0 * 4; i < frame_elems; i += stride * 4) {
+            float m[4], a[PRE_FPB][4];
+            Vec4<float>::load(mean + i, m);
 #pragma unroll
-            for (int u = 0; u < PRE_U; ++u) {
-                const long long ii = i + u * stride * 4;
-                if (ii < frame_elems) { Vec4<T>::load(fr + ii, a[u]); Vec4<float>::load(mean + ii, m[u]); }
-            }
+            for (int k = 0; k < PRE_FPB; ++k)
+                if (k < nf) Vec4<T>::load(fr + (long long)k * frame_elems + i, a[k]);
 #pragma unroll
-            for (int u = 0; u < PRE_U; ++u) {
-                const long long ii = i + u * stride * 4;
-                if (ii < frame_elems) {
+            for (int k = 0; k < PRE_FPB; ++k)
+                if (k < nf) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float v = __fmul_rn(__fdiv_rn(__fsub_rn(__fsub_rn(a[u][k], m[u][k]), mn), range), 255.0f);
-                        a[u][k] = (v >= 0.f && v < 256.f) ? v : 0.f;   // NaN (flat frame) -> 0
+                    for (int j = 0; j < 4; ++j) {
+                        const float v = __fmul_rn(__fdiv_rn(__fsub_rn(__fsub_rn(a[k][j], m[j]), mn[k]), range[k]), 255.0f);
+                        a[k][j] = (v >= 0.f && v < 256.f) ? v : 0.f;   // NaN (flat frame) -> 0
                     }
-                    Vec4<unsigned char>::store(o + ii, a[u]);
+                    Vec4<unsigned char>::store(o + (long long)k * frame_elems + i, a[k]);
                 }
-            }
         }
     } else {
         for (long long i = t0; i < frame_elems; i += stride) {
-            const float d = __fsub_rn((float)fr[i], mean[i]);
-            const float v = __fmul_rn(__fdiv_rn(__fsub_rn(d, mn), range), 255.0f);
-            o[i] = (v >= 0.f && v < 256.f) ? (unsigned char)(int)v : (unsigned char)0;   // NaN (flat frame) -> 0
+            const float m = mean[i];
+#pragma unroll
+            for (int k = 0; k < PRE_FPB; ++k)
+                if (k < nf) {
+                    const float d = __fsub_rn((float)fr[(long long)k * frame_elems + i], m);
+                    const float v = __fmul_rn(__fdiv_rn(__fsub_rn(d, mn[k]), range[k]), 255.0f);
+                    o[(long long)k * frame_elems + i] = (v >= 0.f && v < 256.f) ? (unsigned char)(int)v : (unsigned char)0;
+                }
         }
     }
 }
@@ -295,6 +314,85 @@ __global__ void __launch_bounds__(GB_TX* GB_TY) pre_gauss_kernel(const T* __rest
         if (taps.r1 >= 0)
             for (int j = -taps.r1; j <= taps.r1; ++j) a1 = __fadd_rn(a1, __fmul_rn(taps.k1[j + taps.r1], rows1[(threadIdx.y + R + j) * GB_TX + threadIdx.x]));
         o[(long long)y * W + x] = taps.r1 >= 0 ? __fsub_rn(a2, a1) : a2;
+    }
+}
+
+// Fast path for the common kernel sizes (pyorc defaults: smooth wdw=1 -> 3 taps, edge_detect wdw_1=1, wdw_2=2 -> 3 and 5
+// taps): a 128-thread block marches down a 128-column strip row by row.  Per row: one coalesced load per thread into a
+// double-buffered shared row (ONE barrier per row), the row filter from shared memory, and the column filter from a
+// sliding window of row sums kept in registers (the march is fully unrolled, so the window shifts are register renames).
+// Every input pixel is read (2R + GS_SH) / GS_SH times instead of being staged through three shared-memory tiles with
+// two barriers per 32x16 output pixels (pre_gauss_kernel above, kept for the other sizes), which was latency-bound at
+// 8 % of the HBM rate.  Same accumulation order as above (ascending tap index, separate multiply and add).
+constexpr int GS_BW = 128, GS_SH = 32;
+__device__ __forceinline__ int reflect_clamp(int i, int n) {
+    i = i < 0 ? -i : i;
+    i = i >= n ? 2 * n - 2 - i : i;
+    return i < 0 ? 0 : (i >= n ? n - 1 : i);
+}
+template <typename T, int R1, int R2>   // R1 < 0: smooth, i.e. blur(k2) only
+__global__ void __launch_bounds__(GS_BW) pre_gauss_strip_kernel(const T* __restrict__ frames, int H, int W, GaussTaps taps,
+                                                                float* __restrict__ out) {
+    constexpr int R = R2 > R1 ? R2 : R1;
+    constexpr int N2 = R + R2 + 1, N1 = R1 >= 0 ? R + R1 + 1 : 1, NIT = GS_SH + 2 * R;
+    __shared__ float buf[2][GS_BW + 2 * R];
+    const int t = threadIdx.x, x0 = blockIdx.x * GS_BW, y0 = blockIdx.y * GS_SH;
+    const long long fe = (long long)H * W;
+    const T* fr = frames + (long long)blockIdx.z * fe;
+    float* o = out + (long long)blockIdx.z * fe;
+    const int gxa = reflect_clamp(x0 - R + t, W), gxb = reflect_clamp(x0 - R + GS_BW + t, W);
+    const bool halo = t < 2 * R;
+    float pa, pb = 0.f;
+    {
+        const T* row = fr + (long long)reflect_clamp(y0 - R, H) * W;
+        pa = (float)row[gxa];
+        if (halo) pb = (float)row[gxb];
+    }
+    float q2[N2], q1[N1];   // q[d] = row sum of the input row d iterations ago
+#pragma unroll
+    for (int d = 0; d < N2; ++d) q2[d] = 0.f;
+#pragma unroll
+    for (int d = 0; d < N1; ++d) q1[d] = 0.f;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        float* b = buf[it & 1];
+        b[t] = pa;
+        if (halo) b[GS_BW + t] = pb;
+        if (it + 1 < NIT) {   // next input row in flight while this one is filtered
+            const T* row = fr + (long long)reflect_clamp(y0 - R + it + 1, H) * W;
+            pa = (float)row[gxa];
+            if (halo) pb = (float)row[gxb];
+        }
+        __syncthreads();
+        const float* c = b + t + R;
+#pragma unroll
+        for (int d = N2 - 1; d > 0; --d) q2[d] = q2[d - 1];
+        float a2 = 0.f;
+#pragma unroll
+        for (int j = -R2; j <= R2; ++j) a2 = __fadd_rn(a2, __fmul_rn(taps.k2[j + R2], c[j]));
+        q2[0] = a2;
+        if (R1 >= 0) {
+#pragma unroll
+            for (int d = N1 - 1; d > 0; --d) q1[d] = q1[d - 1];
+            float a1 = 0.f;
+#pragma unroll
+            for (int j = -R1; j <= R1; ++j) a1 = __fadd_rn(a1, __fmul_rn(taps.k1[j + (R1 >= 0 ? R1 : 0)], c[j]));
+            q1[0] = a1;
+        }
+        if (it >= 2 * R) {
+            const int yo = y0 + it - 2 * R;   // needs input rows yo - r .. yo + r = delays R + r .. R - r
+            float v2 = 0.f;
+#pragma unroll
+            for (int j = -R2; j <= R2; ++j) v2 = __fadd_rn(v2, __fmul_rn(taps.k2[j + R2], q2[R - j]));
+            float v = v2;
+            if (R1 >= 0) {
+                float v1 = 0.f;
+#pragma unroll
+                for (int j = -R1; j <= R1; ++j) v1 = __fadd_rn(v1, __fmul_rn(taps.k1[j + (R1 >= 0 ? R1 : 0)], q1[(R1 >= 0 ? R - j : 0)]));
+                v = __fsub_rn(v2, v1);
+            }
+            if (yo < H && x0 + t < W) o[(long long)yo * W + x0 + t] = v;
+        }
     }
 }
 

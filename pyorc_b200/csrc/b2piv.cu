@@ -93,7 +93,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 // "FFT, transpose, FFT" block executed twice).
 // Compute phases run unconditionally (an inactive group - only at the tail of the grid - works on garbage and never
 // stores results); only TMA traffic and global stores are predicated, so no shuffle sits in a divergent region.
-template <class R, int G, bool ROLLED, bool ALIGNED, bool F32>
+template <class R, int G, bool ROLLED, bool ALIGNED, bool F32, bool ENS = false>
 __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constant__ CUtensorMap tmap, RParams p) {
     extern __shared__ unsigned char smem_dyn[];
     // the swizzled TMA tiles need 1024-byte aligned bases: align by hand (launch adds 1 KB of slack)
@@ -209,12 +209,16 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
             rows_p5_post<R>(s, r, tid, dead0, dead1);
             __syncthreads();  // E1: block max / sum; X (and the tile aliased on it) is free again
             if (active && tid == 0 && k + 1 < nfr) issue_frame_start(f + 1);
-            rows_p6<R>(s, r, tid);
-            __syncthreads();  // E2: first-argmax key
-            if (active && have_prev) rows_dump_planes<R>(r, tid, p, un, f - 1);
-            rows_p7<R>(s, r, tid);
-            __syncthreads();  // F: neighbour rows dumped
-            if (active && have_prev) rows_p8<R>(s, r, tid, p, un, f - 1);
+            if constexpr (ENS) {
+                rows_ens<R>(s, r, tid, p, un, f - 1, active && have_prev);   // thresholds + accumulate; no peak search per pair
+            } else {
+                rows_p6<R>(s, r, tid);
+                __syncthreads();  // E2: first-argmax key
+                if (active && have_prev) rows_dump_planes<R>(r, tid, p, un, f - 1);
+                rows_p7<R>(s, r, tid);
+                __syncthreads();  // F: neighbour rows dumped
+                if (active && have_prev) rows_p8<R>(s, r, tid, p, un, f - 1);
+            }
             r.half_alpha_prev[0] = r.half_alpha_new[0];
             r.half_alpha_prev[1] = r.half_alpha_new[1];
         }
@@ -629,8 +633,8 @@ static bool rows_eligible(const b2piv_engine* e, const void* d_frames, long long
     return get_encode_tiled() != nullptr;
 }
 
-template <class R, int G, bool ROLLED, bool ALIGNED, bool F32>
-static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st) {
+template <class R, int G, bool ROLLED, bool ALIGNED, bool F32, bool ENS = false>
+static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st, const EnsParams* ep = nullptr) {
     constexpr int W = R::W;
     const int n_frames = gp.n_pairs + 1;
     CUtensorMap tmap;
@@ -651,7 +655,8 @@ static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st) {
     p.clip_norm = gp.clip_norm; p.border_nan = gp.border_nan; p.gauss_eps = gp.gauss_eps; p.keep = gp.keep;
     p.u = gp.u; p.v = gp.v; p.cmax = gp.cmax; p.s2n = gp.s2n; p.planes = gp.planes;
     const size_t smem = sizeof(RSmem<R>) * G + 1024;
-    auto kern = piv_rows_kernel<R, G, ROLLED, ALIGNED, F32>;
+    if (ENS) { p.corr_min = ep->corr_min; p.s2n_min = ep->s2n_min; p.ens_sum = ep->plane_sum; p.ens_count = ep->count; }
+    auto kern = piv_rows_kernel<R, G, ROLLED, ALIGNED, F32, ENS>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, R::NT * G, smem));
@@ -665,7 +670,7 @@ static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st) {
         run = (int)((gp.n_pairs + chunks - 1) / chunks);
         if (run < 8) run = 8;
     }
-    if (run > gp.n_pairs) run = gp.n_pairs;
+    if (run > gp.n_pairs || ENS) run = gp.n_pairs;   // ensemble: one unit owns its windows' accumulators for the whole launch
     p.run_len = run;
     const long long n_units = (long long)n_wp * ((gp.n_pairs + run - 1) / run);
     p.n_units = (int)n_units;
@@ -730,6 +735,21 @@ static int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
     return fail(e, B2PIV_ERR_UNSUPPORTED, "window size not compiled in");
 }
 static int dispatch_ens(b2piv_engine* e, const Params& p, const EnsParams& ep, cudaStream_t st) {
+    if (p.n_pairs <= 0) return B2PIV_OK;
+    const bool can_rows = rows_eligible(e, p.frames, p.frame_stride, p.pitch);
+    if (e->variant == 2 && !can_rows)
+        return fail(e, B2PIV_ERR_UNSUPPORTED, "rows kernel needs a square 32/64 window, 16-byte aligned base/pitch and an x stride that is a multiple of 4");
+    if (can_rows && e->variant != 1 && e->variant != 3) {
+        e->last_variant = 2;
+        const bool aligned = ((e->wx - e->ox) & 15) == 0;
+        if (e->dtype == B2PIV_F32) {
+            if (e->wy == 64) return launch_rows<RCfg<64>, 1, true, true, true, true>(e, p, st, &ep);
+            return launch_rows<RCfg<32>, 4, false, true, true, true>(e, p, st, &ep);
+        }
+        if (e->wy == 64) return aligned ? launch_rows<RCfg<64>, 1, true, true, false, true>(e, p, st, &ep) : launch_rows<RCfg<64>, 1, true, false, false, true>(e, p, st, &ep);
+        return aligned ? launch_rows<RCfg<32>, 4, false, true, false, true>(e, p, st, &ep) : launch_rows<RCfg<32>, 4, false, false, false, true>(e, p, st, &ep);
+    }
+    e->last_variant = 1;
     const bool tiny = !fft_config(e->wy, e->wx) && e->wy * e->wx <= 144;
     if ((e->variant == 3 || tiny) && e->wy <= 64 && e->wx <= 64) return launch_direct_ens(e, p, ep, st);
     int py, px;

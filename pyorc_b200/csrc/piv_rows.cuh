@@ -116,6 +116,10 @@ struct RParams {
     const unsigned char* keep;
     float *u, *v, *cmax, *s2n;
     float* planes;
+    // ensemble mode (piv_rows_kernel<..., ENS = true>): thresholds and the HBM accumulators [n_windows][W][W] / [n_windows]
+    float corr_min, s2n_min;
+    float* ens_sum;
+    float* ens_count;
 };
 
 // Line (row before / column after the transpose) owned by a thread, chosen so that the -kx partner sits in the SAME warp at lane^16
@@ -591,6 +595,51 @@ B2_HD void rows_dump_planes(RRegs<R>& r, int tid, const RParams& p, const RUnit&
         float* dst = p.planes + (((long long)pair * nw + un.w[w]) * W + si) * W;
 #pragma unroll
         for (int x = 0; x < W; ++x) dst[(x + W / 2) % W] = r.dead[w] ? 0.f : (w == 0 ? r.v[x].x : r.v[x].y);
+    }
+}
+
+// Ensemble mode (pyorc/velocimetry/ffpiv.py:200-243 thresholds, :359-365 accumulation): instead of locating the peak of
+// every pair, a plane that passes corr_min / s2n_min is ADDED to the window's accumulator plane in HBM (fftshifted
+// coordinates, the layout ens_finish_kernel reads).  A work unit owns its two windows for every frame of the launch
+// (run_len = n_pairs), so the read-modify-write needs no atomics and adds in frame order like the reference's
+// np.sum(corr, axis=0); thread t updates row sigma(t) with 16-byte accesses.  The accumulators of a 1080p grid are
+// 31 MB, i.e. they live in L2 between frame pairs.
+template <class R>
+B2_HD void rows_ens(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p, const RUnit& un, int pair, bool store) {
+    constexpr int W = R::W;
+    const int si = (column_of<W>(tid) + W / 2) % W;
+    const long long nw = (long long)p.n_rows * p.n_cols;
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        float M = 0.f, S = 0.f;
+#pragma unroll
+        for (int k = 0; k < R::NWARP; ++k) { M = fmaxf(M, bits_f(s.red[k][4 + w])); S += bits_f(s.red[k][6 + w]); }
+        const float ratio = M / (S / (float)R::NPX);
+        const int widx = w == 0 ? un.w[0] : un.w[1];
+        bool ok = (M >= p.corr_min) && (ratio >= p.s2n_min) && !r.dead[w];   // dead: 0 / 0 = NaN fails the test in the reference
+        if (p.keep && !p.keep[widx]) ok = false;                             // NaN plane in the reference -> masked out
+        if (!store || (w == 1 && !un.valid1)) continue;
+        if (ok) {
+            float* dst = p.ens_sum + ((long long)widx * W + si) * W;
+#pragma unroll
+            for (int c = 0; c < W / 4; ++c) {
+                const int x = 4 * c, j = (x + W / 2) % W;   // shifted column of element x; W/2 is a multiple of 4
+#ifdef __CUDA_ARCH__
+                float4 a = *reinterpret_cast<float4*>(dst + j);
+                a.x += w == 0 ? r.v[x].x : r.v[x].y;         a.y += w == 0 ? r.v[x + 1].x : r.v[x + 1].y;
+                a.z += w == 0 ? r.v[x + 2].x : r.v[x + 2].y; a.w += w == 0 ? r.v[x + 3].x : r.v[x + 3].y;
+                *reinterpret_cast<float4*>(dst + j) = a;
+#else
+                for (int q = 0; q < 4; ++q) dst[j + q] += w == 0 ? r.v[x + q].x : r.v[x + q].y;
+#endif
+            }
+        }
+        if (tid == 0) {
+            const long long o = (long long)pair * nw + widx;
+            p.cmax[o] = ok ? M : 0.f;
+            p.s2n[o] = ok ? ratio : 0.f;
+            if (ok && M > 1e-6f) p.ens_count[widx] += 1.f;
+        }
     }
 }
 

@@ -236,11 +236,12 @@ ENS_CASES = [
 
 
 @pytest.mark.parametrize("ws,ov,shape,corr_min,s2n_min", ENS_CASES)
-def test_ensemble_mode_matches_oracle(engine, ws, ov, shape, corr_min, s2n_min):
+@pytest.mark.parametrize("variant", [0, 1])     # 0: row-per-thread kernel where eligible (64x64, 32x32); 1: shared-memory FFT kernel
+def test_ensemble_mode_matches_oracle(engine, ws, ov, shape, corr_min, s2n_min, variant):
     """Ensemble correlation (pyorc/velocimetry/ffpiv.py:182-376): thresholds + plane sums on the device, two chunks."""
     O.CLIP_NORMALIZED = False
     engine.set_option("clip_normalized", 0.0)
-    engine.set_option("kernel_variant", 0.0)
+    engine.set_option("kernel_variant", float(variant))
     imgs = synth.particle_frames(*shape, dtype=np.uint8)
     imgs[:, : ws[0], : ws[1]] = 0                      # one dead window
     imgs[2] = synth.particle_frames(1, shape[1], shape[2], dtype=np.uint8, seed=7)[0]   # a decorrelated frame -> masked pairs
@@ -284,6 +285,44 @@ def test_ensemble_mode_matches_oracle(engine, ws, ov, shape, corr_min, s2n_min):
     same = (np.abs(np.round(gu[ok]) - np.round(u[ok])) + np.abs(np.round(gv[ok]) - np.round(v[ok]))) < 0.5
     assert same.mean() >= 0.99
     assert np.abs(gu[ok][same] - u[ok][same]).max() <= 2e-3 and np.abs(gv[ok][same] - v[ok][same]).max() <= 2e-3
+
+
+@pytest.mark.parametrize("ws,ov,shape,dtype", [((64, 64), (32, 32), (7, 270, 400), np.float32), ((32, 32), (24, 24), (6, 100, 144), np.uint8),
+                                               ((32, 32), (16, 16), (9, 150, 208), np.float32), ((64, 64), (40, 40), (5, 160, 208), np.uint8)])
+def test_ensemble_rows_kernel_device_frames(engine, ws, ov, shape, dtype):
+    """Device-resident chunk in ONE launch (a unit walks all frames and adds its planes to the HBM accumulators): float32
+    frames and window starts that are not 16-byte aligned, against the oracle's plane sums (no thresholds, so no pair can
+    sit on a threshold) and against the shared-memory kernel."""
+    import torch
+
+    O.CLIP_NORMALIZED = False
+    engine.set_option("clip_normalized", 0.0)
+    imgs = synth.particle_frames(*shape, dtype=dtype)
+    imgs[:, : ws[0], : ws[1]] = 0
+    nr, nc = O.get_array_shape(shape[1:], ws, ov)
+    ens = O.Ensemble(nr, nc, ws, ov, corr_min=0.0, s2n_min=0.0, count_min=0.0)
+    ens.add_chunk(imgs)
+    ref_sum = np.asarray(ens.corr_sum, dtype=np.float64).reshape(nr * nc, -1)
+    d = torch.from_numpy(imgs).cuda()
+    res = {}
+    for variant in (0, 1):
+        engine.set_option("kernel_variant", float(variant))
+        engine.ens_begin(shape[1:], ws, ov, dtype)
+        c, s_ = engine.ens_add(d, ws, ov, corr_min=0.0, s2n_min=0.0)
+        plane, count = engine.ens_accumulators()
+        res[variant] = (c.cpu().numpy(), s_.cpu().numpy(), plane.cpu().numpy().copy(), count.cpu().numpy().copy(), engine.ens_finish(0.0))
+    engine.set_option("kernel_variant", 0.0)
+    for variant in (0, 1):
+        c, s_, plane, count, (gu, gv, cnt) = res[variant]
+        assert np.abs(c - ens.corr_chunks[0]).max() <= 5e-6
+        assert np.abs(plane - ref_sum).max() <= 2e-5
+        assert np.array_equal(count, np.asarray(ens.corr_count).reshape(-1))
+    assert np.abs(res[0][2] - res[1][2]).max() <= 1e-5
+    u, v, _, _ = ens.finalize()
+    gu, gv, _ = res[0][4]
+    assert np.array_equal(np.isnan(gu), np.isnan(u.reshape(-1)))
+    ok = np.isfinite(gu)
+    assert np.abs(gu[ok] - u.reshape(-1)[ok]).max() <= 2e-3 and np.abs(gv[ok] - v.reshape(-1)[ok]).max() <= 2e-3
 
 
 def test_ffpiv_api_cross_corr_and_u_v_displacement(engine):

@@ -28,7 +28,34 @@ def run(H, W, ws, ov, n_frames, reps=5, dtype="uint8", variant=0, run_len=0, gro
     print(f"variant {variant} run_len {run_len} groups {groups} rolled {rolled} {H}x{W} win {ws} ov {ov} {dtype}: {nwin} windows in {t:.3f} ms -> {nwin / t / 1e3:.2f} Mwin/s  (u mean {float(torch.nanmean(out[0])):.3f} v mean {float(torch.nanmean(out[1])):.3f})", flush=True)
     e.close()
 
+def run_ens(H, W, ws, ov, n_frames, reps=5, dtype="uint8", variant=0):
+    """Ensemble mode on device-resident frames: begin + add (one launch) + finish, thresholds at pyorc's defaults."""
+    dev = torch.device("cuda", 0)
+    e = Engine(0)
+    e.set_option("kernel_variant", variant)
+    fr = synth.particle_frames_torch(n_frames, H, W, dev, dtype=dtype)
+    npdt = np.uint8 if dtype == "uint8" else np.float32
+    torch.cuda.synchronize()
+    ts = []
+    for i in range(reps + 2):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nr, nc = e.ens_begin((H, W), ws, ov, npdt)
+        a.record(); cm, sn = e.ens_add(fr, ws, ov, corr_min=0.2, s2n_min=3.0); b.record(); torch.cuda.synchronize()
+        u, v, cnt = e.ens_finish(0.2)
+        if i >= 2: ts.append(a.elapsed_time(b))
+    nwin = (n_frames - 1) * nr * nc
+    t = float(np.median(ts))
+    print(f"ENSEMBLE variant {variant} {H}x{W} win {ws} ov {ov} {dtype}: {nwin} windows in {t:.3f} ms -> {nwin / t / 1e3:.2f} Mwin/s  (u mean {np.nanmean(u):.3f} v mean {np.nanmean(v):.3f} count mean {cnt.mean():.1f})", flush=True)
+    e.close()
+
 if __name__ == "__main__":
+    if "--ens" in sys.argv:
+        for variant in (1, 0):
+            run_ens(1080, 1920, (64, 64), (32, 32), 101, variant=variant)
+            run_ens(2160, 3840, (64, 64), (32, 32), 41, variant=variant)
+            run_ens(1080, 1920, (32, 32), (16, 16), 41, variant=variant)
+            run_ens(1080, 1920, (64, 64), (32, 32), 51, dtype="float32", variant=variant)
+        sys.exit(0)
     if "--single" in sys.argv:
         run(1080, 1920, (64, 64), (32, 32), 21, reps=2, variant=int(os.environ.get("B2_VARIANT", "0")), groups=int(os.environ.get("B2_GROUPS", "0")), rolled=int(os.environ.get("B2_ROLLED", "0")))
         sys.exit(0)

@@ -38,13 +38,15 @@ const char* b2piv_last_error(const b2piv_engine* e);
 
 /* Numerical switches for the details that live in ffpiv rather than pyorc (see oracle/ffpiv_oracle.py):
  *   "clip_normalized" (0/1, default 0 = ffpiv), "border_nan" (0/1), "gauss_eps" (float), "copy_chunks" (H2D
- *   pipeline depth), "kernel_variant" (0 auto, 1 shared-memory FFT, 2 row-per-thread TMA, 3 direct), "run_len". */
+ *   pipeline depth), "kernel_variant" (0 auto, 1 shared-memory FFT, 2 row-per-thread TMA, 3 direct, 4 row-per-thread TMA in
+ *   padded mode for uint8 windows up to 32 px), "run_len". */
 int b2piv_set_option(b2piv_engine* e, const char* name, double value);
 
 /* Plan = frame geometry + window geometry.  Replaces the geometry half of ffpiv.cross_corr and
  * ffpiv.window.get_rect_coordinates (pyorc/api/frames.py:85-90): n_rows=(H-wy)/(wy-oy)+1, n_cols likewise.
- * Supported windows: any size 4..64 per axis (powers of two 16..64 take the FFT kernels, the rest - pyorc's 10, 20,
- * 26, 50 ... - a direct-correlation kernel) plus 64x128, 128x64, 128x128; search_area_size == window_size as pyorc
+ * Supported windows: any size 4..64 per axis (32x32 and 64x64 take the row-per-thread FFT kernel, other sizes up to 32 px -
+ * pyorc's 10, 20, 26 ... - its exact zero-padded mode, the rest a shared-memory FFT or a direct-correlation kernel) plus
+ * 64x128, 128x64, 128x128; search_area_size == window_size as pyorc
  * always passes (frames.py:168). */
 int b2piv_plan(b2piv_engine* e, int height, int width, int win_y, int win_x, int ovl_y, int ovl_x, int dtype,
                int* n_rows, int* n_cols);

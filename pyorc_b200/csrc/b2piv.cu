@@ -93,7 +93,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 // "FFT, transpose, FFT" block executed twice).
 // Compute phases run unconditionally (an inactive group - only at the tail of the grid - works on garbage and never
 // stores results); only TMA traffic and global stores are predicated, so no shuffle sits in a divergent region.
-template <class R, int G, bool ROLLED, bool ALIGNED, bool F32, bool ENS = false>
+template <class R, int G, bool ROLLED, bool ALIGNED, bool F32, bool ENS = false, bool PAD = false>
 __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constant__ CUtensorMap tmap, RParams p) {
     extern __shared__ unsigned char smem_dyn[];
     // the swizzled TMA tiles need 1024-byte aligned bases: align by hand (launch adds 1 KB of slack)
@@ -154,7 +154,12 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
                 while (!mbar_try_wait(&s.mbar, parity)) {}
                 parity ^= 1u;
             }
-            if constexpr (!F32) {
+            if constexpr (PAD) {
+                static_assert(!PAD || (!ALIGNED && !F32), "padded mode uses the 16-byte wider uint8 boxes");
+                rows_p1_pad<R>(s, r, tid, p, xoff0, xoff1);
+                __syncthreads();  // A
+                rows_p2_pre_pad<R>(s, r, tid, p);
+            } else if constexpr (!F32) {
                 rows_p1<R, ALIGNED>(s, r, tid, xoff0, xoff1);
                 __syncthreads();  // A: integer moments visible, tile (aliased on X) fully consumed
                 rows_p2_pre<R>(s, r, tid, p.clip_norm);
@@ -193,7 +198,7 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
                 for (int st = 0; st < 4; ++st) {
                     fft_reg<W, 0>(r.v);
                     if ((st & 1) == 0) transpose_device<R>(s, r, tid, st != 0);
-                    else if (st == 1) rows_p3b_device<R>(s, r, tid, true);
+                    else if (st == 1) rows_p3b_device<R, PAD>(s, r, tid, true, &p);
                 }
             } else {
 #pragma unroll 1
@@ -201,23 +206,23 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
                     fft_reg<W, 0>(r.v);
                     transpose_device<R>(s, r, tid, half != 0);
                     fft_reg<W, 0>(r.v);
-                    if (half == 0) rows_p3b_device<R>(s, r, tid, true);
+                    if (half == 0) rows_p3b_device<R, PAD>(s, r, tid, true, &p);
                 }
             }
             const bool dead0 = (r.half_alpha_prev[0] == 0.f) || (r.half_alpha_new[0] == 0.f);
             const bool dead1 = (r.half_alpha_prev[1] == 0.f) || (r.half_alpha_new[1] == 0.f);
-            rows_p5_post<R>(s, r, tid, dead0, dead1);
+            rows_p5_post<R, PAD>(s, r, tid, dead0, dead1, &p);
             __syncthreads();  // E1: block max / sum; X (and the tile aliased on it) is free again
             if (active && tid == 0 && k + 1 < nfr) issue_frame_start(f + 1);
             if constexpr (ENS) {
-                rows_ens<R>(s, r, tid, p, un, f - 1, active && have_prev);   // thresholds + accumulate; no peak search per pair
+                rows_ens<R, PAD>(s, r, tid, p, un, f - 1, active && have_prev);   // thresholds + accumulate; no peak search per pair
             } else {
-                rows_p6<R>(s, r, tid);
+                rows_p6<R, PAD>(s, r, tid, &p);
                 __syncthreads();  // E2: first-argmax key
-                if (active && have_prev) rows_dump_planes<R>(r, tid, p, un, f - 1);
-                rows_p7<R>(s, r, tid);
+                if (active && have_prev) rows_dump_planes<R, PAD>(r, tid, p, un, f - 1);
+                rows_p7<R, PAD>(s, r, tid, &p);
                 __syncthreads();  // F: neighbour rows dumped
-                if (active && have_prev) rows_p8<R>(s, r, tid, p, un, f - 1);
+                if (active && have_prev) rows_p8<R, PAD>(s, r, tid, p, un, f - 1);
             }
             r.half_alpha_prev[0] = r.half_alpha_new[0];
             r.half_alpha_prev[1] = r.half_alpha_new[1];
@@ -633,7 +638,7 @@ static bool rows_eligible(const b2piv_engine* e, const void* d_frames, long long
     return get_encode_tiled() != nullptr;
 }
 
-template <class R, int G, bool ROLLED, bool ALIGNED, bool F32, bool ENS = false>
+template <class R, int G, bool ROLLED, bool ALIGNED, bool F32, bool ENS = false, bool PAD = false>
 static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st, const EnsParams* ep = nullptr) {
     constexpr int W = R::W;
     const int n_frames = gp.n_pairs + 1;
@@ -656,7 +661,14 @@ static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st, const
     p.u = gp.u; p.v = gp.v; p.cmax = gp.cmax; p.s2n = gp.s2n; p.planes = gp.planes;
     const size_t smem = sizeof(RSmem<R>) * G + 1024;
     if (ENS) { p.corr_min = ep->corr_min; p.s2n_min = ep->s2n_min; p.ens_sum = ep->plane_sum; p.ens_count = ep->count; }
-    auto kern = piv_rows_kernel<R, G, ROLLED, ALIGNED, F32, ENS>;
+    p.ny = PAD ? e->wy : W; p.nx = PAD ? e->wx : W;
+    if (PAD) {   // spectrum factor of the 2 x 2 tiling (piv_rows.cuh, "Padded mode")
+        p.pad_scale = (float)(1.0 / ((double)R::NPX * p.ny * p.nx));
+        const double two_pi = 6.283185307179586476925286766559;
+        for (int k = 0; k <= W / 2; ++k) { const double th = two_pi * (double)((k * p.ny) % W) / W; p.pad_ty[k] = make_float2((float)(1.0 + cos(th)), (float)(-sin(th))); }
+        for (int k = 0; k < W; ++k) { const double th = two_pi * (double)((k * p.nx) % W) / W; p.pad_tx[k] = make_float2((float)(1.0 + cos(th)), (float)(-sin(th))); }
+    }
+    auto kern = piv_rows_kernel<R, G, ROLLED, ALIGNED, F32, ENS, PAD>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, R::NT * G, smem));
@@ -680,6 +692,21 @@ static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st, const
     CK(cudaGetLastError());
     e->launches++;
     return B2PIV_OK;
+}
+
+// Padded mode of the row-per-thread kernel: any uint8 window (square or not, any stride) whose larger side is at most
+// 32 px, i.e. at most half of a 64 x 64 (or 32 x 32) plane.  Native 32 x 32 / 64 x 64 windows never come here.
+static bool pad_eligible(const b2piv_engine* e, const void* d_frames, long long frame_stride, int pitch) {
+    const int m = e->wy > e->wx ? e->wy : e->wx;
+    if (e->dtype != B2PIV_U8 || 2 * m > 64 || e->wy < 2 || e->wx < 2) return false;
+    if ((pitch & 15) || (frame_stride & 15) || (((uintptr_t)d_frames) & 15)) return false;
+    return get_encode_tiled() != nullptr;
+}
+template <bool ENS>
+static int launch_rows_pad(b2piv_engine* e, const Params& p, cudaStream_t st, const EnsParams* ep) {
+    const int m = e->wy > e->wx ? e->wy : e->wx;
+    if (2 * m <= 32) return launch_rows<RCfg<32>, 4, false, false, false, ENS, true>(e, p, st, ep);
+    return launch_rows<RCfg<64>, 1, true, false, false, ENS, true>(e, p, st, ep);
 }
 
 // FFT plane for a window size that is not itself a compiled FFT shape: smallest power of two >= 2n per axis (exact
@@ -718,9 +745,16 @@ static int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
         if (e->groups == 1) return aligned ? launch_rows<RCfg<32>, 1, false, true, false>(e, p, st) : launch_rows<RCfg<32>, 1, false, false, false>(e, p, st);
         return aligned ? launch_rows<RCfg<32>, 4, false, true, false>(e, p, st) : launch_rows<RCfg<32>, 4, false, false, false>(e, p, st);
     }
-    // sizes that are not a compiled FFT shape: tiny windows are cheapest by direct correlation, the rest run padded
-    // through the FFT kernel; variant 3 forces the direct kernel
+    // sizes that are not a compiled FFT shape: tiny windows are cheapest by direct correlation, windows up to 32 px run
+    // zero-padded through the row-per-thread kernel (piv_rows.cuh "Padded mode"; variant 4 forces it wherever it applies),
+    // the rest padded through the shared-memory FFT kernel; variant 3 forces the direct kernel
     const bool tiny = !fft_config(e->wy, e->wx) && e->wy * e->wx <= 144;
+    if (e->variant == 4 && !pad_eligible(e, p.frames, p.frame_stride, p.pitch))
+        return fail(e, B2PIV_ERR_UNSUPPORTED, "padded rows kernel needs uint8 frames, a window of at most 32 px and 16-byte aligned base/pitch");
+    if (pad_eligible(e, p.frames, p.frame_stride, p.pitch) && (e->variant == 4 || (e->variant == 0 && !fft_config(e->wy, e->wx) && !tiny))) {
+        e->last_variant = 4;
+        return launch_rows_pad<false>(e, p, st, nullptr);
+    }
     if ((e->variant == 3 || tiny) && e->wy <= 64 && e->wx <= 64) {
         e->last_variant = 3;
         return launch_direct(e, p, st);
@@ -749,8 +783,14 @@ static int dispatch_ens(b2piv_engine* e, const Params& p, const EnsParams& ep, c
         if (e->wy == 64) return aligned ? launch_rows<RCfg<64>, 1, true, true, false, true>(e, p, st, &ep) : launch_rows<RCfg<64>, 1, true, false, false, true>(e, p, st, &ep);
         return aligned ? launch_rows<RCfg<32>, 4, false, true, false, true>(e, p, st, &ep) : launch_rows<RCfg<32>, 4, false, false, false, true>(e, p, st, &ep);
     }
-    e->last_variant = 1;
     const bool tiny = !fft_config(e->wy, e->wx) && e->wy * e->wx <= 144;
+    if (e->variant == 4 && !pad_eligible(e, p.frames, p.frame_stride, p.pitch))
+        return fail(e, B2PIV_ERR_UNSUPPORTED, "padded rows kernel needs uint8 frames, a window of at most 32 px and 16-byte aligned base/pitch");
+    if (pad_eligible(e, p.frames, p.frame_stride, p.pitch) && (e->variant == 4 || (e->variant == 0 && !fft_config(e->wy, e->wx) && !tiny))) {
+        e->last_variant = 4;
+        return launch_rows_pad<true>(e, p, st, &ep);
+    }
+    e->last_variant = 1;
     if ((e->variant == 3 || tiny) && e->wy <= 64 && e->wx <= 64) return launch_direct_ens(e, p, ep, st);
     int py, px;
     plane_shape(e, &py, &px);
@@ -908,11 +948,20 @@ int b2piv_pairs_device(b2piv_engine* e, const void* d_frames, long long frame_st
 
 }  // extern "C"
 
+// Row pitch of the engine's own device copy of host frames: rounded up to 16 bytes so that every frame width qualifies
+// for the TMA kernels (pyorc's orthorectified frames have arbitrary widths, e.g. 371 px for the Ngwerere example)
+static int host_pitch(const b2piv_engine* e) {
+    const int row = e->W * (e->dtype == B2PIV_F32 ? 4 : 1);
+    return (row + 15) & ~15;
+}
+
 // shared H2D pipeline: copy frames chunk-wise on s_copy, call `work(first_pair, n_pairs)` on s_comp per chunk
 template <class F>
 static int pipeline_host(b2piv_engine* e, const void* frames, int n_frames, bool pipelined, F&& work) {
     const size_t esz = e->dtype == B2PIV_F32 ? 4 : 1;
-    const size_t fbytes = (size_t)e->H * e->W * esz;
+    const size_t row_bytes = (size_t)e->W * esz, dpitch = (size_t)host_pitch(e);
+    const size_t hbytes = (size_t)e->H * row_bytes;      // frame on the host (dense)
+    const size_t fbytes = (size_t)e->H * dpitch;         // frame on the device (pitched)
     int rc = ensure(e, &e->d_frames, &e->cap_frames, fbytes * n_frames);
     if (rc) return rc;
     const int n_pairs = n_frames - 1;
@@ -932,8 +981,12 @@ static int pipeline_host(b2piv_engine* e, const void* frames, int n_frames, bool
         if (p0 >= p1) break;
         const int need = p1 + 1;  // frames [0, p1] must be resident
         if (need > copied) {
-            CK(cudaMemcpyAsync(e->d_frames + (size_t)copied * fbytes, (const unsigned char*)frames + (size_t)copied * fbytes,
-                               (size_t)(need - copied) * fbytes, cudaMemcpyHostToDevice, e->s_copy));
+            if (dpitch == row_bytes)
+                CK(cudaMemcpyAsync(e->d_frames + (size_t)copied * fbytes, (const unsigned char*)frames + (size_t)copied * hbytes,
+                                   (size_t)(need - copied) * fbytes, cudaMemcpyHostToDevice, e->s_copy));
+            else   // frames are contiguous on both sides, so a chunk is one 2-D copy of (frames * H) rows
+                CK(cudaMemcpy2DAsync(e->d_frames + (size_t)copied * fbytes, dpitch, (const unsigned char*)frames + (size_t)copied * hbytes,
+                                     row_bytes, row_bytes, (size_t)(need - copied) * e->H, cudaMemcpyHostToDevice, e->s_copy));
             copied = need;
         }
         CK(cudaEventRecord(e->ev_chunk[c], e->s_copy));
@@ -954,8 +1007,7 @@ int b2piv_pairs_host(b2piv_engine* e, const void* frames, int n_frames, float si
     if (!frames || !u || !v || !corr_max || !s2n) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
     if (n_frames < 2) return fail(e, B2PIV_ERR_ARG, "need at least 2 frames (one pair)");
     CK(cudaSetDevice(e->device));
-    const size_t esz = e->dtype == B2PIV_F32 ? 4 : 1;
-    const int pitch = (int)(e->W * esz);
+    const int pitch = host_pitch(e);
     const long long fstride = (long long)e->H * pitch;
     const size_t nw = (size_t)e->n_rows * e->n_cols, n_pairs = (size_t)n_frames - 1;
     const size_t field = nw * n_pairs;
@@ -992,8 +1044,7 @@ int b2piv_corr_planes_host(b2piv_engine* e, const void* frames, int n_frames, fl
     if (!frames || !corr) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
     if (n_frames < 2) return fail(e, B2PIV_ERR_ARG, "need at least 2 frames (one pair)");
     CK(cudaSetDevice(e->device));
-    const size_t esz = e->dtype == B2PIV_F32 ? 4 : 1;
-    const int pitch = (int)(e->W * esz);
+    const int pitch = host_pitch(e);
     const long long fstride = (long long)e->H * pitch;
     const size_t nw = (size_t)e->n_rows * e->n_cols, n_pairs = (size_t)n_frames - 1;
     const size_t field = nw * n_pairs, pl = field * e->wy * e->wx;
@@ -1077,8 +1128,7 @@ int b2piv_ens_add_host(b2piv_engine* e, const void* frames, int n_frames, float 
     if (!frames || !corr_max || !s2n) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
     if (n_frames < 2) return fail(e, B2PIV_ERR_ARG, "need at least 2 frames (one pair)");
     CK(cudaSetDevice(e->device));
-    const size_t esz = e->dtype == B2PIV_F32 ? 4 : 1;
-    const int pitch = (int)(e->W * esz);
+    const int pitch = host_pitch(e);
     const long long fstride = (long long)e->H * pitch;
     const size_t nw = (size_t)e->n_rows * e->n_cols, field = nw * ((size_t)n_frames - 1);
     int rc = ensure(e, &e->d_out, &e->cap_out, field * 4 * sizeof(float));

@@ -120,6 +120,12 @@ struct RParams {
     float corr_min, s2n_min;
     float* ens_sum;
     float* ens_count;
+    // padded mode (PAD = true): the true window ny x nx is at most half the W x W FFT plane (see rows_p1_pad)
+    int ny, nx;
+    float pad_scale;               // 1 / (W*W * ny*nx)
+    float2 pad_ty[33];             // Ty(ky) = 1 + exp(-2 pi i ky ny / W), ky = 0 .. W/2
+    float2 pad_tx[64];             // Tx(kx) = 1 + exp(-2 pi i kx nx / W)
+    int height;                    // host emulator only (rows below the frame read as 0, like the TMA fill)
 };
 
 // Line (row before / column after the transpose) owned by a thread, chosen so that the -kx partner sits in the SAME warp at lane^16
@@ -159,6 +165,7 @@ struct RRegs {
     int pi[2], pj[2];
     float cmaxv[2], sumv[2];
     float2 r0, r1;                // host emulator only: cross spectra of the current ky step
+    float2 tx;                    // padded mode: Tx(own column)
 };
 
 struct RUnit {
@@ -243,6 +250,92 @@ B2_HD void rows_p1(RSmem<R>& s, RRegs<R>& r, int tid, int xoff0 = 0, int xoff1 =
 #else
     for (int k = 0; k < 4; ++k) s.red[tid >> 5][k] += vals[k];
 #endif
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Padded mode: window sizes that are not a power of two (pyorc: 10, 20, 26, 30 ... from the camera configuration).
+// The ny x nx window of frame k is embedded ZERO-PADDED in the W x W plane (2*max(ny, nx) <= W).  The circular
+// correlation of period (ny, nx) the reference computes equals the linear correlation of that plane against the window
+// of frame k+1 TILED 2 x 2 - and the tiled plane is the zero-padded one convolved with four deltas, so its spectrum is the
+// zero-padded spectrum times T(ky, kx) = (1 + w^(ny ky)) (1 + w^(nx kx)), w = exp(-2 pi i / W).  One forward transform
+// per window and frame therefore still serves both roles (as `a` of the next pair, and times T as `b` of this one), and
+// the reference's plane is the central ny x nx block of the fftshifted W x W result.  Exact (no wrap-around) like
+// piv_core.cuh's phase_embed, at the cost of a native W x W window.
+// P1: the TMA box starts at the 16-byte boundary below the window (any x stride); rows are funnel-shifted to the byte
+// offset and masked to nx bytes, rows >= ny are zero, so the integer moments cover exactly the window.
+// ------------------------------------------------------------------------------------------------------------
+B2_HD unsigned funnel_r(unsigned lo, unsigned hi, int sh) {
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+template <class R>
+B2_HD void rows_p1_pad(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p, int xoff0, int xoff1) {
+    constexpr int W = R::W;
+    const int row = column_of<W>(tid);
+    const bool rowok = row < p.ny;
+    unsigned S[2] = {0, 0}, Q[2] = {0, 0};
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        const int xoff = w == 0 ? xoff0 : xoff1;
+        const unsigned char* base = s.tile() + (w * W + row) * R::WB + (xoff & ~3);
+        const int sh = (xoff & 3) * 8;
+        unsigned wd[W / 4 + 1];
+#pragma unroll
+        for (int k = 0; k <= W / 4; ++k) wd[k] = *reinterpret_cast<const unsigned*>(base + 4 * k);
+#pragma unroll
+        for (int k = 0; k < W / 4; ++k) {
+            const int left = p.nx - 4 * k;   // bytes of this word inside the window
+            const unsigned mask = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << (8 * left)) - 1u));
+            r.px[w][k] = rowok ? (funnel_r(wd[k], wd[k + 1], sh) & mask) : 0u;
+            S[w] = dp4a_u(r.px[w][k], 0x01010101u, S[w]);
+            Q[w] = dp4a_u(r.px[w][k], r.px[w][k], Q[w]);
+        }
+    }
+    unsigned vals[4] = {S[0], Q[0], S[1], Q[1]};
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vals[k] += __shfl_xor_sync(0xffffffffu, vals[k], o);
+    }
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s.red[tid >> 5][k] = vals[k];
+    }
+#else
+    for (int k = 0; k < 4; ++k) s.red[tid >> 5][k] += vals[k];
+#endif
+}
+// P2 (padded): moments over the ny*nx window pixels; pixels outside the window stay exactly 0 after centring
+template <class R>
+B2_HD void rows_p2_pre_pad(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p) {
+    constexpr int W = R::W;
+    const unsigned long long npx = (unsigned long long)(p.ny * p.nx);
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        unsigned long long S = 0, Q = 0;
+#pragma unroll
+        for (int k = 0; k < R::NWARP; ++k) { S += s.red[k][2 * w]; Q += s.red[k][2 * w + 1]; }
+        const unsigned long long m2 = npx * Q - S * S;
+        r.mean_new[w] = (float)S / (float)npx;
+        r.half_alpha_new[w] = m2 ? 0.5f * (float)npx * (1.0f / sqrtf((float)m2)) : 0.f;
+    }
+    const bool rowok = column_of<W>(tid) < p.ny;
+#pragma unroll
+    for (int k = 0; k < W / 4; ++k) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const bool ok = rowok && (4 * k + b < p.nx);
+            float a0 = byte_to_float(r.px[0][k], b) - r.mean_new[0];
+            float a1 = byte_to_float(r.px[1][k], b) - r.mean_new[1];
+            if (p.clip_norm) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+            r.v[4 * k + b] = ok ? make_float2(a0, a1) : make_float2(0.f, 0.f);
+        }
+    }
+    r.tx = p.pad_tx[column_of<W>(tid)];
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -401,18 +494,26 @@ B2_HD void separate(float2 z, float2 zn, float b0, float b1, float2& a0, float2&
 
 // One ky step (ky in [0, W/2]) of the cross phase, part A: needs partner's Z(kn) = `pz`.
 // Computes R0, R1 at (ky, own column), parks the new spectra, writes G(ky) into v[ky].
-template <class R>
-B2_HD void cross_step_a(RSmem<R>& s, RRegs<R>& r, int tid, int ky, float2 pz, bool have_prev, float2& r0, float2& r1) {
+template <class R, bool PAD = false>
+B2_HD void cross_step_a(RSmem<R>& s, RRegs<R>& r, int tid, int ky, float2 pz, bool have_prev, float2& r0, float2& r1,
+                        const RParams* pp = nullptr) {
     constexpr float INVN2 = 1.0f / ((float)R::NPX * (float)R::NPX);
+    const float scale = PAD ? pp->pad_scale : INVN2;
     float2 a0, a1;
     separate(r.v[ky], pz, r.half_alpha_new[0], r.half_alpha_new[1], a0, a1);
     if (have_prev) {
         const float2 p0 = s.park[0][ky][tid], p1 = s.park[1][ky][tid];
         r0 = make_float2(p0.x * a0.x + p0.y * a0.y, p0.x * a0.y - p0.y * a0.x);   // conj(p0) * a0
         r1 = make_float2(p1.x * a1.x + p1.y * a1.y, p1.x * a1.y - p1.y * a1.x);
+        if (PAD) {   // new window in its tiled role: times T(ky, own column) = Ty(ky) Tx
+            const float2 ty = pp->pad_ty[ky];
+            const float2 t = make_float2(ty.x * r.tx.x - ty.y * r.tx.y, ty.x * r.tx.y + ty.y * r.tx.x);
+            r0 = make_float2(r0.x * t.x - r0.y * t.y, r0.x * t.y + r0.y * t.x);
+            r1 = make_float2(r1.x * t.x - r1.y * t.y, r1.x * t.y + r1.y * t.x);
+        }
     }
-    s.park[0][ky][tid] = make_float2(a0.x * INVN2, a0.y * INVN2);
-    s.park[1][ky][tid] = make_float2(a1.x * INVN2, a1.y * INVN2);
+    s.park[0][ky][tid] = make_float2(a0.x * scale, a0.y * scale);
+    s.park[1][ky][tid] = make_float2(a1.x * scale, a1.y * scale);
     if (have_prev) r.v[ky] = make_float2(r0.x - r1.y, -(r0.y + r1.x));            // conj(G), G = R0 + i R1
 }
 // part B: the partner's (R0, R1) at (ky, -col) give G(-ky, col) = conj(R0) + i conj(R1), stored conjugated:
@@ -430,15 +531,15 @@ __device__ __forceinline__ float2 shfl2(float2 a, int src) {
     return make_float2(__shfl_sync(0xffffffffu, a.x, src), __shfl_sync(0xffffffffu, a.y, src));
 }
 // device: the whole cross phase for one thread
-template <class R>
-__device__ __forceinline__ void rows_p3b_device(RSmem<R>& s, RRegs<R>& r, int tid, bool have_prev) {
+template <class R, bool PAD = false>
+__device__ __forceinline__ void rows_p3b_device(RSmem<R>& s, RRegs<R>& r, int tid, bool have_prev, const RParams* pp = nullptr) {
     constexpr int W = R::W;
     const int pl = partner_lane_of<W>(tid);
 #pragma unroll
     for (int ky = 0; ky <= W / 2; ++ky) {
         const float2 pz = shfl2(r.v[(W - ky) % W], pl);
         float2 r0 = make_float2(0.f, 0.f), r1 = make_float2(0.f, 0.f);
-        cross_step_a<R>(s, r, tid, ky, pz, have_prev, r0, r1);
+        cross_step_a<R, PAD>(s, r, tid, ky, pz, have_prev, r0, r1, pp);
         if (have_prev && ky != 0 && ky != W / 2) cross_step_b<R>(r, ky, shfl2(cross_mirror(r0, r1), pl));
     }
 }
@@ -449,14 +550,22 @@ __device__ __forceinline__ void rows_p3b_device(RSmem<R>& s, RRegs<R>& r, int ti
 // P5: row from X, (forward FFT along the row, then) conjugate, clip, per-row max / sum.
 // ------------------------------------------------------------------------------------------------------------
 // r.v holds FFT2(conj G) = conj(planes): plane 0 = Re, plane 1 = -Im.
-template <class R>
-B2_HD void rows_p5_post(RSmem<R>& s, RRegs<R>& r, int tid, bool dead0, bool dead1) {
+// Padded mode: the lags 0 .. n-1 of the (unshifted) W x W plane are free of wrap-around - the tiled window covers
+// [0, 2n) - and by periodicity lag q >= n/2 IS the reference's negative lag q - n.  The reference's fftshifted n x n plane
+// is therefore element (q + n/2) % n <- natural index q < n, per axis; everything else is set to 0, which is neutral
+// for the max and the sum of the clipped (>= 0) plane.
+B2_HD int shifted_index(int q, int n) { const int h = n / 2; return q < n - h ? q + h : q - (n - h); }   // (q + n/2) % n, q < n
+
+template <class R, bool PAD = false>
+B2_HD void rows_p5_post(RSmem<R>& s, RRegs<R>& r, int tid, bool dead0, bool dead1, const RParams* pp = nullptr) {
     constexpr int W = R::W;
     float m0 = 0.f, m1 = 0.f, s0 = 0.f, s1 = 0.f;
+    const bool rowok = !PAD || column_of<W>(tid) < pp->ny;
 #pragma unroll
     for (int x = 0; x < W; ++x) {
         // clip to [0, 1] (inputs are uint8, no NaNs can occur, so fmin/fmax are exact here)
-        const float a = fminf(fmaxf(r.v[x].x, 0.f), 1.f), b = fminf(fmaxf(-r.v[x].y, 0.f), 1.f);
+        float a = fminf(fmaxf(r.v[x].x, 0.f), 1.f), b = fminf(fmaxf(-r.v[x].y, 0.f), 1.f);
+        if (PAD && !(rowok && x < pp->nx)) { a = 0.f; b = 0.f; }
         r.v[x] = make_float2(a, b);
         m0 = fmaxf(a, m0); m1 = fmaxf(b, m1);
         s0 += a; s1 += b;
@@ -494,10 +603,12 @@ B2_HD float bits_f(unsigned u) { union { float f; unsigned u; } a; a.u = u; retu
 
 // P6: block max / sum known; rows holding the max search their FIRST matching column in fftshifted order and
 // deposit key = shifted flat index (min wins).
-template <class R>
-B2_HD void rows_p6(RSmem<R>& s, RRegs<R>& r, int tid) {
+template <class R, bool PAD = false>
+B2_HD void rows_p6(RSmem<R>& s, RRegs<R>& r, int tid, const RParams* pp = nullptr) {
     constexpr int W = R::W;
-    const int si = (column_of<W>(tid) + W / 2) % W;   // fftshifted index of this thread's row
+    const bool rowok = !PAD || column_of<W>(tid) < pp->ny;
+    // fftshifted index of this thread's row in the reference's plane
+    const int si = PAD ? (rowok ? shifted_index(column_of<W>(tid), pp->ny) : 0) : (column_of<W>(tid) + W / 2) % W;
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
         float M = 0.f, S = 0.f;
@@ -505,14 +616,23 @@ B2_HD void rows_p6(RSmem<R>& s, RRegs<R>& r, int tid) {
         for (int k = 0; k < R::NWARP; ++k) { M = fmaxf(M, bits_f(s.red[k][4 + w])); S += bits_f(s.red[k][6 + w]); }
         r.cmaxv[w] = M; r.sumv[w] = S;
         unsigned long long key = ~0ull;
-        if (r.rowmax[w] == M) {
+        if (r.rowmax[w] == M && rowok) {
             int first = W;
-            // shifted column j = (x + W/2) % W ; scan j descending so the smallest j survives
+            if (PAD) {
 #pragma unroll
-            for (int j = W - 1; j >= 0; --j) {
-                const int x = (j + W / 2) % W;
-                const float val = w == 0 ? r.v[x].x : r.v[x].y;
-                first = (val == M) ? j : first;
+                for (int x = 0; x < W; ++x) {
+                    const float val = w == 0 ? r.v[x].x : r.v[x].y;
+                    const int j = shifted_index(x, pp->nx);
+                    first = (val == M && x < pp->nx && j < first) ? j : first;
+                }
+            } else {
+                // shifted column j = (x + W/2) % W ; scan j descending so the smallest j survives
+#pragma unroll
+                for (int j = W - 1; j >= 0; --j) {
+                    const int x = (j + W / 2) % W;
+                    const float val = w == 0 ? r.v[x].x : r.v[x].y;
+                    first = (val == M) ? j : first;
+                }
             }
             if (r.dead[w]) first = 0;   // all-zero plane: every element is the maximum
             key = (unsigned long long)(si * W + first);
@@ -531,10 +651,11 @@ B2_HD void rows_p6(RSmem<R>& s, RRegs<R>& r, int tid) {
 }
 
 // P7: peak position known; the three rows around each peak are dumped for the Gaussian fit.
-template <class R>
-B2_HD void rows_p7(RSmem<R>& s, RRegs<R>& r, int tid) {
+template <class R, bool PAD = false>
+B2_HD void rows_p7(RSmem<R>& s, RRegs<R>& r, int tid, const RParams* pp = nullptr) {
     constexpr int W = R::W;
-    const int si = (column_of<W>(tid) + W / 2) % W;
+    const bool rowok = !PAD || column_of<W>(tid) < pp->ny;
+    const int si = PAD ? (rowok ? shifted_index(column_of<W>(tid), pp->ny) : -8) : (column_of<W>(tid) + W / 2) % W;
     float* nb = &s.nb[0][0][0];   // [w][3][W]
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
@@ -546,34 +667,39 @@ B2_HD void rows_p7(RSmem<R>& s, RRegs<R>& r, int tid) {
         const int d = si - r.pi[w];
         if (d >= -1 && d <= 1) {
 #pragma unroll
-            for (int x = 0; x < W; ++x) nb[(w * 3 + (d + 1)) * W + (x + W / 2) % W] = r.dead[w] ? 0.f : (w == 0 ? r.v[x].x : r.v[x].y);
+            for (int x = 0; x < W; ++x) {
+                const float val = r.dead[w] ? 0.f : (w == 0 ? r.v[x].x : r.v[x].y);
+                if (!PAD) nb[(w * 3 + (d + 1)) * W + (x + W / 2) % W] = val;
+                else if (x < pp->nx) nb[(w * 3 + (d + 1)) * W + shifted_index(x, pp->nx)] = val;
+            }
         }
     }
 }
 
 // P8: Gaussian fit + outputs by thread w (pyorc/velocimetry/ffpiv.py:465-466 + ffpiv.u_v_displacement).
-template <class R>
+template <class R, bool PAD = false>
 B2_HD void rows_p8(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p, const RUnit& un, int pair) {
     constexpr int W = R::W;
     if (tid >= 2) return;
+    const int ny = PAD ? p.ny : W, nx = PAD ? p.nx : W;
     const int w = tid;
     if (w == 1 && !un.valid1) return;
     const float* nb = &s.nb[0][0][0] + w * 3 * W;
     // selects, not r.x[w]: a dynamic index would demote the whole register struct to local memory
     const int pi = w == 0 ? r.pi[0] : r.pi[1], pj = w == 0 ? r.pj[0] : r.pj[1];
     const float cmax = w == 0 ? r.cmaxv[0] : r.cmaxv[1];
-    const float mean = (w == 0 ? r.sumv[0] : r.sumv[1]) / (float)R::NPX;
+    const float mean = (w == 0 ? r.sumv[0] : r.sumv[1]) / (PAD ? (float)(ny * nx) : (float)R::NPX);
     float uu, vv;
-    if (pi == 0 || pi == W - 1 || pj == 0 || pj == W - 1) {
+    if (pi == 0 || pi == ny - 1 || pj == 0 || pj == nx - 1) {
         if (p.border_nan) { uu = nanf(""); vv = nanf(""); }
-        else { uu = (float)(pj - W / 2); vv = (float)(pi - W / 2); }
+        else { uu = (float)(pj - nx / 2); vv = (float)(pi - ny / 2); }
     } else {
         const float eps = p.gauss_eps;
         const float lc = logf(cmax + eps);
         const float ll = logf(nb[0 * W + pj] + eps), lr = logf(nb[2 * W + pj] + eps);
         const float ld = logf(nb[1 * W + pj - 1] + eps), lu = logf(nb[1 * W + pj + 1] + eps);
-        vv = ((float)pi + (ll - lr) / (2.f * ll - 4.f * lc + 2.f * lr)) - (float)(W / 2);
-        uu = ((float)pj + (ld - lu) / (2.f * ld - 4.f * lc + 2.f * lu)) - (float)(W / 2);
+        vv = ((float)pi + (ll - lr) / (2.f * ll - 4.f * lc + 2.f * lr)) - (float)(ny / 2);
+        uu = ((float)pj + (ld - lu) / (2.f * ld - 4.f * lc + 2.f * lu)) - (float)(nx / 2);
     }
     float oc = cmax, os = cmax / mean;
     const int widx = w == 0 ? un.w[0] : un.w[1];
@@ -583,18 +709,24 @@ B2_HD void rows_p8(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p, const RU
 }
 
 // optional triage dump of the full planes (fftshifted, clipped) - every thread writes its row
-template <class R>
+template <class R, bool PAD = false>
 B2_HD void rows_dump_planes(RRegs<R>& r, int tid, const RParams& p, const RUnit& un, int pair) {
     constexpr int W = R::W;
     if (!p.planes) return;
-    const int si = (column_of<W>(tid) + W / 2) % W;
+    const int ny = PAD ? p.ny : W, nx = PAD ? p.nx : W;
+    if (PAD && column_of<W>(tid) >= ny) return;
+    const int si = PAD ? shifted_index(column_of<W>(tid), ny) : (column_of<W>(tid) + W / 2) % W;
     const long long nw = (long long)p.n_rows * p.n_cols;
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
         if (w == 1 && !un.valid1) continue;
-        float* dst = p.planes + (((long long)pair * nw + un.w[w]) * W + si) * W;
+        float* dst = p.planes + (((long long)pair * nw + un.w[w]) * ny + si) * nx;
 #pragma unroll
-        for (int x = 0; x < W; ++x) dst[(x + W / 2) % W] = r.dead[w] ? 0.f : (w == 0 ? r.v[x].x : r.v[x].y);
+        for (int x = 0; x < W; ++x) {
+            const float val = r.dead[w] ? 0.f : (w == 0 ? r.v[x].x : r.v[x].y);
+            if (!PAD) dst[(x + W / 2) % W] = val;
+            else if (x < nx) dst[shifted_index(x, nx)] = val;
+        }
     }
 }
 
@@ -604,22 +736,39 @@ B2_HD void rows_dump_planes(RRegs<R>& r, int tid, const RParams& p, const RUnit&
 // (run_len = n_pairs): all additions to one accumulator element come from one thread in frame order, like the
 // reference's np.sum(corr, axis=0); thread t updates row sigma(t) with 16-byte reductions.  The accumulators of a 1080p grid are
 // 31 MB, i.e. they live in L2 between frame pairs.
-template <class R>
+template <class R, bool PAD = false>
 B2_HD void rows_ens(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p, const RUnit& un, int pair, bool store) {
     constexpr int W = R::W;
-    const int si = (column_of<W>(tid) + W / 2) % W;
+    const int ny = PAD ? p.ny : W, nx = PAD ? p.nx : W;
+    const bool rowok = !PAD || column_of<W>(tid) < ny;
+    const int si = PAD ? (rowok ? shifted_index(column_of<W>(tid), ny) : 0) : (column_of<W>(tid) + W / 2) % W;
     const long long nw = (long long)p.n_rows * p.n_cols;
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
         float M = 0.f, S = 0.f;
 #pragma unroll
         for (int k = 0; k < R::NWARP; ++k) { M = fmaxf(M, bits_f(s.red[k][4 + w])); S += bits_f(s.red[k][6 + w]); }
-        const float ratio = M / (S / (float)R::NPX);
+        const float ratio = M / (S / (PAD ? (float)(ny * nx) : (float)R::NPX));
         const int widx = w == 0 ? un.w[0] : un.w[1];
         bool ok = (M >= p.corr_min) && (ratio >= p.s2n_min) && !r.dead[w];   // dead: 0 / 0 = NaN fails the test in the reference
         if (p.keep && !p.keep[widx]) ok = false;                             // NaN plane in the reference -> masked out
         if (!store || (w == 1 && !un.valid1)) continue;
-        if (ok) {
+        if (ok && PAD) {
+            // accumulator planes are [n_windows][ny][nx]: rows are not 16-byte aligned, scalar reductions on the block
+            if (rowok) {
+                float* dst = p.ens_sum + ((long long)widx * ny + si) * nx;
+#pragma unroll
+                for (int x = 0; x < W; ++x) {
+                    if (x < nx) {
+#ifdef __CUDA_ARCH__
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + shifted_index(x, nx)), "f"(w == 0 ? r.v[x].x : r.v[x].y) : "memory");
+#else
+                        dst[shifted_index(x, nx)] += w == 0 ? r.v[x].x : r.v[x].y;
+#endif
+                    }
+                }
+            }
+        } else if (ok) {
             float* dst = p.ens_sum + ((long long)widx * W + si) * W;
 #pragma unroll
             for (int c = 0; c < W / 4; ++c) {

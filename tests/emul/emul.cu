@@ -95,7 +95,7 @@ static void emul_transpose(RSmem<R>& s, std::vector<RRegs<R>>& regs) {
     for (int t = 0; t < W; ++t) { const int wq = t >> 5; load(t, wq, wq); }
 }
 
-template <class R, bool F32>
+template <class R, bool F32, bool PAD = false>
 static int run_rows(RParams p) {
     constexpr int W = R::W;
     RSmem<R>* sp = new RSmem<R>();
@@ -107,7 +107,7 @@ static int run_rows(RParams p) {
             const bool have_prev = f > un.f0;
             if (!F32) {
             // "TMA": fill the tile from frame f (swizzled exact boxes, or 16-byte wider boxes from the boundary below)
-            const bool aligned = (p.sx % 16) == 0;
+            const bool aligned = !PAD && (p.sx % 16) == 0;
             int xoff[2] = {0, 0};
             for (int w = 0; w < 2; ++w) {
                 if (aligned) {
@@ -121,12 +121,18 @@ static int run_rows(RParams p) {
                     for (int row = 0; row < W; ++row)
                         for (int b = 0; b < R::WB; ++b)
                             s.tile()[(w * W + row) * R::WB + b] =
-                                (xa + b < p.pitch) ? p.frames[(long long)f * p.frame_stride + (long long)(un.y0[w] + row) * p.pitch + xa + b] : 0;
+                                (xa + b < p.pitch && (!PAD || un.y0[w] + row < p.height))
+                                    ? p.frames[(long long)f * p.frame_stride + (long long)(un.y0[w] + row) * p.pitch + xa + b] : 0;
                 }
             }
             memset(s.red, 0, sizeof(s.red));
+            if (PAD) {
+                for (int t = 0; t < W; ++t) rows_p1_pad<R>(s, regs[t], t, p, xoff[0], xoff[1]);
+                for (int t = 0; t < W; ++t) rows_p2_pre_pad<R>(s, regs[t], t, p);
+            } else {
             for (int t = 0; t < W; ++t) { if (aligned) rows_p1<R, true>(s, regs[t], t); else rows_p1<R, false>(s, regs[t], t, xoff[0], xoff[1]); }
             for (int t = 0; t < W; ++t) rows_p2_pre<R>(s, regs[t], t, p.clip_norm);
+            }
             } else {
                 // float32: 128-byte-wide boxes, SWIZZLE_128B; one window per TMA phase for 64x64, both for 32x32
                 auto fill = [&](int w, int toff) {
@@ -159,7 +165,7 @@ static int run_rows(RParams p) {
                 for (int t = 0; t < W; ++t) {
                     const int pt = (t & ~31) | partner_lane_of<W>(t);
                     regs[t].r0 = regs[t].r1 = make_float2(0.f, 0.f);
-                    cross_step_a<R>(s, regs[t], t, ky, snap[pt].v[(W - ky) % W], have_prev, regs[t].r0, regs[t].r1);
+                    cross_step_a<R, PAD>(s, regs[t], t, ky, snap[pt].v[(W - ky) % W], have_prev, regs[t].r0, regs[t].r1, &p);
                 }
                 if (have_prev && ky != 0 && ky != W / 2) {
                     std::vector<float2> q(W);
@@ -178,13 +184,13 @@ static int run_rows(RParams p) {
                     const bool d0 = regs[t].half_alpha_prev[0] == 0.f || regs[t].half_alpha_new[0] == 0.f;
                     const bool d1 = regs[t].half_alpha_prev[1] == 0.f || regs[t].half_alpha_new[1] == 0.f;
                     fft_reg<W, 0>(regs[t].v);
-                    rows_p5_post<R>(s, regs[t], t, d0, d1);
+                    rows_p5_post<R, PAD>(s, regs[t], t, d0, d1, &p);
                 }
                 for (int k = 0; k < R::NWARP; ++k) s.redk[k][0] = s.redk[k][1] = ~0ull;
-                for (int t = 0; t < W; ++t) rows_p6<R>(s, regs[t], t);
-                for (int t = 0; t < W; ++t) rows_dump_planes<R>(regs[t], t, p, un, f - 1);
-                for (int t = 0; t < W; ++t) rows_p7<R>(s, regs[t], t);
-                for (int t = 0; t < W; ++t) rows_p8<R>(s, regs[t], t, p, un, f - 1);
+                for (int t = 0; t < W; ++t) rows_p6<R, PAD>(s, regs[t], t, &p);
+                for (int t = 0; t < W; ++t) rows_dump_planes<R, PAD>(regs[t], t, p, un, f - 1);
+                for (int t = 0; t < W; ++t) rows_p7<R, PAD>(s, regs[t], t, &p);
+                for (int t = 0; t < W; ++t) rows_p8<R, PAD>(s, regs[t], t, p, un, f - 1);
             }
             for (int t = 0; t < W; ++t) {
                 regs[t].half_alpha_prev[0] = regs[t].half_alpha_new[0];
@@ -211,6 +217,30 @@ static int emul_rows_any(const unsigned char* frames, int is_f32, int n_frames, 
     if (win == 64) return is_f32 ? run_rows<RCfg<64>, true>(p) : run_rows<RCfg<64>, false>(p);
     if (win == 32) return is_f32 ? run_rows<RCfg<32>, true>(p) : run_rows<RCfg<32>, false>(p);
     return -1;
+}
+// padded mode: any uint8 window up to 32 px per side, any stride (piv_rows.cuh "Padded mode")
+extern "C" int b2piv_emul_rows_pad(const unsigned char* frames, int n_frames, int H, int W, int wy, int wx, int oy, int ox, int run_len,
+                                   int clip_norm, int border_nan, float eps, const unsigned char* keep, float* u, float* v, float* cmax,
+                                   float* s2n, float* planes) {
+    RParams p;
+    memset(&p, 0, sizeof(p));
+    p.frames = frames; p.pitch = W; p.frame_stride = (long long)H * W; p.height = H;
+    p.n_rows = (H - wy) / (wy - oy) + 1; p.n_cols = (W - wx) / (wx - ox) + 1;
+    p.sy = wy - oy; p.sx = wx - ox; p.n_pairs = n_frames - 1;
+    p.run_len = run_len > 0 && run_len < p.n_pairs ? run_len : p.n_pairs;
+    const int nw = p.n_rows * p.n_cols;
+    p.n_units = ((nw + 1) / 2) * ((p.n_pairs + p.run_len - 1) / p.run_len);
+    p.clip_norm = clip_norm; p.border_nan = border_nan; p.gauss_eps = eps; p.keep = keep;
+    p.u = u; p.v = v; p.cmax = cmax; p.s2n = s2n; p.planes = planes;
+    p.ny = wy; p.nx = wx;
+    const int m = wy > wx ? wy : wx;
+    const int P = 2 * m <= 32 ? 32 : 64;
+    if (2 * m > 64) return -1;
+    p.pad_scale = (float)(1.0 / ((double)P * P * wy * wx));
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int k = 0; k <= P / 2; ++k) { const double th = two_pi * (double)((k * wy) % P) / P; p.pad_ty[k] = make_float2((float)(1.0 + cos(th)), (float)(-sin(th))); }
+    for (int k = 0; k < P; ++k) { const double th = two_pi * (double)((k * wx) % P) / P; p.pad_tx[k] = make_float2((float)(1.0 + cos(th)), (float)(-sin(th))); }
+    return P == 32 ? run_rows<RCfg<32>, false, true>(p) : run_rows<RCfg<64>, false, true>(p);
 }
 extern "C" int b2piv_emul_rows(const unsigned char* frames, int n_frames, int H, int W, int win, int ovl, int run_len, int clip_norm,
                                int border_nan, float eps, const unsigned char* keep, float* u, float* v, float* cmax, float* s2n,

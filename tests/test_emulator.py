@@ -199,3 +199,50 @@ def test_rows_phases_float32_frames(emul_rows, win, ovl, shape, run_len):
     ok = np.isfinite(u)
     assert np.abs(eu[ok] - u[ok]).max() < 1e-3 and np.abs(ev[ok] - v[ok]).max() < 1e-3
     assert np.abs(ec - c).max() < 3e-6
+
+
+@pytest.fixture(scope="module")
+def emul_rows_pad():
+    import __graft_entry__ as g
+
+    lib = ctypes.CDLL(g.build_emulator())
+
+    def run(imgs, ws, ov, run_len=0, clip=0, border_nan=1):
+        imgs = np.ascontiguousarray(imgs)
+        n, H, W = imgs.shape
+        nr, nc = O.get_array_shape((H, W), ws, ov)
+        outs = [np.full((n - 1, nr, nc), -7, np.float32) for _ in range(4)]
+        planes = np.zeros((n - 1, nr * nc, ws[0], ws[1]), np.float32)
+        rc = lib.b2piv_emul_rows_pad(
+            imgs.ctypes.data_as(ctypes.c_void_p), n, H, W, ws[0], ws[1], ov[0], ov[1], run_len, clip, border_nan, ctypes.c_float(1e-7), None,
+            *[o.ctypes.data_as(ctypes.c_void_p) for o in outs], planes.ctypes.data_as(ctypes.c_void_p),
+        )
+        assert rc == 0
+        return outs, planes
+
+    return run
+
+
+@pytest.mark.parametrize("ws,ov,shape,run_len", [((26, 26), (12, 12), (3, 96, 128), 0), ((20, 20), (10, 10), (4, 70, 96), 2),
+                                                  ((10, 10), (5, 5), (3, 48, 64), 0), ((30, 18), (15, 9), (3, 100, 80), 0),
+                                                  ((32, 32), (15, 15), (3, 100, 112), 1), ((16, 16), (8, 8), (3, 50, 64), 0),
+                                                  ((26, 26), (12, 12), (2, 90, 96), 0)])
+@pytest.mark.parametrize("clip", [0, 1])
+def test_rows_padded_phases_match_oracle(emul_rows_pad, ws, ov, shape, run_len, clip):
+    """Padded mode of the row-per-thread kernel (pyorc's non power-of-two windows, any stride): zero-padded embedding,
+    byte-granular row offsets, the 2 x 2 tiling applied as a spectrum factor, block-restricted max / mean / first-argmax."""
+    O.CLIP_NORMALIZED = bool(clip)
+    imgs = synth.particle_frames(*shape, dtype=np.uint8)
+    imgs[:, : ws[0], : ws[1] + 3] = 0          # a dead window (and a partly dark neighbour)
+    nr, nc = O.get_array_shape(shape[1:], ws, ov)
+    _, _, corr = O.cross_corr(imgs, ws, ov)
+    u, v, c, s = O.uv_timestep(imgs, nc, nr, ws, ov)
+    (eu, ev, ec, es), pl = emul_rows_pad(imgs, ws, ov, run_len, clip)
+    assert np.abs(pl - corr).max() < 3e-6
+    assert np.array_equal(np.isnan(eu), np.isnan(u)) and np.array_equal(np.isnan(es), np.isnan(s))
+    ok = np.isfinite(u)
+    same = np.abs(np.round(eu[ok]) - np.round(u[ok])) + np.abs(np.round(ev[ok]) - np.round(v[ok])) < 0.5
+    assert same.mean() > 0.99
+    assert np.abs(eu[ok][same] - u[ok][same]).max() < 2e-3 and np.abs(ev[ok][same] - v[ok][same]).max() < 2e-3
+    assert np.abs(ec - c).max() < 3e-6
+    assert np.nanmax(np.abs(es - s) / np.abs(s)) < 2e-5

@@ -170,11 +170,60 @@ PADDED_CASES = [
 
 @pytest.mark.parametrize("ws,ov,shape", PADDED_CASES)
 @pytest.mark.parametrize("dtype", [np.uint8, np.float32])
-def test_padded_fft_kernel_non_power_of_two_windows(engine, ws, ov, shape, dtype):
-    """pyorc's usual windows (26 from a camera-config 25, 20, 50 ...) through the power-of-two FFT kernel, exactly."""
+@pytest.mark.parametrize("variant", [0, 1])   # 0: auto (uint8 windows up to 32 px take the padded row-per-thread kernel); 1: shared-memory kernel
+def test_padded_fft_kernel_non_power_of_two_windows(engine, ws, ov, shape, dtype, variant):
+    """pyorc's usual windows (26 from a camera-config 25, 20, 50 ...) through the power-of-two FFT kernels, exactly."""
     imgs = synth.particle_frames(*shape, dtype=dtype)
     imgs[:, :20, :20] = 0
-    compare(engine, imgs, ws, ov, 0, variant=0)
+    compare(engine, imgs, ws, ov, 0, variant=variant)
+    engine.set_option("kernel_variant", 0.0)
+
+
+ROWS_PAD_CASES = [
+    ((26, 26), (12, 12), (4, 150, 192), 0),     # pyorc's default geometry: window 25 -> 26, overlap 12, stride 14
+    ((26, 26), (12, 12), (5, 100, 176), 2),     # short runs (first frame of every unit stores nothing)
+    ((20, 20), (10, 10), (3, 90, 128), 0),
+    ((30, 18), (15, 9), (3, 100, 96), 0),       # rectangular
+    ((10, 10), (5, 5), (3, 60, 80), 0),         # -> 32x32 plane
+    ((16, 16), (8, 8), (3, 70, 96), 0),         # power of two below the native sizes
+    ((32, 32), (15, 15), (3, 100, 112), 0),     # native size with an odd stride (17): byte-granular window starts
+    ((22, 22), (11, 11), (3, 77, 91), 0),       # frame width that is not a multiple of 16: the engine's device copy is pitched
+]
+
+
+@pytest.mark.parametrize("ws,ov,shape,run_len", ROWS_PAD_CASES)
+@pytest.mark.parametrize("clip", [0, 1])
+def test_rows_kernel_padded_mode(engine, ws, ov, shape, run_len, clip):
+    """Padded mode of the row-per-thread kernel (kernel_variant 4): zero-padded window, tiling as a spectrum factor, the
+    reference's plane read from the wrap-free lags - against the oracle, planes included."""
+    imgs = synth.particle_frames(*shape, dtype=np.uint8)
+    imgs[:, : ws[0], : ws[1] + 3] = 0
+    compare(engine, imgs, ws, ov, clip, variant=4, run_len=run_len)
+    engine.set_option("kernel_variant", 0.0)
+    engine.set_option("run_len", 0.0)
+
+
+def test_rows_kernels_on_device_tensors_need_an_aligned_pitch(engine):
+    """Host frames are copied into a 16-byte pitched buffer by the engine (any width qualifies); a caller-owned device
+    tensor is used in place, so an odd pitch is refused by the TMA kernels and taken by the shared-memory kernel."""
+    import torch
+
+    O.CLIP_NORMALIZED = False
+    engine.set_option("clip_normalized", 0.0)
+    imgs = synth.particle_frames(3, 77, 91, dtype=np.uint8)
+    d = torch.from_numpy(imgs).cuda()
+    engine.set_option("kernel_variant", 4.0)
+    with pytest.raises(NotImplementedError):
+        engine.pairs(d, (22, 22), (11, 11))
+    engine.set_option("kernel_variant", 0.0)
+    got = [t.cpu().numpy() for t in engine.pairs(d, (22, 22), (11, 11))]
+    host = engine.pairs(imgs, (22, 22), (11, 11))           # padded rows kernel on the pitched copy
+    nr, nc = O.get_array_shape(imgs.shape[1:], (22, 22), (11, 11))
+    u, v, c, s_ = O.uv_timestep(imgs, nc, nr, (22, 22), (11, 11))
+    for g in (got, host):
+        ok = np.isfinite(u) & np.isfinite(g[0])
+        assert np.array_equal(np.isnan(g[0]), np.isnan(u))
+        assert np.abs(g[0][ok] - u[ok]).max() <= 2e-3 and np.abs(g[2] - c).max() <= 5e-6
 
 
 def test_odd_window_count_and_ragged_edges(engine):

@@ -49,6 +49,13 @@ def run_ens(H, W, ws, ov, n_frames, reps=5, dtype="uint8", variant=0):
     e.close()
 
 if __name__ == "__main__":
+    if "--pad" in sys.argv:   # non power-of-two windows: padded row-per-thread kernel (4) vs shared-memory padded (1) vs direct (3)
+        for ws, ov in (((26, 26), (12, 12)), ((20, 20), (10, 10)), ((30, 30), (15, 15)), ((10, 10), (5, 5)), ((12, 12), (6, 6)), ((16, 16), (8, 8)), ((14, 14), (7, 7))):
+            for variant in (4, 1, 3):
+                run(1080, 1920, ws, ov, 11, variant=variant)
+        run_ens(1080, 1920, (26, 26), (12, 12), 21, variant=0)
+        run_ens(1080, 1920, (26, 26), (12, 12), 21, variant=1)
+        sys.exit(0)
     if "--ens" in sys.argv:
         for variant in (1, 0):
             run_ens(1080, 1920, (64, 64), (32, 32), 101, variant=variant)

@@ -131,13 +131,19 @@ def test_rows_kernel_refuses_stride_not_multiple_of_4(engine):
     compare(engine, imgs, (32, 32), (22, 22), 0)        # auto: generic kernel
 
 
-def test_rows_kernel_refuses_unaligned_pitch(engine):
-    imgs = synth.particle_frames(3, 150, 203, dtype=np.uint8)   # pitch 203 B: TMA needs 16-byte strides
+def test_rows_kernel_takes_any_frame_width_from_the_host(engine):
+    """pitch 203 B: TMA needs 16-byte strides, so the engine's device copy of host frames is pitched (a caller-owned
+    device tensor with that pitch is refused, see test_rows_kernels_on_device_tensors_need_an_aligned_pitch)."""
+    import torch
+
+    imgs = synth.particle_frames(3, 150, 203, dtype=np.uint8)
+    compare(engine, imgs, (64, 64), (32, 32), 1, variant=2)
     engine.set_option("kernel_variant", 2.0)
     with pytest.raises(NotImplementedError):
-        engine.pairs(imgs, (64, 64), (32, 32))
+        engine.pairs(torch.from_numpy(imgs).cuda(), (64, 64), (32, 32))
     engine.set_option("kernel_variant", 0.0)
-    compare(engine, imgs, (64, 64), (32, 32), 1)   # auto falls back to the generic kernel
+    compare(engine, imgs.astype(np.float32), (64, 64), (32, 32), 0, variant=2)   # float32 rows: 812-byte rows -> 816
+    engine.set_option("kernel_variant", 0.0)
 
 
 DIRECT_CASES = [

@@ -480,6 +480,7 @@ struct b2piv_engine {
     unsigned char* d_frames = nullptr; size_t cap_frames = 0;
     float* d_out = nullptr; size_t cap_out = 0;       // 4 result fields
     float* d_planes = nullptr; size_t cap_planes = 0;
+    float* d_planes_nat = nullptr; size_t cap_planes_nat = 0;   // padded rows kernel: W x W planes in natural lag order
     unsigned char* d_keep = nullptr; size_t cap_keep = 0;
     // ensemble accumulators
     float* d_pre_mean = nullptr; size_t cap_pre_mean = 0;   // pre-processing workspaces
@@ -638,6 +639,18 @@ static bool rows_eligible(const b2piv_engine* e, const void* d_frames, long long
     return get_encode_tiled() != nullptr;
 }
 
+// triage path of the padded rows kernel: W x W planes in natural lag order -> the reference's fftshifted ny x nx planes
+__global__ void planes_reorder_kernel(const float* __restrict__ nat, float* __restrict__ out, long long n_planes, int W, int ny, int nx) {
+    const long long n = n_planes * ny * nx;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int ix = (int)(i % nx), iy = (int)((i / nx) % ny);
+        const long long pl = i / ((long long)nx * ny);
+        const int hy = ny / 2, hx = nx / 2;
+        const int qy = iy < hy ? iy + ny - hy : iy - hy, qx = ix < hx ? ix + nx - hx : ix - hx;   // lag (j + n - n/2) % n
+        out[i] = nat[(pl * W + qy) * W + qx];
+    }
+}
+
 template <class R, int G, bool ROLLED, bool ALIGNED, bool F32, bool ENS = false, bool PAD = false>
 static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st, const EnsParams* ep = nullptr) {
     constexpr int W = R::W;
@@ -667,6 +680,13 @@ static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st, const
         const double two_pi = 6.283185307179586476925286766559;
         for (int k = 0; k <= W / 2; ++k) { const double th = two_pi * (double)((k * p.ny) % W) / W; p.pad_ty[k] = make_float2((float)(1.0 + cos(th)), (float)(-sin(th))); }
         for (int k = 0; k < W; ++k) { const double th = two_pi * (double)((k * p.nx) % W) / W; p.pad_tx[k] = make_float2((float)(1.0 + cos(th)), (float)(-sin(th))); }
+        for (int k = 0; k < W / 4; ++k) { const int left = p.nx - 4 * k; p.pad_mask[k] = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << (8 * left)) - 1u)); }
+        for (int x = 0; x < W; ++x) p.pad_cm[x] = x < p.nx ? 1.f : 0.f;
+        if (gp.planes) {
+            const int rcp = ensure(e, &e->d_planes_nat, &e->cap_planes_nat, (size_t)gp.n_pairs * gp.n_rows * gp.n_cols * W * W * sizeof(float));
+            if (rcp) return rcp;
+            p.planes = e->d_planes_nat;
+        }
     }
     auto kern = piv_rows_kernel<R, G, ROLLED, ALIGNED, F32, ENS, PAD>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -691,6 +711,12 @@ static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st, const
     kern<<<(unsigned)grid, R::NT * G, smem, st>>>(tmap, p);
     CK(cudaGetLastError());
     e->launches++;
+    if (PAD && gp.planes) {
+        const long long n_planes = (long long)gp.n_pairs * gp.n_rows * gp.n_cols;
+        planes_reorder_kernel<<<e->sm_count * 8, 256, 0, st>>>(e->d_planes_nat, gp.planes, n_planes, W, p.ny, p.nx);
+        CK(cudaGetLastError());
+        e->launches++;
+    }
     return B2PIV_OK;
 }
 
@@ -871,7 +897,7 @@ void b2piv_destroy(b2piv_engine* e) {
     cudaDeviceSynchronize();
     cudaFree(e->d_twx); cudaFree(e->d_twy); cudaFree(e->d_frames); cudaFree(e->d_out); cudaFree(e->d_planes);
     cudaFree(e->d_keep); cudaFree(e->d_ens_sum); cudaFree(e->d_ens_cnt); cudaFree(e->d_pre_mean); cudaFree(e->d_pre_mm);
-    cudaFree(e->d_proj_off); cudaFree(e->d_proj_src);
+    cudaFree(e->d_proj_off); cudaFree(e->d_proj_src); cudaFree(e->d_planes_nat);
     for (auto ev : e->ev_chunk) cudaEventDestroy(ev);
     if (e->ev_k0) cudaEventDestroy(e->ev_k0);
     if (e->ev_k1) cudaEventDestroy(e->ev_k1);

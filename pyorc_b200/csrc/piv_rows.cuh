@@ -125,6 +125,8 @@ struct RParams {
     float pad_scale;               // 1 / (W*W * ny*nx)
     float2 pad_ty[33];             // Ty(ky) = 1 + exp(-2 pi i ky ny / W), ky = 0 .. W/2
     float2 pad_tx[64];             // Tx(kx) = 1 + exp(-2 pi i kx nx / W)
+    unsigned pad_mask[16];         // byte mask of source word k: bytes 4k .. 4k+3 that lie inside the window (x < nx)
+    float pad_cm[64];              // 1.0f for x < nx, else 0.0f (statically indexed -> constant-bank operands)
     int height;                    // host emulator only (rows below the frame read as 0, like the TMA fill)
 };
 
@@ -275,7 +277,7 @@ template <class R>
 B2_HD void rows_p1_pad(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p, int xoff0, int xoff1) {
     constexpr int W = R::W;
     const int row = column_of<W>(tid);
-    const bool rowok = row < p.ny;
+    const unsigned rowmask = row < p.ny ? 0xffffffffu : 0u;
     unsigned S[2] = {0, 0}, Q[2] = {0, 0};
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
@@ -287,9 +289,7 @@ B2_HD void rows_p1_pad(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p, int 
         for (int k = 0; k <= W / 4; ++k) wd[k] = *reinterpret_cast<const unsigned*>(base + 4 * k);
 #pragma unroll
         for (int k = 0; k < W / 4; ++k) {
-            const int left = p.nx - 4 * k;   // bytes of this word inside the window
-            const unsigned mask = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << (8 * left)) - 1u));
-            r.px[w][k] = rowok ? (funnel_r(wd[k], wd[k + 1], sh) & mask) : 0u;
+            r.px[w][k] = funnel_r(wd[k], wd[k + 1], sh) & p.pad_mask[k] & rowmask;
             S[w] = dp4a_u(r.px[w][k], 0x01010101u, S[w]);
             Q[w] = dp4a_u(r.px[w][k], r.px[w][k], Q[w]);
         }
@@ -323,16 +323,18 @@ B2_HD void rows_p2_pre_pad(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p) 
         r.mean_new[w] = (float)S / (float)npx;
         r.half_alpha_new[w] = m2 ? 0.5f * (float)npx * (1.0f / sqrtf((float)m2)) : 0.f;
     }
+    // masked bytes are 0, so a pixel outside the window must only NOT get the mean subtracted: rows >= ny use mean 0,
+    // columns >= nx a 0/1 factor from the constant bank - one FFMA per value, like the FADD of the native path
     const bool rowok = column_of<W>(tid) < p.ny;
+    const float nm0 = rowok ? -r.mean_new[0] : 0.f, nm1 = rowok ? -r.mean_new[1] : 0.f;
 #pragma unroll
     for (int k = 0; k < W / 4; ++k) {
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            const bool ok = rowok && (4 * k + b < p.nx);
-            float a0 = byte_to_float(r.px[0][k], b) - r.mean_new[0];
-            float a1 = byte_to_float(r.px[1][k], b) - r.mean_new[1];
+            float a0 = fmaf(p.pad_cm[4 * k + b], nm0, byte_to_float(r.px[0][k], b));
+            float a1 = fmaf(p.pad_cm[4 * k + b], nm1, byte_to_float(r.px[1][k], b));
             if (p.clip_norm) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-            r.v[4 * k + b] = ok ? make_float2(a0, a1) : make_float2(0.f, 0.f);
+            r.v[4 * k + b] = make_float2(a0, a1);
         }
     }
     r.tx = p.pad_tx[column_of<W>(tid)];
@@ -560,20 +562,20 @@ template <class R, bool PAD = false>
 B2_HD void rows_p5_post(RSmem<R>& s, RRegs<R>& r, int tid, bool dead0, bool dead1, const RParams* pp = nullptr) {
     constexpr int W = R::W;
     float m0 = 0.f, m1 = 0.f, s0 = 0.f, s1 = 0.f;
-    const bool rowok = !PAD || column_of<W>(tid) < pp->ny;
 #pragma unroll
     for (int x = 0; x < W; ++x) {
-        // clip to [0, 1] (inputs are uint8, no NaNs can occur, so fmin/fmax are exact here)
-        float a = fminf(fmaxf(r.v[x].x, 0.f), 1.f), b = fminf(fmaxf(-r.v[x].y, 0.f), 1.f);
-        if (PAD && !(rowok && x < pp->nx)) { a = 0.f; b = 0.f; }
+        // clip to [0, 1] (inputs are uint8, no NaNs can occur, so fmin/fmax are exact here); padded mode: the upper bound
+        // is 0 for the columns outside the window's lags (rows outside are dropped below and never read afterwards)
+        const float hi = PAD ? pp->pad_cm[x] : 1.f;
+        const float a = fminf(fmaxf(r.v[x].x, 0.f), hi), b = fminf(fmaxf(-r.v[x].y, 0.f), hi);
         r.v[x] = make_float2(a, b);
         m0 = fmaxf(a, m0); m1 = fmaxf(b, m1);
         s0 += a; s1 += b;
     }
     // a window with zero variance has an exactly-zero plane in the reference (the packed inverse FFT leaves ~1e-10
     // cross-talk from its partner window): force max = sum = 0 here, first-argmax 0 in rows_p6, zeros in the dumps
-    if (dead0) { m0 = 0.f; s0 = 0.f; }
-    if (dead1) { m1 = 0.f; s1 = 0.f; }
+    if (dead0 || (PAD && column_of<W>(tid) >= pp->ny)) { m0 = 0.f; s0 = 0.f; }
+    if (dead1 || (PAD && column_of<W>(tid) >= pp->ny)) { m1 = 0.f; s1 = 0.f; }
     r.dead[0] = dead0; r.dead[1] = dead1;
     r.rowmax[0] = m0; r.rowmax[1] = m1; r.rowsum[0] = s0; r.rowsum[1] = s1;
 #ifdef __CUDA_ARCH__
@@ -619,12 +621,25 @@ B2_HD void rows_p6(RSmem<R>& s, RRegs<R>& r, int tid, const RParams* pp = nullpt
         if (r.rowmax[w] == M && rowok) {
             int first = W;
             if (PAD) {
+                // match mask over natural columns, then first match in the reference's order: lags >= nx - nx/2 (its
+                // columns 0 ..) before lags < nx - nx/2.  M == 0: every element of the plane is the maximum -> first = 0.
+                unsigned mlo = 0u, mhi = 0u;
 #pragma unroll
                 for (int x = 0; x < W; ++x) {
                     const float val = w == 0 ? r.v[x].x : r.v[x].y;
-                    const int j = shifted_index(x, pp->nx);
-                    first = (val == M && x < pp->nx && j < first) ? j : first;
+                    if (x < 32) mlo |= (val == M) ? (1u << x) : 0u; else mhi |= (val == M) ? (1u << (x - 32)) : 0u;
                 }
+                const unsigned long long mm = ((unsigned long long)mhi << 32) | mlo;
+                const int nh = pp->nx - pp->nx / 2;
+                const unsigned long long seg_hi = mm >> nh, seg_lo = mm & ((1ull << nh) - 1ull);
+                unsigned long long t = seg_hi ? seg_hi : seg_lo;
+#ifdef __CUDA_ARCH__
+                const int k = __ffsll((long long)t) - 1;
+#else
+                int k = 0;
+                while (!(t & 1ull) && k < 63) { t >>= 1; ++k; }
+#endif
+                first = M == 0.f ? 0 : (seg_hi ? k : k + pp->nx / 2);
             } else {
                 // shifted column j = (x + W/2) % W ; scan j descending so the smallest j survives
 #pragma unroll
@@ -669,8 +684,7 @@ B2_HD void rows_p7(RSmem<R>& s, RRegs<R>& r, int tid, const RParams* pp = nullpt
 #pragma unroll
             for (int x = 0; x < W; ++x) {
                 const float val = r.dead[w] ? 0.f : (w == 0 ? r.v[x].x : r.v[x].y);
-                if (!PAD) nb[(w * 3 + (d + 1)) * W + (x + W / 2) % W] = val;
-                else if (x < pp->nx) nb[(w * 3 + (d + 1)) * W + shifted_index(x, pp->nx)] = val;
+                nb[(w * 3 + (d + 1)) * W + (PAD ? x : (x + W / 2) % W)] = val;   // padded: natural lag order, mapped in rows_p8
             }
         }
     }
@@ -696,8 +710,13 @@ B2_HD void rows_p8(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p, const RU
     } else {
         const float eps = p.gauss_eps;
         const float lc = logf(cmax + eps);
-        const float ll = logf(nb[0 * W + pj] + eps), lr = logf(nb[2 * W + pj] + eps);
-        const float ld = logf(nb[1 * W + pj - 1] + eps), lu = logf(nb[1 * W + pj + 1] + eps);
+        // padded mode keeps the rows in natural lag order: reference column j <- lag (j + nx - nx/2) % nx
+        const int h = nx / 2;
+        const int q0 = PAD ? (pj < h ? pj + nx - h : pj - h) : pj;
+        const int qm = PAD ? (pj - 1 < h ? pj - 1 + nx - h : pj - 1 - h) : pj - 1;
+        const int qp = PAD ? (pj + 1 < h ? pj + 1 + nx - h : pj + 1 - h) : pj + 1;
+        const float ll = logf(nb[0 * W + q0] + eps), lr = logf(nb[2 * W + q0] + eps);
+        const float ld = logf(nb[1 * W + qm] + eps), lu = logf(nb[1 * W + qp] + eps);
         vv = ((float)pi + (ll - lr) / (2.f * ll - 4.f * lc + 2.f * lr)) - (float)(ny / 2);
         uu = ((float)pj + (ld - lu) / (2.f * ld - 4.f * lc + 2.f * lu)) - (float)(nx / 2);
     }
@@ -713,20 +732,16 @@ template <class R, bool PAD = false>
 B2_HD void rows_dump_planes(RRegs<R>& r, int tid, const RParams& p, const RUnit& un, int pair) {
     constexpr int W = R::W;
     if (!p.planes) return;
-    const int ny = PAD ? p.ny : W, nx = PAD ? p.nx : W;
-    if (PAD && column_of<W>(tid) >= ny) return;
-    const int si = PAD ? shifted_index(column_of<W>(tid), ny) : (column_of<W>(tid) + W / 2) % W;
+    // padded mode dumps the whole W x W plane in NATURAL lag order (planes_reorder_kernel crops / shifts it afterwards):
+    // no per-element conditions in this kernel's instruction stream
+    const int si = PAD ? column_of<W>(tid) : (column_of<W>(tid) + W / 2) % W;
     const long long nw = (long long)p.n_rows * p.n_cols;
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
         if (w == 1 && !un.valid1) continue;
-        float* dst = p.planes + (((long long)pair * nw + un.w[w]) * ny + si) * nx;
+        float* dst = p.planes + (((long long)pair * nw + un.w[w]) * W + si) * W;
 #pragma unroll
-        for (int x = 0; x < W; ++x) {
-            const float val = r.dead[w] ? 0.f : (w == 0 ? r.v[x].x : r.v[x].y);
-            if (!PAD) dst[(x + W / 2) % W] = val;
-            else if (x < nx) dst[shifted_index(x, nx)] = val;
-        }
+        for (int x = 0; x < W; ++x) dst[PAD ? x : (x + W / 2) % W] = r.dead[w] ? 0.f : (w == 0 ? r.v[x].x : r.v[x].y);
     }
 }
 
@@ -756,14 +771,19 @@ B2_HD void rows_ens(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p, const R
         if (ok && PAD) {
             // accumulator planes are [n_windows][ny][nx]: rows are not 16-byte aligned, scalar reductions on the block
             if (rowok) {
-                float* dst = p.ens_sum + ((long long)widx * ny + si) * nx;
+                // lag x goes to column x + nx/2 (x < nx - nx/2) or x - (nx - nx/2): two base pointers, static offsets
+                float* row = p.ens_sum + ((long long)widx * ny + si) * nx;
+                float* base_lo = row + nx / 2;
+                float* base_hi = row - (nx - nx / 2);
+                const int nh = nx - nx / 2;
 #pragma unroll
                 for (int x = 0; x < W; ++x) {
                     if (x < nx) {
+                        float* dst = (x < nh ? base_lo : base_hi) + x;
 #ifdef __CUDA_ARCH__
-                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + shifted_index(x, nx)), "f"(w == 0 ? r.v[x].x : r.v[x].y) : "memory");
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst), "f"(w == 0 ? r.v[x].x : r.v[x].y) : "memory");
 #else
-                        dst[shifted_index(x, nx)] += w == 0 ? r.v[x].x : r.v[x].y;
+                        *dst += w == 0 ? r.v[x].x : r.v[x].y;
 #endif
                     }
                 }

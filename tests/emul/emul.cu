@@ -240,7 +240,22 @@ extern "C" int b2piv_emul_rows_pad(const unsigned char* frames, int n_frames, in
     const double two_pi = 6.283185307179586476925286766559;
     for (int k = 0; k <= P / 2; ++k) { const double th = two_pi * (double)((k * wy) % P) / P; p.pad_ty[k] = make_float2((float)(1.0 + cos(th)), (float)(-sin(th))); }
     for (int k = 0; k < P; ++k) { const double th = two_pi * (double)((k * wx) % P) / P; p.pad_tx[k] = make_float2((float)(1.0 + cos(th)), (float)(-sin(th))); }
-    return P == 32 ? run_rows<RCfg<32>, false, true>(p) : run_rows<RCfg<64>, false, true>(p);
+    for (int k = 0; k < P / 4; ++k) { const int left = wx - 4 * k; p.pad_mask[k] = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << (8 * left)) - 1u)); }
+    for (int x = 0; x < P; ++x) p.pad_cm[x] = x < wx ? 1.f : 0.f;
+    // the kernel dumps W x W planes in natural lag order; crop / shift like planes_reorder_kernel
+    std::vector<float> nat;
+    const long long n_planes = (long long)p.n_pairs * nw;
+    if (planes) { nat.assign((size_t)n_planes * P * P, 0.f); p.planes = nat.data(); }
+    const int rc = P == 32 ? run_rows<RCfg<32>, false, true>(p) : run_rows<RCfg<64>, false, true>(p);
+    if (planes)
+        for (long long pl = 0; pl < n_planes; ++pl)
+            for (int iy = 0; iy < wy; ++iy)
+                for (int ix = 0; ix < wx; ++ix) {
+                    const int hy = wy / 2, hx = wx / 2;
+                    const int qy = iy < hy ? iy + wy - hy : iy - hy, qx = ix < hx ? ix + wx - hx : ix - hx;
+                    planes[(pl * wy + iy) * wx + ix] = nat[(pl * P + qy) * P + qx];
+                }
+    return rc;
 }
 extern "C" int b2piv_emul_rows(const unsigned char* frames, int n_frames, int H, int W, int win, int ovl, int run_len, int clip_norm,
                                int border_nan, float eps, const unsigned char* keep, float* u, float* v, float* cmax, float* s2n,

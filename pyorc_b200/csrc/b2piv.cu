@@ -771,13 +771,15 @@ static int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
         if (e->groups == 1) return aligned ? launch_rows<RCfg<32>, 1, false, true, false>(e, p, st) : launch_rows<RCfg<32>, 1, false, false, false>(e, p, st);
         return aligned ? launch_rows<RCfg<32>, 4, false, true, false>(e, p, st) : launch_rows<RCfg<32>, 4, false, false, false>(e, p, st);
     }
-    // sizes that are not a compiled FFT shape: tiny windows are cheapest by direct correlation, windows up to 32 px run
-    // zero-padded through the row-per-thread kernel (piv_rows.cuh "Padded mode"; variant 4 forces it wherever it applies),
-    // the rest padded through the shared-memory FFT kernel; variant 3 forces the direct kernel
+    // sizes that are not a compiled FFT shape: uint8 windows up to 32 px run zero-padded through the row-per-thread kernel
+    // (piv_rows.cuh "Padded mode"; variant 4 forces it wherever it applies; measured 3.3x the direct kernel at 10x10 and
+    // 2.6x the shared-memory kernel at 26x26).  Otherwise (float32 frames, caller-owned tensors with an odd pitch, larger
+    // windows): tiny windows by direct correlation, the rest padded through the shared-memory FFT kernel; variant 3
+    // forces the direct kernel
     const bool tiny = !fft_config(e->wy, e->wx) && e->wy * e->wx <= 144;
     if (e->variant == 4 && !pad_eligible(e, p.frames, p.frame_stride, p.pitch))
         return fail(e, B2PIV_ERR_UNSUPPORTED, "padded rows kernel needs uint8 frames, a window of at most 32 px and 16-byte aligned base/pitch");
-    if (pad_eligible(e, p.frames, p.frame_stride, p.pitch) && (e->variant == 4 || (e->variant == 0 && !fft_config(e->wy, e->wx) && !tiny))) {
+    if (pad_eligible(e, p.frames, p.frame_stride, p.pitch) && (e->variant == 4 || (e->variant == 0 && !fft_config(e->wy, e->wx)))) {
         e->last_variant = 4;
         return launch_rows_pad<false>(e, p, st, nullptr);
     }
@@ -812,7 +814,7 @@ static int dispatch_ens(b2piv_engine* e, const Params& p, const EnsParams& ep, c
     const bool tiny = !fft_config(e->wy, e->wx) && e->wy * e->wx <= 144;
     if (e->variant == 4 && !pad_eligible(e, p.frames, p.frame_stride, p.pitch))
         return fail(e, B2PIV_ERR_UNSUPPORTED, "padded rows kernel needs uint8 frames, a window of at most 32 px and 16-byte aligned base/pitch");
-    if (pad_eligible(e, p.frames, p.frame_stride, p.pitch) && (e->variant == 4 || (e->variant == 0 && !fft_config(e->wy, e->wx) && !tiny))) {
+    if (pad_eligible(e, p.frames, p.frame_stride, p.pitch) && (e->variant == 4 || (e->variant == 0 && !fft_config(e->wy, e->wx)))) {
         e->last_variant = 4;
         return launch_rows_pad<true>(e, p, st, &ep);
     }

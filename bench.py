@@ -233,6 +233,23 @@ def main():
     h2d = int(host.nbytes)
     d2h = int(4 * hu.nbytes)
 
+    # the PCIe floor under e2e: the same number of bytes, pinned host -> device, nothing else (N = 1 only)
+    pcie = None
+    if world == 1:
+        hp = torch.empty(frames.numel(), dtype=torch.uint8, pin_memory=True)
+        dd = torch.empty_like(frames).view(-1)
+        dd.copy_(hp, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            dd.copy_(hp, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize(dev)
+        h2d_ms = c0.elapsed_time(c1) / 3
+        pcie = {"h2d_only_ms": h2d_ms, "h2d_gbs": hp.numel() / h2d_ms / 1e6}
+        del hp, dd
+
     if rank != 0:
         eng.close()
         if world > 1:
@@ -281,7 +298,7 @@ def main():
                    "parallelism": f"frame-pair shard x{world}"},
         "roofline": roofline, "fp32": fp32, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                "ms_per_step": 1e3 * e2e_s / args.steps, "api": "pyorc_b200.engine.Engine.pairs(numpy pinned)"},
+                "ms_per_step": 1e3 * e2e_s / args.steps, "api": "pyorc_b200.engine.Engine.pairs(numpy pinned)", "pcie": pcie},
         "gpu_launches": int(launches), "clocks": clocks, "rmse_vs_oracle": rmse,
     }
     print(json.dumps(line), flush=True)

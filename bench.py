@@ -51,43 +51,87 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed regions: NVML polled in-process every ~2 ms (the timed
+    region of the default run lasts tens of milliseconds, too short for `nvidia-smi -lms`), nvidia-smi as fall-back."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index=0, uuid=None):
+        self.index, self.uuid = index, uuid
+        self.sm, self.reasons, self.power = [], set(), []
+        self.sm_max, self.how = None, None
+        self._stop = threading.Event()
+        self._thread, self._nvml, self._h = None, None, None
+
+    def _open_nvml(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = None
+        if self.uuid is not None:
+            for u in (f"GPU-{self.uuid}", str(self.uuid)):
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(u)
+                    break
+                except Exception:
+                    h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self._nvml, self._h = pynvml, h
+        self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+    def _poll_nvml(self):
+        n, h = self._nvml, self._h
+        bits = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, b in bits.items():
+                    if r & b:
+                        self.reasons.add(k)
+                self.power.append(n.nvmlDeviceGetPowerUsage(h) / 1e3)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _poll_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0]
+                r = [c.strip() for c in out.split(",")]
+                self.sm.append(float(r[0]))
+                self.sm_max = float(r[1])
+                self.power.append(float(r[2]))
+                for nme, val in zip(names, r[3:7]):
+                    if val.lower().startswith("active"):
+                        self.reasons.add(nme)
+            except Exception:
+                time.sleep(0.05)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            self._open_nvml()
+            self.how = "nvml, 2 ms period, during the timed regions"
+            target = self._poll_nvml
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.how = "nvidia-smi, back to back, during the timed regions"
+            target = self._poll_smi
+        self._thread = threading.Thread(target=target, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for nme, val in zip(names, r[3:7]):
-                    if val.lower().startswith("active"):
-                        reasons.add(nme)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=15)
+        sm = self.sm
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(sm), "sm_mhz_min": float(min(sm)) if sm else None,
+                "power_w_max": float(max(self.power)) if self.power else None, "how": self.how}
 
 
 def cpu_reference(frames_np, workers):
@@ -133,7 +177,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-pairs", type=int, default=0, help="frame pairs of the workload the CPU baseline times (0: min(max(4, cores), 16))")
@@ -185,7 +229,11 @@ def main():
         step_device()
     sync_all()
     launches0 = eng.launch_count
-    sampler = ClockSampler(local_rank)
+    try:
+        uuid = torch.cuda.get_device_properties(dev).uuid
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local_rank, uuid)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

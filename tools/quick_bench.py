@@ -63,6 +63,14 @@ if __name__ == "__main__":
             run_ens(1080, 1920, (32, 32), (16, 16), 41, variant=variant)
             run_ens(1080, 1920, (64, 64), (32, 32), 51, dtype="float32", variant=variant)
         sys.exit(0)
+    if "--configs" in sys.argv:   # the five BASELINE.json geometries, one shard of frames each
+        run(475, 371, (32, 32), (16, 16), 3)
+        run(1080, 1920, (64, 64), (32, 32), 101)
+        run(1080, 1920, (32, 32), (24, 24), 41)
+        run(2160, 3840, (64, 64), (32, 32), 41)
+        run(4320, 7680, (128, 128), (64, 64), 11)
+        run(4320, 7680, (128, 128), (64, 64), 6, dtype="float32")
+        sys.exit(0)
     if "--single" in sys.argv:
         run(1080, 1920, (64, 64), (32, 32), 21, reps=2, variant=int(os.environ.get("B2_VARIANT", "0")), groups=int(os.environ.get("B2_GROUPS", "0")), rolled=int(os.environ.get("B2_ROLLED", "0")))
         sys.exit(0)

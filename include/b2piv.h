@@ -123,6 +123,58 @@ int b2piv_project_plan(b2piv_engine* e, int height, int width, int out_height, i
 int b2piv_project_device(b2piv_engine* e, const void* d_frames, int dtype, int n_frames, void* d_out, int out_dtype,
                          void* cuda_stream);
 
+/* ---- Velocimetry mask stack on the device ------------------------------------------------------------
+ * Replaces the xarray passes of pyorc/api/mask.py:147-403 on the result fields while they are still in HBM.  Fields are
+ * contiguous float32 [n_time][n_xy] (n_xy = ny * nx, row-major y, x) device buffers; masks are uint8 (1 = keep), either
+ * [n_time][n_xy] or, where noted, [n_xy].  float32 arithmetic in numpy's operation order; stream-ordered.
+ *   elementwise  op MINMAX   : p0 < sqrt(a^2 + b^2) < p1, a = v_x, b = v_y          (mask.py:147-161)
+ *                op ANGLE    : |atan2(a, b) - p0| < p1                               (mask.py:163-186)
+ *                op THRESHOLD: a > p0 (corr: mask.py:203-213, s2n: :215-225; b unused)
+ *   time_stats   count of non-NaN samples, skipna mean and std (ddof 0) over time -> [n_xy] each (any output may be NULL)
+ *   count        count > tolerance * n_time -> [n_xy]                                (mask.py:188-201)
+ *   outliers     |(v - mean_t) / std_t| < tolerance per component, or (mode_and = 0) / and   (mask.py:227-252)
+ *   variance     |std_t / max(mean_t, 1e30)| < tolerance -> [n_xy]                   (mask.py:254-285, its clamp included)
+ *   rolling      s > tolerance * max of s over the centred window of wdw steps       (mask.py:287-303)
+ *   window_nan / window_mean / window_replace: helpers.stack_window neighbourhoods (helpers.py:638-679), strides =
+ *                {wdw_x_min, wdw_x_max, wdw_y_min, wdw_y_max} with the y maximum EXCLUSIVE as in the reference's range();
+ *                window_nan: #valid >= tolerance * #strides (mask.py:305-337); window_mean: |v - mean| / mean <
+ *                tolerance (mask.py:339-377); window_replace: NaNs of up to four fields <- window mean, in place,
+ *                `iterations` times (mask.py:379-403)
+ *   apply        field = mask ? field : NaN for up to four fields (ds[var].where(mask), mask.py:131-144) */
+enum { B2PIV_MASK_MINMAX = 0, B2PIV_MASK_ANGLE = 1, B2PIV_MASK_THRESHOLD = 2 };
+int b2piv_mask_elementwise(b2piv_engine* e, int op, const float* d_a, const float* d_b, long long count, float p0, float p1,
+                           unsigned char* d_mask, void* cuda_stream);
+int b2piv_time_stats(b2piv_engine* e, const float* d_field, int n_time, long long n_xy, int* d_count, float* d_mean, float* d_std,
+                     void* cuda_stream);
+int b2piv_mask_count(b2piv_engine* e, const float* d_vx, int n_time, long long n_xy, double tolerance, unsigned char* d_mask_xy,
+                     void* cuda_stream);
+int b2piv_mask_outliers(b2piv_engine* e, const float* d_vx, const float* d_vy, int n_time, long long n_xy, float tolerance,
+                        int mode_and, unsigned char* d_mask, void* cuda_stream);
+int b2piv_mask_variance(b2piv_engine* e, const float* d_vx, const float* d_vy, int n_time, long long n_xy, float tolerance,
+                        int mode_and, unsigned char* d_mask_xy, void* cuda_stream);
+int b2piv_mask_rolling(b2piv_engine* e, const float* d_vx, const float* d_vy, int n_time, long long n_xy, int wdw, float tolerance,
+                       unsigned char* d_mask, void* cuda_stream);
+int b2piv_mask_window_nan(b2piv_engine* e, const float* d_vx, int n_time, int ny, int nx, const int* strides, double tolerance,
+                          unsigned char* d_mask, void* cuda_stream);
+int b2piv_mask_window_mean(b2piv_engine* e, const float* d_vx, const float* d_vy, int n_time, int ny, int nx, const int* strides,
+                           float tolerance, int mode_and, unsigned char* d_mask, void* cuda_stream);
+int b2piv_window_replace(b2piv_engine* e, float* const* d_fields, int n_fields, int n_time, int ny, int nx, const int* strides,
+                         int iterations, void* cuda_stream);
+int b2piv_mask_apply(b2piv_engine* e, float* const* d_fields, int n_fields, int n_time, long long n_xy, const unsigned char* d_mask,
+                     int mask_has_time, void* cuda_stream);
+
+/* ---- Result packing ----------------------------------------------------------------------------------
+ * The CF packing pyorc sets for v_x, v_y, corr, s2n (pyorc/const.py:80-83, Velocimetry.set_encoding,
+ * pyorc/api/velocimetry.py:239-253): int16 = round_half_even(field / scale_factor), NaN -> fill_value (values beyond the
+ * int16 range saturate); decode is the inverse xarray applies on reading.  rotate_uv: helpers.rotate_u_v
+ * (pyorc/helpers.py:602-630) as used by Velocimetry.to_ugrid (api/velocimetry.py:284-289), float64 out. */
+int b2piv_encode_int16(b2piv_engine* e, const float* d_field, long long count, float scale_factor, int fill_value, short* d_out,
+                       void* cuda_stream);
+int b2piv_decode_int16(b2piv_engine* e, const short* d_packed, long long count, float scale_factor, int fill_value, float* d_out,
+                       void* cuda_stream);
+int b2piv_rotate_uv(b2piv_engine* e, const float* d_u, const float* d_v, long long count, double theta, double* d_u2, double* d_v2,
+                    void* cuda_stream);
+
 /* Page-locked host memory so H2D copies run at full PCIe rate without staging. */
 void* b2piv_host_alloc(size_t bytes);
 void b2piv_host_free(void* p);

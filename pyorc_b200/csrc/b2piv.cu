@@ -9,6 +9,7 @@
 #include "piv_direct.cuh"
 #include "preproc.cuh"
 #include "project.cuh"
+#include "mask.cuh"
 
 #include <cuda.h>   // CUtensorMap (types only; the encoder is resolved at run time, libcuda is not linked)
 
@@ -489,6 +490,7 @@ struct b2piv_engine {
     int* d_proj_off = nullptr; size_t cap_proj_off = 0;
     int* d_proj_src = nullptr; size_t cap_proj_src = 0;
     int proj_h = 0, proj_w = 0, proj_out_h = 0, proj_out_w = 0; long long proj_samples = 0;
+    float* d_mask_ws = nullptr; size_t cap_mask_ws = 0;     // mask stack: time statistics / window_replace ping-pong
     float* d_ens_sum = nullptr; float* d_ens_cnt = nullptr; size_t cap_ens = 0, cap_ens_windows = 0; bool ens_open = false;
     // stats
     float last_kernel_ms = 0.f;
@@ -898,7 +900,7 @@ void b2piv_destroy(b2piv_engine* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     cudaFree(e->d_twx); cudaFree(e->d_twy); cudaFree(e->d_frames); cudaFree(e->d_out); cudaFree(e->d_planes);
-    cudaFree(e->d_keep); cudaFree(e->d_ens_sum); cudaFree(e->d_ens_cnt); cudaFree(e->d_pre_mean); cudaFree(e->d_pre_mm);
+    cudaFree(e->d_keep); cudaFree(e->d_ens_sum); cudaFree(e->d_ens_cnt); cudaFree(e->d_pre_mean); cudaFree(e->d_pre_mm); cudaFree(e->d_mask_ws);
     cudaFree(e->d_proj_off); cudaFree(e->d_proj_src); cudaFree(e->d_planes_nat);
     for (auto ev : e->ev_chunk) cudaEventDestroy(ev);
     if (e->ev_k0) cudaEventDestroy(e->ev_k0);
@@ -1454,6 +1456,184 @@ int b2piv_project_device(b2piv_engine* e, const void* d_frames, int dtype, int n
     CK(cudaGetLastError());
     e->launches++;
     return B2PIV_OK;
+}
+
+// ---- velocimetry mask stack and result packing on the device (kernels in mask.cuh) -------------
+static int mask_grid(const b2piv_engine* e, long long n, int block = 256) {
+    long long g = (n + block - 1) / block, cap = (long long)e->sm_count * 8;
+    return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+#define MASK_PROLOGUE(cond_null)                                                        \
+    if (!e) return B2PIV_ERR_ARG;                                                       \
+    if (cond_null) return fail(e, B2PIV_ERR_ARG, "NULL pointer");                       \
+    CK(cudaSetDevice(e->device));                                                       \
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+#define MASK_EPILOGUE(k)                                                                \
+    CK(cudaGetLastError());                                                             \
+    e->launches += (k);                                                                 \
+    return B2PIV_OK;
+
+int b2piv_mask_elementwise(b2piv_engine* e, int op, const float* d_a, const float* d_b, long long count, float p0, float p1,
+                           unsigned char* d_mask, void* cuda_stream) {
+    MASK_PROLOGUE(!d_a || !d_mask || (op != B2PIV_MASK_THRESHOLD && !d_b))
+    if (count < 0) return fail(e, B2PIV_ERR_ARG, "negative count");
+    if (count == 0) return B2PIV_OK;
+    const int g = mask_grid(e, count);
+    if (op == B2PIV_MASK_MINMAX) mask_elem_kernel<0><<<g, 256, 0, st>>>(d_a, d_b, count, p0, p1, d_mask);
+    else if (op == B2PIV_MASK_ANGLE) mask_elem_kernel<1><<<g, 256, 0, st>>>(d_a, d_b, count, p0, p1, d_mask);
+    else if (op == B2PIV_MASK_THRESHOLD) mask_elem_kernel<2><<<g, 256, 0, st>>>(d_a, d_a, count, p0, p1, d_mask);
+    else return fail(e, B2PIV_ERR_ARG, "unknown element-wise mask op");
+    MASK_EPILOGUE(1)
+}
+
+int b2piv_time_stats(b2piv_engine* e, const float* d_field, int n_time, long long n_xy, int* d_count, float* d_mean, float* d_std,
+                     void* cuda_stream) {
+    MASK_PROLOGUE(!d_field)
+    if (n_time < 1 || n_xy < 1) return fail(e, B2PIV_ERR_ARG, "empty field");
+    time_stats_kernel<<<mask_grid(e, n_xy, 128), 128, 0, st>>>(d_field, n_time, n_xy, d_count, d_mean, d_std);
+    MASK_EPILOGUE(1)
+}
+
+int b2piv_mask_count(b2piv_engine* e, const float* d_vx, int n_time, long long n_xy, double tolerance, unsigned char* d_mask_xy,
+                     void* cuda_stream) {
+    MASK_PROLOGUE(!d_vx || !d_mask_xy)
+    if (n_time < 1 || n_xy < 1) return fail(e, B2PIV_ERR_ARG, "empty field");
+    int rc = ensure(e, &e->d_mask_ws, &e->cap_mask_ws, (size_t)n_xy * sizeof(int));
+    if (rc) return rc;
+    int* cnt = reinterpret_cast<int*>(e->d_mask_ws);
+    time_stats_kernel<<<mask_grid(e, n_xy, 128), 128, 0, st>>>(d_vx, n_time, n_xy, cnt, nullptr, nullptr);
+    mask_count_kernel<<<mask_grid(e, n_xy), 256, 0, st>>>(cnt, n_xy, tolerance * (double)n_time, d_mask_xy);
+    MASK_EPILOGUE(2)
+}
+
+// mean / std over time of both components into the engine's workspace: [xm | xs | ym | ys], n_xy floats each
+static int mask_stats_xy(b2piv_engine* e, const float* d_vx, const float* d_vy, int n_time, long long n_xy, cudaStream_t st) {
+    int rc = ensure(e, &e->d_mask_ws, &e->cap_mask_ws, (size_t)4 * n_xy * sizeof(float));
+    if (rc) return rc;
+    float* w = e->d_mask_ws;
+    time_stats_kernel<<<mask_grid(e, n_xy, 128), 128, 0, st>>>(d_vx, n_time, n_xy, nullptr, w, w + n_xy);
+    time_stats_kernel<<<mask_grid(e, n_xy, 128), 128, 0, st>>>(d_vy, n_time, n_xy, nullptr, w + 2 * n_xy, w + 3 * n_xy);
+    return B2PIV_OK;
+}
+
+int b2piv_mask_outliers(b2piv_engine* e, const float* d_vx, const float* d_vy, int n_time, long long n_xy, float tolerance, int mode_and,
+                        unsigned char* d_mask, void* cuda_stream) {
+    MASK_PROLOGUE(!d_vx || !d_vy || !d_mask)
+    if (n_time < 1 || n_xy < 1) return fail(e, B2PIV_ERR_ARG, "empty field");
+    int rc = mask_stats_xy(e, d_vx, d_vy, n_time, n_xy, st);
+    if (rc) return rc;
+    const float* w = e->d_mask_ws;
+    mask_outliers_kernel<<<mask_grid(e, (long long)n_time * n_xy), 256, 0, st>>>(d_vx, d_vy, n_time, n_xy, w, w + n_xy, w + 2 * n_xy,
+                                                                                   w + 3 * n_xy, tolerance, mode_and, d_mask);
+    MASK_EPILOGUE(3)
+}
+
+int b2piv_mask_variance(b2piv_engine* e, const float* d_vx, const float* d_vy, int n_time, long long n_xy, float tolerance, int mode_and,
+                        unsigned char* d_mask_xy, void* cuda_stream) {
+    MASK_PROLOGUE(!d_vx || !d_vy || !d_mask_xy)
+    if (n_time < 1 || n_xy < 1) return fail(e, B2PIV_ERR_ARG, "empty field");
+    int rc = mask_stats_xy(e, d_vx, d_vy, n_time, n_xy, st);
+    if (rc) return rc;
+    const float* w = e->d_mask_ws;
+    mask_variance_kernel<<<mask_grid(e, n_xy), 256, 0, st>>>(n_xy, w, w + n_xy, w + 2 * n_xy, w + 3 * n_xy, tolerance, mode_and, d_mask_xy);
+    MASK_EPILOGUE(3)
+}
+
+int b2piv_mask_rolling(b2piv_engine* e, const float* d_vx, const float* d_vy, int n_time, long long n_xy, int wdw, float tolerance,
+                       unsigned char* d_mask, void* cuda_stream) {
+    MASK_PROLOGUE(!d_vx || !d_vy || !d_mask)
+    if (n_time < 1 || n_xy < 1) return fail(e, B2PIV_ERR_ARG, "empty field");
+    if (wdw < 1) return fail(e, B2PIV_ERR_ARG, "rolling window must be >= 1");
+    mask_rolling_kernel<<<mask_grid(e, (long long)n_time * n_xy), 256, 0, st>>>(d_vx, d_vy, n_time, n_xy, wdw, tolerance, d_mask);
+    MASK_EPILOGUE(1)
+}
+
+static bool window_args(b2piv_engine* e, int n_time, int ny, int nx, const int* strides, WindowArgs* w) {
+    if (n_time < 1 || ny < 1 || nx < 1 || !strides) { e->err = "empty field or NULL strides"; return false; }
+    *w = WindowArgs{n_time, ny, nx, strides[0], strides[1], strides[2], strides[3]};
+    if (w->wx1 < w->wx0 || w->wy1 <= w->wy0) { e->err = "window has no strides (x: [min, max], y: [min, max) like helpers.stack_window)"; return false; }
+    return true;
+}
+
+int b2piv_mask_window_nan(b2piv_engine* e, const float* d_vx, int n_time, int ny, int nx, const int* strides, double tolerance,
+                          unsigned char* d_mask, void* cuda_stream) {
+    MASK_PROLOGUE(!d_vx || !d_mask)
+    WindowArgs w;
+    if (!window_args(e, n_time, ny, nx, strides, &w)) return B2PIV_ERR_ARG;
+    const double n_strides = (double)(w.wx1 - w.wx0 + 1) * (double)(w.wy1 - w.wy0);
+    mask_window_nan_kernel<<<mask_grid(e, (long long)n_time * ny * nx), 256, 0, st>>>(d_vx, w, tolerance * n_strides, d_mask);
+    MASK_EPILOGUE(1)
+}
+
+int b2piv_mask_window_mean(b2piv_engine* e, const float* d_vx, const float* d_vy, int n_time, int ny, int nx, const int* strides,
+                           float tolerance, int mode_and, unsigned char* d_mask, void* cuda_stream) {
+    MASK_PROLOGUE(!d_vx || !d_vy || !d_mask)
+    WindowArgs w;
+    if (!window_args(e, n_time, ny, nx, strides, &w)) return B2PIV_ERR_ARG;
+    mask_window_mean_kernel<<<mask_grid(e, (long long)n_time * ny * nx), 256, 0, st>>>(d_vx, d_vy, w, tolerance, mode_and, d_mask);
+    MASK_EPILOGUE(1)
+}
+
+int b2piv_window_replace(b2piv_engine* e, float* const* d_fields, int n_fields, int n_time, int ny, int nx, const int* strides,
+                         int iterations, void* cuda_stream) {
+    MASK_PROLOGUE(!d_fields)
+    WindowArgs w;
+    if (!window_args(e, n_time, ny, nx, strides, &w)) return B2PIV_ERR_ARG;
+    if (n_fields < 1 || n_fields > 4) return fail(e, B2PIV_ERR_ARG, "1..4 fields");
+    const long long n = (long long)n_time * ny * nx;
+    int rc = ensure(e, &e->d_mask_ws, &e->cap_mask_ws, (size_t)n * sizeof(float));
+    if (rc) return rc;
+    int launches = 0;
+    for (int it = 0; it < iterations; ++it) {
+        for (int k = 0; k < n_fields; ++k) {
+            if (!d_fields[k]) return fail(e, B2PIV_ERR_ARG, "NULL field");
+            window_replace_kernel<<<mask_grid(e, n), 256, 0, st>>>(d_fields[k], w, e->d_mask_ws);
+            CK(cudaMemcpyAsync(d_fields[k], e->d_mask_ws, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            ++launches;
+        }
+    }
+    MASK_EPILOGUE(launches)
+}
+
+int b2piv_mask_apply(b2piv_engine* e, float* const* d_fields, int n_fields, int n_time, long long n_xy, const unsigned char* d_mask,
+                     int mask_has_time, void* cuda_stream) {
+    MASK_PROLOGUE(!d_fields || !d_mask)
+    if (n_fields < 1 || n_fields > 4) return fail(e, B2PIV_ERR_ARG, "1..4 fields");
+    if (n_time < 1 || n_xy < 1) return fail(e, B2PIV_ERR_ARG, "empty field");
+    Fields4 fs;
+    fs.n = n_fields;
+    for (int k = 0; k < 4; ++k) {
+        fs.f[k] = k < n_fields ? d_fields[k] : nullptr;
+        if (k < n_fields && !fs.f[k]) return fail(e, B2PIV_ERR_ARG, "NULL field");
+    }
+    const long long n = (long long)n_time * n_xy;
+    mask_apply_kernel<<<mask_grid(e, n), 256, 0, st>>>(fs, n, n_xy, d_mask, mask_has_time);
+    MASK_EPILOGUE(1)
+}
+
+int b2piv_encode_int16(b2piv_engine* e, const float* d_field, long long count, float scale_factor, int fill_value, short* d_out,
+                       void* cuda_stream) {
+    MASK_PROLOGUE(!d_field || !d_out)
+    if (count <= 0) return count == 0 ? B2PIV_OK : fail(e, B2PIV_ERR_ARG, "negative count");
+    if (!(scale_factor > 0.f) || fill_value < -32768 || fill_value > 32767) return fail(e, B2PIV_ERR_ARG, "bad scale_factor / _FillValue");
+    encode_i16_kernel<<<mask_grid(e, count), 256, 0, st>>>(d_field, count, scale_factor, fill_value, d_out);
+    MASK_EPILOGUE(1)
+}
+
+int b2piv_decode_int16(b2piv_engine* e, const short* d_packed, long long count, float scale_factor, int fill_value, float* d_out,
+                       void* cuda_stream) {
+    MASK_PROLOGUE(!d_packed || !d_out)
+    if (count <= 0) return count == 0 ? B2PIV_OK : fail(e, B2PIV_ERR_ARG, "negative count");
+    decode_i16_kernel<<<mask_grid(e, count), 256, 0, st>>>(d_packed, count, scale_factor, fill_value, d_out);
+    MASK_EPILOGUE(1)
+}
+
+int b2piv_rotate_uv(b2piv_engine* e, const float* d_u, const float* d_v, long long count, double theta, double* d_u2, double* d_v2,
+                    void* cuda_stream) {
+    MASK_PROLOGUE(!d_u || !d_v || !d_u2 || !d_v2)
+    if (count <= 0) return count == 0 ? B2PIV_OK : fail(e, B2PIV_ERR_ARG, "negative count");
+    rotate_uv_kernel<<<mask_grid(e, count), 256, 0, st>>>(d_u, d_v, count, std::cos(theta), std::sin(theta), d_u2, d_v2);
+    MASK_EPILOGUE(1)
 }
 
 void* b2piv_host_alloc(size_t bytes) {

@@ -43,6 +43,19 @@ ABI_SYMBOLS = (
     "b2piv_pre_gauss_device",
     "b2piv_project_plan",
     "b2piv_project_device",
+    "b2piv_mask_elementwise",
+    "b2piv_time_stats",
+    "b2piv_mask_count",
+    "b2piv_mask_outliers",
+    "b2piv_mask_variance",
+    "b2piv_mask_rolling",
+    "b2piv_mask_window_nan",
+    "b2piv_mask_window_mean",
+    "b2piv_window_replace",
+    "b2piv_mask_apply",
+    "b2piv_encode_int16",
+    "b2piv_decode_int16",
+    "b2piv_rotate_uv",
     "b2piv_host_alloc",
     "b2piv_host_free",
     "b2piv_last_kernel_ms",
@@ -87,6 +100,20 @@ def load_library(path: Optional[str] = None):
     lib.b2piv_pre_gauss_device.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp, vp]
     lib.b2piv_project_plan.argtypes = [vp, ci, ci, ci, ci, vp, vp, cll, vp, vp, cll, vp, cll]
     lib.b2piv_project_device.argtypes = [vp, vp, ci, ci, vp, ci, vp]
+    cd, ip, vpp = ctypes.c_double, ctypes.POINTER(ci), ctypes.POINTER(vp)
+    lib.b2piv_mask_elementwise.argtypes = [vp, ci, vp, vp, cll, cf, cf, vp, vp]
+    lib.b2piv_time_stats.argtypes = [vp, vp, ci, cll, vp, vp, vp, vp]
+    lib.b2piv_mask_count.argtypes = [vp, vp, ci, cll, cd, vp, vp]
+    lib.b2piv_mask_outliers.argtypes = [vp, vp, vp, ci, cll, cf, ci, vp, vp]
+    lib.b2piv_mask_variance.argtypes = [vp, vp, vp, ci, cll, cf, ci, vp, vp]
+    lib.b2piv_mask_rolling.argtypes = [vp, vp, vp, ci, cll, ci, cf, vp, vp]
+    lib.b2piv_mask_window_nan.argtypes = [vp, vp, ci, ci, ci, ip, cd, vp, vp]
+    lib.b2piv_mask_window_mean.argtypes = [vp, vp, vp, ci, ci, ci, ip, cf, ci, vp, vp]
+    lib.b2piv_window_replace.argtypes = [vp, vpp, ci, ci, ci, ci, ip, ci, vp]
+    lib.b2piv_mask_apply.argtypes = [vp, vpp, ci, ci, cll, vp, ci, vp]
+    lib.b2piv_encode_int16.argtypes = [vp, vp, cll, cf, ci, vp, vp]
+    lib.b2piv_decode_int16.argtypes = [vp, vp, cll, cf, ci, vp, vp]
+    lib.b2piv_rotate_uv.argtypes = [vp, vp, vp, cll, cd, vp, vp, vp]
     lib.b2piv_host_alloc.argtypes = [ctypes.c_size_t]
     lib.b2piv_host_alloc.restype = vp
     lib.b2piv_host_free.argtypes = [vp]

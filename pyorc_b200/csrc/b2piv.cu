@@ -1459,6 +1459,26 @@ int b2piv_project_device(b2piv_engine* e, const void* d_frames, int dtype, int n
 }
 
 // ---- velocimetry mask stack and result packing on the device (kernels in mask.cuh) -------------
+// 2-D launch over (locations, time): x covers the locations (at most sm_count * 8 blocks), y strides over time so that the
+// whole grid holds about sm_count * 16 blocks
+static dim3 mask_grid2(const b2piv_engine* e, long long n_xy, int n_time, int block = 256) {
+    long long gx = (n_xy + block - 1) / block, cap = (long long)e->sm_count * 8;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    long long gy = ((long long)e->sm_count * 16 + gx - 1) / gx;
+    if (gy > n_time) gy = n_time;
+    if (gy > 65535) gy = 65535;
+    if (gy < 1) gy = 1;
+    return dim3((unsigned)gx, (unsigned)gy, 1);
+}
+static dim3 window_grid(const b2piv_engine* e, int n_time, int ny, int nx) {
+    const unsigned gx = (unsigned)((nx + 31) / 32), gy = (unsigned)((ny + 7) / 8);
+    long long gz = ((long long)e->sm_count * 16 + (long long)gx * gy - 1) / ((long long)gx * gy);
+    if (gz > n_time) gz = n_time;
+    if (gz > 65535) gz = 65535;
+    if (gz < 1) gz = 1;
+    return dim3(gx, gy, (unsigned)gz);
+}
 static int mask_grid(const b2piv_engine* e, long long n, int block = 256) {
     long long g = (n + block - 1) / block, cap = (long long)e->sm_count * 8;
     return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
@@ -1490,7 +1510,7 @@ int b2piv_time_stats(b2piv_engine* e, const float* d_field, int n_time, long lon
                      void* cuda_stream) {
     MASK_PROLOGUE(!d_field)
     if (n_time < 1 || n_xy < 1) return fail(e, B2PIV_ERR_ARG, "empty field");
-    time_stats_kernel<<<mask_grid(e, n_xy, 128), 128, 0, st>>>(d_field, n_time, n_xy, d_count, d_mean, d_std);
+    time_stats_kernel<<<mask_grid(e, n_xy, 64), 64, 0, st>>>(d_field, n_time, n_xy, d_count, d_mean, d_std);
     MASK_EPILOGUE(1)
 }
 
@@ -1501,8 +1521,11 @@ int b2piv_mask_count(b2piv_engine* e, const float* d_vx, int n_time, long long n
     int rc = ensure(e, &e->d_mask_ws, &e->cap_mask_ws, (size_t)n_xy * sizeof(int));
     if (rc) return rc;
     int* cnt = reinterpret_cast<int*>(e->d_mask_ws);
-    time_stats_kernel<<<mask_grid(e, n_xy, 128), 128, 0, st>>>(d_vx, n_time, n_xy, cnt, nullptr, nullptr);
-    mask_count_kernel<<<mask_grid(e, n_xy), 256, 0, st>>>(cnt, n_xy, tolerance * (double)n_time, d_mask_xy);
+    time_stats_kernel<<<mask_grid(e, n_xy, 64), 64, 0, st>>>(d_vx, n_time, n_xy, cnt, nullptr, nullptr);
+    // count > tolerance * T  <=>  count >= floor(tolerance * T) + 1 (count is an integer; the product is the reference's float64 one)
+    const double thr = tolerance * (double)n_time;
+    const int min_count = thr < -1.0 ? 0 : (thr > 2.0e9 ? 2147483647 : (int)std::floor(thr) + 1);
+    mask_count_kernel<<<mask_grid(e, n_xy), 256, 0, st>>>(cnt, n_xy, min_count, d_mask_xy);
     MASK_EPILOGUE(2)
 }
 
@@ -1511,8 +1534,8 @@ static int mask_stats_xy(b2piv_engine* e, const float* d_vx, const float* d_vy, 
     int rc = ensure(e, &e->d_mask_ws, &e->cap_mask_ws, (size_t)4 * n_xy * sizeof(float));
     if (rc) return rc;
     float* w = e->d_mask_ws;
-    time_stats_kernel<<<mask_grid(e, n_xy, 128), 128, 0, st>>>(d_vx, n_time, n_xy, nullptr, w, w + n_xy);
-    time_stats_kernel<<<mask_grid(e, n_xy, 128), 128, 0, st>>>(d_vy, n_time, n_xy, nullptr, w + 2 * n_xy, w + 3 * n_xy);
+    time_stats_kernel<<<mask_grid(e, n_xy, 64), 64, 0, st>>>(d_vx, n_time, n_xy, nullptr, w, w + n_xy);
+    time_stats_kernel<<<mask_grid(e, n_xy, 64), 64, 0, st>>>(d_vy, n_time, n_xy, nullptr, w + 2 * n_xy, w + 3 * n_xy);
     return B2PIV_OK;
 }
 
@@ -1523,8 +1546,8 @@ int b2piv_mask_outliers(b2piv_engine* e, const float* d_vx, const float* d_vy, i
     int rc = mask_stats_xy(e, d_vx, d_vy, n_time, n_xy, st);
     if (rc) return rc;
     const float* w = e->d_mask_ws;
-    mask_outliers_kernel<<<mask_grid(e, (long long)n_time * n_xy), 256, 0, st>>>(d_vx, d_vy, n_time, n_xy, w, w + n_xy, w + 2 * n_xy,
-                                                                                   w + 3 * n_xy, tolerance, mode_and, d_mask);
+    mask_outliers_kernel<<<mask_grid2(e, n_xy, n_time), 256, 0, st>>>(d_vx, d_vy, n_time, n_xy, w, w + n_xy, w + 2 * n_xy, w + 3 * n_xy,
+                                                                        tolerance, mode_and, d_mask);
     MASK_EPILOGUE(3)
 }
 
@@ -1544,7 +1567,18 @@ int b2piv_mask_rolling(b2piv_engine* e, const float* d_vx, const float* d_vy, in
     MASK_PROLOGUE(!d_vx || !d_vy || !d_mask)
     if (n_time < 1 || n_xy < 1) return fail(e, B2PIV_ERR_ARG, "empty field");
     if (wdw < 1) return fail(e, B2PIV_ERR_ARG, "rolling window must be >= 1");
-    mask_rolling_kernel<<<mask_grid(e, (long long)n_time * n_xy), 256, 0, st>>>(d_vx, d_vy, n_time, n_xy, wdw, tolerance, d_mask);
+    // time is cut into chunks of >= 8 * wdw steps (a chunk re-reads wdw - 1 steps of halo), one chunk per grid.y index
+    dim3 g = mask_grid2(e, n_xy, n_time, 128);
+    int t_chunk = (n_time + (int)g.y - 1) / (int)g.y;
+    if (t_chunk < 8 * wdw) t_chunk = 8 * wdw;
+    g.y = (unsigned)((n_time + t_chunk - 1) / t_chunk);
+#define ROLL_CASE(WD) case WD: mask_rolling_kernel<WD><<<g, 128, 0, st>>>(d_vx, d_vy, n_time, n_xy, wdw, tolerance, t_chunk, d_mask); break;
+    switch (wdw) {
+        ROLL_CASE(1) ROLL_CASE(2) ROLL_CASE(3) ROLL_CASE(4) ROLL_CASE(5) ROLL_CASE(6) ROLL_CASE(7) ROLL_CASE(8) ROLL_CASE(9) ROLL_CASE(10)
+        ROLL_CASE(11) ROLL_CASE(12) ROLL_CASE(13) ROLL_CASE(14) ROLL_CASE(15) ROLL_CASE(16)
+        default: mask_rolling_kernel<0><<<g, 128, 0, st>>>(d_vx, d_vy, n_time, n_xy, wdw, tolerance, t_chunk, d_mask);
+    }
+#undef ROLL_CASE
     MASK_EPILOGUE(1)
 }
 
@@ -1561,7 +1595,10 @@ int b2piv_mask_window_nan(b2piv_engine* e, const float* d_vx, int n_time, int ny
     WindowArgs w;
     if (!window_args(e, n_time, ny, nx, strides, &w)) return B2PIV_ERR_ARG;
     const double n_strides = (double)(w.wx1 - w.wx0 + 1) * (double)(w.wy1 - w.wy0);
-    mask_window_nan_kernel<<<mask_grid(e, (long long)n_time * ny * nx), 256, 0, st>>>(d_vx, w, tolerance * n_strides, d_mask);
+    // valid >= tolerance * n_strides  <=>  valid >= ceil(tolerance * n_strides)
+    const double thr = tolerance * n_strides;
+    const int min_count = thr <= 0.0 ? 0 : (thr > 2.0e9 ? 2147483647 : (int)std::ceil(thr));
+    mask_window_nan_kernel<<<window_grid(e, n_time, ny, nx), dim3(32, 8), 0, st>>>(d_vx, w, min_count, d_mask);
     MASK_EPILOGUE(1)
 }
 
@@ -1570,7 +1607,7 @@ int b2piv_mask_window_mean(b2piv_engine* e, const float* d_vx, const float* d_vy
     MASK_PROLOGUE(!d_vx || !d_vy || !d_mask)
     WindowArgs w;
     if (!window_args(e, n_time, ny, nx, strides, &w)) return B2PIV_ERR_ARG;
-    mask_window_mean_kernel<<<mask_grid(e, (long long)n_time * ny * nx), 256, 0, st>>>(d_vx, d_vy, w, tolerance, mode_and, d_mask);
+    mask_window_mean_kernel<<<window_grid(e, n_time, ny, nx), dim3(32, 8), 0, st>>>(d_vx, d_vy, w, tolerance, mode_and, d_mask);
     MASK_EPILOGUE(1)
 }
 
@@ -1587,7 +1624,7 @@ int b2piv_window_replace(b2piv_engine* e, float* const* d_fields, int n_fields, 
     for (int it = 0; it < iterations; ++it) {
         for (int k = 0; k < n_fields; ++k) {
             if (!d_fields[k]) return fail(e, B2PIV_ERR_ARG, "NULL field");
-            window_replace_kernel<<<mask_grid(e, n), 256, 0, st>>>(d_fields[k], w, e->d_mask_ws);
+            window_replace_kernel<<<window_grid(e, n_time, ny, nx), dim3(32, 8), 0, st>>>(d_fields[k], w, e->d_mask_ws);
             CK(cudaMemcpyAsync(d_fields[k], e->d_mask_ws, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st));
             ++launches;
         }
@@ -1606,8 +1643,7 @@ int b2piv_mask_apply(b2piv_engine* e, float* const* d_fields, int n_fields, int 
         fs.f[k] = k < n_fields ? d_fields[k] : nullptr;
         if (k < n_fields && !fs.f[k]) return fail(e, B2PIV_ERR_ARG, "NULL field");
     }
-    const long long n = (long long)n_time * n_xy;
-    mask_apply_kernel<<<mask_grid(e, n), 256, 0, st>>>(fs, n, n_xy, d_mask, mask_has_time);
+    mask_apply_kernel<<<mask_grid2(e, n_xy, n_time), 256, 0, st>>>(fs, n_time, n_xy, d_mask, mask_has_time);
     MASK_EPILOGUE(1)
 }
 

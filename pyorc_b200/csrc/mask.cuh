@@ -29,31 +29,52 @@ __device__ __forceinline__ float speed_rn(float vx, float vy) {
 }
 
 // ---- element-wise masks ----------------------------------------------------------------------------------------------
+// Pure streams: four consecutive elements per thread and access (16-byte loads, 4-byte mask stores) and two accesses in
+// flight, scalar tail / unaligned fall-back (same shape as preproc.cuh's streams).
+__device__ __forceinline__ bool mask_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+__device__ __forceinline__ bool mask_al4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3) == 0; }
+
 // OP 0: minmax, 1: angle, 2: threshold of a single field (corr / s2n)
+template <int OP>
+__device__ __forceinline__ unsigned char mask_elem(float a, float b, float p0, float p1) {
+    if (OP == 0) {
+        const float s = speed_rn(a, b);
+        return ((s > p0) && (s < p1)) ? 1 : 0;
+    } else if (OP == 1) {
+        return (fabsf(__fsub_rn(atan2f(a, b), p0)) < p1) ? 1 : 0;
+    }
+    return (a > p0) ? 1 : 0;
+}
 template <int OP>
 __global__ void __launch_bounds__(256) mask_elem_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float p0,
                                                         float p1, unsigned char* __restrict__ m) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        bool keep;
-        if (OP == 0) {
-            const float s = speed_rn(a[i], b[i]);
-            keep = (s > p0) && (s < p1);
-        } else if (OP == 1) {
-            const float ang = atan2f(a[i], b[i]);
-            keep = fabsf(__fsub_rn(ang, p0)) < p1;
-        } else {
-            keep = a[i] > p0;
-        }
-        m[i] = keep ? 1 : 0;
+    const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nv = (mask_al16(a) && mask_al16(b) && mask_al4(m)) ? (n & ~3ll) : 0;
+    long long i = t0 * 4;
+    for (; i + stride * 4 < nv; i += stride * 8) {
+        const float4 a0 = *reinterpret_cast<const float4*>(a + i), a1 = *reinterpret_cast<const float4*>(a + i + stride * 4);
+        float4 b0 = a0, b1 = a1;
+        if (OP != 2) { b0 = *reinterpret_cast<const float4*>(b + i); b1 = *reinterpret_cast<const float4*>(b + i + stride * 4); }
+        *reinterpret_cast<uchar4*>(m + i) = make_uchar4(mask_elem<OP>(a0.x, b0.x, p0, p1), mask_elem<OP>(a0.y, b0.y, p0, p1),
+                                                        mask_elem<OP>(a0.z, b0.z, p0, p1), mask_elem<OP>(a0.w, b0.w, p0, p1));
+        *reinterpret_cast<uchar4*>(m + i + stride * 4) = make_uchar4(mask_elem<OP>(a1.x, b1.x, p0, p1), mask_elem<OP>(a1.y, b1.y, p0, p1),
+                                                                     mask_elem<OP>(a1.z, b1.z, p0, p1), mask_elem<OP>(a1.w, b1.w, p0, p1));
     }
+    for (; i < nv; i += stride * 4) {
+        const float4 a0 = *reinterpret_cast<const float4*>(a + i);
+        float4 b0 = a0;
+        if (OP != 2) b0 = *reinterpret_cast<const float4*>(b + i);
+        *reinterpret_cast<uchar4*>(m + i) = make_uchar4(mask_elem<OP>(a0.x, b0.x, p0, p1), mask_elem<OP>(a0.y, b0.y, p0, p1),
+                                                        mask_elem<OP>(a0.z, b0.z, p0, p1), mask_elem<OP>(a0.w, b0.w, p0, p1));
+    }
+    for (long long j = nv + t0; j < n; j += stride) m[j] = mask_elem<OP>(a[j], OP != 2 ? b[j] : 0.f, p0, p1);
 }
 
 // ---- time statistics (skipna): count, mean, std (ddof = 0) per location ------------------------------------------------
 // One thread per location (coalesced along x), SEQUENTIAL float32 sums over time - the order numpy uses for a reduction
 // over the leading axis - two passes like np.nanvar (mean first, then squared deviations).  MS_U loads in flight.
-constexpr int MS_U = 8;
-__global__ void __launch_bounds__(128) time_stats_kernel(const float* __restrict__ f, int T, long long nxy, int* __restrict__ count,
+constexpr int MS_U = 32;
+__global__ void __launch_bounds__(64) time_stats_kernel(const float* __restrict__ f, int T, long long nxy, int* __restrict__ count,
                                                          float* __restrict__ mean, float* __restrict__ stdv) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nxy; i += stride) {
@@ -103,22 +124,26 @@ __global__ void __launch_bounds__(128) time_stats_kernel(const float* __restrict
     }
 }
 
-__global__ void __launch_bounds__(256) mask_count_kernel(const int* __restrict__ count, long long nxy, double thr,
+__global__ void __launch_bounds__(256) mask_count_kernel(const int* __restrict__ count, long long nxy, int min_count,
                                                          unsigned char* __restrict__ m) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nxy; i += stride) m[i] = ((double)count[i] > thr) ? 1 : 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nxy; i += stride) m[i] = (count[i] >= min_count) ? 1 : 0;
 }
 
+// grid: x over locations (grid-stride), y over time steps (grid-stride) - no 64-bit divisions per element
 __global__ void __launch_bounds__(256) mask_outliers_kernel(const float* __restrict__ vx, const float* __restrict__ vy, int T, long long nxy,
                                                             const float* __restrict__ xm, const float* __restrict__ xs,
                                                             const float* __restrict__ ym, const float* __restrict__ ys, float tol,
                                                             int mode_and, unsigned char* __restrict__ m) {
-    const long long n = (long long)T * nxy, stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const long long j = i % nxy;
-        const bool xc = fabsf(__fdiv_rn(__fsub_rn(vx[i], xm[j]), xs[j])) < tol;
-        const bool yc = fabsf(__fdiv_rn(__fsub_rn(vy[i], ym[j]), ys[j])) < tol;
-        m[i] = (mode_and ? (xc && yc) : (xc || yc)) ? 1 : 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nxy; j += stride) {
+        const float mx = xm[j], sx = xs[j], my = ym[j], sy = ys[j];
+        for (int t = blockIdx.y; t < T; t += gridDim.y) {
+            const long long i = (long long)t * nxy + j;
+            const bool xc = fabsf(__fdiv_rn(__fsub_rn(vx[i], mx), sx)) < tol;
+            const bool yc = fabsf(__fdiv_rn(__fsub_rn(vy[i], my), sy)) < tol;
+            m[i] = (mode_and ? (xc && yc) : (xc || yc)) ? 1 : 0;
+        }
     }
 }
 
@@ -136,25 +161,58 @@ __global__ void __launch_bounds__(256) mask_variance_kernel(long long nxy, const
     }
 }
 
-// rolling: window of label t covers [t - w/2, t + w - 1 - w/2]; a window that leaves the axis gives NaN -> False
-__global__ void __launch_bounds__(256) mask_rolling_kernel(const float* __restrict__ vx, const float* __restrict__ vy, int T, long long nxy,
-                                                           int wdw, float tol, unsigned char* __restrict__ m) {
-    const long long n = (long long)T * nxy, stride = (long long)gridDim.x * blockDim.x;
-    const int lo = wdw / 2, hi = wdw - 1 - wdw / 2;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int t = (int)(i / nxy);
-        const long long j = i - (long long)t * nxy;
-        bool keep = false;
-        if (t - lo >= 0 && t + hi < T) {
-            float mx = 0.f;   // NaN counts as 0 and speeds are >= 0
-            for (int q = t - lo; q <= t + hi; ++q) {
-                const float s = speed_rn(vx[(long long)q * nxy + j], vy[(long long)q * nxy + j]);
-                mx = (s == s) ? fmaxf(mx, s) : mx;
+// rolling: window of label t covers [t - w/2, t + w - 1 - w/2]; a window that leaves the axis gives NaN -> False.
+// A thread walks down time for one location with the last `wdw` speeds in a register ring (wdw <= ROLL_MAX), so every
+// element is read once; larger windows recompute the speeds (served by L1 / L2).
+constexpr int ROLL_MAX = 16;
+template <int WD>   // WD > 0: compile-time window (register ring); WD = 0: generic
+__global__ void __launch_bounds__(128) mask_rolling_kernel(const float* __restrict__ vx, const float* __restrict__ vy, int T, long long nxy,
+                                                           int wdw, float tol, int t_chunk, unsigned char* __restrict__ m) {
+    const int w = WD > 0 ? WD : wdw;
+    const int lo = w / 2, hi = w - 1 - w / 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nxy; j += stride) {
+        for (int c = blockIdx.y; c * t_chunk < T; c += gridDim.y) {
+            const int t0 = c * t_chunk, t1 = min(T, t0 + t_chunk);
+            if constexpr (WD > 0) {
+                float ring[WD > 0 ? WD : 1];   // ring[k] = speed (NaN as 0) of time t - lo + k, shifted every step
+#pragma unroll
+                for (int k = 0; k < WD - 1; ++k) {
+                    const int q = t0 - lo + k;
+                    float sp = 0.f;
+                    if (q >= 0 && q < T) { sp = speed_rn(vx[(long long)q * nxy + j], vy[(long long)q * nxy + j]); sp = (sp == sp) ? sp : 0.f; }
+                    ring[k] = sp;
+                }
+                for (int t = t0; t < t1; ++t) {
+                    const int q = t + hi;
+                    float sp = 0.f;
+                    if (q < T) { sp = speed_rn(vx[(long long)q * nxy + j], vy[(long long)q * nxy + j]); sp = (sp == sp) ? sp : 0.f; }
+                    ring[WD - 1] = sp;
+                    float mx = 0.f;
+#pragma unroll
+                    for (int k = 0; k < WD; ++k) mx = fmaxf(mx, ring[k]);
+                    const long long i = (long long)t * nxy + j;
+                    const float s0 = speed_rn(vx[i], vy[i]);     // own sample again: NaN must stay NaN here (L1 hit)
+                    m[i] = (t - lo >= 0 && t + hi < T && s0 > __fmul_rn(tol, mx)) ? 1 : 0;
+#pragma unroll
+                    for (int k = 0; k < WD - 1; ++k) ring[k] = ring[k + 1];
+                }
+            } else {
+                for (int t = t0; t < t1; ++t) {
+                    const long long i = (long long)t * nxy + j;
+                    bool keep = false;
+                    if (t - lo >= 0 && t + hi < T) {
+                        float mx = 0.f;   // NaN counts as 0 and speeds are >= 0
+                        for (int q = t - lo; q <= t + hi; ++q) {
+                            const float sp = speed_rn(vx[(long long)q * nxy + j], vy[(long long)q * nxy + j]);
+                            mx = (sp == sp) ? fmaxf(mx, sp) : mx;
+                        }
+                        keep = speed_rn(vx[i], vy[i]) > __fmul_rn(tol, mx);
+                    }
+                    m[i] = keep ? 1 : 0;
+                }
             }
-            const float s0 = speed_rn(vx[i], vy[i]);
-            keep = s0 > __fmul_rn(tol, mx);
         }
-        m[i] = keep ? 1 : 0;
     }
 }
 
@@ -169,35 +227,41 @@ __device__ __forceinline__ void window_sum(const float* __restrict__ f, const Wi
                                            int& cnt) {
     sum = 0.f;
     cnt = 0;
-    for (int xs = w.wx0; xs <= w.wx1; ++xs) {
-        const int xx = x - xs;
-        for (int ys = w.wy0; ys < w.wy1; ++ys) {
-            const int yy = y - ys;
-            if (xx < 0 || xx >= w.nx || yy < 0 || yy >= w.ny) continue;
-            const float v = f[base + (long long)yy * w.nx + xx];
+    // strides that land inside the field: xs in [x - nx + 1, x], ys in [y - ny + 1, y] - clipped once, the loops are then
+    // free of conditions (order unchanged: xs outer ascending, ys inner ascending)
+    const int xs0 = max(w.wx0, x - w.nx + 1), xs1 = min(w.wx1, x);
+    const int ys0 = max(w.wy0, y - w.ny + 1), ys1 = min(w.wy1 - 1, y);
+    const float* p = f + base + (long long)y * w.nx + x;
+    for (int xs = xs0; xs <= xs1; ++xs) {
+        const float* q = p - xs - ys0 * w.nx;
+        for (int ys = ys0; ys <= ys1; ++ys, q -= w.nx) {
+            const float v = *q;
             if (v == v) { sum = __fadd_rn(sum, v); ++cnt; }
         }
     }
 }
 
-__global__ void __launch_bounds__(256) mask_window_nan_kernel(const float* __restrict__ vx, WindowArgs w, double thr,
+// blocks of 32 x 8 outputs, grid.z strided over time: neighbours come from L1
+#define B2_WINDOW_LOOP                                                                     \
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;         \
+    const long long nxy = (long long)w.ny * w.nx;                                          \
+    if (x >= w.nx || y >= w.ny) return;                                                    \
+    for (int t = blockIdx.z; t < w.T; t += gridDim.z)
+
+__global__ void __launch_bounds__(256) mask_window_nan_kernel(const float* __restrict__ vx, WindowArgs w, int min_count,
                                                               unsigned char* __restrict__ m) {
-    const long long nxy = (long long)w.ny * w.nx, n = (long long)w.T * nxy, stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const long long t = i / nxy, j = i - t * nxy;
+    B2_WINDOW_LOOP {
         float sum;
         int cnt;
-        window_sum(vx, w, t * nxy, (int)(j / w.nx), (int)(j % w.nx), sum, cnt);
-        m[i] = ((double)cnt >= thr) ? 1 : 0;
+        window_sum(vx, w, t * nxy, y, x, sum, cnt);
+        m[t * nxy + (long long)y * w.nx + x] = (cnt >= min_count) ? 1 : 0;
     }
 }
 
 __global__ void __launch_bounds__(256) mask_window_mean_kernel(const float* __restrict__ vx, const float* __restrict__ vy, WindowArgs w,
                                                                float tol, int mode_and, unsigned char* __restrict__ m) {
-    const long long nxy = (long long)w.ny * w.nx, n = (long long)w.T * nxy, stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const long long t = i / nxy, j = i - t * nxy;
-        const int y = (int)(j / w.nx), x = (int)(j % w.nx);
+    B2_WINDOW_LOOP {
+        const long long i = t * nxy + (long long)y * w.nx + x;
         float sx, sy;
         int cx, cy;
         window_sum(vx, w, t * nxy, y, x, sx, cx);
@@ -211,14 +275,13 @@ __global__ void __launch_bounds__(256) mask_window_mean_kernel(const float* __re
 
 // one iteration of window_replace for one field (out-of-place: every mean reads the field before this iteration)
 __global__ void __launch_bounds__(256) window_replace_kernel(const float* __restrict__ in, WindowArgs w, float* __restrict__ out) {
-    const long long nxy = (long long)w.ny * w.nx, n = (long long)w.T * nxy, stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    B2_WINDOW_LOOP {
+        const long long i = t * nxy + (long long)y * w.nx + x;
         float v = in[i];
         if (v != v) {
-            const long long t = i / nxy, j = i - t * nxy;
             float s;
             int c;
-            window_sum(in, w, t * nxy, (int)(j / w.nx), (int)(j % w.nx), s, c);
+            window_sum(in, w, t * nxy, y, x, s, c);
             v = __fdiv_rn(s, (float)c);
         }
         out[i] = v;
@@ -227,12 +290,15 @@ __global__ void __launch_bounds__(256) window_replace_kernel(const float* __rest
 
 // ---- where(mask): up to four fields in one pass, mask [T][nxy] or [nxy] (broadcast over time) ---------------------------
 struct Fields4 { float* f[4]; int n; };
-__global__ void __launch_bounds__(256) mask_apply_kernel(Fields4 fs, long long n, long long nxy, const unsigned char* __restrict__ m,
+__global__ void __launch_bounds__(256) mask_apply_kernel(Fields4 fs, int T, long long nxy, const unsigned char* __restrict__ m,
                                                          int mask_has_time) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const bool keep = m[mask_has_time ? i : i % nxy] != 0;
-        if (!keep) {
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nxy; j += stride) {
+        const bool keep_xy = mask_has_time ? true : (m[j] != 0);
+        if (!mask_has_time && keep_xy) continue;
+        for (int t = blockIdx.y; t < T; t += gridDim.y) {
+            const long long i = (long long)t * nxy + j;
+            if (mask_has_time && m[i] != 0) continue;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 if (k < fs.n) fs.f[k][i] = CUDART_NAN_F;
@@ -241,19 +307,34 @@ __global__ void __launch_bounds__(256) mask_apply_kernel(Fields4 fs, long long n
 }
 
 // ---- f-4: CF packing ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ short encode_one(float a, float scale, int fill) {
+    const float v = rintf(__fdiv_rn(a, scale));          // round half to even, like np.rint
+    return (v != v) ? (short)fill : (short)fminf(fmaxf(v, -32768.f), 32767.f);
+}
 __global__ void __launch_bounds__(256) encode_i16_kernel(const float* __restrict__ a, long long n, float scale, int fill,
                                                          short* __restrict__ q) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float v = rintf(__fdiv_rn(a[i], scale));          // round half to even, like np.rint
-        q[i] = (v != v) ? (short)fill : (short)fminf(fmaxf(v, -32768.f), 32767.f);
+    const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nv = (mask_al16(a) && (reinterpret_cast<uintptr_t>(q) & 7) == 0) ? (n & ~3ll) : 0;
+    for (long long i = t0 * 4; i < nv; i += stride * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(a + i);
+        *reinterpret_cast<short4*>(q + i) = make_short4(encode_one(v.x, scale, fill), encode_one(v.y, scale, fill), encode_one(v.z, scale, fill),
+                                                        encode_one(v.w, scale, fill));
     }
+    for (long long j = nv + t0; j < n; j += stride) q[j] = encode_one(a[j], scale, fill);
+}
+__device__ __forceinline__ float decode_one(short q, float scale, int fill) {
+    return (q == (short)fill) ? CUDART_NAN_F : __fmul_rn((float)q, scale);
 }
 __global__ void __launch_bounds__(256) decode_i16_kernel(const short* __restrict__ q, long long n, float scale, int fill,
                                                          float* __restrict__ a) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        a[i] = (q[i] == (short)fill) ? CUDART_NAN_F : __fmul_rn((float)q[i], scale);
+    const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nv = (mask_al16(a) && (reinterpret_cast<uintptr_t>(q) & 7) == 0) ? (n & ~3ll) : 0;
+    for (long long i = t0 * 4; i < nv; i += stride * 4) {
+        const short4 v = *reinterpret_cast<const short4*>(q + i);
+        *reinterpret_cast<float4*>(a + i) = make_float4(decode_one(v.x, scale, fill), decode_one(v.y, scale, fill), decode_one(v.z, scale, fill),
+                                                        decode_one(v.w, scale, fill));
+    }
+    for (long long j = nv + t0; j < n; j += stride) a[j] = decode_one(q[j], scale, fill);
 }
 // u2 = c u - s v ; v2 = s u + c v in float64 (numpy promotes float32 fields times a float64 array element)
 __global__ void __launch_bounds__(256) rotate_uv_kernel(const float* __restrict__ u, const float* __restrict__ v, long long n, double c,

@@ -60,12 +60,11 @@ def _stream(t):
 def _mask_out(t, shape):
     import torch
 
-    return torch.empty(shape, dtype=torch.uint8, device=t.device)
+    # torch.bool is one byte holding 0 / 1 - exactly what the kernels write, so no conversion pass afterwards
+    return torch.empty(shape, dtype=torch.bool, device=t.device)
 
 
 def _back(m, was_np, as_bool=True):
-    if as_bool:
-        m = m.bool()
     return m.cpu().numpy() if was_np else m
 
 
@@ -266,7 +265,8 @@ def apply_masks(fields, masks, device: int = 0):
         masks = [masks]
     for m in masks:
         if _is_torch(m):
-            tm = m.to(device=ts[0].device, dtype=torch.uint8).contiguous()
+            tm = m.to(ts[0].device).contiguous()
+            tm = tm.view(torch.uint8) if tm.dtype == torch.bool else (tm != 0).view(torch.uint8)
         else:
             tm = torch.from_numpy(np.ascontiguousarray(np.asarray(m), dtype=np.uint8)).to(ts[0].device)
         if tuple(tm.shape) == (T, ny, nx) and ts[0].dim() == 3:

@@ -1,0 +1,310 @@
+// piv_rows128.cuh - 128x128 windows on the row-per-thread machinery of piv_rows.cuh (sm_100a, uint8 frames).
+//
+// A thread cannot hold a 128-point line in registers, so the 128 x 128 window is split into its four POLYPHASE
+// components a_p[m1, m2] = a[2 m1 + p1, 2 m2 + p2], p = (p1, p2) in {0,1}^2: four 64 x 64 images.  The circular
+// cross-correlation c[n] = sum_m a[m] b[m + n] (period 128) of the reference,
+//     irfft2(conj(rfft2 a) * rfft2 b)                                  (ffpiv.cross_corr, pyorc/velocimetry/ffpiv.py:450-459)
+// has the polyphase components (n = 2 n' + q, p + q = 2 s + r per axis, i.e. r = p xor q, s = p and q)
+//     c_q[n'] = sum_p corr64(a_p, b_r)[n' + s]
+// and therefore, in the 64 x 64 frequency domain,
+//     C_q[k] = sum_p conj(A_p[k]) B_{p xor q}[k] * exp(+2 pi i (k1 s1 + k2 s2) / 64).
+// No 128-point transform is needed at all: FOUR sub-groups of 64 threads (one per component) each run the unchanged
+// 64 x 64 pipeline of piv_rows.cuh - TMA tile -> rows in registers -> FFT -> transpose -> FFT -> Hermitian separation of the
+// two packed windows - and only the cross-spectrum step couples them: sub-group q gathers the parked spectra A_p of the
+// previous frame and the new spectra B_r of all four components (through shared memory, in batches of 11 ky rows), forms
+// C_q with the two phase factors, and inverse-transforms it with the unchanged code.  The result rows a thread ends up
+// with are rows of the polyphase component c_q, i.e. every other element of every other row of the reference's plane;
+// max / sum / first-occurrence argmax / the three rows around the peak only need the index map
+//     reference (fftshifted) row = (2 m1 + q1 + 64) % 128,  column = (2 m2 + q2 + 64) % 128.
+// Work per window pair: 1.0 complex 64x64 FFT per component and frame, like the native sizes (the shared-memory kernel
+// this replaces for 128 x 128 does 2.0 complex 128x128 FFTs per window and pair).
+#pragma once
+#include "piv_rows.cuh"
+
+namespace b2piv {
+
+using R6 = RCfg<64>;
+
+struct R128Smem {
+    RSmem<R6> sub[4];              // per polyphase component: transpose blocks (+ TMA tile / exchange aliases) and parked spectra
+    float nb[2][3][128];           // the three plane rows around each peak (reference order)
+    unsigned long long mbar;       // TMA completion barrier of the whole group
+};
+constexpr int R128_BATCH = 11;     // ky rows per exchange batch (3 batches cover ky = 0 .. 32)
+constexpr int R128_NPX = 128 * 128;
+// tile: window w rows [32 j, 32 j + 32) -> sub[j].tile() + w * 4096 ([32 rows][128 B], SWIZZLE_128B)
+static_assert(sizeof(float2) * R6::NWARP * R6::XBLK >= 2 * 4096, "tile quarter must fit in a sub-group's transpose blocks");
+static_assert(sizeof(float2) * R6::XBLK >= sizeof(float2) * 2 * R128_BATCH * 32, "exchange batch must fit in one warp's block");
+
+#ifdef __CUDACC__
+// P1: row 2 sigma(t) + p1 of both windows from the tile, bytes of column parity p2 packed (64 bytes per window), exact
+// integer moments of the sub-image -> sub[own].red[warp][0..3]
+__device__ __forceinline__ void r128_p1(R128Smem& s, RRegs<R6>& r, int sub, int t) {
+    const int p1 = sub >> 1, p2 = sub & 1;
+    const int row = 2 * column_of<64>(t) + p1;
+    const int j = row >> 5, rr = row & 31;
+    const unsigned sel = p2 ? 0x7531u : 0x6420u;
+    unsigned S[2] = {0, 0}, Q[2] = {0, 0};
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        const unsigned char* base = s.sub[j].tile() + w * 4096 + rr * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint4 q = *reinterpret_cast<const uint4*>(base + ((c ^ (rr & 7)) << 4));
+            r.px[w][2 * c + 0] = __byte_perm(q.x, q.y, sel);
+            r.px[w][2 * c + 1] = __byte_perm(q.z, q.w, sel);
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            S[w] = __dp4a(r.px[w][k], 0x01010101u, S[w]);
+            Q[w] = __dp4a(r.px[w][k], r.px[w][k], Q[w]);
+        }
+    }
+    unsigned vals[4] = {S[0], Q[0], S[1], Q[1]};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vals[k] += __shfl_xor_sync(0xffffffffu, vals[k], o);
+    }
+    if ((t & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s.sub[sub].red[t >> 5][k] = vals[k];
+    }
+}
+
+// P2: moments of the whole 128 x 128 windows (all four components) -> mean, 0.5 / std; convert + centre
+__device__ __forceinline__ void r128_p2(R128Smem& s, RRegs<R6>& r, int clip_norm) {
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        unsigned long long S = 0, Q = 0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) { S += s.sub[g].red[k][2 * w]; Q += s.sub[g].red[k][2 * w + 1]; }
+        }
+        const unsigned long long m2 = (unsigned long long)R128_NPX * Q - S * S;   // N^2 * variance, exact
+        r.mean_new[w] = (float)S * (1.0f / (float)R128_NPX);
+        r.half_alpha_new[w] = m2 ? 0.5f * (float)R128_NPX * (1.0f / sqrtf((float)m2)) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            float a0 = byte_to_float(r.px[0][k], b) - r.mean_new[0];
+            float a1 = byte_to_float(r.px[1][k], b) - r.mean_new[1];
+            if (clip_norm) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+            r.v[4 * k + b] = make_float2(a0, a1);
+        }
+    }
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cmulc(float2 p, float2 a) {   // conj(p) * a
+    return make_float2(p.x * a.x + p.y * a.y, p.x * a.y - p.y * a.x);
+}
+__device__ __forceinline__ float2 cfma(float2 m, float2 b, float2 a) {   // a + m * b
+    return make_float2(fmaf(m.x, b.x, fmaf(-m.y, b.y, a.x)), fmaf(m.x, b.y, fmaf(m.y, b.x, a.y)));
+}
+
+// exchange slot of (window w, batch slot sl) for lane `lane` of warp wq of sub-group g: inside that WARP's own transpose block,
+// so a warp only ever overwrites memory it has finished reading itself
+__device__ __forceinline__ float2* r128_xch(R128Smem& s, int g, int wq, int w, int sl, int lane) {
+    return &s.sub[g].X[wq][(w * R128_BATCH + sl) * 32 + lane];
+}
+
+// exp(+2 pi i ky / 64), ky = 0 .. 32: phase of a carry along y (indexed at run time by the rolled batch loop below)
+__device__ __constant__ float2 R128_TWY[33] = {{1.0000000000e+00f, 0.0000000000e+00f}, {9.9518472667e-01f, 9.8017140330e-02f}, {9.8078528040e-01f, 1.9509032202e-01f}, {9.5694033573e-01f, 2.9028467725e-01f}, {9.2387953251e-01f, 3.8268343237e-01f}, {8.8192126435e-01f, 4.7139673683e-01f}, {8.3146961230e-01f, 5.5557023302e-01f}, {7.7301045336e-01f, 6.3439328416e-01f}, {7.0710678119e-01f, 7.0710678119e-01f}, {6.3439328416e-01f, 7.7301045336e-01f}, {5.5557023302e-01f, 8.3146961230e-01f}, {4.7139673683e-01f, 8.8192126435e-01f}, {3.8268343237e-01f, 9.2387953251e-01f}, {2.9028467725e-01f, 9.5694033573e-01f}, {1.9509032202e-01f, 9.8078528040e-01f}, {9.8017140330e-02f, 9.9518472667e-01f}, {0.0f, 1.0f}, {-9.8017140330e-02f, 9.9518472667e-01f}, {-1.9509032202e-01f, 9.8078528040e-01f}, {-2.9028467725e-01f, 9.5694033573e-01f}, {-3.8268343237e-01f, 9.2387953251e-01f}, {-4.7139673683e-01f, 8.8192126435e-01f}, {-5.5557023302e-01f, 8.3146961230e-01f}, {-6.3439328416e-01f, 7.7301045336e-01f}, {-7.0710678119e-01f, 7.0710678119e-01f}, {-7.7301045336e-01f, 6.3439328416e-01f}, {-8.3146961230e-01f, 5.5557023302e-01f}, {-8.8192126435e-01f, 4.7139673683e-01f}, {-9.2387953251e-01f, 3.8268343237e-01f}, {-9.5694033573e-01f, 2.9028467725e-01f}, {-9.8078528040e-01f, 1.9509032202e-01f}, {-9.9518472667e-01f, 9.8017140330e-02f}, {-1.0f, 0.0f}};
+
+// The cross phase for one thread of sub-group q = sub.  r.v holds Z_q(ky, own column) = FFT of (window 0 + i window 1) of
+// component q; on return r.v holds conj(G_q), G_q = C_q(window 0) + i C_q(window 1), ready for the inverse pass.
+//
+// Code size matters more than instruction count here (the frame loop is far beyond the instruction caches: a fully
+// unrolled version of this phase - 33 ky steps - ran at HALF the speed), so the three batches share ONE copy of the code:
+// the registers are viewed as lo[ky] = Z(ky) and hi[ky] = Z(-ky) (ky = 0 .. 32; hi[0], hi[32] are copies of the self-paired
+// lines), a batch always works on lo[0..10] / hi[0..10], and both arrays are rotated by 11 between batches (66 register
+// moves per batch) - after three batches they are back in natural order.
+__device__ __forceinline__ void r128_cross(R128Smem& s, RRegs<R6>& r, int sub, int t) {
+    constexpr float SCALE = 1.0f / (4096.0f * (float)R128_NPX);   // 1/4096 of the 64x64 inverse, 1/N of the coefficient
+    constexpr int B = R128_BATCH;
+    const int lane = t & 31, wq = t >> 5;
+    const int q1 = sub >> 1, q2 = sub & 1;
+    const int pl = partner_lane_of<64>(t);
+    // phase factor of a carry along x: exp(+2 pi i c / 64) for the own column c (1 when q2 = 0)
+    const int c = column_of<64>(t);
+    float sn, cs;
+    sincospif((float)c * (1.0f / 32.0f), &sn, &cs);
+    const float2 m2 = q2 ? make_float2(cs, sn) : make_float2(1.f, 0.f);
+    // new spectra of component p xor q come from sub-group p xor q's exchange block
+    const float2* xb[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) xb[p] = r128_xch(s, p ^ sub, wq, 0, 0, lane);
+    float2* own = r128_xch(s, sub, wq, 0, 0, lane);
+    float2 lo[33], hi[33];
+#pragma unroll
+    for (int k = 0; k <= 32; ++k) { lo[k] = r.v[k]; hi[k] = r.v[(64 - k) % 64]; }
+#pragma unroll 1
+    for (int b0 = 0; b0 < 33; b0 += B) {
+        // -- publish the separated new spectra A0, A1 of this batch
+#pragma unroll
+        for (int sl = 0; sl < B; ++sl) {
+            const float2 pz = shfl2(hi[sl], pl);
+            float2 a0, a1;
+            separate(lo[sl], pz, r.half_alpha_new[0], r.half_alpha_new[1], a0, a1);
+            own[(0 * B + sl) * 32] = a0;
+            own[(1 * B + sl) * 32] = a1;
+        }
+        __syncthreads();
+        // -- cross spectra of this batch
+#pragma unroll
+        for (int sl = 0; sl < B; ++sl) {
+            const int ky = b0 + sl;
+            const float2 tw = R128_TWY[ky];
+            const float2 m1 = q1 ? tw : make_float2(1.f, 0.f);
+            float2 R[2];
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                float2 term[4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+                    term[p] = cmulc(s.sub[p].park[w][ky][t], xb[p][(w * B + sl) * 32]);
+                // p = (p1, p2) = (p >> 1, p & 1): R = t00 + m2 t01 + m1 (t10 + m2 t11)
+                const float2 l = cfma(m2, term[1], term[0]);
+                const float2 h = cfma(m2, term[3], term[2]);
+                R[w] = cfma(m1, h, l);
+            }
+            lo[sl] = make_float2(R[0].x - R[1].y, -(R[0].y + R[1].x));            // conj(G), G = R0 + i R1
+            hi[sl] = shfl2(cross_mirror(R[0], R[1]), pl);                         // conj(G(-ky)); unused for ky = 0, 32
+        }
+        __syncthreads();
+        // -- the new spectra become the parked ones (scaled once, here)
+#pragma unroll
+        for (int sl = 0; sl < B; ++sl) {
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                const float2 a = own[(w * B + sl) * 32];
+                s.sub[sub].park[w][b0 + sl][t] = make_float2(a.x * SCALE, a.y * SCALE);
+            }
+        }
+        // -- rotate both register arrays by one batch
+        float2 tl[B], th[B];
+#pragma unroll
+        for (int k = 0; k < B; ++k) { tl[k] = lo[k]; th[k] = hi[k]; }
+#pragma unroll
+        for (int k = 0; k + B < 33; ++k) { lo[k] = lo[k + B]; hi[k] = hi[k + B]; }
+#pragma unroll
+        for (int k = 0; k < B; ++k) { lo[33 - B + k] = tl[k]; hi[33 - B + k] = th[k]; }
+    }
+#pragma unroll
+    for (int k = 0; k <= 32; ++k) r.v[k] = lo[k];
+#pragma unroll
+    for (int k = 1; k < 32; ++k) r.v[64 - k] = hi[k];
+}
+
+// P6: rows holding the block maximum look for their first matching column in the reference's (fftshifted) order
+__device__ __forceinline__ void r128_p6(R128Smem& s, RRegs<R6>& r, int sub, int t) {
+    const int q1 = sub >> 1, q2 = sub & 1;
+    const int si = (2 * column_of<64>(t) + q1 + 64) & 127;
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        float M = 0.f, S = 0.f;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) { M = fmaxf(M, bits_f(s.sub[g].red[k][4 + w])); S += bits_f(s.sub[g].red[k][6 + w]); }
+        }
+        r.cmaxv[w] = M; r.sumv[w] = S;
+        unsigned long long key = ~0ull;
+        if (r.rowmax[w] == M) {
+            int first = 64;
+            // reference column j = (2 x + q2 + 64) % 128 ascends with pos = (x + 32) % 64: scan pos descending
+#pragma unroll
+            for (int pos = 63; pos >= 0; --pos) {
+                const int x = (pos + 32) % 64;
+                const float val = w == 0 ? r.v[x].x : r.v[x].y;
+                first = (val == M) ? pos : first;
+            }
+            int j = 2 * first + q2;
+            int i = si;
+            if (r.dead[w]) { i = 0; j = 0; }   // all-zero plane: every element is the maximum -> flat index 0
+            key = (unsigned long long)(i * 128 + j);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other < key ? other : key;
+        }
+        if ((t & 31) == 0) s.sub[sub].redk[t >> 5][w] = key;
+    }
+}
+
+// P7: the three reference rows around each peak; a reference row is shared by the two components with the same q1
+__device__ __forceinline__ void r128_p7(R128Smem& s, RRegs<R6>& r, int sub, int t) {
+    const int q1 = sub >> 1, q2 = sub & 1;
+    const int si = (2 * column_of<64>(t) + q1 + 64) & 127;
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        unsigned long long key = ~0ull;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) key = s.sub[g].redk[k][w] < key ? s.sub[g].redk[k][w] : key;
+        }
+        const int idx = (int)key;
+        r.pi[w] = idx >> 7; r.pj[w] = idx & 127;
+        const int d = si - r.pi[w];
+        if (d >= -1 && d <= 1) {
+            float* row = &s.nb[w][d + 1][0];
+#pragma unroll
+            for (int x = 0; x < 64; ++x) {
+                const float val = r.dead[w] ? 0.f : (w == 0 ? r.v[x].x : r.v[x].y);
+                row[(2 * x + q2 + 64) & 127] = val;
+            }
+        }
+    }
+}
+
+// P8: Gaussian fit + outputs by threads 0 / 1 of the group (pyorc/velocimetry/ffpiv.py:465-466 + ffpiv.u_v_displacement)
+__device__ __forceinline__ void r128_p8(R128Smem& s, RRegs<R6>& r, int tid, const RParams& p, const RUnit& un, int pair) {
+    if (tid >= 2) return;
+    const int w = tid;
+    if (w == 1 && !un.valid1) return;
+    const float* nb = &s.nb[w][0][0];
+    const int pi = w == 0 ? r.pi[0] : r.pi[1], pj = w == 0 ? r.pj[0] : r.pj[1];
+    const float cmax = w == 0 ? r.cmaxv[0] : r.cmaxv[1];
+    const float mean = (w == 0 ? r.sumv[0] : r.sumv[1]) / (float)R128_NPX;
+    float uu, vv;
+    if (pi == 0 || pi == 127 || pj == 0 || pj == 127) {
+        if (p.border_nan) { uu = nanf(""); vv = nanf(""); }
+        else { uu = (float)(pj - 64); vv = (float)(pi - 64); }
+    } else {
+        const float eps = p.gauss_eps;
+        const float lc = logf(cmax + eps);
+        const float ll = logf(nb[0 * 128 + pj] + eps), lr = logf(nb[2 * 128 + pj] + eps);
+        const float ld = logf(nb[1 * 128 + pj - 1] + eps), lu = logf(nb[1 * 128 + pj + 1] + eps);
+        vv = ((float)pi + (ll - lr) / (2.f * ll - 4.f * lc + 2.f * lr)) - 64.f;
+        uu = ((float)pj + (ld - lu) / (2.f * ld - 4.f * lc + 2.f * lu)) - 64.f;
+    }
+    float oc = cmax, os = cmax / mean;
+    const int widx = w == 0 ? un.w[0] : un.w[1];
+    if (p.keep && !p.keep[widx]) { uu = vv = oc = os = nanf(""); }
+    const long long o = (long long)pair * p.n_rows * p.n_cols + widx;
+    p.u[o] = uu; p.v[o] = vv; p.cmax[o] = oc; p.s2n[o] = os;
+}
+
+// optional triage dump of the full planes (fftshifted, clipped): every thread writes its 64 elements of one reference row
+__device__ __forceinline__ void r128_dump_planes(RRegs<R6>& r, int sub, int t, const RParams& p, const RUnit& un, int pair) {
+    if (!p.planes) return;
+    const int q1 = sub >> 1, q2 = sub & 1;
+    const int si = (2 * column_of<64>(t) + q1 + 64) & 127;
+    const long long nw = (long long)p.n_rows * p.n_cols;
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        if (w == 1 && !un.valid1) continue;
+        float* dst = p.planes + (((long long)pair * nw + un.w[w]) * 128 + si) * 128;
+#pragma unroll
+        for (int x = 0; x < 64; ++x) dst[(2 * x + q2 + 64) & 127] = r.dead[w] ? 0.f : (w == 0 ? r.v[x].x : r.v[x].y);
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace b2piv

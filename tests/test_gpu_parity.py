@@ -122,6 +122,51 @@ def test_rows_kernel_window_starts_not_16_byte_aligned(engine, ws, ov, shape, ru
     engine.set_option("kernel_variant", 0.0)
 
 
+ROWS128_CASES = [
+    ((128, 128), (64, 64), (4, 300, 420), 0),       # 3 x 5 windows: odd count -> last unit has one window
+    ((128, 128), (64, 64), (6, 256 + 9, 384 + 16), 2),   # runs of 2 pairs: unit boundaries inside the stack
+    ((128, 128), (32, 32), (3, 330, 450), 0),       # stride 96
+    ((128, 128), (112, 112), (3, 170, 200), 1),     # stride 16: heavy overlap, many windows per TMA row band
+]
+
+
+@pytest.mark.parametrize("ws,ov,shape,run_len", ROWS128_CASES)
+@pytest.mark.parametrize("clip", [1, 0])
+def test_rows128_kernel_matches_oracle(engine, ws, ov, shape, run_len, clip):
+    """128x128 windows on the polyphase row-per-thread kernel (forced): four 64x64 sub-groups coupled in the cross phase."""
+    imgs = synth.particle_frames(*shape, dtype=np.uint8)
+    imgs[:, :140, :150] = 0                        # a dead window (zero variance) next to live ones
+    compare(engine, imgs, ws, ov, clip, variant=2, run_len=run_len)
+    engine.set_option("kernel_variant", 0.0)
+
+
+def test_rows128_and_generic_kernels_agree_and_signal_threshold(engine):
+    imgs = synth.particle_frames(4, 300, 420, dtype=np.uint8)
+    imgs[:, 150:, 200:] = 0
+    engine.set_option("clip_normalized", 0.0)
+    engine.set_option("run_len", 0.0)
+    engine.set_option("kernel_variant", 1.0)
+    a = engine.pairs(imgs, (128, 128), (64, 64))
+    engine.set_option("kernel_variant", 2.0)
+    b = engine.pairs(imgs, (128, 128), (64, 64))
+    engine.set_option("kernel_variant", 0.0)
+    for x, y in zip(a, b):
+        assert np.array_equal(np.isnan(x), np.isnan(y))
+        assert np.nanmax(np.abs(x - y) / (1 + np.abs(x))) < 2e-5
+    compare(engine, imgs, (128, 128), (64, 64), 0, signal_threshold=0.6, variant=2)
+    engine.set_option("kernel_variant", 0.0)
+
+
+def test_rows128_kernel_needs_16_byte_strides(engine):
+    imgs = synth.particle_frames(3, 300, 420, dtype=np.uint8)
+    engine.set_option("kernel_variant", 2.0)
+    with pytest.raises(NotImplementedError):
+        engine.pairs(imgs, (128, 128), (60, 60))          # stride 68
+    engine.set_option("kernel_variant", 0.0)
+    compare(engine, imgs, (128, 128), (60, 60), 0)      # auto: shared-memory kernel
+    compare(engine, imgs.astype(np.float32), (128, 128), (64, 64), 0)   # float32 frames: shared-memory kernel
+
+
 def test_rows_kernel_refuses_stride_not_multiple_of_4(engine):
     imgs = synth.particle_frames(3, 100, 144, dtype=np.uint8)
     engine.set_option("kernel_variant", 2.0)

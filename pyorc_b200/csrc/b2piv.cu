@@ -527,7 +527,8 @@ struct b2piv_engine {
     int device = 0;
     std::string err;
     // options
-    int clip_norm = 0, border_nan = 1, copy_chunks = 8;   // clip_norm = 0 is what ffpiv does (pinned, tests/test_golden.py)
+    int clip_norm = 0, border_nan = 1, copy_chunks = 0;   // copy_chunks = 0: auto (about 10 MB of frames per H2D chunk)
+      // clip_norm = 0 is what ffpiv does (pinned, tests/test_golden.py)
     int variant = 0;    // 0: auto, 1: generic shared-memory FFT kernel, 2: row-per-thread TMA kernel (error if
                         // ineligible), 3: direct any-size kernel
     int run_len = 0;    // frame pairs per work unit of the rows kernel (0: auto)
@@ -1039,7 +1040,7 @@ int b2piv_set_option(b2piv_engine* e, const char* name, double value) {
     if (n == "clip_normalized") e->clip_norm = value != 0.0;
     else if (n == "border_nan") e->border_nan = value != 0.0;
     else if (n == "gauss_eps") e->gauss_eps = (float)value;
-    else if (n == "copy_chunks") e->copy_chunks = value < 1 ? 1 : (int)value;
+    else if (n == "copy_chunks") e->copy_chunks = value < 0 ? 0 : (int)value;
     else if (n == "kernel_variant") e->variant = (int)value;
     else if (n == "run_len") e->run_len = value < 0 ? 0 : (int)value;
     else if (n == "groups") e->groups = value < 0 ? 0 : (int)value;
@@ -1118,7 +1119,17 @@ static int pipeline_host(b2piv_engine* e, const void* frames, int n_frames, bool
     int rc = ensure(e, &e->d_frames, &e->cap_frames, fbytes * n_frames);
     if (rc) return rc;
     const int n_pairs = n_frames - 1;
-    int chunks = pipelined ? e->copy_chunks : 1;
+    // auto: ~10 MB per chunk, at most 32 chunks (measured on B200, tools/e2e_sweep.py: 100 pairs of 1080p are fastest with
+    // 16-25 chunks - the tail after the last H2D is one chunk of compute, and every chunk costs one extra transform per unit)
+    int chunks = 1;
+    if (pipelined) {
+        chunks = e->copy_chunks;
+        if (chunks <= 0) {
+            const size_t target = (size_t)10 << 20;
+            size_t c = (fbytes * (size_t)n_frames + target - 1) / target;
+            chunks = (int)(c < 1 ? 1 : (c > 32 ? 32 : c));
+        }
+    }
     if (chunks > n_pairs) chunks = n_pairs;
     while ((int)e->ev_chunk.size() < chunks) {
         cudaEvent_t ev;

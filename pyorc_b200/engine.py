@@ -139,6 +139,55 @@ class _CudaView:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
+class _PinnedPool:
+    """Page-locked result buffers, recycled: a block goes back to the pool when the last numpy view of it is collected.
+
+    Results copied into pageable ``np.empty`` arrays go through the driver's staging buffer (measured: ~0.3 ms for the 3 MB of
+    a 100-pair 1080p call, 7 % of the whole end-to-end step); blocks are only ever allocated while the caller still holds
+    every earlier result, so a steady loop allocates nothing."""
+
+    def __init__(self, lib):
+        import threading
+
+        self._lib, self._free, self._lock, self._closed = lib, {}, threading.Lock(), False
+
+    @staticmethod
+    def _cls(nbytes: int) -> int:
+        return max(1 << 16, 1 << (int(nbytes) - 1).bit_length())          # power-of-two size classes >= 64 KB
+
+    def empty(self, shape, dtype=np.float32) -> np.ndarray:
+        import weakref
+
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        size = self._cls(max(count * dtype.itemsize, 1))
+        with self._lock:
+            lst = self._free.get(size)
+            ptr = lst.pop() if lst else None
+        if ptr is None:
+            ptr = self._lib.b2piv_host_alloc(size)
+            if not ptr:
+                raise MemoryError("cudaHostAlloc failed")
+        buf = (ctypes.c_ubyte * size).from_address(ptr)
+        weakref.finalize(buf, self._give, ptr, size)
+        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+    def _give(self, ptr, size):
+        with self._lock:
+            if not self._closed:
+                self._free.setdefault(size, []).append(ptr)
+                return
+        self._lib.b2piv_host_free(ptr)
+
+    def close(self):
+        with self._lock:
+            self._closed = True
+            blocks = [p for lst in self._free.values() for p in lst]
+            self._free = {}
+        for ptr in blocks:
+            self._lib.b2piv_host_free(ptr)
+
+
 class Engine:
     """One PIV engine bound to one CUDA device (mirrors the role of ffpiv's ``engine=`` back-ends)."""
 
@@ -154,6 +203,7 @@ class Engine:
         self.device = int(device)
         self._plan = None
         self._pinned = []
+        self._results = _PinnedPool(self._lib)
         if clip_normalized is not None:
             self.set_option("clip_normalized", float(bool(clip_normalized)))
         if border_nan is not None:
@@ -172,6 +222,7 @@ class Engine:
             for p in self._pinned:
                 self._lib.b2piv_host_free(p)
             self._pinned = []
+            self._results.close()
             self._lib.b2piv_destroy(self._h)
             self._h = None
 
@@ -288,7 +339,9 @@ class Engine:
                 "b2piv_pairs_device",
             )
             return out[0], out[1], out[2], out[3]
-        outs = [np.empty((n - 1, nr, nc), dtype=np.float32) for _ in range(4)]
+        # the four fields are views of ONE page-locked block that returns to the engine's pool when they are all released
+        block = self._results.empty((4, n - 1, nr, nc), np.float32)
+        outs = [block[k] for k in range(4)]
         self._check(
             self._lib.b2piv_pairs_host(self._h, frames.ctypes.data, n, thr, *[o.ctypes.data for o in outs]),
             "b2piv_pairs_host",

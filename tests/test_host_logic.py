@@ -145,3 +145,50 @@ def test_window_memory_model():
         window.get_axis_shape(100, 16, 16)
     with pytest.raises(NotImplementedError):
         window.get_rect_coordinates((100, 100), (32, 32), (16, 16), search_area_size=(64, 64))
+
+
+def test_pinned_result_pool_recycles_blocks_only_when_every_view_is_gone():
+    """Engine.pairs returns four views of one page-locked block; the block goes back to the pool when all are collected."""
+    import ctypes
+    import gc
+
+    from pyorc_b200.engine import _PinnedPool
+
+    class FakeLib:
+        def __init__(self):
+            self.live, self.allocs = {}, 0
+
+        def b2piv_host_alloc(self, size):
+            b = ctypes.create_string_buffer(size)
+            self.live[ctypes.addressof(b)] = b
+            self.allocs += 1
+            return ctypes.addressof(b)
+
+        def b2piv_host_free(self, p):
+            del self.live[p]
+
+    lib = FakeLib()
+    pool = _PinnedPool(lib)
+    a = pool.empty((4, 10, 3, 5))
+    a[...] = 1.5
+    view = a[2]
+    del a
+    gc.collect()
+    assert lib.allocs == 1 and not pool._free          # a view is still alive
+    b = pool.empty((4, 10, 3, 5))
+    assert lib.allocs == 2                              # so a second call must not reuse the block
+    assert float(view[0, 0, 0]) == 1.5
+    del view
+    gc.collect()
+    c = pool.empty((4, 10, 3, 5))
+    assert lib.allocs == 2                              # recycled
+    del b, c
+    gc.collect()
+    pool.close()
+    assert not lib.live
+    late = _PinnedPool(lib)
+    d = late.empty((8,))
+    late.close()
+    del d
+    gc.collect()
+    assert not lib.live                                 # released after close: freed, not pooled

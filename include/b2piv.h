@@ -176,6 +176,18 @@ int b2piv_decode_int16(b2piv_engine* e, const short* d_packed, long long count, 
 int b2piv_rotate_uv(b2piv_engine* e, const float* d_u, const float* d_v, long long count, double theta, double* d_u2, double* d_v2,
                     void* cuda_stream);
 
+/* ---- Two-pass PIV (BASELINE.json configs[2] "2-pass deform") --------------------------------
+ * No reference counterpart: ffpiv is single pass (pyorc/velocimetry/ffpiv.py:446-474 calls cross_corr once), so the scheme is
+ * defined in oracle/multipass_oracle.py.  predictor: pass-1 fields u1, v1 (float32 [n_pairs][rows1][cols1], px/frame, NaN
+ * allowed) of the coarse grid (wy1, wx1, oy1, ox1) -> universal outlier detection on 3x3 neighbourhoods -> bilinear
+ * interpolation at the window centres of the CURRENT plan (the fine grid) -> whole-pixel shifts (dy, dx), clamped so the
+ * displaced window stays inside the frame: int16 [n_pairs][n_rows * n_cols][2].  pairs_shifted: like b2piv_pairs_device,
+ * but frame k+1's window of every (pair, window) is displaced by its shift; u, v are shift + residual. */
+int b2piv_predictor_device(b2piv_engine* e, const float* d_u1, const float* d_v1, int n_pairs, int rows1, int cols1, int wy1, int wx1,
+                           int oy1, int ox1, short* d_shift, void* cuda_stream);
+int b2piv_pairs_shifted_device(b2piv_engine* e, const void* d_frames, long long frame_stride_bytes, int pitch_bytes, int n_frames,
+                               const short* d_shift, float* d_u, float* d_v, float* d_corr_max, float* d_s2n, void* cuda_stream);
+
 /* Page-locked host memory so H2D copies run at full PCIe rate without staging. */
 void* b2piv_host_alloc(size_t bytes);
 void b2piv_host_free(void* p);

@@ -11,6 +11,7 @@
 #include "preproc.cuh"
 #include "project.cuh"
 #include "mask.cuh"
+#include "multipass.cuh"
 
 #include <cuda.h>   // CUtensorMap (types only; the encoder is resolved at run time, libcuda is not linked)
 
@@ -558,6 +559,7 @@ struct b2piv_engine {
     int* d_proj_off = nullptr; size_t cap_proj_off = 0;
     int* d_proj_src = nullptr; size_t cap_proj_src = 0;
     int proj_h = 0, proj_w = 0, proj_out_h = 0, proj_out_w = 0; long long proj_samples = 0;
+    double* d_mp_ws = nullptr; size_t cap_mp_ws = 0;        // two-pass scheme: validated pass-1 fields
     float* d_mask_ws = nullptr; size_t cap_mask_ws = 0;     // mask stack: time statistics / window_replace ping-pong
     float* d_ens_sum = nullptr; float* d_ens_cnt = nullptr; size_t cap_ens = 0, cap_ens_windows = 0; bool ens_open = false;
     // stats
@@ -865,8 +867,22 @@ static void plane_shape(const b2piv_engine* e, int* py, int* px) {
     *py = a; *px = b;
 }
 
+// shared-memory FFT kernel (piv_core.cuh) on the window's own plane or, for sizes that are not a compiled FFT shape, padded
+static int launch_generic(b2piv_engine* e, const Params& p, cudaStream_t st) {
+    e->last_variant = 1;
+    int py, px;
+    plane_shape(e, &py, &px);
+    const bool padded = !(py == e->wy && px == e->wx);
+#define X(Y, XX, T, NW) if (py == Y && px == XX) return padded ? launch_pairs<Cfg<Y, XX, T, NW, true>>(e, p, st) : launch_pairs<Cfg<Y, XX, T, NW, false>>(e, p, st);
+    B2PIV_CONFIGS(X)
+#undef X
+    return fail(e, B2PIV_ERR_UNSUPPORTED, "window size not compiled in");
+}
+
 static int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
     if (p.n_pairs <= 0) return B2PIV_OK;
+    // displaced second-pass windows (multipass.cuh) break the frame-to-frame spectrum sharing of the row-per-thread kernels
+    if (p.shift) return launch_generic(e, p, st);
     const bool can_rows = rows_eligible(e, p.frames, p.frame_stride, p.pitch);
     if (e->variant == 2 && !can_rows && e->wy != 128)
         return fail(e, B2PIV_ERR_UNSUPPORTED, "rows kernel needs a square 32/64 window, 16-byte aligned base/pitch and an x stride that is a multiple of 4");
@@ -913,14 +929,7 @@ static int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
         e->last_variant = 3;
         return launch_direct(e, p, st);
     }
-    e->last_variant = 1;
-    int py, px;
-    plane_shape(e, &py, &px);
-    const bool padded = !(py == e->wy && px == e->wx);
-#define X(Y, XX, T, NW) if (py == Y && px == XX) return padded ? launch_pairs<Cfg<Y, XX, T, NW, true>>(e, p, st) : launch_pairs<Cfg<Y, XX, T, NW, false>>(e, p, st);
-    B2PIV_CONFIGS(X)
-#undef X
-    return fail(e, B2PIV_ERR_UNSUPPORTED, "window size not compiled in");
+    return launch_generic(e, p, st);
 }
 static int dispatch_ens(b2piv_engine* e, const Params& p, const EnsParams& ep, cudaStream_t st) {
     if (p.n_pairs <= 0) return B2PIV_OK;
@@ -1024,7 +1033,7 @@ void b2piv_destroy(b2piv_engine* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     cudaFree(e->d_twx); cudaFree(e->d_twy); cudaFree(e->d_frames); cudaFree(e->d_out); cudaFree(e->d_planes);
-    cudaFree(e->d_keep); cudaFree(e->d_ens_sum); cudaFree(e->d_ens_cnt); cudaFree(e->d_pre_mean); cudaFree(e->d_pre_mm); cudaFree(e->d_mask_ws);
+    cudaFree(e->d_keep); cudaFree(e->d_ens_sum); cudaFree(e->d_ens_cnt); cudaFree(e->d_pre_mean); cudaFree(e->d_pre_mm); cudaFree(e->d_mask_ws); cudaFree(e->d_mp_ws);
     cudaFree(e->d_proj_off); cudaFree(e->d_proj_src); cudaFree(e->d_planes_nat);
     for (auto ev : e->ev_chunk) cudaEventDestroy(ev);
     if (e->ev_k0) cudaEventDestroy(e->ev_k0);
@@ -1804,6 +1813,48 @@ int b2piv_rotate_uv(b2piv_engine* e, const float* d_u, const float* d_v, long lo
     if (count <= 0) return count == 0 ? B2PIV_OK : fail(e, B2PIV_ERR_ARG, "negative count");
     rotate_uv_kernel<<<mask_grid(e, count), 256, 0, st>>>(d_u, d_v, count, std::cos(theta), std::sin(theta), d_u2, d_v2);
     MASK_EPILOGUE(1)
+}
+
+// ---- two-pass scheme (BASELINE configs[2]; kernels in multipass.cuh, definition in DESIGN.md §8) ----------
+int b2piv_predictor_device(b2piv_engine* e, const float* d_u1, const float* d_v1, int n_pairs, int rows1, int cols1, int wy1, int wx1,
+                           int oy1, int ox1, short* d_shift, void* cuda_stream) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (!e->planned) return fail(e, B2PIV_ERR_STATE, "b2piv_plan (fine grid) has not been called");
+    if (!d_u1 || !d_v1 || !d_shift) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
+    if (n_pairs < 1 || rows1 < 1 || cols1 < 1 || wy1 <= oy1 || wx1 <= ox1 || oy1 < 0 || ox1 < 0)
+        return fail(e, B2PIV_ERR_ARG, "bad coarse grid");
+    if ((e->H - wy1) / (wy1 - oy1) + 1 != rows1 || (e->W - wx1) / (wx1 - ox1) + 1 != cols1)
+        return fail(e, B2PIV_ERR_ARG, "coarse field shape does not match the planned frame size");
+    if (e->H > 32767 || e->W > 32767) return fail(e, B2PIV_ERR_UNSUPPORTED, "shifts are 16-bit");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t n1 = (size_t)n_pairs * rows1 * cols1;
+    int rc = ensure(e, &e->d_mp_ws, &e->cap_mp_ws, 2 * n1 * sizeof(double));
+    if (rc) return rc;
+    double* vu = e->d_mp_ws;
+    double* vv = e->d_mp_ws + n1;
+    mp_validate_kernel<<<mask_grid(e, (long long)n1, 128), 128, 0, st>>>(d_u1, d_v1, n_pairs, rows1, cols1, 0.1, 2.0, vu, vv);
+    const MpGrid g1{rows1, cols1, wy1, wx1, wy1 - oy1, wx1 - ox1};
+    const MpGrid g2{e->n_rows, e->n_cols, e->wy, e->wx, e->wy - e->oy, e->wx - e->ox};
+    const long long n2 = (long long)n_pairs * e->n_rows * e->n_cols;
+    mp_predictor_kernel<<<mask_grid(e, n2, 128), 128, 0, st>>>(vu, vv, n_pairs, g1, g2, e->H, e->W, d_shift);
+    CK(cudaGetLastError());
+    e->launches += 2;
+    return B2PIV_OK;
+}
+
+int b2piv_pairs_shifted_device(b2piv_engine* e, const void* d_frames, long long frame_stride_bytes, int pitch_bytes, int n_frames,
+                               const short* d_shift, float* d_u, float* d_v, float* d_corr_max, float* d_s2n, void* cuda_stream) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (!e->planned) return fail(e, B2PIV_ERR_STATE, "b2piv_plan has not been called");
+    if (!d_frames || !d_shift || !d_u || !d_v || !d_corr_max || !d_s2n) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
+    if (n_frames < 2) return fail(e, B2PIV_ERR_ARG, "need at least 2 frames (one pair)");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    Params p = base_params(e, d_frames, frame_stride_bytes, pitch_bytes, n_frames - 1);
+    p.shift = d_shift;
+    p.u = d_u; p.v = d_v; p.cmax = d_corr_max; p.s2n = d_s2n;
+    return dispatch_pairs(e, p, st);
 }
 
 void* b2piv_host_alloc(size_t bytes) {

@@ -140,6 +140,8 @@ struct Params {
     int n_pairs;              // frame pairs in this launch
     int ny, nx;               // true window size; equal to the FFT plane (WY, WX) or, for sizes that are not a power
                               // of two, at most half of it ("padded mode", see phase_embed)
+    const short* shift;       // optional [n_pairs][n_windows][2] = (dy, dx): whole-pixel displacement of frame k+1's window
+                              // (second pass of the two-pass scheme, multipass.cuh); the result is shift + residual
     int clip_norm;            // 1: clip normalised windows at 0 (OpenPIV normalize_intensity)
     int border_nan;           // 1: border peak -> NaN displacement, 0: integer peak
     float gauss_eps;          // epsilon added before logs
@@ -268,6 +270,12 @@ B2_HD void phase_load(Smem<C>& s, int tid, const Params& p, const Item& it) {
         const int r = it.w[w] / p.n_cols, c = it.w[w] % p.n_cols;
         const long long off = (long long)(r * p.sy) * p.pitch;
         const int x0 = c * p.sx;
+        // frame k+1's window, optionally displaced by whole pixels (the caller keeps it inside the frame)
+        long long boff = p.frame_stride;
+        if (p.shift) {
+            const short* sh = p.shift + 2 * ((long long)it.pair * p.n_rows * p.n_cols + it.w[w]);
+            boff += (long long)sh[0] * p.pitch + (long long)sh[1] * (p.is_f32 ? 4 : 1);
+        }
         unsigned long long sa = 0, sb = 0, qa = 0, qb = 0;
         float fa = 0.f, fb = 0.f;
         for (int e = tid; e < win_ny<C>(p) * win_nx<C>(p); e += C::NT) {
@@ -275,13 +283,13 @@ B2_HD void phase_load(Smem<C>& s, int tid, const Params& p, const Item& it) {
             float a, b;
             if (!p.is_f32) {
                 const unsigned char* ra = base + off + (long long)y * p.pitch + x0 + x;
-                const unsigned ua = ra[0], ub = ra[p.frame_stride];
+                const unsigned ua = ra[0], ub = ra[boff];
                 sa += ua; sb += ub; qa += ua * ua; qb += ub * ub;
                 a = (float)ua; b = (float)ub;
             } else {
                 const float* ra = (const float*)(base + off + (long long)y * p.pitch) + x0 + x;
                 a = ra[0];
-                b = *(const float*)((const unsigned char*)ra + p.frame_stride);
+                b = *(const float*)((const unsigned char*)ra + boff);
                 fa += a; fb += b;
             }
             s.plane[w][y * C::P + x] = make_float2(a, b);
@@ -543,6 +551,7 @@ B2_HD void phase_peak(Smem<C>& s, int tid, const Params& p, const Item& it) {
     float o_c = cmax, o_s = cmax / mean;
     if (p.keep && !p.keep[it.w[w]]) { uu = vv = o_c = o_s = nanf(""); }
     const long long o = (long long)it.pair * p.n_rows * p.n_cols + it.w[w];
+    if (p.shift) { vv += (float)p.shift[2 * o]; uu += (float)p.shift[2 * o + 1]; }
     p.u[o] = uu; p.v[o] = vv; p.cmax[o] = o_c; p.s2n[o] = o_s;
 }
 

@@ -56,6 +56,8 @@ ABI_SYMBOLS = (
     "b2piv_encode_int16",
     "b2piv_decode_int16",
     "b2piv_rotate_uv",
+    "b2piv_predictor_device",
+    "b2piv_pairs_shifted_device",
     "b2piv_host_alloc",
     "b2piv_host_free",
     "b2piv_last_kernel_ms",
@@ -114,6 +116,8 @@ def load_library(path: Optional[str] = None):
     lib.b2piv_encode_int16.argtypes = [vp, vp, cll, cf, ci, vp, vp]
     lib.b2piv_decode_int16.argtypes = [vp, vp, cll, cf, ci, vp, vp]
     lib.b2piv_rotate_uv.argtypes = [vp, vp, vp, cll, cd, vp, vp, vp]
+    lib.b2piv_predictor_device.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, vp]
+    lib.b2piv_pairs_shifted_device.argtypes = [vp, vp, cll, ci, ci, vp, vp, vp, vp, vp, vp]
     lib.b2piv_host_alloc.argtypes = [ctypes.c_size_t]
     lib.b2piv_host_alloc.restype = vp
     lib.b2piv_host_free.argtypes = [vp]
@@ -347,6 +351,62 @@ class Engine:
             "b2piv_pairs_host",
         )
         return tuple(outs)
+
+    # ---- two-pass (BASELINE configs[2]) -----------------------------------------------------------------------
+    def predictor(self, u1, v1, dim_size, coarse, fine, dtype=np.uint8):
+        """Whole-pixel window shifts ``[n_pairs, n_rows, n_cols, 2]`` (dy, dx; int16, on the device) for a second pass on the
+        ``fine = (window_size, overlap)`` grid from the pass-1 fields ``u1, v1`` of the ``coarse`` grid (CUDA tensors):
+        universal outlier detection on 3x3 neighbourhoods, bilinear interpolation, rounding, clamping to the frame."""
+        import torch
+
+        (ws1, ov1), (ws2, ov2) = coarse, fine
+        nr, nc = self.plan(dim_size, ws2, ov2, dtype)
+        u1 = u1.contiguous().float()
+        v1 = v1.contiguous().float()
+        P, r1, c1 = u1.shape
+        shift = torch.empty((P, nr, nc, 2), dtype=torch.int16, device=u1.device)
+        st = torch.cuda.current_stream(u1.device).cuda_stream
+        self._check(self._lib.b2piv_predictor_device(self._h, u1.data_ptr(), v1.data_ptr(), P, r1, c1, int(ws1[0]), int(ws1[1]),
+                                                     int(ov1[0]), int(ov1[1]), shift.data_ptr(), st), "b2piv_predictor_device")
+        return shift
+
+    def pairs_shifted(self, frames, window_size, overlap, shift):
+        """Second pass: frame k+1's window of every (pair, window) displaced by ``shift[pair, row, col] = (dy, dx)``;
+        returns ``u, v`` (= shift + residual), ``corr_max, s2n`` as CUDA tensors.  ``frames``: CUDA tensor [n, H, W]."""
+        import torch
+
+        frames, n, nr, nc, on_dev = self._prep(frames, window_size, overlap)
+        if not on_dev:
+            raise TypeError("pairs_shifted takes device-resident frames (use pairs_two_pass for host arrays)")
+        if tuple(shift.shape) != (n - 1, nr, nc, 2) or shift.dtype != torch.int16 or not shift.is_cuda:
+            raise ValueError(f"shift must be a CUDA int16 tensor of shape {(n - 1, nr, nc, 2)}")
+        shift = shift.contiguous()
+        out = torch.empty((4, n - 1, nr, nc), dtype=torch.float32, device=frames.device)
+        st = torch.cuda.current_stream(frames.device).cuda_stream
+        es = frames.element_size()
+        self._check(self._lib.b2piv_pairs_shifted_device(self._h, frames.data_ptr(), frames.stride(0) * es, frames.stride(1) * es, n,
+                                                         shift.data_ptr(), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                                         out[3].data_ptr(), st), "b2piv_pairs_shifted_device")
+        return out[0], out[1], out[2], out[3]
+
+    def pairs_two_pass(self, frames, coarse=((64, 64), (48, 48)), fine=((32, 32), (24, 24))):
+        """Two-pass PIV with a discrete window offset (BASELINE.json configs[2]; defined in DESIGN.md §8, no reference
+        counterpart): pass 1 on the coarse grid -> validated, interpolated whole-pixel predictor -> pass 2 on the fine grid
+        with frame k+1's windows displaced.  numpy in -> numpy out; CUDA tensor in -> CUDA tensors out.
+        Returns ``u, v, corr_max, s2n`` on the fine grid (u, v = predictor + residual, px / frame)."""
+        import torch
+
+        was_np = not _is_torch(frames)
+        if was_np:
+            a = np.asarray(frames)
+            if a.dtype not in (np.uint8, np.float32):
+                a = a.astype(np.float32)
+            frames = torch.from_numpy(np.ascontiguousarray(a)).to(f"cuda:{self.device}")
+        dt = np.uint8 if frames.dtype == torch.uint8 else np.float32
+        u1, v1, _, _ = self.pairs(frames, coarse[0], coarse[1])
+        shift = self.predictor(u1, v1, tuple(frames.shape[-2:]), coarse, fine, dt)
+        res = self.pairs_shifted(frames, fine[0], fine[1], shift)
+        return tuple(r.cpu().numpy() for r in res) if was_np else res
 
     def corr_planes(self, frames, window_size, overlap, signal_threshold: Optional[float] = None) -> np.ndarray:
         """Full correlation planes ``[n-1, n_windows, wy, wx]`` float32 as ``ffpiv.cross_corr`` returns them

@@ -1,0 +1,179 @@
+"""Two-pass PIV of BASELINE.json configs[2] ("2-pass deform").  There is no reference implementation (ffpiv is single pass),
+so the scheme is defined in oracle/multipass_oracle.py (parity UNPINNED, stated there): the CPU tests check the definition on
+hand-made fields, the GPU tests check the CUDA path against it stage by stage and against the imposed synthetic field."""
+import numpy as np
+import pytest
+
+from oracle import ffpiv_oracle as O
+from oracle import multipass_oracle as MP
+from pyorc_b200 import synth
+
+COARSE, FINE = ((64, 64), (48, 48)), ((32, 32), (24, 24))
+
+
+# ---- CPU: the definition -------------------------------------------------------------------------------------------------
+def test_validate_replaces_outliers_and_nans_by_the_neighbourhood_median():
+    u = np.full((1, 5, 6), 3.0)
+    v = np.full((1, 5, 6), -1.0)
+    u += np.arange(6)[None, None, :] * 0.01
+    u[0, 2, 3] = 40.0          # spurious vector
+    v[0, 1, 1] = np.nan        # invalid vector
+    u[0, 4, 5] = 3.3           # |3.3 - 3.04| / (0.01 + 0.1) > 2  -> replaced as well
+    ou, ov = MP.validate(u, v)
+    assert abs(ou[0, 2, 3] - 3.03) < 0.011 and ov[0, 2, 3] == -1.0
+    assert np.isfinite(ov[0, 1, 1]) and ov[0, 1, 1] == -1.0 and abs(ou[0, 1, 1] - 3.01) < 0.011
+    assert abs(ou[0, 4, 5] - 3.04) < 0.011
+    keep = np.ones_like(u, bool)
+    keep[0, 2, 3] = keep[0, 1, 1] = keep[0, 4, 5] = False
+    assert np.array_equal(ou[keep], u[keep]) and np.array_equal(ov[keep], v[keep])
+    # a lone vector without any valid neighbour is kept; a lone NaN becomes 0
+    lone = np.full((1, 1, 1), 7.0)
+    assert MP.validate(lone, lone)[0][0, 0, 0] == 7.0
+    assert MP.validate(np.full((1, 1, 1), np.nan), lone)[0][0, 0, 0] == 0.0
+
+
+def test_predictor_interpolates_rounds_and_clamps():
+    H, W = 256, 320
+    nr1, nc1 = O.get_array_shape((H, W), *COARSE)
+    u = np.full((1, nr1, nc1), 2.5)              # rint(2.5) = 2 (half to even)
+    v = np.full((1, nr1, nc1), -3.5)             # rint(-3.5) = -4
+    dy, dx = MP.predictor(u, v, (H, W), COARSE, FINE)
+    nr2, nc2 = O.get_array_shape((H, W), *FINE)
+    assert dy.shape == (1, nr2, nc2)
+    y2, x2 = O.window_origins((H, W), *FINE)
+    assert (dx[0, :, :-1] == 2).all() and (dy[0, 1:, :] == -4).all()
+    assert (dy[0, 0, :] == 0).all()                                   # row 0 cannot move up: clamped to the frame
+    assert ((x2[None, :] + dx[0] + 32) <= W).all() and ((y2[:, None] + dy[0]) >= 0).all()
+    # a linear field is reproduced by the bilinear interpolation between the coarse centres
+    yc = (np.arange(nr1) * 16 + 32)[:, None] * np.ones((1, nc1))
+    dy2, _ = MP.predictor(np.zeros((1, nr1, nc1)), 0.05 * yc[None], (H, W), COARSE, FINE)
+    inner = (y2 + 16 >= 32) & (y2 + 16 <= yc[-1, 0])
+    assert np.array_equal(dy2[0, inner, 3], np.rint(0.05 * (y2[inner] + 16)).astype(int))
+
+
+def test_two_pass_recovers_large_displacements_better_than_a_single_fine_pass():
+    """10 px shifts are beyond what a 32 px window resolves well (a third of the particles leave the window); the coarse
+    predictor brings the second pass back to a near-zero residual."""
+    rng = np.random.default_rng(4)
+    base = synth.particle_frames(1, 200 + 40, 260 + 40, dtype=np.uint8, seed=11)[0]
+    a = base[20:220, 20:280]
+    b = base[20 - 7:220 - 7, 20 - 10:280 - 10]       # content moved by +7 rows, +10 columns
+    imgs = np.stack([a, b])
+    u, v, cm, sn, dy, dx = MP.two_pass(imgs, COARSE, FINE)
+    inner = (slice(None), slice(1, -1), slice(1, -1))
+    assert np.median(dx[inner]) == 10 and np.median(dy[inner]) == 7
+    ok = np.isfinite(u[inner])
+    assert ok.mean() > 0.95
+    assert np.abs(u[inner][ok] - 10).max() < 0.2 and np.abs(v[inner][ok] - 7).max() < 0.2
+    nr, nc = O.get_array_shape(imgs.shape[-2:], *FINE)
+    u1, v1, c1, _ = O.uv_timestep(imgs, nc, nr, *FINE)
+    assert np.nanmean(cm[inner]) > np.nanmean(c1[inner]) + 0.15      # the peak is much stronger once the window follows the flow
+
+
+# ---- GPU ---------------------------------------------------------------------------------------------------------------
+gpu = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from pyorc_b200.engine import Engine
+
+    e = Engine(0)
+    e.set_option("clip_normalized", 0.0)
+    O.CLIP_NORMALIZED = False
+    yield e
+    e.close()
+
+
+@gpu
+def test_gpu_predictor_equals_the_definition_on_the_same_pass1_fields(engine):
+    import torch
+
+    imgs = synth.particle_frames(4, 300, 420, dtype=np.uint8)
+    imgs[:, :70, :90] = 0                                    # dead coarse windows -> NaN vectors to validate away
+    d = torch.from_numpy(imgs).cuda()
+    u1, v1, _, _ = engine.pairs(d, *COARSE)
+    hu, hv = u1.cpu().numpy().copy(), v1.cpu().numpy().copy()
+    hu[1, 3, 4] += 25.0                                      # a spurious vector
+    u1 = torch.from_numpy(hu).cuda()
+    shift = engine.predictor(u1, v1, imgs.shape[-2:], COARSE, FINE).cpu().numpy()
+    vu, vv = MP.validate(hu, hv)
+    dy, dx = MP.predictor(vu, vv, imgs.shape[-2:], COARSE, FINE)
+    assert np.array_equal(shift[..., 0], dy) and np.array_equal(shift[..., 1], dx)
+    assert np.isnan(hu).any() and np.abs(dx).max() < 12
+
+
+@gpu
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32])
+def test_gpu_shifted_pass_matches_the_definition(engine, dtype):
+    import torch
+
+    imgs = synth.particle_frames(3, 200, 280, dtype=dtype)
+    nr, nc = O.get_array_shape(imgs.shape[-2:], *FINE)
+    rng = np.random.default_rng(2)
+    y0, x0 = O.window_origins(imgs.shape[-2:], *FINE)
+    dy = np.clip(rng.integers(-6, 7, (2, nr, nc)), -y0[None, :, None], (200 - 32 - y0)[None, :, None])
+    dx = np.clip(rng.integers(-6, 7, (2, nr, nc)), -x0[None, None, :], (280 - 32 - x0)[None, None, :])
+    shift = torch.from_numpy(np.stack([dy, dx], axis=-1).astype(np.int16)).cuda()
+    gu, gv, gc, gs = (t.cpu().numpy() for t in engine.pairs_shifted(torch.from_numpy(imgs).cuda(), *FINE, shift))
+    u, v, c, s = MP.shifted_pass(imgs, dy, dx, *FINE)
+    assert np.array_equal(np.isnan(gu), np.isnan(u))
+    fin = np.isfinite(u)
+    same = fin & (np.abs(np.round(gu) - np.round(u)) + np.abs(np.round(gv) - np.round(v)) < 0.5)
+    assert same[fin].mean() >= 0.995
+    assert np.abs(gu[same] - u[same]).max() <= 2e-3 and np.abs(gv[same] - v[same]).max() <= 2e-3
+    assert np.abs(gc - c).max() <= 5e-6
+    ok = np.isfinite(s) & (s != 0)
+    assert (np.abs(gs[ok] - s[ok]) / s[ok]).max() <= 2e-5
+    # zero shifts reproduce the ordinary single pass bit for bit
+    engine.set_option("kernel_variant", 1.0)
+    ref = engine.pairs(torch.from_numpy(imgs).cuda(), *FINE)
+    engine.set_option("kernel_variant", 0.0)
+    z = engine.pairs_shifted(torch.from_numpy(imgs).cuda(), *FINE, torch.zeros_like(shift))
+    for a, b in zip(ref, z):
+        assert np.array_equal(a.cpu().numpy(), b.cpu().numpy(), equal_nan=True)
+
+
+@gpu
+def test_gpu_two_pass_end_to_end_against_definition_and_truth(engine):
+    """configs[2] geometry at reduced frame size, host arrays in / out."""
+    H, W = 360, 480
+    imgs = synth.particle_frames(3, H, W, dtype=np.uint8)
+    gu, gv, gc, gs = engine.pairs_two_pass(imgs, COARSE, FINE)
+    u, v, c, s, dy, dx = MP.two_pass(imgs, COARSE, FINE)
+    assert gu.shape == u.shape == (2,) + O.get_array_shape((H, W), *FINE)
+    fin = np.isfinite(u) & np.isfinite(gu)
+    assert np.array_equal(np.isnan(gu), np.isnan(u))
+    close = np.abs(gu[fin] - u[fin]) + np.abs(gv[fin] - v[fin]) < 4e-3
+    assert close.mean() >= 0.995          # a pass-1 vector at a rounding boundary may move a predictor by one pixel
+    assert np.abs(gc[fin][close] - c[fin][close]).max() <= 5e-6
+    # truth: the imposed field at the window centres
+    y0, x0 = O.window_origins((H, W), *FINE)
+    yc, xc = np.meshgrid(y0 + 16.0, x0 + 16.0, indexing="ij")
+    tx, ty = synth.displacement_field(H, W, yc, xc)
+    nr, nc = gu.shape[1:]
+    one = engine.pairs(imgs, *FINE)
+    e2 = np.nanmedian(np.abs(gu - tx[None])) + np.nanmedian(np.abs(gv - ty[None]))
+    e1 = np.nanmedian(np.abs(one[0] - tx[None])) + np.nanmedian(np.abs(one[1] - ty[None]))
+    assert e2 < 0.2 and e2 <= e1 + 0.01
+    assert np.nanmean(gc) > np.nanmean(one[2])           # following the flow strengthens the correlation peak
+
+
+@gpu
+def test_gpu_two_pass_config2_full_frame(engine):
+    """BASELINE configs[2] at full 1080p frame size (132 x 237 windows per pair), a shard of 4 pairs, device resident."""
+    import torch
+
+    H, W = 1080, 1920
+    d = synth.particle_frames_torch(5, H, W, torch.device("cuda", 0), dtype="uint8")
+    u, v, c, s = engine.pairs_two_pass(d, COARSE, FINE)
+    assert tuple(u.shape) == (4, 132, 237) and u.is_cuda
+    y0, x0 = O.window_origins((H, W), *FINE)
+    yc, xc = np.meshgrid(y0 + 16.0, x0 + 16.0, indexing="ij")
+    tx, ty = synth.displacement_field(H, W, yc, xc)
+    hu, hv = u.cpu().numpy(), v.cpu().numpy()
+    assert np.isfinite(hu).mean() > 0.97
+    assert np.nanmedian(np.abs(hu - tx[None])) < 0.1 and np.nanmedian(np.abs(hv - ty[None])) < 0.1
+    # spot check against the definition on one pair of a frame crop is covered above; here: determinism
+    u2, v2, _, _ = engine.pairs_two_pass(d, COARSE, FINE)
+    assert torch.equal(torch.nan_to_num(u), torch.nan_to_num(u2)) and torch.equal(torch.nan_to_num(v), torch.nan_to_num(v2))

@@ -28,6 +28,25 @@ def run(H, W, ws, ov, n_frames, reps=5, dtype="uint8", variant=0, run_len=0, gro
     print(f"variant {variant} run_len {run_len} groups {groups} rolled {rolled} {H}x{W} win {ws} ov {ov} {dtype}: {nwin} windows in {t:.3f} ms -> {nwin / t / 1e3:.2f} Mwin/s  (u mean {float(torch.nanmean(out[0])):.3f} v mean {float(torch.nanmean(out[1])):.3f})", flush=True)
     e.close()
 
+def run_two_pass(H, W, n_frames, coarse=((64, 64), (48, 48)), fine=((32, 32), (24, 24)), reps=5):
+    """BASELINE configs[2]: pass 1 + validation / predictor + displaced pass 2, device resident."""
+    dev = torch.device("cuda", 0)
+    e = Engine(0)
+    fr = synth.particle_frames_torch(n_frames, H, W, dev, dtype="uint8")
+    for _ in range(3):
+        out = e.pairs_two_pass(fr, coarse, fine)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); out = e.pairs_two_pass(fr, coarse, fine); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    nr, nc = out[0].shape[1:]
+    nwin = (n_frames - 1) * nr * nc
+    t = float(np.median(ts))
+    print(f"TWO-PASS {coarse} -> {fine} {H}x{W} uint8: {nwin} fine windows in {t:.3f} ms -> {nwin / t / 1e3:.2f} Mwin/s  (u mean {float(torch.nanmean(out[0])):.3f} v mean {float(torch.nanmean(out[1])):.3f})", flush=True)
+    e.close()
+
 def run_ens(H, W, ws, ov, n_frames, reps=5, dtype="uint8", variant=0):
     """Ensemble mode on device-resident frames: begin + add (one launch) + finish, thresholds at pyorc's defaults."""
     dev = torch.device("cuda", 0)
@@ -67,8 +86,9 @@ if __name__ == "__main__":
         run(475, 371, (32, 32), (16, 16), 3)
         run(1080, 1920, (64, 64), (32, 32), 101)
         run(1080, 1920, (32, 32), (24, 24), 41)
+        run_two_pass(1080, 1920, 41)
         run(2160, 3840, (64, 64), (32, 32), 41)
-        run(4320, 7680, (128, 128), (64, 64), 11)
+        run(4320, 7680, (128, 128), (64, 64), 41)
         run(4320, 7680, (128, 128), (64, 64), 6, dtype="float32")
         sys.exit(0)
     if "--single" in sys.argv:

@@ -174,12 +174,62 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def other_configs(eng, dev):
+    """windows/s of BASELINE.json configs[0], [2], [3], [4] (their geometry, a shard of frame pairs each, frames resident in
+    HBM, CUDA events, median of 5 after 2 warm-ups) with the algorithmic HBM bytes / fp32 flops of SURVEY.md §8(d)."""
+    import torch
+
+    from pyorc_b200 import synth
+
+    peak, _ = measured_peaks()
+
+    def timed(fn, reps=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = fn()
+            b.record()
+            torch.cuda.synchronize(dev)
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts)), out
+
+    rows = []
+    cases = [("configs[0] geometry: 475x371, 32x32 / 50 %", 475, 371, (32, 32), (16, 16), 3, False),
+             ("configs[2] single pass: 1080p, 32x32 / 75 %", 1080, 1920, (32, 32), (24, 24), 21, False),
+             ("configs[2] two-pass (64x64 / 75 % -> 32x32 / 75 %, discrete window offset)", 1080, 1920, (32, 32), (24, 24), 21, True),
+             ("configs[3] geometry: 4K, 64x64 / 50 %", 2160, 3840, (64, 64), (32, 32), 21, False),
+             ("configs[4] geometry: 8K, 128x128 / 50 %", 4320, 7680, (128, 128), (64, 64), 11, False)]
+    for name, h, w, ws, ov, n, two_pass in cases:
+        try:
+            fr = synth.particle_frames_torch(n, h, w, dev, dtype="uint8")
+            if two_pass:
+                ms, out = timed(lambda: eng.pairs_two_pass(fr, ((64, 64), (48, 48)), (ws, ov)))
+            else:
+                ms, out = timed(lambda: eng.pairs(fr, ws, ov))
+            nwin = int(out[0].numel())
+            b_alg = 2 * (ws[0] - ov[0]) * (ws[1] - ov[1]) + 16
+            f_alg = 3 * 2.5 * ws[0] * ws[1] * np.log2(ws[0] * ws[1]) + 6 * ws[0] * (ws[1] // 2 + 1)
+            rows.append({"config": name, "pairs": n - 1, "windows": nwin, "ms": ms, "windows_per_s": nwin / (ms * 1e-3),
+                         "hbm_frac": b_alg * nwin / (ms * 1e-3) / 1e9 / peak,
+                         "fp32_tflops": f_alg * nwin / (ms * 1e-3) / 1e12})
+            del fr, out
+        except Exception as exc:   # a shard that does not fit must not take the headline down with it
+            rows.append({"config": name, "error": str(exc)[:200]})
+    eng.plan((H, W), WS, OV, np.uint8)
+    return rows
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of BASELINE.json configs[0], [2], [3], [4]")
     ap.add_argument("--cpu-pairs", type=int, default=0, help="frame pairs of the workload the CPU baseline times (0: min(max(4, cores), 16))")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -337,6 +387,12 @@ def main():
                 "v_px": float(np.sqrt(np.mean((hv[: args.cpu_pairs][ok] - v[ok]) ** 2))),
                 "windows": int(ok.sum()), "nan_mask_equal": bool(np.array_equal(np.isnan(u), np.isnan(hu[: args.cpu_pairs])))}
 
+    # ---- the other BASELINE.json configurations, device resident, one shard of frames each (N = 1 only; reported beside
+    # the headline, not part of it: the metric is quoted on configs[1]) ------------------------------------------------------
+    other = None
+    if world == 1 and not args.no_other_configs:
+        other = other_configs(eng, dev)
+
     line = {
         "metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -347,7 +403,7 @@ def main():
         "roofline": roofline, "fp32": fp32, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                 "ms_per_step": 1e3 * e2e_s / args.steps, "api": "pyorc_b200.engine.Engine.pairs(numpy pinned)", "pcie": pcie},
-        "gpu_launches": int(launches), "clocks": clocks, "rmse_vs_oracle": rmse,
+        "gpu_launches": int(launches), "clocks": clocks, "rmse_vs_oracle": rmse, "other_configs": other,
     }
     print(json.dumps(line), flush=True)
     eng.close()

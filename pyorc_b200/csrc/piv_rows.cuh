@@ -78,11 +78,14 @@ struct RCfg {
     static constexpr int FBOX = W * 128;                 // bytes per box
     static constexpr int FWIN = (W / 32) * FBOX;         // bytes per window
     static constexpr int F_PHASES = (W == 64) ? 2 : 1;   // TMA round trips per frame
-    // Transposes move 32x32 blocks: block b (pitch 33 float2) is READ by warp b.  A 64x64 transpose first moves the
+    // Transposes move 32x32 blocks: block b (pitch BP float2) is READ by warp b.  A 64x64 transpose first moves the
     // two off-diagonal blocks (one CTA barrier), then the diagonal ones (warp-synchronous), reusing the same two
     // blocks - half a plane - so a group needs ~52 KB of shared memory and FOUR groups (8 warps, two per
     // scheduler) fit on an SM.
-    static constexpr int BP = 33;                 // block pitch in float2
+    // block pitch in float2.  64x64: 33 (odd -> conflict-free 8-byte accesses both ways).  32x32: 34, rows start 16-byte
+    // aligned (272 B apart) and a thread stores its 32 values as 16 STS.128 (banks 4*lane + 4*j mod 32: conflict-free).
+    // A/B on one B200 (tools/ab.sh): STS.128 gains 1.7 % at 32x32 and loses 1 % at 64x64 / 128x128.
+    static constexpr int BP = (W == 32) ? 34 : 33;
     static constexpr int XBLK = 32 * BP;          // float2 per block
 };
 
@@ -232,11 +235,16 @@ B2_HD void rows_p1(RSmem<R>& s, RRegs<R>& r, int tid, int xoff0 = 0, int xoff1 =
 #pragma unroll
             for (int k = 0; k < W / 4; ++k) r.px[w][k] = *reinterpret_cast<const unsigned*>(row + 4 * k);
         }
+        // two accumulators per moment: the dp4a chains are the critical path of this phase (ncu: 27 % `wait` stalls)
+        unsigned S2 = 0, Q2 = 0;
 #pragma unroll
-        for (int k = 0; k < W / 4; ++k) {
+        for (int k = 0; k < W / 4; k += 2) {
             S[w] = dp4a_u(r.px[w][k], 0x01010101u, S[w]);
             Q[w] = dp4a_u(r.px[w][k], r.px[w][k], Q[w]);
+            S2 = dp4a_u(r.px[w][k + 1], 0x01010101u, S2);
+            Q2 = dp4a_u(r.px[w][k + 1], r.px[w][k + 1], Q2);
         }
+        S[w] += S2; Q[w] += Q2;
     }
     unsigned vals[4] = {S[0], Q[0], S[1], Q[1]};
 #ifdef __CUDA_ARCH__
@@ -446,7 +454,16 @@ B2_HD void rows_p2_pre(RSmem<R>& s, RRegs<R>& r, int tid, int clip_norm) {
 template <class R, int SET>
 B2_HD void tr_store_set(float2* blk, const RRegs<R>& r, int lane) {
 #pragma unroll
-    for (int sl = 0; sl < 32; ++sl) blk[lane * R::BP + sl] = r.v[column_of<R::W>(32 * SET + sl)];
+    if constexpr (R::BP % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float2 a = r.v[column_of<R::W>(32 * SET + 2 * j)], b = r.v[column_of<R::W>(32 * SET + 2 * j + 1)];
+            reinterpret_cast<float4*>(blk + lane * R::BP)[j] = make_float4(a.x, a.y, b.x, b.y);
+        }
+    } else {
+#pragma unroll
+        for (int sl = 0; sl < 32; ++sl) blk[lane * R::BP + sl] = r.v[column_of<R::W>(32 * SET + sl)];
+    }
 }
 template <class R, int SET>
 B2_HD void tr_load_set(const float2* blk, RRegs<R>& r, int lane) {

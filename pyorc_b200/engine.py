@@ -14,7 +14,8 @@ from typing import Optional, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libb2piv.so")
+# B2PIV_LIB: development override (A/B builds of the kernels); the default is the in-tree library
+_LIB_PATH = os.environ.get("B2PIV_LIB") or os.path.join(_HERE, "libb2piv.so")
 _lib = None
 
 B2PIV_U8, B2PIV_F32 = 0, 1

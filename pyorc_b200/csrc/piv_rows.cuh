@@ -106,6 +106,16 @@ static_assert(sizeof(float2) * RCfg<64>::NWARP * RCfg<64>::XBLK >= RCfg<64>::FWI
 static_assert(sizeof(float2) * RCfg<32>::NWARP * RCfg<32>::XBLK >= 2 * RCfg<32>::FWIN, "float tiles must fit in the transpose blocks");
 static_assert(sizeof(float2) * RCfg<32>::NWARP * RCfg<32>::XBLK >= RCfg<32>::TILE_U, "tile must fit in the transpose blocks");
 
+// displaced-window variant (second pass of the two-pass scheme): dedicated tile buffers so that both tiles of the next frame
+// can be prefetched while the transposes use X
+template <class R>
+struct RShiftSmem {
+    RSmem<R> base;
+    alignas(128) unsigned char tile_u[R::TILE_U];   // undisplaced windows of the frame (parked as `a` of the next pair)
+    alignas(128) unsigned char tile_d[R::TILE_U];   // displaced windows of the frame (`b` of this pair)
+    unsigned long long mbar_d;
+};
+
 struct RParams {
     const unsigned char* frames;   // only used by the host emulator (device reads through the tensor map)
     long long frame_stride;
@@ -117,6 +127,7 @@ struct RParams {
     int clip_norm, border_nan;
     float gauss_eps;
     const unsigned char* keep;
+    const short* shift;            // displaced second pass: [n_pairs][n_windows][2] = (dy, dx) of frame k+1's window, added to (v, u)
     float *u, *v, *cmax, *s2n;
     float* planes;
     // ensemble mode (piv_rows_kernel<..., ENS = true>): thresholds and the HBM accumulators [n_windows][W][W] / [n_windows]
@@ -219,19 +230,20 @@ B2_HD float byte_to_float(unsigned word, int b) {
 }
 
 template <class R, bool ALIGNED = true>
-B2_HD void rows_p1(RSmem<R>& s, RRegs<R>& r, int tid, int xoff0 = 0, int xoff1 = 0) {
+B2_HD void rows_p1(RSmem<R>& s, RRegs<R>& r, int tid, int xoff0 = 0, int xoff1 = 0, const unsigned char* tile_override = nullptr) {
     constexpr int W = R::W;
+    const unsigned char* tile_base = tile_override ? tile_override : s.tile();
     unsigned S[2] = {0, 0}, Q[2] = {0, 0};
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
         if (ALIGNED) {
 #pragma unroll
             for (int j = 0; j < W / 16; ++j) {
-                const uint4 q = *reinterpret_cast<const uint4*>(s.tile() + tile_chunk_offset<W>(w, column_of<W>(tid), j));
+                const uint4 q = *reinterpret_cast<const uint4*>(tile_base + tile_chunk_offset<W>(w, column_of<W>(tid), j));
                 r.px[w][4 * j + 0] = q.x; r.px[w][4 * j + 1] = q.y; r.px[w][4 * j + 2] = q.z; r.px[w][4 * j + 3] = q.w;
             }
         } else {
-            const unsigned char* row = s.tile() + (w * W + column_of<W>(tid)) * R::WB + (w == 0 ? xoff0 : xoff1);
+            const unsigned char* row = tile_base + (w * W + column_of<W>(tid)) * R::WB + (w == 0 ? xoff0 : xoff1);
 #pragma unroll
             for (int k = 0; k < W / 4; ++k) r.px[w][k] = *reinterpret_cast<const unsigned*>(row + 4 * k);
         }
@@ -565,6 +577,84 @@ __device__ __forceinline__ void rows_p3b_device(RSmem<R>& s, RRegs<R>& r, int ti
 #endif
 
 // ------------------------------------------------------------------------------------------------------------
+// Displaced windows (second pass of the two-pass scheme, multipass.cuh): frame k+1's window of a pair is read at
+// (y0 + dy, x0 + dx), any byte offset.  The TMA box starts at the 16-byte boundary below (16 bytes wider, no swizzle, like
+// ALIGNED = false); rows are funnel-shifted to the byte offset.  The displaced window only serves as `b` of its pair, the
+// undisplaced one as `a` of the next pair, so a frame costs two forward transforms: cross-only for the displaced tile,
+// park-only for the undisplaced one.
+// ------------------------------------------------------------------------------------------------------------
+template <class R>
+B2_HD void rows_p1_shift(RSmem<R>& s, RRegs<R>& r, int tid, const unsigned char* tile, int xoff0, int xoff1) {
+    constexpr int W = R::W;
+    const int row = column_of<W>(tid);
+    unsigned S[2] = {0, 0}, Q[2] = {0, 0};
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        const int xoff = w == 0 ? xoff0 : xoff1;
+        const unsigned char* base = tile + (w * W + row) * R::WB + (xoff & ~3);
+        const int sh = (xoff & 3) * 8;
+        unsigned wd[W / 4 + 1];
+#pragma unroll
+        for (int k = 0; k <= W / 4; ++k) wd[k] = *reinterpret_cast<const unsigned*>(base + 4 * k);
+#pragma unroll
+        for (int k = 0; k < W / 4; ++k) {
+            r.px[w][k] = funnel_r(wd[k], wd[k + 1], sh);
+            S[w] = dp4a_u(r.px[w][k], 0x01010101u, S[w]);
+            Q[w] = dp4a_u(r.px[w][k], r.px[w][k], Q[w]);
+        }
+    }
+    unsigned vals[4] = {S[0], Q[0], S[1], Q[1]};
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vals[k] += __shfl_xor_sync(0xffffffffu, vals[k], o);
+    }
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s.red[tid >> 5][k] = vals[k];
+    }
+#else
+    for (int k = 0; k < 4; ++k) s.red[tid >> 5][k] += vals[k];
+#endif
+}
+
+#ifdef __CUDACC__
+// displaced tile: cross spectra against the parked (undisplaced, previous frame) spectra, nothing is parked
+template <class R>
+__device__ __forceinline__ void rows_cross_only_device(RSmem<R>& s, RRegs<R>& r, int tid) {
+    constexpr int W = R::W;
+    const int pl = partner_lane_of<W>(tid);
+#pragma unroll
+    for (int ky = 0; ky <= W / 2; ++ky) {
+        const float2 pz = shfl2(r.v[(W - ky) % W], pl);
+        float2 a0, a1;
+        separate(r.v[ky], pz, r.half_alpha_new[0], r.half_alpha_new[1], a0, a1);
+        const float2 p0 = s.park[0][ky][tid], p1 = s.park[1][ky][tid];
+        const float2 r0 = make_float2(p0.x * a0.x + p0.y * a0.y, p0.x * a0.y - p0.y * a0.x);   // conj(p0) * a0
+        const float2 r1 = make_float2(p1.x * a1.x + p1.y * a1.y, p1.x * a1.y - p1.y * a1.x);
+        r.v[ky] = make_float2(r0.x - r1.y, -(r0.y + r1.x));                                    // conj(G), G = R0 + i R1
+        if (ky != 0 && ky != W / 2) cross_step_b<R>(r, ky, shfl2(cross_mirror(r0, r1), pl));
+    }
+}
+// undisplaced tile: park the scaled spectra for the next pair
+template <class R>
+__device__ __forceinline__ void rows_park_only_device(RSmem<R>& s, RRegs<R>& r, int tid) {
+    constexpr int W = R::W;
+    constexpr float INVN2 = 1.0f / ((float)R::NPX * (float)R::NPX);
+    const int pl = partner_lane_of<W>(tid);
+#pragma unroll
+    for (int ky = 0; ky <= W / 2; ++ky) {
+        const float2 pz = shfl2(r.v[(W - ky) % W], pl);
+        float2 a0, a1;
+        separate(r.v[ky], pz, r.half_alpha_new[0], r.half_alpha_new[1], a0, a1);
+        s.park[0][ky][tid] = make_float2(a0.x * INVN2, a0.y * INVN2);
+        s.park[1][ky][tid] = make_float2(a1.x * INVN2, a1.y * INVN2);
+    }
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------------------
 // P4: (forward FFT of conj G along columns, then) store column into X.
 // P5: row from X, (forward FFT along the row, then) conjugate, clip, per-row max / sum.
 // ------------------------------------------------------------------------------------------------------------
@@ -741,6 +831,7 @@ B2_HD void rows_p8(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p, const RU
     const int widx = w == 0 ? un.w[0] : un.w[1];
     if (p.keep && !p.keep[widx]) { uu = vv = oc = os = nanf(""); }
     const long long o = (long long)pair * p.n_rows * p.n_cols + widx;
+    if (p.shift) { vv += (float)p.shift[2 * o]; uu += (float)p.shift[2 * o + 1]; }
     p.u[o] = uu; p.v[o] = vv; p.cmax[o] = oc; p.s2n[o] = os;
 }
 

@@ -125,13 +125,53 @@ def test_gpu_shifted_pass_matches_the_definition(engine, dtype):
     assert np.abs(gc - c).max() <= 5e-6
     ok = np.isfinite(s) & (s != 0)
     assert (np.abs(gs[ok] - s[ok]) / s[ok]).max() <= 2e-5
-    # zero shifts reproduce the ordinary single pass bit for bit
+    # zero shifts reproduce the ordinary single pass: bit for bit on the shared-memory kernel (same code path) ...
     engine.set_option("kernel_variant", 1.0)
     ref = engine.pairs(torch.from_numpy(imgs).cuda(), *FINE)
-    engine.set_option("kernel_variant", 0.0)
     z = engine.pairs_shifted(torch.from_numpy(imgs).cuda(), *FINE, torch.zeros_like(shift))
     for a, b in zip(ref, z):
         assert np.array_equal(a.cpu().numpy(), b.cpu().numpy(), equal_nan=True)
+    # ... and the displaced row-per-thread kernel (uint8 frames, the default) agrees with the shared-memory kernel
+    gen = [t.cpu().numpy() for t in engine.pairs_shifted(torch.from_numpy(imgs).cuda(), *FINE, shift)]
+    engine.set_option("kernel_variant", 0.0)
+    for a, b in zip((gu, gv, gc, gs), gen):
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        assert np.nanmax(np.abs(a - b) / (1 + np.abs(a))) < 2e-5
+
+
+@gpu
+@pytest.mark.parametrize("ov,shape,run_len", [((24, 24), (5, 200, 288), 0), ((24, 24), (6, 130, 176), 2), ((16, 16), (4, 150, 208), 0),
+                                              ((20, 20), (3, 120, 160), 1)])
+def test_gpu_displaced_rows_kernel(engine, ov, shape, run_len):
+    """The displaced second pass on the row-per-thread kernel (forced): arbitrary byte offsets, unit boundaries inside the
+    stack, shifts up to the frame border, dead windows."""
+    import torch
+
+    imgs = synth.particle_frames(*shape, dtype=np.uint8)
+    imgs[:, :50, :60] = 0
+    n, H, W = shape
+    ws = (32, 32)
+    nr, nc = O.get_array_shape((H, W), ws, ov)
+    rng = np.random.default_rng(7)
+    y0, x0 = O.window_origins((H, W), ws, ov)
+    dy = np.clip(rng.integers(-40, 41, (n - 1, nr, nc)), -y0[None, :, None], (H - 32 - y0)[None, :, None])
+    dx = np.clip(rng.integers(-40, 41, (n - 1, nr, nc)), -x0[None, None, :], (W - 32 - x0)[None, None, :])
+    shift = torch.from_numpy(np.stack([dy, dx], axis=-1).astype(np.int16)).cuda()
+    engine.set_option("kernel_variant", 2.0)
+    engine.set_option("run_len", float(run_len))
+    gu, gv, gc, gs = (t.cpu().numpy() for t in engine.pairs_shifted(torch.from_numpy(imgs).cuda(), ws, ov, shift))
+    engine.set_option("kernel_variant", 0.0)
+    engine.set_option("run_len", 0.0)
+    u, v, c, s = MP.shifted_pass(imgs, dy, dx, ws, ov)
+    assert np.array_equal(np.isnan(gu), np.isnan(u))
+    fin = np.isfinite(u)
+    same = fin & (np.abs(np.round(gu) - np.round(u)) + np.abs(np.round(gv) - np.round(v)) < 0.5)
+    assert same[fin].mean() >= 0.99          # random 40 px shifts decorrelate most windows: noisy planes, a few near-ties
+    assert np.abs(gu[same] - u[same]).max() <= 2e-3 and np.abs(gv[same] - v[same]).max() <= 2e-3
+    assert np.abs(gc - c).max() <= 5e-6
+    ok = np.isfinite(s) & (s != 0)
+    assert np.array_equal(np.isnan(gs), np.isnan(s))
+    assert (np.abs(gs[ok] - s[ok]) / s[ok]).max() <= 2e-5
 
 
 @gpu

@@ -1,0 +1,31 @@
+"""Small invocations of every fused kernel family (for compute-sanitizer memcheck / racecheck runs)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from pyorc_b200.engine import Engine
+from pyorc_b200 import synth
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    e = Engine(0)
+    dev = torch.device("cuda", 0)
+    def frames(n, h, w, dtype="uint8"):
+        return synth.particle_frames_torch(n, h, w, dev, dtype=dtype)
+    if which in ("all", "rows64"):
+        out = e.pairs(frames(4, 200, 304), (64, 64), (32, 32)); print("rows64", float(torch.nanmean(out[0])))
+    if which in ("all", "rows32"):
+        out = e.pairs(frames(4, 120, 176), (32, 32), (24, 24)); print("rows32 unaligned", float(torch.nanmean(out[0])))
+    if which in ("all", "rows128"):
+        out = e.pairs(frames(4, 300, 420), (128, 128), (64, 64)); print("rows128", float(torch.nanmean(out[0])))
+    if which in ("all", "pad"):
+        out = e.pairs(frames(3, 120, 176), (26, 26), (12, 12)); print("pad26", float(torch.nanmean(out[0])))
+    if which in ("all", "twopass"):
+        out = e.pairs_two_pass(frames(4, 200, 288)); print("two-pass", float(torch.nanmean(out[0])))
+    if which in ("all", "ens"):
+        fr = frames(5, 200, 304)
+        e.ens_begin((200, 304), (64, 64), (32, 32), np.uint8); e.ens_add(fr, (64, 64), (32, 32), corr_min=0.2, s2n_min=3.0)
+        u, v, cnt = e.ens_finish(0.2); print("ens", float(np.nanmean(u)))
+    if which in ("all", "f32"):
+        out = e.pairs(frames(3, 200, 304, "float32"), (64, 64), (32, 32)); print("rows64 f32", float(torch.nanmean(out[0])))
+    torch.cuda.synchronize()
+    e.close()

@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -653,7 +654,8 @@ struct b2piv_engine {
     // plan
     bool planned = false;
     int H = 0, W = 0, wy = 0, wx = 0, oy = 0, ox = 0, dtype = 0, n_rows = 0, n_cols = 0;
-    float2 *d_twx = nullptr, *d_twy = nullptr;
+    float2 *d_twx = nullptr, *d_twy = nullptr;   // point into tw_cache
+    std::map<int, float2*> tw_cache;              // transform length -> exp(-2 pi i j / n) table on the device
     int sm_count = 0;
     // streams / events
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
@@ -1206,7 +1208,8 @@ void b2piv_destroy(b2piv_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    cudaFree(e->d_twx); cudaFree(e->d_twy); cudaFree(e->d_frames); cudaFree(e->d_out); cudaFree(e->d_planes);
+    for (auto& kv : e->tw_cache) cudaFree(kv.second);
+    cudaFree(e->d_frames); cudaFree(e->d_out); cudaFree(e->d_planes);
     cudaFree(e->d_keep); cudaFree(e->d_ens_sum); cudaFree(e->d_ens_cnt); cudaFree(e->d_pre_mean); cudaFree(e->d_pre_mm); cudaFree(e->d_mask_ws); cudaFree(e->d_mp_ws);
     cudaFree(e->d_proj_off); cudaFree(e->d_proj_src); cudaFree(e->d_planes_nat);
     for (auto ev : e->ev_chunk) cudaEventDestroy(ev);
@@ -1249,15 +1252,19 @@ int b2piv_plan(b2piv_engine* e, int height, int width, int win_y, int win_x, int
     // twiddle tables exp(-2 pi i j / N) for the FFT plane (= the window, or its padded power-of-two plane), in double
     int py = win_y, px = win_x;
     plane_shape(e, &py, &px);
-    std::vector<float2> tx(px), ty(py);
-    for (int j = 0; j < px; ++j) tx[j] = make_float2((float)cos(2.0 * M_PI * j / px), (float)-sin(2.0 * M_PI * j / px));
-    for (int j = 0; j < py; ++j) ty[j] = make_float2((float)cos(2.0 * M_PI * j / py), (float)-sin(2.0 * M_PI * j / py));
-    if (e->d_twx) { CK(cudaFree(e->d_twx)); e->d_twx = nullptr; }
-    if (e->d_twy) { CK(cudaFree(e->d_twy)); e->d_twy = nullptr; }
-    CK(cudaMalloc((void**)&e->d_twx, sizeof(float2) * px));
-    CK(cudaMalloc((void**)&e->d_twy, sizeof(float2) * py));
-    CK(cudaMemcpy(e->d_twx, tx.data(), sizeof(float2) * px, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(e->d_twy, ty.data(), sizeof(float2) * py, cudaMemcpyHostToDevice));
+    // (one table per transform length, built on first use and kept until the engine is destroyed: re-planning - e.g. the
+    // coarse / fine grids of the two-pass scheme, twice per call - must not allocate, free or synchronise)
+    for (int axis = 0; axis < 2; ++axis) {
+        const int n = axis == 0 ? px : py;
+        float2*& slot = e->tw_cache[n];
+        if (!slot) {
+            std::vector<float2> t(n);
+            for (int j = 0; j < n; ++j) t[j] = make_float2((float)cos(2.0 * M_PI * j / n), (float)-sin(2.0 * M_PI * j / n));
+            CK(cudaMalloc((void**)&slot, sizeof(float2) * n));
+            CK(cudaMemcpy(slot, t.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+        }
+        (axis == 0 ? e->d_twx : e->d_twy) = slot;
+    }
     e->planned = true;
     e->ens_open = false;
     if (n_rows) *n_rows = e->n_rows;

@@ -265,7 +265,7 @@ def main():
     def step_device():
         res = eng.pairs(frames, WS, OV)
         if world > 1:
-            return parallel.gather_fields(torch.stack(res), N_PAIRS * world, table)
+            return parallel.gather_fields(res, N_PAIRS * world, table)   # four fields, gathered in place
         return res
 
     def sync_all():

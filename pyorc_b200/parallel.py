@@ -52,6 +52,18 @@ def gather_fields(local, n_pairs_total: int, table: np.ndarray, group=None):
     world = dist.get_world_size(group)
     counts = (table[:, 1] - table[:, 0]).astype(int)
     pmax = int(counts.max()) if len(counts) else 0
+    # equal shards (the usual case): every field is gathered straight into its final place - rank r's pairs are the r-th
+    # contiguous block of out[k] - with one collective per field and no staging copies (stack / pad / trim cost 10 % of a
+    # 100-pair 1080p step on 8 GPUs).  `local` may be the engine's tuple of four tensors or a stacked tensor.
+    if len(counts) and int(counts.min()) == pmax and pmax > 0 and all(local[k].is_contiguous() for k in range(len(local))):
+        nf = len(local)
+        _, rows, cols = local[0].shape
+        out = torch.empty((nf, n_pairs_total, rows, cols), dtype=local[0].dtype, device=local[0].device)
+        for k in range(nf):
+            dist.all_gather_into_tensor(out[k], local[k], group=group)
+        return out
+    if isinstance(local, (tuple, list)):
+        local = torch.stack(list(local))
     nf, _, rows, cols = local.shape
     pad = torch.zeros((nf, pmax, rows, cols), dtype=local.dtype, device=local.device)
     pad[:, : local.shape[1]] = local

@@ -56,7 +56,7 @@ def _worker(rank, world, port, n_pairs, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_pairs", [5, 1])
+@pytest.mark.parametrize("n_pairs", [5, 1, 4])   # ragged shards, an empty shard, equal shards (in-place gather)
 def test_sharded_piv_over_gloo_equals_single_process(tmp_path, n_pairs):
     world = 2
     port = _free_port()

@@ -229,6 +229,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nccl-gather", action="store_true", help="N > 1: gather results with NCCL instead of the fused P2P stores")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of BASELINE.json configs[0], [2], [3], [4]")
     ap.add_argument("--cpu-pairs", type=int, default=0, help="frame pairs of the workload the CPU baseline times (0: min(max(4, cores), 16))")
     args = ap.parse_args()
@@ -254,6 +255,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL writes its version banner / debug lines to stdout by default: keep stdout for the ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     eng = Engine(local_rank)
     n_frames = N_PAIRS + 1
@@ -262,8 +265,24 @@ def main():
     nwin_rank = N_PAIRS * nr * nc
     table = parallel.shard_pairs(N_PAIRS * world, world)
 
+    # N > 1: the gather of the 16 B / window results is fused into the kernel epilogue (P2P stores into every rank's
+    # symmetric-memory buffer, then a device-side barrier); NCCL all-gather when peer memory is not available
+    peer = None
+    gather_how = None
+    if world > 1 and not args.nccl_gather:
+        try:
+            peer = parallel.PeerGather(eng, N_PAIRS * world, table)
+            gather_how = "fused: P2P stores from the kernel epilogue into symmetric memory + barrier"
+        except Exception as exc:   # no peer access / symmetric memory: keep the collective
+            peer = None
+            gather_how = f"nccl all_gather_into_tensor per field (symmetric memory unavailable: {str(exc)[:80]})"
+    elif world > 1:
+        gather_how = "nccl all_gather_into_tensor per field"
+
     def step_device():
         res = eng.pairs(frames, WS, OV)
+        if peer is not None:
+            return peer.wait()
         if world > 1:
             return parallel.gather_fields(res, N_PAIRS * world, table)   # four fields, gathered in place
         return res
@@ -295,6 +314,16 @@ def main():
     sync_all()
     ms_total = e0.elapsed_time(e1)
     launches = eng.launch_count - launches0
+    if peer is not None:
+        sync_all()
+        gathered = step_device()
+        sync_all()
+        # every rank must hold every rank's results: compare with an NCCL gather of the same step
+        ref_g = parallel.gather_fields(eng.pairs(frames, WS, OV), N_PAIRS * world, table)
+        same = bool(torch.equal(torch.nan_to_num(gathered), torch.nan_to_num(ref_g)))
+        gather_how += f"; equals NCCL gather: {same}"
+        sync_all()
+        peer.close()
     # kernel-only average launch duration (same stream, no gather) for the roofline
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(dev)
@@ -399,7 +428,7 @@ def main():
         "config": {"workload": WORKLOAD, "frame": [H, W], "pairs_per_gpu": N_PAIRS, "window": list(WS), "overlap": list(OV),
                    "input_dtype": "uint8", "windows_per_step": nwin_rank * world,
                    "l2": f"inputs {frames.numel() / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)",
-                   "parallelism": f"frame-pair shard x{world}"},
+                   "parallelism": f"frame-pair shard x{world}", "gather": gather_how},
         "roofline": roofline, "fp32": fp32, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                 "ms_per_step": 1e3 * e2e_s / args.steps, "api": "pyorc_b200.engine.Engine.pairs(numpy pinned)", "pcie": pcie},

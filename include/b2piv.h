@@ -188,6 +188,16 @@ int b2piv_predictor_device(b2piv_engine* e, const float* d_u1, const float* d_v1
 int b2piv_pairs_shifted_device(b2piv_engine* e, const void* d_frames, long long frame_stride_bytes, int pitch_bytes, int n_frames,
                                const short* d_shift, float* d_u, float* d_v, float* d_corr_max, float* d_s2n, void* cuda_stream);
 
+/* ---- Fused result gather over peer memory (multi-GPU) -------------------------------------------------------
+ * pyorc processes chunks sequentially in one process (pyorc/velocimetry/ffpiv.py:399-440); sharded over the GPUs of a box,
+ * every rank needs the [time] axis back together.  After this call b2piv_pairs_device stores every window's four results
+ * not only into the caller's arrays but straight into each peer's gather buffer - float32 [4][pairs_total][n_rows * n_cols],
+ * peer-mapped device memory (e.g. torch symmetric memory over NVLink) - at this rank's `pair_offset`: the all-gather is done
+ * by P2P stores in the kernel epilogue (16 B per window and peer), no collective follows; the caller only needs a cross-rank
+ * barrier before reading.  n_peers = 0 switches back to local-only results; re-planning keeps the setting, so set it after
+ * b2piv_plan. */
+int b2piv_set_peer_outputs(b2piv_engine* e, int n_peers, void* const* peer_bases, long long pairs_total, long long pair_offset);
+
 /* Page-locked host memory so H2D copies run at full PCIe rate without staging. */
 void* b2piv_host_alloc(size_t bytes);
 void b2piv_host_free(void* p);

@@ -674,6 +674,7 @@ struct b2piv_engine {
     int* d_proj_off = nullptr; size_t cap_proj_off = 0;
     int* d_proj_src = nullptr; size_t cap_proj_src = 0;
     int proj_h = 0, proj_w = 0, proj_out_h = 0, proj_out_w = 0; long long proj_samples = 0;
+    PeerOut peer = {};                                       // fused gather over peer memory (b2piv_set_peer_outputs)
     double* d_mp_ws = nullptr; size_t cap_mp_ws = 0;        // two-pass scheme: validated pass-1 fields
     float* d_mask_ws = nullptr; size_t cap_mask_ws = 0;     // mask stack: time statistics / window_replace ping-pong
     float* d_ens_sum = nullptr; float* d_ens_cnt = nullptr; size_t cap_ens = 0, cap_ens_windows = 0; bool ens_open = false;
@@ -858,7 +859,7 @@ static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st, const
     p.frames = (const unsigned char*)gp.frames; p.frame_stride = gp.frame_stride; p.pitch = gp.pitch;
     p.n_rows = gp.n_rows; p.n_cols = gp.n_cols; p.sy = gp.sy; p.sx = gp.sx; p.n_pairs = gp.n_pairs;
     p.clip_norm = gp.clip_norm; p.border_nan = gp.border_nan; p.gauss_eps = gp.gauss_eps; p.keep = gp.keep;
-    p.u = gp.u; p.v = gp.v; p.cmax = gp.cmax; p.s2n = gp.s2n; p.planes = gp.planes;
+    p.u = gp.u; p.v = gp.v; p.cmax = gp.cmax; p.s2n = gp.s2n; p.planes = gp.planes; p.peer = gp.peer;
     const size_t smem = sizeof(RSmem<R>) * G + 1024;
     if (ENS) { p.corr_min = ep->corr_min; p.s2n_min = ep->s2n_min; p.ens_sum = ep->plane_sum; p.ens_count = ep->count; }
     p.ny = PAD ? e->wy : W; p.nx = PAD ? e->wx : W;
@@ -932,7 +933,7 @@ static int launch_rows_shift(b2piv_engine* e, const Params& gp, cudaStream_t st)
     p.frames = (const unsigned char*)gp.frames; p.frame_stride = gp.frame_stride; p.pitch = gp.pitch;
     p.n_rows = gp.n_rows; p.n_cols = gp.n_cols; p.sy = gp.sy; p.sx = gp.sx; p.n_pairs = gp.n_pairs;
     p.clip_norm = gp.clip_norm; p.border_nan = gp.border_nan; p.gauss_eps = gp.gauss_eps; p.keep = gp.keep;
-    p.u = gp.u; p.v = gp.v; p.cmax = gp.cmax; p.s2n = gp.s2n; p.planes = gp.planes; p.shift = gp.shift;
+    p.u = gp.u; p.v = gp.v; p.cmax = gp.cmax; p.s2n = gp.s2n; p.planes = gp.planes; p.peer = gp.peer; p.shift = gp.shift;
     p.ny = p.nx = R::W;
     const size_t smem = sizeof(RShiftSmem<R>) * G + 1024;
     auto kern = piv_rows_shift_kernel<R, G>;
@@ -984,7 +985,7 @@ static int launch_rows128(b2piv_engine* e, const Params& gp, cudaStream_t st) {
     p.frames = (const unsigned char*)gp.frames; p.frame_stride = gp.frame_stride; p.pitch = gp.pitch;
     p.n_rows = gp.n_rows; p.n_cols = gp.n_cols; p.sy = gp.sy; p.sx = gp.sx; p.n_pairs = gp.n_pairs;
     p.clip_norm = gp.clip_norm; p.border_nan = gp.border_nan; p.gauss_eps = gp.gauss_eps; p.keep = gp.keep;
-    p.u = gp.u; p.v = gp.v; p.cmax = gp.cmax; p.s2n = gp.s2n; p.planes = gp.planes;
+    p.u = gp.u; p.v = gp.v; p.cmax = gp.cmax; p.s2n = gp.s2n; p.planes = gp.planes; p.peer = gp.peer;
     p.ny = p.nx = 128;
     const size_t smem = sizeof(R128Smem) + 1024;
     CK(cudaFuncSetAttribute(piv_rows128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1287,7 +1288,31 @@ int b2piv_pairs_device(b2piv_engine* e, const void* d_frames, long long frame_st
         p.keep = e->d_keep;
     }
     p.u = d_u; p.v = d_v; p.cmax = d_corr_max; p.s2n = d_s2n;
+    if (e->peer.n) {
+        if (e->peer.field % ((long long)e->n_rows * e->n_cols) != 0 ||
+            e->peer.pair0 + (n_frames - 1) > e->peer.field / ((long long)e->n_rows * e->n_cols))
+            return fail(e, B2PIV_ERR_ARG, "peer gather buffers do not hold this call's pair range (b2piv_set_peer_outputs)");
+        p.peer = e->peer;
+    }
     return dispatch_pairs(e, p, st);
+}
+
+int b2piv_set_peer_outputs(b2piv_engine* e, int n_peers, void* const* peer_bases, long long pairs_total, long long pair_offset) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (n_peers == 0) { e->peer = PeerOut{}; return B2PIV_OK; }
+    if (!e->planned) return fail(e, B2PIV_ERR_STATE, "b2piv_plan has not been called");
+    if (n_peers < 0 || n_peers > 8 || !peer_bases) return fail(e, B2PIV_ERR_ARG, "1..8 peer buffers");
+    if (pairs_total < 1 || pair_offset < 0 || pair_offset >= pairs_total) return fail(e, B2PIV_ERR_ARG, "bad pair range");
+    PeerOut po = {};
+    po.n = n_peers;
+    for (int r = 0; r < n_peers; ++r) {
+        if (!peer_bases[r]) return fail(e, B2PIV_ERR_ARG, "NULL peer buffer");
+        po.base[r] = (float*)peer_bases[r];
+    }
+    po.field = pairs_total * (long long)e->n_rows * e->n_cols;
+    po.pair0 = pair_offset;
+    e->peer = po;
+    return B2PIV_OK;
 }
 
 }  // extern "C"

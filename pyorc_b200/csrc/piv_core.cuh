@@ -129,6 +129,23 @@ struct Smem {
     float stat[2][4];                  // per window: corr_max, sum, peak index (as float bits), unused
 };
 
+// Fused result gather over peer memory (multi-GPU): when n > 0 every window's four results are ALSO stored into each peer's
+// gather buffer [4][pairs_total][n_windows] (peer-mapped device memory, e.g. torch symmetric memory over NVLink) at this
+// rank's pair offset - the all-gather of pyorc_b200.parallel happens as P2P stores from the kernel epilogue.
+struct PeerOut {
+    int n;
+    float* base[8];
+    long long field;     // pairs_total * n_windows: distance between the four fields of a gather buffer
+    long long pair0;     // global index of this launch's first pair
+};
+B2_HD void peer_store(const PeerOut& po, long long local_pair, long long n_windows, int widx, float uu, float vv, float oc, float os) {
+    const long long go = (po.pair0 + local_pair) * n_windows + widx;
+    for (int r = 0; r < po.n; ++r) {
+        float* b = po.base[r];
+        b[go] = uu; b[go + po.field] = vv; b[go + 2 * po.field] = oc; b[go + 3 * po.field] = os;
+    }
+}
+
 // Per-launch parameters (plain data, passed by value).
 struct Params {
     const void* frames;       // [n_frames][H][pitch] u8 or f32
@@ -148,6 +165,7 @@ struct Params {
     const unsigned char* keep;  // optional [n_windows] keep mask (signal_threshold); nullptr = keep all
     float* u; float* v; float* cmax; float* s2n;   // [n_pairs][n_rows*n_cols]
     float* planes;            // optional debug dump [n_pairs][n_windows][WY][WX] (fftshifted, clipped), or nullptr
+    PeerOut peer;             // optional fused gather (n = 0: off)
 };
 
 template <class C> B2_HD int win_ny(const Params& p) { return C::PADDED ? p.ny : C::WY; }
@@ -553,6 +571,7 @@ B2_HD void phase_peak(Smem<C>& s, int tid, const Params& p, const Item& it) {
     const long long o = (long long)it.pair * p.n_rows * p.n_cols + it.w[w];
     if (p.shift) { vv += (float)p.shift[2 * o]; uu += (float)p.shift[2 * o + 1]; }
     p.u[o] = uu; p.v[o] = vv; p.cmax[o] = o_c; p.s2n[o] = o_s;
+    if (p.peer.n) peer_store(p.peer, it.pair, (long long)p.n_rows * p.n_cols, it.w[w], uu, vv, o_c, o_s);
 }
 
 }  // namespace b2piv

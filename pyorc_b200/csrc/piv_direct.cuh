@@ -165,6 +165,7 @@ B2_HD void direct_peak(DView& s, int tid, const Params& p, int pair, int widx) {
     if (p.keep && !p.keep[widx]) { uu = vv = oc = os = nanf(""); }
     const long long o = (long long)pair * p.n_rows * p.n_cols + widx;
     p.u[o] = uu; p.v[o] = vv; p.cmax[o] = oc; p.s2n[o] = os;
+    if (p.peer.n) peer_store(p.peer, pair, (long long)p.n_rows * p.n_cols, widx, uu, vv, oc, os);
 }
 
 }  // namespace b2piv

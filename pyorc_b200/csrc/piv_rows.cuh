@@ -129,6 +129,7 @@ struct RParams {
     const unsigned char* keep;
     const short* shift;            // displaced second pass: [n_pairs][n_windows][2] = (dy, dx) of frame k+1's window, added to (v, u)
     float *u, *v, *cmax, *s2n;
+    PeerOut peer;                  // optional fused gather over peer memory (piv_core.cuh)
     float* planes;
     // ensemble mode (piv_rows_kernel<..., ENS = true>): thresholds and the HBM accumulators [n_windows][W][W] / [n_windows]
     float corr_min, s2n_min;
@@ -833,6 +834,7 @@ B2_HD void rows_p8(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p, const RU
     const long long o = (long long)pair * p.n_rows * p.n_cols + widx;
     if (p.shift) { vv += (float)p.shift[2 * o]; uu += (float)p.shift[2 * o + 1]; }
     p.u[o] = uu; p.v[o] = vv; p.cmax[o] = oc; p.s2n[o] = os;
+    if (p.peer.n) peer_store(p.peer, pair, (long long)p.n_rows * p.n_cols, widx, uu, vv, oc, os);
 }
 
 // optional triage dump of the full planes (fftshifted, clipped) - every thread writes its row

@@ -289,6 +289,7 @@ __device__ __forceinline__ void r128_p8(R128Smem& s, RRegs<R6>& r, int tid, cons
     if (p.keep && !p.keep[widx]) { uu = vv = oc = os = nanf(""); }
     const long long o = (long long)pair * p.n_rows * p.n_cols + widx;
     p.u[o] = uu; p.v[o] = vv; p.cmax[o] = oc; p.s2n[o] = os;
+    if (p.peer.n) peer_store(p.peer, pair, (long long)p.n_rows * p.n_cols, widx, uu, vv, oc, os);
 }
 
 // optional triage dump of the full planes (fftshifted, clipped): every thread writes its 64 elements of one reference row

@@ -59,6 +59,7 @@ ABI_SYMBOLS = (
     "b2piv_rotate_uv",
     "b2piv_predictor_device",
     "b2piv_pairs_shifted_device",
+    "b2piv_set_peer_outputs",
     "b2piv_host_alloc",
     "b2piv_host_free",
     "b2piv_last_kernel_ms",
@@ -119,6 +120,7 @@ def load_library(path: Optional[str] = None):
     lib.b2piv_rotate_uv.argtypes = [vp, vp, vp, cll, cd, vp, vp, vp]
     lib.b2piv_predictor_device.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, vp]
     lib.b2piv_pairs_shifted_device.argtypes = [vp, vp, cll, ci, ci, vp, vp, vp, vp, vp, vp]
+    lib.b2piv_set_peer_outputs.argtypes = [vp, ci, vpp, cll, cll]
     lib.b2piv_host_alloc.argtypes = [ctypes.c_size_t]
     lib.b2piv_host_alloc.restype = vp
     lib.b2piv_host_free.argtypes = [vp]
@@ -352,6 +354,16 @@ class Engine:
             "b2piv_pairs_host",
         )
         return tuple(outs)
+
+    # ---- fused multi-GPU gather ---------------------------------------------------------------------------------
+    def set_peer_outputs(self, peer_ptrs, pairs_total: int, pair_offset: int):
+        """Make :meth:`pairs` (device tensors) also store its results straight into every peer's gather buffer
+        ``[4, pairs_total, n_rows, n_cols]`` float32 (raw device pointers, e.g. ``symm_mem_handle.buffer_ptrs``) at this
+        rank's ``pair_offset``; ``peer_ptrs=None`` or ``[]`` switches back.  Call after :meth:`plan`."""
+        ptrs = list(peer_ptrs or [])
+        arr = (ctypes.c_void_p * max(len(ptrs), 1))(*[int(p) for p in ptrs])
+        self._check(self._lib.b2piv_set_peer_outputs(self._h, len(ptrs), arr, int(pairs_total), int(pair_offset)),
+                    "b2piv_set_peer_outputs")
 
     # ---- two-pass (BASELINE configs[2]) -----------------------------------------------------------------------
     def predictor(self, u1, v1, dim_size, coarse, fine, dtype=np.uint8):

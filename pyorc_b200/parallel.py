@@ -76,6 +76,45 @@ def gather_fields(local, n_pairs_total: int, table: np.ndarray, group=None):
     return out
 
 
+class PeerGather:
+    """The result gather fused into the PIV kernel: every rank's kernel stores its 16 B / window straight into the gather
+    buffer of EVERY rank (torch symmetric memory = peer-mapped HBM over NVLink / NVSwitch), so no collective follows the
+    compute - only a cross-rank barrier before the buffer is read.
+
+        pg = PeerGather(engine, n_pairs_total, table)       # after engine.plan(...); collective (rendezvous)
+        engine.pairs(d_frames_of_this_rank, ws, ov)          # results land in pg.out on every rank
+        pg.wait()                                            # device-side barrier on the current stream
+        fields = pg.out                                      # [4, n_pairs_total, rows, cols]
+
+    The NCCL path (:func:`gather_fields`) remains for ragged use and for backends without peer access (gloo tests)."""
+
+    def __init__(self, engine, n_pairs_total: int, table: np.ndarray, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        if engine._plan is None:
+            raise RuntimeError("plan the engine before creating a PeerGather")
+        rows, cols = engine._plan[1]
+        group = group if group is not None else dist.group.WORLD
+        rank = dist.get_rank(group)
+        self.engine = engine
+        self.out = symm_mem.empty((4, int(n_pairs_total), rows, cols), dtype=torch.float32, device=torch.device("cuda", engine.device))
+        self.handle = symm_mem.rendezvous(self.out, group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(ptrs) > 8:
+            raise NotImplementedError("at most 8 peers (one box)")
+        engine.set_peer_outputs(ptrs, int(n_pairs_total), int(table[rank, 0]))
+
+    def wait(self):
+        """All ranks' kernels (enqueued before this call on the current stream) have delivered their results everywhere."""
+        self.handle.barrier()
+        return self.out
+
+    def close(self):
+        self.engine.set_peer_outputs(None, 1, 0)
+
+
 def piv_pairs_sharded(frames_for_rank: Callable[[int, int], object], n_pairs_total: int,
                       compute: Callable[[object], Tuple], group=None, device=None):
     """Distributed per-time-step PIV.

@@ -457,3 +457,50 @@ def test_rows_kernel_float32_frames(engine, ws, ov, shape, run_len):
     imgs[1:] -= 0.25 * imgs[:-1]
     compare(engine, imgs, ws, ov, 0, variant=2, run_len=run_len)
     engine.set_option("kernel_variant", 0.0)
+
+
+def test_fused_peer_gather_two_engines_one_device():
+    """b2piv_set_peer_outputs: two engines (stand-ins for two ranks, both on cuda:0) each process half of the frame pairs and
+    store their results straight into BOTH gather buffers; each buffer ends up with the whole time axis."""
+    import torch
+
+    from pyorc_b200.engine import Engine
+
+    imgs = synth.particle_frames(7, 200, 304, dtype=np.uint8)
+    d = torch.from_numpy(imgs).cuda()
+    ws, ov = (64, 64), (32, 32)
+    with Engine(0) as e0, Engine(0) as e1, Engine(0) as ref:
+        for e in (e0, e1, ref):
+            e.set_option("clip_normalized", 0.0)
+        whole = torch.stack(ref.pairs(d, ws, ov))
+        nr, nc = e0.plan((200, 304), ws, ov, np.uint8)
+        e1.plan((200, 304), ws, ov, np.uint8)
+        bufs = [torch.full((4, 6, nr, nc), -7.0, device="cuda") for _ in range(2)]
+        ptrs = [b.data_ptr() for b in bufs]
+        e0.set_peer_outputs(ptrs, 6, 0)
+        e1.set_peer_outputs(ptrs, 6, 4)
+        a = e0.pairs(d[:5], ws, ov)            # pairs 0..3
+        b = e1.pairs(d[4:], ws, ov)            # pairs 4..5
+        torch.cuda.synchronize()
+        for buf in bufs:
+            assert torch.equal(torch.nan_to_num(buf), torch.nan_to_num(whole))
+        assert torch.equal(torch.nan_to_num(torch.stack(a)), torch.nan_to_num(whole[:, :4]))     # local results still written
+        with pytest.raises(ValueError):
+            e1.pairs(d[3:], ws, ov)            # 3 pairs from offset 4 do not fit 6
+        e0.set_peer_outputs(None, 1, 0)
+        bufs[0].fill_(-7.0)
+        e0.pairs(d[:5], ws, ov)
+        torch.cuda.synchronize()
+        assert float(bufs[0].max()) == -7.0    # switched off
+        # the 128x128 polyphase kernel and the shared-memory kernel have the same epilogue hook
+        for wsz, ovl, variant in (((128, 128), (64, 64), 0), ((64, 64), (32, 32), 1)):
+            e0.set_option("kernel_variant", float(variant))
+            ref.set_option("kernel_variant", float(variant))
+            w2 = torch.stack(ref.pairs(d, wsz, ovl))
+            r2, c2 = e0.plan((200, 304), wsz, ovl, np.uint8)
+            buf = torch.full((4, 8, r2, c2), -7.0, device="cuda")
+            e0.set_peer_outputs([buf.data_ptr()], 8, 2)
+            e0.pairs(d, wsz, ovl)
+            torch.cuda.synchronize()
+            assert torch.equal(torch.nan_to_num(buf[:, 2:]), torch.nan_to_num(w2)) and float(buf[:, :2].max()) == -7.0
+            e0.set_peer_outputs(None, 1, 0)

@@ -171,7 +171,7 @@ def run_reference(args, rank, world):
                          "sample": f"{sample_pairs} of the 100 frame pairs per step; restated ffpiv CPU path (upstream ffpiv/rocket-fft unavailable offline), float64 pocketfft, one thread per frame pair on {cores} cores"},
         "e2e": {"value": val, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def other_configs(eng, dev):
@@ -223,7 +223,30 @@ def other_configs(eng, dev):
     return rows
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner / NCCL_DEBUG output) are sent to
+    stderr by pointing fd 1 at fd 2 for the whole run; emit() writes the line to the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -255,8 +278,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL writes its version banner / debug lines to stdout by default: keep stdout for the ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     eng = Engine(local_rank)
     n_frames = N_PAIRS + 1
@@ -434,7 +455,7 @@ def main():
                 "ms_per_step": 1e3 * e2e_s / args.steps, "api": "pyorc_b200.engine.Engine.pairs(numpy pinned)", "pcie": pcie},
         "gpu_launches": int(launches), "clocks": clocks, "rmse_vs_oracle": rmse, "other_configs": other,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

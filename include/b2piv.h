@@ -194,8 +194,8 @@ int b2piv_pairs_shifted_device(b2piv_engine* e, const void* d_frames, long long 
  * not only into the caller's arrays but straight into each peer's gather buffer - float32 [4][pairs_total][n_rows * n_cols],
  * peer-mapped device memory (e.g. torch symmetric memory over NVLink) - at this rank's `pair_offset`: the all-gather is done
  * by P2P stores in the kernel epilogue (16 B per window and peer), no collective follows; the caller only needs a cross-rank
- * barrier before reading.  n_peers = 0 switches back to local-only results; re-planning keeps the setting, so set it after
- * b2piv_plan. */
+ * barrier before reading.  n_peers = 0 switches back to local-only results; so does a b2piv_plan that changes the field shape
+ * (set it after b2piv_plan). */
 int b2piv_set_peer_outputs(b2piv_engine* e, int n_peers, void* const* peer_bases, long long pairs_total, long long pair_offset);
 
 /* Page-locked host memory so H2D copies run at full PCIe rate without staging. */

@@ -1248,8 +1248,10 @@ int b2piv_plan(b2piv_engine* e, int height, int width, int win_y, int win_x, int
                                                   " not supported (any size 4..64 per axis, or 64x128 / 128x64 / 128x128)");
     CK(cudaSetDevice(e->device));
     e->H = height; e->W = width; e->wy = win_y; e->wx = win_x; e->oy = ovl_y; e->ox = ovl_x; e->dtype = dtype;
+    const int old_rows = e->n_rows, old_cols = e->n_cols;
     e->n_rows = (height - win_y) / (win_y - ovl_y) + 1;
     e->n_cols = (width - win_x) / (win_x - ovl_x) + 1;
+    if (e->n_rows != old_rows || e->n_cols != old_cols) e->peer = PeerOut{};   // gather buffers were sized for the old field
     // twiddle tables exp(-2 pi i j / N) for the FFT plane (= the window, or its padded power-of-two plane), in double
     int py = win_y, px = win_x;
     plane_shape(e, &py, &px);

@@ -34,7 +34,8 @@ constexpr int R128_BATCH = 11;     // ky rows per exchange batch (3 batches cove
 constexpr int R128_NPX = 128 * 128;
 // tile: window w rows [32 j, 32 j + 32) -> sub[j].tile() + w * 4096 ([32 rows][128 B], SWIZZLE_128B)
 static_assert(sizeof(float2) * R6::NWARP * R6::XBLK >= 2 * 4096, "tile quarter must fit in a sub-group's transpose blocks");
-static_assert(sizeof(float2) * R6::XBLK >= sizeof(float2) * 2 * R128_BATCH * 32, "exchange batch must fit in one warp's block");
+static_assert(sizeof(float2) * R6::XBLK >= sizeof(float4) * R128_BATCH * 32, "exchange batch must fit in one warp's block");
+static_assert(sizeof(float2) * 2 * R6::HS * R6::NT == sizeof(float4) * 33 * 64, "parked spectra are re-viewed as [33][64] float4");
 
 #ifdef __CUDACC__
 // P1: row 2 sigma(t) + p1 of both windows from the tile, bytes of column parity p2 packed (64 bytes per window), exact
@@ -106,10 +107,15 @@ __device__ __forceinline__ float2 cfma(float2 m, float2 b, float2 a) {   // a + 
     return make_float2(fmaf(m.x, b.x, fmaf(-m.y, b.y, a.x)), fmaf(m.x, b.y, fmaf(m.y, b.x, a.y)));
 }
 
-// exchange slot of (window w, batch slot sl) for lane `lane` of warp wq of sub-group g: inside that WARP's own transpose block,
-// so a warp only ever overwrites memory it has finished reading itself
-__device__ __forceinline__ float2* r128_xch(R128Smem& s, int g, int wq, int w, int sl, int lane) {
-    return &s.sub[g].X[wq][(w * R128_BATCH + sl) * 32 + lane];
+// Both windows of a spectrum bin travel together as one float4 (A0.x, A0.y, A1.x, A1.y): 16-byte shared-memory accesses halve
+// the LSU instruction count of this phase (it is `mio_throttle` bound).  The parked spectra use the memory of
+// RSmem::park ([2][33][64] float2 = [33][64] float4); the exchange slot of batch slot sl for lane `lane` of warp wq of
+// sub-group g lies inside that WARP's own transpose block, so a warp only ever overwrites memory it has finished reading.
+__device__ __forceinline__ float4* r128_xch(R128Smem& s, int g, int wq, int sl, int lane) {
+    return reinterpret_cast<float4*>(&s.sub[g].X[wq][0]) + sl * 32 + lane;
+}
+__device__ __forceinline__ float4* r128_park(R128Smem& s, int g, int ky, int t) {
+    return reinterpret_cast<float4*>(&s.sub[g].park[0][0][0]) + ky * 64 + t;
 }
 
 // exp(+2 pi i ky / 64), ky = 0 .. 32: phase of a carry along y (indexed at run time by the rolled batch loop below)
@@ -135,10 +141,10 @@ __device__ __forceinline__ void r128_cross(R128Smem& s, RRegs<R6>& r, int sub, i
     sincospif((float)c * (1.0f / 32.0f), &sn, &cs);
     const float2 m2 = q2 ? make_float2(cs, sn) : make_float2(1.f, 0.f);
     // new spectra of component p xor q come from sub-group p xor q's exchange block
-    const float2* xb[4];
+    const float4* xb[4];
 #pragma unroll
-    for (int p = 0; p < 4; ++p) xb[p] = r128_xch(s, p ^ sub, wq, 0, 0, lane);
-    float2* own = r128_xch(s, sub, wq, 0, 0, lane);
+    for (int p = 0; p < 4; ++p) xb[p] = r128_xch(s, p ^ sub, wq, 0, lane);
+    float4* own = r128_xch(s, sub, wq, 0, lane);
     float2 lo[33], hi[33];
 #pragma unroll
     for (int k = 0; k <= 32; ++k) { lo[k] = r.v[k]; hi[k] = r.v[(64 - k) % 64]; }
@@ -150,8 +156,7 @@ __device__ __forceinline__ void r128_cross(R128Smem& s, RRegs<R6>& r, int sub, i
             const float2 pz = shfl2(hi[sl], pl);
             float2 a0, a1;
             separate(lo[sl], pz, r.half_alpha_new[0], r.half_alpha_new[1], a0, a1);
-            own[(0 * B + sl) * 32] = a0;
-            own[(1 * B + sl) * 32] = a1;
+            own[sl * 32] = make_float4(a0.x, a0.y, a1.x, a1.y);
         }
         __syncthreads();
         // -- cross spectra of this batch
@@ -160,16 +165,20 @@ __device__ __forceinline__ void r128_cross(R128Smem& s, RRegs<R6>& r, int sub, i
             const int ky = b0 + sl;
             const float2 tw = R128_TWY[ky];
             const float2 m1 = q1 ? tw : make_float2(1.f, 0.f);
+            float2 term[2][4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const float4 pk = *r128_park(s, p, ky, t);
+                const float4 nw = xb[p][sl * 32];
+                term[0][p] = cmulc(make_float2(pk.x, pk.y), make_float2(nw.x, nw.y));
+                term[1][p] = cmulc(make_float2(pk.z, pk.w), make_float2(nw.z, nw.w));
+            }
             float2 R[2];
 #pragma unroll
             for (int w = 0; w < 2; ++w) {
-                float2 term[4];
-#pragma unroll
-                for (int p = 0; p < 4; ++p)
-                    term[p] = cmulc(s.sub[p].park[w][ky][t], xb[p][(w * B + sl) * 32]);
                 // p = (p1, p2) = (p >> 1, p & 1): R = t00 + m2 t01 + m1 (t10 + m2 t11)
-                const float2 l = cfma(m2, term[1], term[0]);
-                const float2 h = cfma(m2, term[3], term[2]);
+                const float2 l = cfma(m2, term[w][1], term[w][0]);
+                const float2 h = cfma(m2, term[w][3], term[w][2]);
                 R[w] = cfma(m1, h, l);
             }
             lo[sl] = make_float2(R[0].x - R[1].y, -(R[0].y + R[1].x));            // conj(G), G = R0 + i R1
@@ -179,11 +188,8 @@ __device__ __forceinline__ void r128_cross(R128Smem& s, RRegs<R6>& r, int sub, i
         // -- the new spectra become the parked ones (scaled once, here)
 #pragma unroll
         for (int sl = 0; sl < B; ++sl) {
-#pragma unroll
-            for (int w = 0; w < 2; ++w) {
-                const float2 a = own[(w * B + sl) * 32];
-                s.sub[sub].park[w][b0 + sl][t] = make_float2(a.x * SCALE, a.y * SCALE);
-            }
+            const float4 a = own[sl * 32];
+            *r128_park(s, sub, b0 + sl, t) = make_float4(a.x * SCALE, a.y * SCALE, a.z * SCALE, a.w * SCALE);
         }
         // -- rotate both register arrays by one batch
         float2 tl[B], th[B];

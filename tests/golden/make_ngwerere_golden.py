@@ -24,6 +24,7 @@ import numpy as np
 REF = "/root/reference"
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ngwerere_proj.npz")
 OUT_MAPS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ngwerere_maps.npz")
+OUT_TAIL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ngwerere_gray_tail.npz")
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -232,6 +233,17 @@ def main():
                "examples/ngwerere frame 0; generated by tests/golden/make_ngwerere_golden.py",
     )
     print("wrote", OUT_MAPS, os.path.getsize(OUT_MAPS), "bytes; nearest", idx_img.size, "samples", src_idx.size, "groups", uidx.size)
+    # ---- third fixture: the bottom-right corner of the raw grayscale frames (32 rows x 64 columns of each of the three
+    # frames) - enough context for the pins of pyorc's filter tests on `frames_grayscale` (tests/test_frames.py:54-93:
+    # the last four values of smooth(); time_diff / range are pinned on the same corner)
+    np.savez_compressed(
+        OUT_TAIL, gray_tail=imgs[:, -32:, -64:], frame_shape=np.array(imgs.shape[1:]),
+        pinned_smooth_last4=np.array([158.125, 153.5, 151.375, 151.0]),
+        pinned_edge_detect_proj_last4=np.array([-5.6953125, 4.0703125, 8.0625, 4.3125]),
+        source="pyorc @ be7d7c8 tests/test_frames.py:86-103 (test_smooth on frames_grayscale, test_edge_detect on frames_proj); "
+               "generated by tests/golden/make_ngwerere_golden.py",
+    )
+    print("wrote", OUT_TAIL, os.path.getsize(OUT_TAIL), "bytes")
 
 
 if __name__ == "__main__":

@@ -272,3 +272,69 @@ def test_gpu_masks_on_device_resident_results_config2_size():
     assert np.array_equal(d[0].cpu().numpy(), vx, equal_nan=True)       # inputs untouched
     q = M.encode_int16(out[0])
     same(q.cpu().numpy(), MO.encode_int16(want[0]))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# GPU: pyorc's own mask tests (tests/test_mask.py of the reference: they only check that every method RUNS, raises and warns
+# as documented) repeated call for call on the `piv` fixture's counterpart - get_piv() of the projected Ngwerere frames
+# (tests/conftest.py:390-398; window_size 25 from the camera configuration) - with every returned mask also checked against
+# the oracle.
+# ---------------------------------------------------------------------------------------------------------------------------
+def _ngwerere_piv(ensemble_corr=False):
+    import os
+
+    from pyorc_b200 import _xr
+    from pyorc_b200 import frames as b2frames
+
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ngwerere_proj.npz"))
+    fr, t, res = d["frames"], d["time_s"], float(d["resolution"])
+    H, W = fr.shape[1:]
+    da = _xr.DataArray(fr, ("time", "y", "x"), {"time": t, "y": np.flipud(np.linspace(res / 2, res * (H - 0.5), H)),
+                                                "x": np.linspace(res / 2, res * (W - 0.5), W)})
+    return b2frames.get_piv(da, window_size=25, engine="b200", resolution=res, ensemble_corr=ensemble_corr)
+
+
+def _vals(piv):
+    return [np.asarray(piv[k].values, np.float32) for k in ("v_x", "v_y", "corr", "s2n")]
+
+
+@gpu
+def test_reference_mask_suite_runs_like_pyorc():
+    from pyorc_b200.mask import Masks
+
+    piv = _ngwerere_piv()
+    vx, vy, c, s = _vals(piv)
+    assert vx.ndim == 3 and vx.shape[0] == 2
+    # test_mask_minmax / test_mask: masks with and without time, combined
+    m1 = Masks(piv).minmax(inplace=False)
+    same(m1.values, MO.minmax(vx, vy))
+    piv_mean = piv.mean(dim="time", keep_attrs=True)
+    m2 = Masks(piv_mean).minmax(inplace=False)
+    assert m2.dims == ("y", "x")
+    out = Masks(piv)([m1, m2])
+    want = MO.apply_masks([vx, vy, c, s], [m1.values, m2.values])
+    assert all(np.array_equal(out[k].values, w, equal_nan=True) for k, w in zip(("v_x", "v_y", "corr", "s2n"), want))
+    m3 = Masks(piv).angle()
+    m4 = Masks(piv_mean).window_mean()
+    Masks(piv)([m3, m4])
+    # every method "runs" with the reference tests' arguments and equals the oracle
+    same(Masks(piv).corr(tolerance=0.3).values, MO.corr(c, 0.3))
+    same(Masks(piv).count().values, MO.count(vx))
+    same(Masks(piv).rolling(tolerance=0.4).values, MO.rolling(vx, vy, tolerance=0.4))
+    same(Masks(piv).outliers(mode="or").values, MO.outliers(vx, vy, mode="or"))
+    same(Masks(piv).variance(tolerance=1.0, mode="or").values, MO.variance(vx, vy, 1.0, "or"))
+    same(Masks(piv).window_mean().values, MO.window_mean(vx, vy))
+    # test_mask_window_nan: first a filter that creates missings, in place, then the window filter in place
+    p2 = _ngwerere_piv()
+    Masks(p2).minmax(s_max=0.6, inplace=True)
+    vx2 = np.asarray(p2["v_x"].values, np.float32)
+    assert np.isnan(vx2).sum() > np.isnan(vx).sum()
+    mw = Masks(p2).window_nan(inplace=True)
+    same(mw.values, MO.window_nan(vx2))
+    assert np.array_equal(np.isnan(p2["v_x"].values), ~mw.values | np.isnan(vx2))
+    # test_error_no_time / test_error_single_time_step
+    with pytest.raises(AssertionError, match='This mask requires dimension "time"'):
+        Masks(piv_mean).variance()
+    with pytest.warns(UserWarning, match="This mask requires multiple timesteps"):
+        one = Masks(_ngwerere_piv(ensemble_corr=True)).count(inplace=True, tolerance=0.3)      # test_mask_count_ens_corr
+    assert bool(one.values.all())

@@ -24,6 +24,36 @@ def test_oracle_gaussian_kernel_rule_matches_opencv():
         assert np.abs(cv2.getGaussianKernel(k, 0, cv2.CV_32F).ravel() - g / g.sum()).max() < 1e-7
 
 
+def _golden(name):
+    import os
+
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+
+
+def test_oracle_pinned_on_the_references_filter_goldens():
+    """pyorc pins two filter results: test_smooth (tests/test_frames.py:86-93, last four values of smooth() on the raw
+    grayscale Ngwerere frames) and test_edge_detect (:96-103, last four values of edge_detect() on the projected frames,
+    atol 0 on x86).  The fixtures hold exactly those inputs (made by the reference's own decode / projection code,
+    tests/golden/make_ngwerere_golden.py); the oracle reproduces both pins to the last digit."""
+    tail = _golden("ngwerere_gray_tail.npz")
+    assert np.array_equal(P.smooth(tail["gray_tail"]).ravel()[-4:], tail["pinned_smooth_last4"].astype(np.float32))
+    proj = _golden("ngwerere_proj.npz")["frames"]
+    assert np.array_equal(P.edge_detect(proj).ravel()[-4:], tail["pinned_edge_detect_proj_last4"].astype(np.float32))
+
+
+@pytest.mark.gpu
+def test_gpu_filters_reproduce_the_references_pins():
+    from pyorc_b200 import preprocess as G
+
+    tail = _golden("ngwerere_gray_tail.npz")
+    got = G.smooth(tail["gray_tail"])
+    assert got.dtype == np.float32 and np.abs(got.ravel()[-4:] - tail["pinned_smooth_last4"]).max() <= 1e-4
+    proj = _golden("ngwerere_proj.npz")["frames"]
+    got = G.edge_detect(proj)
+    assert got.shape == proj.shape and np.abs(got.ravel()[-4:] - tail["pinned_edge_detect_proj_last4"]).max() <= 1e-4
+    assert np.abs(got - P.edge_detect(proj)).max() <= 1e-4
+
+
 def test_oracle_normalize_properties():
     fr = synth.particle_frames(30, 40, 50, dtype=np.uint8)
     out = P.normalize(fr, samples=15)

@@ -241,6 +241,36 @@ __device__ __forceinline__ void window_sum(const float* __restrict__ f, const Wi
     }
 }
 
+// Compile-time neighbourhood (the reference's defaults wdw = 1 and wdw = 2): fully unrolled, 32-bit offsets, predicated loads.
+// ncu on the run-time version: 293 instructions per warp and output, 85 % issue-bound - the loop machinery, not memory.
+template <int WX0, int WX1, int WY0, int WY1>
+__device__ __forceinline__ void window_sum_ct(const float* __restrict__ p, int ny, int nx, int y, int x, float& sum, int& cnt) {
+    sum = 0.f;
+    cnt = 0;
+#pragma unroll
+    for (int xs = WX0; xs <= WX1; ++xs) {
+#pragma unroll
+        for (int ys = WY0; ys < WY1; ++ys) {
+            const int xx = x - xs, yy = y - ys;
+            const bool in = (unsigned)xx < (unsigned)nx && (unsigned)yy < (unsigned)ny;
+            const float v = in ? p[-ys * nx - xs] : CUDART_NAN_F;
+            if (v == v) { sum = __fadd_rn(sum, v); ++cnt; }
+        }
+    }
+}
+// dispatch on the neighbourhood: 0 = run time, 1 = (-1, 1, -1, 1), 2 = (-2, 2, -2, 2)
+__device__ __forceinline__ void window_sum_any(int kind, const float* __restrict__ f, const WindowArgs& w, long long base, int y, int x,
+                                               float& sum, int& cnt) {
+    if (kind == 1) window_sum_ct<-1, 1, -1, 1>(f + base + y * w.nx + x, w.ny, w.nx, y, x, sum, cnt);
+    else if (kind == 2) window_sum_ct<-2, 2, -2, 2>(f + base + y * w.nx + x, w.ny, w.nx, y, x, sum, cnt);
+    else window_sum(f, w, base, y, x, sum, cnt);
+}
+__host__ __device__ inline int window_kind(const WindowArgs& w) {
+    if (w.wx0 == -1 && w.wx1 == 1 && w.wy0 == -1 && w.wy1 == 1) return 1;
+    if (w.wx0 == -2 && w.wx1 == 2 && w.wy0 == -2 && w.wy1 == 2) return 2;
+    return 0;
+}
+
 // blocks of 32 x 8 outputs, grid.z strided over time: neighbours come from L1
 #define B2_WINDOW_LOOP                                                                     \
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;         \
@@ -250,22 +280,24 @@ __device__ __forceinline__ void window_sum(const float* __restrict__ f, const Wi
 
 __global__ void __launch_bounds__(256) mask_window_nan_kernel(const float* __restrict__ vx, WindowArgs w, int min_count,
                                                               unsigned char* __restrict__ m) {
+    const int kind = window_kind(w);
     B2_WINDOW_LOOP {
         float sum;
         int cnt;
-        window_sum(vx, w, t * nxy, y, x, sum, cnt);
+        window_sum_any(kind, vx, w, t * nxy, y, x, sum, cnt);
         m[t * nxy + (long long)y * w.nx + x] = (cnt >= min_count) ? 1 : 0;
     }
 }
 
 __global__ void __launch_bounds__(256) mask_window_mean_kernel(const float* __restrict__ vx, const float* __restrict__ vy, WindowArgs w,
                                                                float tol, int mode_and, unsigned char* __restrict__ m) {
+    const int kind = window_kind(w);
     B2_WINDOW_LOOP {
         const long long i = t * nxy + (long long)y * w.nx + x;
         float sx, sy;
         int cx, cy;
-        window_sum(vx, w, t * nxy, y, x, sx, cx);
-        window_sum(vy, w, t * nxy, y, x, sy, cy);
+        window_sum_any(kind, vx, w, t * nxy, y, x, sx, cx);
+        window_sum_any(kind, vy, w, t * nxy, y, x, sy, cy);
         const float mx = __fdiv_rn(sx, (float)cx), my = __fdiv_rn(sy, (float)cy);
         const bool xc = __fdiv_rn(fabsf(__fsub_rn(vx[i], mx)), mx) < tol;
         const bool yc = __fdiv_rn(fabsf(__fsub_rn(vy[i], my)), my) < tol;
@@ -275,13 +307,14 @@ __global__ void __launch_bounds__(256) mask_window_mean_kernel(const float* __re
 
 // one iteration of window_replace for one field (out-of-place: every mean reads the field before this iteration)
 __global__ void __launch_bounds__(256) window_replace_kernel(const float* __restrict__ in, WindowArgs w, float* __restrict__ out) {
+    const int kind = window_kind(w);
     B2_WINDOW_LOOP {
         const long long i = t * nxy + (long long)y * w.nx + x;
         float v = in[i];
         if (v != v) {
             float s;
             int c;
-            window_sum(in, w, t * nxy, y, x, s, c);
+            window_sum_any(kind, in, w, t * nxy, y, x, s, c);
             v = __fdiv_rn(s, (float)c);
         }
         out[i] = v;

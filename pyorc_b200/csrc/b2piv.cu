@@ -1844,6 +1844,21 @@ static int mask_grid(const b2piv_engine* e, long long n, int block = 256) {
     e->launches += (k);                                                                 \
     return B2PIV_OK;
 
+// time statistics: segmented kernel (loads parallel in time, sums sequential) up to 1024 time steps, else one thread per location
+static void launch_time_stats(const b2piv_engine* e, const float* d_field, int n_time, long long n_xy, int* d_count, float* d_mean,
+                              float* d_std, cudaStream_t st) {
+    const long long n_blocks = (n_xy + 31) / 32;
+    if (n_time <= 1024 && n_time >= 16) {
+        constexpr int L = 32;
+        const int S = (n_time + L - 1) / L;
+        const long long cap = (long long)e->sm_count * (2048 / (32 * S));
+        const unsigned grid = (unsigned)(n_blocks < cap ? n_blocks : cap);
+        time_stats_seg_kernel<L><<<grid, dim3(32, S), 0, st>>>(d_field, n_time, n_xy, d_count, d_mean, d_std);
+    } else {
+        time_stats_kernel<<<mask_grid(e, n_xy, 64), 64, 0, st>>>(d_field, n_time, n_xy, d_count, d_mean, d_std);
+    }
+}
+
 int b2piv_mask_elementwise(b2piv_engine* e, int op, const float* d_a, const float* d_b, long long count, float p0, float p1,
                            unsigned char* d_mask, void* cuda_stream) {
     MASK_PROLOGUE(!d_a || !d_mask || (op != B2PIV_MASK_THRESHOLD && !d_b))
@@ -1861,7 +1876,7 @@ int b2piv_time_stats(b2piv_engine* e, const float* d_field, int n_time, long lon
                      void* cuda_stream) {
     MASK_PROLOGUE(!d_field)
     if (n_time < 1 || n_xy < 1) return fail(e, B2PIV_ERR_ARG, "empty field");
-    time_stats_kernel<<<mask_grid(e, n_xy, 64), 64, 0, st>>>(d_field, n_time, n_xy, d_count, d_mean, d_std);
+    launch_time_stats(e, d_field, n_time, n_xy, d_count, d_mean, d_std, st);
     MASK_EPILOGUE(1)
 }
 
@@ -1872,7 +1887,7 @@ int b2piv_mask_count(b2piv_engine* e, const float* d_vx, int n_time, long long n
     int rc = ensure(e, &e->d_mask_ws, &e->cap_mask_ws, (size_t)n_xy * sizeof(int));
     if (rc) return rc;
     int* cnt = reinterpret_cast<int*>(e->d_mask_ws);
-    time_stats_kernel<<<mask_grid(e, n_xy, 64), 64, 0, st>>>(d_vx, n_time, n_xy, cnt, nullptr, nullptr);
+    launch_time_stats(e, d_vx, n_time, n_xy, cnt, nullptr, nullptr, st);
     // count > tolerance * T  <=>  count >= floor(tolerance * T) + 1 (count is an integer; the product is the reference's float64 one)
     const double thr = tolerance * (double)n_time;
     const int min_count = thr < -1.0 ? 0 : (thr > 2.0e9 ? 2147483647 : (int)std::floor(thr) + 1);
@@ -1885,8 +1900,8 @@ static int mask_stats_xy(b2piv_engine* e, const float* d_vx, const float* d_vy, 
     int rc = ensure(e, &e->d_mask_ws, &e->cap_mask_ws, (size_t)4 * n_xy * sizeof(float));
     if (rc) return rc;
     float* w = e->d_mask_ws;
-    time_stats_kernel<<<mask_grid(e, n_xy, 64), 64, 0, st>>>(d_vx, n_time, n_xy, nullptr, w, w + n_xy);
-    time_stats_kernel<<<mask_grid(e, n_xy, 64), 64, 0, st>>>(d_vy, n_time, n_xy, nullptr, w + 2 * n_xy, w + 3 * n_xy);
+    launch_time_stats(e, d_vx, n_time, n_xy, nullptr, w, w + n_xy, st);
+    launch_time_stats(e, d_vy, n_time, n_xy, nullptr, w + 2 * n_xy, w + 3 * n_xy, st);
     return B2PIV_OK;
 }
 

@@ -166,6 +166,13 @@ def test_gpu_time_statistics_match_numpy_bit_for_bit():
     assert np.isnan(mean[3, 4]) and std[7, 8] == 0.0
     same(M.count(vx, 0.9), MO.count(vx, 0.9))
     same(M.count(vx), MO.count(vx))
+    # the segmented kernel (16 <= T <= 1024, loads parallel in time) and the one-thread-per-location kernel give the same bits
+    for T in (12, 16, 33, 64, 1024, 1030):
+        a = fields(T=T, ny=12, nx=45, seed=T)[0]
+        cnt, mean, std = M.time_stats(a)
+        om, os_ = MO.time_stats(a)
+        assert np.array_equal(cnt, (~np.isnan(a)).sum(axis=0)), T
+        assert np.array_equal(mean, om, equal_nan=True) and np.array_equal(std, os_, equal_nan=True), T
 
 
 @gpu

@@ -380,6 +380,20 @@ def main():
     e2e_value = nwin_rank * world * args.steps / e2e_s
     h2d = int(host.nbytes)
     d2h = int(4 * hu.nbytes)
+    # the same call on ORDINARY numpy memory (what pyorc hands over: frame_chunk.values): the engine stages it through its
+    # page-locked ring with a few copy threads (N = 1 only; reported beside the pinned number, not instead of it)
+    pageable = None
+    if world == 1:
+        host_pg = np.array(host, copy=True)
+        for _ in range(2):
+            eng.pairs(host_pg, WS, OV)
+        reps = min(args.steps, 10)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            eng.pairs(host_pg, WS, OV)
+        dt = (time.perf_counter() - t0) / reps
+        pageable = {"value": nwin_rank / dt, "ms_per_step": 1e3 * dt}
+        del host_pg
 
     # the PCIe floor under e2e: the same number of bytes, pinned host -> device, nothing else (N = 1 only)
     pcie = None
@@ -452,7 +466,8 @@ def main():
                    "parallelism": f"frame-pair shard x{world}", "gather": gather_how},
         "roofline": roofline, "fp32": fp32, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                "ms_per_step": 1e3 * e2e_s / args.steps, "api": "pyorc_b200.engine.Engine.pairs(numpy pinned)", "pcie": pcie},
+                "ms_per_step": 1e3 * e2e_s / args.steps, "api": "pyorc_b200.engine.Engine.pairs(numpy pinned)", "pcie": pcie,
+                "pageable_numpy": pageable},
         "gpu_launches": int(launches), "clocks": clocks, "rmse_vs_oracle": rmse, "other_configs": other,
     }
     emit(line)

@@ -38,7 +38,8 @@ const char* b2piv_last_error(const b2piv_engine* e);
 
 /* Numerical switches for the details that live in ffpiv rather than pyorc (see oracle/ffpiv_oracle.py):
  *   "clip_normalized" (0/1, default 0 = ffpiv), "border_nan" (0/1), "gauss_eps" (float), "copy_chunks" (H2D
- *   pipeline depth of the *_host calls; 0 = auto, about 10 MB of frames per chunk), "kernel_variant" (0 auto, 1 shared-memory FFT,
+ *   pipeline depth of the *_host calls; 0 = auto, about 10 MB of frames per chunk), "stage_threads" (threads that copy
+ *   ordinary pageable host frames into the engine's page-locked staging ring; 0 = auto, min(8, hardware threads)), "kernel_variant" (0 auto, 1 shared-memory FFT,
  *   2 row-per-thread TMA - 32x32 / 64x64 and the polyphase 128x128 kernel, 3 direct, 4 row-per-thread TMA in
  *   padded mode for uint8 windows up to 32 px), "run_len". */
 int b2piv_set_option(b2piv_engine* e, const char* name, double value);

@@ -504,3 +504,27 @@ def test_fused_peer_gather_two_engines_one_device():
             torch.cuda.synchronize()
             assert torch.equal(torch.nan_to_num(buf[:, 2:]), torch.nan_to_num(w2)) and float(buf[:, :2].max()) == -7.0
             e0.set_peer_outputs(None, 1, 0)
+
+
+def test_pageable_and_pinned_host_frames_give_identical_results(engine):
+    """Ordinary numpy memory is staged through the engine's page-locked ring by copy threads (any thread count, any frame
+    width - 203 px rows are re-pitched on the way), page-locked memory goes straight to the device: same bits."""
+    imgs = synth.particle_frames(23, 190, 203, dtype=np.uint8)
+    pinned = engine.pinned_empty(imgs.shape, np.uint8)
+    pinned[...] = imgs
+    engine.set_option("clip_normalized", 0.0)
+    engine.set_option("kernel_variant", 0.0)
+    ref = engine.pairs(pinned, (32, 32), (16, 16))
+    for threads, chunks in ((1, 0), (3, 5), (8, 1), (0, 0)):
+        engine.set_option("stage_threads", float(threads))
+        engine.set_option("copy_chunks", float(chunks))
+        got = engine.pairs(imgs, (32, 32), (16, 16))
+        for a, b in zip(ref, got):
+            assert np.array_equal(a, b, equal_nan=True)
+    engine.set_option("copy_chunks", 0.0)
+    f32 = imgs.astype(np.float32)
+    a = engine.pairs(f32, (32, 32), (16, 16))
+    p32 = engine.pinned_empty(f32.shape, np.float32)
+    p32[...] = f32
+    b = engine.pairs(p32, (32, 32), (16, 16))
+    assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(a, b))

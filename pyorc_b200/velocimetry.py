@@ -65,11 +65,17 @@ def get_b2piv(
     count_min: float = 0.2,
     signal_threshold: Optional[float] = None,
     device: int = 0,
+    coarse_pass: Optional[Tuple[Tuple[int, int], Tuple[int, int]]] = None,
 ):
     """Time-resolved or ensemble PIV on the B200 engine; same contract as ``get_ffpiv`` (ffpiv.py:24-179).
 
     Returns a Dataset with ``s2n``, ``corr``, ``v_x``, ``v_y`` on ``(time, y, x)``; velocities in m/s
     (``u * res_x / dt``), float32.  ``engine`` must be ``"b200"``; ``device`` selects the GPU.
+
+    ``coarse_pass=((wy, wx), (oy, ox))`` (no reference counterpart - ffpiv is single pass): two-pass PIV with a discrete
+    window offset, BASELINE.json ``configs[2]``: a first pass on that coarse grid gives a validated, interpolated
+    whole-pixel predictor, ``window_size`` / ``overlap`` are the grid of the second pass (``Engine.pairs_two_pass``);
+    per-time-step mode only.
     """
     CHUNK_SIZE_ERROR = (
         "Chunk size with selected nr of chunks ({chunks}) is 2 or less. If you manually "
@@ -121,20 +127,32 @@ def get_b2piv(
         raise ValueError("dt must hold one interval per frame pair")
     eng = get_engine(device)
     common = (frames, bounds, times, dt_vals, y, x, res_y, res_x, n_rows, n_cols, window_size, overlap, eng)
+    if coarse_pass is not None:
+        if ensemble_corr:
+            raise NotImplementedError("coarse_pass (two-pass PIV) is available in per-time-step mode only")
+        if signal_threshold is not None:
+            raise NotImplementedError("coarse_pass (two-pass PIV) does not take a signal_threshold")
+        (cwy, cwx), (coy, cox) = coarse_pass
+        if cwy < window_size[0] or cwx < window_size[1] or cwy > dim_size[0] or cwx > dim_size[1]:
+            raise ValueError("the coarse window must be at least as large as window_size and fit the frame")
+        coarse_pass = ((int(cwy), int(cwx)), (int(coy), int(cox)))
     if ensemble_corr:
         return _get_b2piv_mean(*common, corr_min, s2n_min, count_min, signal_threshold)
-    return _get_b2piv_timestep(*common, signal_threshold)
+    return _get_b2piv_timestep(*common, signal_threshold, coarse_pass)
 
 
-def _get_uv_timestep(da, n_cols, n_rows, window_size, overlap, search_area_size, engine, signal_threshold=None):
+def _get_uv_timestep(da, n_cols, n_rows, window_size, overlap, search_area_size, engine, signal_threshold=None, coarse_pass=None):
     """``u, v`` [px/frame], ``corr_max``, ``s2n`` - the narrow waist (ffpiv.py:446-474), fused on the GPU."""
-    u, v, corr_max, s2n = engine.pairs(_values(da), window_size, overlap, signal_threshold=signal_threshold)
+    if coarse_pass is not None:
+        u, v, corr_max, s2n = engine.pairs_two_pass(_values(da), coarse_pass, (tuple(window_size), tuple(overlap)))
+    else:
+        u, v, corr_max, s2n = engine.pairs(_values(da), window_size, overlap, signal_threshold=signal_threshold)
     assert u.shape[1:] == (n_rows, n_cols)
     return u, v, corr_max, s2n
 
 
 def _get_b2piv_timestep(frames, bounds, times, dt_vals, y, x, res_y, res_x, n_rows, n_cols, window_size, overlap, eng,
-                        signal_threshold):
+                        signal_threshold, coarse_pass=None):
     """Per-time-step mode (ffpiv.py:379-443)."""
     ds_piv_chunks = []
     for a, b in bounds:
@@ -144,7 +162,7 @@ def _get_b2piv_timestep(frames, bounds, times, dt_vals, y, x, res_y, res_x, n_ro
         b = a + len(da)
         time = times[a + 1 : b]
         dt_chunk = dt_vals[a : b - 1]
-        u, v, corr_max, s2n = _get_uv_timestep(da, n_cols, n_rows, window_size, overlap, window_size, eng, signal_threshold)
+        u, v, corr_max, s2n = _get_uv_timestep(da, n_cols, n_rows, window_size, overlap, window_size, eng, signal_threshold, coarse_pass)
         u = (u * res_x / np.expand_dims(dt_chunk, (1, 2))).astype(np.float32)
         v = (v * res_y / np.expand_dims(dt_chunk, (1, 2))).astype(np.float32)
         ds = xr.Dataset(

@@ -21,6 +21,13 @@ class FakeEngine:
         u, v, c, s = O.uv_timestep(np.asarray(imgs), nc, nr, ws, ov, signal_threshold=signal_threshold)
         return u.astype(np.float32), v.astype(np.float32), c, s
 
+    def pairs_two_pass(self, imgs, coarse, fine):
+        from oracle import multipass_oracle as MP
+
+        self.calls.append(("two_pass", np.asarray(imgs).shape[0], coarse, fine))
+        u, v, c, s, _, _ = MP.two_pass(np.asarray(imgs), coarse, fine)
+        return u.astype(np.float32), v.astype(np.float32), c.astype(np.float32), s.astype(np.float32)
+
     def ens_begin(self, dim_size, ws, ov, dtype):
         nr, nc = O.get_array_shape(dim_size, ws, ov)
         self._ens = None
@@ -192,3 +199,26 @@ def test_pinned_result_pool_recycles_blocks_only_when_every_view_is_gone():
     del d
     gc.collect()
     assert not lib.live                                 # released after close: freed, not pooled
+
+
+def test_coarse_pass_routes_chunks_through_the_two_pass_engine(fake):
+    """get_b2piv(coarse_pass=...) - the two-pass scheme of BASELINE configs[2] behind the reference-shaped binding: chunks with
+    a 1-frame halo, unit conversion and Dataset layout as in the single pass; refused in ensemble mode."""
+    O.CLIP_NORMALIZED = False
+    da, res = make_frames(n=6, H=150, W=200)
+    ws, ov, coarse = (32, 32), (24, 24), ((64, 64), (48, 48))
+    nr, nc = O.get_array_shape((150, 200), ws, ov)
+    y, x = np.arange(nr), np.arange(nc)
+    ds = velocimetry.get_b2piv(da, y, x, np.full(5, 1 / 30), ws, ov, ws, res, res, chunksize=4, coarse_pass=coarse)
+    assert [c[:2] for c in fake.calls] == [("two_pass", 4), ("two_pass", 3)] and fake.calls[0][2:] == (coarse, (ws, ov))
+    assert ds["v_x"].values.shape == (5, nr, nc) and ds["v_x"].values.dtype == np.float32
+    from oracle import multipass_oracle as MP
+
+    u, v, c, s, _, _ = MP.two_pass(da.values, coarse, (ws, ov))
+    assert np.allclose(ds["v_x"].values, (u * res * 30).astype(np.float32), equal_nan=True, rtol=1e-6)
+    assert np.allclose(ds["corr"].values, c, equal_nan=True)
+    with pytest.raises(NotImplementedError):
+        velocimetry.get_b2piv(da, y, x, np.full(5, 1 / 30), ws, ov, ws, res, res, coarse_pass=coarse, ensemble_corr=True)
+    with pytest.raises(ValueError):
+        velocimetry.get_b2piv(da, y, x, np.full(5, 1 / 30), ws, ov, ws, res, res, coarse_pass=((16, 16), (8, 8)))
+    O.CLIP_NORMALIZED = True

@@ -217,3 +217,24 @@ def test_gpu_two_pass_config2_full_frame(engine):
     # spot check against the definition on one pair of a frame crop is covered above; here: determinism
     u2, v2, _, _ = engine.pairs_two_pass(d, COARSE, FINE)
     assert torch.equal(torch.nan_to_num(u), torch.nan_to_num(u2)) and torch.equal(torch.nan_to_num(v), torch.nan_to_num(v2))
+
+
+@gpu
+def test_gpu_get_piv_with_coarse_pass(engine):
+    """The two-pass scheme behind the get_piv-shaped binding: get_piv(window_size=32, overlap=(24, 24), coarse_pass=...) returns the
+    usual Dataset (v_x, v_y, corr, s2n on time / y / x, m/s) and equals Engine.pairs_two_pass times res / dt."""
+    from pyorc_b200 import _xr
+    from pyorc_b200 import frames as b2frames
+    from pyorc_b200.engine import get_engine
+
+    get_engine(0).set_option("clip_normalized", 0.0)
+    H, W, res = 200, 288, 0.01
+    imgs = synth.particle_frames(5, H, W, dtype=np.uint8)
+    da = _xr.DataArray(imgs, ("time", "y", "x"), {"time": np.arange(5) / 30.0, "y": np.flipud(np.linspace(res / 2, res * (H - 0.5), H)),
+                                                  "x": np.linspace(res / 2, res * (W - 0.5), W)})
+    ds = b2frames.get_piv(da, window_size=32, overlap=(24, 24), engine="b200", resolution=res, coarse_pass=COARSE)
+    u, v, c, s = engine.pairs_two_pass(imgs, COARSE, FINE)
+    assert ds["v_x"].values.shape == u.shape
+    assert np.allclose(ds["v_x"].values, (u * res * 30.0).astype(np.float32), equal_nan=True, rtol=1e-6, atol=0)
+    assert np.allclose(ds["v_y"].values, (v * res * 30.0).astype(np.float32), equal_nan=True, rtol=1e-6, atol=0)
+    assert np.array_equal(ds["corr"].values, c, equal_nan=True)

@@ -129,3 +129,46 @@ def test_ensemble_matches_manual_average():
     u2, v2 = O.u_v_displacement(corr.mean(axis=0, keepdims=True), nr, nc)
     assert np.allclose(u, u2, atol=1e-4, equal_nan=True) and np.allclose(v, v2, atol=1e-4, equal_nan=True)
     assert cm.shape == (1, nr, nc) and sn.shape == (1, nr, nc)
+
+
+def test_polyphase_identity_behind_the_128x128_kernel():
+    """piv_rows128.cuh never runs a 128-point transform: with a_p[m] = a[2m + p] the period-128 circular cross-correlation has
+    the polyphase components c_q[n'] = sum_p corr64(a_p, b_{p xor q})[n' + (p and q)], i.e. in the 64x64 frequency domain
+    C_q[k] = sum_p conj(A_p[k]) B_{p xor q}[k] exp(+2 pi i (k1 s1 + k2 s2) / 64), s = p and q.  Checked here in float64 against
+    the reference formula irfft2(conj(rfft2 a) rfft2 b)."""
+    rng = np.random.default_rng(12)
+    a, b = rng.standard_normal((128, 128)), rng.standard_normal((128, 128))
+    ref = np.fft.irfft2(np.conj(np.fft.rfft2(a)) * np.fft.rfft2(b), s=(128, 128))
+    comp = lambda x, p1, p2: x[p1::2, p2::2]
+    A = {(p1, p2): np.fft.fft2(comp(a, p1, p2)) for p1 in (0, 1) for p2 in (0, 1)}
+    B = {(p1, p2): np.fft.fft2(comp(b, p1, p2)) for p1 in (0, 1) for p2 in (0, 1)}
+    k1, k2 = np.meshgrid(np.arange(64), np.arange(64), indexing="ij")
+    got = np.empty_like(ref)
+    for q1 in (0, 1):
+        for q2 in (0, 1):
+            C = np.zeros((64, 64), complex)
+            for p1 in (0, 1):
+                for p2 in (0, 1):
+                    s1, s2 = p1 & q1, p2 & q2
+                    C += np.conj(A[p1, p2]) * B[p1 ^ q1, p2 ^ q2] * np.exp(2j * np.pi * (k1 * s1 + k2 * s2) / 64)
+            cq = np.fft.ifft2(C)
+            assert np.abs(cq.imag).max() < 1e-9
+            got[q1::2, q2::2] = cq.real
+    assert np.abs(got - ref).max() < 1e-9 * np.abs(ref).max() + 1e-9
+    # the index map of the kernel's epilogue: reference (fftshifted) row of element m1 of component q1 is (2 m1 + q1 + 64) % 128
+    sh = np.fft.fftshift(ref)
+    m1, q1, m2, q2 = 5, 1, 40, 0
+    assert sh[(2 * m1 + q1 + 64) % 128, (2 * m2 + q2 + 64) % 128] == ref[2 * m1 + q1, 2 * m2 + q2]
+
+
+def test_displaced_second_pass_needs_two_forward_transforms_per_frame():
+    """piv_rows_shift_kernel: pair k correlates the undisplaced window of frame k with the DISPLACED window of frame k+1, pair
+    k+1 the undisplaced window of frame k+1 with the displaced one of frame k+2 - the displaced spectrum cannot be reused as
+    the next pair's `a` (a shift of the window is not a phase ramp of its spectrum: the content changes at the borders)."""
+    rng = np.random.default_rng(3)
+    img = rng.standard_normal((96, 96))
+    w0 = img[32:64, 32:64]
+    w_shift = img[35:67, 30:62]                       # the window displaced by (+3, -2)
+    k1, k2 = np.meshgrid(np.fft.fftfreq(32), np.fft.fftfreq(32), indexing="ij")
+    ramp = np.fft.fft2(w0) * np.exp(2j * np.pi * (3 * k1 - 2 * k2))
+    assert np.abs(np.fft.ifft2(ramp).real - w_shift).max() > 0.5     # circular shift != displaced window

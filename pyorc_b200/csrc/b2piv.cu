@@ -1451,7 +1451,12 @@ static int pipeline_host(b2piv_engine* e, const void* frames, int n_frames, bool
         if (!e->pool) {
             int nt = e->stage_threads;
             if (nt <= 0) { nt = (int)std::thread::hardware_concurrency(); nt = nt > 8 ? 8 : (nt < 1 ? 1 : nt); }
-            e->pool = new CopyPool(nt);
+            try {
+                e->pool = new CopyPool(nt);
+            } catch (...) {   // no threads to be had: let the driver stage the pageable copy (nothing may throw across the ABI)
+                e->pool = nullptr;
+                pageable = false;
+            }
         }
     }
     // enqueue the H2D copy of frames [f0, f1) on s_copy

@@ -9,7 +9,7 @@ Ensemble mode all-reduces the plane sums / counts before the peak fit.
 
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Tuple
+from typing import Callable, Optional, Tuple
 
 import numpy as np
 

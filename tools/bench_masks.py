@@ -5,7 +5,7 @@ Algorithmic bytes: every input field read once (twice where the reference's two-
 """
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from pyorc_b200 import mask as M
 
 def timeit(fn, reps=10):

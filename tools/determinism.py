@@ -1,7 +1,7 @@
 """Run-to-run bit determinism of the fused kernels (same process, repeated launches)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from pyorc_b200.engine import Engine
 from pyorc_b200 import synth
 e = Engine(0)

@@ -1,7 +1,7 @@
 """Two-pass timing (development aid): repeated device-resident runs + per-stage CUDA-event times."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from pyorc_b200.engine import Engine
 from pyorc_b200 import synth
 e = Engine(0)

@@ -1,0 +1,112 @@
+// k_rows128.cu - 128x128 uint8 windows on the polyphase row-per-thread kernel (piv_rows128.cuh).
+#include "rows_kernel.cuh"
+#include "piv_rows128.cuh"
+
+// 128 x 128 windows: four polyphase sub-groups of 64 threads run the 64 x 64 pipeline above and meet in the cross-spectrum
+// phase (piv_rows128.cuh).  One CTA = one group of 256 threads = one pair of adjacent windows followed through a run of
+// frames; 213 KB of shared memory (4 x transpose blocks + parked spectra), one CTA per SM.
+__global__ void __launch_bounds__(256, 1) piv_rows128_kernel(const __grid_constant__ CUtensorMap tmap, RParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    R128Smem& s = *reinterpret_cast<R128Smem*>(base);
+    const int tid = threadIdx.x;
+    const int sub = tid >> 6;      // polyphase component (p1, p2) = (sub >> 1, sub & 1)
+    const int t = tid & 63;        // thread within the sub-group (= line slot of the 64 x 64 pipeline)
+    RSmem<R6>& ss = s.sub[sub];
+    if (tid == 0) {
+        mbar_init(&s.mbar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+    RRegs<R6> r;
+    r.half_alpha_prev[0] = r.half_alpha_prev[1] = 0.f;
+    for (long long unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
+        const RUnit un = decode_unit(p, (int)unit);
+        const int nfr = un.f1 - un.f0 + 1;
+        auto issue_frame = [&](int frame) {
+            fence_proxy_async();
+            mbar_expect_tx(&s.mbar, 2 * 128 * 128);
+#pragma unroll
+            for (int w = 0; w < 2; ++w)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    tma_load_3d(s.sub[j].tile() + w * 4096, &tmap, &s.mbar, un.x0[w], un.y0[w] + 32 * j, frame);
+        };
+        if (tid == 0) issue_frame(un.f0);
+        for (int k = 0; k < nfr; ++k) {
+            const bool have_prev = k > 0;
+            const int f = un.f0 + k;
+            while (!mbar_try_wait(&s.mbar, parity)) {}
+            parity ^= 1u;
+            r128_p1(s, r, sub, t);
+            __syncthreads();  // A: integer moments visible, tile (aliased on the transpose blocks) fully consumed
+            r128_p2(s, r, p.clip_norm);
+            // forward: FFT(rows) T FFT(cols) per component; cross spectra across components; inverse: FFT(cols) T FFT(rows)
+            // (one copy of the unrolled FFT: the loop body is far beyond the instruction caches, every KB counts)
+#pragma unroll 1
+            for (int stg = 0; stg < 4; ++stg) {
+                fft_reg<64, 0>(r.v);
+                if ((stg & 1) == 0) transpose_device<R6>(ss, r, t, stg != 0);
+                else if (stg == 1) r128_cross(s, r, sub, t);
+            }
+            const bool dead0 = (r.half_alpha_prev[0] == 0.f) || (r.half_alpha_new[0] == 0.f);
+            const bool dead1 = (r.half_alpha_prev[1] == 0.f) || (r.half_alpha_new[1] == 0.f);
+            rows_p5_post<R6, false>(ss, r, t, dead0, dead1, &p);
+            __syncthreads();  // E1: block max / sum of all components; the transpose blocks are free again
+            if (tid == 0 && k + 1 < nfr) issue_frame(f + 1);
+            r128_p6(s, r, sub, t);
+            __syncthreads();  // E2: first-argmax keys
+            if (have_prev) r128_dump_planes(r, sub, t, p, un, f - 1);
+            r128_p7(s, r, sub, t);
+            __syncthreads();  // F: neighbour rows dumped
+            if (have_prev) r128_p8(s, r, tid, p, un, f - 1);
+            r.half_alpha_prev[0] = r.half_alpha_new[0];
+            r.half_alpha_prev[1] = r.half_alpha_new[1];
+        }
+        __syncthreads();  // unit boundary: the next unit's first TMA overwrites the transpose blocks
+    }
+}
+
+int launch_rows128(b2piv_engine* e, const Params& gp, cudaStream_t st) {
+    const int n_frames = gp.n_pairs + 1;
+    CUtensorMap tmap;
+    const cuuint64_t dims[3] = {(cuuint64_t)e->W, (cuuint64_t)e->H, (cuuint64_t)n_frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)gp.pitch, (cuuint64_t)gp.frame_stride};
+    const cuuint32_t box[3] = {128, 32, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult cr = get_encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(gp.frames), dims, strides, box, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(e, B2PIV_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)cr));
+    RParams p;
+    memset(&p, 0, sizeof(p));
+    p.frames = (const unsigned char*)gp.frames; p.frame_stride = gp.frame_stride; p.pitch = gp.pitch;
+    p.n_rows = gp.n_rows; p.n_cols = gp.n_cols; p.sy = gp.sy; p.sx = gp.sx; p.n_pairs = gp.n_pairs;
+    p.clip_norm = gp.clip_norm; p.border_nan = gp.border_nan; p.gauss_eps = gp.gauss_eps; p.keep = gp.keep;
+    p.u = gp.u; p.v = gp.v; p.cmax = gp.cmax; p.s2n = gp.s2n; p.planes = gp.planes; p.peer = gp.peer;
+    p.ny = p.nx = 128;
+    const size_t smem = sizeof(R128Smem) + 1024;
+    CK(cudaFuncSetAttribute(piv_rows128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, piv_rows128_kernel, 256, smem));
+    if (occ < 1) return fail(e, B2PIV_ERR_CUDA, "128x128 rows kernel does not fit on an SM");
+    const long long resident = (long long)occ * e->sm_count;
+    const int nw = gp.n_rows * gp.n_cols, n_wp = (nw + 1) / 2;
+    int run = e->run_len;
+    if (run <= 0) {  // aim for >= 8 waves of work units; every unit start costs one extra forward transform
+        long long chunks = (8 * resident + n_wp - 1) / n_wp;
+        if (chunks < 1) chunks = 1;
+        run = (int)((gp.n_pairs + chunks - 1) / chunks);
+        if (run < 8) run = 8;
+    }
+    if (run > gp.n_pairs) run = gp.n_pairs;
+    p.run_len = run;
+    const long long n_units = (long long)n_wp * ((gp.n_pairs + run - 1) / run);
+    p.n_units = (int)n_units;
+    long long grid = n_units < resident ? n_units : resident;
+    piv_rows128_kernel<<<(unsigned)grid, 256, smem, st>>>(tmap, p);
+    CK(cudaGetLastError());
+    e->launches++;
+    return B2PIV_OK;
+}

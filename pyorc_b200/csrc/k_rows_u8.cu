@@ -1,0 +1,12 @@
+// k_rows_u8.cu - row-per-thread kernel, native 32x32 / 64x64 uint8 windows, per-time-step mode (the headline kernel).
+#include "rows_kernel.cuh"
+
+bool tma_available() { return get_encode_tiled() != nullptr; }
+
+// Compiled variants (measured on B200, profiles/r01/quick_sweeps.log): 64x64 is fastest with one group per CTA (four
+// 64-thread CTAs per SM) and one shared FFT body, 32x32 with four single-warp groups and two FFT copies.
+int launch_rows_u8(b2piv_engine* e, const Params& p, cudaStream_t st) {
+    const bool aligned = ((e->wx - e->ox) & 15) == 0;
+    if (e->wy == 64) return aligned ? launch_rows<RCfg<64>, 1, true, true, false>(e, p, st) : launch_rows<RCfg<64>, 1, true, false, false>(e, p, st);
+    return aligned ? launch_rows<RCfg<32>, 4, false, true, false>(e, p, st) : launch_rows<RCfg<32>, 4, false, false, false>(e, p, st);
+}

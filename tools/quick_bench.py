@@ -5,13 +5,14 @@ import numpy as np, torch
 from pyorc_b200.engine import Engine
 from pyorc_b200 import synth
 
-def run(H, W, ws, ov, n_frames, reps=5, dtype="uint8", variant=0, run_len=0, groups=0, rolled=0):
+def run(H, W, ws, ov, n_frames, reps=5, dtype="uint8", variant=0, run_len=0, **opts):
+    """opts: further engine options (name=value) for A/B runs."""
     dev = torch.device("cuda", 0)
     e = Engine(0)
     e.set_option("kernel_variant", variant)
     e.set_option("run_len", run_len)
-    e.set_option("groups", groups)
-    e.set_option("rolled", rolled)
+    for k, v in opts.items():
+        e.set_option(k, v)
     fr = synth.particle_frames_torch(n_frames, H, W, dev, dtype=dtype)
     torch.cuda.synchronize()
     for _ in range(3):
@@ -25,7 +26,7 @@ def run(H, W, ws, ov, n_frames, reps=5, dtype="uint8", variant=0, run_len=0, gro
     nr, nc = out[0].shape[1:]
     nwin = (n_frames - 1) * nr * nc
     t = float(np.median(ts))
-    print(f"variant {variant} run_len {run_len} groups {groups} rolled {rolled} {H}x{W} win {ws} ov {ov} {dtype}: {nwin} windows in {t:.3f} ms -> {nwin / t / 1e3:.2f} Mwin/s  (u mean {float(torch.nanmean(out[0])):.3f} v mean {float(torch.nanmean(out[1])):.3f})", flush=True)
+    print(f"variant {variant} run_len {run_len} {opts if opts else ""} {H}x{W} win {ws} ov {ov} {dtype}: {nwin} windows in {t:.3f} ms -> {nwin / t / 1e3:.2f} Mwin/s  (u mean {float(torch.nanmean(out[0])):.3f} v mean {float(torch.nanmean(out[1])):.3f})", flush=True)
     e.close()
 
 def run_two_pass(H, W, n_frames, coarse=((64, 64), (48, 48)), fine=((32, 32), (24, 24)), reps=5):

@@ -74,8 +74,17 @@ int b2piv_corr_planes_host(b2piv_engine* e, const void* frames, int n_frames, fl
  *   add        : process_frame_chunk + accumulation (ffpiv.py:200-243, :359-365); returns the masked per-pair
  *                corr_max and s2n [n_frames-1][n_windows] that aggregate_results averages on the host
  *   finish     : count filter, mean plane, peak fit (ffpiv.py:280-282, :324); min_count = count_min * n_chunks
- *   accum      : device pointers of the accumulators so ranks can all-reduce them (NCCL) before `finish`. */
+ *   accum      : device pointers of the accumulators so ranks can reduce them (NCCL) before `finish`.
+ * The accumulators are engine state shared by these calls, which may run on different streams (the engine's own for the
+ * *_host calls, the caller's for the *_device calls): the engine orders every call after the previous one's work on
+ * the accumulators (an event), so begin -> add -> add -> finish is safe on any mix of streams.  Work the CALLER enqueues on
+ * the accumulator pointers (a collective) must be on the stream it then passes to b2piv_ens_finish_device.
+ *   begin_device  : like begin, stream-ordered on `cuda_stream`, no synchronisation
+ *   finish_device : count filter + mean plane + peak fit of windows [first_window, first_window + n_windows) into
+ *                   d_u / d_v [n_windows] (device), stream-ordered - a rank that owns a window slice after a
+ *                   reduce-scatter of the plane sums finishes just that slice */
 int b2piv_ens_begin(b2piv_engine* e);
+int b2piv_ens_begin_device(b2piv_engine* e, void* cuda_stream);
 int b2piv_ens_add_host(b2piv_engine* e, const void* frames, int n_frames, float corr_min, float s2n_min,
                        float signal_threshold, float* corr_max, float* s2n);
 int b2piv_ens_add_device(b2piv_engine* e, const void* d_frames, long long frame_stride_bytes, int pitch_bytes,
@@ -84,6 +93,8 @@ int b2piv_ens_add_device(b2piv_engine* e, const void* d_frames, long long frame_
 int b2piv_ens_accum(b2piv_engine* e, float** d_plane_sum, float** d_count, long long* n_plane_floats,
                     long long* n_windows);
 int b2piv_ens_finish_host(b2piv_engine* e, float min_count, float* u, float* v, float* count);
+int b2piv_ens_finish_device(b2piv_engine* e, float min_count, long long first_window, long long n_windows, float* d_u, float* d_v,
+                            void* cuda_stream);
 
 /* Sub-pixel peak of arbitrary correlation planes [n_planes][wy][wx] (host): first-occurrence argmax + 3-point
  * Gaussian fit minus the plane centre - the standalone `ffpiv.u_v_displacement` (pyorc/velocimetry/ffpiv.py:324,471),

@@ -239,7 +239,8 @@ int b2piv_create(b2piv_engine** out, int device) {
     e->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&e->ev_k0) != cudaSuccess || cudaEventCreate(&e->ev_k1) != cudaSuccess) {
+        cudaEventCreate(&e->ev_k0) != cudaSuccess || cudaEventCreate(&e->ev_k1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_ens, cudaEventDisableTiming) != cudaSuccess) {
         g_create_err = "stream/event creation failed";
         delete e;
         return B2PIV_ERR_CUDA;
@@ -261,6 +262,7 @@ void b2piv_destroy(b2piv_engine* e) {
     delete e->pool;
     if (e->ev_k0) cudaEventDestroy(e->ev_k0);
     if (e->ev_k1) cudaEventDestroy(e->ev_k1);
+    if (e->ev_ens) cudaEventDestroy(e->ev_ens);
     if (e->s_copy) cudaStreamDestroy(e->s_copy);
     if (e->s_comp) cudaStreamDestroy(e->s_comp);
     delete e;
@@ -562,13 +564,15 @@ int b2piv_corr_planes_host(b2piv_engine* e, const void* frames, int n_frames, fl
     return B2PIV_OK;
 }
 
-int b2piv_ens_begin(b2piv_engine* e) {
-    if (!e) return B2PIV_ERR_ARG;
+// Accumulators are (re)allocated here; the zero-fill runs on `st`.  Work of an earlier ensemble that other streams may still have
+// in flight on the accumulators (ens_add_device on a caller stream) is ordered first through ev_ens.
+static int ens_begin_on(b2piv_engine* e, cudaStream_t st) {
     if (!e->planned) return fail(e, B2PIV_ERR_STATE, "b2piv_plan has not been called");
     CK(cudaSetDevice(e->device));
     const size_t nw = (size_t)e->n_rows * e->n_cols, npx = (size_t)e->wy * e->wx;
     const size_t need = nw * npx * sizeof(float);
     if (e->cap_ens < need || e->cap_ens_windows < nw) {
+        if (e->ens_pending) CK(cudaEventSynchronize(e->ev_ens));
         if (e->d_ens_sum) CK(cudaFree(e->d_ens_sum));
         if (e->d_ens_cnt) CK(cudaFree(e->d_ens_cnt));
         e->d_ens_sum = e->d_ens_cnt = nullptr; e->cap_ens = 0; e->cap_ens_windows = 0;
@@ -577,11 +581,26 @@ int b2piv_ens_begin(b2piv_engine* e) {
         e->cap_ens = need;
         e->cap_ens_windows = nw;
     }
-    CK(cudaMemsetAsync(e->d_ens_sum, 0, need, e->s_comp));
-    CK(cudaMemsetAsync(e->d_ens_cnt, 0, nw * sizeof(float), e->s_comp));
-    CK(cudaStreamSynchronize(e->s_comp));
+    if (e->ens_pending) CK(cudaStreamWaitEvent(st, e->ev_ens, 0));
+    CK(cudaMemsetAsync(e->d_ens_sum, 0, need, st));
+    CK(cudaMemsetAsync(e->d_ens_cnt, 0, nw * sizeof(float), st));
+    CK(cudaEventRecord(e->ev_ens, st));
+    e->ens_pending = true;
     e->ens_open = true;
     return B2PIV_OK;
+}
+
+int b2piv_ens_begin(b2piv_engine* e) {
+    if (!e) return B2PIV_ERR_ARG;
+    int rc = ens_begin_on(e, e->s_comp);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(e->s_comp));
+    return B2PIV_OK;
+}
+
+int b2piv_ens_begin_device(b2piv_engine* e, void* cuda_stream) {
+    if (!e) return B2PIV_ERR_ARG;
+    return ens_begin_on(e, (cudaStream_t)cuda_stream);
 }
 
 int b2piv_ens_add_device(b2piv_engine* e, const void* d_frames, long long frame_stride_bytes, int pitch_bytes, int n_frames,
@@ -601,7 +620,14 @@ int b2piv_ens_add_device(b2piv_engine* e, const void* d_frames, long long frame_
     }
     p.cmax = d_corr_max; p.s2n = d_s2n;
     EnsParams ep{corr_min, s2n_min, e->d_ens_sum, e->d_ens_cnt};
-    return dispatch_ens(e, p, ep, st);
+    // the accumulators are shared state: whatever stream touched them last (zero-fill, an earlier add) comes first, and this
+    // launch is what the next user - possibly on another stream - has to wait for
+    if (e->ens_pending) CK(cudaStreamWaitEvent(st, e->ev_ens, 0));
+    const int rc = dispatch_ens(e, p, ep, st);
+    if (rc) return rc;
+    CK(cudaEventRecord(e->ev_ens, st));
+    e->ens_pending = true;
+    return B2PIV_OK;
 }
 
 int b2piv_ens_add_host(b2piv_engine* e, const void* frames, int n_frames, float corr_min, float s2n_min,
@@ -640,6 +666,24 @@ int b2piv_ens_accum(b2piv_engine* e, float** d_plane_sum, float** d_count, long 
     return B2PIV_OK;
 }
 
+int b2piv_ens_finish_device(b2piv_engine* e, float min_count, long long first_window, long long n_windows, float* d_u, float* d_v,
+                            void* cuda_stream) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (!e->planned || !e->ens_open) return fail(e, B2PIV_ERR_STATE, "call b2piv_plan and b2piv_ens_begin first");
+    if (!d_u || !d_v) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
+    const long long nw = (long long)e->n_rows * e->n_cols;
+    if (first_window < 0 || n_windows < 0 || first_window + n_windows > nw) return fail(e, B2PIV_ERR_ARG, "window range outside the field");
+    if (n_windows == 0) return B2PIV_OK;
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (e->ens_pending) CK(cudaStreamWaitEvent(st, e->ev_ens, 0));
+    ens_finish_kernel<<<(unsigned)n_windows, 256, 0, st>>>(e->d_ens_sum + first_window * e->wy * e->wx, e->d_ens_cnt + first_window, e->wy, e->wx,
+                                                          min_count, e->border_nan, e->gauss_eps, d_u, d_v);
+    CK(cudaGetLastError());
+    e->launches++;
+    return B2PIV_OK;
+}
+
 int b2piv_ens_finish_host(b2piv_engine* e, float min_count, float* u, float* v, float* count) {
     if (!e) return B2PIV_ERR_ARG;
     if (!e->planned || !e->ens_open) return fail(e, B2PIV_ERR_STATE, "call b2piv_plan and b2piv_ens_begin first");
@@ -648,10 +692,8 @@ int b2piv_ens_finish_host(b2piv_engine* e, float min_count, float* u, float* v, 
     const size_t nw = (size_t)e->n_rows * e->n_cols;
     int rc = ensure(e, &e->d_out, &e->cap_out, nw * 4 * sizeof(float));
     if (rc) return rc;
-    ens_finish_kernel<<<(unsigned)nw, 256, 0, e->s_comp>>>(e->d_ens_sum, e->d_ens_cnt, e->wy, e->wx, min_count, e->border_nan,
-                                                           e->gauss_eps, e->d_out, e->d_out + nw);
-    CK(cudaGetLastError());
-    e->launches++;
+    rc = b2piv_ens_finish_device(e, min_count, 0, (long long)nw, e->d_out, e->d_out + nw, e->s_comp);   // waits for ev_ens
+    if (rc) return rc;
     CK(cudaMemcpyAsync(u, e->d_out, nw * sizeof(float), cudaMemcpyDeviceToHost, e->s_comp));
     CK(cudaMemcpyAsync(v, e->d_out + nw, nw * sizeof(float), cudaMemcpyDeviceToHost, e->s_comp));
     if (count) CK(cudaMemcpyAsync(count, e->d_ens_cnt, nw * sizeof(float), cudaMemcpyDeviceToHost, e->s_comp));

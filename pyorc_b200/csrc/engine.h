@@ -129,6 +129,9 @@ struct b2piv_engine {
     double* d_mp_ws = nullptr; size_t cap_mp_ws = 0;        // two-pass scheme: validated pass-1 fields
     float* d_mask_ws = nullptr; size_t cap_mask_ws = 0;     // mask stack: time statistics / window_replace ping-pong
     float* d_ens_sum = nullptr; float* d_ens_cnt = nullptr; size_t cap_ens = 0, cap_ens_windows = 0; bool ens_open = false;
+    // last work enqueued on the accumulators, whatever its stream: every later user waits for it first (ens_begin / ens_add_device
+    // / ens_finish may run on different streams - the engine's own or the caller's)
+    cudaEvent_t ev_ens = nullptr; bool ens_pending = false;
     // stats
     float last_kernel_ms = 0.f;
     long long launches = 0;

@@ -33,10 +33,12 @@ ABI_SYMBOLS = (
     "b2piv_pairs_device",
     "b2piv_corr_planes_host",
     "b2piv_ens_begin",
+    "b2piv_ens_begin_device",
     "b2piv_ens_add_host",
     "b2piv_ens_add_device",
     "b2piv_ens_accum",
     "b2piv_ens_finish_host",
+    "b2piv_ens_finish_device",
     "b2piv_peaks_host",
     "b2piv_pre_normalize_device",
     "b2piv_pre_time_diff_device",
@@ -93,10 +95,12 @@ def load_library(path: Optional[str] = None):
     lib.b2piv_pairs_device.argtypes = [vp, vp, cll, ci, ci, cf, vp, vp, vp, vp, vp]
     lib.b2piv_corr_planes_host.argtypes = [vp, vp, ci, cf, vp]
     lib.b2piv_ens_begin.argtypes = [vp]
+    lib.b2piv_ens_begin_device.argtypes = [vp, vp]
     lib.b2piv_ens_add_host.argtypes = [vp, vp, ci, cf, cf, cf, vp, vp]
     lib.b2piv_ens_add_device.argtypes = [vp, vp, cll, ci, ci, cf, cf, cf, vp, vp, vp]
     lib.b2piv_ens_accum.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(cll), ctypes.POINTER(cll)]
     lib.b2piv_ens_finish_host.argtypes = [vp, cf, vp, vp, vp]
+    lib.b2piv_ens_finish_device.argtypes = [vp, cf, cll, cll, vp, vp, vp]
     lib.b2piv_peaks_host.argtypes = [vp, vp, cll, ci, ci, vp, vp]
     lib.b2piv_pre_normalize_device.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp]
     lib.b2piv_pre_time_diff_device.argtypes = [vp, vp, ci, ci, ci, ci, cf, ci, vp, vp]
@@ -137,6 +141,18 @@ def load_library(path: Optional[str] = None):
 
 def _is_torch(x) -> bool:
     return type(x).__module__.startswith("torch")
+
+
+def _stream_ctx(torch, device, stream):
+    """(raw stream handle, context manager that makes it torch's current stream) for an optional ``stream=`` argument (a raw
+    ``cudaStream_t`` value or a ``torch.cuda.Stream``).  Tensors allocated inside the context belong to that stream for the
+    caching allocator, so a kernel launched on it may use them without ``record_stream`` bookkeeping."""
+    import contextlib
+
+    if stream is None:
+        return torch.cuda.current_stream(device).cuda_stream, contextlib.nullcontext()
+    ts = stream if isinstance(stream, torch.cuda.Stream) else torch.cuda.ExternalStream(int(stream), device=device)
+    return ts.cuda_stream, torch.cuda.stream(ts)
 
 
 class _CudaView:
@@ -322,6 +338,10 @@ class Engine:
         nr, nc = self.plan((H, W), window_size, overlap, frames.dtype)
         return frames, n, nr, nc, False
 
+    def _same_device(self, t):
+        if t.device.index != self.device:
+            raise ValueError(f"frames are on cuda:{t.device.index}, engine on cuda:{self.device}")
+
     # ---- per-time-step ----------------------------------------------------------------------------------------
     def pairs(self, frames, window_size, overlap, signal_threshold: Optional[float] = None, stream=None):
         """``u, v, corr_max, s2n`` for every consecutive frame pair, each ``[n-1, n_rows, n_cols]`` float32.
@@ -335,10 +355,12 @@ class Engine:
         if on_dev:
             import torch
 
-            if frames.device.index != self.device:
-                raise ValueError(f"frames are on cuda:{frames.device.index}, engine on cuda:{self.device}")
-            out = torch.empty((4, n - 1, nr, nc), dtype=torch.float32, device=frames.device)
-            st = stream if stream is not None else torch.cuda.current_stream(frames.device).cuda_stream
+            self._same_device(frames)
+            st, ctx = _stream_ctx(torch, frames.device, stream)
+            with ctx:
+                out = torch.empty((4, n - 1, nr, nc), dtype=torch.float32, device=frames.device)
+                if stream is not None:
+                    frames.record_stream(torch.cuda.current_stream(frames.device))   # also covers a .contiguous() temporary
             es = frames.element_size()
             self._check(
                 self._lib.b2piv_pairs_device(self._h, frames.data_ptr(), frames.stride(0) * es, frames.stride(1) * es, n, thr,
@@ -393,6 +415,7 @@ class Engine:
             raise TypeError("pairs_shifted takes device-resident frames (use pairs_two_pass for host arrays)")
         if tuple(shift.shape) != (n - 1, nr, nc, 2) or shift.dtype != torch.int16 or not shift.is_cuda:
             raise ValueError(f"shift must be a CUDA int16 tensor of shape {(n - 1, nr, nc, 2)}")
+        self._same_device(frames)
         shift = shift.contiguous()
         out = torch.empty((4, n - 1, nr, nc), dtype=torch.float32, device=frames.device)
         st = torch.cuda.current_stream(frames.device).cuda_stream
@@ -449,9 +472,17 @@ class Engine:
         return u.reshape(lead), v.reshape(lead)
 
     # ---- ensemble ---------------------------------------------------------------------------------------------
-    def ens_begin(self, dim_size, window_size, overlap, dtype):
+    def ens_begin(self, dim_size, window_size, overlap, dtype, stream=None, device_ordered: bool = False):
+        """Zero the accumulators.  ``device_ordered`` (or a ``stream``): stream-ordered on torch's current stream (or
+        ``stream``) without synchronising; otherwise on the engine's own stream, synchronous."""
         nr, nc = self.plan(dim_size, window_size, overlap, dtype)
-        self._check(self._lib.b2piv_ens_begin(self._h), "b2piv_ens_begin")
+        if stream is not None or device_ordered:
+            import torch
+
+            st, _ = _stream_ctx(torch, torch.device("cuda", self.device), stream)
+            self._check(self._lib.b2piv_ens_begin_device(self._h, st), "b2piv_ens_begin_device")
+        else:
+            self._check(self._lib.b2piv_ens_begin(self._h), "b2piv_ens_begin")
         return nr, nc
 
     def ens_add(self, frames, window_size, overlap, corr_min=0.2, s2n_min=3.0, signal_threshold=None, stream=None):
@@ -463,8 +494,12 @@ class Engine:
         if on_dev:
             import torch
 
-            out = torch.empty((2, n - 1, nr * nc), dtype=torch.float32, device=frames.device)
-            st = stream if stream is not None else torch.cuda.current_stream(frames.device).cuda_stream
+            self._same_device(frames)
+            st, ctx = _stream_ctx(torch, frames.device, stream)
+            with ctx:
+                out = torch.empty((2, n - 1, nr * nc), dtype=torch.float32, device=frames.device)
+                if stream is not None:
+                    frames.record_stream(torch.cuda.current_stream(frames.device))
             es = frames.element_size()
             self._check(
                 self._lib.b2piv_ens_add_device(self._h, frames.data_ptr(), frames.stride(0) * es, frames.stride(1) * es, n,
@@ -481,8 +516,10 @@ class Engine:
         return cm, sn
 
     def ens_accumulators(self):
-        """torch views of the device accumulators ``(plane_sum [n_windows, wy, wx], count [n_windows])`` so that
-        ranks can ``all_reduce`` them before :meth:`ens_finish`."""
+        """torch views of the device accumulators ``(plane_sum [n_windows, wy * wx], count [n_windows])`` so that ranks can
+        reduce them before the peak fit.  The engine orders its own calls on the accumulators whatever their streams; work
+        the caller enqueues on these views (a collective on torch's current stream) is ordered by finishing on the same
+        stream: :meth:`ens_finish_device`."""
         import torch
 
         ps, pc = ctypes.c_void_p(), ctypes.c_void_p()
@@ -494,7 +531,8 @@ class Engine:
         return plane.view(nw.value, -1), count
 
     def ens_finish(self, min_count: float):
-        """Count filter + mean plane + peak fit; returns ``u, v, count`` each ``[n_windows]``."""
+        """Count filter + mean plane + peak fit; returns ``u, v, count`` each ``[n_windows]`` (numpy; synchronous, ordered
+        after every earlier ``ens_add`` whatever stream it ran on)."""
         nr, nc = self._plan[1]
         u = np.empty(nr * nc, dtype=np.float32)
         v = np.empty(nr * nc, dtype=np.float32)
@@ -502,12 +540,57 @@ class Engine:
         self._check(self._lib.b2piv_ens_finish_host(self._h, float(min_count), u.ctypes.data, v.ctypes.data, cnt.ctypes.data), "b2piv_ens_finish_host")
         return u, v, cnt
 
+    def ens_finish_device(self, min_count: float, first_window: int = 0, n_windows: Optional[int] = None, stream=None):
+        """Peak fit of the windows ``[first_window, first_window + n_windows)`` on torch's current stream (or ``stream``):
+        returns CUDA tensors ``u, v`` ``[n_windows]``, no synchronisation.  After a reduce-scatter of the plane sums over the
+        window axis each rank finishes its own slice (:func:`pyorc_b200.parallel.ensemble_reduce_finish`)."""
+        import torch
+
+        nr, nc = self._plan[1]
+        if n_windows is None:
+            n_windows = nr * nc - first_window
+        dev = torch.device("cuda", self.device)
+        st, ctx = _stream_ctx(torch, dev, stream)
+        with ctx:
+            out = torch.empty((2, max(int(n_windows), 0)), dtype=torch.float32, device=dev)
+        self._check(self._lib.b2piv_ens_finish_device(self._h, float(min_count), int(first_window), int(n_windows),
+                                                      out[0].data_ptr(), out[1].data_ptr(), st), "b2piv_ens_finish_device")
+        return out[0], out[1]
+
 
 _default_engines = {}
 
 
-def get_engine(device: int = 0) -> Engine:
-    """Process-wide engine per device (created on first use)."""
-    if device not in _default_engines:
-        _default_engines[device] = Engine(device)
-    return _default_engines[device]
+_default_lock = __import__("threading").Lock()
+
+
+def get_engine(device: int = 0, slot: int = 0) -> Engine:
+    """Process-wide engine per ``(device, slot)`` (created on first use).  An engine is used by one host thread at a time
+    (the ABI's "one engine per thread and device"); ``slot > 0`` gives further engines on the same GPU -
+    ``get_b2piv(devices=[0, 0])`` runs two of them side by side, each with its own streams and staging buffers."""
+    key = (int(device), int(slot))
+    with _default_lock:
+        if key not in _default_engines:
+            _default_engines[key] = Engine(int(device))
+        return _default_engines[key]
+
+
+def merge_ensembles(engines, min_count: float):
+    """Finish an ensemble whose frame pairs were accumulated on several devices of ONE process (``get_b2piv(devices=...)``):
+    the other engines' plane sums and counts are added to the first engine's accumulators (peer copies over NVLink, on its
+    current torch stream) and the peak fit runs there, ordered behind the additions.  Returns numpy ``u, v, count``
+    ``[n_windows]``.  (One process per GPU: :func:`pyorc_b200.parallel.ensemble_sharded`.)"""
+    if len(engines) == 1:
+        return engines[0].ens_finish(min_count)
+    import torch
+
+    e0 = engines[0]
+    plane0, count0 = e0.ens_accumulators()
+    with torch.cuda.device(e0.device):
+        for e in engines[1:]:
+            pk, ck = e.ens_accumulators()
+            torch.cuda.synchronize(e.device)   # its ens_add_host calls have returned, i.e. are complete; belt and braces
+            plane0.add_(pk.to(plane0.device))
+            count0.add_(ck.to(count0.device))
+        u, v = e0.ens_finish_device(min_count)
+        return u.cpu().numpy(), v.cpu().numpy(), count0.cpu().numpy()

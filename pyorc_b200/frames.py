@@ -7,6 +7,7 @@ Everything above the engine call (window rounding, default overlap, result coord
 
 from __future__ import annotations
 
+import contextvars
 from typing import Optional
 
 import numpy as np
@@ -14,7 +15,7 @@ import numpy as np
 from . import window
 from .velocimetry import get_b2piv
 
-__all__ = ["get_piv", "get_piv_coords", "install"]
+__all__ = ["get_piv", "get_piv_coords", "install", "uninstall"]
 
 ENGINES = ["b200"]
 
@@ -88,13 +89,21 @@ def get_piv(
     return ds
 
 
+# per-call options of a ``get_piv(engine="b200", ...)`` in flight in THIS thread / task (None: not a b200 call)
+_B200_CALL = contextvars.ContextVar("pyorc_b200_call", default=None)
+_B200_KWARGS = ("device", "devices", "coarse_pass")
+
+
 def install():
     """Register ``engine="b200"`` in an importable pyorc (see INTEGRATION.md for the two-line upstream patch).
 
-    ``Frames.get_piv`` is wrapped: for ``engine="b200"`` the reference body runs unchanged (window rounding, coords,
-    attrs, encoding - frames.py:156-197) with ``engine="numba"`` passing its whitelist (frames.py:176-177), while
-    ``pyorc.velocimetry.ffpiv.get_ffpiv`` - looked up at call time at frames.py:186 - is redirected to
-    :func:`pyorc_b200.velocimetry.get_b2piv` for the duration of the call.
+    Two wrappers are installed ONCE and stay: ``Frames.get_piv`` accepts ``engine="b200"`` (plus ``device=``, ``devices=``,
+    ``coarse_pass=``), runs the reference body unchanged (window rounding, coords, attrs, encoding - frames.py:156-197) with
+    ``engine="numba"`` passing its whitelist (frames.py:176-177) and marks the call in a context variable;
+    ``pyorc.velocimetry.ffpiv.get_ffpiv`` - looked up at call time at frames.py:186 - sends a marked call to
+    :func:`pyorc_b200.velocimetry.get_b2piv` and every other call to the original.  Context variables are per thread (and per
+    asyncio task), so concurrent ``get_piv`` calls with different engines - pyorc under dask's threaded scheduler - do
+    not see each other, and no module global is swapped at call time.
     """
     import pyorc.api.frames as ref_frames  # noqa: PLC0415  (only present in a pyorc installation)
     import pyorc.velocimetry.ffpiv as ref_ffpiv  # noqa: PLC0415
@@ -102,23 +111,41 @@ def install():
     orig_get_piv = ref_frames.Frames.get_piv
     if getattr(orig_get_piv, "_b200", False):
         return True
+    orig_get_ffpiv = ref_ffpiv.get_ffpiv
+
+    def get_ffpiv(frames, y, x, dt, *args, **kwargs):
+        call = _B200_CALL.get()
+        if call is None:
+            return orig_get_ffpiv(frames, y, x, dt, *args, **kwargs)
+        kwargs = {**kwargs, **call, "engine": "b200"}
+        return get_b2piv(frames, y, x, dt, *args, **kwargs)
 
     def get_piv_b200(self, window_size=None, overlap=None, engine="numba", ensemble_corr=False, **kwargs):
         if engine != "b200":
             return orig_get_piv(self, window_size=window_size, overlap=overlap, engine=engine, ensemble_corr=ensemble_corr, **kwargs)
-        device = kwargs.pop("device", 0)
-        saved = ref_ffpiv.get_ffpiv
-
-        def forced(frames, y, x, dt, *a, engine="numba", **kw):
-            return get_b2piv(frames, y, x, dt.values, *a, engine="b200", device=device, **kw)
-
-        ref_ffpiv.get_ffpiv = forced
+        call = {k: kwargs.pop(k) for k in _B200_KWARGS if k in kwargs}
+        token = _B200_CALL.set(call)
         try:
             return orig_get_piv(self, window_size=window_size, overlap=overlap, engine="numba", ensemble_corr=ensemble_corr, **kwargs)
         finally:
-            ref_ffpiv.get_ffpiv = saved
+            _B200_CALL.reset(token)
 
+    get_ffpiv.__doc__ = orig_get_ffpiv.__doc__
+    get_ffpiv._b200_original = orig_get_ffpiv
     get_piv_b200._b200 = True
+    get_piv_b200._b200_original = orig_get_piv
     get_piv_b200.__doc__ = orig_get_piv.__doc__
+    ref_ffpiv.get_ffpiv = get_ffpiv
     ref_frames.Frames.get_piv = get_piv_b200
     return True
+
+
+def uninstall():
+    """Undo :func:`install` (tests)."""
+    import pyorc.api.frames as ref_frames  # noqa: PLC0415
+    import pyorc.velocimetry.ffpiv as ref_ffpiv  # noqa: PLC0415
+
+    if getattr(ref_frames.Frames.get_piv, "_b200", False):
+        ref_frames.Frames.get_piv = ref_frames.Frames.get_piv._b200_original
+    if hasattr(ref_ffpiv.get_ffpiv, "_b200_original"):
+        ref_ffpiv.get_ffpiv = ref_ffpiv.get_ffpiv._b200_original

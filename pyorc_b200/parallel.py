@@ -4,7 +4,8 @@ Per-time-step PIV is embarrassingly parallel over frame pairs (pyorc/velocimetry
 a 1-frame halo, :140), so rank *r* of *R* owns the contiguous pair range ``[r*P/R, (r+1)*P/R)`` and frames
 ``[start, end]`` inclusive.  The only collectives are the broadcast of the pair-range table and the gather of the
 16 B/window results (NCCL on GPUs; the same code runs over gloo for CPU tests with an injected compute function).
-Ensemble mode all-reduces the plane sums / counts before the peak fit.
+Ensemble mode reduce-scatters the plane sums over the window axis, each rank peak-fits its slice, and the 8 B/window results
+are all-gathered (:func:`ensemble_sharded`).
 """
 
 from __future__ import annotations
@@ -145,11 +146,114 @@ def piv_pairs_sharded(frames_for_rank: Callable[[int, int], object], n_pairs_tot
     return gather_fields(local.float(), n_pairs_total, table, group=group)
 
 
-def allreduce_ensemble(engine, group=None):
-    """Sum the ensemble accumulators (plane sums + valid counts) over ranks before ``ens_finish``."""
+def window_slices(n_windows: int, world_size: int) -> np.ndarray:
+    """``[world_size, 2]`` (first, stop) window ranges of the ensemble peak fit: ``n_windows // world_size`` windows per rank -
+    the equal blocks a reduce-scatter needs - and the remainder (fewer than ``world_size`` windows) on the last rank."""
+    base = n_windows // world_size
+    t = np.array([[r * base, (r + 1) * base] for r in range(world_size)], dtype=np.int64)
+    t[-1, 1] = n_windows
+    return t
+
+
+def ensemble_reduce_finish(plane, count, finish: Callable[[int, int], Tuple], group=None):
+    """Ensemble mode across ranks: every rank holds partial plane sums ``plane [n_windows, wy * wx]`` and
+    valid counts ``count [n_windows]`` of ITS frame pairs (pyorc/velocimetry/ffpiv.py:361-363 accumulates them over chunks).
+
+    1. ``count`` is all-reduced (4 B / window);
+    2. ``plane`` is REDUCE-SCATTERED over the window axis: rank r receives the global sums of its window slice
+       (:func:`window_slices`) - each rank moves 1/R of the planes instead of all of them - written back into its rows of
+       ``plane``; the remainder rows (fewer than R windows) are all-reduced and belong to the last rank;
+    3. ``finish(first, n) -> (u, v)`` ([n] tensors: count filter, mean plane, peak fit of those rows - ffpiv.py:280-282, :324)
+       runs on the slice;
+    4. the 8 B / window results are all-gathered.
+
+    Returns ``u, v`` ``[n_windows]`` (the same on every rank) and the reduced ``count``.  Works on any backend (NCCL with the
+    engine's accumulators; gloo in the CPU tests with a numpy ``finish``)."""
+    import torch
     import torch.distributed as dist
 
-    plane, count = engine.ens_accumulators()
-    dist.all_reduce(plane, op=dist.ReduceOp.SUM, group=group)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    nw = plane.shape[0]
     dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
-    return plane, count
+    table = window_slices(nw, world)
+    base = nw // world
+    if world > 1:
+        if base > 0:
+            mine = torch.empty((base,) + tuple(plane.shape[1:]), dtype=plane.dtype, device=plane.device)
+            dist.reduce_scatter_tensor(mine, plane[: base * world], op=dist.ReduceOp.SUM, group=group)
+            plane[rank * base : (rank + 1) * base].copy_(mine)
+            del mine
+        if nw > base * world:
+            tail = plane[base * world :]
+            dist.all_reduce(tail, op=dist.ReduceOp.SUM, group=group)
+    first, stop = int(table[rank, 0]), int(table[rank, 1])
+    u, v = finish(first, stop - first)
+    smax = int((table[:, 1] - table[:, 0]).max())
+    send = torch.zeros((2, smax), dtype=torch.float32, device=plane.device)
+    send[0, : stop - first] = torch.as_tensor(u, dtype=torch.float32, device=plane.device)
+    send[1, : stop - first] = torch.as_tensor(v, dtype=torch.float32, device=plane.device)
+    recv = torch.empty((world * 2, smax), dtype=torch.float32, device=plane.device)   # concatenation along dim 0 (all backends)
+    if world > 1:
+        dist.all_gather_into_tensor(recv, send, group=group)
+    else:
+        recv.copy_(send)
+    recv = recv.view(world, 2, smax)
+    out = torch.empty((2, nw), dtype=torch.float32, device=plane.device)
+    for r in range(world):
+        a, b = int(table[r, 0]), int(table[r, 1])
+        out[:, a:b] = recv[r, :, : b - a]
+    return out[0], out[1], count
+
+
+def aggregate_ensemble(corr_max_concat: np.ndarray, s2n_concat: np.ndarray, corr_count: np.ndarray, min_count: float, n_rows: int,
+                       n_cols: int):
+    """The host half of ``aggregate_results`` (ffpiv.py:263-286): count filter on the per-pair maxima, time means of the
+    per-pair ``corr_max`` and ``s2n`` ``[pairs, n_windows]`` -> ``[1, n_rows, n_cols]`` each."""
+    import warnings
+
+    corr_max_concat = np.array(corr_max_concat, dtype=np.float32, copy=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", category=RuntimeWarning)
+        corr_max_concat[:, np.asarray(corr_count).reshape(-1) < min_count] = np.nan
+        corr_max_mean = np.nanmean(corr_max_concat, axis=0).reshape(-1, n_rows, n_cols)
+        s2n_mean = np.nanmean(s2n_concat, axis=0).reshape(-1, n_rows, n_cols)
+    return corr_max_mean, s2n_mean
+
+
+def ensemble_sharded(engine, frames, window_size, overlap, n_pairs_total: int, table: np.ndarray, corr_min=0.2, s2n_min=3.0,
+                     count_min=0.2, n_chunks_total: Optional[int] = None, signal_threshold=None, group=None):
+    """Ensemble-correlation PIV with the frame pairs sharded over the ranks (one process per GPU).
+
+    ``frames``: this rank's device-resident frames (its pair range of ``table`` plus the 1-frame halo; None for an empty
+    shard).  Every rank accumulates the planes of its pairs in its engine (one launch), the plane sums are reduce-scattered
+    over the window axis, each rank peak-fits its slice, and the results plus the per-pair ``corr_max`` / ``s2n`` statistics
+    are all-gathered (:func:`ensemble_reduce_finish`, :func:`gather_fields`).  ``n_chunks_total``: the reference's
+    ``n_frames`` of the count filter - its number of CHUNKS (ffpiv.py:373), default one chunk per rank.
+
+    Returns ``u, v`` [px / frame], ``corr_max_mean``, ``s2n_mean`` as numpy ``[1, n_rows, n_cols]`` (identical on every rank)
+    and the valid count ``[n_windows]``."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = torch.device("cuda", engine.device)
+    a, b = int(table[rank, 0]), int(table[rank, 1])
+    n_chunks_total = world if n_chunks_total is None else int(n_chunks_total)
+    min_count = float(count_min) * n_chunks_total
+    if frames is not None:
+        dims, dtype = tuple(frames.shape[-2:]), (np.uint8 if frames.dtype == torch.uint8 else np.float32)
+    else:
+        dims, dtype = engine._plan[0][0], (np.uint8 if engine._plan[0][3] == 0 else np.float32)
+    nr, nc = engine.ens_begin(dims, window_size, overlap, dtype, device_ordered=True)
+    if b > a:
+        cm, sn = engine.ens_add(frames, window_size, overlap, corr_min=corr_min, s2n_min=s2n_min, signal_threshold=signal_threshold)
+        local = torch.stack([cm, sn]).view(2, b - a, nr, nc)
+    else:
+        local = torch.zeros((2, 0, nr, nc), dtype=torch.float32, device=dev)
+    plane, count = engine.ens_accumulators()
+    u, v, count = ensemble_reduce_finish(plane, count, lambda first, n: engine.ens_finish_device(min_count, first, n), group=group)
+    stats = gather_fields(local, n_pairs_total, table, group=group)          # [2, pairs_total, rows, cols]
+    count_np = count.cpu().numpy()
+    cm_mean, sn_mean = aggregate_ensemble(stats[0].reshape(n_pairs_total, -1).cpu().numpy(), stats[1].reshape(n_pairs_total, -1).cpu().numpy(),
+                                          count_np, min_count, nr, nc)
+    return u.cpu().numpy().reshape(1, nr, nc), v.cpu().numpy().reshape(1, nr, nc), cm_mean, sn_mean, count_np

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import gc
 import warnings
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -20,7 +20,7 @@ except Exception:  # pragma: no cover - exercised in this image
     from . import _xr as xr
 
 from . import window
-from .engine import get_engine
+from .engine import get_engine, merge_ensembles
 
 __all__ = ["get_b2piv", "load_frame_chunk"]
 
@@ -66,11 +66,19 @@ def get_b2piv(
     signal_threshold: Optional[float] = None,
     device: int = 0,
     coarse_pass: Optional[Tuple[Tuple[int, int], Tuple[int, int]]] = None,
+    devices: Optional[Sequence[int]] = None,
 ):
     """Time-resolved or ensemble PIV on the B200 engine; same contract as ``get_ffpiv`` (ffpiv.py:24-179).
 
     Returns a Dataset with ``s2n``, ``corr``, ``v_x``, ``v_y`` on ``(time, y, x)``; velocities in m/s
     (``u * res_x / dt``), float32.  ``engine`` must be ``"b200"``; ``device`` selects the GPU.
+
+    ``devices=[0, 1, ...]`` shards the work over several GPUs of the box from this ONE call: the frame pairs of
+    every chunk of the reference's chunk list (ffpiv.py:140-142) are cut into contiguous sub-ranges with the same 1-frame
+    halo, one per device, each handled by that device's engine on its own host thread (the ABI's "one engine per thread
+    and device"; a device named twice gets two engines); results are put back in time order.  Per-time-step results are bit-identical to ``devices=[0]`` (frame
+    pairs are independent); in ensemble mode the devices' plane sums are added before the peak fit (same result up to the
+    float32 summation order), and the count filter keeps using the reference's chunk count.
 
     ``coarse_pass=((wy, wx), (oy, ox))`` (no reference counterpart - ffpiv is single pass): two-pass PIV with a discrete
     window offset, BASELINE.json ``configs[2]``: a first pass on that coarse grid gives a validated, interpolated
@@ -95,11 +103,15 @@ def get_b2piv(
         raise NotImplementedError("search_area_size must equal window_size (pyorc/api/frames.py:168)")
     n_total = len(frames)
     dim_size = frames[0].shape
+    devices = [int(device)] if devices is None else [int(d) for d in devices]
+    if not devices:
+        raise ValueError("devices must name at least one GPU")
     req_mem = window.required_memory(
         n_frames=n_total, dim_size=dim_size, window_size=window_size, overlap=overlap, search_area_size=search_area_size
     )
     if chunksize is None:
-        avail_mem = window.available_memory() / memory_factor
+        # the smallest free HBM of the devices used sizes the chunks (every device holds one sub-range of a chunk at a time)
+        avail_mem = min(window.available_memory(d) for d in devices) / memory_factor
         chunks = int((req_mem // avail_mem) + 1)
         chunksize = int(np.ceil(n_total / chunks))
         if chunksize <= 5:
@@ -125,8 +137,9 @@ def get_b2piv(
     dt_vals = np.asarray(_values(dt), dtype=np.float64).reshape(-1)
     if dt_vals.size != n_total - 1:
         raise ValueError("dt must hold one interval per frame pair")
-    eng = get_engine(device)
-    common = (frames, bounds, times, dt_vals, y, x, res_y, res_x, n_rows, n_cols, window_size, overlap, eng)
+    # a device named k times gets k engines (slots): each engine is driven by one host thread only
+    engs = [get_engine(d, devices[:i].count(d)) if devices[:i].count(d) else get_engine(d) for i, d in enumerate(devices)]
+    common = (frames, bounds, times, dt_vals, y, x, res_y, res_x, n_rows, n_cols, window_size, overlap, engs)
     if coarse_pass is not None:
         if ensemble_corr:
             raise NotImplementedError("coarse_pass (two-pass PIV) is available in per-time-step mode only")
@@ -151,14 +164,65 @@ def _get_uv_timestep(da, n_cols, n_rows, window_size, overlap, search_area_size,
     return u, v, corr_max, s2n
 
 
-def _get_b2piv_timestep(frames, bounds, times, dt_vals, y, x, res_y, res_x, n_rows, n_cols, window_size, overlap, eng,
+def _work_items(bounds, n_dev):
+    """Cut every chunk ``(a, b)`` (frames a .. b-1, pairs a .. b-2) into at most ``n_dev`` contiguous sub-ranges of frame
+    pairs, each with its 1-frame halo (the rule of ffpiv.py:140 applied once more): ``[(chunk index, a_k, b_k)]`` in time
+    order.  One device -> the reference's chunk list unchanged."""
+    items = []
+    for c, (a, b) in enumerate(bounds):
+        n_pairs = b - a - 1
+        parts = max(1, min(n_dev, n_pairs))
+        base, rem = divmod(n_pairs, parts)
+        p0 = a
+        for k in range(parts):
+            p1 = p0 + base + (1 if k < rem else 0)
+            items.append((c, p0, p1 + 1))
+            p0 = p1
+    return items
+
+
+def _run_items(items, engs, job):
+    """``job(item, engine)`` for every work item; item i runs on device i % D.  One host thread per device, each working
+    through ITS items in order (an engine is used by one thread only); the first exception is re-raised.  Returns the results
+    in item order."""
+    n_dev = len(engs)
+    results = [None] * len(items)
+    if n_dev == 1:
+        for i, it in enumerate(items):
+            results[i] = job(it, engs[0])
+        return results
+    import threading
+
+    errors = []
+
+    def worker(k):
+        try:
+            for i in range(k, len(items), n_dev):
+                if errors:
+                    return
+                results[i] = job(items[i], engs[k])
+        except BaseException as exc:  # noqa: BLE001 - re-raised in the caller's thread
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(k,), name=f"b2piv-dev{engs[k].device}") for k in range(min(n_dev, len(items)))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return results
+
+
+def _get_b2piv_timestep(frames, bounds, times, dt_vals, y, x, res_y, res_x, n_rows, n_cols, window_size, overlap, engs,
                         signal_threshold, coarse_pass=None):
     """Per-time-step mode (ffpiv.py:379-443)."""
-    ds_piv_chunks = []
-    for a, b in bounds:
+
+    def job(item, eng):
+        _, a, b = item
         da = load_frame_chunk(frames[a:b])
         if len(da) < 2:
-            continue
+            return None
         b = a + len(da)
         time = times[a + 1 : b]
         dt_chunk = dt_vals[a : b - 1]
@@ -174,44 +238,59 @@ def _get_b2piv_timestep(frames, bounds, times, dt_vals, y, x, res_y, res_x, n_ro
             },
             coords={"time": time, "y": y, "x": x},
         )
-        ds_piv_chunks.append(ds)
         del da
-        gc.collect()
+        return ds
+
+    if signal_threshold is not None and len(engs) > 1:
+        # the reference scores a window over ALL frames of a chunk (ffpiv.py:93-97): sub-ranges would change the score
+        engs = engs[:1]
+    ds_piv_chunks = [ds for ds in _run_items(_work_items(bounds, len(engs)), engs, job) if ds is not None]
+    gc.collect()
     return xr.concat(ds_piv_chunks, dim="time")
 
 
-def _get_b2piv_mean(frames, bounds, times, dt_vals, y, x, res_y, res_x, n_rows, n_cols, window_size, overlap, eng,
+def _get_b2piv_mean(frames, bounds, times, dt_vals, y, x, res_y, res_x, n_rows, n_cols, window_size, overlap, engs,
                     corr_min, s2n_min, count_min, signal_threshold):
-    """Ensemble-correlation mode (ffpiv.py:182-376): thresholds and plane sums on the device, the tiny
+    """Ensemble-correlation mode (ffpiv.py:182-376): thresholds and plane sums on the device(s), the tiny
     per-pair statistics aggregated on the host exactly like ``aggregate_results``."""
-    corr_chunks, s2n_chunks = [], []
-    time = None
-    opened = False
-    for a, b in bounds:
+    from .parallel import aggregate_ensemble
+
+    if signal_threshold is not None and len(engs) > 1:
+        engs = engs[:1]   # see _get_b2piv_timestep
+    items = _work_items(bounds, len(engs))
+    opened = set()      # id() of the engines that hold accumulators of this call
+    chunk_seen = set()
+
+    def job(item, eng):
+        c, a, b = item
         da = load_frame_chunk(frames[a:b])
         if len(da) < 2:
-            continue
+            return None
         vals = _values(da)
-        if not opened:
+        if id(eng) not in opened:
             dtype = vals.dtype if vals.dtype in (np.uint8, np.float32) else np.float32
             eng.ens_begin(vals.shape[-2:], window_size, overlap, dtype)
-            opened = True
-        time = times[a + 1 : a + len(da)]
+            opened.add(id(eng))
+        chunk_seen.add(c)
         corr_max, s2n = eng.ens_add(vals, window_size, overlap, corr_min=corr_min, s2n_min=s2n_min, signal_threshold=signal_threshold)
-        corr_chunks.append(corr_max)
-        s2n_chunks.append(s2n)
         del da
-        gc.collect()
+        return corr_max, s2n
+
+    results = _run_items(items, engs, job)
+    done = [(it, r) for it, r in zip(items, results) if r is not None]
+    corr_chunks = [r[0] for _, r in done]
+    s2n_chunks = [r[1] for _, r in done]
+    # time coordinate: first stamp of the last chunk processed (ffpiv.py:336: time[0:1] of the last loop iteration)
+    c_last = max(c for (c, _, _), _ in done)
+    a_last = min(a for (c, a, _), _ in done if c == c_last)
+    time = times[a_last + 1 : a_last + 2]
+    gc.collect()
     dt_av = dt_vals.mean()
-    n_frames = len(corr_chunks)  # number of CHUNKS, as in the reference (ffpiv.py:373)
-    u, v, corr_count = eng.ens_finish(count_min * n_frames)
-    s2n_concat = np.concatenate(s2n_chunks, axis=0)
-    corr_max_concat = np.concatenate(corr_chunks, axis=0)
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore", category=RuntimeWarning)
-        corr_max_concat[:, corr_count < count_min * n_frames] = np.nan
-        corr_max_mean = np.nanmean(corr_max_concat, axis=0).reshape(-1, n_rows, n_cols)
-        s2n_mean = np.nanmean(s2n_concat, axis=0).reshape(-1, n_rows, n_cols)
+    n_frames = len(chunk_seen)  # number of CHUNKS, as in the reference (ffpiv.py:373) - not of device sub-ranges
+    used = [e for e in engs if id(e) in opened]
+    u, v, corr_count = merge_ensembles(used, count_min * n_frames)
+    corr_max_mean, s2n_mean = aggregate_ensemble(np.concatenate(corr_chunks, axis=0), np.concatenate(s2n_chunks, axis=0), corr_count,
+                                                 count_min * n_frames, n_rows, n_cols)
     u = (u.reshape(-1, n_rows, n_cols) * res_x / dt_av).astype(np.float32)
     v = (v.reshape(-1, n_rows, n_cols) * res_y / dt_av).astype(np.float32)
     return xr.Dataset(
@@ -221,5 +300,5 @@ def _get_b2piv_mean(frames, bounds, times, dt_vals, y, x, res_y, res_x, n_rows, 
             "v_x": (["time", "y", "x"], u),
             "v_y": (["time", "y", "x"], v),
         },
-        coords={"time": time[0:1], "y": y, "x": x},
+        coords={"time": time, "y": y, "x": x},
     )

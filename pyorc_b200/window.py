@@ -67,11 +67,11 @@ def required_memory(n_frames, dim_size, window_size, overlap, search_area_size=N
     return safety * (n_frames * dim_size[0] * dim_size[1] * itemsize + max(n_frames - 1, 0) * n_rows * n_cols * 16)
 
 
-def available_memory() -> float:
-    """Free HBM of the current CUDA device in bytes (ffpiv.py:129 asks for free host RAM)."""
+def available_memory(device=None) -> float:
+    """Free HBM in bytes of CUDA device ``device`` (default: the current one); ffpiv.py:129 asks for free host RAM."""
     import torch
 
     if not torch.cuda.is_available():
         raise RuntimeError("pyorc_b200 needs a CUDA device (no CPU fallback)")
-    free, _total = torch.cuda.mem_get_info()
+    free, _total = torch.cuda.mem_get_info() if device is None else torch.cuda.mem_get_info(int(device))
     return float(free)

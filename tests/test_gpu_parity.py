@@ -528,3 +528,149 @@ def test_pageable_and_pinned_host_frames_give_identical_results(engine):
     p32[...] = f32
     b = engine.pairs(p32, (32, 32), (16, 16))
     assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(a, b))
+
+
+# ---- round 2: multi-engine / multi-device binding, stream-ordered ensemble, install() with the real engine ------------------
+def _golden_frames():
+    import os
+
+    from pyorc_b200 import _xr
+
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ngwerere_proj.npz"))
+    fr, t, res = d["frames"], d["time_s"], float(d["resolution"])
+    H, W = fr.shape[1:]
+    y = np.flipud(np.linspace(res / 2, res * (H - 0.5), H))
+    x = np.linspace(res / 2, res * (W - 0.5), W)
+    return _xr.DataArray(fr, ("time", "y", "x"), {"time": t, "y": y, "x": x}), res, d["pinned_vx_timestep"], d["pinned_vx_ensemble"]
+
+
+def test_get_b2piv_devices_equals_single_engine():
+    """`get_b2piv(devices=[...])`: sub-ranges of every chunk on several engines (here three engines on cuda:0, one host thread
+    each) give the Dataset of a single engine - bit-identical per time step, equal up to float32 summation order in ensemble mode."""
+    from pyorc_b200 import _xr, velocimetry
+
+    n = 14
+    imgs = synth.particle_frames(n, 200, 304, dtype=np.uint8)
+    da = _xr.DataArray(imgs, ("time", "y", "x"), {"time": np.arange(n) / 30.0})
+    ws, ov = (64, 64), (32, 32)
+    nr, nc = O.get_array_shape(imgs.shape[-2:], ws, ov)
+    args = (da, np.arange(nr), np.arange(nc), np.full(n - 1, 1 / 30), ws, ov, ws, 0.01, 0.01)
+    one = velocimetry.get_b2piv(*args, chunksize=8)
+    many = velocimetry.get_b2piv(*args, chunksize=8, devices=[0, 0, 0])
+    for k in ("v_x", "v_y", "corr", "s2n"):
+        assert np.array_equal(one[k].values, many[k].values, equal_nan=True), k
+    assert np.array_equal(one.coords["time"], many.coords["time"])
+    kw = dict(ensemble_corr=True, corr_min=0.1, s2n_min=1.5, count_min=0.2, chunksize=8)
+    one = velocimetry.get_b2piv(*args, **kw)
+    many = velocimetry.get_b2piv(*args, **kw, devices=[0, 0, 0])
+    assert np.isfinite(one["v_x"].values).mean() > 0.9
+    for k in ("corr", "s2n"):
+        assert np.array_equal(one[k].values, many[k].values, equal_nan=True), k
+    for k in ("v_x", "v_y"):
+        assert np.array_equal(np.isnan(one[k].values), np.isnan(many[k].values))
+        assert np.nanmax(np.abs(one[k].values - many[k].values)) <= 2e-3 * 0.01 * 30      # 2e-3 px / frame in m / s
+
+
+def test_ensemble_is_stream_ordered_without_host_synchronisation(engine):
+    """begin / add / finish on different streams: accumulate device frames on a side stream behind a long
+    dependency, then finish at once on the engine's stream (host call) and on torch's current stream (device call) - both must
+    wait for the accumulation and equal the fully synchronous result."""
+    import torch
+
+    imgs = synth.particle_frames(9, 270, 400, dtype=np.uint8)
+    ws, ov = (64, 64), (32, 32)
+    engine.set_option("clip_normalized", 0.0)
+    engine.set_option("kernel_variant", 0.0)
+    engine.ens_begin(imgs.shape[-2:], ws, ov, np.uint8)
+    engine.ens_add(imgs, ws, ov, corr_min=0.1, s2n_min=1.5)
+    u0, v0, c0 = engine.ens_finish(0.2)
+    d = torch.from_numpy(imgs).cuda()
+    side = torch.cuda.Stream()
+    big = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for finish_on_device in (False, True):
+        torch.cuda.synchronize()
+        engine.ens_begin(imgs.shape[-2:], ws, ov, np.uint8, device_ordered=True)     # zero-fill on torch's current stream
+        with torch.cuda.stream(side):
+            for _ in range(20):
+                big.add_(1)                                                             # keeps the side stream busy for a while
+            engine.ens_add(d, ws, ov, corr_min=0.1, s2n_min=1.5)                        # launched behind it, not awaited
+        if finish_on_device:
+            ut, vt = engine.ens_finish_device(0.2)
+            u, v = ut.cpu().numpy(), vt.cpu().numpy()
+        else:
+            u, v, c = engine.ens_finish(0.2)
+            assert np.array_equal(c, c0)
+        assert np.array_equal(u, u0, equal_nan=True) and np.array_equal(v, v0, equal_nan=True)
+    torch.cuda.synchronize()
+
+
+def test_ensemble_window_slices_finish_like_the_whole(engine):
+    """`ens_finish_device(first, n)` on window slices (what a rank does after the reduce-scatter) = the whole-field finish."""
+    from pyorc_b200 import parallel
+
+    imgs = synth.particle_frames(5, 270, 400, dtype=np.uint8)
+    ws, ov = (32, 32), (16, 16)
+    nr, nc = engine.ens_begin(imgs.shape[-2:], ws, ov, np.uint8)
+    engine.ens_add(imgs, ws, ov, corr_min=0.1, s2n_min=1.5)
+    u0, v0, _ = engine.ens_finish(0.2)
+    for world in (2, 3, 8):
+        u = np.empty_like(u0)
+        v = np.empty_like(v0)
+        for a, b in parallel.window_slices(nr * nc, world):
+            ut, vt = engine.ens_finish_device(0.2, int(a), int(b - a))
+            u[a:b], v[a:b] = ut.cpu().numpy(), vt.cpu().numpy()
+        assert np.array_equal(u, u0, equal_nan=True) and np.array_equal(v, v0, equal_nan=True)
+
+
+def test_install_dispatch_real_engine(monkeypatch):
+    """`pyorc_b200.frames.install()` on a pyorc-shaped module pair (the real pyorc cannot travel to this box - see
+    tests/test_reference_dropin.py for its own body): `Frames.get_piv(engine="b200")` reaches the CUDA engine through the
+    patched `pyorc.velocimetry.ffpiv.get_ffpiv` call site and reproduces pyorc's pinned vectors (tests/test_frames.py:139-153)."""
+    import sys
+    import types
+
+    from pyorc_b200 import frames as b2frames, window
+
+    da, res, pin_ts, pin_ens = _golden_frames()
+    calls = []
+    ffpiv_mod = types.ModuleType("pyorc.velocimetry.ffpiv")
+
+    def get_ffpiv(frames, y, x, dt, *a, **kw):       # stands for the reference's CPU arm
+        calls.append(kw.get("engine"))
+        raise RuntimeError("reference arm reached")
+
+    ffpiv_mod.get_ffpiv = get_ffpiv
+    frames_mod = types.ModuleType("pyorc.api.frames")
+
+    class Frames:                                      # the call site of pyorc/api/frames.py:156-188, nothing else
+        def __init__(self, obj):
+            self._obj = obj
+
+        def get_piv(self, window_size=None, overlap=None, engine="numba", ensemble_corr=False, **kwargs):
+            dt = self._obj["time"].diff(dim="time")
+            ws = window.round_to_even(2 * (window_size,))
+            if overlap is None:
+                overlap = 2 * (int(round(window_size) / 2),)
+            cols, rows = window.get_rect_coordinates(dim_size=self._obj[0].shape, window_size=ws, search_area_size=ws, overlap=overlap)
+            if engine not in ["numba", "numpy"]:
+                raise ValueError(f"Selected PIV engine {engine} does not exist.")
+            kwargs = {**kwargs, "search_area_size": ws, "window_size": ws, "overlap": overlap, "res_x": res, "res_y": res}
+            return ffpiv_mod.get_ffpiv(self._obj, self._obj.y.values[rows], self._obj.x.values[cols], dt, engine=engine,
+                                       ensemble_corr=ensemble_corr, **kwargs)
+
+    frames_mod.Frames = Frames
+    for name, m in {"pyorc": types.ModuleType("pyorc"), "pyorc.api": types.ModuleType("pyorc.api"), "pyorc.api.frames": frames_mod,
+                    "pyorc.velocimetry": types.ModuleType("pyorc.velocimetry"), "pyorc.velocimetry.ffpiv": ffpiv_mod}.items():
+        monkeypatch.setitem(sys.modules, name, m)
+    assert b2frames.install()
+    try:
+        for ens, pin in ((False, pin_ts), (True, pin_ens)):
+            piv = Frames(da).get_piv(window_size=10, engine="b200", ensemble_corr=ens, s2n_min=0, corr_min=0, count_min=0, devices=[0, 0])
+            got = piv.mean(dim="time", keep_attrs=True)["v_x"].values.flatten()[-4:]
+            assert np.allclose(got, pin, rtol=0, atol=2e-6, equal_nan=True), (got, pin)
+        assert calls == []
+        with pytest.raises(RuntimeError, match="reference arm reached"):
+            Frames(da).get_piv(window_size=10, engine="numba")
+        assert calls == ["numba"]
+    finally:
+        b2frames.uninstall()

@@ -12,8 +12,9 @@ from pyorc_b200 import _xr, frames as b2frames, synth, velocimetry, window
 class FakeEngine:
     """Test double with the Engine interface, computing with the oracle (never used by the product)."""
 
-    def __init__(self):
-        self.calls = []
+    def __init__(self, device=0, log=None):
+        self.device = device
+        self.calls = [] if log is None else log
 
     def pairs(self, imgs, ws, ov, signal_threshold=None, stream=None):
         self.calls.append(np.asarray(imgs).shape[0])
@@ -35,6 +36,7 @@ class FakeEngine:
         return nr, nc
 
     def ens_add(self, imgs, ws, ov, corr_min=0.2, s2n_min=3.0, signal_threshold=None, stream=None):
+        self.calls.append(("ens", np.asarray(imgs).shape[0]))
         if self._ens is None:
             self._ens = O.Ensemble(*self._shape, ws, ov, corr_min, s2n_min, 0.0, signal_threshold)
         self._ens.add_chunk(np.asarray(imgs))
@@ -54,8 +56,24 @@ class FakeEngine:
 @pytest.fixture()
 def fake(monkeypatch):
     fe = FakeEngine()
-    monkeypatch.setattr(velocimetry, "get_engine", lambda device=0: fe)
-    monkeypatch.setattr(window, "available_memory", lambda: 64e9)
+    fakes = {0: fe}
+
+    def get_engine(device=0, slot=0):   # one fake per (device, slot), sharing device 0's call log
+        key = device if slot == 0 else (device, slot)
+        if key not in fakes:
+            fakes[key] = FakeEngine(device, fe.calls)
+        return fakes[key]
+
+    def merge(engines, min_count):   # numpy stand-in for engine.merge_ensembles (peer adds + peak fit on the first device)
+        e0 = engines[0]
+        for e in engines[1:]:
+            e0._ens.corr_sum = e0._ens.corr_sum + e._ens.corr_sum
+            e0._ens.corr_count = e0._ens.corr_count + e._ens.corr_count
+        return e0.ens_finish(min_count)
+
+    monkeypatch.setattr(velocimetry, "get_engine", get_engine)
+    monkeypatch.setattr(velocimetry, "merge_ensembles", merge)
+    monkeypatch.setattr(window, "available_memory", lambda device=None: 64e9)
     O.CLIP_NORMALIZED = True
     return fe
 
@@ -118,7 +136,7 @@ def test_chunksize_errors_and_warning(fake, monkeypatch):
     y, x = np.arange(nr), np.arange(nc)
     with pytest.raises(OverflowError):
         velocimetry.get_b2piv(da, y, x, np.full(5, 1 / 30), (32, 32), (16, 16), (32, 32), res, res, chunksize=1)
-    monkeypatch.setattr(window, "available_memory", lambda: 1e5)   # tiny "device" -> chunksize floor 5 + warning
+    monkeypatch.setattr(window, "available_memory", lambda device=None: 1e5)   # tiny "device" -> chunksize floor 5 + warning
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter("always")
         ds = velocimetry.get_b2piv(da, y, x, np.full(5, 1 / 30), (32, 32), (16, 16), (32, 32), res, res)
@@ -222,3 +240,63 @@ def test_coarse_pass_routes_chunks_through_the_two_pass_engine(fake):
     with pytest.raises(ValueError):
         velocimetry.get_b2piv(da, y, x, np.full(5, 1 / 30), ws, ov, ws, res, res, coarse_pass=((16, 16), (8, 8)))
     O.CLIP_NORMALIZED = True
+
+
+# ---- devices=[...]: one call, several GPUs ------------------------------------------------------------------
+def test_work_items_cover_every_pair_once_with_halo():
+    for bounds in ([(0, 11)], [(0, 4), (3, 8), (7, 11)], [(0, 2)], [(0, 3), (2, 4)]):
+        for n_dev in (1, 2, 3, 8):
+            items = velocimetry._work_items(bounds, n_dev)
+            pairs = [p for _, a, b in items for p in range(a, b - 1)]
+            assert pairs == [p for a, b in bounds for p in range(a, b - 1)]
+            assert all(b - a >= 2 for _, a, b in items)
+            if n_dev == 1:
+                assert [(a, b) for _, a, b in items] == list(bounds)
+            for c, (a, b) in enumerate(bounds):
+                assert len([1 for cc, _, _ in items if cc == c]) == min(n_dev, b - a - 1)
+
+
+@pytest.mark.parametrize("devices", [[0, 1], [0, 1, 2], list(range(8)), [0, 0, 1]])
+def test_devices_sharding_equals_single_device(fake, devices):
+    da, res = make_frames(n=11)
+    nr, nc = O.get_array_shape((100, 140), (32, 32), (16, 16))
+    y, x = np.arange(nr), np.arange(nc)
+    args = (da, y, x, np.full(10, 1 / 30), (32, 32), (16, 16), (32, 32), res, res)
+    one = velocimetry.get_b2piv(*args, chunksize=6)
+    fake.calls.clear()
+    many = velocimetry.get_b2piv(*args, chunksize=6, devices=devices)
+    assert sum(n - 1 for n in fake.calls) == 10 and len(fake.calls) == min(len(devices), 5) * 2
+    for k in ("v_x", "v_y", "corr", "s2n"):
+        assert np.array_equal(one[k].values, many[k].values, equal_nan=True)
+    assert np.array_equal(one.coords["time"], many.coords["time"])
+
+
+def test_devices_sharding_ensemble_equals_single_device(fake):
+    da, res = make_frames(n=9)
+    nr, nc = O.get_array_shape((100, 140), (32, 32), (16, 16))
+    y, x = np.arange(nr), np.arange(nc)
+    args = (da, y, x, np.full(8, 1 / 30), (32, 32), (16, 16), (32, 32), res, res)
+    kw = dict(ensemble_corr=True, corr_min=0.1, s2n_min=1.0, count_min=0.2, chunksize=5)
+    one = velocimetry.get_b2piv(*args, **kw)
+    many = velocimetry.get_b2piv(*args, **kw, devices=[0, 1, 2])
+    assert np.isfinite(one["v_x"].values).sum() > 0
+    for k in ("corr", "s2n"):
+        assert np.array_equal(one[k].values, many[k].values, equal_nan=True)
+    for k in ("v_x", "v_y"):   # plane sums are added in a different order: float32 rounding of the sums only
+        assert np.array_equal(np.isnan(one[k].values), np.isnan(many[k].values))
+        assert np.nanmax(np.abs(one[k].values - many[k].values)) < 1e-4
+    assert np.array_equal(one.coords["time"], many.coords["time"])
+
+
+def test_device_thread_errors_propagate(fake):
+    da, res = make_frames(n=6)
+    nr, nc = O.get_array_shape((100, 140), (32, 32), (16, 16))
+    with pytest.raises(ValueError, match="do not match"):
+        velocimetry.get_b2piv(da, np.arange(nr + 1), np.arange(nc), np.full(5, 1 / 30), (32, 32), (16, 16), (32, 32), res, res, devices=[0, 1])
+
+    def boom(*a, **k):
+        raise RuntimeError("device lost")
+
+    velocimetry.get_engine(1).pairs = boom
+    with pytest.raises(RuntimeError, match="device lost"):
+        velocimetry.get_b2piv(da, np.arange(nr), np.arange(nc), np.full(5, 1 / 30), (32, 32), (16, 16), (32, 32), res, res, devices=[0, 1])

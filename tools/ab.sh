@@ -3,6 +3,6 @@
 for i in 1 2; do
   for lib in "$@"; do
     echo "== $lib"
-    B2PIV_LIB=$PWD/$lib python tools/quick_bench.py --configs 2>&1 | sed -n '2,3p;5,6p' | sed 's/variant 0 run_len 0 groups 0 rolled 0 //'
+    B2PIV_LIB=$PWD/$lib python tools/quick_bench.py --configs 2>&1 | sed -n '2,3p;5,6p' | sed 's/variant 0 run_len 0  //'
   done
 done

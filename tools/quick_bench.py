@@ -93,20 +93,15 @@ if __name__ == "__main__":
         run(4320, 7680, (128, 128), (64, 64), 6, dtype="float32")
         sys.exit(0)
     if "--single" in sys.argv:
-        run(1080, 1920, (64, 64), (32, 32), 21, reps=2, variant=int(os.environ.get("B2_VARIANT", "0")), groups=int(os.environ.get("B2_GROUPS", "0")), rolled=int(os.environ.get("B2_ROLLED", "0")))
+        run(1080, 1920, (64, 64), (32, 32), 21, reps=2, variant=int(os.environ.get("B2_VARIANT", "0")))
         sys.exit(0)
     if "--variants" in sys.argv:
         run(1080, 1920, (64, 64), (32, 32), 101, variant=1)
-        for rolled in (0, 1):
-            for g in (1, 2, 4):
-                run(1080, 1920, (64, 64), (32, 32), 101, variant=2, groups=g, rolled=rolled)
-        run(1080, 1920, (64, 64), (32, 32), 101, variant=2, groups=4, rolled=0, run_len=50)
-        run(1080, 1920, (64, 64), (32, 32), 101, variant=2, groups=1, rolled=0, run_len=50)
+        run(1080, 1920, (64, 64), (32, 32), 101, variant=2)
+        run(1080, 1920, (64, 64), (32, 32), 101, variant=2, run_len=50)
         run(2160, 3840, (64, 64), (32, 32), 41, variant=2)
         run(1080, 1920, (32, 32), (16, 16), 41, variant=1)
-        for rolled in (0, 1):
-            for g in (1, 4, 12):
-                run(1080, 1920, (32, 32), (16, 16), 41, variant=2, groups=g, rolled=rolled)
+        run(1080, 1920, (32, 32), (16, 16), 41, variant=2)
         run(1080, 1920, (32, 32), (24, 24), 11, variant=0)
         run(1080, 1920, (64, 64), (32, 32), 51, variant=0, dtype="float32")
         run(1080, 1920, (64, 64), (32, 32), 51, variant=1, dtype="float32")

@@ -218,6 +218,10 @@ void b2piv_host_free(void* p);
  * number of kernels this engine has launched since creation. */
 int b2piv_last_kernel_ms(const b2piv_engine* e, float* ms);
 long long b2piv_launch_count(const b2piv_engine* e);
+/* Measured fp32 FMA throughput of the engine's device in TFLOP/s (independent FFMA chains, `iters` per thread and chain,
+ * best of 4 runs): the denominator of the fp32 fraction bench.py reports for the fused kernels, which are bound by fp32
+ * issue rather than HBM. */
+int b2piv_fp32_peak(b2piv_engine* e, int iters, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -338,17 +338,44 @@ def _pair_job(args):
     return u[0], v[0], corr_max.reshape(n_rows, n_cols).astype(np.float32), s2n.reshape(n_rows, n_cols).astype(np.float32)
 
 
-def cpu_reference_pairs(imgs, window_size, overlap, workers=None):
+def cpu_reference_pairs(imgs, window_size, overlap, workers=None, pool=None):
     """The reference's per-time-step CPU path on ``imgs`` using all host cores the way ffpiv's numba engine does
-    (``prange`` over frame pairs): one thread per frame pair (numpy and pocketfft release the GIL), each doing
-    gather -> normalise -> rfft2.conj.irfft2 -> fftshift,/N,clip -> f32 corr -> nanmax, nanmean -> argmax + Gaussian,
-    i.e. the same passes over memory pyorc performs (ffpiv.py:446-474)."""
+    (``prange`` over frame pairs): one worker per frame pair, each doing gather -> normalise -> rfft2.conj.irfft2 ->
+    fftshift,/N,clip -> f32 corr -> nanmax, nanmean -> argmax + Gaussian, i.e. the same passes over memory pyorc performs
+    (ffpiv.py:446-474).  ``pool``: a :func:`make_pool` PROCESS pool (every core busy: the window gather is numpy fancy indexing
+    and holds the GIL, so threads top out at a fraction of the cores - round 1 measured 16 threads of 32 cores, and a 128-core box
+    SLOWER than a 16-core one); without a pool: threads."""
     from concurrent.futures import ThreadPoolExecutor
 
     imgs = np.asarray(imgs)
-    workers = workers or os.cpu_count() or 1
     n_rows, n_cols = get_array_shape(imgs.shape[-2:], window_size, overlap)
     jobs = [(imgs[k], imgs[k + 1], tuple(window_size), tuple(overlap), n_rows, n_cols) for k in range(imgs.shape[0] - 1)]
-    with ThreadPoolExecutor(max_workers=max(1, min(workers, len(jobs)))) as ex:
-        res = list(ex.map(_pair_job, jobs))
+    if pool is not None:
+        res = list(pool.map(_pair_job, jobs))
+    else:
+        workers = workers or os.cpu_count() or 1
+        with ThreadPoolExecutor(max_workers=max(1, min(workers, len(jobs)))) as ex:
+            res = list(ex.map(_pair_job, jobs))
     return tuple(np.stack([r[i] for r in res]) for i in range(4))
+
+
+def _pool_warm(_):
+    import time
+
+    np.fft.rfft2(np.zeros((8, 8)))
+    time.sleep(0.05)   # keeps the worker busy long enough for every worker of the pool to take one warm-up job
+    return os.getpid()
+
+
+def make_pool(workers=None):
+    """Process pool (fork) for :func:`cpu_reference_pairs`, every worker started and warmed.  Create it BEFORE the parent
+    initialises CUDA (bench.py does): the children only ever run numpy."""
+    import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
+
+    workers = workers or os.cpu_count() or 1
+    pool = ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("fork"))
+    pids = set(pool.map(_pool_warm, range(4 * workers)))
+    pool.n_workers = workers
+    pool.n_started = len(pids)
+    return pool

@@ -495,4 +495,52 @@ int b2piv_predictor_device(b2piv_engine* e, const float* d_u1, const float* d_v1
     return B2PIV_OK;
 }
 
+// ---- fp32 FMA peak of this device, measured (bench.py's `fp32.peak_measured`; tools/fp32_peak.py) --------------------------------
+// The fused PIV kernels are bound by fp32 issue, not by HBM, and MEASURED_PEAKS.json holds only the HBM and
+// bf16 tensor peaks: this is the missing denominator.  Every thread runs 16 independent FFMA chains (enough to cover the
+// 4-cycle dependent-issue latency with 8 warps per scheduler); 2 flop per FFMA.
+}  // extern "C"
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float a, float b) {
+    float x[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x[k] = (float)(threadIdx.x + k) * 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = fmaf(x[k], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += x[k];
+    if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // never true: keeps the chains alive
+}
+extern "C" {
+
+int b2piv_fp32_peak(b2piv_engine* e, int iters, double* tflops) {
+    if (!e || !tflops) return B2PIV_ERR_ARG;
+    if (iters < 1) return fail(e, B2PIV_ERR_ARG, "iters must be >= 1");
+    CK(cudaSetDevice(e->device));
+    int rc = ensure(e, &e->d_mask_ws, &e->cap_mask_ws, (size_t)e->sm_count * 8 * 256 * sizeof(float));
+    if (rc) return rc;
+    const int grid = e->sm_count * 8;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {   // first repetition warms up
+        CK(cudaEventRecord(a, e->s_comp));
+        fp32_peak_kernel<<<grid, 256, 0, e->s_comp>>>(e->d_mask_ws, iters, 0.999f, 1e-3f);
+        CK(cudaEventRecord(b, e->s_comp));
+        CK(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    CK(cudaEventDestroy(a));
+    CK(cudaEventDestroy(b));
+    CK(cudaGetLastError());
+    e->launches += 5;
+    *tflops = 2.0 * 16.0 * (double)iters * 256.0 * grid / ((double)best * 1e-3) / 1e12;
+    return B2PIV_OK;
+}
+
 }  // extern "C"

@@ -66,6 +66,7 @@ ABI_SYMBOLS = (
     "b2piv_host_free",
     "b2piv_last_kernel_ms",
     "b2piv_launch_count",
+    "b2piv_fp32_peak",
 )
 
 
@@ -132,6 +133,7 @@ def load_library(path: Optional[str] = None):
     lib.b2piv_last_kernel_ms.argtypes = [vp, fp]
     lib.b2piv_launch_count.argtypes = [vp]
     lib.b2piv_launch_count.restype = cll
+    lib.b2piv_fp32_peak.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_double)]
     for name in ABI_SYMBOLS:
         getattr(lib, name)
     if path == _LIB_PATH:
@@ -273,6 +275,12 @@ class Engine:
         ms = ctypes.c_float()
         self._check(self._lib.b2piv_last_kernel_ms(self._h, ctypes.byref(ms)), "b2piv_last_kernel_ms")
         return float(ms.value)
+
+    def fp32_peak(self, iters: int = 20000) -> float:
+        """Measured fp32 FMA throughput of this device in TFLOP/s (micro-benchmark of independent FFMA chains)."""
+        t = ctypes.c_double()
+        self._check(self._lib.b2piv_fp32_peak(self._h, int(iters), ctypes.byref(t)), "b2piv_fp32_peak")
+        return float(t.value)
 
     def pinned_empty(self, shape, dtype=np.uint8) -> np.ndarray:
         """A page-locked numpy array (freed with the engine) - H2D at full PCIe rate."""

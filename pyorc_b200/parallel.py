@@ -80,39 +80,104 @@ def gather_fields(local, n_pairs_total: int, table: np.ndarray, group=None):
 class PeerGather:
     """The result gather fused into the PIV kernel: every rank's kernel stores its 16 B / window straight into the gather
     buffer of EVERY rank (torch symmetric memory = peer-mapped HBM over NVLink / NVSwitch), so no collective follows the
-    compute - only a cross-rank barrier before the buffer is read.
+    compute - only a cross-rank completion barrier before a buffer is read.
 
-        pg = PeerGather(engine, n_pairs_total, table)       # after engine.plan(...); collective (rendezvous)
-        engine.pairs(d_frames_of_this_rank, ws, ov)          # results land in pg.out on every rank
-        pg.wait()                                            # device-side barrier on the current stream
-        fields = pg.out                                      # [4, n_pairs_total, rows, cols]
+    The buffers form a ring of ``depth`` slots and the barrier runs on a separate high-priority CONSUMER stream, so the compute
+    stream never waits for the other ranks in steady state (round 1 had one buffer and a barrier on the compute stream after
+    every step: 6 % of an 8-GPU step):
 
-    The NCCL path (:func:`gather_fields`) remains for ragged use and for backends without peer access (gloo tests)."""
+        pg = PeerGather(engine, n_pairs_total, table)        # after engine.plan(...); collective (rendezvous)
+        for step in ...:
+            pg.begin()                                        # next slot; waits only if that slot is still being read anywhere
+            engine.pairs(d_frames_of_this_rank, ws, ov)       # results land in the slot on every rank
+            fields, ready = pg.end()                          # consumer stream: this rank's kernel done -> barrier -> `ready`
+            ...                                               # whoever reads `fields` [4, n_pairs_total, rows, cols] first waits
+                                                              # for `ready` (stream.wait_event / ready.synchronize())
+        pg.wait()                                             # or: make the current stream wait for the last slot (blocking use)
 
-    def __init__(self, engine, n_pairs_total: int, table: np.ndarray, group=None):
+    Slot reuse: step s + depth writes the slot of step s.  It may start once every rank has stopped reading that slot, which a
+    rank has (in consumer-stream order) when it reaches the barrier of step s + 1; so ``begin`` makes the compute stream wait
+    for the local ``ready`` event of step s + 1 - with ``depth = 3`` that is two steps behind the compute.  A consumer reads a slot
+    on the consumer stream (``with torch.cuda.stream(pg.consumer)``) or makes the consumer stream wait for its read before the
+    next ``end()``.  The NCCL path (:func:`gather_fields`) remains for ragged use and for backends without peer access."""
+
+    def __init__(self, engine, n_pairs_total: int, table: np.ndarray, group=None, depth: int = 3):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
 
         if engine._plan is None:
             raise RuntimeError("plan the engine before creating a PeerGather")
+        if depth < 2:
+            raise ValueError("depth >= 2 (a slot is rewritten only after the barrier of the NEXT step, see the class docstring)")
         rows, cols = engine._plan[1]
         group = group if group is not None else dist.group.WORLD
         rank = dist.get_rank(group)
-        self.engine = engine
-        self.out = symm_mem.empty((4, int(n_pairs_total), rows, cols), dtype=torch.float32, device=torch.device("cuda", engine.device))
-        self.handle = symm_mem.rendezvous(self.out, group)
-        ptrs = [int(p) for p in self.handle.buffer_ptrs]
-        if len(ptrs) > 8:
+        dev = torch.device("cuda", engine.device)
+        self.engine, self.depth, self.n_pairs_total, self.pair_offset = engine, int(depth), int(n_pairs_total), int(table[rank, 0])
+        self.ring = symm_mem.empty((self.depth, 4, self.n_pairs_total, rows, cols), dtype=torch.float32, device=dev)
+        self.handle = symm_mem.rendezvous(self.ring, group)
+        self._ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(self._ptrs) > 8:
             raise NotImplementedError("at most 8 peers (one box)")
-        engine.set_peer_outputs(ptrs, int(n_pairs_total), int(table[rank, 0]))
+        self._slot_bytes = self.ring[0].numel() * 4
+        self.consumer = torch.cuda.Stream(device=dev, priority=-1)
+        self._ready = [None] * self.depth      # event per slot: every rank's results of the step that used it have landed here
+        self._step = self._ended = -1
+        self._device = dev
+        self.out = self.ring[0]
+
+    def begin(self):
+        """Start the next step: pick its slot, wait (compute stream) until no rank still reads it, point the kernels at it."""
+        import torch
+
+        self._step += 1
+        slot = self._step % self.depth
+        nxt = self._ready[(slot + 1) % self.depth]
+        if self._step >= self.depth and nxt is not None:
+            torch.cuda.current_stream(self._device).wait_event(nxt)     # barrier of step (s - depth + 1) has been passed here
+        self.engine.set_peer_outputs([p + slot * self._slot_bytes for p in self._ptrs], self.n_pairs_total, self.pair_offset)
+        self.out = self.ring[slot]
+        return slot
+
+    def end(self):
+        """After ``engine.pairs``: completion barrier of this step on the consumer stream.  Returns the slot's tensor and the event
+        after which it holds every rank's results."""
+        import torch
+
+        if self._step < 0:
+            raise RuntimeError("begin() first")
+        slot = self._step % self.depth
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(self._device))
+        with torch.cuda.stream(self.consumer):
+            self.consumer.wait_event(done)
+            self.handle.barrier()
+            ready = torch.cuda.Event()
+            ready.record(self.consumer)
+        self._ready[slot] = ready
+        self._ended = self._step
+        return self.ring[slot], ready
 
     def wait(self):
-        """All ranks' kernels (enqueued before this call on the current stream) have delivered their results everywhere."""
-        self.handle.barrier()
-        return self.out
+        """Blocking use (one step at a time): ``end()`` if it has not been called for this step, then the CURRENT stream waits until
+        all ranks' results of the step are in ``self.out``; returns it."""
+        import torch
+
+        if self._step < 0:
+            raise RuntimeError("begin() / engine.pairs() first")
+        slot = self._step % self.depth
+        if self._ended != self._step:
+            self.end()
+        torch.cuda.current_stream(self._device).wait_event(self._ready[slot])
+        return self.ring[slot]
+
+    def drain(self):
+        """Host-side: wait for the consumer stream (all outstanding barriers)."""
+        self.consumer.synchronize()
 
     def close(self):
+        self.drain()
         self.engine.set_peer_outputs(None, 1, 0)
 
 

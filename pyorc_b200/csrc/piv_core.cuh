@@ -24,13 +24,66 @@ namespace b2piv {
 // ------------------------------------------------------------------------------------------------------------
 // complex helpers
 // ------------------------------------------------------------------------------------------------------------
-B2_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-B2_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Blackwell packed fp32 arithmetic (PTX add / sub / mul / fma .f32x2 -> SASS FADD2 / FMUL2 / FFMA2): ONE instruction works on
+// a register pair, i.e. on a whole complex number.  Measured on B200 (tools/fp32x2_bench.cu, profiles/r02/fp32x2_bench.log):
+// the same 128 values / clk / SM as the scalar forms - no extra flops - but HALF the issue slots and half the code bytes, and
+// ptxas folds component swaps and sign changes (x -> (x.y, -x.x), the +-i rotations of a butterfly) into operand selectors
+// (`R14.F32x2.LO_HI.NP`) and broadcasts scalar factors (`UR6.F32`), so a complex add is 1 instruction instead of 2 and a twiddle
+// multiplication 2 instead of 4.  The row-per-thread kernels were limited by instruction issue and fetch (ncu, round 1: 60 %
+// issue-active, the FFT passes stalled on `no_instruction` only), which is exactly what this relieves.  The host build (tests/emul)
+// keeps the scalar forms; both are round-to-nearest IEEE operations, the fused multiply-adds being chosen explicitly here.
+#ifdef __CUDA_ARCH__
+#define B2_PK_IN(a) "l"(pk_bits(a))
+__device__ __forceinline__ unsigned long long pk_bits(float2 a) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ float2 pk_float2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ float2 pk_add(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : B2_PK_IN(a), B2_PK_IN(b));
+    return pk_float2(d);
+}
+__device__ __forceinline__ float2 pk_sub(float2 a, float2 b) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : B2_PK_IN(a), B2_PK_IN(b));
+    return pk_float2(d);
+}
+__device__ __forceinline__ float2 pk_mul(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : B2_PK_IN(a), B2_PK_IN(b));
+    return pk_float2(d);
+}
+__device__ __forceinline__ float2 pk_fma(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : B2_PK_IN(a), B2_PK_IN(b), B2_PK_IN(c));
+    return pk_float2(d);
+}
+#else
+inline float2 pk_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+inline float2 pk_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+inline float2 pk_mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+inline float2 pk_fma(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#endif
+B2_HD float2 pk_scale(float2 a, float s) { return pk_mul(a, make_float2(s, s)); }
+
+B2_HD float2 cadd(float2 a, float2 b) { return pk_add(a, b); }
+B2_HD float2 csub(float2 a, float2 b) { return pk_sub(a, b); }
+// a * (c - i s)  (INV = 0)   or   a * (c + i s)  (INV = 1):  c * (a.x, a.y) + s * (+-a.y, -+a.x)
+template <int INV>
+B2_HD float2 ctw(float2 a, float c, float s) {
+    const float2 r = INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+    return pk_fma(r, make_float2(s, s), pk_mul(a, make_float2(c, c)));
+}
 // a * w  (INV=0)   or   a * conj(w)  (INV=1)
 template <int INV>
 B2_HD float2 cmulw(float2 a, float2 w) {
-    if (INV == 0) return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
-    return make_float2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y);
+    return INV == 0 ? ctw<1>(a, w.x, w.y) : ctw<0>(a, w.x, w.y);
 }
 
 // cos/sin(2*pi*j/16), j = 0..7, as compile-time literals (fold to immediates after unrolling)
@@ -66,8 +119,7 @@ struct RegDFT {
                 t = INV ? make_float2(-o[k].y, o[k].x) : make_float2(o[k].y, -o[k].x);
             } else {
                 const float c = cos16(j), s = sin16(j);  // w = c - i s (fwd), c + i s (inv)
-                t = INV ? make_float2(o[k].x * c - o[k].y * s, o[k].y * c + o[k].x * s)
-                        : make_float2(o[k].x * c + o[k].y * s, o[k].y * c - o[k].x * s);
+                t = ctw<INV>(o[k], c, s);
             }
             v[k] = cadd(e[k], t);
             v[k + R / 2] = csub(e[k], t);

@@ -39,10 +39,7 @@ B2_HD void fft_reg(float2* v) {
             if (n2 * k1 == 0) {
                 v[B * k1 + n2] = t[k1];
             } else {
-                const float c = cos128(e), sn = sin128(e);
-                const float2 a = t[k1];
-                v[B * k1 + n2] = INV ? make_float2(a.x * c - a.y * sn, a.y * c + a.x * sn)
-                                     : make_float2(a.x * c + a.y * sn, a.y * c - a.x * sn);
+                v[B * k1 + n2] = ctw<INV>(t[k1], cos128(e), sin128(e));
             }
         }
     }
@@ -448,10 +445,9 @@ B2_HD void rows_p2_pre(RSmem<R>& s, RRegs<R>& r, int tid, int clip_norm) {
     for (int k = 0; k < W / 4; ++k) {
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            float a0 = byte_to_float(r.px[0][k], b) - r.mean_new[0];
-            float a1 = byte_to_float(r.px[1][k], b) - r.mean_new[1];
-            if (clip_norm) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-            r.v[4 * k + b] = make_float2(a0, a1);
+            float2 a = pk_sub(make_float2(byte_to_float(r.px[0][k], b), byte_to_float(r.px[1][k], b)), make_float2(r.mean_new[0], r.mean_new[1]));
+            if (clip_norm) a = make_float2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f));
+            r.v[4 * k + b] = a;
         }
     }
 }
@@ -520,38 +516,46 @@ __device__ __forceinline__ void transpose_device(RSmem<R>& s, RRegs<R>& r, int t
 //   A0 = (z + conj zn) * (0.5/std0),  A1 = -i (z - conj zn) * (0.5/std1),  parked value = A / N^2
 // `zn` = Z(-ky, -kx) comes from the partner lane (register index (W-ky)%W).
 B2_HD void separate(float2 z, float2 zn, float b0, float b1, float2& a0, float2& a1) {
-    a0 = make_float2((z.x + zn.x) * b0, (z.y - zn.y) * b0);
-    a1 = make_float2((z.y + zn.y) * b1, (zn.x - z.x) * b1);
+    a0 = pk_scale(pk_add(z, make_float2(zn.x, -zn.y)), b0);                         // ((z.x + zn.x) b0, (z.y - zn.y) b0)
+    a1 = pk_scale(pk_add(make_float2(z.y, -z.x), make_float2(zn.y, zn.x)), b1);     // ((z.y + zn.y) b1, (zn.x - z.x) b1)
 }
 
 // One ky step (ky in [0, W/2]) of the cross phase, part A: needs partner's Z(kn) = `pz`.
 // Computes R0, R1 at (ky, own column), parks the new spectra, writes G(ky) into v[ky].
+// Scaling: the planes need 1 / N^2 (N = W * W: one 1/N for the unnormalised inverse transform, one for the mean of the
+// correlation).  N is a power of two, so the native mode folds 1/N into the 0.5/std factor of BOTH roles of a spectrum (exact:
+// only exponents change) and parks the separated spectra as they are; padded mode scales the parked copy by its 1 / (N ny nx).
 template <class R, bool PAD = false>
 B2_HD void cross_step_a(RSmem<R>& s, RRegs<R>& r, int tid, int ky, float2 pz, bool have_prev, float2& r0, float2& r1,
                         const RParams* pp = nullptr) {
-    constexpr float INVN2 = 1.0f / ((float)R::NPX * (float)R::NPX);
-    const float scale = PAD ? pp->pad_scale : INVN2;
+    constexpr float INVN = 1.0f / (float)R::NPX;
     float2 a0, a1;
-    separate(r.v[ky], pz, r.half_alpha_new[0], r.half_alpha_new[1], a0, a1);
+    if (PAD) separate(r.v[ky], pz, r.half_alpha_new[0], r.half_alpha_new[1], a0, a1);
+    else separate(r.v[ky], pz, r.half_alpha_new[0] * INVN, r.half_alpha_new[1] * INVN, a0, a1);
     if (have_prev) {
         const float2 p0 = s.park[0][ky][tid], p1 = s.park[1][ky][tid];
-        r0 = make_float2(p0.x * a0.x + p0.y * a0.y, p0.x * a0.y - p0.y * a0.x);   // conj(p0) * a0
-        r1 = make_float2(p1.x * a1.x + p1.y * a1.y, p1.x * a1.y - p1.y * a1.x);
+        r0 = ctw<0>(a0, p0.x, p0.y);   // conj(p0) * a0
+        r1 = ctw<0>(a1, p1.x, p1.y);
         if (PAD) {   // new window in its tiled role: times T(ky, own column) = Ty(ky) Tx
             const float2 ty = pp->pad_ty[ky];
-            const float2 t = make_float2(ty.x * r.tx.x - ty.y * r.tx.y, ty.x * r.tx.y + ty.y * r.tx.x);
-            r0 = make_float2(r0.x * t.x - r0.y * t.y, r0.x * t.y + r0.y * t.x);
-            r1 = make_float2(r1.x * t.x - r1.y * t.y, r1.x * t.y + r1.y * t.x);
+            const float2 t = ctw<1>(ty, r.tx.x, r.tx.y);
+            r0 = ctw<1>(r0, t.x, t.y);
+            r1 = ctw<1>(r1, t.x, t.y);
         }
     }
-    s.park[0][ky][tid] = make_float2(a0.x * scale, a0.y * scale);
-    s.park[1][ky][tid] = make_float2(a1.x * scale, a1.y * scale);
-    if (have_prev) r.v[ky] = make_float2(r0.x - r1.y, -(r0.y + r1.x));            // conj(G), G = R0 + i R1
+    if (PAD) {
+        s.park[0][ky][tid] = pk_scale(a0, pp->pad_scale);
+        s.park[1][ky][tid] = pk_scale(a1, pp->pad_scale);
+    } else {
+        s.park[0][ky][tid] = a0;
+        s.park[1][ky][tid] = a1;
+    }
+    if (have_prev) r.v[ky] = pk_sub(make_float2(r0.x, -r0.y), make_float2(r1.y, r1.x));   // conj(G), G = R0 + i R1
 }
 // part B: the partner's (R0, R1) at (ky, -col) give G(-ky, col) = conj(R0) + i conj(R1), stored conjugated:
 // conj(G(-ky, col)) = (R0.x + R1.y, R0.y - R1.x).  The SENDER forms that value (cross_mirror) so only one complex number
 // crosses the warp per step.
-B2_HD float2 cross_mirror(float2 r0, float2 r1) { return make_float2(r0.x + r1.y, r0.y - r1.x); }
+B2_HD float2 cross_mirror(float2 r0, float2 r1) { return pk_add(r0, make_float2(r1.y, -r1.x)); }
 template <class R>
 B2_HD void cross_step_b(RRegs<R>& r, int ky, float2 q) {
     constexpr int W = R::W;
@@ -632,9 +636,9 @@ __device__ __forceinline__ void rows_cross_only_device(RSmem<R>& s, RRegs<R>& r,
         float2 a0, a1;
         separate(r.v[ky], pz, r.half_alpha_new[0], r.half_alpha_new[1], a0, a1);
         const float2 p0 = s.park[0][ky][tid], p1 = s.park[1][ky][tid];
-        const float2 r0 = make_float2(p0.x * a0.x + p0.y * a0.y, p0.x * a0.y - p0.y * a0.x);   // conj(p0) * a0
-        const float2 r1 = make_float2(p1.x * a1.x + p1.y * a1.y, p1.x * a1.y - p1.y * a1.x);
-        r.v[ky] = make_float2(r0.x - r1.y, -(r0.y + r1.x));                                    // conj(G), G = R0 + i R1
+        const float2 r0 = ctw<0>(a0, p0.x, p0.y);   // conj(p0) * a0
+        const float2 r1 = ctw<0>(a1, p1.x, p1.y);
+        r.v[ky] = pk_sub(make_float2(r0.x, -r0.y), make_float2(r1.y, r1.x));                   // conj(G), G = R0 + i R1
         if (ky != 0 && ky != W / 2) cross_step_b<R>(r, ky, shfl2(cross_mirror(r0, r1), pl));
     }
 }
@@ -649,8 +653,8 @@ __device__ __forceinline__ void rows_park_only_device(RSmem<R>& s, RRegs<R>& r, 
         const float2 pz = shfl2(r.v[(W - ky) % W], pl);
         float2 a0, a1;
         separate(r.v[ky], pz, r.half_alpha_new[0], r.half_alpha_new[1], a0, a1);
-        s.park[0][ky][tid] = make_float2(a0.x * INVN2, a0.y * INVN2);
-        s.park[1][ky][tid] = make_float2(a1.x * INVN2, a1.y * INVN2);
+        s.park[0][ky][tid] = pk_scale(a0, INVN2);
+        s.park[1][ky][tid] = pk_scale(a1, INVN2);
     }
 }
 #endif
@@ -669,17 +673,21 @@ B2_HD int shifted_index(int q, int n) { const int h = n / 2; return q < n - h ? 
 template <class R, bool PAD = false>
 B2_HD void rows_p5_post(RSmem<R>& s, RRegs<R>& r, int tid, bool dead0, bool dead1, const RParams* pp = nullptr) {
     constexpr int W = R::W;
-    float m0 = 0.f, m1 = 0.f, s0 = 0.f, s1 = 0.f;
+    float m0 = 0.f, m1 = 0.f;
+    float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);   // two running (window 0, window 1) sums: shorter dependency chains
 #pragma unroll
-    for (int x = 0; x < W; ++x) {
+    for (int x = 0; x < W; x += 2) {
         // clip to [0, 1] (inputs are uint8, no NaNs can occur, so fmin/fmax are exact here); padded mode: the upper bound
         // is 0 for the columns outside the window's lags (rows outside are dropped below and never read afterwards)
-        const float hi = PAD ? pp->pad_cm[x] : 1.f;
-        const float a = fminf(fmaxf(r.v[x].x, 0.f), hi), b = fminf(fmaxf(-r.v[x].y, 0.f), hi);
-        r.v[x] = make_float2(a, b);
-        m0 = fmaxf(a, m0); m1 = fmaxf(b, m1);
-        s0 += a; s1 += b;
+        const float h0 = PAD ? pp->pad_cm[x] : 1.f, h1 = PAD ? pp->pad_cm[x + 1] : 1.f;
+        const float2 e0 = make_float2(fminf(fmaxf(r.v[x].x, 0.f), h0), fminf(fmaxf(-r.v[x].y, 0.f), h0));
+        const float2 e1 = make_float2(fminf(fmaxf(r.v[x + 1].x, 0.f), h1), fminf(fmaxf(-r.v[x + 1].y, 0.f), h1));
+        r.v[x] = e0; r.v[x + 1] = e1;
+        m0 = fmaxf(fmaxf(e0.x, e1.x), m0); m1 = fmaxf(fmaxf(e0.y, e1.y), m1);
+        sa = pk_add(sa, e0); sb = pk_add(sb, e1);
     }
+    sa = pk_add(sa, sb);
+    float s0 = sa.x, s1 = sa.y;
     // a window with zero variance has an exactly-zero plane in the reference (the packed inverse FFT leaves ~1e-10
     // cross-talk from its partner window): force max = sum = 0 here, first-argmax 0 in rows_p6, zeros in the dumps
     if (dead0 || (PAD && column_of<W>(tid) >= pp->ny)) { m0 = 0.f; s0 = 0.f; }

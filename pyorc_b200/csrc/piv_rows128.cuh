@@ -91,20 +91,18 @@ __device__ __forceinline__ void r128_p2(R128Smem& s, RRegs<R6>& r, int clip_norm
     for (int k = 0; k < 16; ++k) {
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            float a0 = byte_to_float(r.px[0][k], b) - r.mean_new[0];
-            float a1 = byte_to_float(r.px[1][k], b) - r.mean_new[1];
-            if (clip_norm) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-            r.v[4 * k + b] = make_float2(a0, a1);
+            float2 a = pk_sub(make_float2(byte_to_float(r.px[0][k], b), byte_to_float(r.px[1][k], b)), make_float2(r.mean_new[0], r.mean_new[1]));
+            if (clip_norm) a = make_float2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f));
+            r.v[4 * k + b] = a;
         }
     }
 }
 
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ float2 cmulc(float2 p, float2 a) {   // conj(p) * a
-    return make_float2(p.x * a.x + p.y * a.y, p.x * a.y - p.y * a.x);
-}
-__device__ __forceinline__ float2 cfma(float2 m, float2 b, float2 a) {   // a + m * b
-    return make_float2(fmaf(m.x, b.x, fmaf(-m.y, b.y, a.x)), fmaf(m.x, b.y, fmaf(m.y, b.x, a.y)));
+// packed fp32 forms (piv_core.cuh): two instructions each
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return ctw<1>(a, b.x, b.y); }
+__device__ __forceinline__ float2 cmulc(float2 p, float2 a) { return ctw<0>(a, p.x, p.y); }   // conj(p) * a
+__device__ __forceinline__ float2 cfma(float2 m, float2 b, float2 a) {   // a + m * b = a + m.x (b.x, b.y) + m.y (-b.y, b.x)
+    return pk_fma(make_float2(-b.y, b.x), make_float2(m.y, m.y), pk_fma(b, make_float2(m.x, m.x), a));
 }
 
 // Both windows of a spectrum bin travel together as one float4 (A0.x, A0.y, A1.x, A1.y): 16-byte shared-memory accesses halve
@@ -181,7 +179,7 @@ __device__ __forceinline__ void r128_cross(R128Smem& s, RRegs<R6>& r, int sub, i
                 const float2 h = cfma(m2, term[w][3], term[w][2]);
                 R[w] = cfma(m1, h, l);
             }
-            lo[sl] = make_float2(R[0].x - R[1].y, -(R[0].y + R[1].x));            // conj(G), G = R0 + i R1
+            lo[sl] = pk_sub(make_float2(R[0].x, -R[0].y), make_float2(R[1].y, R[1].x));   // conj(G), G = R0 + i R1
             hi[sl] = shfl2(cross_mirror(R[0], R[1]), pl);                         // conj(G(-ky)); unused for ky = 0, 32
         }
         __syncthreads();
@@ -189,7 +187,8 @@ __device__ __forceinline__ void r128_cross(R128Smem& s, RRegs<R6>& r, int sub, i
 #pragma unroll
         for (int sl = 0; sl < B; ++sl) {
             const float4 a = own[sl * 32];
-            *r128_park(s, sub, b0 + sl, t) = make_float4(a.x * SCALE, a.y * SCALE, a.z * SCALE, a.w * SCALE);
+            const float2 s0 = pk_scale(make_float2(a.x, a.y), SCALE), s1 = pk_scale(make_float2(a.z, a.w), SCALE);
+            *r128_park(s, sub, b0 + sl, t) = make_float4(s0.x, s0.y, s1.x, s1.y);
         }
         // -- rotate both register arrays by one batch
         float2 tl[B], th[B];

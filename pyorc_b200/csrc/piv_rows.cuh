@@ -95,6 +95,8 @@ struct RSmem {
     float2 park[2][R::HS][R::NT];                // previous frame: scaled spectra A0, A1 at (ky <= W/2, own column)
     unsigned red[R::NWARP][8];                   // block reductions (integer moments, float bits)
     unsigned long long redk[R::NWARP][2];
+    unsigned rowc[R::NWARP][2];                  // per warp and window: first row (reference order) holding the warp's maximum
+    int peak_j[2];                               // column of the peak, found by the thread that owns the peak's row
     unsigned long long mbar;                     // TMA completion barrier
     B2_HD unsigned char* tile() { return reinterpret_cast<unsigned char*>(X); }
 };
@@ -259,10 +261,7 @@ B2_HD void rows_p1(RSmem<R>& s, RRegs<R>& r, int tid, int xoff0 = 0, int xoff1 =
     unsigned vals[4] = {S[0], Q[0], S[1], Q[1]};
 #ifdef __CUDA_ARCH__
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) vals[k] += __shfl_xor_sync(0xffffffffu, vals[k], o);
-    }
+    for (int k = 0; k < 4; ++k) vals[k] = __reduce_add_sync(0xffffffffu, vals[k]);   // one REDUX each (exact: sums stay below 2^32)
     if ((tid & 31) == 0) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) s.red[tid >> 5][k] = vals[k];
@@ -315,10 +314,7 @@ B2_HD void rows_p1_pad(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p, int 
     unsigned vals[4] = {S[0], Q[0], S[1], Q[1]};
 #ifdef __CUDA_ARCH__
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) vals[k] += __shfl_xor_sync(0xffffffffu, vals[k], o);
-    }
+    for (int k = 0; k < 4; ++k) vals[k] = __reduce_add_sync(0xffffffffu, vals[k]);   // one REDUX each (exact: sums stay below 2^32)
     if ((tid & 31) == 0) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) s.red[tid >> 5][k] = vals[k];
@@ -611,10 +607,7 @@ B2_HD void rows_p1_shift(RSmem<R>& s, RRegs<R>& r, int tid, const unsigned char*
     unsigned vals[4] = {S[0], Q[0], S[1], Q[1]};
 #ifdef __CUDA_ARCH__
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) vals[k] += __shfl_xor_sync(0xffffffffu, vals[k], o);
-    }
+    for (int k = 0; k < 4; ++k) vals[k] = __reduce_add_sync(0xffffffffu, vals[k]);   // one REDUX each (exact: sums stay below 2^32)
     if ((tid & 31) == 0) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) s.red[tid >> 5][k] = vals[k];
@@ -695,17 +688,23 @@ B2_HD void rows_p5_post(RSmem<R>& s, RRegs<R>& r, int tid, bool dead0, bool dead
     r.dead[0] = dead0; r.dead[1] = dead1;
     r.rowmax[0] = m0; r.rowmax[1] = m1; r.rowsum[0] = s0; r.rowsum[1] = s1;
 #ifdef __CUDA_ARCH__
-    float vm0 = m0, vm1 = m1;
+    // warp maxima with one REDUX each (non-negative floats order like their bit patterns), the first row (reference order)
+    // that holds the warp maximum with another, sums by packed shuffle-adds
+    const unsigned b0 = __float_as_uint(m0), b1 = __float_as_uint(m1);
+    const unsigned wm0 = __reduce_max_sync(0xffffffffu, b0), wm1 = __reduce_max_sync(0xffffffffu, b1);
+    {
+        const bool rowok = !PAD || column_of<W>(tid) < pp->ny;
+        const unsigned si = PAD ? (rowok ? (unsigned)shifted_index(column_of<W>(tid), pp->ny) : 0xffffu) : (unsigned)((column_of<W>(tid) + W / 2) % W);
+        const unsigned c0 = (b0 == wm0 && rowok) ? si : 0xffffu, c1 = (b1 == wm1 && rowok) ? si : 0xffffu;
+        const unsigned wr0 = __reduce_min_sync(0xffffffffu, c0), wr1 = __reduce_min_sync(0xffffffffu, c1);
+        float2 ss = make_float2(s0, s1);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        vm0 = fmaxf(vm0, __shfl_xor_sync(0xffffffffu, vm0, o));
-        vm1 = fmaxf(vm1, __shfl_xor_sync(0xffffffffu, vm1, o));
-        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-    }
-    if ((tid & 31) == 0) {
-        s.red[tid >> 5][4] = __float_as_uint(vm0); s.red[tid >> 5][5] = __float_as_uint(vm1);
-        s.red[tid >> 5][6] = __float_as_uint(s0);  s.red[tid >> 5][7] = __float_as_uint(s1);
+        for (int o = 16; o > 0; o >>= 1) ss = pk_add(ss, make_float2(__shfl_xor_sync(0xffffffffu, ss.x, o), __shfl_xor_sync(0xffffffffu, ss.y, o)));
+        if ((tid & 31) == 0) {
+            s.red[tid >> 5][4] = wm0; s.red[tid >> 5][5] = wm1;
+            s.red[tid >> 5][6] = __float_as_uint(ss.x); s.red[tid >> 5][7] = __float_as_uint(ss.y);
+            s.rowc[tid >> 5][0] = wr0; s.rowc[tid >> 5][1] = wr1;
+        }
     }
 #else
     union { float f; unsigned u; } a;
@@ -781,6 +780,73 @@ B2_HD void rows_p6(RSmem<R>& s, RRegs<R>& r, int tid, const RParams* pp = nullpt
     }
 }
 
+#ifdef __CUDACC__
+// P6x (device, replaces P6 + P7 of the first version and one CTA barrier): after E1 every thread knows the block maximum AND
+// the peak's row - the first row in reference order among the warps' candidates (rows_p5_post) - so the thread that owns that
+// row looks for the first matching column in its registers while the rows around it are dumped for the Gaussian fit; only the
+// column has to travel (peak_j).  First-occurrence argmax of the flattened plane = smallest row holding the maximum, then the
+// smallest column in that row.
+template <class R, bool PAD = false>
+__device__ __forceinline__ void rows_p6x(RSmem<R>& s, RRegs<R>& r, int tid, const RParams* pp = nullptr) {
+    constexpr int W = R::W;
+    const bool rowok = !PAD || column_of<W>(tid) < pp->ny;
+    const int si = PAD ? (rowok ? shifted_index(column_of<W>(tid), pp->ny) : -8) : (column_of<W>(tid) + W / 2) % W;
+    float* nb = &s.nb[0][0][0];   // [w][3][W]
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        unsigned mb = 0u, row = 0xffffu;
+        float S = 0.f;
+#pragma unroll
+        for (int k = 0; k < R::NWARP; ++k) {
+            const unsigned m = s.red[k][4 + w], rc = s.rowc[k][w];
+            row = m > mb ? rc : (m == mb ? min(row, rc) : row);
+            mb = max(mb, m);
+            S += bits_f(s.red[k][6 + w]);
+        }
+        const float M = __uint_as_float(mb);
+        r.cmaxv[w] = M; r.sumv[w] = S;
+        const int pi = r.dead[w] ? 0 : (int)row;      // all-zero plane: every element is the maximum -> flat index 0
+        r.pi[w] = pi;
+        if (si == pi) {
+            int first = 0;
+            if (!r.dead[w]) {
+                if (PAD) {
+                    unsigned mlo = 0u, mhi = 0u;
+#pragma unroll
+                    for (int x = 0; x < W; ++x) {
+                        const float val = w == 0 ? r.v[x].x : r.v[x].y;
+                        if (x < 32) mlo |= (val == M) ? (1u << x) : 0u; else mhi |= (val == M) ? (1u << (x - 32)) : 0u;
+                    }
+                    const unsigned long long mm = ((unsigned long long)mhi << 32) | mlo;
+                    const int nh = pp->nx - pp->nx / 2;
+                    const unsigned long long seg_hi = mm >> nh, seg_lo = mm & ((1ull << nh) - 1ull);
+                    const unsigned long long t = seg_hi ? seg_hi : seg_lo;
+                    const int k = __ffsll((long long)t) - 1;
+                    first = M == 0.f ? 0 : (seg_hi ? k : k + pp->nx / 2);
+                } else {
+                    first = W;
+#pragma unroll
+                    for (int j = W - 1; j >= 0; --j) {   // shifted column j = (x + W/2) % W ; scan j descending so the smallest j survives
+                        const int x = (j + W / 2) % W;
+                        const float val = w == 0 ? r.v[x].x : r.v[x].y;
+                        first = (val == M) ? j : first;
+                    }
+                }
+            }
+            s.peak_j[w] = first;
+        }
+        const int d = si - pi;
+        if (d >= -1 && d <= 1) {
+#pragma unroll
+            for (int x = 0; x < W; ++x) {
+                const float val = r.dead[w] ? 0.f : (w == 0 ? r.v[x].x : r.v[x].y);
+                nb[(w * 3 + (d + 1)) * W + (PAD ? x : (x + W / 2) % W)] = val;   // padded: natural lag order, mapped in rows_p8
+            }
+        }
+    }
+}
+#endif
+
 // P7: peak position known; the three rows around each peak are dumped for the Gaussian fit.
 template <class R, bool PAD = false>
 B2_HD void rows_p7(RSmem<R>& s, RRegs<R>& r, int tid, const RParams* pp = nullptr) {
@@ -808,9 +874,10 @@ B2_HD void rows_p7(RSmem<R>& s, RRegs<R>& r, int tid, const RParams* pp = nullpt
 
 // P8: Gaussian fit + outputs by thread w (pyorc/velocimetry/ffpiv.py:465-466 + ffpiv.u_v_displacement).
 template <class R, bool PAD = false>
-B2_HD void rows_p8(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p, const RUnit& un, int pair) {
+B2_HD void rows_p8(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p, const RUnit& un, int pair, bool pj_from_smem = false) {
     constexpr int W = R::W;
     if (tid >= 2) return;
+    if (pj_from_smem) { r.pj[0] = s.peak_j[0]; r.pj[1] = s.peak_j[1]; }
     const int ny = PAD ? p.ny : W, nx = PAD ? p.nx : W;
     const int w = tid;
     if (w == 1 && !un.valid1) return;

@@ -168,12 +168,10 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
             if constexpr (ENS) {
                 rows_ens<R, PAD>(s, r, tid, p, un, f - 1, active && have_prev);   // thresholds + accumulate; no peak search per pair
             } else {
-                rows_p6<R, PAD>(s, r, tid, &p);
-                __syncthreads();  // E2: first-argmax key
                 if (active && have_prev) rows_dump_planes<R, PAD>(r, tid, p, un, f - 1);
-                rows_p7<R, PAD>(s, r, tid, &p);
-                __syncthreads();  // F: neighbour rows dumped
-                if (active && have_prev) rows_p8<R, PAD>(s, r, tid, p, un, f - 1);
+                rows_p6x<R, PAD>(s, r, tid, &p);   // peak row known from E1: column search + neighbour rows in one phase
+                __syncthreads();  // F: neighbour rows dumped, peak column published
+                if (active && have_prev) rows_p8<R, PAD>(s, r, tid, p, un, f - 1, true);
             }
             r.half_alpha_prev[0] = r.half_alpha_new[0];
             r.half_alpha_prev[1] = r.half_alpha_new[1];

@@ -376,12 +376,15 @@ def ensemble_check(eng, dev, rank, world):
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     u, v, cm, sn, cnt = res
     out = None
+    # the single-GPU reference must see the SAME frames: the device renderer scatters the particles with atomics (index_add_),
+    # so two renderings of one frame can differ in a last bit - every rank's stack, halo frame included, is gathered instead
+    stacks = torch.empty((world,) + tuple(fr.shape), dtype=fr.dtype, device=dev)
+    dist.all_gather_into_tensor(stacks.view(world * fr.shape[0], H, W), fr)
     if rank == 0:
-        full = synth.particle_frames_torch(total + 1, H, W, dev, dtype="uint8")
         eng.ens_begin((H, W), WS, OV, np.uint8, device_ordered=True)
         cms, sns = [], []
-        for ra, rb in table:
-            c_, s_ = eng.ens_add(full[int(ra) : int(rb) + 1], WS, OV, corr_min=kw["corr_min"], s2n_min=kw["s2n_min"])
+        for r_ in range(world):
+            c_, s_ = eng.ens_add(stacks[r_], WS, OV, corr_min=kw["corr_min"], s2n_min=kw["s2n_min"])
             cms.append(c_.cpu().numpy())
             sns.append(s_.cpu().numpy())
         u1, v1, cnt1 = eng.ens_finish(kw["count_min"] * world)
@@ -394,8 +397,7 @@ def ensemble_check(eng, dev, rank, world):
                "valid_windows": int(ok.sum()), "timed": "ens_begin + accumulate (1 launch) + reduce-scatter + peak fit of the slice + all-gather + host means, wall clock"}
         out["equals_single_gpu"] = bool(out["counts_bit_equal"] and out["nan_mask_equal"] and out["max_abs_du_px"] <= 2e-3 and out["max_abs_dv_px"] <= 2e-3
                                         and out["corr_s2n_means_equal"])
-        del full
-    del fr
+    del fr, stacks
     torch.cuda.empty_cache()
     eng.plan((H, W), WS, OV, np.uint8)
     return out

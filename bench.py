@@ -465,6 +465,13 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     eng = get_engine(local_rank)          # the engine get_b2piv(device=local_rank) uses
+    host_cores = os.cpu_count() or 1
+    try:
+        host_cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    stage_threads = max(2, min(8, host_cores // world))
+    eng.set_option("stage_threads", stage_threads)    # the ranks share one host: split its cores between their staging pools
     n_frames = N_PAIRS + 1
     frames = synth.particle_frames_torch(n_frames, H, W, dev, dtype="uint8", seed=synth.SEED + rank)
     nr, nc = eng.plan((H, W), WS, OV, np.uint8)
@@ -715,7 +722,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                 "ms_per_step": 1e3 * e2e_s / args.steps,
                 "api": "pyorc_b200.velocimetry.get_b2piv(pageable numpy DataArray) -> Dataset" + ("; then NCCL gather of the four fields to every rank's host memory" if world > 1 else ""),
-                "pcie": pcie, "pinned_engine_pairs": pinned},
+                "pcie": pcie, "pinned_engine_pairs": pinned, "host_cores": host_cores, "stage_threads_per_rank": stage_threads},
         "gpu_launches": int(launches), "clocks": clocks, "rmse_vs_oracle": rmse, "other_configs": other, "sharded_configs": sharded,
         "ensemble_multi_gpu": ens,
     }

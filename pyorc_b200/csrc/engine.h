@@ -163,6 +163,24 @@ static int ensure(b2piv_engine* e, T** ptr, size_t* cap, size_t bytes) {
     return B2PIV_OK;
 }
 
+// Frame pairs per work unit of the row-per-thread kernels.  A unit follows its window pair through `run` consecutive frame
+// pairs and pays ONE extra forward transform at its start, and the units are dealt to `resident` persistent groups in waves:
+// cost ~ ceil(units / resident) * (run + 1) frame times.  The number of time chunks that minimises it is searched (round 1
+// aimed at >= 8 waves, which for 100 pairs of 1080p - 944 window pairs on 592 groups - gave 6 chunks: 9.6 waves, the last one
+// 57 % full, 180 frame times; 5 chunks fill 7.97 waves: 168).
+static inline int pick_run_len(int n_pairs, long long n_wp, long long resident) {
+    long long best_cost = -1;
+    int best_run = n_pairs;
+    for (int c = 1; c <= n_pairs && c <= 64; ++c) {
+        const int run = (n_pairs + c - 1) / c;
+        const long long chunks = (n_pairs + run - 1) / run;
+        const long long waves = (n_wp * chunks + resident - 1) / resident;
+        const long long cost = waves * (run + 1);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_run = run; }
+    }
+    return best_run < 1 ? 1 : best_run;
+}
+
 // ---- launch entry points of the kernel families (k_*.cu) ------------------------------------------------------------
 using b2piv::Params;
 bool fft_config(int wy, int wx);

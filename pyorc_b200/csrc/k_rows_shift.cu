@@ -143,12 +143,7 @@ int launch_rows_shift(b2piv_engine* e, const Params& gp, cudaStream_t st) {
     const long long resident = (long long)occ * e->sm_count * G;
     const int nw = gp.n_rows * gp.n_cols, n_wp = (nw + 1) / 2;
     int run = e->run_len;
-    if (run <= 0) {
-        long long chunks = (8 * resident + n_wp - 1) / n_wp;
-        if (chunks < 1) chunks = 1;
-        run = (int)((gp.n_pairs + chunks - 1) / chunks);
-        if (run < 8) run = 8;
-    }
+    if (run <= 0) run = pick_run_len(gp.n_pairs, n_wp, resident);   // engine.h
     if (run > gp.n_pairs) run = gp.n_pairs;
     p.run_len = run;
     const long long n_units = (long long)n_wp * ((gp.n_pairs + run - 1) / run);

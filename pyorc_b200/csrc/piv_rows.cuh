@@ -92,7 +92,7 @@ struct RSmem {
     // consumed into registers before the first transpose of a frame and refilled after the last one
     alignas(1024) float2 X[R::NWARP][R::XBLK];
     float nb[2][3][R::W];                        // the three plane rows around each peak (Gaussian fit)
-    float2 park[2][R::HS][R::NT];                // previous frame: scaled spectra A0, A1 at (ky <= W/2, own column)
+    float4 park[R::HS][R::NT];                   // previous frame: scaled spectra (A0, A1) at (ky <= W/2, own column), one 16-byte access
     unsigned red[R::NWARP][8];                   // block reductions (integer moments, float bits)
     unsigned long long redk[R::NWARP][2];
     unsigned rowc[R::NWARP][2];                  // per warp and window: first row (reference order) holding the warp's maximum
@@ -529,9 +529,9 @@ B2_HD void cross_step_a(RSmem<R>& s, RRegs<R>& r, int tid, int ky, float2 pz, bo
     if (PAD) separate(r.v[ky], pz, r.half_alpha_new[0], r.half_alpha_new[1], a0, a1);
     else separate(r.v[ky], pz, r.half_alpha_new[0] * INVN, r.half_alpha_new[1] * INVN, a0, a1);
     if (have_prev) {
-        const float2 p0 = s.park[0][ky][tid], p1 = s.park[1][ky][tid];
-        r0 = ctw<0>(a0, p0.x, p0.y);   // conj(p0) * a0
-        r1 = ctw<0>(a1, p1.x, p1.y);
+        const float4 pk = s.park[ky][tid];
+        r0 = ctw<0>(a0, pk.x, pk.y);   // conj(p0) * a0
+        r1 = ctw<0>(a1, pk.z, pk.w);
         if (PAD) {   // new window in its tiled role: times T(ky, own column) = Ty(ky) Tx
             const float2 ty = pp->pad_ty[ky];
             const float2 t = ctw<1>(ty, r.tx.x, r.tx.y);
@@ -540,11 +540,10 @@ B2_HD void cross_step_a(RSmem<R>& s, RRegs<R>& r, int tid, int ky, float2 pz, bo
         }
     }
     if (PAD) {
-        s.park[0][ky][tid] = pk_scale(a0, pp->pad_scale);
-        s.park[1][ky][tid] = pk_scale(a1, pp->pad_scale);
+        const float2 q0 = pk_scale(a0, pp->pad_scale), q1 = pk_scale(a1, pp->pad_scale);
+        s.park[ky][tid] = make_float4(q0.x, q0.y, q1.x, q1.y);
     } else {
-        s.park[0][ky][tid] = a0;
-        s.park[1][ky][tid] = a1;
+        s.park[ky][tid] = make_float4(a0.x, a0.y, a1.x, a1.y);
     }
     if (have_prev) r.v[ky] = pk_sub(make_float2(r0.x, -r0.y), make_float2(r1.y, r1.x));   // conj(G), G = R0 + i R1
 }
@@ -628,9 +627,9 @@ __device__ __forceinline__ void rows_cross_only_device(RSmem<R>& s, RRegs<R>& r,
         const float2 pz = shfl2(r.v[(W - ky) % W], pl);
         float2 a0, a1;
         separate(r.v[ky], pz, r.half_alpha_new[0], r.half_alpha_new[1], a0, a1);
-        const float2 p0 = s.park[0][ky][tid], p1 = s.park[1][ky][tid];
-        const float2 r0 = ctw<0>(a0, p0.x, p0.y);   // conj(p0) * a0
-        const float2 r1 = ctw<0>(a1, p1.x, p1.y);
+        const float4 pk = s.park[ky][tid];
+        const float2 r0 = ctw<0>(a0, pk.x, pk.y);   // conj(p0) * a0
+        const float2 r1 = ctw<0>(a1, pk.z, pk.w);
         r.v[ky] = pk_sub(make_float2(r0.x, -r0.y), make_float2(r1.y, r1.x));                   // conj(G), G = R0 + i R1
         if (ky != 0 && ky != W / 2) cross_step_b<R>(r, ky, shfl2(cross_mirror(r0, r1), pl));
     }
@@ -646,8 +645,8 @@ __device__ __forceinline__ void rows_park_only_device(RSmem<R>& s, RRegs<R>& r, 
         const float2 pz = shfl2(r.v[(W - ky) % W], pl);
         float2 a0, a1;
         separate(r.v[ky], pz, r.half_alpha_new[0], r.half_alpha_new[1], a0, a1);
-        s.park[0][ky][tid] = pk_scale(a0, INVN2);
-        s.park[1][ky][tid] = pk_scale(a1, INVN2);
+        const float2 q0 = pk_scale(a0, INVN2), q1 = pk_scale(a1, INVN2);
+        s.park[ky][tid] = make_float4(q0.x, q0.y, q1.x, q1.y);
     }
 }
 #endif

@@ -35,7 +35,7 @@ constexpr int R128_NPX = 128 * 128;
 // tile: window w rows [32 j, 32 j + 32) -> sub[j].tile() + w * 4096 ([32 rows][128 B], SWIZZLE_128B)
 static_assert(sizeof(float2) * R6::NWARP * R6::XBLK >= 2 * 4096, "tile quarter must fit in a sub-group's transpose blocks");
 static_assert(sizeof(float2) * R6::XBLK >= sizeof(float4) * R128_BATCH * 32, "exchange batch must fit in one warp's block");
-static_assert(sizeof(float2) * 2 * R6::HS * R6::NT == sizeof(float4) * 33 * 64, "parked spectra are re-viewed as [33][64] float4");
+static_assert(sizeof(RSmem<R6>::park) == sizeof(float4) * 33 * 64, "parked spectra are [33][64] float4");
 
 #ifdef __CUDACC__
 // P1: row 2 sigma(t) + p1 of both windows from the tile, bytes of column parity p2 packed (64 bytes per window), exact
@@ -113,7 +113,7 @@ __device__ __forceinline__ float4* r128_xch(R128Smem& s, int g, int wq, int sl, 
     return reinterpret_cast<float4*>(&s.sub[g].X[wq][0]) + sl * 32 + lane;
 }
 __device__ __forceinline__ float4* r128_park(R128Smem& s, int g, int ky, int t) {
-    return reinterpret_cast<float4*>(&s.sub[g].park[0][0][0]) + ky * 64 + t;
+    return &s.sub[g].park[ky][t];
 }
 
 // exp(+2 pi i ky / 64), ky = 0 .. 32: phase of a carry along y (indexed at run time by the rolled batch loop below)

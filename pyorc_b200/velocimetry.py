@@ -138,6 +138,14 @@ def get_b2piv(
         raise ValueError("dt must hold one interval per frame pair")
     # a device named k times gets k engines (slots): each engine is driven by one host thread only
     engs = [get_engine(d, devices[:i].count(d)) if devices[:i].count(d) else get_engine(d) for i, d in enumerate(devices)]
+    if len(engs) > 1:
+        # every engine stages pageable frames with its own copy threads: share the host's cores instead of oversubscribing them
+        import os
+
+        per = max(2, min(8, (os.cpu_count() or 8) // len(engs)))
+        for e in engs:
+            if hasattr(e, "set_option"):
+                e.set_option("stage_threads", per)
     common = (frames, bounds, times, dt_vals, y, x, res_y, res_x, n_rows, n_cols, window_size, overlap, engs)
     if coarse_pass is not None:
         if ensemble_corr:

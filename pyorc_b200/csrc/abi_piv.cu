@@ -254,6 +254,7 @@ void b2piv_destroy(b2piv_engine* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (auto& kv : e->tw_cache) cudaFree(kv.second);
+    for (auto& t : e->unit_tables) cudaFree(t.d);
     cudaFree(e->d_frames); cudaFree(e->d_out); cudaFree(e->d_planes);
     cudaFree(e->d_keep); cudaFree(e->d_ens_sum); cudaFree(e->d_ens_cnt); cudaFree(e->d_pre_mean); cudaFree(e->d_pre_mm); cudaFree(e->d_mask_ws); cudaFree(e->d_mp_ws);
     cudaFree(e->d_proj_off); cudaFree(e->d_proj_src); cudaFree(e->d_planes_nat);
@@ -278,6 +279,8 @@ int b2piv_set_option(b2piv_engine* e, const char* name, double value) {
     else if (n == "stage_threads") { e->stage_threads = value < 0 ? 0 : (int)value; delete e->pool; e->pool = nullptr; }
     else if (n == "kernel_variant") e->variant = (int)value;
     else if (n == "run_len") e->run_len = value < 0 ? 0 : (int)value;
+    else if (n == "tmem") e->tmem = value != 0.0;
+    else if (n == "unit_parts") e->force_parts = value < 0 ? 0 : (int)value;
     else return fail(e, B2PIV_ERR_ARG, "unknown option " + n);
     return B2PIV_OK;
 }

@@ -9,6 +9,7 @@
 #include <cuda.h>   // CUtensorMap (types only; the encoder is resolved at run time, libcuda is not linked)
 
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -95,6 +96,8 @@ struct b2piv_engine {
     int variant = 0;    // 0: auto, 1: generic shared-memory FFT kernel, 2: row-per-thread TMA kernel (error if
                         // ineligible), 3: direct any-size kernel
     int run_len = 0;    // frame pairs per work unit of the rows kernel (0: auto)
+    int tmem = 1;       // 64x64 rows kernel: parked spectra in Tensor Memory (1) or in shared memory (0)
+    int force_parts = 0; // > 0: force the even work partition of the rows kernels into this many parts (tests)
     int last_variant = 0;
     float gauss_eps = 1e-7f;
     // plan
@@ -132,6 +135,10 @@ struct b2piv_engine {
     // last work enqueued on the accumulators, whatever its stream: every later user waits for it first (ens_begin / ens_add_device
     // / ens_finish may run on different streams - the engine's own or the caller's)
     cudaEvent_t ev_ens = nullptr; bool ens_pending = false;
+    // explicit work-unit lists of the row-per-thread kernels (build_unit_table), cached per problem shape
+    struct UnitTable { long long n_wp = -1; int n_pairs = -1, n_parts = -1, n_units = 0; long long cost = 0; int* d = nullptr; };
+    UnitTable unit_tables[4];
+    int unit_table_next = 0;
     // stats
     float last_kernel_ms = 0.f;
     long long launches = 0;
@@ -179,6 +186,52 @@ static inline int pick_run_len(int n_pairs, long long n_wp, long long resident) 
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_run = run; }
     }
     return best_run < 1 ? 1 : best_run;
+}
+
+// Even 1-D partition of the (window pair, frame pair) space over `n_parts` independent groups: part i gets the items
+// [i * total / n_parts, (i + 1) * total / n_parts) of the window-pair-major list, cut at window-pair boundaries into segments
+// (a segment = one work unit: a window pair followed through consecutive frame pairs, one extra forward transform at its start).
+// Layout [round][part][3] so that the kernels' round-robin walk (unit = part + round * n_parts) gives part i its own segments.
+// Returns the device table (cached in the engine) or nullptr when the partition is not worth it / not possible; *n_units and
+// *cost (frame times of the longest part) are set.
+static inline const int* build_unit_table(b2piv_engine* e, long long n_wp, int n_pairs, int n_parts, cudaStream_t st, int* n_units, long long* cost,
+                                          bool forced = false) {
+    const long long total = n_wp * (long long)n_pairs;
+    if (n_parts < 1 || total < (forced ? 1LL : 4LL) * n_parts) return nullptr;
+    for (auto& t : e->unit_tables)
+        if (t.d && t.n_wp == n_wp && t.n_pairs == n_pairs && t.n_parts == n_parts) { *n_units = t.n_units; *cost = t.cost; return t.d; }
+    std::vector<std::vector<int>> segs((size_t)n_parts);
+    size_t max_seg = 0;
+    long long worst = 0;
+    for (int i = 0; i < n_parts; ++i) {
+        long long pos = total * i / n_parts;
+        const long long end = total * (i + 1) / n_parts;
+        long long c = 0;
+        while (pos < end) {
+            const long long wp = pos / n_pairs;
+            const int f0 = (int)(pos % n_pairs);
+            const long long len = std::min<long long>(n_pairs - f0, end - pos);
+            segs[i].push_back((int)wp); segs[i].push_back(f0); segs[i].push_back(f0 + (int)len);
+            c += len + 1;
+            pos += len;
+        }
+        max_seg = std::max(max_seg, segs[i].size() / 3);
+        worst = std::max(worst, c);
+    }
+    std::vector<int> tab(max_seg * (size_t)n_parts * 3);
+    for (size_t rd = 0; rd < max_seg; ++rd)
+        for (int i = 0; i < n_parts; ++i) {
+            int* dst = &tab[(rd * (size_t)n_parts + i) * 3];
+            if (rd < segs[i].size() / 3) { dst[0] = segs[i][3 * rd]; dst[1] = segs[i][3 * rd + 1]; dst[2] = segs[i][3 * rd + 2]; }
+            else { dst[0] = -1; dst[1] = 0; dst[2] = -1; }
+        }
+    b2piv_engine::UnitTable& t = e->unit_tables[e->unit_table_next++ % 4];
+    if (t.d) { cudaStreamSynchronize(st); cudaFree(t.d); t.d = nullptr; }      // an older table may still be in use by a launch in flight
+    if (cudaMalloc((void**)&t.d, tab.size() * sizeof(int)) != cudaSuccess) { t.d = nullptr; t.n_wp = -1; cudaGetLastError(); return nullptr; }
+    if (cudaMemcpy(t.d, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(t.d); t.d = nullptr; t.n_wp = -1; cudaGetLastError(); return nullptr; }
+    t.n_wp = n_wp; t.n_pairs = n_pairs; t.n_parts = n_parts; t.n_units = (int)(max_seg * (size_t)n_parts); t.cost = worst;
+    *n_units = t.n_units; *cost = t.cost;
+    return t.d;
 }
 
 // ---- launch entry points of the kernel families (k_*.cu) ------------------------------------------------------------

@@ -17,6 +17,7 @@
 // The phases are __host__ __device__ and barrier-delimited like piv_core.cuh so tests/emul can run them on the CPU.
 #pragma once
 #include "piv_core.cuh"
+#include <cstddef>
 #include "twiddle128.h"
 
 namespace b2piv {
@@ -92,14 +93,20 @@ struct RSmem {
     // consumed into registers before the first transpose of a frame and refilled after the last one
     alignas(1024) float2 X[R::NWARP][R::XBLK];
     float nb[2][3][R::W];                        // the three plane rows around each peak (Gaussian fit)
-    float4 park[R::HS][R::NT];                   // previous frame: scaled spectra (A0, A1) at (ky <= W/2, own column), one 16-byte access
     unsigned red[R::NWARP][8];                   // block reductions (integer moments, float bits)
     unsigned long long redk[R::NWARP][2];
     unsigned rowc[R::NWARP][2];                  // per warp and window: first row (reference order) holding the warp's maximum
     int peak_j[2];                               // column of the peak, found by the thread that owns the peak's row
     unsigned long long mbar;                     // TMA completion barrier
+    // previous frame: scaled spectra (A0, A1) at (ky <= W/2, own column), one 16-byte access.  LAST member: the kernel variant
+    // that parks the spectra in Tensor Memory (rows_kernel.cuh, piv_rows_tm_kernel) packs its groups at tm_group_stride() and never
+    // touches this array
+    float4 park[R::HS][R::NT];
     B2_HD unsigned char* tile() { return reinterpret_cast<unsigned char*>(X); }
 };
+// distance between the groups of a CTA when the parked spectra live in Tensor Memory (everything but `park`)
+template <class R>
+constexpr size_t tm_group_stride() { return (offsetof(RSmem<R>, park) + 1023) / 1024 * 1024; }
 static_assert(sizeof(float2) * RCfg<64>::NWARP * RCfg<64>::XBLK >= RCfg<64>::TILE_U, "tile must fit in the transpose blocks");
 static_assert(sizeof(float2) * RCfg<64>::NWARP * RCfg<64>::XBLK >= RCfg<64>::FWIN, "float tile must fit in the transpose blocks");
 static_assert(sizeof(float2) * RCfg<32>::NWARP * RCfg<32>::XBLK >= 2 * RCfg<32>::FWIN, "float tiles must fit in the transpose blocks");
@@ -123,6 +130,10 @@ struct RParams {
     int n_pairs;                   // frame pairs in this launch (frames = n_pairs + 1)
     int run_len;                   // frame pairs per work unit
     int n_units;                   // = n_wpairs * ceil(n_pairs / run_len)
+    // optional explicit unit list [n_units][3] = (window pair, first pair, one past the last pair), window pair < 0: no unit.
+    // Kernels whose groups run independently get an even 1-D partition of the (window pair, frame pair) space this way
+    // (engine.h, build_unit_table): every group the same number of frame pairs instead of whole waves of equal units.
+    const int* unit_table;
     int clip_norm, border_nan;
     float gauss_eps;
     const unsigned char* keep;
@@ -195,12 +206,20 @@ B2_HD RUnit decode_unit(const RParams& p, int unit) {
     const int nw = p.n_rows * p.n_cols;
     const int n_wp = (nw + 1) / 2;
     RUnit u;
-    const int wp = unit % n_wp, chunk = unit / n_wp;
+    int wp, chunk = 0;
+    if (p.unit_table) {
+        wp = p.unit_table[3 * unit];
+        u.f0 = p.unit_table[3 * unit + 1];
+        u.f1 = p.unit_table[3 * unit + 2];
+        if (wp < 0) { wp = 0; u.f0 = 0; u.f1 = -1; }          // no unit: f1 - f0 + 1 = 0 frames
+    } else {
+        wp = unit % n_wp; chunk = unit / n_wp;
+        u.f0 = chunk * p.run_len;
+        u.f1 = u.f0 + p.run_len < p.n_pairs ? u.f0 + p.run_len : p.n_pairs;
+    }
     u.w[0] = 2 * wp;
     u.valid1 = (2 * wp + 1 < nw);
     u.w[1] = u.valid1 ? 2 * wp + 1 : 2 * wp;
-    u.f0 = chunk * p.run_len;
-    u.f1 = u.f0 + p.run_len < p.n_pairs ? u.f0 + p.run_len : p.n_pairs;
     for (int k = 0; k < 2; ++k) {
         u.y0[k] = (u.w[k] / p.n_cols) * p.sy;
         u.x0[k] = (u.w[k] % p.n_cols) * p.sx;
@@ -479,13 +498,20 @@ B2_HD void tr_load_set(const float2* blk, RRegs<R>& r, int lane) {
 #ifdef __CUDACC__
 // Device-side transpose for one thread.  Block b of X is read by warp b; the off-diagonal 32x32 blocks need one CTA
 // barrier, the diagonal ones are warp-synchronous.  `pre_barrier`: the other warp may still be reading its block.
-template <class R>
-__device__ __forceinline__ void transpose_device(RSmem<R>& s, RRegs<R>& r, int tid, bool pre_barrier) {
+// Barrier of one group: the whole CTA (one group per CTA, or lockstep groups), or - NAMED - hardware barrier `id` with the group's
+// R::NT threads, so that the groups of a CTA run independently (piv_rows_tm_kernel).
+template <bool NAMED, int NT>
+__device__ __forceinline__ void group_barrier(int id) {
+    if constexpr (NAMED) asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory");
+    else __syncthreads();
+}
+template <class R, bool NAMED = false>
+__device__ __forceinline__ void transpose_device(RSmem<R>& s, RRegs<R>& r, int tid, bool pre_barrier, int bar_id = 0) {
     const int lane = tid & 31, wq = tid >> 5;
     if constexpr (R::NWARP == 2) {
-        if (pre_barrier) __syncthreads();
+        if (pre_barrier) group_barrier<NAMED, R::NT>(bar_id);
         if (wq == 0) tr_store_set<R, 1>(s.X[1], r, lane); else tr_store_set<R, 0>(s.X[0], r, lane);
-        __syncthreads();
+        group_barrier<NAMED, R::NT>(bar_id);
         if (wq == 0) {
             tr_load_set<R, 1>(s.X[0], r, lane);
             __syncwarp();
@@ -573,6 +599,76 @@ __device__ __forceinline__ void rows_p3b_device(RSmem<R>& s, RRegs<R>& r, int ti
         cross_step_a<R, PAD>(s, r, tid, ky, pz, have_prev, r0, r1, pp);
         if (have_prev && ky != 0 && ky != W / 2) cross_step_b<R>(r, ky, shfl2(cross_mirror(r0, r1), pl));
     }
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------------------
+// Parked spectra in Tensor Memory.  The 33.8 KB of parked spectra per 64 x 64 group are what limits an SM to four groups
+// (8 warps, two per scheduler - far too few to hide the latencies of the non-FFT phases: ncu, round 2).  Tensor Memory
+// (256 KB per SM, idle in a kernel without tensor-core work) holds them instead: with the .32x32b shape thread t of a warp
+// owns lane 32 * (warp % 4) + t, i.e. a private row of 32-bit columns - exactly "the spectra of my column".  A thread's
+// (A0, A1)(ky) are 4 columns at 4 * ky; the warps that share a lane quarter use disjoint column ranges.  Loads are issued
+// one batch of two ky steps ahead (tcgen05.wait::ld waits for everything outstanding), stores are fire-and-forget until
+// the end of the phase.  Verified as plain scratch memory by tools/tmem_probe.cu (profiles/r02/tmem_probe.log).
+// ------------------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void tm_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tm_ld4(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tm_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tm_st4(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+// wait for the outstanding loads; the registers pass through the statement so that no use of them can be scheduled above it
+__device__ __forceinline__ void tm_wait_ld(uint32_t (&v)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]) :: "memory");
+}
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// the cross phase of rows_p3b_device with the parked spectra in Tensor Memory (native 64 x 64 / 32 x 32 windows)
+template <class R>
+__device__ __forceinline__ void rows_p3b_tm(RRegs<R>& r, int tid, uint32_t tm) {
+    constexpr int W = R::W;
+    constexpr float INVN = 1.0f / (float)R::NPX;
+    constexpr int NB = (W / 2 + 1 + 1) / 2;          // batches of two ky steps; the last one holds ky = W / 2 alone
+    const int pl = partner_lane_of<W>(tid);
+    const float b0 = r.half_alpha_new[0] * INVN, b1 = r.half_alpha_new[1] * INVN;
+    uint32_t pk[2][8];
+    tm_ld8(tm, pk[0]);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        uint32_t (&cur)[8] = pk[b & 1];
+        tm_wait_ld(cur);
+        if (b + 1 < NB) {
+            if (2 * (b + 1) + 1 <= W / 2) tm_ld8(tm + 8 * (b + 1), pk[(b + 1) & 1]); else tm_ld4(tm + 8 * (b + 1), pk[(b + 1) & 1]);
+        }
+        uint32_t out[8];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int ky = 2 * b + j;
+            if (ky <= W / 2) {
+                const float2 pz = shfl2(r.v[(W - ky) % W], pl);
+                float2 a0, a1;
+                separate(r.v[ky], pz, b0, b1, a0, a1);
+                const float2 r0 = ctw<0>(a0, __uint_as_float(cur[4 * j]), __uint_as_float(cur[4 * j + 1]));       // conj(p0) * a0
+                const float2 r1 = ctw<0>(a1, __uint_as_float(cur[4 * j + 2]), __uint_as_float(cur[4 * j + 3]));
+                out[4 * j] = __float_as_uint(a0.x); out[4 * j + 1] = __float_as_uint(a0.y);
+                out[4 * j + 2] = __float_as_uint(a1.x); out[4 * j + 3] = __float_as_uint(a1.y);
+                r.v[ky] = pk_sub(make_float2(r0.x, -r0.y), make_float2(r1.y, r1.x));                                // conj(G), G = R0 + i R1
+                if (ky != 0 && ky != W / 2) cross_step_b<R>(r, ky, shfl2(cross_mirror(r0, r1), pl));
+            }
+        }
+        if (2 * b + 1 <= W / 2) tm_st8(tm + 8 * b, out); else tm_st4(tm + 8 * b, out);
+    }
+    tm_wait_st();
 }
 #endif
 

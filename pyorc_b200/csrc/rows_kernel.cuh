@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
                 if (R::F_PHASES == 1) issue_f32(1, frame, R::FWIN);
             }
         };
-        if (has_unit && tid == 0) issue_frame_start(un.f0);
+        if (nfr > 0 && tid == 0) issue_frame_start(un.f0);
         for (int k = 0; k < maxn; ++k) {
             const bool active = k < nfr;
             const bool have_prev = k > 0;
@@ -180,6 +180,89 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// The same pipeline with the parked spectra in Tensor Memory (piv_rows.cuh, rows_p3b_tm): native uint8 windows, per-time-step
+// mode.  ONE CTA per SM holds G independent groups (G * W threads); a group synchronises on its own named barrier, fetches
+// its tiles on its own mbarrier and walks through its own work units, so the groups drift apart like separate CTAs would -
+// but without the 33.8 KB of shared memory per group that capped an SM at four of them, and with one Tensor-Memory
+// allocation (all 512 columns) for the CTA.
+// ------------------------------------------------------------------------------------------------------------
+template <class R, int G, bool ALIGNED>
+__global__ void __launch_bounds__(R::NT* G, 1) piv_rows_tm_kernel(const __grid_constant__ CUtensorMap tmap, RParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    constexpr int W = R::W;
+    constexpr int COLS = 4 * R::HS;                                   // Tensor-Memory columns per thread: (A0, A1) at ky = 0 .. W/2
+    static_assert(((R::NT * G / 32 + 3) / 4) * COLS <= 512, "the warps of a lane quarter must fit into 512 columns");
+    __shared__ uint32_t tm_base_s;
+    const int g = threadIdx.x / R::NT;     // group within the CTA
+    const int tid = threadIdx.x % R::NT;   // thread within the group (= row / column slot)
+    const int warp = threadIdx.x >> 5;
+    const int bar = g + 1;                 // named barrier of the group (0 is __syncthreads)
+    RSmem<R>& s = *reinterpret_cast<RSmem<R>*>(base + (size_t)g * tm_group_stride<R>());
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tm_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        mbar_init(&s.mbar, 1);
+        fence_mbar_init();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // lane quarter of this warp, column range of this warp within the quarter
+    const uint32_t tm = tm_base_s + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(COLS * (warp >> 2));
+    uint32_t parity = 0;
+    RRegs<R> r;
+    r.half_alpha_prev[0] = r.half_alpha_prev[1] = 0.f;
+    for (long long unit = (long long)blockIdx.x * G + g; unit < p.n_units; unit += (long long)gridDim.x * G) {
+        const RUnit un = decode_unit(p, (int)unit);
+        const int nfr = un.f1 - un.f0 + 1;
+        constexpr int TILE_BYTES = ALIGNED ? R::TILE : R::TILE_U;
+        constexpr int WIN_BYTES = TILE_BYTES / 2;
+        const int xa0 = ALIGNED ? un.x0[0] : (un.x0[0] & ~15), xa1 = ALIGNED ? un.x0[1] : (un.x0[1] & ~15);
+        const int xoff0 = un.x0[0] - xa0, xoff1 = un.x0[1] - xa1;
+        auto issue_frame_start = [&](int frame) {
+            fence_proxy_async();
+            mbar_expect_tx(&s.mbar, TILE_BYTES);
+            tma_load_3d(s.tile(), &tmap, &s.mbar, xa0, un.y0[0], frame);
+            tma_load_3d(s.tile() + WIN_BYTES, &tmap, &s.mbar, xa1, un.y0[1], frame);
+        };
+        if (tid == 0 && nfr > 0) issue_frame_start(un.f0);
+        for (int k = 0; k < nfr; ++k) {
+            const bool have_prev = k > 0;
+            const int f = un.f0 + k;
+            while (!mbar_try_wait(&s.mbar, parity)) {}
+            parity ^= 1u;
+            rows_p1<R, ALIGNED>(s, r, tid, xoff0, xoff1);
+            group_barrier<true, R::NT>(bar);  // A: integer moments visible, tile (aliased on X) fully consumed
+            rows_p2_pre<R>(s, r, tid, p.clip_norm);
+#pragma unroll 1
+            for (int st = 0; st < 4; ++st) {
+                fft_reg<W, 0>(r.v);
+                if ((st & 1) == 0) transpose_device<R, true>(s, r, tid, st != 0, bar);
+                else if (st == 1) rows_p3b_tm<R>(r, tid, tm);
+            }
+            const bool dead0 = (r.half_alpha_prev[0] == 0.f) || (r.half_alpha_new[0] == 0.f);
+            const bool dead1 = (r.half_alpha_prev[1] == 0.f) || (r.half_alpha_new[1] == 0.f);
+            rows_p5_post<R, false>(s, r, tid, dead0, dead1, &p);
+            group_barrier<true, R::NT>(bar);  // E1: block max / sum / peak row; X (and the tile aliased on it) is free again
+            if (tid == 0 && k + 1 < nfr) issue_frame_start(f + 1);
+            if (have_prev) rows_dump_planes<R, false>(r, tid, p, un, f - 1);
+            rows_p6x<R, false>(s, r, tid, &p);
+            group_barrier<true, R::NT>(bar);  // F: neighbour rows dumped, peak column published
+            if (have_prev) rows_p8<R, false>(s, r, tid, p, un, f - 1, true);
+            r.half_alpha_prev[0] = r.half_alpha_new[0];
+            r.half_alpha_prev[1] = r.half_alpha_new[1];
+        }
+        group_barrier<true, R::NT>(bar);  // unit boundary: the next unit's first TMA overwrites X
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm_base_s) : "memory");
+}
+
 // ---- tensor map + launch ---------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -248,10 +331,20 @@ static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st, const
     if (run <= 0) run = pick_run_len(gp.n_pairs, n_wp, resident);   // engine.h
     if (run > gp.n_pairs || ENS) run = gp.n_pairs;   // ensemble: one unit owns its windows' accumulators for the whole launch
     p.run_len = run;
-    const long long n_units = (long long)n_wp * ((gp.n_pairs + run - 1) / run);
-    p.n_units = (int)n_units;
+    long long n_units = (long long)n_wp * ((gp.n_pairs + run - 1) / run);
     long long grid = (n_units + G - 1) / G;
     if (grid > (long long)occ * e->sm_count) grid = (long long)occ * e->sm_count;
+    if (G == 1 && !ENS && e->run_len <= 0) {
+        // independent groups: even partition of the work instead of waves of equal units when its longest part is shorter
+        // (option "unit_parts" forces a partition into that many parts - tests)
+        const long long waves = (n_units + resident - 1) / resident;
+        const int parts = e->force_parts > 0 ? e->force_parts : (int)resident;
+        int tn = 0;
+        long long tcost = 0;
+        const int* tab = build_unit_table(e, n_wp, gp.n_pairs, parts, st, &tn, &tcost, e->force_parts > 0);
+        if (tab && (e->force_parts > 0 || tcost < waves * (run + 1))) { p.unit_table = tab; n_units = tn; grid = parts; }
+    }
+    p.n_units = (int)n_units;
     kern<<<(unsigned)grid, R::NT * G, smem, st>>>(tmap, p);
     CK(cudaGetLastError());
     e->launches++;
@@ -261,5 +354,54 @@ static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st, const
         CK(cudaGetLastError());
         e->launches++;
     }
+    return B2PIV_OK;
+}
+
+// launch of the Tensor-Memory variant (native uint8 windows, per-time-step mode)
+template <class R, int G, bool ALIGNED>
+static int launch_rows_tm(b2piv_engine* e, const Params& gp, cudaStream_t st) {
+    constexpr int W = R::W;
+    const int n_frames = gp.n_pairs + 1;
+    CUtensorMap tmap;
+    const cuuint64_t dims[3] = {(cuuint64_t)e->W, (cuuint64_t)e->H, (cuuint64_t)n_frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)gp.pitch, (cuuint64_t)gp.frame_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)(ALIGNED ? W : R::WB), (cuuint32_t)W, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapSwizzle swz = !ALIGNED ? CU_TENSOR_MAP_SWIZZLE_NONE : (W == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    const CUresult cr = get_encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(gp.frames), dims, strides, box, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(e, B2PIV_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)cr));
+    RParams p;
+    memset(&p, 0, sizeof(p));
+    p.frames = (const unsigned char*)gp.frames; p.frame_stride = gp.frame_stride; p.pitch = gp.pitch;
+    p.n_rows = gp.n_rows; p.n_cols = gp.n_cols; p.sy = gp.sy; p.sx = gp.sx; p.n_pairs = gp.n_pairs;
+    p.clip_norm = gp.clip_norm; p.border_nan = gp.border_nan; p.gauss_eps = gp.gauss_eps; p.keep = gp.keep;
+    p.u = gp.u; p.v = gp.v; p.cmax = gp.cmax; p.s2n = gp.s2n; p.planes = gp.planes; p.peer = gp.peer;
+    p.ny = p.nx = W;
+    const size_t smem = tm_group_stride<R>() * G + 1024;
+    auto kern = piv_rows_tm_kernel<R, G, ALIGNED>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long resident = (long long)e->sm_count * G;
+    const int nw = gp.n_rows * gp.n_cols, n_wp = (nw + 1) / 2;
+    int run = e->run_len;
+    if (run <= 0) run = pick_run_len(gp.n_pairs, n_wp, resident);
+    if (run > gp.n_pairs) run = gp.n_pairs;
+    p.run_len = run;
+    long long n_units = (long long)n_wp * ((gp.n_pairs + run - 1) / run);
+    long long grid = (n_units + G - 1) / G;
+    if (grid > e->sm_count) grid = e->sm_count;
+    if (e->run_len <= 0) {
+        const long long waves = (n_units + resident - 1) / resident;
+        const bool forced = e->force_parts >= G;
+        const int parts = forced ? (e->force_parts / G) * G : (int)resident;
+        int tn = 0;
+        long long tcost = 0;
+        const int* tab = build_unit_table(e, n_wp, gp.n_pairs, parts, st, &tn, &tcost, forced);
+        if (tab && (forced || tcost < waves * (run + 1))) { p.unit_table = tab; n_units = tn; grid = parts / G; }
+    }
+    p.n_units = (int)n_units;
+    kern<<<(unsigned)grid, R::NT * G, smem, st>>>(tmap, p);
+    CK(cudaGetLastError());
+    e->launches++;
     return B2PIV_OK;
 }

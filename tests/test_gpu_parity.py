@@ -674,3 +674,23 @@ def test_install_dispatch_real_engine(monkeypatch):
         assert calls == ["numba"]
     finally:
         b2frames.uninstall()
+
+
+@pytest.mark.parametrize("tmem", [1, 0])
+@pytest.mark.parametrize("ws,ov,shape,parts", [((64, 64), (32, 32), (7, 200, 304), 12), ((64, 64), (32, 32), (4, 270, 400), 6),
+                                                   ((64, 64), (40, 40), (9, 160, 208), 18), ((64, 64), (32, 32), (12, 200, 304), 30)])
+def test_rows64_even_work_partition_and_tensor_memory(engine, ws, ov, shape, parts, tmem):
+    """64x64 kernel variants: parked spectra in Tensor Memory (6 groups per SM) or in shared memory, work dealt as an even 1-D
+    partition of the (window pair, frame pair) space (forced here on small problems: parts end inside window pairs, parts
+    with several segments, more parts than window pairs) - same planes, peaks and NaN masks as the oracle."""
+    imgs = synth.particle_frames(*shape, dtype=np.uint8)
+    imgs[1:, 60:150, 100:230] = 7            # dead windows
+    engine.set_option("tmem", float(tmem))
+    engine.set_option("unit_parts", float(parts))
+    try:
+        compare(engine, imgs, ws, ov, 0, variant=2, run_len=0)
+        engine.set_option("unit_parts", 0.0)
+        compare(engine, imgs, ws, ov, 0, variant=2, run_len=3)    # the unit / wave scheme with runs of three pairs
+    finally:
+        engine.set_option("unit_parts", 0.0)
+        engine.set_option("tmem", 1.0)

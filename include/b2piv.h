@@ -46,9 +46,10 @@ int b2piv_set_option(b2piv_engine* e, const char* name, double value);
 
 /* Plan = frame geometry + window geometry.  Replaces the geometry half of ffpiv.cross_corr and
  * ffpiv.window.get_rect_coordinates (pyorc/api/frames.py:85-90): n_rows=(H-wy)/(wy-oy)+1, n_cols likewise.
- * Supported windows: any size 4..64 per axis (32x32 and 64x64 take the row-per-thread FFT kernel, other sizes up to 32 px -
- * pyorc's 10, 20, 26 ... - its exact zero-padded mode, the rest a shared-memory FFT or a direct-correlation kernel) plus
- * 64x128, 128x64, 128x128; search_area_size == window_size as pyorc
+ * Supported windows: any size 4..128 per axis - every even size pyorc can produce (frames.py:159-171).  32x32 / 64x64 /
+ * 128x128 take the row-per-thread FFT kernels, other sizes up to 32 px - pyorc's 10, 20, 26 ... - their exact zero-padded
+ * mode, 33..64 px and the rectangular powers of two a shared-memory FFT kernel, sizes with a side of 65..127 px a
+ * direct-correlation kernel (exact, O(N^2) per window: a compatibility path).  search_area_size == window_size as pyorc
  * always passes (frames.py:168). */
 int b2piv_plan(b2piv_engine* e, int height, int width, int win_y, int win_x, int ovl_y, int ovl_x, int dtype,
                int* n_rows, int* n_cols);

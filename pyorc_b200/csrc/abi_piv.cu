@@ -85,7 +85,9 @@ __global__ void __launch_bounds__(256) signal_keep_kernel(const unsigned char* _
     }
 }
 
-static bool supported(int wy, int wx) { return fft_config(wy, wx) || (wy >= 4 && wx >= 4 && wy <= 64 && wx <= 64); }
+static bool supported(int wy, int wx) { return fft_config(wy, wx) || (wy >= 4 && wx >= 4 && wy <= 128 && wx <= 128); }
+// a side above 64 px that is not a compiled FFT shape: large-window direct kernel (k_direct.cu)
+static bool big_direct(const b2piv_engine* e) { return !fft_config(e->wy, e->wx) && (e->wy > 64 || e->wx > 64); }
 
 static bool rows_eligible(const b2piv_engine* e, const void* d_frames, long long frame_stride, int pitch) {
     if (e->wy != e->wx || (e->wy != 64 && e->wy != 32)) return false;   // uint8 and float32 frames both qualify
@@ -150,6 +152,11 @@ int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
     // 2.6x the shared-memory kernel at 26x26).  Otherwise (float32 frames, caller-owned tensors with an odd pitch, larger
     // windows): tiny windows by direct correlation, the rest padded through the shared-memory FFT kernel; variant 3
     // forces the direct kernel
+    if (big_direct(e)) {
+        if (p.shift) return fail(e, B2PIV_ERR_UNSUPPORTED, "displaced windows need a window of at most 64 px per side");
+        e->last_variant = 3;
+        return launch_direct_big(e, p, st);
+    }
     const bool tiny = !fft_config(e->wy, e->wx) && e->wy * e->wx <= 144;
     if (e->variant == 4 && !pad_eligible(e, p.frames, p.frame_stride, p.pitch))
         return fail(e, B2PIV_ERR_UNSUPPORTED, "padded rows kernel needs uint8 frames, a window of at most 32 px and 16-byte aligned base/pitch");
@@ -180,6 +187,7 @@ int dispatch_ens(b2piv_engine* e, const Params& p, const EnsParams& ep, cudaStre
         return launch_rows_pad(e, p, st, &ep);
     }
     e->last_variant = 1;
+    if (big_direct(e)) return launch_direct_big_ens(e, p, ep, st);
     if ((e->variant == 3 || tiny) && e->wy <= 64 && e->wx <= 64) return launch_direct_ens(e, p, ep, st);
     return launch_generic_ens(e, p, ep, st);
 }
@@ -257,7 +265,7 @@ void b2piv_destroy(b2piv_engine* e) {
     for (auto& t : e->unit_tables) cudaFree(t.d);
     cudaFree(e->d_frames); cudaFree(e->d_out); cudaFree(e->d_planes);
     cudaFree(e->d_keep); cudaFree(e->d_ens_sum); cudaFree(e->d_ens_cnt); cudaFree(e->d_pre_mean); cudaFree(e->d_pre_mm); cudaFree(e->d_mask_ws); cudaFree(e->d_mp_ws);
-    cudaFree(e->d_proj_off); cudaFree(e->d_proj_src); cudaFree(e->d_planes_nat);
+    cudaFree(e->d_proj_off); cudaFree(e->d_proj_src); cudaFree(e->d_planes_nat); cudaFree(e->d_direct_ws);
     for (auto ev : e->ev_chunk) cudaEventDestroy(ev);
     for (int i = 0; i < 3; ++i) { if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]); if (e->ev_stage[i]) cudaEventDestroy(e->ev_stage[i]); }
     delete e->pool;
@@ -294,7 +302,7 @@ int b2piv_plan(b2piv_engine* e, int height, int width, int win_y, int win_x, int
     if (height < win_y || width < win_x) return fail(e, B2PIV_ERR_ARG, "frame smaller than the interrogation window");
     if (!supported(win_y, win_x))
         return fail(e, B2PIV_ERR_UNSUPPORTED, "window " + std::to_string(win_y) + "x" + std::to_string(win_x) +
-                                                  " not supported (any size 4..64 per axis, or 64x128 / 128x64 / 128x128)");
+                                                  " not supported (any size 4..128 per axis)");
     CK(cudaSetDevice(e->device));
     e->H = height; e->W = width; e->wy = win_y; e->wx = win_x; e->oy = ovl_y; e->ox = ovl_x; e->dtype = dtype;
     const int old_rows = e->n_rows, old_cols = e->n_cols;

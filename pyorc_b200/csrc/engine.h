@@ -130,6 +130,7 @@ struct b2piv_engine {
     int proj_h = 0, proj_w = 0, proj_out_h = 0, proj_out_w = 0; long long proj_samples = 0;
     b2piv::PeerOut peer = {};                                       // fused gather over peer memory (b2piv_set_peer_outputs)
     double* d_mp_ws = nullptr; size_t cap_mp_ws = 0;        // two-pass scheme: validated pass-1 fields
+    float* d_direct_ws = nullptr; size_t cap_direct_ws = 0; // large-window direct kernel: one correlation plane per CTA
     float* d_mask_ws = nullptr; size_t cap_mask_ws = 0;     // mask stack: time statistics / window_replace ping-pong
     float* d_ens_sum = nullptr; float* d_ens_cnt = nullptr; size_t cap_ens = 0, cap_ens_windows = 0; bool ens_open = false;
     // last work enqueued on the accumulators, whatever its stream: every later user waits for it first (ens_begin / ens_add_device
@@ -242,6 +243,8 @@ int launch_generic(b2piv_engine* e, const Params& p, cudaStream_t st);          
 int launch_generic_ens(b2piv_engine* e, const Params& p, const EnsParams& ep, cudaStream_t st);      // k_generic_ens.cu
 int launch_direct(b2piv_engine* e, const Params& p, cudaStream_t st);                                // k_direct.cu
 int launch_direct_ens(b2piv_engine* e, const Params& p, const EnsParams& ep, cudaStream_t st);
+int launch_direct_big(b2piv_engine* e, const Params& p, cudaStream_t st);                            // windows with a side of 65 .. 128 px
+int launch_direct_big_ens(b2piv_engine* e, const Params& p, const EnsParams& ep, cudaStream_t st);
 bool tma_available();                                                                                // k_rows_u8.cu
 int launch_rows_u8(b2piv_engine* e, const Params& p, cudaStream_t st);                               // 32x32 / 64x64 uint8
 int launch_rows_f32(b2piv_engine* e, const Params& p, cudaStream_t st);                              // k_rows_f32.cu

@@ -217,6 +217,7 @@ struct Params {
     const unsigned char* keep;  // optional [n_windows] keep mask (signal_threshold); nullptr = keep all
     float* u; float* v; float* cmax; float* s2n;   // [n_pairs][n_rows*n_cols]
     float* planes;            // optional debug dump [n_pairs][n_windows][WY][WX] (fftshifted, clipped), or nullptr
+    float* scratch;           // large-window direct kernel (k_direct.cu): one correlation plane per CTA, [grid][wy * wx]
     PeerOut peer;             // optional fused gather (n = 0: off)
 };
 

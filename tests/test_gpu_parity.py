@@ -317,16 +317,33 @@ def test_errors(engine):
     imgs = synth.particle_frames(2, 100, 100, dtype=np.uint8)
     big = synth.particle_frames(2, 200, 200, dtype=np.uint8)
     with pytest.raises(NotImplementedError):
-        engine.pairs(big, (96, 96), (48, 48))          # > 64 and not one of the compiled FFT shapes
-    with pytest.raises(NotImplementedError):
-        engine.pairs(big, (70, 70), (35, 35))
+        engine.pairs(big, (130, 130), (64, 64))        # beyond 128 px per side
     with pytest.raises(ValueError):
         engine.pairs(imgs[:1], (64, 64), (32, 32))
     with pytest.raises(ValueError):
         engine.pairs(imgs, (128, 128), (64, 64))  # frame smaller than window
 
 
+BIG_CASES = [   # a side of 65 .. 128 px that is not a compiled FFT shape: large-window direct kernel (pyorc accepts any even size)
+    ((66, 66), (33, 33), (3, 200, 240)),
+    ((100, 100), (50, 50), (2, 260, 320)),
+    ((126, 126), (62, 62), (2, 260, 400)),
+    ((96, 40), (48, 20), (2, 250, 130)),
+    ((70, 128), (30, 64), (2, 200, 330)),
+]
+
+
+@pytest.mark.parametrize("ws,ov,shape", BIG_CASES)
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32])
+def test_large_windows_between_the_fft_sizes(engine, ws, ov, shape, dtype):
+    imgs = synth.particle_frames(*shape, dtype=dtype)
+    imgs[:, : ws[0], : ws[1]] = 3              # a dead window
+    compare(engine, imgs, ws, ov, 0, variant=0)
+    compare(engine, imgs, ws, ov, 1, variant=0, check_planes=False, signal_threshold=0.999)
+
+
 ENS_CASES = [
+    ((100, 100), (50, 50), (5, 260, 320), 0.2, 2.0),
     ((64, 64), (32, 32), (6, 200, 304), 0.3, 2.0),
     ((32, 32), (16, 16), (6, 100, 160), 0.2, 3.0),
     ((10, 10), (5, 5), (5, 60, 80), 0.0, 0.0),

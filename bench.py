@@ -239,14 +239,17 @@ def other_configs(eng, dev, fp32_peak):
 
     peak, _ = measured_peaks()
     rows = []
-    cases = [("configs[0] geometry: 475x371, 32x32 / 50 %", 475, 371, (32, 32), (16, 16), 3, False),
-             ("configs[2] single pass: 1080p, 32x32 / 75 %", 1080, 1920, (32, 32), (24, 24), 21, False),
-             ("configs[2] two-pass (64x64 / 75 % -> 32x32 / 75 %, discrete window offset)", 1080, 1920, (32, 32), (24, 24), 21, True)]
+    c75, c50 = ((64, 64), (48, 48)), ((64, 64), (32, 32))
+    cases = [("configs[0] geometry: 475x371, 32x32 / 50 %", 475, 371, (32, 32), (16, 16), 3, None),
+             ("configs[2] single pass: 1080p, 32x32 / 75 %", 1080, 1920, (32, 32), (24, 24), 21, None),
+             ("configs[2] two-pass, discrete window offset (64x64 / 75 % -> 32x32 / 75 %; round 1's row)", 1080, 1920, (32, 32), (24, 24), 21, (c75, "offset")),
+             ("configs[2] two-pass, discrete window offset (64x64 / 50 % -> 32x32 / 75 %)", 1080, 1920, (32, 32), (24, 24), 21, (c50, "offset")),
+             ("configs[2] two-pass DEFORM: bilinear window deformation (64x64 / 50 % -> 32x32 / 75 %)", 1080, 1920, (32, 32), (24, 24), 21, (c50, "deform"))]
     for name, h, w, ws, ov, n, two_pass in cases:
         try:
             fr = synth.particle_frames_torch(n, h, w, dev, dtype="uint8")
             if two_pass:
-                ms, out = _timed(torch, dev, lambda: eng.pairs_two_pass(fr, ((64, 64), (48, 48)), (ws, ov)))
+                ms, out = _timed(torch, dev, lambda: eng.pairs_two_pass(fr, two_pass[0], (ws, ov), mode=two_pass[1]))
             else:
                 ms, out = _timed(torch, dev, lambda: eng.pairs(fr, ws, ov))
             nwin = int(out[0].numel())
@@ -255,6 +258,13 @@ def other_configs(eng, dev, fp32_peak):
                          "hbm_frac": b_alg * nwin / (ms * 1e-3) / 1e9 / peak,
                          "fp32_tflops": f_alg * nwin / (ms * 1e-3) / 1e12,
                          "fp32_frac_of_measured": f_alg * nwin / (ms * 1e-3) / 1e12 / fp32_peak if fp32_peak else None})
+            if h == 1080:   # accuracy against the imposed synthetic field (synth.displacement_field), px
+                y0 = np.arange(out[0].shape[1]) * (ws[0] - ov[0]) + ws[0] / 2.0
+                x0 = np.arange(out[0].shape[2]) * (ws[1] - ov[1]) + ws[1] / 2.0
+                yc, xc = np.meshgrid(y0, x0, indexing="ij")
+                tx, ty = synth.displacement_field(h, w, yc, xc)
+                uu, vv = out[0].cpu().numpy(), out[1].cpu().numpy()
+                rows[-1]["rmse_vs_imposed_field_px"] = float(np.sqrt(np.nanmean((uu - tx[None]) ** 2 + (vv - ty[None]) ** 2)))
             del fr, out
         except Exception as exc:   # a shard that does not fit must not take the headline down with it
             rows.append({"config": name, "error": str(exc)[:200]})

@@ -201,6 +201,18 @@ int b2piv_predictor_device(b2piv_engine* e, const float* d_u1, const float* d_v1
 int b2piv_pairs_shifted_device(b2piv_engine* e, const void* d_frames, long long frame_stride_bytes, int pitch_bytes, int n_frames,
                                const short* d_shift, float* d_u, float* d_v, float* d_corr_max, float* d_s2n, void* cuda_stream);
 
+/* Window DEFORMATION instead of a whole-pixel offset (the "deform" of configs[2]; definition: oracle/multipass_oracle.py,
+ * two_pass_deform).  deform: the validated pass-1 field is interpolated to every pixel and frame k+1 of every pair is resampled at
+ * (y + dv, x + du) (bilinear): writes the interleaved float32 stack [2 (n_frames - 1)][height][width] = (frame k, warped frame
+ * k+1) and the un-rounded predictor at the centres of the CURRENT plan's windows, float32 [n_pairs][n_windows][2] = (dv, du).
+ * pairs_interleaved: pass 2 on that stack (plan with B2PIV_F32; only the pairs (2k, 2k+1) are correlated), u, v = predictor +
+ * residual. */
+int b2piv_deform_device(b2piv_engine* e, const void* d_frames, long long frame_stride_bytes, int pitch_bytes, int dtype, int n_frames,
+                        const float* d_u1, const float* d_v1, int rows1, int cols1, int wy1, int wx1, int oy1, int ox1, float* d_stack,
+                        float* d_pred, void* cuda_stream);
+int b2piv_pairs_interleaved_device(b2piv_engine* e, const float* d_stack, int n_pairs, const float* d_pred, float* d_u, float* d_v,
+                                   float* d_corr_max, float* d_s2n, void* cuda_stream);
+
 /* ---- Fused result gather over peer memory (multi-GPU) -------------------------------------------------------
  * pyorc processes chunks sequentially in one process (pyorc/velocimetry/ffpiv.py:399-440); sharded over the GPUs of a box,
  * every rank needs the [time] axis back together.  After this call b2piv_pairs_device stores every window's four results

@@ -18,6 +18,13 @@ correlation being ffpiv's own (oracle/ffpiv_oracle.py):
   5. result: u = dx + u2, v = dy + v2; corr / s2n are those of pass 2.
 
 The accuracy claim is checked against the IMPOSED synthetic displacement field, not against another implementation.
+
+WINDOW DEFORMATION (``two_pass_deform`` - the "deform" of configs[2]; Scarano 2002, one-sided image deformation):
+  3'. the validated field is interpolated bilinearly to EVERY pixel centre (y + 0.5, x + 0.5) (edge values outside the coarse
+      grid) and frame k+1 is resampled at (y + dv, x + du): bilinear between the four neighbours, sample coordinates clamped
+      to the frame, float64 arithmetic, the result rounded once to float32 -> B'_k;
+  4'. pass 2: ffpiv correlation of the fine windows of frame k (as float32) with the SAME windows of B'_k;
+  5'. result: the un-rounded predictor at the fine window centre (float32) + the residual of pass 2.
 """
 from __future__ import annotations
 
@@ -131,3 +138,79 @@ def two_pass(imgs, coarse, fine):
     dy, dx = predictor(u1, v1, imgs.shape[-2:], coarse, fine)
     u, v, cm, sn = shifted_pass(imgs, dy, dx, ws2, ov2)
     return u, v, cm, sn, dy, dx
+
+
+# ---- window deformation ------------------------------------------------------------------------------------------------------
+def _cell(pos, w1, s1, n1):
+    f = np.clip((pos - w1 / 2.0) / s1, 0.0, n1 - 1.0)
+    i = np.minimum(np.floor(f).astype(int), max(n1 - 2, 0))
+    return i, np.minimum(i + 1, n1 - 1), f - i
+
+
+def _bilin(f, iy, iy1, ix, ix1, ty, tx):
+    """f [P, R, C] at cells (iy, ix) with weights (ty [ny], tx [nx]) -> [P, ny, nx]; operation order of the device kernel."""
+    f00 = f[:, iy][:, :, ix]
+    f01 = f[:, iy][:, :, ix1]
+    f10 = f[:, iy1][:, :, ix]
+    f11 = f[:, iy1][:, :, ix1]
+    top = f00 + (f01 - f00) * tx[None, None, :]
+    bot = f10 + (f11 - f10) * tx[None, None, :]
+    return top + (bot - top) * ty[None, :, None]
+
+
+def deform(imgs, u, v, coarse):
+    """Step 3': interleaved float32 stack [2 (n - 1), H, W] = (frame k, frame k+1 resampled with the per-pixel predictor)."""
+    imgs = np.asarray(imgs)
+    n, H, W = imgs.shape
+    (ws1, ov1) = coarse
+    R, C = u.shape[1:]
+    iy, iy1, ty = _cell(np.arange(H) + 0.5, ws1[0], ws1[0] - ov1[0], R)
+    ix, ix1, tx = _cell(np.arange(W) + 0.5, ws1[1], ws1[1] - ov1[1], C)
+    du = _bilin(np.asarray(u, np.float64), iy, iy1, ix, ix1, ty, tx)
+    dv = _bilin(np.asarray(v, np.float64), iy, iy1, ix, ix1, ty, tx)
+    yy = np.clip(np.arange(H, dtype=np.float64)[None, :, None] + dv, 0.0, H - 1.0)
+    xx = np.clip(np.arange(W, dtype=np.float64)[None, None, :] + du, 0.0, W - 1.0)
+    y0 = np.minimum(np.floor(yy).astype(int), max(H - 2, 0))
+    x0 = np.minimum(np.floor(xx).astype(int), max(W - 2, 0))
+    y1, x1 = np.minimum(y0 + 1, H - 1), np.minimum(x0 + 1, W - 1)
+    wy, wx = yy - y0, xx - x0
+    stack = np.empty((2 * (n - 1), H, W), np.float32)
+    for k in range(n - 1):
+        fb = imgs[k + 1].astype(np.float64)
+        b00, b01, b10, b11 = fb[y0[k], x0[k]], fb[y0[k], x1[k]], fb[y1[k], x0[k]], fb[y1[k], x1[k]]
+        top = b00 + (b01 - b00) * wx[k]
+        bot = b10 + (b11 - b10) * wx[k]
+        stack[2 * k] = imgs[k].astype(np.float32)
+        stack[2 * k + 1] = (top + (bot - top) * wy[k]).astype(np.float32)
+    return stack
+
+
+def predictor_float(u, v, dim_size, coarse, fine):
+    """Un-rounded predictor (dv, du) float32 [P, rows2, cols2] at the fine window centres."""
+    (ws1, ov1), (ws2, ov2) = coarse, fine
+    y2, x2 = O.window_origins(dim_size, ws2, ov2)
+    R, C = u.shape[1:]
+    iy, iy1, ty = _cell(y2 + ws2[0] / 2.0, ws1[0], ws1[0] - ov1[0], R)
+    ix, ix1, tx = _cell(x2 + ws2[1] / 2.0, ws1[1], ws1[1] - ov1[1], C)
+    du = _bilin(np.asarray(u, np.float64), iy, iy1, ix, ix1, ty, tx).astype(np.float32)
+    dv = _bilin(np.asarray(v, np.float64), iy, iy1, ix, ix1, ty, tx).astype(np.float32)
+    return dv, du
+
+
+def two_pass_deform(imgs, coarse, fine):
+    """Two-pass PIV with window deformation: returns (u, v, corr_max, s2n) on the fine grid, the stack and the predictor."""
+    imgs = np.asarray(imgs)
+    (ws1, ov1), (ws2, ov2) = coarse, fine
+    nr1, nc1 = O.get_array_shape(imgs.shape[-2:], ws1, ov1)
+    nr2, nc2 = O.get_array_shape(imgs.shape[-2:], ws2, ov2)
+    u1, v1, _, _ = O.uv_timestep(imgs, nc1, nr1, ws1, ov1)
+    u1, v1 = validate(u1, v1)
+    stack = deform(imgs, u1, v1, coarse)
+    dv, du = predictor_float(u1, v1, imgs.shape[-2:], coarse, fine)
+    P = imgs.shape[0] - 1
+    u = np.empty((P, nr2, nc2), np.float64)
+    v, cm, sn = np.empty_like(u), np.empty_like(u), np.empty_like(u)
+    for k in range(P):
+        uk, vk, ck, sk = O.uv_timestep(stack[2 * k : 2 * k + 2], nc2, nr2, ws2, ov2)
+        u[k], v[k], cm[k], sn[k] = uk[0] + du[k], vk[0] + dv[k], ck[0], sk[0]
+    return u, v, cm, sn, stack, (dv, du)

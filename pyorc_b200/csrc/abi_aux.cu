@@ -495,6 +495,45 @@ int b2piv_predictor_device(b2piv_engine* e, const float* d_u1, const float* d_v1
     return B2PIV_OK;
 }
 
+// Deformation pass of the two-pass scheme (multipass.cuh): validated pass-1 fields -> per-pixel predictor -> frame k+1 of every pair
+// resampled; writes the interleaved float32 stack [2 (n_frames - 1)][H][W] = (frame k, warped frame k+1) and the predictor at the
+// centres of the CURRENT plan's windows, float32 [n_pairs][n_rows * n_cols][2] = (dv, du).
+int b2piv_deform_device(b2piv_engine* e, const void* d_frames, long long frame_stride_bytes, int pitch_bytes, int dtype, int n_frames,
+                        const float* d_u1, const float* d_v1, int rows1, int cols1, int wy1, int wx1, int oy1, int ox1, float* d_stack,
+                        float* d_pred, void* cuda_stream) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (!e->planned) return fail(e, B2PIV_ERR_STATE, "b2piv_plan (fine grid) has not been called");
+    if (!d_frames || !d_u1 || !d_v1 || !d_stack || !d_pred) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
+    if (dtype != B2PIV_U8 && dtype != B2PIV_F32) return fail(e, B2PIV_ERR_ARG, "dtype must be B2PIV_U8 or B2PIV_F32");
+    if (n_frames < 2 || rows1 < 1 || cols1 < 1 || wy1 <= oy1 || wx1 <= ox1 || oy1 < 0 || ox1 < 0) return fail(e, B2PIV_ERR_ARG, "bad coarse grid");
+    if ((e->H - wy1) / (wy1 - oy1) + 1 != rows1 || (e->W - wx1) / (wx1 - ox1) + 1 != cols1)
+        return fail(e, B2PIV_ERR_ARG, "coarse field shape does not match the planned frame size");
+    const int esz = dtype == B2PIV_F32 ? 4 : 1;
+    if (pitch_bytes % esz || frame_stride_bytes % esz) return fail(e, B2PIV_ERR_ARG, "pitch / frame stride must be a multiple of the element size");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int n_pairs = n_frames - 1;
+    const size_t n1 = (size_t)n_pairs * rows1 * cols1;
+    int rc = ensure(e, &e->d_mp_ws, &e->cap_mp_ws, 2 * n1 * sizeof(double));
+    if (rc) return rc;
+    double* vu = e->d_mp_ws;
+    double* vv = e->d_mp_ws + n1;
+    mp_validate_kernel<<<mask_grid(e, (long long)n1, 128), 128, 0, st>>>(d_u1, d_v1, n_pairs, rows1, cols1, 0.1, 2.0, vu, vv);
+    const MpGrid g1{rows1, cols1, wy1, wx1, wy1 - oy1, wx1 - ox1};
+    const MpGrid g2{e->n_rows, e->n_cols, e->wy, e->wx, e->wy - e->oy, e->wx - e->ox};
+    const long long npx = (long long)n_pairs * e->H * e->W;
+    if (dtype == B2PIV_U8)
+        mp_deform_kernel<unsigned char><<<mask_grid(e, npx), 256, 0, st>>>((const unsigned char*)d_frames, frame_stride_bytes, pitch_bytes, n_pairs, e->H,
+                                                                          e->W, vu, vv, g1, d_stack);
+    else
+        mp_deform_kernel<float><<<mask_grid(e, npx), 256, 0, st>>>((const float*)d_frames, frame_stride_bytes / 4, pitch_bytes / 4, n_pairs, e->H, e->W, vu,
+                                                                  vv, g1, d_stack);
+    mp_predictor_float_kernel<<<mask_grid(e, (long long)n_pairs * e->n_rows * e->n_cols, 128), 128, 0, st>>>(vu, vv, n_pairs, g1, g2, d_pred);
+    CK(cudaGetLastError());
+    e->launches += 3;
+    return B2PIV_OK;
+}
+
 // ---- fp32 FMA peak of this device, measured (bench.py's `fp32.peak_measured`; tools/fp32_peak.py) --------------------------------
 // The fused PIV kernels are bound by fp32 issue, not by HBM, and MEASURED_PEAKS.json holds only the HBM and
 // bf16 tensor peaks: this is the missing denominator.  Every thread runs 16 independent FFMA chains (enough to cover the

@@ -751,6 +751,30 @@ int b2piv_pairs_shifted_device(b2piv_engine* e, const void* d_frames, long long 
     return dispatch_pairs(e, p, st);
 }
 
+// Pass 2 of the deformation scheme: `d_stack` is the interleaved float32 stack [2 n_pairs][H][W] of b2piv_deform_device, only the pairs
+// (2k, 2k+1) are correlated; d_pred [n_pairs][n_windows][2] = (dv, du) is added to (v, u).  The plan must be float32.
+int b2piv_pairs_interleaved_device(b2piv_engine* e, const float* d_stack, int n_pairs, const float* d_pred, float* d_u, float* d_v,
+                                   float* d_corr_max, float* d_s2n, void* cuda_stream) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (!e->planned) return fail(e, B2PIV_ERR_STATE, "b2piv_plan has not been called");
+    if (e->dtype != B2PIV_F32) return fail(e, B2PIV_ERR_STATE, "the interleaved stack is float32: plan with B2PIV_F32");
+    if (!d_stack || !d_u || !d_v || !d_corr_max || !d_s2n) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
+    if (n_pairs < 1) return fail(e, B2PIV_ERR_ARG, "need at least one pair");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int pitch = e->W * 4;
+    const long long fstride = (long long)e->H * pitch;
+    if (!rows_eligible(e, d_stack, fstride, pitch))
+        return fail(e, B2PIV_ERR_UNSUPPORTED, "the deformation pass runs on the row-per-thread kernel: square 32 / 64 px windows, x stride a multiple of 4, "
+                                              "frame width a multiple of 4 px");
+    Params p = base_params(e, d_stack, fstride, pitch, 2 * n_pairs - 1);
+    p.pair_step = 2;
+    p.fshift = d_pred;
+    p.u = d_u; p.v = d_v; p.cmax = d_corr_max; p.s2n = d_s2n;
+    e->last_variant = 2;
+    return launch_rows_f32(e, p, st);
+}
+
 void* b2piv_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;

@@ -97,4 +97,76 @@ __global__ void __launch_bounds__(128) mp_predictor_kernel(const double* __restr
     }
 }
 
+// ---- window DEFORMATION (BASELINE.json configs[2] "2-pass deform") -----------------------------------------------------------
+// The validated pass-1 field is interpolated to EVERY pixel (bilinear between the coarse window centres, edge values outside)
+// and frame k+1 is resampled at (y + dv, x + du) (bilinear between the four neighbours, coordinates clamped to the frame):
+// B'_k(y, x) ~ frame k+1 warped back onto frame k, so that pass 2 - an ordinary correlation of frame k with B'_k on the fine
+// grid - only sees the residual, whatever the velocity GRADIENT inside a window (a discrete offset removes the mean only).
+// The arithmetic is float64 in the operation order of the CPU definition (two-pass scheme), rounded once to float32, so the
+// warped frames are identical to the definition's.  Output: an interleaved float32 stack [2 P][H][W] = (frame k, B'_k).
+__device__ __forceinline__ double mp_interp(const double* __restrict__ f, int cols, int iy, int iy1, int ix, int ix1, double ty, double tx) {
+    const double f00 = f[iy * cols + ix], f01 = f[iy * cols + ix1], f10 = f[iy1 * cols + ix], f11 = f[iy1 * cols + ix1];
+    const double top = __dadd_rn(f00, __dmul_rn(__dsub_rn(f01, f00), tx));
+    const double bot = __dadd_rn(f10, __dmul_rn(__dsub_rn(f11, f10), tx));
+    return __dadd_rn(top, __dmul_rn(__dsub_rn(bot, top), ty));
+}
+// fractional coarse index of position `pos` (pixel-edge coordinates) along one axis, and its cell
+__device__ __forceinline__ void mp_cell(double pos, int w1, int s1, int n1, int* i0, int* i1, double* t) {
+    double f = __ddiv_rn(__dsub_rn(pos, (double)w1 / 2.0), (double)s1);
+    f = fmin(fmax(f, 0.0), (double)(n1 - 1));
+    int i = (int)floor(f);
+    i = min(i, max(n1 - 2, 0));
+    *t = __dsub_rn(f, (double)i);
+    *i0 = i;
+    *i1 = min(i + 1, n1 - 1);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) mp_deform_kernel(const T* __restrict__ frames, long long frame_stride_el, int pitch_el, int n_pairs, int H,
+                                                        int W, const double* __restrict__ u, const double* __restrict__ v, MpGrid g1,
+                                                        float* __restrict__ stack) {
+    const long long fe = (long long)H * W, n = (long long)n_pairs * fe;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W), y = (int)((i / W) % H);
+        const long long k = i / fe;
+        const T* fa = frames + k * frame_stride_el;
+        const T* fb = fa + frame_stride_el;
+        int iy, iy1, ix, ix1;
+        double ty, tx;
+        mp_cell((double)y + 0.5, g1.wy, g1.sy, g1.rows, &iy, &iy1, &ty);
+        mp_cell((double)x + 0.5, g1.wx, g1.sx, g1.cols, &ix, &ix1, &tx);
+        const long long fo = k * g1.rows * g1.cols;
+        const double du = mp_interp(u + fo, g1.cols, iy, iy1, ix, ix1, ty, tx);
+        const double dv = mp_interp(v + fo, g1.cols, iy, iy1, ix, ix1, ty, tx);
+        // sample frame k+1 at (y + dv, x + du), clamped to the frame
+        const double yy = fmin(fmax(__dadd_rn((double)y, dv), 0.0), (double)(H - 1)), xx = fmin(fmax(__dadd_rn((double)x, du), 0.0), (double)(W - 1));
+        int y0 = (int)floor(yy), x0 = (int)floor(xx);
+        y0 = min(y0, max(H - 2, 0)); x0 = min(x0, max(W - 2, 0));
+        const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+        const double wy = __dsub_rn(yy, (double)y0), wx = __dsub_rn(xx, (double)x0);
+        const double b00 = (double)fb[(long long)y0 * pitch_el + x0], b01 = (double)fb[(long long)y0 * pitch_el + x1];
+        const double b10 = (double)fb[(long long)y1 * pitch_el + x0], b11 = (double)fb[(long long)y1 * pitch_el + x1];
+        const double top = __dadd_rn(b00, __dmul_rn(__dsub_rn(b01, b00), wx));
+        const double bot = __dadd_rn(b10, __dmul_rn(__dsub_rn(b11, b10), wx));
+        stack[(2 * k) * fe + (long long)y * W + x] = (float)fa[(long long)y * pitch_el + x];
+        stack[(2 * k + 1) * fe + (long long)y * W + x] = (float)__dadd_rn(top, __dmul_rn(__dsub_rn(bot, top), wy));
+    }
+}
+// the same predictor at the centres of the fine windows, NOT rounded: float32 [n_pairs][rows2 * cols2][2] = (dv, du), what the
+// residual of pass 2 is added to
+__global__ void __launch_bounds__(128) mp_predictor_float_kernel(const double* __restrict__ u, const double* __restrict__ v, int n_pairs, MpGrid g1,
+                                                                 MpGrid g2, float* __restrict__ pred) {
+    const long long n = (long long)n_pairs * g2.rows * g2.cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % g2.cols), r = (int)((i / g2.cols) % g2.rows);
+        const long long k = i / ((long long)g2.cols * g2.rows);
+        int iy, iy1, ix, ix1;
+        double ty, tx;
+        mp_cell(__dadd_rn((double)(r * g2.sy), (double)g2.wy / 2.0), g1.wy, g1.sy, g1.rows, &iy, &iy1, &ty);
+        mp_cell(__dadd_rn((double)(c * g2.sx), (double)g2.wx / 2.0), g1.wx, g1.sx, g1.cols, &ix, &ix1, &tx);
+        const long long fo = k * g1.rows * g1.cols;
+        pred[2 * i + 0] = (float)mp_interp(v + fo, g1.cols, iy, iy1, ix, ix1, ty, tx);
+        pred[2 * i + 1] = (float)mp_interp(u + fo, g1.cols, iy, iy1, ix, ix1, ty, tx);
+    }
+}
+
 }  // namespace b2piv

@@ -217,6 +217,9 @@ struct Params {
     const unsigned char* keep;  // optional [n_windows] keep mask (signal_threshold); nullptr = keep all
     float* u; float* v; float* cmax; float* s2n;   // [n_pairs][n_rows*n_cols]
     float* planes;            // optional debug dump [n_pairs][n_windows][WY][WX] (fftshifted, clipped), or nullptr
+    const float* fshift;      // optional [n_out_pairs][n_windows][2] = (dv, du) float predictor added to (v, u) (deformation pass)
+    int pair_step;            // 0 / 1: consecutive frame pairs (k, k+1); 2: the frames are an interleaved stack (a_0, b_0, a_1, b_1 ...) and
+                              // only the pairs (2k, 2k+1) are computed, result index k (deformation pass, multipass.cuh)
     float* scratch;           // large-window direct kernel (k_direct.cu): one correlation plane per CTA, [grid][wy * wx]
     PeerOut peer;             // optional fused gather (n = 0: off)
 };

@@ -138,6 +138,8 @@ struct RParams {
     float gauss_eps;
     const unsigned char* keep;
     const short* shift;            // displaced second pass: [n_pairs][n_windows][2] = (dy, dx) of frame k+1's window, added to (v, u)
+    const float* fshift;           // deformation pass: [n_out_pairs][n_windows][2] = (dv, du) float predictor added to (v, u)
+    int pair_step;                 // 2: interleaved stack (a_0, b_0, a_1, b_1 ...), units = the pairs (2k, 2k+1), result index k; else 0 / 1
     float *u, *v, *cmax, *s2n;
     PeerOut peer;                  // optional fused gather over peer memory (piv_core.cuh)
     float* planes;
@@ -214,8 +216,11 @@ B2_HD RUnit decode_unit(const RParams& p, int unit) {
         if (wp < 0) { wp = 0; u.f0 = 0; u.f1 = -1; }          // no unit: f1 - f0 + 1 = 0 frames
     } else {
         wp = unit % n_wp; chunk = unit / n_wp;
-        u.f0 = chunk * p.run_len;
-        u.f1 = u.f0 + p.run_len < p.n_pairs ? u.f0 + p.run_len : p.n_pairs;
+        if (p.pair_step == 2) { u.f0 = 2 * chunk; u.f1 = u.f0 + 1; }
+        else {
+            u.f0 = chunk * p.run_len;
+            u.f1 = u.f0 + p.run_len < p.n_pairs ? u.f0 + p.run_len : p.n_pairs;
+        }
     }
     u.w[0] = 2 * wp;
     u.valid1 = (2 * wp + 1 < nw);
@@ -1001,10 +1006,12 @@ B2_HD void rows_p8(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p, const RU
     float oc = cmax, os = cmax / mean;
     const int widx = w == 0 ? un.w[0] : un.w[1];
     if (p.keep && !p.keep[widx]) { uu = vv = oc = os = nanf(""); }
-    const long long o = (long long)pair * p.n_rows * p.n_cols + widx;
+    const int opair = p.pair_step == 2 ? pair / 2 : pair;
+    const long long o = (long long)opair * p.n_rows * p.n_cols + widx;
     if (p.shift) { vv += (float)p.shift[2 * o]; uu += (float)p.shift[2 * o + 1]; }
+    if (p.fshift) { vv += p.fshift[2 * o]; uu += p.fshift[2 * o + 1]; }
     p.u[o] = uu; p.v[o] = vv; p.cmax[o] = oc; p.s2n[o] = os;
-    if (p.peer.n) peer_store(p.peer, pair, (long long)p.n_rows * p.n_cols, widx, uu, vv, oc, os);
+    if (p.peer.n) peer_store(p.peer, opair, (long long)p.n_rows * p.n_cols, widx, uu, vv, oc, os);
 }
 
 // optional triage dump of the full planes (fftshifted, clipped) - every thread writes its row

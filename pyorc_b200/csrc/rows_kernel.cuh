@@ -304,6 +304,7 @@ static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st, const
     p.n_rows = gp.n_rows; p.n_cols = gp.n_cols; p.sy = gp.sy; p.sx = gp.sx; p.n_pairs = gp.n_pairs;
     p.clip_norm = gp.clip_norm; p.border_nan = gp.border_nan; p.gauss_eps = gp.gauss_eps; p.keep = gp.keep;
     p.u = gp.u; p.v = gp.v; p.cmax = gp.cmax; p.s2n = gp.s2n; p.planes = gp.planes; p.peer = gp.peer;
+    p.fshift = gp.fshift; p.pair_step = gp.pair_step;
     const size_t smem = sizeof(RSmem<R>) * G + 1024;
     if (ENS) { p.corr_min = ep->corr_min; p.s2n_min = ep->s2n_min; p.ens_sum = ep->plane_sum; p.ens_count = ep->count; }
     p.ny = PAD ? e->wy : W; p.nx = PAD ? e->wx : W;
@@ -330,11 +331,12 @@ static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st, const
     int run = e->run_len;
     if (run <= 0) run = pick_run_len(gp.n_pairs, n_wp, resident);   // engine.h
     if (run > gp.n_pairs || ENS) run = gp.n_pairs;   // ensemble: one unit owns its windows' accumulators for the whole launch
+    if (gp.pair_step == 2) run = 1;                  // interleaved stack: a unit is one (a_k, b_k) pair; gp.n_pairs = 2 P - 1
     p.run_len = run;
-    long long n_units = (long long)n_wp * ((gp.n_pairs + run - 1) / run);
+    long long n_units = gp.pair_step == 2 ? (long long)n_wp * ((gp.n_pairs + 1) / 2) : (long long)n_wp * ((gp.n_pairs + run - 1) / run);
     long long grid = (n_units + G - 1) / G;
     if (grid > (long long)occ * e->sm_count) grid = (long long)occ * e->sm_count;
-    if (G == 1 && !ENS && e->run_len <= 0) {
+    if (G == 1 && !ENS && e->run_len <= 0 && gp.pair_step != 2) {
         // independent groups: even partition of the work instead of waves of equal units when its longest part is shorter
         // (option "unit_parts" forces a partition into that many parts - tests)
         const long long waves = (n_units + resident - 1) / resident;

@@ -61,6 +61,8 @@ ABI_SYMBOLS = (
     "b2piv_rotate_uv",
     "b2piv_predictor_device",
     "b2piv_pairs_shifted_device",
+    "b2piv_deform_device",
+    "b2piv_pairs_interleaved_device",
     "b2piv_set_peer_outputs",
     "b2piv_host_alloc",
     "b2piv_host_free",
@@ -125,6 +127,8 @@ def load_library(path: Optional[str] = None):
     lib.b2piv_rotate_uv.argtypes = [vp, vp, vp, cll, cd, vp, vp, vp]
     lib.b2piv_predictor_device.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, vp]
     lib.b2piv_pairs_shifted_device.argtypes = [vp, vp, cll, ci, ci, vp, vp, vp, vp, vp, vp]
+    lib.b2piv_deform_device.argtypes = [vp, vp, cll, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp, vp]
+    lib.b2piv_pairs_interleaved_device.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp]
     lib.b2piv_set_peer_outputs.argtypes = [vp, ci, vpp, cll, cll]
     lib.b2piv_host_alloc.argtypes = [ctypes.c_size_t]
     lib.b2piv_host_alloc.restype = vp
@@ -433,13 +437,16 @@ class Engine:
                                                          out[3].data_ptr(), st), "b2piv_pairs_shifted_device")
         return out[0], out[1], out[2], out[3]
 
-    def pairs_two_pass(self, frames, coarse=((64, 64), (48, 48)), fine=((32, 32), (24, 24))):
-        """Two-pass PIV with a discrete window offset (BASELINE.json configs[2]; defined in DESIGN.md §8, no reference
-        counterpart): pass 1 on the coarse grid -> validated, interpolated whole-pixel predictor -> pass 2 on the fine grid
-        with frame k+1's windows displaced.  numpy in -> numpy out; CUDA tensor in -> CUDA tensors out.
-        Returns ``u, v, corr_max, s2n`` on the fine grid (u, v = predictor + residual, px / frame)."""
+    def pairs_two_pass(self, frames, coarse=((64, 64), (32, 32)), fine=((32, 32), (24, 24)), mode: str = "offset", chunk_pairs: int = 64):
+        """Two-pass PIV (BASELINE.json configs[2]; defined in DESIGN.md, no reference counterpart):
+        pass 1 on the coarse grid -> validated predictor -> pass 2 on the fine grid.  ``mode="offset"``: frame k+1's windows are
+        displaced by the predictor rounded to whole pixels; ``mode="deform"``: frame k+1 is resampled with the per-pixel
+        predictor (bilinear window deformation), pass 2 sees the residual only.  numpy in -> numpy out; CUDA tensor in -> CUDA
+        tensors out.  Returns ``u, v, corr_max, s2n`` on the fine grid (u, v = predictor + residual, px / frame)."""
         import torch
 
+        if mode not in ("offset", "deform"):
+            raise ValueError("mode must be 'offset' or 'deform'")
         was_np = not _is_torch(frames)
         if was_np:
             a = np.asarray(frames)
@@ -448,9 +455,56 @@ class Engine:
             frames = torch.from_numpy(np.ascontiguousarray(a)).to(f"cuda:{self.device}")
         dt = np.uint8 if frames.dtype == torch.uint8 else np.float32
         u1, v1, _, _ = self.pairs(frames, coarse[0], coarse[1])
-        shift = self.predictor(u1, v1, tuple(frames.shape[-2:]), coarse, fine, dt)
-        res = self.pairs_shifted(frames, fine[0], fine[1], shift)
+        if mode == "offset":
+            shift = self.predictor(u1, v1, tuple(frames.shape[-2:]), coarse, fine, dt)
+            res = self.pairs_shifted(frames, fine[0], fine[1], shift)
+        else:
+            res = self._pairs_deformed(frames, u1, v1, coarse, fine, chunk_pairs)
         return tuple(r.cpu().numpy() for r in res) if was_np else res
+
+    def deform(self, frames, u1, v1, coarse, fine):
+        """The deformation step alone: interleaved float32 stack ``[2 (n - 1), H, W]`` = (frame k, warped frame k+1) and the
+        un-rounded predictor ``[n - 1, n_rows, n_cols, 2]`` = (dv, du) at the fine window centres (CUDA tensors)."""
+        import torch
+
+        (ws1, ov1), (ws2, ov2) = coarse, fine
+        if frames.stride(2) != 1:
+            frames = frames.contiguous()
+        self._same_device(frames)
+        n, H, W = frames.shape
+        nr, nc = self.plan((H, W), ws2, ov2, np.float32)
+        u1 = u1.contiguous().float()
+        v1 = v1.contiguous().float()
+        P, r1, c1 = u1.shape
+        if P != n - 1:
+            raise ValueError("pass-1 fields must hold one field per frame pair")
+        stack = torch.empty((2 * P, H, W), dtype=torch.float32, device=frames.device)
+        pred = torch.empty((P, nr, nc, 2), dtype=torch.float32, device=frames.device)
+        st = torch.cuda.current_stream(frames.device).cuda_stream
+        es = frames.element_size()
+        code = B2PIV_U8 if frames.dtype == torch.uint8 else B2PIV_F32
+        self._check(self._lib.b2piv_deform_device(self._h, frames.data_ptr(), frames.stride(0) * es, frames.stride(1) * es, code, n,
+                                                  u1.data_ptr(), v1.data_ptr(), r1, c1, int(ws1[0]), int(ws1[1]), int(ov1[0]), int(ov1[1]),
+                                                  stack.data_ptr(), pred.data_ptr(), st), "b2piv_deform_device")
+        return stack, pred
+
+    def _pairs_deformed(self, frames, u1, v1, coarse, fine, chunk_pairs):
+        """Pass 2 of the deformation scheme, ``chunk_pairs`` frame pairs at a time (the float32 stack of a chunk is
+        2 * chunk_pairs frames: 1 GB for 64 pairs of 1080p)."""
+        import torch
+
+        n = frames.shape[0]
+        nr, nc = self.plan(tuple(frames.shape[-2:]), fine[0], fine[1], np.float32)
+        out = torch.empty((4, n - 1, nr, nc), dtype=torch.float32, device=frames.device)
+        st = torch.cuda.current_stream(frames.device).cuda_stream
+        for a in range(0, n - 1, max(int(chunk_pairs), 1)):
+            b = min(a + max(int(chunk_pairs), 1), n - 1)
+            stack, pred = self.deform(frames[a : b + 1], u1[a:b], v1[a:b], coarse, fine)
+            self._check(self._lib.b2piv_pairs_interleaved_device(self._h, stack.data_ptr(), b - a, pred.data_ptr(), out[0, a:b].data_ptr(),
+                                                                 out[1, a:b].data_ptr(), out[2, a:b].data_ptr(), out[3, a:b].data_ptr(), st),
+                        "b2piv_pairs_interleaved_device")
+            del stack, pred
+        return out[0], out[1], out[2], out[3]
 
     def corr_planes(self, frames, window_size, overlap, signal_threshold: Optional[float] = None) -> np.ndarray:
         """Full correlation planes ``[n-1, n_windows, wy, wx]`` float32 as ``ffpiv.cross_corr`` returns them

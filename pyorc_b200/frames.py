@@ -91,14 +91,14 @@ def get_piv(
 
 # per-call options of a ``get_piv(engine="b200", ...)`` in flight in THIS thread / task (None: not a b200 call)
 _B200_CALL = contextvars.ContextVar("pyorc_b200_call", default=None)
-_B200_KWARGS = ("device", "devices", "coarse_pass")
+_B200_KWARGS = ("device", "devices", "coarse_pass", "multipass")
 
 
 def install():
     """Register ``engine="b200"`` in an importable pyorc (see INTEGRATION.md for the two-line upstream patch).
 
     Two wrappers are installed ONCE and stay: ``Frames.get_piv`` accepts ``engine="b200"`` (plus ``device=``, ``devices=``,
-    ``coarse_pass=``), runs the reference body unchanged (window rounding, coords, attrs, encoding - frames.py:156-197) with
+    ``coarse_pass=``, ``multipass=``), runs the reference body unchanged (window rounding, coords, attrs, encoding - frames.py:156-197) with
     ``engine="numba"`` passing its whitelist (frames.py:176-177) and marks the call in a context variable;
     ``pyorc.velocimetry.ffpiv.get_ffpiv`` - looked up at call time at frames.py:186 - sends a marked call to
     :func:`pyorc_b200.velocimetry.get_b2piv` and every other call to the original.  Context variables are per thread (and per

@@ -66,6 +66,7 @@ def get_b2piv(
     device: int = 0,
     coarse_pass: Optional[Tuple[Tuple[int, int], Tuple[int, int]]] = None,
     devices: Optional[Sequence[int]] = None,
+    multipass: str = "offset",
 ):
     """Time-resolved or ensemble PIV on the B200 engine; same contract as ``get_ffpiv`` (ffpiv.py:24-179).
 
@@ -82,7 +83,8 @@ def get_b2piv(
     ``coarse_pass=((wy, wx), (oy, ox))`` (no reference counterpart - ffpiv is single pass): two-pass PIV with a discrete
     window offset, BASELINE.json ``configs[2]``: a first pass on that coarse grid gives a validated, interpolated
     whole-pixel predictor, ``window_size`` / ``overlap`` are the grid of the second pass (``Engine.pairs_two_pass``);
-    per-time-step mode only.
+    per-time-step mode only.  ``multipass="deform"``: the second pass correlates frame k with frame k+1 RESAMPLED by the
+    per-pixel predictor (bilinear window deformation) instead of displacing whole windows by whole pixels.
     """
     CHUNK_SIZE_ERROR = (
         "Chunk size with selected nr of chunks ({chunks}) is 2 or less. If you manually "
@@ -155,7 +157,9 @@ def get_b2piv(
         (cwy, cwx), (coy, cox) = coarse_pass
         if cwy < window_size[0] or cwx < window_size[1] or cwy > dim_size[0] or cwx > dim_size[1]:
             raise ValueError("the coarse window must be at least as large as window_size and fit the frame")
-        coarse_pass = ((int(cwy), int(cwx)), (int(coy), int(cox)))
+        if multipass not in ("offset", "deform"):
+            raise ValueError("multipass must be 'offset' or 'deform'")
+        coarse_pass = ((int(cwy), int(cwx)), (int(coy), int(cox)), multipass)
     if ensemble_corr:
         return _get_b2piv_mean(*common, corr_min, s2n_min, count_min, signal_threshold)
     return _get_b2piv_timestep(*common, signal_threshold, coarse_pass)
@@ -164,7 +168,9 @@ def get_b2piv(
 def _get_uv_timestep(da, n_cols, n_rows, window_size, overlap, search_area_size, engine, signal_threshold=None, coarse_pass=None):
     """``u, v`` [px/frame], ``corr_max``, ``s2n`` - the narrow waist (ffpiv.py:446-474), fused on the GPU."""
     if coarse_pass is not None:
-        u, v, corr_max, s2n = engine.pairs_two_pass(_values(da), coarse_pass, (tuple(window_size), tuple(overlap)))
+        mode = coarse_pass[2] if len(coarse_pass) > 2 else "offset"
+        kw = {"mode": mode} if mode != "offset" else {}
+        u, v, corr_max, s2n = engine.pairs_two_pass(_values(da), tuple(coarse_pass[:2]), (tuple(window_size), tuple(overlap)), **kw)
     else:
         u, v, corr_max, s2n = engine.pairs(_values(da), window_size, overlap, signal_threshold=signal_threshold)
     assert u.shape[1:] == (n_rows, n_cols)

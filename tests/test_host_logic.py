@@ -22,11 +22,12 @@ class FakeEngine:
         u, v, c, s = O.uv_timestep(np.asarray(imgs), nc, nr, ws, ov, signal_threshold=signal_threshold)
         return u.astype(np.float32), v.astype(np.float32), c, s
 
-    def pairs_two_pass(self, imgs, coarse, fine):
+    def pairs_two_pass(self, imgs, coarse, fine, mode="offset"):
         from oracle import multipass_oracle as MP
 
-        self.calls.append(("two_pass", np.asarray(imgs).shape[0], coarse, fine))
-        u, v, c, s, _, _ = MP.two_pass(np.asarray(imgs), coarse, fine)
+        self.calls.append(("two_pass", np.asarray(imgs).shape[0], coarse, fine) + ((mode,) if mode != "offset" else ()))
+        fn = MP.two_pass if mode == "offset" else MP.two_pass_deform
+        u, v, c, s, _, _ = fn(np.asarray(imgs), coarse, fine)
         return u.astype(np.float32), v.astype(np.float32), c.astype(np.float32), s.astype(np.float32)
 
     def ens_begin(self, dim_size, ws, ov, dtype):

@@ -238,3 +238,112 @@ def test_gpu_get_piv_with_coarse_pass(engine):
     assert np.allclose(ds["v_x"].values, (u * res * 30.0).astype(np.float32), equal_nan=True, rtol=1e-6, atol=0)
     assert np.allclose(ds["v_y"].values, (v * res * 30.0).astype(np.float32), equal_nan=True, rtol=1e-6, atol=0)
     assert np.array_equal(ds["corr"].values, c, equal_nan=True)
+
+
+# ---- window deformation (the "deform" of configs[2]) -------------------------------------------------------------------------
+COARSE50 = ((64, 64), (32, 32))
+
+
+def test_deform_definition_uniform_field_is_a_plain_shift():
+    rng = np.random.default_rng(5)
+    imgs = rng.integers(0, 255, (2, 96, 128)).astype(np.uint8)
+    nr, nc = O.get_array_shape((96, 128), *COARSE50)
+    u = np.full((1, nr, nc), 3.0)
+    v = np.full((1, nr, nc), -2.0)
+    stack = MP.deform(imgs, u, v, COARSE50[0:2])
+    assert stack.shape == (2, 96, 128) and stack.dtype == np.float32
+    assert np.array_equal(stack[0], imgs[0].astype(np.float32))
+    # B'(y, x) = frame1(y - 2, x + 3) wherever the sample stays inside the frame
+    assert np.array_equal(stack[1][2:, :-3], imgs[1][:-2, 3:].astype(np.float32))
+    # half-pixel predictor: the mean of two neighbours
+    stack = MP.deform(imgs, u + 0.5, v, COARSE50)
+    assert np.allclose(stack[1][2:, :-4], 0.5 * (imgs[1][:-2, 3:-1].astype(np.float64) + imgs[1][:-2, 4:]), atol=1e-4)
+    dv, du = MP.predictor_float(u + 0.5, v, (96, 128), COARSE50, FINE)
+    assert np.all(du == 3.5) and np.all(dv == -2.0) and du.shape == (1,) + O.get_array_shape((96, 128), *FINE)
+
+
+def test_two_pass_deform_definition_recovers_the_imposed_field():
+    H, W = 192, 256
+    imgs = synth.particle_frames(2, H, W, dtype=np.uint8)
+    u, v, c, s, stack, (dv, du) = MP.two_pass_deform(imgs, COARSE50, FINE)
+    y0, x0 = O.window_origins((H, W), *FINE)
+    yc, xc = np.meshgrid(y0 + 16.0, x0 + 16.0, indexing="ij")
+    tx, ty = synth.displacement_field(H, W, yc, xc)
+    assert np.nanmedian(np.abs(u[0] - tx)) < 0.1 and np.nanmedian(np.abs(v[0] - ty)) < 0.1
+    one = O.uv_timestep(imgs, *O.get_array_shape((H, W), *FINE)[::-1], *FINE)
+    assert np.nanmean(c) > np.nanmean(one[2])       # the warped frame correlates better than the raw one
+
+
+@gpu
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32])
+def test_gpu_deformed_stack_and_predictor_equal_the_definition(engine, dtype):
+    import torch
+
+    H, W = 200, 288
+    imgs = synth.particle_frames(4, H, W, dtype=dtype)
+    nr1, nc1 = O.get_array_shape((H, W), *COARSE50)
+    u1, v1, _, _ = O.uv_timestep(imgs, nc1, nr1, *COARSE50)
+    u1, v1 = u1.astype(np.float32), v1.astype(np.float32)      # the pass-1 fields the engine hands over are float32
+    u1[0, 1, 2] = np.nan                    # a hole and an outlier for the validation step
+    v1[1, 0, 0] = 25.0
+    vu, vv = MP.validate(u1, v1)
+    want = MP.deform(imgs, vu, vv, COARSE50)
+    wdv, wdu = MP.predictor_float(vu, vv, (H, W), COARSE50, FINE)
+    d = torch.from_numpy(imgs).cuda()
+    stack, pred = engine.deform(d, torch.from_numpy(u1).cuda(), torch.from_numpy(v1).cuda(), COARSE50, FINE)
+    got = stack.cpu().numpy()
+    assert got.shape == want.shape
+    assert np.array_equal(got[0::2], want[0::2])
+    assert np.abs(got[1::2] - want[1::2]).max() <= 1e-4          # float64 arithmetic in the same order: differences are last-bit roundings
+    assert (got[1::2] != want[1::2]).mean() < 1e-3
+    p = pred.cpu().numpy()
+    assert np.abs(p[..., 0] - wdv).max() <= 1e-6 and np.abs(p[..., 1] - wdu).max() <= 1e-6
+
+
+@gpu
+def test_gpu_two_pass_deform_against_definition_and_truth(engine):
+    H, W = 360, 480
+    imgs = synth.particle_frames(3, H, W, dtype=np.uint8)
+    engine.set_option("clip_normalized", 0.0)
+    O.CLIP_NORMALIZED = False
+    gu, gv, gc, gs = engine.pairs_two_pass(imgs, COARSE50, FINE, mode="deform")
+    u, v, c, s, _, _ = MP.two_pass_deform(imgs, COARSE50, FINE)
+    assert gu.shape == u.shape == (2,) + O.get_array_shape((H, W), *FINE)
+    assert np.array_equal(np.isnan(gu), np.isnan(u))
+    fin = np.isfinite(u) & np.isfinite(gu)
+    close = np.abs(gu[fin] - u[fin]) + np.abs(gv[fin] - v[fin]) < 4e-3
+    assert close.mean() >= 0.995
+    assert np.abs(gc[fin][close] - c[fin][close]).max() <= 1e-5
+    y0, x0 = O.window_origins((H, W), *FINE)
+    yc, xc = np.meshgrid(y0 + 16.0, x0 + 16.0, indexing="ij")
+    tx, ty = synth.displacement_field(H, W, yc, xc)
+    off = engine.pairs_two_pass(imgs, COARSE50, FINE, mode="offset")
+    one = engine.pairs(imgs, *FINE)
+    err = lambda r: np.nanmedian(np.abs(r[0] - tx[None])) + np.nanmedian(np.abs(r[1] - ty[None]))   # noqa: E731
+    assert err((gu, gv)) < 0.15 and err((gu, gv)) <= err(off) + 0.01 and err((gu, gv)) <= err(one) + 0.01
+    assert np.nanmean(gc) >= np.nanmean(off[2]) - 1e-3 and np.nanmean(gc) > np.nanmean(one[2])
+    # chunking of the float32 stack does not change anything
+    g2 = engine.pairs_two_pass(imgs, COARSE50, FINE, mode="deform", chunk_pairs=1)
+    assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip((gu, gv, gc, gs), g2))
+
+
+@gpu
+def test_gpu_get_piv_with_deformation(engine):
+    """`get_piv(..., coarse_pass=..., multipass="deform")`: the deformation scheme behind the get_piv-shaped binding."""
+    from pyorc_b200 import _xr
+    from pyorc_b200 import frames as b2frames
+    from pyorc_b200.engine import get_engine
+
+    get_engine(0).set_option("clip_normalized", 0.0)
+    engine.set_option("clip_normalized", 0.0)
+    H, W, res = 200, 288, 0.01
+    imgs = synth.particle_frames(5, H, W, dtype=np.uint8)
+    da = _xr.DataArray(imgs, ("time", "y", "x"), {"time": np.arange(5) / 30.0, "y": np.flipud(np.linspace(res / 2, res * (H - 0.5), H)),
+                                                  "x": np.linspace(res / 2, res * (W - 0.5), W)})
+    ds = b2frames.get_piv(da, window_size=32, overlap=(24, 24), engine="b200", resolution=res, coarse_pass=COARSE50, multipass="deform", chunksize=3)
+    u, v, c, s = engine.pairs_two_pass(imgs, COARSE50, FINE, mode="deform")
+    assert ds["v_x"].values.shape == u.shape
+    assert np.allclose(ds["v_x"].values, (u * res * 30.0).astype(np.float32), equal_nan=True, rtol=1e-6, atol=0)
+    assert np.array_equal(ds["corr"].values, c, equal_nan=True)
+    with pytest.raises(ValueError):
+        b2frames.get_piv(da, window_size=32, overlap=(24, 24), engine="b200", resolution=res, coarse_pass=COARSE50, multipass="spline")

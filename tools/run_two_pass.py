@@ -1,19 +1,40 @@
-"""Two-pass timing (development aid): repeated device-resident runs + per-stage CUDA-event times."""
+"""Two-pass PIV of BASELINE configs[2] on 1080p: discrete window offset vs window deformation, coarse pass at 75 % / 50 % overlap
+(development aid; bench.py reports the same rows)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch
+import numpy as np, torch
 from pyorc_b200.engine import Engine
 from pyorc_b200 import synth
-e = Engine(0)
+from oracle import ffpiv_oracle as O
+
+H, W, N = 1080, 1920, 41
 dev = torch.device("cuda", 0)
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 41
-fr = synth.particle_frames_torch(n, 1080, 1920, dev, dtype="uint8")
-coarse, fine = ((64, 64), (48, 48)), ((32, 32), (24, 24))
-def ev(): return torch.cuda.Event(enable_timing=True)
-for rep in range(6):
-    a, b, c, d = ev(), ev(), ev(), ev()
-    a.record(); u1, v1, _, _ = e.pairs(fr, *coarse)
-    b.record(); sh = e.predictor(u1, v1, (1080, 1920), coarse, fine)
-    c.record(); out = e.pairs_shifted(fr, *fine, sh)
-    d.record(); torch.cuda.synchronize()
-    print(f"rep {rep}: pass1 {a.elapsed_time(b):.3f} ms  predictor {b.elapsed_time(c):.3f} ms  pass2 {c.elapsed_time(d):.3f} ms  total {a.elapsed_time(d):.3f} ms  -> {out[0].numel() / a.elapsed_time(d) / 1e3:.1f} Mwin/s", flush=True)
+e = Engine(0)
+fr = synth.particle_frames_torch(N, H, W, dev, dtype="uint8")
+FINE = ((32, 32), (24, 24))
+y0, x0 = O.window_origins((H, W), *FINE)
+yc, xc = np.meshgrid(y0 + 16.0, x0 + 16.0, indexing="ij")
+tx, ty = synth.displacement_field(H, W, yc, xc)
+
+def timed(fn, reps=5):
+    for _ in range(2):
+        out = fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); out = fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts)), out
+
+def report(name, ms, out):
+    u, v = out[0].cpu().numpy(), out[1].cpu().numpy()
+    nwin = u.size
+    rmse = np.sqrt(np.nanmean((u - tx[None]) ** 2 + (v - ty[None]) ** 2))
+    print(f"{name:58s} {ms:7.3f} ms  {nwin / ms / 1e3:7.1f} M fine windows/s  rmse vs imposed field {rmse:.4f} px  finite {np.isfinite(u).mean():.4f}  corr {float(torch.nanmean(out[2])):.4f}", flush=True)
+
+ms, out = timed(lambda: e.pairs(fr, *FINE)); report("single pass 32x32 / 75 %", ms, out)
+for coarse in (((64, 64), (48, 48)), ((64, 64), (32, 32))):
+    for mode in ("offset", "deform"):
+        ms, out = timed(lambda: e.pairs_two_pass(fr, coarse, FINE, mode=mode))
+        report(f"two-pass {mode}, coarse {coarse[0][0]}x{coarse[0][1]} / {100 * coarse[1][0] // coarse[0][0]} %", ms, out)

@@ -27,7 +27,7 @@ def normalize(frames: np.ndarray, samples: int = 15) -> np.ndarray:
 
 
 def minmax(frames: np.ndarray, min=-np.inf, max=np.inf) -> np.ndarray:  # noqa: A002
-    return np.maximum(np.minimum(frames, max), min).astype(frames.dtype)
+    return np.maximum(np.minimum(frames, max), min)   # pyorc/api/frames.py:361 verbatim: float64 whenever a bound is a Python float
 
 
 def time_diff(frames: np.ndarray, thres: float = 0.0, abs: bool = False) -> np.ndarray:  # noqa: A002

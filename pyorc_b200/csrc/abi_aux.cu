@@ -20,6 +20,7 @@ static int pre_grid(const b2piv_engine* e, long long n) {
 int b2piv_pre_normalize_device(b2piv_engine* e, const void* d_frames, int dtype, int n_frames, int height, int width, int time_interval,
                                unsigned char* d_out, void* cuda_stream) {
     if (!e) return B2PIV_ERR_ARG;
+    NvtxRange nvtx_range("b2piv_pre_normalize_device");
     if (!d_frames || !d_out) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
     if (dtype != B2PIV_U8 && dtype != B2PIV_F32) return fail(e, B2PIV_ERR_ARG, "dtype must be B2PIV_U8 or B2PIV_F32");
     if (n_frames < 1 || height < 1 || width < 1) return fail(e, B2PIV_ERR_ARG, "bad shape");
@@ -107,6 +108,7 @@ static bool gauss_taps(int ksize, float* k) {
 int b2piv_pre_gauss_device(b2piv_engine* e, const void* d_frames, int dtype, int n_frames, int height, int width, int ksize1, int ksize2,
                            float* d_out, void* cuda_stream) {
     if (!e) return B2PIV_ERR_ARG;
+    NvtxRange nvtx_range("b2piv_pre_gauss_device");
     if (!d_frames || !d_out) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
     if (dtype != B2PIV_U8 && dtype != B2PIV_F32) return fail(e, B2PIV_ERR_ARG, "dtype must be B2PIV_U8 or B2PIV_F32");
     GaussTaps taps;
@@ -222,6 +224,7 @@ extern "C" {
 
 int b2piv_project_device(b2piv_engine* e, const void* d_frames, int dtype, int n_frames, void* d_out, int out_dtype, void* cuda_stream) {
     if (!e) return B2PIV_ERR_ARG;
+    NvtxRange nvtx_range("b2piv_project_device");
     if (!e->d_proj_off) return fail(e, B2PIV_ERR_STATE, "b2piv_project_plan has not been called");
     if (!d_frames || !d_out) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
     if (dtype != B2PIV_U8 && dtype != B2PIV_F32) return fail(e, B2PIV_ERR_ARG, "dtype must be B2PIV_U8 or B2PIV_F32");
@@ -471,6 +474,7 @@ int b2piv_rotate_uv(b2piv_engine* e, const float* d_u, const float* d_v, long lo
 int b2piv_predictor_device(b2piv_engine* e, const float* d_u1, const float* d_v1, int n_pairs, int rows1, int cols1, int wy1, int wx1,
                            int oy1, int ox1, short* d_shift, void* cuda_stream) {
     if (!e) return B2PIV_ERR_ARG;
+    NvtxRange nvtx_range("b2piv_predictor_device");
     if (!e->planned) return fail(e, B2PIV_ERR_STATE, "b2piv_plan (fine grid) has not been called");
     if (!d_u1 || !d_v1 || !d_shift) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
     if (n_pairs < 1 || rows1 < 1 || cols1 < 1 || wy1 <= oy1 || wx1 <= ox1 || oy1 < 0 || ox1 < 0)
@@ -502,6 +506,7 @@ int b2piv_deform_device(b2piv_engine* e, const void* d_frames, long long frame_s
                         const float* d_u1, const float* d_v1, int rows1, int cols1, int wy1, int wx1, int oy1, int ox1, float* d_stack,
                         float* d_pred, void* cuda_stream) {
     if (!e) return B2PIV_ERR_ARG;
+    NvtxRange nvtx_range("b2piv_deform_device");
     if (!e->planned) return fail(e, B2PIV_ERR_STATE, "b2piv_plan (fine grid) has not been called");
     if (!d_frames || !d_u1 || !d_v1 || !d_stack || !d_pred) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
     if (dtype != B2PIV_U8 && dtype != B2PIV_F32) return fail(e, B2PIV_ERR_ARG, "dtype must be B2PIV_U8 or B2PIV_F32");

@@ -335,6 +335,7 @@ int b2piv_plan(b2piv_engine* e, int height, int width, int win_y, int win_x, int
 int b2piv_pairs_device(b2piv_engine* e, const void* d_frames, long long frame_stride_bytes, int pitch_bytes, int n_frames,
                        float signal_threshold, float* d_u, float* d_v, float* d_corr_max, float* d_s2n, void* cuda_stream) {
     if (!e) return B2PIV_ERR_ARG;
+    NvtxRange nvtx_range("b2piv_pairs_device");
     if (!e->planned) return fail(e, B2PIV_ERR_STATE, "b2piv_plan has not been called");
     if (!d_frames || !d_u || !d_v || !d_corr_max || !d_s2n) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
     if (n_frames < 2) return fail(e, B2PIV_ERR_ARG, "need at least 2 frames (one pair)");
@@ -499,6 +500,7 @@ extern "C" {
 int b2piv_pairs_host(b2piv_engine* e, const void* frames, int n_frames, float signal_threshold, float* u, float* v,
                      float* corr_max, float* s2n) {
     if (!e) return B2PIV_ERR_ARG;
+    NvtxRange nvtx_range("b2piv_pairs_host");
     if (!e->planned) return fail(e, B2PIV_ERR_STATE, "b2piv_plan has not been called");
     if (!frames || !u || !v || !corr_max || !s2n) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
     if (n_frames < 2) return fail(e, B2PIV_ERR_ARG, "need at least 2 frames (one pair)");
@@ -536,6 +538,7 @@ int b2piv_pairs_host(b2piv_engine* e, const void* frames, int n_frames, float si
 
 int b2piv_corr_planes_host(b2piv_engine* e, const void* frames, int n_frames, float signal_threshold, float* corr) {
     if (!e) return B2PIV_ERR_ARG;
+    NvtxRange nvtx_range("b2piv_corr_planes_host");
     if (!e->planned) return fail(e, B2PIV_ERR_STATE, "b2piv_plan has not been called");
     if (!frames || !corr) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
     if (n_frames < 2) return fail(e, B2PIV_ERR_ARG, "need at least 2 frames (one pair)");
@@ -618,6 +621,7 @@ int b2piv_ens_add_device(b2piv_engine* e, const void* d_frames, long long frame_
                          float corr_min, float s2n_min, float signal_threshold, float* d_corr_max, float* d_s2n,
                          void* cuda_stream) {
     if (!e) return B2PIV_ERR_ARG;
+    NvtxRange nvtx_range("b2piv_ens_add_device");
     if (!e->planned || !e->ens_open) return fail(e, B2PIV_ERR_STATE, "call b2piv_plan and b2piv_ens_begin first");
     if (!d_frames || !d_corr_max || !d_s2n) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
     if (n_frames < 2) return fail(e, B2PIV_ERR_ARG, "need at least 2 frames (one pair)");
@@ -644,6 +648,7 @@ int b2piv_ens_add_device(b2piv_engine* e, const void* d_frames, long long frame_
 int b2piv_ens_add_host(b2piv_engine* e, const void* frames, int n_frames, float corr_min, float s2n_min,
                        float signal_threshold, float* corr_max, float* s2n) {
     if (!e) return B2PIV_ERR_ARG;
+    NvtxRange nvtx_range("b2piv_ens_add_host");
     if (!e->planned || !e->ens_open) return fail(e, B2PIV_ERR_STATE, "call b2piv_plan and b2piv_ens_begin first");
     if (!frames || !corr_max || !s2n) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
     if (n_frames < 2) return fail(e, B2PIV_ERR_ARG, "need at least 2 frames (one pair)");
@@ -680,6 +685,7 @@ int b2piv_ens_accum(b2piv_engine* e, float** d_plane_sum, float** d_count, long 
 int b2piv_ens_finish_device(b2piv_engine* e, float min_count, long long first_window, long long n_windows, float* d_u, float* d_v,
                             void* cuda_stream) {
     if (!e) return B2PIV_ERR_ARG;
+    NvtxRange nvtx_range("b2piv_ens_finish_device");
     if (!e->planned || !e->ens_open) return fail(e, B2PIV_ERR_STATE, "call b2piv_plan and b2piv_ens_begin first");
     if (!d_u || !d_v) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
     const long long nw = (long long)e->n_rows * e->n_cols;
@@ -740,6 +746,7 @@ int b2piv_peaks_host(b2piv_engine* e, const float* corr, long long n_planes, int
 int b2piv_pairs_shifted_device(b2piv_engine* e, const void* d_frames, long long frame_stride_bytes, int pitch_bytes, int n_frames,
                                const short* d_shift, float* d_u, float* d_v, float* d_corr_max, float* d_s2n, void* cuda_stream) {
     if (!e) return B2PIV_ERR_ARG;
+    NvtxRange nvtx_range("b2piv_pairs_shifted_device");
     if (!e->planned) return fail(e, B2PIV_ERR_STATE, "b2piv_plan has not been called");
     if (!d_frames || !d_shift || !d_u || !d_v || !d_corr_max || !d_s2n) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
     if (n_frames < 2) return fail(e, B2PIV_ERR_ARG, "need at least 2 frames (one pair)");
@@ -756,6 +763,7 @@ int b2piv_pairs_shifted_device(b2piv_engine* e, const void* d_frames, long long 
 int b2piv_pairs_interleaved_device(b2piv_engine* e, const float* d_stack, int n_pairs, const float* d_pred, float* d_u, float* d_v,
                                    float* d_corr_max, float* d_s2n, void* cuda_stream) {
     if (!e) return B2PIV_ERR_ARG;
+    NvtxRange nvtx_range("b2piv_pairs_interleaved_device");
     if (!e->planned) return fail(e, B2PIV_ERR_STATE, "b2piv_plan has not been called");
     if (e->dtype != B2PIV_F32) return fail(e, B2PIV_ERR_STATE, "the interleaved stack is float32: plan with B2PIV_F32");
     if (!d_stack || !d_u || !d_v || !d_corr_max || !d_s2n) return fail(e, B2PIV_ERR_ARG, "NULL pointer");

@@ -9,6 +9,7 @@
 #include <cuda.h>   // CUtensorMap (types only; the encoder is resolved at run time, libcuda is not linked)
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges show up when a tool (nsys / ncu --nvtx) is attached, otherwise no-ops
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -19,6 +20,12 @@
 #include <string>
 #include <thread>
 #include <vector>
+
+// NVTX range around an ABI call (the reference has no tracing at all; its tqdm bars are the closest thing)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // Ensemble accumulate (pyorc/velocimetry/ffpiv.py:200-243 thresholds, :361-363 accumulation)
 struct EnsParams {

@@ -217,6 +217,18 @@ class _PinnedPool:
             self._lib.b2piv_host_free(ptr)
 
 
+def _serialised(fn):
+    """Run an Engine method under the engine's lock (re-entrant: the composite calls nest)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with self.lock:
+            return fn(self, *args, **kwargs)
+
+    return wrapper
+
+
 class Engine:
     """One PIV engine bound to one CUDA device (mirrors the role of ffpiv's ``engine=`` back-ends)."""
 
@@ -231,6 +243,12 @@ class Engine:
         self._h = h
         self.device = int(device)
         self._plan = None
+        # An engine owns workspaces (device copy of the frames, result block, keep mask, ensemble accumulators ...) that its calls
+        # share: one host thread at a time.  The lock makes a second thread WAIT instead of racing on them (pyorc under dask's
+        # threaded scheduler); independent work belongs on a second engine (get_engine(device, slot)).
+        import threading
+
+        self.lock = threading.RLock()
         self._pinned = []
         self._results = _PinnedPool(self._lib)
         if clip_normalized is not None:
@@ -298,6 +316,7 @@ class Engine:
         return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     # ---- plan -----------------------------------------------------------------------------------------------
+    @_serialised
     def plan(self, dim_size: Tuple[int, int], window_size: Tuple[int, int], overlap: Tuple[int, int], dtype) -> Tuple[int, int]:
         """Fix frame and window geometry; returns ``(n_rows, n_cols)``."""
         dt = np.dtype(dtype) if not isinstance(dtype, int) else None
@@ -355,6 +374,7 @@ class Engine:
             raise ValueError(f"frames are on cuda:{t.device.index}, engine on cuda:{self.device}")
 
     # ---- per-time-step ----------------------------------------------------------------------------------------
+    @_serialised
     def pairs(self, frames, window_size, overlap, signal_threshold: Optional[float] = None, stream=None):
         """``u, v, corr_max, s2n`` for every consecutive frame pair, each ``[n-1, n_rows, n_cols]`` float32.
 
@@ -390,6 +410,7 @@ class Engine:
         return tuple(outs)
 
     # ---- fused multi-GPU gather ---------------------------------------------------------------------------------
+    @_serialised
     def set_peer_outputs(self, peer_ptrs, pairs_total: int, pair_offset: int):
         """Make :meth:`pairs` (device tensors) also store its results straight into every peer's gather buffer
         ``[4, pairs_total, n_rows, n_cols]`` float32 (raw device pointers, e.g. ``symm_mem_handle.buffer_ptrs``) at this
@@ -400,6 +421,7 @@ class Engine:
                     "b2piv_set_peer_outputs")
 
     # ---- two-pass (BASELINE configs[2]) -----------------------------------------------------------------------
+    @_serialised
     def predictor(self, u1, v1, dim_size, coarse, fine, dtype=np.uint8):
         """Whole-pixel window shifts ``[n_pairs, n_rows, n_cols, 2]`` (dy, dx; int16, on the device) for a second pass on the
         ``fine = (window_size, overlap)`` grid from the pass-1 fields ``u1, v1`` of the ``coarse`` grid (CUDA tensors):
@@ -417,6 +439,7 @@ class Engine:
                                                      int(ov1[0]), int(ov1[1]), shift.data_ptr(), st), "b2piv_predictor_device")
         return shift
 
+    @_serialised
     def pairs_shifted(self, frames, window_size, overlap, shift):
         """Second pass: frame k+1's window of every (pair, window) displaced by ``shift[pair, row, col] = (dy, dx)``;
         returns ``u, v`` (= shift + residual), ``corr_max, s2n`` as CUDA tensors.  ``frames``: CUDA tensor [n, H, W]."""
@@ -437,6 +460,7 @@ class Engine:
                                                          out[3].data_ptr(), st), "b2piv_pairs_shifted_device")
         return out[0], out[1], out[2], out[3]
 
+    @_serialised
     def pairs_two_pass(self, frames, coarse=((64, 64), (32, 32)), fine=((32, 32), (24, 24)), mode: str = "offset", chunk_pairs: int = 64):
         """Two-pass PIV (BASELINE.json configs[2]; defined in DESIGN.md, no reference counterpart):
         pass 1 on the coarse grid -> validated predictor -> pass 2 on the fine grid.  ``mode="offset"``: frame k+1's windows are
@@ -462,6 +486,7 @@ class Engine:
             res = self._pairs_deformed(frames, u1, v1, coarse, fine, chunk_pairs)
         return tuple(r.cpu().numpy() for r in res) if was_np else res
 
+    @_serialised
     def deform(self, frames, u1, v1, coarse, fine):
         """The deformation step alone: interleaved float32 stack ``[2 (n - 1), H, W]`` = (frame k, warped frame k+1) and the
         un-rounded predictor ``[n - 1, n_rows, n_cols, 2]`` = (dv, du) at the fine window centres (CUDA tensors)."""
@@ -506,6 +531,7 @@ class Engine:
             del stack, pred
         return out[0], out[1], out[2], out[3]
 
+    @_serialised
     def corr_planes(self, frames, window_size, overlap, signal_threshold: Optional[float] = None) -> np.ndarray:
         """Full correlation planes ``[n-1, n_windows, wy, wx]`` float32 as ``ffpiv.cross_corr`` returns them
         (triage / parity only - the fast path never materialises them)."""
@@ -519,6 +545,7 @@ class Engine:
         self._check(self._lib.b2piv_corr_planes_host(self._h, frames.ctypes.data, n, thr, corr.ctypes.data), "b2piv_corr_planes_host")
         return corr
 
+    @_serialised
     def peaks(self, corr) -> Tuple[np.ndarray, np.ndarray]:
         """``u, v`` (pixels, shape ``corr.shape[:-2]``) of arbitrary correlation planes ``[..., wy, wx]``: first-occurrence
         argmax + 3-point Gaussian fit minus the centre - ``ffpiv.u_v_displacement`` without the reshape."""
@@ -534,6 +561,7 @@ class Engine:
         return u.reshape(lead), v.reshape(lead)
 
     # ---- ensemble ---------------------------------------------------------------------------------------------
+    @_serialised
     def ens_begin(self, dim_size, window_size, overlap, dtype, stream=None, device_ordered: bool = False):
         """Zero the accumulators.  ``device_ordered`` (or a ``stream``): stream-ordered on torch's current stream (or
         ``stream``) without synchronising; otherwise on the engine's own stream, synchronous."""
@@ -547,6 +575,7 @@ class Engine:
             self._check(self._lib.b2piv_ens_begin(self._h), "b2piv_ens_begin")
         return nr, nc
 
+    @_serialised
     def ens_add(self, frames, window_size, overlap, corr_min=0.2, s2n_min=3.0, signal_threshold=None, stream=None):
         """Accumulate one chunk; returns masked per-pair ``corr_max, s2n`` ``[n-1, n_windows]``."""
         frames, n, nr, nc, on_dev = self._prep(frames, window_size, overlap)
@@ -577,6 +606,7 @@ class Engine:
         )
         return cm, sn
 
+    @_serialised
     def ens_accumulators(self):
         """torch views of the device accumulators ``(plane_sum [n_windows, wy * wx], count [n_windows])`` so that ranks can
         reduce them before the peak fit.  The engine orders its own calls on the accumulators whatever their streams; work
@@ -592,6 +622,7 @@ class Engine:
         count = torch.as_tensor(_CudaView(pc.value, (nw.value,)), device=dev)
         return plane.view(nw.value, -1), count
 
+    @_serialised
     def ens_finish(self, min_count: float):
         """Count filter + mean plane + peak fit; returns ``u, v, count`` each ``[n_windows]`` (numpy; synchronous, ordered
         after every earlier ``ens_add`` whatever stream it ran on)."""
@@ -602,6 +633,7 @@ class Engine:
         self._check(self._lib.b2piv_ens_finish_host(self._h, float(min_count), u.ctypes.data, v.ctypes.data, cnt.ctypes.data), "b2piv_ens_finish_host")
         return u, v, cnt
 
+    @_serialised
     def ens_finish_device(self, min_count: float, first_window: int = 0, n_windows: Optional[int] = None, stream=None):
         """Peak fit of the windows ``[first_window, first_window + n_windows)`` on torch's current stream (or ``stream``):
         returns CUDA tensors ``u, v`` ``[n_windows]``, no synchronisation.  After a reduce-scatter of the plane sums over the

@@ -18,6 +18,7 @@ from .velocimetry import get_b2piv
 __all__ = ["get_piv", "get_piv_coords", "install", "uninstall"]
 
 ENGINES = ["b200"]
+ENCODING_PARAMS = {"zlib": True, "dtype": "int16", "scale_factor": 0.01, "_FillValue": -9999}   # pyorc/const.py:80
 
 
 def get_piv_coords(frames, window_size, search_area_size, overlap):
@@ -85,7 +86,25 @@ def get_piv(
         "res_y": resolution,
     }
     ds = get_b2piv(frames, coords["y"], coords["x"], dt, engine=engine, ensemble_corr=ensemble_corr, **kwargs)
+    # metadata like the reference body (frames.py:190-196): the frames' attrs, the camera configuration actually used when it
+    # can serialise itself, and pyorc's int16 CF encoding on the four variables (const.py:80-83).  The 2-D mesh coordinates
+    # (xs, ys, lon, lat, xp, yp) need pyorc's CameraConfig and are added by the reference's own body - `install()`.
     ds.attrs = dict(getattr(frames, "attrs", {}))
+    if camera_config is not None and hasattr(camera_config, "to_json"):
+        try:
+            import copy
+
+            cc = copy.deepcopy(camera_config)
+            if window_size is not None:
+                cc.window_size = window_size
+            ds.attrs["camera_config"] = cc.to_json()
+        except Exception:  # a foreign object that cannot be copied / serialised keeps the frames' own attribute
+            pass
+    for k in ("v_x", "v_y", "corr", "s2n"):
+        try:
+            ds[k].encoding = dict(ENCODING_PARAMS)
+        except Exception:
+            pass
     return ds
 
 

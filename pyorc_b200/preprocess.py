@@ -88,11 +88,17 @@ def time_diff(frames, thres: float = 0.0, abs: bool = False, device: int = 0):  
 
 
 def minmax(frames, min=-np.inf, max=np.inf, device: int = 0):  # noqa: A002
-    """Bound intensities to ``[min, max]`` (dtype preserved)."""
+    """Bound intensities to ``[min, max]``: ``np.maximum(np.minimum(frames, max), min)`` (pyorc/api/frames.py:343-361).
+    VALUES are the reference's.  dtype: numpy promotes uint8 frames to float64 as soon as a bound is a Python float - the
+    +-inf defaults included - although the clamped values stay whole numbers unless a bound has a fraction; here uint8 frames
+    stay uint8 (a quarter of the bytes, the integer PIV path) when the finite bounds are whole numbers, and are clamped as
+    float32 when a bound has a fraction (``min=10.5`` clamps a pixel to 10.5, not 10)."""
     import torch
 
     eng = get_engine(device)
     t, was_np = _to_device(frames, eng)
+    if t.dtype == torch.uint8 and any(np.isfinite(b) and float(b) != np.floor(b) for b in (min, max)):
+        t = t.float()
     out = torch.empty_like(t)
     lo = float(np.clip(min, -3.0e38, 3.0e38))
     hi = float(np.clip(max, -3.0e38, 3.0e38))

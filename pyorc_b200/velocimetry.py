@@ -24,6 +24,22 @@ from .engine import get_engine, merge_ensembles
 __all__ = ["get_b2piv", "load_frame_chunk"]
 
 
+def _metrics_sidecar(record: dict):
+    """One JSON line per ``get_b2piv`` call in the file ``$B2PIV_METRICS`` names (the reference logs nothing about
+    its PIV step; here: windows, windows/s, algorithmic bytes and flops of SURVEY.md 8d, wall time, devices)."""
+    import json
+    import os
+
+    path = os.environ.get("B2PIV_METRICS")
+    if not path:
+        return
+    try:
+        with open(path, "a") as f:
+            f.write(json.dumps(record) + "\n")
+    except OSError:
+        pass
+
+
 def load_frame_chunk(da):
     """Load a frame chunk into memory; on ``TypeError`` retry with one frame less (ffpiv.py:13-21)."""
     if not hasattr(da, "load"):
@@ -160,9 +176,26 @@ def get_b2piv(
         if multipass not in ("offset", "deform"):
             raise ValueError("multipass must be 'offset' or 'deform'")
         coarse_pass = ((int(cwy), int(cwx)), (int(coy), int(cox)), multipass)
+    import time as _time
+
+    t0 = _time.perf_counter()
     if ensemble_corr:
-        return _get_b2piv_mean(*common, corr_min, s2n_min, count_min, signal_threshold)
-    return _get_b2piv_timestep(*common, signal_threshold, coarse_pass)
+        ds = _get_b2piv_mean(*common, corr_min, s2n_min, count_min, signal_threshold)
+    else:
+        ds = _get_b2piv_timestep(*common, signal_threshold, coarse_pass)
+    wall = _time.perf_counter() - t0
+    n_win = (n_total - 1) * n_rows * n_cols
+    wy, wx = window_size
+    s_in = 1 if getattr(frames, "dtype", None) == np.uint8 else 4
+    _metrics_sidecar({
+        "call": "get_b2piv", "mode": "ensemble" if ensemble_corr else ("two-pass " + coarse_pass[2] if coarse_pass else "per-time-step"),
+        "frames": n_total, "frame_shape": [int(dim_size[0]), int(dim_size[1])], "window": [int(wy), int(wx)], "overlap": [int(overlap[0]), int(overlap[1])],
+        "chunks": len(bounds), "devices": devices, "windows": int(n_win), "wall_s": wall, "windows_per_s": n_win / wall if wall > 0 else None,
+        "alg_bytes": int(n_win * (2 * (wy - overlap[0]) * (wx - overlap[1]) * s_in + 16)),
+        "alg_flops": float(n_win * (3 * 2.5 * wy * wx * np.log2(wy * wx) + 6 * wy * (wx // 2 + 1))),
+        "kernel_launches": int(sum(getattr(e, "launch_count", 0) for e in engs)),
+    })
+    return ds
 
 
 def _get_uv_timestep(da, n_cols, n_rows, window_size, overlap, search_area_size, engine, signal_threshold=None, coarse_pass=None):

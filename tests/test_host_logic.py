@@ -301,3 +301,38 @@ def test_device_thread_errors_propagate(fake):
     velocimetry.get_engine(1).pairs = boom
     with pytest.raises(RuntimeError, match="device lost"):
         velocimetry.get_b2piv(da, np.arange(nr), np.arange(nc), np.full(5, 1 / 30), (32, 32), (16, 16), (32, 32), res, res, devices=[0, 1])
+
+
+def test_get_piv_sets_encoding_and_keeps_attrs(fake):
+    da, res = make_frames(n=3)
+    ds = b2frames.get_piv(da, window_size=32, engine="b200", resolution=res)
+    for k in ("v_x", "v_y", "corr", "s2n"):
+        assert ds[k].encoding == {"zlib": True, "dtype": "int16", "scale_factor": 0.01, "_FillValue": -9999}   # pyorc/const.py:80-83
+    assert ds.attrs == da.attrs
+
+    class Cfg:   # duck-typed camera configuration: window size / resolution defaults, JSON like CameraConfig.to_json
+        window_size, resolution = 25, res
+
+        def to_json(self):
+            return '{"window_size": %d}' % self.window_size
+
+    ds = b2frames.get_piv(da, engine="b200", camera_config=Cfg())
+    nr, nc = O.get_array_shape((100, 140), (26, 26), (12, 12))     # 25 -> 26 (round_to_even), overlap int(round(25) / 2)
+    assert ds["v_x"].values.shape == (2, nr, nc) and ds.attrs["camera_config"] == '{"window_size": 25}'
+    ds = b2frames.get_piv(da, window_size=32, engine="b200", camera_config=Cfg())
+    assert ds.attrs["camera_config"] == '{"window_size": 32}'       # frames.py:194-195: the window size actually used
+
+
+def test_metrics_sidecar_one_json_line_per_call(fake, tmp_path, monkeypatch):
+    import json
+
+    path = tmp_path / "b2piv_metrics.jsonl"
+    monkeypatch.setenv("B2PIV_METRICS", str(path))
+    da, res = make_frames(n=6)
+    nr, nc = O.get_array_shape((100, 140), (32, 32), (16, 16))
+    velocimetry.get_b2piv(da, np.arange(nr), np.arange(nc), np.full(5, 1 / 30), (32, 32), (16, 16), (32, 32), res, res, chunksize=4)
+    velocimetry.get_b2piv(da, np.arange(nr), np.arange(nc), np.full(5, 1 / 30), (32, 32), (16, 16), (32, 32), res, res, ensemble_corr=True)
+    recs = [json.loads(line) for line in open(path)]
+    assert [r["mode"] for r in recs] == ["per-time-step", "ensemble"]
+    assert recs[0]["windows"] == 5 * nr * nc and recs[0]["chunks"] == 2 and recs[0]["alg_bytes"] == 5 * nr * nc * (2 * 16 * 16 + 16)
+    assert recs[0]["windows_per_s"] > 0 and recs[0]["devices"] == [0]

@@ -78,7 +78,11 @@ def test_gpu_normalize_minmax_timediff_bit_exact(dtype, shape):
         a, b = G.normalize(fr, samples=15), P.normalize(fr, samples=15)     # float mean: summation order differs by an ulp
         assert (np.abs(a.astype(int) - b.astype(int)) <= 1).all() and (a != b).mean() < 1e-3
     assert np.array_equal(G.minmax(fr, min=20, max=180), P.minmax(fr, min=20, max=180))
-    assert np.array_equal(G.minmax(fr, max=100), P.minmax(fr, max=100))
+    assert np.array_equal(G.minmax(fr, max=100), P.minmax(fr, max=100)) and G.minmax(fr, max=100).dtype == fr.dtype   # same values; dtype kept
+    # fractional bounds: numpy promotes uint8 frames to floating point and keeps the fraction (pyorc/api/frames.py:343-361)
+    want = np.maximum(np.minimum(fr, 180.25), 20.5)
+    got = G.minmax(fr, min=20.5, max=180.25)
+    assert got.dtype == np.float32 and np.array_equal(got, want.astype(np.float32)) and got.min() == 20.5
     for thres, ab in ((0.0, False), (5.0, False), (2.0, True)):
         assert np.array_equal(G.time_diff(fr, thres=thres, abs=ab), P.time_diff(fr, thres=thres, abs=ab))
     with pytest.raises(AssertionError):

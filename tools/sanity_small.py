@@ -25,6 +25,18 @@ if __name__ == "__main__":
         fr = frames(5, 200, 304)
         e.ens_begin((200, 304), (64, 64), (32, 32), np.uint8); e.ens_add(fr, (64, 64), (32, 32), corr_min=0.2, s2n_min=3.0)
         u, v, cnt = e.ens_finish(0.2); print("ens", float(np.nanmean(u)))
+    if which in ("all", "rows64smem"):
+        e.set_option("tmem", 0.0)
+        out = e.pairs(frames(4, 200, 304), (64, 64), (32, 32)); print("rows64 (parked spectra in shared memory)", float(torch.nanmean(out[0])))
+        e.set_option("tmem", 1.0)
+    if which in ("all", "parts"):
+        e.set_option("unit_parts", 12.0)
+        out = e.pairs(frames(6, 200, 304), (64, 64), (32, 32)); print("rows64 tmem, forced even partition", float(torch.nanmean(out[0])))
+        e.set_option("unit_parts", 0.0)
+    if which in ("all", "big"):
+        out = e.pairs(frames(3, 200, 260), (100, 100), (50, 50)); print("direct 100x100", float(torch.nanmean(out[0])))
+    if which in ("all", "deform"):
+        out = e.pairs_two_pass(frames(4, 200, 288), mode="deform"); print("two-pass deform", float(torch.nanmean(out[0])))
     if which in ("all", "f32"):
         out = e.pairs(frames(3, 200, 304, "float32"), (64, 64), (32, 32)); print("rows64 f32", float(torch.nanmean(out[0])))
     torch.cuda.synchronize()

@@ -60,6 +60,13 @@ int b2piv_plan(b2piv_engine* e, int height, int width, int win_y, int win_x, int
 int b2piv_pairs_host(b2piv_engine* e, const void* frames, int n_frames, float signal_threshold, float* u, float* v,
                      float* corr_max, float* s2n);
 
+/* The same call with the unit conversion of `_get_ffpiv_timestep` fused in (ffpiv.py:418-419: `u * res_x / dt`, `v * res_y / dt`,
+ * float32): v_x, v_y come back in m / s - float32 product with the resolution, float64 division by the pair's time step `dt[k]`
+ * (host array, n_frames - 1 values), one rounding to float32, i.e. numpy's arithmetic for a float32 `u` - computed while the
+ * fields are still in HBM instead of in four numpy passes on the host. */
+int b2piv_pairs_host_units(b2piv_engine* e, const void* frames, int n_frames, float signal_threshold, float res_x, float res_y, const double* dt,
+                           float* v_x, float* v_y, float* corr_max, float* s2n);
+
 /* Same on DEVICE-resident frames (stream-ordered, no synchronisation): rows `pitch_bytes` apart, frames
  * `frame_stride_bytes` apart.  Output pointers are device memory.  `cuda_stream` is a cudaStream_t (may be 0). */
 int b2piv_pairs_device(b2piv_engine* e, const void* d_frames, long long frame_stride_bytes, int pitch_bytes,

@@ -58,6 +58,17 @@ __global__ void __launch_bounds__(256) ens_finish_kernel(const float* __restrict
     }
 }
 
+// px / frame -> m / s on the device, the arithmetic of `u * res_x / dt` in numpy for a float32 `u` (pyorc/velocimetry/ffpiv.py:418-419):
+// float32 product with the float32-rounded resolution, float64 division by the pair's dt, one rounding to float32
+__global__ void __launch_bounds__(256) units_kernel(float* __restrict__ u, float* __restrict__ v, long long n, long long nw, float res_x, float res_y,
+                                                    const double* __restrict__ dt) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double d = dt[i / nw];
+        u[i] = (float)((double)__fmul_rn(u[i], res_x) / d);
+        v[i] = (float)((double)__fmul_rn(v[i], res_y) / d);
+    }
+}
+
 // signal_threshold: fraction of non-zero pixels of a window over all frames of the call (ffpiv.py:93-97).
 __global__ void __launch_bounds__(256) signal_keep_kernel(const unsigned char* __restrict__ frames, long long frame_stride,
                                                           int pitch, int is_f32, int n_frames, int n_cols, int wy, int wx,
@@ -265,7 +276,7 @@ void b2piv_destroy(b2piv_engine* e) {
     for (auto& t : e->unit_tables) cudaFree(t.d);
     cudaFree(e->d_frames); cudaFree(e->d_out); cudaFree(e->d_planes);
     cudaFree(e->d_keep); cudaFree(e->d_ens_sum); cudaFree(e->d_ens_cnt); cudaFree(e->d_pre_mean); cudaFree(e->d_pre_mm); cudaFree(e->d_mask_ws); cudaFree(e->d_mp_ws);
-    cudaFree(e->d_proj_off); cudaFree(e->d_proj_src); cudaFree(e->d_planes_nat); cudaFree(e->d_direct_ws);
+    cudaFree(e->d_proj_off); cudaFree(e->d_proj_src); cudaFree(e->d_planes_nat); cudaFree(e->d_direct_ws); cudaFree(e->d_dt);
     for (auto ev : e->ev_chunk) cudaEventDestroy(ev);
     for (int i = 0; i < 3; ++i) { if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]); if (e->ev_stage[i]) cudaEventDestroy(e->ev_stage[i]); }
     delete e->pool;
@@ -497,10 +508,11 @@ static int pipeline_host(b2piv_engine* e, const void* frames, int n_frames, bool
 
 extern "C" {
 
-int b2piv_pairs_host(b2piv_engine* e, const void* frames, int n_frames, float signal_threshold, float* u, float* v,
-                     float* corr_max, float* s2n) {
+static int pairs_host_impl(b2piv_engine* e, const void* frames, int n_frames, float signal_threshold, float* u, float* v, float* corr_max, float* s2n,
+                           const double* dt, float res_x, float res_y) {
     if (!e) return B2PIV_ERR_ARG;
     NvtxRange nvtx_range("b2piv_pairs_host");
+    if (dt && !(res_x > 0.f && res_y > 0.f)) return fail(e, B2PIV_ERR_ARG, "resolution must be positive");
     if (!e->planned) return fail(e, B2PIV_ERR_STATE, "b2piv_plan has not been called");
     if (!frames || !u || !v || !corr_max || !s2n) return fail(e, B2PIV_ERR_ARG, "NULL pointer");
     if (n_frames < 2) return fail(e, B2PIV_ERR_ARG, "need at least 2 frames (one pair)");
@@ -526,6 +538,17 @@ int b2piv_pairs_host(b2piv_engine* e, const void* frames, int n_frames, float si
         return dispatch_pairs(e, p, e->s_comp);
     });
     if (rc) return rc;
+    if (dt) {   // unit conversion while the fields are still in HBM (one tiny launch instead of four numpy passes on the host)
+        rc = ensure(e, &e->d_dt, &e->cap_dt, n_pairs * sizeof(double));
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(e->d_dt, dt, n_pairs * sizeof(double), cudaMemcpyHostToDevice, e->s_comp));
+        const long long n = (long long)field;
+        long long g = (n + 255) / 256;
+        if (g > (long long)e->sm_count * 8) g = (long long)e->sm_count * 8;
+        units_kernel<<<(unsigned)g, 256, 0, e->s_comp>>>(e->d_out, e->d_out + field, n, (long long)nw, res_x, res_y, e->d_dt);
+        CK(cudaGetLastError());
+        e->launches++;
+    }
     CK(cudaMemcpyAsync(u, e->d_out + 0 * field, field * sizeof(float), cudaMemcpyDeviceToHost, e->s_comp));
     CK(cudaMemcpyAsync(v, e->d_out + 1 * field, field * sizeof(float), cudaMemcpyDeviceToHost, e->s_comp));
     CK(cudaMemcpyAsync(corr_max, e->d_out + 2 * field, field * sizeof(float), cudaMemcpyDeviceToHost, e->s_comp));
@@ -534,6 +557,17 @@ int b2piv_pairs_host(b2piv_engine* e, const void* frames, int n_frames, float si
     CK(cudaStreamSynchronize(e->s_copy));
     CK(cudaEventElapsedTime(&e->last_kernel_ms, e->ev_k0, e->ev_k1));
     return B2PIV_OK;
+}
+
+int b2piv_pairs_host(b2piv_engine* e, const void* frames, int n_frames, float signal_threshold, float* u, float* v,
+                     float* corr_max, float* s2n) {
+    return pairs_host_impl(e, frames, n_frames, signal_threshold, u, v, corr_max, s2n, nullptr, 0.f, 0.f);
+}
+
+int b2piv_pairs_host_units(b2piv_engine* e, const void* frames, int n_frames, float signal_threshold, float res_x, float res_y, const double* dt,
+                           float* v_x, float* v_y, float* corr_max, float* s2n) {
+    if (!dt) return e ? fail(e, B2PIV_ERR_ARG, "NULL pointer") : B2PIV_ERR_ARG;
+    return pairs_host_impl(e, frames, n_frames, signal_threshold, v_x, v_y, corr_max, s2n, dt, res_x, res_y);
 }
 
 int b2piv_corr_planes_host(b2piv_engine* e, const void* frames, int n_frames, float signal_threshold, float* corr) {

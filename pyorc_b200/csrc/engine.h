@@ -164,6 +164,7 @@ struct b2piv_engine {
     int proj_h = 0, proj_w = 0, proj_out_h = 0, proj_out_w = 0; long long proj_samples = 0;
     b2piv::PeerOut peer = {};                                       // fused gather over peer memory (b2piv_set_peer_outputs)
     double* d_mp_ws = nullptr; size_t cap_mp_ws = 0;        // two-pass scheme: validated pass-1 fields
+    double* d_dt = nullptr; size_t cap_dt = 0;              // per-pair time steps of b2piv_pairs_host_units
     float* d_direct_ws = nullptr; size_t cap_direct_ws = 0; // large-window direct kernel: one correlation plane per CTA
     float* d_mask_ws = nullptr; size_t cap_mask_ws = 0;     // mask stack: time statistics / window_replace ping-pong
     float* d_ens_sum = nullptr; float* d_ens_cnt = nullptr; size_t cap_ens = 0, cap_ens_windows = 0; bool ens_open = false;

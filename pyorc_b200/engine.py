@@ -30,6 +30,7 @@ ABI_SYMBOLS = (
     "b2piv_set_option",
     "b2piv_plan",
     "b2piv_pairs_host",
+    "b2piv_pairs_host_units",
     "b2piv_pairs_device",
     "b2piv_corr_planes_host",
     "b2piv_ens_begin",
@@ -95,6 +96,7 @@ def load_library(path: Optional[str] = None):
     lib.b2piv_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_double]
     lib.b2piv_plan.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
     lib.b2piv_pairs_host.argtypes = [vp, vp, ci, cf, vp, vp, vp, vp]
+    lib.b2piv_pairs_host_units.argtypes = [vp, vp, ci, cf, cf, cf, vp, vp, vp, vp, vp]
     lib.b2piv_pairs_device.argtypes = [vp, vp, cll, ci, ci, cf, vp, vp, vp, vp, vp]
     lib.b2piv_corr_planes_host.argtypes = [vp, vp, ci, cf, vp]
     lib.b2piv_ens_begin.argtypes = [vp]
@@ -231,6 +233,8 @@ def _serialised(fn):
 
 class Engine:
     """One PIV engine bound to one CUDA device (mirrors the role of ffpiv's ``engine=`` back-ends)."""
+
+    fused_units = True      # pairs(..., units=...) converts px / frame to m / s on the device
 
     def __init__(self, device: int = 0, clip_normalized: Optional[bool] = None, border_nan: Optional[bool] = None,
                  gauss_eps: Optional[float] = None):
@@ -375,11 +379,13 @@ class Engine:
 
     # ---- per-time-step ----------------------------------------------------------------------------------------
     @_serialised
-    def pairs(self, frames, window_size, overlap, signal_threshold: Optional[float] = None, stream=None):
+    def pairs(self, frames, window_size, overlap, signal_threshold: Optional[float] = None, stream=None, units=None):
         """``u, v, corr_max, s2n`` for every consecutive frame pair, each ``[n-1, n_rows, n_cols]`` float32.
 
         numpy in -> numpy out (H2D/D2H inside, synchronous); torch CUDA tensor in -> torch CUDA tensors out
-        (stream-ordered on ``stream`` or torch's current stream, no synchronisation)."""
+        (stream-ordered on ``stream`` or torch's current stream, no synchronisation).
+        ``units=(res_x, res_y, dt)`` (host frames): ``u, v`` come back in m / s, ``u * res_x / dt[k]`` with numpy's float32 /
+        float64 arithmetic (ffpiv.py:418-419), converted on the device before the D2H copy."""
         frames, n, nr, nc, on_dev = self._prep(frames, window_size, overlap)
         if n < 2:
             raise ValueError("need at least 2 frames (one frame pair)")
@@ -387,6 +393,8 @@ class Engine:
         if on_dev:
             import torch
 
+            if units is not None:
+                raise TypeError("units= applies to host (numpy) frames; device results stay in px / frame")
             self._same_device(frames)
             st, ctx = _stream_ctx(torch, frames.device, stream)
             with ctx:
@@ -403,6 +411,17 @@ class Engine:
         # the four fields are views of ONE page-locked block that returns to the engine's pool when they are all released
         block = self._results.empty((4, n - 1, nr, nc), np.float32)
         outs = [block[k] for k in range(4)]
+        if units is not None:
+            res_x, res_y, dt = units
+            dt = np.ascontiguousarray(dt, dtype=np.float64).reshape(-1)
+            if dt.size != n - 1:
+                raise ValueError("units: dt must hold one time step per frame pair")
+            self._check(
+                self._lib.b2piv_pairs_host_units(self._h, frames.ctypes.data, n, thr, float(np.float32(res_x)), float(np.float32(res_y)),
+                                                 dt.ctypes.data, *[o.ctypes.data for o in outs]),
+                "b2piv_pairs_host_units",
+            )
+            return tuple(outs)
         self._check(
             self._lib.b2piv_pairs_host(self._h, frames.ctypes.data, n, thr, *[o.ctypes.data for o in outs]),
             "b2piv_pairs_host",

@@ -198,12 +198,15 @@ def get_b2piv(
     return ds
 
 
-def _get_uv_timestep(da, n_cols, n_rows, window_size, overlap, search_area_size, engine, signal_threshold=None, coarse_pass=None):
-    """``u, v`` [px/frame], ``corr_max``, ``s2n`` - the narrow waist (ffpiv.py:446-474), fused on the GPU."""
+def _get_uv_timestep(da, n_cols, n_rows, window_size, overlap, search_area_size, engine, signal_threshold=None, coarse_pass=None, units=None):
+    """``u, v`` [px/frame], ``corr_max``, ``s2n`` - the narrow waist (ffpiv.py:446-474), fused on the GPU.  ``units=(res_x, res_y,
+    dt)``: the engine converts to m / s itself (single pass only)."""
     if coarse_pass is not None:
         mode = coarse_pass[2] if len(coarse_pass) > 2 else "offset"
         kw = {"mode": mode} if mode != "offset" else {}
         u, v, corr_max, s2n = engine.pairs_two_pass(_values(da), tuple(coarse_pass[:2]), (tuple(window_size), tuple(overlap)), **kw)
+    elif units is not None:
+        u, v, corr_max, s2n = engine.pairs(_values(da), window_size, overlap, signal_threshold=signal_threshold, units=units)
     else:
         u, v, corr_max, s2n = engine.pairs(_values(da), window_size, overlap, signal_threshold=signal_threshold)
     assert u.shape[1:] == (n_rows, n_cols)
@@ -272,9 +275,14 @@ def _get_b2piv_timestep(frames, bounds, times, dt_vals, y, x, res_y, res_x, n_ro
         b = a + len(da)
         time = times[a + 1 : b]
         dt_chunk = dt_vals[a : b - 1]
-        u, v, corr_max, s2n = _get_uv_timestep(da, n_cols, n_rows, window_size, overlap, window_size, eng, signal_threshold, coarse_pass)
-        u = (u * res_x / np.expand_dims(dt_chunk, (1, 2))).astype(np.float32)
-        v = (v * res_y / np.expand_dims(dt_chunk, (1, 2))).astype(np.float32)
+        if coarse_pass is None and getattr(eng, "fused_units", False):
+            # px -> m/s inside the engine call (ffpiv.py:418-419 with numpy's own float32 / float64 arithmetic), no host passes
+            u, v, corr_max, s2n = _get_uv_timestep(da, n_cols, n_rows, window_size, overlap, window_size, eng, signal_threshold, None,
+                                                   units=(res_x, res_y, dt_chunk))
+        else:
+            u, v, corr_max, s2n = _get_uv_timestep(da, n_cols, n_rows, window_size, overlap, window_size, eng, signal_threshold, coarse_pass)
+            u = (u * res_x / np.expand_dims(dt_chunk, (1, 2))).astype(np.float32)
+            v = (v * res_y / np.expand_dims(dt_chunk, (1, 2))).astype(np.float32)
         ds = xr.Dataset(
             {
                 "s2n": (["time", "y", "x"], s2n),
@@ -294,6 +302,8 @@ def _get_b2piv_timestep(frames, bounds, times, dt_vals, y, x, res_y, res_x, n_ro
     # (the reference runs gc.collect() after every chunk to get its window stacks and correlation planes - GBs - out of RAM,
     # ffpiv.py:436-438; nothing of that size exists here, and a full collection costs ~35 ms in a process that has torch loaded,
     # nine times the whole 100-pair 1080p call)
+    if len(ds_piv_chunks) == 1:       # nothing to concatenate: no copy of the four fields
+        return ds_piv_chunks[0]
     return xr.concat(ds_piv_chunks, dim="time")
 
 

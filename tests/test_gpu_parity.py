@@ -711,3 +711,22 @@ def test_rows64_even_work_partition_and_tensor_memory(engine, ws, ov, shape, par
     finally:
         engine.set_option("unit_parts", 0.0)
         engine.set_option("tmem", 1.0)
+
+
+def test_fused_unit_conversion_is_numpys_arithmetic(engine):
+    """`pairs(..., units=(res_x, res_y, dt))` = `(u * res / dt[:, None, None]).astype(float32)` bit for bit (float32 product,
+    float64 division, one rounding - what numpy does for a float32 `u`, pyorc/velocimetry/ffpiv.py:418-419), non-uniform dt."""
+    imgs = synth.particle_frames(6, 200, 304, dtype=np.uint8)
+    imgs[:, :64, :64] = 0
+    ws, ov = (64, 64), (32, 32)
+    engine.set_option("kernel_variant", 0.0)
+    u, v, c, s = engine.pairs(imgs, ws, ov)
+    dt = np.array([1 / 30.0, 1 / 25.0, 0.04, 1 / 29.97, 0.0333])
+    res_x, res_y = 0.01, 0.0125
+    vx, vy, c2, s2 = engine.pairs(imgs, ws, ov, units=(res_x, res_y, dt))
+    want_x = (u * res_x / np.expand_dims(dt, (1, 2))).astype(np.float32)
+    want_y = (v * res_y / np.expand_dims(dt, (1, 2))).astype(np.float32)
+    assert np.array_equal(vx, want_x, equal_nan=True) and np.array_equal(vy, want_y, equal_nan=True)
+    assert np.array_equal(c, c2) and np.array_equal(s, s2, equal_nan=True)
+    with pytest.raises(ValueError):
+        engine.pairs(imgs, ws, ov, units=(res_x, res_y, dt[:3]))

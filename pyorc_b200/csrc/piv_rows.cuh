@@ -58,7 +58,7 @@ B2_HD void fft_reg(float2* v) {
 // ------------------------------------------------------------------------------------------------------------
 // Configuration / shared memory / parameters
 // ------------------------------------------------------------------------------------------------------------
-template <int W_>
+template <int W_, int BP_ = 34>
 struct RCfg {
     static constexpr int W = W_;
     static constexpr int NT = W;              // one thread per row
@@ -80,10 +80,12 @@ struct RCfg {
     // two off-diagonal blocks (one CTA barrier), then the diagonal ones (warp-synchronous), reusing the same two
     // blocks - half a plane - so a group needs ~52 KB of shared memory and FOUR groups (8 warps, two per
     // scheduler) fit on an SM.
-    // block pitch in float2.  64x64: 33 (odd -> conflict-free 8-byte accesses both ways).  32x32: 34, rows start 16-byte
-    // aligned (272 B apart) and a thread stores its 32 values as 16 STS.128 (banks 4*lane + 4*j mod 32: conflict-free).
-    // A/B on one B200 (tools/ab.sh): STS.128 gains 1.7 % at 32x32 and loses 1 % at 64x64 / 128x128.
-    static constexpr int BP = (W == 32) ? 34 : 33;
+    // block pitch in float2.  34: rows start 16-byte aligned (272 B apart) and a thread stores its 32 values as 16 STS.128 (banks
+    // 4*lane + 4*j mod 32: conflict-free); 33 (odd -> conflict-free 8-byte accesses both ways) stores them as 32 STS.64.
+    // A/B on one B200 (tools/ab_lib.py).  Round 1: STS.128 gained 1.7 % at 32x32 and lost 1 % at 64x64 / 128x128.  Round 2, with
+    // packed fp32 arithmetic and the parked spectra out of shared memory: +3.5 % at 64x64 (106.2 -> 110.3 M windows/s), -0.7 % for
+    // the 128x128 kernel, which keeps 33 (R6 in piv_rows128.cuh).
+    static constexpr int BP = BP_;
     static constexpr int XBLK = 32 * BP;          // float2 per block
 };
 
@@ -465,7 +467,14 @@ B2_HD void rows_p2_pre(RSmem<R>& s, RRegs<R>& r, int tid, int clip_norm) {
     for (int k = 0; k < W / 4; ++k) {
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
+#if defined(__CUDA_ARCH__) && defined(B2_MAGIC_CVT)
+            // EXPERIMENT (timing only): byte -> float by byte permute into the mantissa of 32768.0f, mean quantised to 1/256
+            const float2 mg = make_float2(__uint_as_float(__byte_perm(r.px[0][k], 0x47000000u, 0x7404u | (b << 4))),
+                                          __uint_as_float(__byte_perm(r.px[1][k], 0x47000000u, 0x7404u | (b << 4))));
+            float2 a = pk_sub(mg, make_float2(32768.0f + r.mean_new[0], 32768.0f + r.mean_new[1]));
+#else
             float2 a = pk_sub(make_float2(byte_to_float(r.px[0][k], b), byte_to_float(r.px[1][k], b)), make_float2(r.mean_new[0], r.mean_new[1]));
+#endif
             if (clip_norm) a = make_float2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f));
             r.v[4 * k + b] = a;
         }

@@ -191,6 +191,7 @@ struct RRegs {
     float half_alpha_prev[2];     // 0.5 / std of the previous frame's windows (0: dead)
     float half_alpha_new[2];
     float mean_new[2];
+    float dc_fix[2];              // N * (mean - quantised mean) of the magic-number centring (rows_p2_pre<.., true>), removed from Z(0, 0)
     float rowmax[2], rowsum[2];
     bool dead[2];                 // window w has zero variance in the previous or the current frame
     int pi[2], pj[2];
@@ -450,7 +451,13 @@ B2_HD void rows_f3(RSmem<R>& s, RRegs<R>& r, int tid, int clip_norm) {
 // ------------------------------------------------------------------------------------------------------------
 // P2: statistics -> mean, 0.5/std ; convert + centre (+clip) ; forward row FFT ; transposed store into X
 // ------------------------------------------------------------------------------------------------------------
-template <class R>
+// MAGIC (device, un-clipped normalisation only): a byte becomes a float by ONE byte permute into the mantissa of 32768.0f
+// (0x47000000 | b << 8 = 32768 + b exactly) - an ALU instruction instead of an I2F conversion, which goes through the MIO queue
+// like shared memory and shuffles (A/B on one B200: +3.6 %).  The packed subtraction of c = fl(32768 + mean) then centres with the
+// mean rounded to 1/256: (32768 + b) - c = b - mq EXACTLY.  The difference delta = mean - mq is known exactly (|delta| <= 2^-9, a
+// multiple of 1/N) and only shifts the DC bin: FFT2(b - mq) = FFT2(b - mean) + N delta at k = 0, so the cross phase subtracts
+// N (delta0 + i delta1) - a small whole number - from Z(0, 0) (RRegs::dc_fix) and everything downstream is unchanged.
+template <class R, bool MAGIC = false>
 B2_HD void rows_p2_pre(RSmem<R>& s, RRegs<R>& r, int tid, int clip_norm) {
     constexpr int W = R::W;
 #pragma unroll
@@ -462,19 +469,31 @@ B2_HD void rows_p2_pre(RSmem<R>& s, RRegs<R>& r, int tid, int clip_norm) {
         r.mean_new[w] = (float)S * (1.0f / (float)R::NPX);
         // 0.5 / std = 0.5 * N / sqrt(N*Q - S^2)
         r.half_alpha_new[w] = m2 ? 0.5f * (float)R::NPX * (1.0f / sqrtf((float)m2)) : 0.f;
+        r.dc_fix[w] = 0.f;
     }
+#ifdef __CUDA_ARCH__
+    if (MAGIC && !clip_norm) {
+        const float c0 = __fadd_rn(32768.0f, r.mean_new[0]), c1 = __fadd_rn(32768.0f, r.mean_new[1]);
+        r.dc_fix[0] = (r.mean_new[0] - (c0 - 32768.0f)) * (float)R::NPX;     // exact: every term is a multiple of 1/N below 2^16
+        r.dc_fix[1] = (r.mean_new[1] - (c1 - 32768.0f)) * (float)R::NPX;
+        const float2 c = make_float2(c0, c1);
+#pragma unroll
+        for (int k = 0; k < W / 4; ++k) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const float2 mg = make_float2(__uint_as_float(__byte_perm(r.px[0][k], 0x47000000u, 0x7404u | (b << 4))),
+                                              __uint_as_float(__byte_perm(r.px[1][k], 0x47000000u, 0x7404u | (b << 4))));
+                r.v[4 * k + b] = pk_sub(mg, c);
+            }
+        }
+        return;
+    }
+#endif
 #pragma unroll
     for (int k = 0; k < W / 4; ++k) {
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-#if defined(__CUDA_ARCH__) && defined(B2_MAGIC_CVT)
-            // EXPERIMENT (timing only): byte -> float by byte permute into the mantissa of 32768.0f, mean quantised to 1/256
-            const float2 mg = make_float2(__uint_as_float(__byte_perm(r.px[0][k], 0x47000000u, 0x7404u | (b << 4))),
-                                          __uint_as_float(__byte_perm(r.px[1][k], 0x47000000u, 0x7404u | (b << 4))));
-            float2 a = pk_sub(mg, make_float2(32768.0f + r.mean_new[0], 32768.0f + r.mean_new[1]));
-#else
             float2 a = pk_sub(make_float2(byte_to_float(r.px[0][k], b), byte_to_float(r.px[1][k], b)), make_float2(r.mean_new[0], r.mean_new[1]));
-#endif
             if (clip_norm) a = make_float2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f));
             r.v[4 * k + b] = a;
         }
@@ -606,6 +625,7 @@ template <class R, bool PAD = false>
 __device__ __forceinline__ void rows_p3b_device(RSmem<R>& s, RRegs<R>& r, int tid, bool have_prev, const RParams* pp = nullptr) {
     constexpr int W = R::W;
     const int pl = partner_lane_of<W>(tid);
+    if (!PAD && tid == 0) r.v[0] = pk_sub(r.v[0], make_float2(r.dc_fix[0], r.dc_fix[1]));   // Z(0, 0): thread 0 owns column 0 (rows_p2_pre)
 #pragma unroll
     for (int ky = 0; ky <= W / 2; ++ky) {
         const float2 pz = shfl2(r.v[(W - ky) % W], pl);
@@ -655,6 +675,7 @@ __device__ __forceinline__ void rows_p3b_tm(RRegs<R>& r, int tid, uint32_t tm) {
     constexpr int NB = (W / 2 + 1 + 1) / 2;          // batches of two ky steps; the last one holds ky = W / 2 alone
     const int pl = partner_lane_of<W>(tid);
     const float b0 = r.half_alpha_new[0] * INVN, b1 = r.half_alpha_new[1] * INVN;
+    if (tid == 0) r.v[0] = pk_sub(r.v[0], make_float2(r.dc_fix[0], r.dc_fix[1]));   // Z(0, 0): thread 0 owns column 0 (rows_p2_pre)
     uint32_t pk[2][8];
     tm_ld8(tm, pk[0]);
 #pragma unroll

@@ -87,6 +87,25 @@ __device__ __forceinline__ void r128_p2(R128Smem& s, RRegs<R6>& r, int clip_norm
         r.mean_new[w] = (float)S * (1.0f / (float)R128_NPX);
         r.half_alpha_new[w] = m2 ? 0.5f * (float)R128_NPX * (1.0f / sqrtf((float)m2)) : 0.f;
     }
+    r.dc_fix[0] = r.dc_fix[1] = 0.f;
+    if (!clip_norm) {
+        // magic-number conversion + centring with the mean rounded to 1/256 (rows_p2_pre in piv_rows.cuh): the offset
+        // delta = mean - mq shifts the DC bin of EVERY polyphase component by 4096 delta, removed in r128_cross
+        const float c0 = __fadd_rn(32768.0f, r.mean_new[0]), c1 = __fadd_rn(32768.0f, r.mean_new[1]);
+        r.dc_fix[0] = (r.mean_new[0] - (c0 - 32768.0f)) * 4096.0f;
+        r.dc_fix[1] = (r.mean_new[1] - (c1 - 32768.0f)) * 4096.0f;
+        const float2 c = make_float2(c0, c1);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const float2 mg = make_float2(__uint_as_float(__byte_perm(r.px[0][k], 0x47000000u, 0x7404u | (b << 4))),
+                                              __uint_as_float(__byte_perm(r.px[1][k], 0x47000000u, 0x7404u | (b << 4))));
+                r.v[4 * k + b] = pk_sub(mg, c);
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
 #pragma unroll
@@ -143,6 +162,7 @@ __device__ __forceinline__ void r128_cross(R128Smem& s, RRegs<R6>& r, int sub, i
 #pragma unroll
     for (int p = 0; p < 4; ++p) xb[p] = r128_xch(s, p ^ sub, wq, 0, lane);
     float4* own = r128_xch(s, sub, wq, 0, lane);
+    if (t == 0) r.v[0] = pk_sub(r.v[0], make_float2(r.dc_fix[0], r.dc_fix[1]));   // Z_q(0, 0): thread 0 of a sub-group owns column 0 (r128_p2)
     float2 lo[33], hi[33];
 #pragma unroll
     for (int k = 0; k <= 32; ++k) { lo[k] = r.v[k]; hi[k] = r.v[(64 - k) % 64]; }

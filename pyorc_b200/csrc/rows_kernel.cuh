@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
     uint32_t parity = 0;
     RRegs<R> r;
     r.half_alpha_prev[0] = r.half_alpha_prev[1] = 0.f;
+    r.dc_fix[0] = r.dc_fix[1] = 0.f;   // only the magic-number centring of uint8 windows sets it (rows_p2_pre)
     for (long long ubase = (long long)blockIdx.x * G; ubase < p.n_units; ubase += (long long)gridDim.x * G) {
         int maxn = 0;  // frames of the longest unit of this round (uniform over the CTA)
 #pragma unroll
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
             } else if constexpr (!F32) {
                 rows_p1<R, ALIGNED>(s, r, tid, xoff0, xoff1);
                 __syncthreads();  // A: integer moments visible, tile (aliased on X) fully consumed
-                rows_p2_pre<R>(s, r, tid, p.clip_norm);
+                rows_p2_pre<R, true>(s, r, tid, p.clip_norm);
             } else {
                 rows_f1<R>(s, r, tid, 0, 0);
                 if (R::F_PHASES == 1) rows_f1<R>(s, r, tid, 1, R::FWIN);
@@ -216,6 +217,7 @@ __global__ void __launch_bounds__(R::NT* G, 1) piv_rows_tm_kernel(const __grid_c
     uint32_t parity = 0;
     RRegs<R> r;
     r.half_alpha_prev[0] = r.half_alpha_prev[1] = 0.f;
+    r.dc_fix[0] = r.dc_fix[1] = 0.f;   // only the magic-number centring of uint8 windows sets it (rows_p2_pre)
     for (long long unit = (long long)blockIdx.x * G + g; unit < p.n_units; unit += (long long)gridDim.x * G) {
         const RUnit un = decode_unit(p, (int)unit);
         const int nfr = un.f1 - un.f0 + 1;
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(R::NT* G, 1) piv_rows_tm_kernel(const __grid_c
             parity ^= 1u;
             rows_p1<R, ALIGNED>(s, r, tid, xoff0, xoff1);
             group_barrier<true, R::NT>(bar);  // A: integer moments visible, tile (aliased on X) fully consumed
-            rows_p2_pre<R>(s, r, tid, p.clip_norm);
+            rows_p2_pre<R, true>(s, r, tid, p.clip_norm);
 #pragma unroll 1
             for (int st = 0; st < 4; ++st) {
                 fft_reg<W, 0>(r.v);

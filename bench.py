@@ -688,7 +688,7 @@ def main():
     peak, peak_src = measured_peaks()
     achieved = B_ALG * nwin_rank / (ms_kernel * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "piv_rows_kernel<64> (row-per-thread, TMA)", "ms_per_launch": ms_kernel, "alg_bytes_per_window": B_ALG,
+                "kernel": "piv_rows_tm_kernel<RCfg<64>, 6, aligned> (row-per-thread register FFTs in packed fp32, TMA tiles, parked spectra in Tensor Memory)", "ms_per_launch": ms_kernel, "alg_bytes_per_window": B_ALG,
                 "windows_per_launch": nwin_rank, "peak_source": peak_src,
                 "note": "fused kernel is fp32-issue/shared-memory bound by construction (SURVEY.md 8d); see fp32"}
     prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")

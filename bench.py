@@ -277,8 +277,8 @@ def sharded_configs(eng, dev, rank, world, fp32_peak):
 
     Frame pairs shard over the ranks; every rank renders ITS frames on the device from (seed, frame index) (the stacks - 17 GB
     and 166 GB - never exist on the host), holds them in HBM and walks through them in chunks with the reference's 1-frame halo
-    (pyorc/velocimetry/ffpiv.py:140, :399-440), one kernel launch per chunk; for N > 1 every launch stores its 16 B / window
-    into every rank's gather buffer (P2P stores in the epilogue, parallel.PeerGather).  The per-rank share is BASELINE's own
+    (pyorc/velocimetry/ffpiv.py:140, :399-440), one kernel launch per chunk; for N > 1 every chunk's 16 B / window are
+    pushed into every rank's gather buffer (P2P stores on a side stream, parallel.PeerGather).  The per-rank share is BASELINE's own
     at the N it names - 500 pairs of 4K, 625 pairs of 8K - so the row at N = 4 (configs[3]) and at N = 8 (configs[4]) IS that
     configuration in full, and the rows at the other N are its weak-scaling series (N = 1: the single-GPU reference point)."""
     import torch
@@ -307,12 +307,12 @@ def sharded_configs(eng, dev, rank, world, fp32_peak):
 
             def job():
                 if peer is not None:
-                    slot = peer.begin()
+                    peer.begin()
                 for a, b in bounds:
-                    if peer is not None:      # this chunk's pairs start at (rank offset + a) of the gathered time axis
-                        eng.set_peer_outputs([p + slot * peer._slot_bytes for p in peer._ptrs], total, int(table[rank, 0]) + a)
                     res = eng.pairs(fr[a : b + 1], ws, ov)
-                    if peer is None:
+                    if peer is not None:      # this chunk's pairs start at (rank offset + a) of the gathered time axis
+                        peer.push(res[0]._base, int(table[rank, 0]) + a)
+                    else:
                         for k in range(4):
                             local[k, a:b] = res[k]
                 if peer is not None:
@@ -442,7 +442,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--nccl-gather", action="store_true", help="N > 1: gather results with NCCL instead of the fused P2P stores")
+    ap.add_argument("--nccl-gather", action="store_true", help="N > 1: gather results with NCCL instead of our own P2P stores")
+    ap.add_argument("--fused-gather", action="store_true", help="N > 1: P2P stores from the PIV kernel's epilogue instead of the push kernel on the side stream")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the runs of BASELINE.json configs[0], [2], [3], [4] and the N > 1 ensemble check")
     ap.add_argument("--cpu-pairs", type=int, default=0, help="frame pairs of the workload the CPU baseline times per step (0: sized from the host's speed)")
     args = ap.parse_args()
@@ -489,14 +490,18 @@ def main():
     nwin_rank = N_PAIRS * nr * nc
     table = parallel.shard_pairs(N_PAIRS * world, world)
 
-    # N > 1: the gather of the 16 B / window results is fused into the kernel epilogue (P2P stores into every rank's
-    # symmetric-memory slot ring; the completion barrier runs on a consumer stream); NCCL all-gather when peer memory is missing
+    # N > 1: the gather of the 16 B / window results is P2P stores of our own kernels into every rank's symmetric-memory slot
+    # ring - by a push kernel on the consumer stream, overlapped with the next step (default), or from the PIV kernel's epilogue
+    # (--fused-gather: its end-of-kernel wait for NVLink costs 2 .. 4 % of the step) - and a completion barrier on the consumer
+    # stream; NCCL all-gather when peer memory is missing
     peer = None
     gather_how = None
     if world > 1 and not args.nccl_gather:
         try:
-            peer = parallel.PeerGather(eng, N_PAIRS * world, table)
-            gather_how = "fused: P2P stores from the kernel epilogue into a ring of 3 symmetric-memory slots, completion barrier on a consumer stream"
+            peer = parallel.PeerGather(eng, N_PAIRS * world, table, mode="fused" if args.fused_gather else "push")
+            gather_how = ("P2P stores from the PIV kernel's epilogue" if args.fused_gather else
+                          "P2P push kernel (16-byte stores to every rank) on the consumer stream, overlapped with the next step's PIV kernel")
+            gather_how += "; ring of 3 symmetric-memory slots, completion barrier on the consumer stream"
         except Exception as exc:   # no peer access / symmetric memory: keep the collective
             peer = None
             gather_how = f"nccl all_gather_into_tensor per field (symmetric memory unavailable: {str(exc)[:80]})"
@@ -506,8 +511,8 @@ def main():
     def step_device():
         if peer is not None:
             peer.begin()
-            eng.pairs(frames, WS, OV)
-            return peer.end()
+            res = eng.pairs(frames, WS, OV)
+            return peer.end(res[0]._base if peer.mode == "push" else None)
         res = eng.pairs(frames, WS, OV)
         if world > 1:
             return parallel.gather_fields(res, N_PAIRS * world, table), None   # four fields, gathered in place

@@ -229,6 +229,12 @@ int b2piv_pairs_interleaved_device(b2piv_engine* e, const float* d_stack, int n_
  * barrier before reading.  n_peers = 0 switches back to local-only results; so does a b2piv_plan that changes the field shape
  * (set it after b2piv_plan). */
 int b2piv_set_peer_outputs(b2piv_engine* e, int n_peers, void* const* peer_bases, long long pairs_total, long long pair_offset);
+/* The same gather as a separate PUSH for a side stream: copies the caller's contiguous result block float32 [4][n_pairs][n_rows *
+ * n_cols] (what b2piv_pairs_device wrote) into every peer's buffer at `pair_offset` (16-byte P2P stores), stream-ordered.  A kernel
+ * that writes peer memory waits for NVLink's acknowledgements when it ends; in the PIV kernel's epilogue that wait is on the compute
+ * stream (+2 .. 4 % of a 1.6 ms step), here it overlaps the next step (pyorc_b200.parallel.PeerGather(mode="push")). */
+int b2piv_peer_push(b2piv_engine* e, const float* d_local, int n_pairs, int n_peers, void* const* peer_bases, long long pairs_total,
+                    long long pair_offset, void* cuda_stream);
 
 /* Page-locked host memory so H2D copies run at full PCIe rate without staging. */
 void* b2piv_host_alloc(size_t bytes);

@@ -200,6 +200,9 @@ int b2piv_project_plan(b2piv_engine* e, int height, int width, int out_height, i
     }
     off[(size_t)n_out] = (int)src.size();
     CK(cudaSetDevice(e->device));
+    // a projection of the previous plan may still be in flight on a caller stream (non-blocking streams do not synchronise with
+    // the copies below): re-planning is rare (once per camera configuration), so simply wait for the device
+    if (e->d_proj_off) CK(cudaDeviceSynchronize());
     int rc = ensure(e, &e->d_proj_off, &e->cap_proj_off, off.size() * sizeof(int));
     if (rc) return rc;
     rc = ensure(e, &e->d_proj_src, &e->cap_proj_src, (src.size() + 1) * sizeof(int));

@@ -817,6 +817,53 @@ int b2piv_pairs_interleaved_device(b2piv_engine* e, const float* d_stack, int n_
     return launch_rows_f32(e, p, st);
 }
 
+// The gather as a separate push: copy this rank's result block [4][n_pairs][n_windows] into every peer's gather buffer
+// [4][pairs_total][n_windows] at `pair_offset` with 16-byte stores.  Meant for a side stream, overlapped with the next step's
+// compute: a kernel that writes peer memory pays for NVLink's acknowledgements when it ends (measured: +30 us per launch at N = 2,
+// +64 us at N = 8, whatever thread issues the stores and however they are batched - tools/scale_probe.py), and in the epilogue of
+// the PIV kernel that wait sits on the compute stream.
+__global__ void __launch_bounds__(256) peer_push_kernel(const float* __restrict__ src, long long n_local /* floats per field */, b2piv::PeerOut po, long long nw) {
+    const long long dst0 = po.pair0 * nw;
+    const bool vec = ((n_local | dst0 | po.field) & 3) == 0;
+    const long long n4 = vec ? n_local / 4 : 0;
+    for (int f = 0; f < 4; ++f) {
+        const float* s = src + f * n_local;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+            const float4 v = reinterpret_cast<const float4*>(s)[i];
+            for (int r = 0; r < po.n; ++r) reinterpret_cast<float4*>(po.base[r] + f * po.field + dst0)[i] = v;
+        }
+        for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (long long)gridDim.x * blockDim.x) {
+            const float v = s[i];
+            for (int r = 0; r < po.n; ++r) po.base[r][f * po.field + dst0 + i] = v;
+        }
+    }
+}
+
+int b2piv_peer_push(b2piv_engine* e, const float* d_local, int n_pairs, int n_peers, void* const* peer_bases, long long pairs_total,
+                    long long pair_offset, void* cuda_stream) {
+    if (!e) return B2PIV_ERR_ARG;
+    if (!e->planned) return fail(e, B2PIV_ERR_STATE, "b2piv_plan has not been called");
+    if (!d_local || !peer_bases || n_peers < 1 || n_peers > 8) return fail(e, B2PIV_ERR_ARG, "1..8 peer buffers");
+    if (n_pairs < 1 || pair_offset < 0 || pair_offset + n_pairs > pairs_total) return fail(e, B2PIV_ERR_ARG, "bad pair range");
+    CK(cudaSetDevice(e->device));
+    const long long nw = (long long)e->n_rows * e->n_cols;
+    b2piv::PeerOut po = {};
+    po.n = n_peers;
+    for (int r = 0; r < n_peers; ++r) {
+        if (!peer_bases[r]) return fail(e, B2PIV_ERR_ARG, "NULL peer buffer");
+        po.base[r] = (float*)peer_bases[r];
+    }
+    po.field = pairs_total * nw;
+    po.pair0 = pair_offset;
+    const long long n_local = (long long)n_pairs * nw;
+    long long g = (n_local / 4 + 255) / 256;
+    g = g < 1 ? 1 : (g > 64 ? 64 : g);     // a small kernel on purpose: it shares the SMs with the PIV kernel of the next step
+    peer_push_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)cuda_stream>>>(d_local, n_local, po, nw);
+    CK(cudaGetLastError());
+    e->launches++;
+    return B2PIV_OK;
+}
+
 void* b2piv_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;

@@ -367,6 +367,30 @@ B2_HD void rows_p2_pre_pad(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p) 
     // masked bytes are 0, so a pixel outside the window must only NOT get the mean subtracted: rows >= ny use mean 0,
     // columns >= nx a 0/1 factor from the constant bank - one FFMA per value, like the FADD of the native path
     const bool rowok = column_of<W>(tid) < p.ny;
+    r.dc_fix[0] = r.dc_fix[1] = 0.f;
+#ifdef __CUDA_ARCH__
+    if (!p.clip_norm) {
+        // magic-number conversion (rows_p2_pre): byte -> 32768 + b by a byte permute, exact subtraction of 32768, then
+        // byte - cm * mq with the mean rounded to 1/256; the DC offset n_px * (mean - mq) is removed from Z(0, 0) in the cross phase
+        const float c0 = __fadd_rn(32768.0f, r.mean_new[0]), c1 = __fadd_rn(32768.0f, r.mean_new[1]);
+        const float mq0 = c0 - 32768.0f, mq1 = c1 - 32768.0f;
+        r.dc_fix[0] = (r.mean_new[0] - mq0) * (float)npx;
+        r.dc_fix[1] = (r.mean_new[1] - mq1) * (float)npx;
+        const float2 nm = rowok ? make_float2(-mq0, -mq1) : make_float2(0.f, 0.f);
+        const float2 base = make_float2(32768.0f, 32768.0f);
+#pragma unroll
+        for (int k = 0; k < W / 4; ++k) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const float2 mg = make_float2(__uint_as_float(__byte_perm(r.px[0][k], 0x47000000u, 0x7404u | (b << 4))),
+                                              __uint_as_float(__byte_perm(r.px[1][k], 0x47000000u, 0x7404u | (b << 4))));
+                r.v[4 * k + b] = pk_fma(make_float2(p.pad_cm[4 * k + b], p.pad_cm[4 * k + b]), nm, pk_sub(mg, base));
+            }
+        }
+        r.tx = p.pad_tx[column_of<W>(tid)];
+        return;
+    }
+#endif
     const float nm0 = rowok ? -r.mean_new[0] : 0.f, nm1 = rowok ? -r.mean_new[1] : 0.f;
 #pragma unroll
     for (int k = 0; k < W / 4; ++k) {
@@ -625,7 +649,7 @@ template <class R, bool PAD = false>
 __device__ __forceinline__ void rows_p3b_device(RSmem<R>& s, RRegs<R>& r, int tid, bool have_prev, const RParams* pp = nullptr) {
     constexpr int W = R::W;
     const int pl = partner_lane_of<W>(tid);
-    if (!PAD && tid == 0) r.v[0] = pk_sub(r.v[0], make_float2(r.dc_fix[0], r.dc_fix[1]));   // Z(0, 0): thread 0 owns column 0 (rows_p2_pre)
+    if (tid == 0) r.v[0] = pk_sub(r.v[0], make_float2(r.dc_fix[0], r.dc_fix[1]));   // Z(0, 0): thread 0 owns column 0 (rows_p2_pre / _pad)
 #pragma unroll
     for (int ky = 0; ky <= W / 2; ++ky) {
         const float2 pz = shfl2(r.v[(W - ky) % W], pl);

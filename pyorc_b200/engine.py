@@ -65,6 +65,7 @@ ABI_SYMBOLS = (
     "b2piv_deform_device",
     "b2piv_pairs_interleaved_device",
     "b2piv_set_peer_outputs",
+    "b2piv_peer_push",
     "b2piv_host_alloc",
     "b2piv_host_free",
     "b2piv_last_kernel_ms",
@@ -132,6 +133,7 @@ def load_library(path: Optional[str] = None):
     lib.b2piv_deform_device.argtypes = [vp, vp, cll, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp, vp]
     lib.b2piv_pairs_interleaved_device.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp]
     lib.b2piv_set_peer_outputs.argtypes = [vp, ci, vpp, cll, cll]
+    lib.b2piv_peer_push.argtypes = [vp, vp, ci, ci, vpp, cll, cll, vp]
     lib.b2piv_host_alloc.argtypes = [ctypes.c_size_t]
     lib.b2piv_host_alloc.restype = vp
     lib.b2piv_host_free.argtypes = [vp]
@@ -438,6 +440,20 @@ class Engine:
         arr = (ctypes.c_void_p * max(len(ptrs), 1))(*[int(p) for p in ptrs])
         self._check(self._lib.b2piv_set_peer_outputs(self._h, len(ptrs), arr, int(pairs_total), int(pair_offset)),
                     "b2piv_set_peer_outputs")
+
+    @_serialised
+    def peer_push(self, local, peer_ptrs, pairs_total: int, pair_offset: int, stream=None):
+        """Copy a contiguous result block ``[4, n_pairs, n_rows, n_cols]`` (CUDA tensor, e.g. the base of what :meth:`pairs`
+        returned) into every peer's gather buffer at ``pair_offset``, stream-ordered on ``stream`` / torch's current stream."""
+        import torch
+
+        if local.dim() != 4 or local.shape[0] != 4 or not local.is_contiguous() or local.dtype != torch.float32:
+            raise ValueError("local must be a contiguous float32 [4, n_pairs, n_rows, n_cols] tensor")
+        ptrs = [int(p) for p in peer_ptrs]
+        arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        st, _ = _stream_ctx(torch, local.device, stream)
+        self._check(self._lib.b2piv_peer_push(self._h, local.data_ptr(), int(local.shape[1]), len(ptrs), arr, int(pairs_total), int(pair_offset), st),
+                    "b2piv_peer_push")
 
     # ---- two-pass (BASELINE configs[2]) -----------------------------------------------------------------------
     @_serialised

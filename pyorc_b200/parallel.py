@@ -78,9 +78,16 @@ def gather_fields(local, n_pairs_total: int, table: np.ndarray, group=None):
 
 
 class PeerGather:
-    """The result gather fused into the PIV kernel: every rank's kernel stores its 16 B / window straight into the gather
-    buffer of EVERY rank (torch symmetric memory = peer-mapped HBM over NVLink / NVSwitch), so no collective follows the
-    compute - only a cross-rank completion barrier before a buffer is read.
+    """The result gather as P2P stores of our own kernels: every rank writes its 16 B / window straight into the gather buffer
+    of EVERY rank (torch symmetric memory = peer-mapped HBM over NVLink / NVSwitch), so no collective follows the compute - only
+    a cross-rank completion barrier before a buffer is read.  Two modes:
+
+    * ``"push"`` (default): the PIV kernel writes this rank's own block; a small copy kernel on the consumer stream forwards it
+      to every rank's slot (16-byte stores) while the compute stream is already in the next step.
+    * ``"fused"``: the PIV kernel's epilogue stores each result to all ranks itself.  One launch less, but a kernel that writes
+      peer memory waits for NVLink's acknowledgements when it ends, on the compute stream: +25 .. 30 us per launch at N = 2 and
+      +64 us at N = 8 on a 1.63 ms step, however the stores are issued (per frame by the fitting threads, spread over a warp's
+      lanes, or batched per work unit - tools/scale_probe.py), against +3 us for the push.
 
     The buffers form a ring of ``depth`` slots and the barrier runs on a separate high-priority CONSUMER stream, so the compute
     stream never waits for the other ranks in steady state (round 1 had one buffer and a barrier on the compute stream after
@@ -89,8 +96,8 @@ class PeerGather:
         pg = PeerGather(engine, n_pairs_total, table)        # after engine.plan(...); collective (rendezvous)
         for step in ...:
             pg.begin()                                        # next slot; waits only if that slot is still being read anywhere
-            engine.pairs(d_frames_of_this_rank, ws, ov)       # results land in the slot on every rank
-            fields, ready = pg.end()                          # consumer stream: this rank's kernel done -> barrier -> `ready`
+            res = engine.pairs(d_frames_of_this_rank, ws, ov) # "fused": results land in the slot on every rank
+            fields, ready = pg.end(res[0]._base)              # consumer stream: kernel done -> ("push": copy to all) -> barrier -> `ready`
             ...                                               # whoever reads `fields` [4, n_pairs_total, rows, cols] first waits
                                                               # for `ready` (stream.wait_event / ready.synchronize())
         pg.wait()                                             # or: make the current stream wait for the last slot (blocking use)
@@ -101,7 +108,7 @@ class PeerGather:
     on the consumer stream (``with torch.cuda.stream(pg.consumer)``) or makes the consumer stream wait for its read before the
     next ``end()``.  The NCCL path (:func:`gather_fields`) remains for ragged use and for backends without peer access."""
 
-    def __init__(self, engine, n_pairs_total: int, table: np.ndarray, group=None, depth: int = 3):
+    def __init__(self, engine, n_pairs_total: int, table: np.ndarray, group=None, depth: int = 3, mode: str = "push"):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -114,6 +121,9 @@ class PeerGather:
         group = group if group is not None else dist.group.WORLD
         rank = dist.get_rank(group)
         dev = torch.device("cuda", engine.device)
+        if mode not in ("fused", "push"):
+            raise ValueError("mode must be 'fused' or 'push'")
+        self.mode = mode
         self.engine, self.depth, self.n_pairs_total, self.pair_offset = engine, int(depth), int(n_pairs_total), int(table[rank, 0])
         self.ring = symm_mem.empty((self.depth, 4, self.n_pairs_total, rows, cols), dtype=torch.float32, device=dev)
         self.handle = symm_mem.rendezvous(self.ring, group)
@@ -136,18 +146,43 @@ class PeerGather:
         nxt = self._ready[(slot + 1) % self.depth]
         if self._step >= self.depth and nxt is not None:
             torch.cuda.current_stream(self._device).wait_event(nxt)     # barrier of step (s - depth + 1) has been passed here
-        self.engine.set_peer_outputs([p + slot * self._slot_bytes for p in self._ptrs], self.n_pairs_total, self.pair_offset)
+        if self.mode == "fused":
+            self.engine.set_peer_outputs([p + slot * self._slot_bytes for p in self._ptrs], self.n_pairs_total, self.pair_offset)
         self.out = self.ring[slot]
         return slot
 
-    def end(self):
+    def push(self, local, pair_offset=None):
+        """``mode="push"``: forward ``local`` - the contiguous ``[4, n_pairs, rows, cols]`` block ``engine.pairs`` wrote
+        (``res[0]._base`` of its four views) - to every rank's current slot at ``pair_offset`` of the gathered time axis (default:
+        this rank's first pair), on the consumer stream, after the work queued so far on the current stream.  A step made of several
+        chunk launches pushes each chunk with its own offset and then calls :meth:`end` without a block."""
+        import torch
+
+        if self.mode != "push":
+            raise RuntimeError("PeerGather(mode='fused') stores from the kernel epilogue; push() is for mode='push'")
+        if self._step < 0:
+            raise RuntimeError("begin() first")
+        slot = self._step % self.depth
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(self._device))
+        self.consumer.wait_event(done)
+        local.record_stream(self.consumer)
+        self.engine.peer_push(local, [p + slot * self._slot_bytes for p in self._ptrs], self.n_pairs_total,
+                              self.pair_offset if pair_offset is None else int(pair_offset), stream=self.consumer)
+        self._pushed = self._step
+
+    def end(self, local=None, pair_offset=None):
         """After ``engine.pairs``: completion barrier of this step on the consumer stream.  Returns the slot's tensor and the event
-        after which it holds every rank's results."""
+        after which it holds every rank's results.  ``mode="push"``: pass the result block here (or to :meth:`push` before)."""
         import torch
 
         if self._step < 0:
             raise RuntimeError("begin() first")
         slot = self._step % self.depth
+        if local is not None:
+            self.push(local, pair_offset)
+        elif self.mode == "push" and getattr(self, "_pushed", -1) != self._step:
+            raise ValueError("mode='push': pass the local result block to end() or push() first")
         done = torch.cuda.Event()
         done.record(torch.cuda.current_stream(self._device))
         with torch.cuda.stream(self.consumer):
@@ -168,7 +203,7 @@ class PeerGather:
             raise RuntimeError("begin() / engine.pairs() first")
         slot = self._step % self.depth
         if self._ended != self._step:
-            self.end()
+            self.end()      # mode="push": the block must have been push()ed
         torch.cuda.current_stream(self._device).wait_event(self._ready[slot])
         return self.ring[slot]
 

@@ -476,6 +476,37 @@ def test_rows_kernel_float32_frames(engine, ws, ov, shape, run_len):
     engine.set_option("kernel_variant", 0.0)
 
 
+def test_peer_push_two_engines_one_device():
+    """b2piv_peer_push: the gather as a separate copy kernel.  Two engines (stand-ins for two ranks) push their blocks into both
+    gather buffers at their offsets - vector path (element counts divisible by 4) and the scalar tail (odd window counts)."""
+    import torch
+
+    from pyorc_b200.engine import Engine
+
+    for shape, ws, ov in (((200, 304), (64, 64), (32, 32)), ((150, 210), (32, 32), (16, 16)), ((131, 197), (30, 30), (15, 15))):
+        imgs = synth.particle_frames(7, *shape, dtype=np.uint8)
+        d = torch.from_numpy(imgs).cuda()
+        with Engine(0) as e0, Engine(0) as e1:
+            whole = torch.stack(e0.pairs(d, ws, ov))
+            nr, nc = e0.plan(shape, ws, ov, np.uint8)
+            e1.plan(shape, ws, ov, np.uint8)
+            bufs = [torch.full((4, 6, nr, nc), -7.0, device="cuda") for _ in range(2)]
+            ptrs = [b.data_ptr() for b in bufs]
+            a = e0.pairs(d[:4], ws, ov)            # pairs 0..2
+            b = e1.pairs(d[3:], ws, ov)            # pairs 3..5
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            e0.peer_push(a[0]._base, ptrs, 6, 0, stream=side)
+            e1.peer_push(b[0]._base, ptrs, 6, 3, stream=side)
+            side.synchronize()
+            for buf in bufs:
+                assert torch.equal(torch.nan_to_num(buf), torch.nan_to_num(whole))
+            with pytest.raises(ValueError):
+                e1.peer_push(b[0]._base, ptrs, 6, 4)       # 3 pairs from offset 4 do not fit 6
+            with pytest.raises(ValueError):
+                e1.peer_push(b[0], ptrs, 6, 3)             # one field, not the [4, pairs, rows, cols] block
+
+
 def test_fused_peer_gather_two_engines_one_device():
     """b2piv_set_peer_outputs: two engines (stand-ins for two ranks, both on cuda:0) each process half of the frame pairs and
     store their results straight into BOTH gather buffers; each buffer ends up with the whole time axis."""
@@ -730,3 +761,16 @@ def test_fused_unit_conversion_is_numpys_arithmetic(engine):
     assert np.array_equal(c, c2) and np.array_equal(s, s2, equal_nan=True)
     with pytest.raises(ValueError):
         engine.pairs(imgs, ws, ov, units=(res_x, res_y, dt[:3]))
+
+
+@pytest.mark.parametrize("ws,ov,shape,run_len", [((128, 128), (64, 64), (30, 300, 420), 4), ((128, 128), (64, 64), (26, 300, 420), 0),
+                                                   ((64, 64), (32, 32), (40, 200, 304), 5), ((64, 64), (32, 32), (40, 200, 304), 0),
+                                                   ((32, 32), (24, 24), (34, 100, 144), 3)])
+def test_long_sequences_wrap_the_run_length_many_times(engine, ws, ov, shape, run_len):
+    """Work units that start and stop many times along a long frame sequence (the full-size tests only wrap a run a
+    few times): 128x128 with runs of 4 pairs over 29 pairs, 64x64 / 32x32 likewise, and the default unit / partition schemes."""
+    imgs = synth.particle_frames(*shape, dtype=np.uint8)
+    imgs[7:9, : ws[0], : ws[1]] = 9          # a window that is dead for two frames in the middle of a run
+    compare(engine, imgs, ws, ov, 0, variant=2, run_len=run_len, check_planes=False)
+    engine.set_option("kernel_variant", 0.0)
+    engine.set_option("run_len", 0.0)

@@ -311,7 +311,7 @@ def sharded_configs(eng, dev, rank, world, fp32_peak):
                 for a, b in bounds:
                     res = eng.pairs(fr[a : b + 1], ws, ov)
                     if peer is not None:      # this chunk's pairs start at (rank offset + a) of the gathered time axis
-                        peer.push(res[0]._base, int(table[rank, 0]) + a)
+                        peer.push(res, int(table[rank, 0]) + a)
                     else:
                         for k in range(4):
                             local[k, a:b] = res[k]
@@ -512,7 +512,7 @@ def main():
         if peer is not None:
             peer.begin()
             res = eng.pairs(frames, WS, OV)
-            return peer.end(res[0]._base if peer.mode == "push" else None)
+            return peer.end(res if peer.mode == "push" else None)
         res = eng.pairs(frames, WS, OV)
         if world > 1:
             return parallel.gather_fields(res, N_PAIRS * world, table), None   # four fields, gathered in place

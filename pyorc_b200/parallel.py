@@ -77,6 +77,22 @@ def gather_fields(local, n_pairs_total: int, table: np.ndarray, group=None):
     return out
 
 
+def _result_block(res):
+    """The contiguous ``[4, n_pairs, rows, cols]`` block behind the four fields ``Engine.pairs`` returned (they are views of one
+    allocation); any other 4-tuple of tensors is stacked (one copy)."""
+    import torch
+
+    if isinstance(res, torch.Tensor):
+        return res
+    f0 = res[0]
+    n = f0.numel()
+    if (len(res) == 4 and f0.dim() == 3 and n > 0 and all(r.is_contiguous() and r.shape == f0.shape and r.dtype == f0.dtype for r in res)
+            and all(res[k].data_ptr() == f0.data_ptr() + k * n * f0.element_size() for k in range(4))
+            and all(res[k].untyped_storage().data_ptr() == f0.untyped_storage().data_ptr() for k in range(4))):
+        return f0.as_strided((4, *f0.shape), (n, *f0.stride()), f0.storage_offset())
+    return torch.stack(list(res))
+
+
 class PeerGather:
     """The result gather as P2P stores of our own kernels: every rank writes its 16 B / window straight into the gather buffer
     of EVERY rank (torch symmetric memory = peer-mapped HBM over NVLink / NVSwitch), so no collective follows the compute - only
@@ -97,7 +113,7 @@ class PeerGather:
         for step in ...:
             pg.begin()                                        # next slot; waits only if that slot is still being read anywhere
             res = engine.pairs(d_frames_of_this_rank, ws, ov) # "fused": results land in the slot on every rank
-            fields, ready = pg.end(res[0]._base)              # consumer stream: kernel done -> ("push": copy to all) -> barrier -> `ready`
+            fields, ready = pg.end(res)                       # consumer stream: kernel done -> ("push": copy to all) -> barrier -> `ready`
             ...                                               # whoever reads `fields` [4, n_pairs_total, rows, cols] first waits
                                                               # for `ready` (stream.wait_event / ready.synchronize())
         pg.wait()                                             # or: make the current stream wait for the last slot (blocking use)
@@ -152,8 +168,8 @@ class PeerGather:
         return slot
 
     def push(self, local, pair_offset=None):
-        """``mode="push"``: forward ``local`` - the contiguous ``[4, n_pairs, rows, cols]`` block ``engine.pairs`` wrote
-        (``res[0]._base`` of its four views) - to every rank's current slot at ``pair_offset`` of the gathered time axis (default:
+        """``mode="push"``: forward ``local`` - what ``engine.pairs`` returned (its four fields are views of one contiguous
+        ``[4, n_pairs, rows, cols]`` block) or such a block itself - to every rank's current slot at ``pair_offset`` of the gathered time axis (default:
         this rank's first pair), on the consumer stream, after the work queued so far on the current stream.  A step made of several
         chunk launches pushes each chunk with its own offset and then calls :meth:`end` without a block."""
         import torch
@@ -163,6 +179,7 @@ class PeerGather:
         if self._step < 0:
             raise RuntimeError("begin() first")
         slot = self._step % self.depth
+        local = _result_block(local)
         done = torch.cuda.Event()
         done.record(torch.cuda.current_stream(self._device))
         self.consumer.wait_event(done)

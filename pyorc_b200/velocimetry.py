@@ -128,7 +128,8 @@ def get_b2piv(
     )
     if chunksize is None:
         # the smallest free HBM of the devices used sizes the chunks (every device holds one sub-range of a chunk at a time)
-        avail_mem = min(window.available_memory(d) for d in devices) / memory_factor
+        # (a recent answer is reused while it is at least twice what this call needs - window.available_memory)
+        avail_mem = min(window.available_memory(d, need=req_mem * memory_factor) for d in devices) / memory_factor
         chunks = int((req_mem // avail_mem) + 1)
         chunksize = int(np.ceil(n_total / chunks))
         if chunksize <= 5:

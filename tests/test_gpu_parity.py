@@ -774,3 +774,23 @@ def test_long_sequences_wrap_the_run_length_many_times(engine, ws, ov, shape, ru
     compare(engine, imgs, ws, ov, 0, variant=2, run_len=run_len, check_planes=False)
     engine.set_option("kernel_variant", 0.0)
     engine.set_option("run_len", 0.0)
+
+
+def test_available_memory_cache():
+    """window.available_memory: the driver is asked when no need is given, when the cached value is old, or when it is less than twice
+    the need; otherwise the recent answer is reused (cudaMemGetInfo costs 1 - 7 ms, a whole get_b2piv call 4.6 ms)."""
+    import torch
+
+    from pyorc_b200 import window
+
+    window._FREE_CACHE.clear()
+    a = window.available_memory(0)
+    assert 0 < a <= torch.cuda.get_device_properties(0).total_memory
+    hold = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # changes the free memory (unless the caching allocator had it)
+    assert window.available_memory(0, need=1e6) == a                      # reused: a >= 2 * need
+    assert window.available_memory(0, need=a) <= a                        # too close to the limit: asked again
+    assert window.available_memory(0, need=1e6, max_age=0.0) > 0          # too old: asked again
+    window._FREE_CACHE[0] = (window._FREE_CACHE[0][0], 123.0)
+    assert window.available_memory(0, need=50.0) == 123.0
+    assert window.available_memory(0) != 123.0                            # no need given: always the driver
+    del hold

@@ -74,7 +74,7 @@ def fake(monkeypatch):
 
     monkeypatch.setattr(velocimetry, "get_engine", get_engine)
     monkeypatch.setattr(velocimetry, "merge_ensembles", merge)
-    monkeypatch.setattr(window, "available_memory", lambda device=None: 64e9)
+    monkeypatch.setattr(window, "available_memory", lambda device=None, **kw: 64e9)
     O.CLIP_NORMALIZED = True
     return fe
 
@@ -137,7 +137,7 @@ def test_chunksize_errors_and_warning(fake, monkeypatch):
     y, x = np.arange(nr), np.arange(nc)
     with pytest.raises(OverflowError):
         velocimetry.get_b2piv(da, y, x, np.full(5, 1 / 30), (32, 32), (16, 16), (32, 32), res, res, chunksize=1)
-    monkeypatch.setattr(window, "available_memory", lambda device=None: 1e5)   # tiny "device" -> chunksize floor 5 + warning
+    monkeypatch.setattr(window, "available_memory", lambda device=None, **kw: 1e5)   # tiny "device" -> chunksize floor 5 + warning
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter("always")
         ds = velocimetry.get_b2piv(da, y, x, np.full(5, 1 / 30), (32, 32), (16, 16), (32, 32), res, res)
@@ -336,3 +336,21 @@ def test_metrics_sidecar_one_json_line_per_call(fake, tmp_path, monkeypatch):
     assert [r["mode"] for r in recs] == ["per-time-step", "ensemble"]
     assert recs[0]["windows"] == 5 * nr * nc and recs[0]["chunks"] == 2 and recs[0]["alg_bytes"] == 5 * nr * nc * (2 * 16 * 16 + 16)
     assert recs[0]["windows_per_s"] > 0 and recs[0]["devices"] == [0]
+
+
+def test_result_block_of_engine_fields():
+    """parallel._result_block: the four fields Engine.pairs returns are views of one [4, pairs, rows, cols] block - the push gather
+    forwards that block without a copy; anything else is stacked."""
+    import torch
+
+    from pyorc_b200 import parallel
+
+    block = torch.arange(4 * 3 * 5 * 6, dtype=torch.float32).reshape(4, 3, 5, 6)
+    views = (block[0], block[1], block[2], block[3])
+    assert parallel._result_block(views).data_ptr() == block.data_ptr()
+    assert parallel._result_block(block) is block
+    loose = tuple(v.clone() for v in views)
+    got = parallel._result_block(loose)
+    assert got.data_ptr() != block.data_ptr() and torch.equal(got, block)
+    partial = (block[0, 1:], block[1, 1:], block[2, 1:], block[3, 1:])     # views, but not of the whole block: must be copied
+    assert torch.equal(parallel._result_block(partial), block[:, 1:])

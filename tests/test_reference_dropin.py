@@ -74,7 +74,7 @@ def frames_proj(ref):
 def fake(monkeypatch):
     fe = FakeEngine()
     monkeypatch.setattr(velocimetry, "get_engine", lambda device=0, slot=0: fe)
-    monkeypatch.setattr(b2window, "available_memory", lambda device=None: 64e9)
+    monkeypatch.setattr(b2window, "available_memory", lambda device=None, **kw: 64e9)
     O.CLIP_NORMALIZED = False
     return fe
 
@@ -146,7 +146,7 @@ def test_concurrent_calls_with_different_engines_do_not_cross(ref, frames_proj, 
 
     fe = SlowFake()
     monkeypatch.setattr(velocimetry, "get_engine", lambda device=0, slot=0: fe)
-    monkeypatch.setattr(b2window, "available_memory", lambda device=None: 64e9)
+    monkeypatch.setattr(b2window, "available_memory", lambda device=None, **kw: 64e9)
     out = {}
     t = threading.Thread(target=lambda: out.setdefault("b200", frames_proj.frames.get_piv(window_size=10, engine="b200")))
     t.start()

@@ -28,3 +28,22 @@ for _ in range(10):
     velocimetry.get_b2piv(*args)
 pr.disable()
 pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
+from pyorc_b200 import window
+t0 = time.perf_counter()
+for _ in range(20):
+    window.available_memory(0)
+print("available_memory: %.3f ms" % ((time.perf_counter() - t0) * 50))
+pin = eng.pinned_empty(host.shape, np.uint8) if hasattr(eng, "pinned_empty") else None
+if pin is not None:
+    pin[...] = host
+    t0 = time.perf_counter()
+    for _ in range(10):
+        eng.pairs(pin, WS, OV)
+    print("Engine.pairs page-locked: %.2f ms" % ((time.perf_counter() - t0) * 100))
+for thr in (4, 8, 12, 16):
+    eng.set_option("stage_threads", thr)
+    eng.pairs(host, WS, OV)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        eng.pairs(host, WS, OV)
+    print("Engine.pairs pageable, %d stage threads: %.2f ms" % (thr, (time.perf_counter() - t0) * 100))

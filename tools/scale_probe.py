@@ -41,7 +41,7 @@ def full():
     pg.begin(); eng.pairs(fr, WS, OV); pg.end()
 def push():
     eng.set_peer_outputs(None, 1, 0)
-    pp.begin(); res = eng.pairs(fr, WS, OV); pp.end(res[0]._base)
+    pp.begin(); res = eng.pairs(fr, WS, OV); pp.end(res)
 for name, fn in (("kernel alone", alone), ("fused: + P2P stores", stores_only), ("fused: + barrier (consumer)", full), ("push on the consumer stream", push), ("kernel alone", alone),
                  ("fused: + barrier (consumer)", full), ("push on the consumer stream", push)):
     ms = timed(fn)

@@ -4,7 +4,8 @@
 
 // 128 x 128 windows: four polyphase sub-groups of 64 threads run the 64 x 64 pipeline above and meet in the cross-spectrum
 // phase (piv_rows128.cuh).  One CTA = one group of 256 threads = one pair of adjacent windows followed through a run of
-// frames; 213 KB of shared memory (4 x transpose blocks + parked spectra), one CTA per SM.
+// frames; 213 KB of shared memory (4 x transpose blocks + exchange of the new spectra), the parked spectra in Tensor Memory,
+// one CTA per SM.
 __global__ void __launch_bounds__(256, 1) piv_rows128_kernel(const __grid_constant__ CUtensorMap tmap, RParams p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -13,11 +14,22 @@ __global__ void __launch_bounds__(256, 1) piv_rows128_kernel(const __grid_consta
     const int sub = tid >> 6;      // polyphase component (p1, p2) = (sub >> 1, sub & 1)
     const int t = tid & 63;        // thread within the sub-group (= line slot of the 64 x 64 pipeline)
     RSmem<R6>& ss = s.sub[sub];
+    __shared__ uint32_t tm_base_s;
+    const int warp = tid >> 5;
+    static_assert(2 * R128_TM_COLS <= 512, "the two warps of a lane quarter must fit into 512 columns");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tm_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
     if (tid == 0) {
         mbar_init(&s.mbar, 1);
         fence_mbar_init();
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // lane quarter of this warp, column range of this warp within the quarter (piv_rows_tm_kernel)
+    const uint32_t tm = tm_base_s + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(R128_TM_COLS * (warp >> 2));
     uint32_t parity = 0;
     RRegs<R6> r;
     r.half_alpha_prev[0] = r.half_alpha_prev[1] = 0.f;
@@ -48,7 +60,7 @@ __global__ void __launch_bounds__(256, 1) piv_rows128_kernel(const __grid_consta
             for (int stg = 0; stg < 4; ++stg) {
                 fft_reg<64, 0>(r.v);
                 if ((stg & 1) == 0) transpose_device<R6>(ss, r, t, stg != 0);
-                else if (stg == 1) r128_cross(s, r, sub, t);
+                else if (stg == 1) r128_cross(s, r, sub, t, tm);
             }
             const bool dead0 = (r.half_alpha_prev[0] == 0.f) || (r.half_alpha_new[0] == 0.f);
             const bool dead1 = (r.half_alpha_prev[1] == 0.f) || (r.half_alpha_new[1] == 0.f);
@@ -66,6 +78,9 @@ __global__ void __launch_bounds__(256, 1) piv_rows128_kernel(const __grid_consta
         }
         __syncthreads();  // unit boundary: the next unit's first TMA overwrites the transpose blocks
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm_base_s) : "memory");
 }
 
 int launch_rows128(b2piv_engine* e, const Params& gp, cudaStream_t st) {

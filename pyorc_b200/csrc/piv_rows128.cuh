@@ -34,7 +34,8 @@ constexpr int R128_BATCH = 11;     // ky rows per exchange batch (3 batches cove
 constexpr int R128_NPX = 128 * 128;
 // tile: window w rows [32 j, 32 j + 32) -> sub[j].tile() + w * 4096 ([32 rows][128 B], SWIZZLE_128B)
 static_assert(sizeof(float2) * R6::NWARP * R6::XBLK >= 2 * 4096, "tile quarter must fit in a sub-group's transpose blocks");
-static_assert(sizeof(float2) * R6::XBLK >= sizeof(float4) * R128_BATCH * 32, "exchange batch must fit in one warp's block");
+static_assert(sizeof(float2) * R6::NWARP * R6::XBLK >= sizeof(float4) * R128_BATCH * 64, "a batch of returned cross spectra must fit in a sub-group's transpose blocks");
+constexpr int R128_TM_COLS = 4 * 9 * 4;   // Tensor-Memory columns per thread: 4 components x 9 own bins x (A0, A1)
 static_assert(sizeof(RSmem<R6>::park) == sizeof(float4) * 33 * 64, "parked spectra are [33][64] float4");
 
 #ifdef __CUDACC__
@@ -124,91 +125,133 @@ __device__ __forceinline__ float2 cfma(float2 m, float2 b, float2 a) {   // a + 
     return pk_fma(make_float2(-b.y, b.x), make_float2(m.y, m.y), pk_fma(b, make_float2(m.x, m.x), a));
 }
 
-// Both windows of a spectrum bin travel together as one float4 (A0.x, A0.y, A1.x, A1.y): 16-byte shared-memory accesses halve
-// the LSU instruction count of this phase (it is `mio_throttle` bound).  The parked spectra use the memory of
-// RSmem::park ([2][33][64] float2 = [33][64] float4); the exchange slot of batch slot sl for lane `lane` of warp wq of
-// sub-group g lies inside that WARP's own transpose block, so a warp only ever overwrites memory it has finished reading.
-__device__ __forceinline__ float4* r128_xch(R128Smem& s, int g, int wq, int sl, int lane) {
-    return reinterpret_cast<float4*>(&s.sub[g].X[wq][0]) + sl * 32 + lane;
-}
-__device__ __forceinline__ float4* r128_park(R128Smem& s, int g, int ky, int t) {
+// Both windows of a spectrum bin travel together as one float4 (A0.x, A0.y, A1.x, A1.y).  The NEW separated spectra of all four
+// components are published in the memory of RSmem::park ([33][64] float4 per component); the cross spectra travel back to
+// their owners through the transpose blocks ([11][64] float4 per component and batch).  The PARKED spectra of the previous
+// frame live in Tensor Memory, private to the thread that needs them (r128_cross).
+__device__ __forceinline__ float4* r128_pub(R128Smem& s, int g, int ky, int t) {
     return &s.sub[g].park[ky][t];
+}
+__device__ __forceinline__ float4* r128_ret(R128Smem& s, int q, int sl, int t) {
+    return reinterpret_cast<float4*>(&s.sub[q].X[0][0]) + sl * 64 + t;
+}
+__device__ __forceinline__ void tm_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tm_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+                   "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+// wait for the outstanding loads; the registers pass through the statement so that no use of them can be scheduled above it
+__device__ __forceinline__ void tm_wait_ld16(uint32_t (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]) :: "memory");
 }
 
 // exp(+2 pi i ky / 64), ky = 0 .. 32: phase of a carry along y (indexed at run time by the rolled batch loop below)
 __device__ __constant__ float2 R128_TWY[33] = {{1.0000000000e+00f, 0.0000000000e+00f}, {9.9518472667e-01f, 9.8017140330e-02f}, {9.8078528040e-01f, 1.9509032202e-01f}, {9.5694033573e-01f, 2.9028467725e-01f}, {9.2387953251e-01f, 3.8268343237e-01f}, {8.8192126435e-01f, 4.7139673683e-01f}, {8.3146961230e-01f, 5.5557023302e-01f}, {7.7301045336e-01f, 6.3439328416e-01f}, {7.0710678119e-01f, 7.0710678119e-01f}, {6.3439328416e-01f, 7.7301045336e-01f}, {5.5557023302e-01f, 8.3146961230e-01f}, {4.7139673683e-01f, 8.8192126435e-01f}, {3.8268343237e-01f, 9.2387953251e-01f}, {2.9028467725e-01f, 9.5694033573e-01f}, {1.9509032202e-01f, 9.8078528040e-01f}, {9.8017140330e-02f, 9.9518472667e-01f}, {0.0f, 1.0f}, {-9.8017140330e-02f, 9.9518472667e-01f}, {-1.9509032202e-01f, 9.8078528040e-01f}, {-2.9028467725e-01f, 9.5694033573e-01f}, {-3.8268343237e-01f, 9.2387953251e-01f}, {-4.7139673683e-01f, 8.8192126435e-01f}, {-5.5557023302e-01f, 8.3146961230e-01f}, {-6.3439328416e-01f, 7.7301045336e-01f}, {-7.0710678119e-01f, 7.0710678119e-01f}, {-7.7301045336e-01f, 6.3439328416e-01f}, {-8.3146961230e-01f, 5.5557023302e-01f}, {-8.8192126435e-01f, 4.7139673683e-01f}, {-9.2387953251e-01f, 3.8268343237e-01f}, {-9.5694033573e-01f, 2.9028467725e-01f}, {-9.8078528040e-01f, 1.9509032202e-01f}, {-9.9518472667e-01f, 9.8017140330e-02f}, {-1.0f, 0.0f}};
 
-// The cross phase for one thread of sub-group q = sub.  r.v holds Z_q(ky, own column) = FFT of (window 0 + i window 1) of
-// component q; on return r.v holds conj(G_q), G_q = C_q(window 0) + i C_q(window 1), ready for the inverse pass.
+// The cross phase.  On entry r.v holds Z_q(ky, own column) = FFT of (window 0 + i window 1) of the thread's component q = sub;
+// on return r.v holds conj(G_q), G_q = C_q(window 0) + i C_q(window 1), ready for the inverse pass.
+//
+// The sixteen products conj(A_p) B_r of a spectrum bin feed the four C_q, each product exactly one of them.  Round 1 let every
+// sub-group q gather all four parked A_p and all four new B_r of every bin from shared memory - each spectrum value was read
+// four times, 1.1 MB of shared-memory reads per frame and CTA, a third of the frame time.  Now the BINS are dealt out
+// instead of the components: thread (sub, t) takes the ky rows {b0 + sub, b0 + sub + 4, b0 + sub + 8} of each batch of 11 at
+// its own column, for all four components: it reads the four new B_r once (published by their owners), forms the sixteen
+// products and the four C_q with their phase factors, hands (R0, R1)_q back to the owner of component q through the transpose
+// blocks, and keeps the scaled B_p as the next frame's parked spectra - in TENSOR MEMORY, since nobody else ever needs them
+// again: 4 components x 9 bins x 4 floats = 144 columns per thread (.32x32b shape: thread t of warp w owns lane
+// 32 (w % 4) + t; the two warps of a lane quarter use columns [0, 144) and [144, 288)).  Shared-memory traffic of the phase:
+// 0.54 MB per frame instead of 1.5 MB.
 //
 // Code size matters more than instruction count here (the frame loop is far beyond the instruction caches: a fully
-// unrolled version of this phase - 33 ky steps - ran at HALF the speed), so the three batches share ONE copy of the code:
-// the registers are viewed as lo[ky] = Z(ky) and hi[ky] = Z(-ky) (ky = 0 .. 32; hi[0], hi[32] are copies of the self-paired
-// lines), a batch always works on lo[0..10] / hi[0..10], and both arrays are rotated by 11 between batches (66 register
-// moves per batch) - after three batches they are back in natural order.
-__device__ __forceinline__ void r128_cross(R128Smem& s, RRegs<R6>& r, int sub, int t) {
+// unrolled version of this phase ran at HALF the speed), so the three batches share ONE copy of the code: the results are
+// collected in lo[ky] = conj G(ky) and hi[ky] = conj G(-ky) (ky = 0 .. 32), a batch always writes lo[0..10] / hi[0..10], and both
+// arrays are rotated by 11 between batches (66 register moves per batch) - after three batches they are in natural order.
+__device__ __forceinline__ void r128_cross(R128Smem& s, RRegs<R6>& r, int sub, int t, uint32_t tm) {
     constexpr float SCALE = 1.0f / (4096.0f * (float)R128_NPX);   // 1/4096 of the 64x64 inverse, 1/N of the coefficient
     constexpr int B = R128_BATCH;
-    const int lane = t & 31, wq = t >> 5;
-    const int q1 = sub >> 1, q2 = sub & 1;
     const int pl = partner_lane_of<64>(t);
-    // phase factor of a carry along x: exp(+2 pi i c / 64) for the own column c (1 when q2 = 0)
+    // phase factor of a carry along x: exp(+2 pi i c / 64) for the own column c
     const int c = column_of<64>(t);
     float sn, cs;
     sincospif((float)c * (1.0f / 32.0f), &sn, &cs);
-    const float2 m2 = q2 ? make_float2(cs, sn) : make_float2(1.f, 0.f);
-    // new spectra of component p xor q come from sub-group p xor q's exchange block
-    const float4* xb[4];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) xb[p] = r128_xch(s, p ^ sub, wq, 0, lane);
-    float4* own = r128_xch(s, sub, wq, 0, lane);
+    const float2 mx = make_float2(cs, sn);
     if (t == 0) r.v[0] = pk_sub(r.v[0], make_float2(r.dc_fix[0], r.dc_fix[1]));   // Z_q(0, 0): thread 0 of a sub-group owns column 0 (r128_p2)
-    float2 lo[33], hi[33];
+    // -- publish the separated new spectra B0, B1 of the own component, all ky
 #pragma unroll
-    for (int k = 0; k <= 32; ++k) { lo[k] = r.v[k]; hi[k] = r.v[(64 - k) % 64]; }
+    for (int ky = 0; ky <= 32; ++ky) {
+        const float2 pz = shfl2(r.v[(64 - ky) % 64], pl);
+        float2 a0, a1;
+        separate(r.v[ky], pz, r.half_alpha_new[0], r.half_alpha_new[1], a0, a1);
+        *r128_pub(s, sub, ky, t) = make_float4(a0.x, a0.y, a1.x, a1.y);
+    }
+    uint32_t cur[16];
+    tm_ld16(tm, cur);            // parked spectra of the first own bin (batch 0, j = 0); in flight across the barrier
+    __syncthreads();
+    float2 lo[33], hi[33];
+    int n_bin = 0;               // running index of the own bins: 3 * batch + j
 #pragma unroll 1
     for (int b0 = 0; b0 < 33; b0 += B) {
-        // -- publish the separated new spectra A0, A1 of this batch
+        // -- own bins of this batch: ky = b0 + sub + 4 j
 #pragma unroll
-        for (int sl = 0; sl < B; ++sl) {
-            const float2 pz = shfl2(hi[sl], pl);
-            float2 a0, a1;
-            separate(lo[sl], pz, r.half_alpha_new[0], r.half_alpha_new[1], a0, a1);
-            own[sl * 32] = make_float4(a0.x, a0.y, a1.x, a1.y);
-        }
-        __syncthreads();
-        // -- cross spectra of this batch
+        for (int j = 0; j < 3; ++j) {
+            const int sl = sub + 4 * j;
+            if (sl < B) {        // warp-uniform (sub-group 3 has two bins per batch)
+                tm_wait_ld16(cur);
+                const int ky = b0 + sl;
+                const float2 my = R128_TWY[ky];
+                float4 nw[4];
 #pragma unroll
-        for (int sl = 0; sl < B; ++sl) {
-            const int ky = b0 + sl;
-            const float2 tw = R128_TWY[ky];
-            const float2 m1 = q1 ? tw : make_float2(1.f, 0.f);
-            float2 term[2][4];
+                for (int p = 0; p < 4; ++p) nw[p] = *r128_pub(s, p, ky, t);
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                const float4 pk = *r128_park(s, p, ky, t);
-                const float4 nw = xb[p][sl * 32];
-                term[0][p] = cmulc(make_float2(pk.x, pk.y), make_float2(nw.x, nw.y));
-                term[1][p] = cmulc(make_float2(pk.z, pk.w), make_float2(nw.z, nw.w));
+                for (int q = 0; q < 4; ++q) {
+                    float2 R[2];
+#pragma unroll
+                    for (int w = 0; w < 2; ++w) {
+                        float2 term[4];
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            const float2 a = make_float2(__uint_as_float(cur[4 * p + 2 * w]), __uint_as_float(cur[4 * p + 2 * w + 1]));
+                            const float4 n4 = nw[p ^ q];
+                            term[p] = cmulc(a, w == 0 ? make_float2(n4.x, n4.y) : make_float2(n4.z, n4.w));
+                        }
+                        // p = (p1, p2) = (p >> 1, p & 1), carry s = p and q: R = t0 + mx^q2 t1 + my^q1 (t2 + mx^q2 t3)
+                        const float2 l = (q & 1) ? cfma(mx, term[1], term[0]) : pk_add(term[0], term[1]);
+                        const float2 h = (q & 1) ? cfma(mx, term[3], term[2]) : pk_add(term[2], term[3]);
+                        R[w] = (q & 2) ? cfma(my, h, l) : pk_add(l, h);
+                    }
+                    *r128_ret(s, q, sl, t) = make_float4(R[0].x, R[0].y, R[1].x, R[1].y);
+                }
+                // the parked spectra of the next own bin (of this batch, else of the next one) travel while the results are stored
+                if (j < 2 && sub + 4 * (j + 1) < B) tm_ld16(tm + 16 * (n_bin + j + 1), cur);
+                else if (b0 + B < 33) tm_ld16(tm + 16 * (n_bin + 3), cur);
+                // the new spectra become the parked ones (scaled once, here)
+                uint32_t out[16];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const float2 s0 = pk_scale(make_float2(nw[p].x, nw[p].y), SCALE), s1 = pk_scale(make_float2(nw[p].z, nw[p].w), SCALE);
+                    out[4 * p] = __float_as_uint(s0.x); out[4 * p + 1] = __float_as_uint(s0.y);
+                    out[4 * p + 2] = __float_as_uint(s1.x); out[4 * p + 3] = __float_as_uint(s1.y);
+                }
+                tm_st16(tm + 16 * (n_bin + j), out);
             }
-            float2 R[2];
-#pragma unroll
-            for (int w = 0; w < 2; ++w) {
-                // p = (p1, p2) = (p >> 1, p & 1): R = t00 + m2 t01 + m1 (t10 + m2 t11)
-                const float2 l = cfma(m2, term[w][1], term[w][0]);
-                const float2 h = cfma(m2, term[w][3], term[w][2]);
-                R[w] = cfma(m1, h, l);
-            }
-            lo[sl] = pk_sub(make_float2(R[0].x, -R[0].y), make_float2(R[1].y, R[1].x));   // conj(G), G = R0 + i R1
-            hi[sl] = shfl2(cross_mirror(R[0], R[1]), pl);                         // conj(G(-ky)); unused for ky = 0, 32
         }
+        n_bin += 3;
         __syncthreads();
-        // -- the new spectra become the parked ones (scaled once, here)
+        // -- the cross spectra of the own component come back
 #pragma unroll
         for (int sl = 0; sl < B; ++sl) {
-            const float4 a = own[sl * 32];
-            const float2 s0 = pk_scale(make_float2(a.x, a.y), SCALE), s1 = pk_scale(make_float2(a.z, a.w), SCALE);
-            *r128_park(s, sub, b0 + sl, t) = make_float4(s0.x, s0.y, s1.x, s1.y);
+            const float4 R = *r128_ret(s, sub, sl, t);
+            const float2 R0 = make_float2(R.x, R.y), R1 = make_float2(R.z, R.w);
+            lo[sl] = pk_sub(make_float2(R0.x, -R0.y), make_float2(R1.y, R1.x));   // conj(G), G = R0 + i R1
+            hi[sl] = shfl2(cross_mirror(R0, R1), pl);                             // conj(G(-ky)); unused for ky = 0, 32
         }
         // -- rotate both register arrays by one batch
         float2 tl[B], th[B];
@@ -218,7 +261,9 @@ __device__ __forceinline__ void r128_cross(R128Smem& s, RRegs<R6>& r, int sub, i
         for (int k = 0; k + B < 33; ++k) { lo[k] = lo[k + B]; hi[k] = hi[k + B]; }
 #pragma unroll
         for (int k = 0; k < B; ++k) { lo[33 - B + k] = tl[k]; hi[33 - B + k] = th[k]; }
+        __syncthreads();         // the next batch (or the transposes of the inverse pass) overwrite the blocks
     }
+    tm_wait_st();
 #pragma unroll
     for (int k = 0; k <= 32; ++k) r.v[k] = lo[k];
 #pragma unroll

@@ -184,11 +184,15 @@ int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
 int dispatch_ens(b2piv_engine* e, const Params& p, const EnsParams& ep, cudaStream_t st) {
     if (p.n_pairs <= 0) return B2PIV_OK;
     const bool can_rows = rows_eligible(e, p.frames, p.frame_stride, p.pitch);
-    if (e->variant == 2 && !can_rows)
-        return fail(e, B2PIV_ERR_UNSUPPORTED, "rows kernel needs a square 32/64 window, 16-byte aligned base/pitch and an x stride that is a multiple of 4");
+    if (e->variant == 2 && !can_rows && !rows128_eligible(e, p.frames, p.frame_stride, p.pitch))
+        return fail(e, B2PIV_ERR_UNSUPPORTED, "rows kernel needs a square 32/64 window (or 128x128 uint8), 16-byte aligned base/pitch and an x stride that is a multiple of 4");
     if (can_rows && e->variant != 1 && e->variant != 3) {
         e->last_variant = 2;
         return launch_rows_ens(e, p, ep, st);
+    }
+    if (rows128_eligible(e, p.frames, p.frame_stride, p.pitch) && (e->variant == 0 || e->variant == 2)) {
+        e->last_variant = 2;
+        return launch_rows128(e, p, st, &ep);     // polyphase kernel, ensemble epilogue
     }
     const bool tiny = !fft_config(e->wy, e->wx) && e->wy * e->wx <= 144;
     if (e->variant == 4 && !pad_eligible(e, p.frames, p.frame_stride, p.pitch))

@@ -6,6 +6,7 @@
 // phase (piv_rows128.cuh).  One CTA = one group of 256 threads = one pair of adjacent windows followed through a run of
 // frames; 213 KB of shared memory (4 x transpose blocks + exchange of the new spectra), the parked spectra in Tensor Memory,
 // one CTA per SM.
+template <bool ENS>
 __global__ void __launch_bounds__(256, 1) piv_rows128_kernel(const __grid_constant__ CUtensorMap tmap, RParams p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -67,12 +68,16 @@ __global__ void __launch_bounds__(256, 1) piv_rows128_kernel(const __grid_consta
             rows_p5_post<R6, false>(ss, r, t, dead0, dead1, &p);
             __syncthreads();  // E1: block max / sum of all components; the transpose blocks are free again
             if (tid == 0 && k + 1 < nfr) issue_frame(f + 1);
-            r128_p6(s, r, sub, t);
-            __syncthreads();  // E2: first-argmax keys
-            if (have_prev) r128_dump_planes(r, sub, t, p, un, f - 1);
-            r128_p7(s, r, sub, t);
-            __syncthreads();  // F: neighbour rows dumped
-            if (have_prev) r128_p8(s, r, tid, p, un, f - 1);
+            if constexpr (ENS) {
+                r128_ens(s, r, sub, t, tid, p, un, f - 1, have_prev);   // thresholds + accumulate; no peak search per pair
+            } else {
+                r128_p6(s, r, sub, t);
+                __syncthreads();  // E2: first-argmax keys
+                if (have_prev) r128_dump_planes(r, sub, t, p, un, f - 1);
+                r128_p7(s, r, sub, t);
+                __syncthreads();  // F: neighbour rows dumped
+                if (have_prev) r128_p8(s, r, tid, p, un, f - 1);
+            }
             r.half_alpha_prev[0] = r.half_alpha_new[0];
             r.half_alpha_prev[1] = r.half_alpha_new[1];
         }
@@ -83,7 +88,7 @@ __global__ void __launch_bounds__(256, 1) piv_rows128_kernel(const __grid_consta
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm_base_s) : "memory");
 }
 
-int launch_rows128(b2piv_engine* e, const Params& gp, cudaStream_t st) {
+int launch_rows128(b2piv_engine* e, const Params& gp, cudaStream_t st, const EnsParams* ep) {
     const int n_frames = gp.n_pairs + 1;
     CUtensorMap tmap;
     const cuuint64_t dims[3] = {(cuuint64_t)e->W, (cuuint64_t)e->H, (cuuint64_t)n_frames};
@@ -101,21 +106,23 @@ int launch_rows128(b2piv_engine* e, const Params& gp, cudaStream_t st) {
     p.clip_norm = gp.clip_norm; p.border_nan = gp.border_nan; p.gauss_eps = gp.gauss_eps; p.keep = gp.keep;
     p.u = gp.u; p.v = gp.v; p.cmax = gp.cmax; p.s2n = gp.s2n; p.planes = gp.planes; p.peer = gp.peer;
     p.ny = p.nx = 128;
+    if (ep) { p.corr_min = ep->corr_min; p.s2n_min = ep->s2n_min; p.ens_sum = ep->plane_sum; p.ens_count = ep->count; }
+    auto kern = ep ? piv_rows128_kernel<true> : piv_rows128_kernel<false>;
     const size_t smem = sizeof(R128Smem) + 1024;
-    CK(cudaFuncSetAttribute(piv_rows128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, piv_rows128_kernel, 256, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
     if (occ < 1) return fail(e, B2PIV_ERR_CUDA, "128x128 rows kernel does not fit on an SM");
     const long long resident = (long long)occ * e->sm_count;
     const int nw = gp.n_rows * gp.n_cols, n_wp = (nw + 1) / 2;
     int run = e->run_len;
     if (run <= 0) run = pick_run_len(gp.n_pairs, n_wp, resident);   // engine.h
-    if (run > gp.n_pairs) run = gp.n_pairs;
+    if (run > gp.n_pairs || ep) run = gp.n_pairs;   // ensemble: one unit owns its windows' accumulators for the whole launch
     p.run_len = run;
     const long long n_units = (long long)n_wp * ((gp.n_pairs + run - 1) / run);
     p.n_units = (int)n_units;
     long long grid = n_units < resident ? n_units : resident;
-    piv_rows128_kernel<<<(unsigned)grid, 256, smem, st>>>(tmap, p);
+    kern<<<(unsigned)grid, 256, smem, st>>>(tmap, p);
     CK(cudaGetLastError());
     e->launches++;
     return B2PIV_OK;

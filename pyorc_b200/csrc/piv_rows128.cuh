@@ -362,6 +362,63 @@ __device__ __forceinline__ void r128_p8(R128Smem& s, RRegs<R6>& r, int tid, cons
     if (p.peer.n) peer_store(p.peer, pair, (long long)p.n_rows * p.n_cols, widx, uu, vv, oc, os);
 }
 
+// Ensemble mode (rows_ens of piv_rows.cuh for the polyphase layout): thresholds on the pair's max / mean, then the plane is added
+// to the window's accumulator in HBM with fire-and-forget reductions at the L2.  A thread holds every other element of one
+// reference row and the lanes of a warp hold different rows, so reductions straight from the registers touch 32 sectors per
+// instruction (measured 7.7 M windows/s, bound by the L2's atomic rate).  The planes are therefore put in reference order in
+// shared memory first - in the memory of the published spectra, idle after the cross phase; row pitch 129 floats: the stores of a
+// warp (32 rows, one column) and the loads (one row, 32 columns) are both conflict-free - and added by all 256 threads with
+// consecutive lanes on consecutive floats: 4 sectors per instruction.  Every element is added by the same thread in every frame,
+// in frame order = the reference's np.sum(corr, axis=0) (pyorc/velocimetry/ffpiv.py:345-376).
+__device__ __forceinline__ float* r128_stage(R128Smem& s, int w, int row) {     // window w, reference row: 64 rows per spectrum block
+    return reinterpret_cast<float*>(&s.sub[2 * w + (row >> 6)].park[0][0]) + (row & 63) * 129;
+}
+static_assert(sizeof(RSmem<R6>::park) >= 64 * 129 * sizeof(float), "half a staged plane must fit in a spectrum block");
+__device__ __forceinline__ void r128_ens(R128Smem& s, RRegs<R6>& r, int sub, int t, int tid, const RParams& p, const RUnit& un, int pair, bool store) {
+    const int q1 = sub >> 1, q2 = sub & 1;
+    const int si = (2 * column_of<64>(t) + q1 + 64) & 127;
+    const long long nw = (long long)p.n_rows * p.n_cols;
+    bool okw[2];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        float M = 0.f, S = 0.f;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) { M = fmaxf(M, bits_f(s.sub[g].red[k][4 + w])); S += bits_f(s.sub[g].red[k][6 + w]); }
+        }
+        const float ratio = M / (S / (float)R128_NPX);
+        const int widx = w == 0 ? un.w[0] : un.w[1];
+        bool ok = (M >= p.corr_min) && (ratio >= p.s2n_min) && !r.dead[w];   // dead: 0 / 0 = NaN fails the test in the reference
+        if (p.keep && !p.keep[widx]) ok = false;                             // NaN plane in the reference -> masked out
+        const bool wr = store && !(w == 1 && !un.valid1);
+        okw[w] = ok && wr;                                                   // the same for every thread of the CTA
+        if (okw[w]) {
+            float* row = r128_stage(s, w, si);
+#pragma unroll
+            for (int x = 0; x < 64; ++x) row[(2 * x + q2 + 64) & 127] = w == 0 ? r.v[x].x : r.v[x].y;
+        }
+        if (wr && tid == 0) {
+            const long long o = (long long)pair * nw + widx;
+            p.cmax[o] = ok ? M : 0.f;
+            p.s2n[o] = ok ? ratio : 0.f;
+            if (ok && M > 1e-6f) p.ens_count[widx] += 1.f;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        if (!okw[w]) continue;
+        float* dst = p.ens_sum + (long long)(w == 0 ? un.w[0] : un.w[1]) * R128_NPX;
+        const int col = tid & 127;
+#pragma unroll 8
+        for (int i = 0; i < 64; ++i) {
+            const int row = 2 * i + (tid >> 7);
+            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + row * 128 + col), "f"(r128_stage(s, w, row)[col]) : "memory");
+        }
+    }
+}
+
 // optional triage dump of the full planes (fftshifted, clipped): every thread writes its 64 elements of one reference row
 __device__ __forceinline__ void r128_dump_planes(RRegs<R6>& r, int sub, int t, const RParams& p, const RUnit& un, int pair) {
     if (!p.planes) return;

@@ -405,7 +405,8 @@ def test_ensemble_mode_matches_oracle(engine, ws, ov, shape, corr_min, s2n_min, 
 
 
 @pytest.mark.parametrize("ws,ov,shape,dtype", [((64, 64), (32, 32), (7, 270, 400), np.float32), ((32, 32), (24, 24), (6, 100, 144), np.uint8),
-                                               ((32, 32), (16, 16), (9, 150, 208), np.float32), ((64, 64), (40, 40), (5, 160, 208), np.uint8)])
+                                               ((32, 32), (16, 16), (9, 150, 208), np.float32), ((64, 64), (40, 40), (5, 160, 208), np.uint8),
+                                               ((128, 128), (64, 64), (5, 300, 432), np.uint8)])     # polyphase kernel, ensemble epilogue
 def test_ensemble_rows_kernel_device_frames(engine, ws, ov, shape, dtype):
     """Device-resident chunk in ONE launch (a unit walks all frames and adds its planes to the HBM accumulators): float32
     frames and window starts that are not 16-byte aligned, against the oracle's plane sums (no thresholds, so no pair can

@@ -76,6 +76,10 @@ if __name__ == "__main__":
         run_ens(1080, 1920, (26, 26), (12, 12), 21, variant=0)
         run_ens(1080, 1920, (26, 26), (12, 12), 21, variant=1)
         sys.exit(0)
+    if "--ens128" in sys.argv:
+        for variant in (0, 1):
+            run_ens(2160, 3840, (128, 128), (64, 64), 21, variant=variant)
+        sys.exit(0)
     if "--ens" in sys.argv:
         for variant in (1, 0):
             run_ens(1080, 1920, (64, 64), (32, 32), 101, variant=variant)

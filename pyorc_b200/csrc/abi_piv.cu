@@ -134,6 +134,15 @@ static bool pad_eligible(const b2piv_engine* e, const void* d_frames, long long 
     return tma_available();
 }
 
+// Padded mode of the 128-plane polyphase kernel: even uint8 windows whose larger side is 34 .. 64 px (piv_rows128.cuh)
+static bool pad128_eligible(const b2piv_engine* e, const void* d_frames, long long frame_stride, int pitch) {
+    const int m = e->wy > e->wx ? e->wy : e->wx;
+    if (e->dtype != B2PIV_U8 || m <= 32 || m > 64 || (e->wy & 1) || (e->wx & 1) || e->wy < 2 || e->wx < 2) return false;
+    if (fft_config(e->wy, e->wx)) return false;   // compiled FFT shapes (64x64, 64x32 ...) have their own kernels
+    if ((pitch & 15) || (frame_stride & 15) || (((uintptr_t)d_frames) & 15)) return false;
+    return tma_available();
+}
+
 int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
     if (p.n_pairs <= 0) return B2PIV_OK;
     // displaced second-pass windows (multipass.cuh) break the frame-to-frame spectrum sharing of the row-per-thread kernels
@@ -168,9 +177,13 @@ int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
         e->last_variant = 3;
         return launch_direct_big(e, p, st);
     }
+    if (pad128_eligible(e, p.frames, p.frame_stride, p.pitch) && (e->variant == 0 || e->variant == 4)) {
+        e->last_variant = 4;
+        return launch_rows128(e, p, st, nullptr, true);
+    }
     const bool tiny = !fft_config(e->wy, e->wx) && e->wy * e->wx <= 144;
     if (e->variant == 4 && !pad_eligible(e, p.frames, p.frame_stride, p.pitch))
-        return fail(e, B2PIV_ERR_UNSUPPORTED, "padded rows kernel needs uint8 frames, a window of at most 32 px and 16-byte aligned base/pitch");
+        return fail(e, B2PIV_ERR_UNSUPPORTED, "padded rows kernels need uint8 frames, an even window of at most 64 px and 16-byte aligned base/pitch");
     if (pad_eligible(e, p.frames, p.frame_stride, p.pitch) && (e->variant == 4 || (e->variant == 0 && !fft_config(e->wy, e->wx)))) {
         e->last_variant = 4;
         return launch_rows_pad(e, p, st, nullptr);

@@ -286,7 +286,7 @@ int launch_rows_f32(b2piv_engine* e, const Params& p, cudaStream_t st);         
 int launch_rows_ens(b2piv_engine* e, const Params& p, const EnsParams& ep, cudaStream_t st);         // k_rows_ens.cu (uint8 and float32)
 int launch_rows_pad(b2piv_engine* e, const Params& p, cudaStream_t st, const EnsParams* ep);         // k_rows_pad.cu
 int launch_rows_shift(b2piv_engine* e, const Params& p, cudaStream_t st);                            // k_rows_shift.cu
-int launch_rows128(b2piv_engine* e, const Params& p, cudaStream_t st, const EnsParams* ep = nullptr);                               // k_rows128.cu
+int launch_rows128(b2piv_engine* e, const Params& p, cudaStream_t st, const EnsParams* ep = nullptr, bool pad = false);                               // k_rows128.cu
 // dispatch (abi_piv.cu)
 int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st);
 int dispatch_ens(b2piv_engine* e, const Params& p, const EnsParams& ep, cudaStream_t st);

@@ -6,7 +6,7 @@
 // phase (piv_rows128.cuh).  One CTA = one group of 256 threads = one pair of adjacent windows followed through a run of
 // frames; 213 KB of shared memory (4 x transpose blocks + exchange of the new spectra), the parked spectra in Tensor Memory,
 // one CTA per SM.
-template <bool ENS>
+template <bool ENS, bool PAD>
 __global__ void __launch_bounds__(256, 1) piv_rows128_kernel(const __grid_constant__ CUtensorMap tmap, RParams p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -37,14 +37,22 @@ __global__ void __launch_bounds__(256, 1) piv_rows128_kernel(const __grid_consta
     for (long long unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
         const RUnit un = decode_unit(p, (int)unit);
         const int nfr = un.f1 - un.f0 + 1;
+        const int xa0 = un.x0[0] & ~15, xa1 = un.x0[1] & ~15;      // padded mode: boxes from the 16-byte boundary below
+        const int xoff0 = un.x0[0] - xa0, xoff1 = un.x0[1] - xa1;
         auto issue_frame = [&](int frame) {
             fence_proxy_async();
-            mbar_expect_tx(&s.mbar, 2 * 128 * 128);
+            if constexpr (PAD) {
+                mbar_expect_tx(&s.mbar, 2 * R128_PWIN);
+                tma_load_3d(s.sub[0].tile(), &tmap, &s.mbar, xa0, un.y0[0], frame);
+                tma_load_3d(s.sub[0].tile() + R128_PWIN, &tmap, &s.mbar, xa1, un.y0[1], frame);
+            } else {
+                mbar_expect_tx(&s.mbar, 2 * 128 * 128);
 #pragma unroll
-            for (int w = 0; w < 2; ++w)
+                for (int w = 0; w < 2; ++w)
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    tma_load_3d(s.sub[j].tile() + w * 4096, &tmap, &s.mbar, un.x0[w], un.y0[w] + 32 * j, frame);
+                    for (int j = 0; j < 4; ++j)
+                        tma_load_3d(s.sub[j].tile() + w * 4096, &tmap, &s.mbar, un.x0[w], un.y0[w] + 32 * j, frame);
+            }
         };
         if (tid == 0) issue_frame(un.f0);
         for (int k = 0; k < nfr; ++k) {
@@ -52,31 +60,31 @@ __global__ void __launch_bounds__(256, 1) piv_rows128_kernel(const __grid_consta
             const int f = un.f0 + k;
             while (!mbar_try_wait(&s.mbar, parity)) {}
             parity ^= 1u;
-            r128_p1(s, r, sub, t);
+            if constexpr (PAD) r128_p1_pad(s, r, sub, t, p, xoff0, xoff1); else r128_p1(s, r, sub, t);
             __syncthreads();  // A: integer moments visible, tile (aliased on the transpose blocks) fully consumed
-            r128_p2(s, r, p.clip_norm);
+            if constexpr (PAD) r128_p2_pad(s, r, t, p); else r128_p2(s, r, p.clip_norm);
             // forward: FFT(rows) T FFT(cols) per component; cross spectra across components; inverse: FFT(cols) T FFT(rows)
             // (one copy of the unrolled FFT: the loop body is far beyond the instruction caches, every KB counts)
 #pragma unroll 1
             for (int stg = 0; stg < 4; ++stg) {
                 fft_reg<64, 0>(r.v);
                 if ((stg & 1) == 0) transpose_device<R6>(ss, r, t, stg != 0);
-                else if (stg == 1) r128_cross(s, r, sub, t, tm);
+                else if (stg == 1) r128_cross<PAD>(s, r, sub, t, tm, p);
             }
             const bool dead0 = (r.half_alpha_prev[0] == 0.f) || (r.half_alpha_new[0] == 0.f);
             const bool dead1 = (r.half_alpha_prev[1] == 0.f) || (r.half_alpha_new[1] == 0.f);
-            rows_p5_post<R6, false>(ss, r, t, dead0, dead1, &p);
+            rows_p5_post<R6, PAD>(ss, r, t, dead0, dead1, &p);
             __syncthreads();  // E1: block max / sum of all components; the transpose blocks are free again
             if (tid == 0 && k + 1 < nfr) issue_frame(f + 1);
             if constexpr (ENS) {
                 r128_ens(s, r, sub, t, tid, p, un, f - 1, have_prev);   // thresholds + accumulate; no peak search per pair
             } else {
-                r128_p6(s, r, sub, t);
+                if constexpr (PAD) r128_p6_pad(s, r, sub, t, p); else r128_p6(s, r, sub, t);
                 __syncthreads();  // E2: first-argmax keys
-                if (have_prev) r128_dump_planes(r, sub, t, p, un, f - 1);
-                r128_p7(s, r, sub, t);
+                if (have_prev) { if constexpr (PAD) r128_dump_planes_pad(r, sub, t, p, un, f - 1); else r128_dump_planes(r, sub, t, p, un, f - 1); }
+                if constexpr (PAD) r128_p7_pad(s, r, sub, t, p); else r128_p7(s, r, sub, t);
                 __syncthreads();  // F: neighbour rows dumped
-                if (have_prev) r128_p8(s, r, tid, p, un, f - 1);
+                if (have_prev) { if constexpr (PAD) r128_p8(s, r, tid, p, un, f - 1, 2 * p.ny, 2 * p.nx); else r128_p8(s, r, tid, p, un, f - 1); }
             }
             r.half_alpha_prev[0] = r.half_alpha_new[0];
             r.half_alpha_prev[1] = r.half_alpha_new[1];
@@ -88,15 +96,16 @@ __global__ void __launch_bounds__(256, 1) piv_rows128_kernel(const __grid_consta
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm_base_s) : "memory");
 }
 
-int launch_rows128(b2piv_engine* e, const Params& gp, cudaStream_t st, const EnsParams* ep) {
+int launch_rows128(b2piv_engine* e, const Params& gp, cudaStream_t st, const EnsParams* ep, bool pad) {
+    if (pad && ep) return fail(e, B2PIV_ERR_UNSUPPORTED, "padded 128-plane rows kernel has no ensemble epilogue");
     const int n_frames = gp.n_pairs + 1;
     CUtensorMap tmap;
     const cuuint64_t dims[3] = {(cuuint64_t)e->W, (cuuint64_t)e->H, (cuuint64_t)n_frames};
     const cuuint64_t strides[2] = {(cuuint64_t)gp.pitch, (cuuint64_t)gp.frame_stride};
-    const cuuint32_t box[3] = {128, 32, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)(pad ? R128_PWB : 128), (cuuint32_t)(pad ? 64 : 32), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult cr = get_encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(gp.frames), dims, strides, box, estr,
-                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, pad ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(e, B2PIV_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)cr));
     RParams p;
@@ -106,8 +115,17 @@ int launch_rows128(b2piv_engine* e, const Params& gp, cudaStream_t st, const Ens
     p.clip_norm = gp.clip_norm; p.border_nan = gp.border_nan; p.gauss_eps = gp.gauss_eps; p.keep = gp.keep;
     p.u = gp.u; p.v = gp.v; p.cmax = gp.cmax; p.s2n = gp.s2n; p.planes = gp.planes; p.peer = gp.peer;
     p.ny = p.nx = 128;
+    if (pad) {   // component size; spectrum factor of the 2 x 2 tiling and masks (piv_rows128.cuh, "Padded mode")
+        p.ny = e->wy / 2; p.nx = e->wx / 2;
+        p.pad_scale = (float)(1.0 / (4096.0 * e->wy * e->wx));
+        const double two_pi = 6.283185307179586476925286766559;
+        for (int k = 0; k <= 32; ++k) { const double th = two_pi * (double)((k * p.ny) % 64) / 64; p.pad_ty[k] = make_float2((float)(1.0 + cos(th)), (float)(-sin(th))); }
+        for (int k = 0; k < 64; ++k) { const double th = two_pi * (double)((k * p.nx) % 64) / 64; p.pad_tx[k] = make_float2((float)(1.0 + cos(th)), (float)(-sin(th))); }
+        for (int k = 0; k < 16; ++k) { const int left = e->wx - 4 * k; p.pad_mask[k] = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << (8 * left)) - 1u)); }
+        for (int x = 0; x < 64; ++x) p.pad_cm[x] = x < p.nx ? 1.f : 0.f;
+    }
     if (ep) { p.corr_min = ep->corr_min; p.s2n_min = ep->s2n_min; p.ens_sum = ep->plane_sum; p.ens_count = ep->count; }
-    auto kern = ep ? piv_rows128_kernel<true> : piv_rows128_kernel<false>;
+    auto kern = pad ? piv_rows128_kernel<false, true> : (ep ? piv_rows128_kernel<true, false> : piv_rows128_kernel<false, false>);
     const size_t smem = sizeof(R128Smem) + 1024;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;

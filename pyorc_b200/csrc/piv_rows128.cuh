@@ -31,6 +31,15 @@ struct R128Smem {
     unsigned long long mbar;       // TMA completion barrier of the whole group
 };
 constexpr int R128_BATCH = 11;     // ky rows per exchange batch (3 batches cover ky = 0 .. 32)
+// Padded mode (PAD = true): even windows of 34 .. 64 px per side (the larger one; the other any even size).  The period-n
+// circular correlation of the reference needs a 2n-point plane (piv_rows.cuh, "Padded mode": window `a` zero-padded, window `b`
+// tiled 2 x 2 through the spectrum factor T), i.e. the 128 x 128 plane of this kernel: each polyphase component holds
+// ny/2 x nx/2 samples of the window, the tiling shift n = 2 (n/2) stays inside a component, so T(k) = (1 + e^{-2 pi i k1 (ny/2)/64})
+// (1 + e^{-2 pi i k2 (nx/2)/64}) multiplies every C_q alike.  RParams::ny / nx hold the COMPONENT size (ny/2, nx/2).
+// Tile: one 80-byte x 64-row unswizzled box per window from the 16-byte boundary below its start, in sub[0]'s transpose blocks.
+constexpr int R128_PWB = 80;                    // padded tile: bytes per row
+constexpr int R128_PWIN = 64 * R128_PWB;        // and per window
+static_assert(sizeof(float2) * R6::NWARP * R6::XBLK >= 2 * R128_PWIN, "padded tile must fit in a sub-group's transpose blocks");
 constexpr int R128_NPX = 128 * 128;
 // tile: window w rows [32 j, 32 j + 32) -> sub[j].tile() + w * 4096 ([32 rows][128 B], SWIZZLE_128B)
 static_assert(sizeof(float2) * R6::NWARP * R6::XBLK >= 2 * 4096, "tile quarter must fit in a sub-group's transpose blocks");
@@ -118,6 +127,94 @@ __device__ __forceinline__ void r128_p2(R128Smem& s, RRegs<R6>& r, int clip_norm
     }
 }
 
+// P1 (padded): row 2 sigma(t) + p1 of both windows at their byte offset in the unswizzled tile, masked to the window, bytes of
+// column parity p2 packed (at most 32 per window) -> r.px[w][0..7]; exact integer moments of the sub-image
+__device__ __forceinline__ void r128_p1_pad(R128Smem& s, RRegs<R6>& r, int sub, int t, const RParams& p, int xoff0, int xoff1) {
+    const int p1 = sub >> 1, p2 = sub & 1;
+    const int row = 2 * column_of<64>(t) + p1;
+    const unsigned rowmask = row < 2 * p.ny ? 0xffffffffu : 0u;
+    const int rr = row < 64 ? row : 0;           // rows past the tile are masked anyway
+    const unsigned sel = p2 ? 0x7531u : 0x6420u;
+    unsigned S[2] = {0, 0}, Q[2] = {0, 0};
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        const int xoff = w == 0 ? xoff0 : xoff1;
+        const unsigned char* base = s.sub[0].tile() + w * R128_PWIN + rr * R128_PWB + (xoff & ~3);
+        const int sh = (xoff & 3) * 8;
+        unsigned wd[17];
+#pragma unroll
+        for (int k = 0; k <= 16; ++k) wd[k] = *reinterpret_cast<const unsigned*>(base + 4 * k);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const unsigned a = funnel_r(wd[2 * k], wd[2 * k + 1], sh) & p.pad_mask[2 * k] & rowmask;
+            const unsigned b = funnel_r(wd[2 * k + 1], wd[2 * k + 2], sh) & p.pad_mask[2 * k + 1] & rowmask;
+            r.px[w][k] = __byte_perm(a, b, sel);
+            r.px[w][8 + k] = 0u;
+            S[w] = __dp4a(r.px[w][k], 0x01010101u, S[w]);
+            Q[w] = __dp4a(r.px[w][k], r.px[w][k], Q[w]);
+        }
+    }
+    unsigned vals[4] = {S[0], Q[0], S[1], Q[1]};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) vals[k] = __reduce_add_sync(0xffffffffu, vals[k]);
+    if ((t & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s.sub[sub].red[t >> 5][k] = vals[k];
+    }
+}
+
+// P2 (padded): moments over the ny * nx window pixels (all four components); pixels outside the window stay exactly 0
+__device__ __forceinline__ void r128_p2_pad(R128Smem& s, RRegs<R6>& r, int t, const RParams& p) {
+    const unsigned long long npx = 4ull * (unsigned long long)(p.ny * p.nx);
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        unsigned long long S = 0, Q = 0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) { S += s.sub[g].red[k][2 * w]; Q += s.sub[g].red[k][2 * w + 1]; }
+        }
+        const unsigned long long m2 = npx * Q - S * S;
+        r.mean_new[w] = (float)S / (float)npx;
+        r.half_alpha_new[w] = m2 ? 0.5f * (float)npx * (1.0f / sqrtf((float)m2)) : 0.f;
+    }
+    const bool rowok = column_of<64>(t) < p.ny;
+    r.dc_fix[0] = r.dc_fix[1] = 0.f;
+    if (!p.clip_norm) {
+        // magic-number conversion (rows_p2_pre_pad): byte - cm * mq with the mean rounded to 1/256; a component holds ny * nx
+        // samples (component size), so its DC bin is off by ny * nx * (mean - mq), removed in r128_cross
+        const float c0 = __fadd_rn(32768.0f, r.mean_new[0]), c1 = __fadd_rn(32768.0f, r.mean_new[1]);
+        const float mq0 = c0 - 32768.0f, mq1 = c1 - 32768.0f;
+        r.dc_fix[0] = (r.mean_new[0] - mq0) * (float)(p.ny * p.nx);
+        r.dc_fix[1] = (r.mean_new[1] - mq1) * (float)(p.ny * p.nx);
+        const float2 nm = rowok ? make_float2(-mq0, -mq1) : make_float2(0.f, 0.f);
+        const float2 base = make_float2(32768.0f, 32768.0f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const float2 mg = make_float2(__uint_as_float(__byte_perm(r.px[0][k], 0x47000000u, 0x7404u | (b << 4))),
+                                              __uint_as_float(__byte_perm(r.px[1][k], 0x47000000u, 0x7404u | (b << 4))));
+                r.v[4 * k + b] = pk_fma(make_float2(p.pad_cm[4 * k + b], p.pad_cm[4 * k + b]), nm, pk_sub(mg, base));
+            }
+        }
+    } else {
+        const float nm0 = rowok ? -r.mean_new[0] : 0.f, nm1 = rowok ? -r.mean_new[1] : 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const float a0 = fmaf(p.pad_cm[4 * k + b], nm0, byte_to_float(r.px[0][k], b));
+                const float a1 = fmaf(p.pad_cm[4 * k + b], nm1, byte_to_float(r.px[1][k], b));
+                r.v[4 * k + b] = make_float2(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+            }
+        }
+    }
+#pragma unroll
+    for (int x = 32; x < 64; ++x) r.v[x] = make_float2(0.f, 0.f);
+    r.tx = p.pad_tx[column_of<64>(t)];
+}
+
 // packed fp32 forms (piv_core.cuh): two instructions each
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return ctw<1>(a, b.x, b.y); }
 __device__ __forceinline__ float2 cmulc(float2 p, float2 a) { return ctw<0>(a, p.x, p.y); }   // conj(p) * a
@@ -174,8 +271,9 @@ __device__ __constant__ float2 R128_TWY[33] = {{1.0000000000e+00f, 0.0000000000e
 // unrolled version of this phase ran at HALF the speed), so the three batches share ONE copy of the code: the results are
 // collected in lo[ky] = conj G(ky) and hi[ky] = conj G(-ky) (ky = 0 .. 32), a batch always writes lo[0..10] / hi[0..10], and both
 // arrays are rotated by 11 between batches (66 register moves per batch) - after three batches they are in natural order.
-__device__ __forceinline__ void r128_cross(R128Smem& s, RRegs<R6>& r, int sub, int t, uint32_t tm) {
-    constexpr float SCALE = 1.0f / (4096.0f * (float)R128_NPX);   // 1/4096 of the 64x64 inverse, 1/N of the coefficient
+template <bool PAD>
+__device__ __forceinline__ void r128_cross(R128Smem& s, RRegs<R6>& r, int sub, int t, uint32_t tm, const RParams& p) {
+    const float SCALE = PAD ? p.pad_scale : 1.0f / (4096.0f * (float)R128_NPX);   // 1/4096 of the 64x64 inverse, 1/N of the coefficient
     constexpr int B = R128_BATCH;
     const int pl = partner_lane_of<64>(t);
     // phase factor of a carry along x: exp(+2 pi i c / 64) for the own column c
@@ -207,6 +305,8 @@ __device__ __forceinline__ void r128_cross(R128Smem& s, RRegs<R6>& r, int sub, i
                 tm_wait_ld16(cur);
                 const int ky = b0 + sl;
                 const float2 my = R128_TWY[ky];
+                float2 tile_f = make_float2(1.f, 0.f);   // padded mode: the new window in its tiled role, T(ky, own column) = Ty(ky) Tx
+                if (PAD) tile_f = ctw<1>(p.pad_ty[ky], r.tx.x, r.tx.y);
                 float4 nw[4];
 #pragma unroll
                 for (int p = 0; p < 4; ++p) nw[p] = *r128_pub(s, p, ky, t);
@@ -226,6 +326,7 @@ __device__ __forceinline__ void r128_cross(R128Smem& s, RRegs<R6>& r, int sub, i
                         const float2 l = (q & 1) ? cfma(mx, term[1], term[0]) : pk_add(term[0], term[1]);
                         const float2 h = (q & 1) ? cfma(mx, term[3], term[2]) : pk_add(term[2], term[3]);
                         R[w] = (q & 2) ? cfma(my, h, l) : pk_add(l, h);
+                        if (PAD) R[w] = ctw<1>(R[w], tile_f.x, tile_f.y);
                     }
                     *r128_ret(s, q, sl, t) = make_float4(R[0].x, R[0].y, R[1].x, R[1].y);
                 }
@@ -333,26 +434,100 @@ __device__ __forceinline__ void r128_p7(R128Smem& s, RRegs<R6>& r, int sub, int 
     }
 }
 
+// P6 / P7 (padded): the thread's row holds the lags (2 sigma(t) + q1, 2 x + q2), x < nx (component size); the reference plane
+// is the fftshifted (2 ny) x (2 nx) plane of the window's own size: row / column (lag + n/2) % n, the lags >= n/2 first.
+__device__ __forceinline__ void r128_p6_pad(R128Smem& s, RRegs<R6>& r, int sub, int t, const RParams& p) {
+    const int q1 = sub >> 1, q2 = sub & 1;
+    const int hy = p.ny, hx = p.nx;
+    const bool rowok = column_of<64>(t) < hy;
+    const int si = rowok ? shifted_index(2 * column_of<64>(t) + q1, 2 * hy) : 0;
+    const int xs = (hx - q2 + 1) >> 1;            // first x whose lag 2 x + q2 is >= nx / 2 (= hx)
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        float M = 0.f, S = 0.f;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) { M = fmaxf(M, bits_f(s.sub[g].red[k][4 + w])); S += bits_f(s.sub[g].red[k][6 + w]); }
+        }
+        r.cmaxv[w] = M; r.sumv[w] = S;
+        unsigned long long key = ~0ull;
+        if (r.rowmax[w] == M && rowok) {
+            unsigned mm = 0u;
+#pragma unroll
+            for (int x = 0; x < 32; ++x) {
+                const float val = w == 0 ? r.v[x].x : r.v[x].y;
+                mm |= (val == M) ? (1u << x) : 0u;
+            }
+            mm &= hx >= 32 ? 0xffffffffu : ((1u << hx) - 1u);
+            const unsigned seg_hi = xs >= 32 ? 0u : (mm >> xs);
+            int j;
+            if (seg_hi) j = 2 * (xs + __ffs((int)seg_hi) - 1) + q2 - hx;
+            else j = 2 * (__ffs((int)mm) - 1) + q2 + hx;
+            key = (unsigned long long)(si * 2 * hx + j);
+            if (M == 0.f || r.dead[w]) key = 0ull;   // all-zero plane: every element is the maximum -> flat index 0
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other < key ? other : key;
+        }
+        if ((t & 31) == 0) s.sub[sub].redk[t >> 5][w] = key;
+    }
+}
+
+__device__ __forceinline__ void r128_p7_pad(R128Smem& s, RRegs<R6>& r, int sub, int t, const RParams& p) {
+    const int q1 = sub >> 1, q2 = sub & 1;
+    const int hy = p.ny, hx = p.nx;
+    const bool rowok = column_of<64>(t) < hy;
+    const int si = rowok ? shifted_index(2 * column_of<64>(t) + q1, 2 * hy) : -8;
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        unsigned long long key = ~0ull;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) key = s.sub[g].redk[k][w] < key ? s.sub[g].redk[k][w] : key;
+        }
+        const int idx = (int)key;
+        r.pi[w] = idx / (2 * hx); r.pj[w] = idx - r.pi[w] * (2 * hx);
+        const int d = si - r.pi[w];
+        if (d >= -1 && d <= 1) {
+            // lag l = 2 x + q2 goes to column l + hx (l < hx) or l - hx: two base pointers, static offsets
+            float* row = &s.nb[w][d + 1][0];
+            float* base_lo = row + hx + q2;
+            float* base_hi = row - hx + q2;
+#pragma unroll
+            for (int x = 0; x < 32; ++x) {
+                if (x < hx) {
+                    const float val = r.dead[w] ? 0.f : (w == 0 ? r.v[x].x : r.v[x].y);
+                    (2 * x + q2 < hx ? base_lo : base_hi)[2 * x] = val;
+                }
+            }
+        }
+    }
+}
+
 // P8: Gaussian fit + outputs by threads 0 / 1 of the group (pyorc/velocimetry/ffpiv.py:465-466 + ffpiv.u_v_displacement)
-__device__ __forceinline__ void r128_p8(R128Smem& s, RRegs<R6>& r, int tid, const RParams& p, const RUnit& un, int pair) {
+__device__ __forceinline__ void r128_p8(R128Smem& s, RRegs<R6>& r, int tid, const RParams& p, const RUnit& un, int pair, int ny = 128, int nx = 128) {
     if (tid >= 2) return;
     const int w = tid;
     if (w == 1 && !un.valid1) return;
     const float* nb = &s.nb[w][0][0];
     const int pi = w == 0 ? r.pi[0] : r.pi[1], pj = w == 0 ? r.pj[0] : r.pj[1];
     const float cmax = w == 0 ? r.cmaxv[0] : r.cmaxv[1];
-    const float mean = (w == 0 ? r.sumv[0] : r.sumv[1]) / (float)R128_NPX;
+    const float mean = (w == 0 ? r.sumv[0] : r.sumv[1]) / (float)(ny * nx);
     float uu, vv;
-    if (pi == 0 || pi == 127 || pj == 0 || pj == 127) {
+    if (pi == 0 || pi == ny - 1 || pj == 0 || pj == nx - 1) {
         if (p.border_nan) { uu = nanf(""); vv = nanf(""); }
-        else { uu = (float)(pj - 64); vv = (float)(pi - 64); }
+        else { uu = (float)(pj - nx / 2); vv = (float)(pi - ny / 2); }
     } else {
         const float eps = p.gauss_eps;
         const float lc = logf(cmax + eps);
         const float ll = logf(nb[0 * 128 + pj] + eps), lr = logf(nb[2 * 128 + pj] + eps);
         const float ld = logf(nb[1 * 128 + pj - 1] + eps), lu = logf(nb[1 * 128 + pj + 1] + eps);
-        vv = ((float)pi + (ll - lr) / (2.f * ll - 4.f * lc + 2.f * lr)) - 64.f;
-        uu = ((float)pj + (ld - lu) / (2.f * ld - 4.f * lc + 2.f * lu)) - 64.f;
+        vv = ((float)pi + (ll - lr) / (2.f * ll - 4.f * lc + 2.f * lr)) - (float)(ny / 2);
+        uu = ((float)pj + (ld - lu) / (2.f * ld - 4.f * lc + 2.f * lu)) - (float)(nx / 2);
     }
     float oc = cmax, os = cmax / mean;
     const int widx = w == 0 ? un.w[0] : un.w[1];
@@ -431,6 +606,24 @@ __device__ __forceinline__ void r128_dump_planes(RRegs<R6>& r, int sub, int t, c
         float* dst = p.planes + (((long long)pair * nw + un.w[w]) * 128 + si) * 128;
 #pragma unroll
         for (int x = 0; x < 64; ++x) dst[(2 * x + q2 + 64) & 127] = r.dead[w] ? 0.f : (w == 0 ? r.v[x].x : r.v[x].y);
+    }
+}
+// padded mode: the planes are [2 ny][2 nx] (the window's own size), reference order
+__device__ __forceinline__ void r128_dump_planes_pad(RRegs<R6>& r, int sub, int t, const RParams& p, const RUnit& un, int pair) {
+    if (!p.planes) return;
+    const int q1 = sub >> 1, q2 = sub & 1;
+    const int hy = p.ny, hx = p.nx;
+    if (column_of<64>(t) >= hy) return;
+    const int si = shifted_index(2 * column_of<64>(t) + q1, 2 * hy);
+    const long long nw = (long long)p.n_rows * p.n_cols;
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        if (w == 1 && !un.valid1) continue;
+        float* dst = p.planes + (((long long)pair * nw + un.w[w]) * (2 * hy) + si) * (2 * hx);
+#pragma unroll
+        for (int x = 0; x < 32; ++x) {
+            if (x < hx) dst[shifted_index(2 * x + q2, 2 * hx)] = r.dead[w] ? 0.f : (w == 0 ? r.v[x].x : r.v[x].y);
+        }
     }
 }
 #endif  // __CUDACC__

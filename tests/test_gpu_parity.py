@@ -254,6 +254,36 @@ def test_rows_kernel_padded_mode(engine, ws, ov, shape, run_len, clip):
     engine.set_option("run_len", 0.0)
 
 
+ROWS_PAD128_CASES = [
+    ((50, 50), (25, 25), (4, 160, 224), 0),     # a 4K user's 50 px window: 128-point plane, 25 x 25 samples per polyphase component
+    ((50, 50), (25, 25), (5, 130, 210), 2),     # short runs, frame width that is not a multiple of 16
+    ((40, 40), (20, 20), (3, 130, 180), 0),
+    ((62, 62), (31, 31), (3, 160, 190), 0),     # odd component size, odd stride
+    ((34, 34), (17, 17), (3, 120, 150), 0),     # the smallest size that needs the 128-point plane
+    ((64, 48), (32, 24), (3, 170, 200), 0),     # rectangular, one side at the plane's limit
+    ((36, 20), (18, 10), (3, 110, 100), 0),     # one side small
+    ((20, 44), (10, 22), (3, 90, 160), 0),
+]
+
+
+@pytest.mark.parametrize("ws,ov,shape,run_len", ROWS_PAD128_CASES)
+@pytest.mark.parametrize("clip", [0, 1])
+def test_rows128_kernel_padded_mode(engine, ws, ov, shape, run_len, clip):
+    """Padded mode of the 128-plane polyphase kernel (even windows of 34 .. 64 px): zero-padded window, 2 x 2 tiling as a spectrum
+    factor on the polyphase components, the reference's plane read from the wrap-free lags - against the oracle, planes included,
+    and against the shared-memory kernel."""
+    imgs = synth.particle_frames(*shape, dtype=np.uint8)
+    imgs[:, : ws[0], : ws[1] + 3] = 0                  # a dead window and a partly empty one
+    compare(engine, imgs, ws, ov, clip, variant=4, run_len=run_len)
+    a = engine.pairs(imgs, ws, ov)
+    engine.set_option("kernel_variant", 1.0)
+    b = engine.pairs(imgs, ws, ov)
+    engine.set_option("kernel_variant", 0.0)
+    engine.set_option("run_len", 0.0)
+    for x, y in zip(a[2:], b[2:]):
+        assert np.array_equal(np.isnan(x), np.isnan(y)) and np.nanmax(np.abs(x - y)) <= 1e-5 * max(1.0, np.nanmax(np.abs(y)))
+
+
 def test_rows_kernels_on_device_tensors_need_an_aligned_pitch(engine):
     """Host frames are copied into a 16-byte pitched buffer by the engine (any width qualifies); a caller-owned device
     tensor is used in place, so an odd pitch is refused by the TMA kernels and taken by the shared-memory kernel."""

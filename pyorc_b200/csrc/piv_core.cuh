@@ -433,7 +433,8 @@ B2_HD void phase_center(Smem<C>& s, int tid, const Params& p) {
 // PHASE 3c (padded mode only, ny*nx < NPX): windows whose size is not a power of two run through the power-of-two
 // FFT as an EXACT circular correlation of period (ny, nx): frame k's window is zero-padded, frame k+1's window is
 // tiled periodically over [0, 2ny) x [0, 2nx) (zero beyond), so  sum_x a'(x) b'(x + s)  for 0 <= s < n never wraps in
-// the (>= 2n)-point plane.  In-region values are rewritten unchanged, so concurrent readers are safe.
+// the (>= 2n)-point plane.  Elements inside the window keep their value and are only READ here (by the threads that fill
+// their tiled copies), elements outside are only written: no barrier needed inside the phase.
 template <class C>
 B2_HD void phase_embed(Smem<C>& s, int tid, const Params& p) {
     if (C::PADDED) {
@@ -441,9 +442,9 @@ B2_HD void phase_embed(Smem<C>& s, int tid, const Params& p) {
         for (int w = 0; w < C::NWIN; ++w) {
             for (int e = tid; e < C::NPX; e += C::NT) {
                 const int y = e / C::WX, x = e % C::WX;
-                const float a = (y < p.ny && x < p.nx) ? s.plane[w][y * C::P + x].x : 0.f;
+                if (y < p.ny && x < p.nx) continue;
                 const float b = (y < 2 * p.ny && x < 2 * p.nx) ? s.plane[w][(y % p.ny) * C::P + (x % p.nx)].y : 0.f;
-                s.plane[w][y * C::P + x] = make_float2(a, b);
+                s.plane[w][y * C::P + x] = make_float2(0.f, b);
             }
         }
     }

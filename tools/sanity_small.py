@@ -16,7 +16,23 @@ if __name__ == "__main__":
     if which in ("all", "rows32"):
         out = e.pairs(frames(4, 120, 176), (32, 32), (24, 24)); print("rows32 unaligned", float(torch.nanmean(out[0])))
     if which in ("all", "rows128"):
-        out = e.pairs(frames(4, 300, 420), (128, 128), (64, 64)); print("rows128", float(torch.nanmean(out[0])))
+        out = e.pairs(frames(4, 300, 432), (128, 128), (64, 64)); print("rows128", float(torch.nanmean(out[0])))
+    if which in ("all", "rows128", "rows128ens"):
+        fr = frames(4, 300, 432)            # device tensors are used in place: the TMA kernels need a 16-byte pitch
+        e.ens_begin((300, 432), (128, 128), (64, 64), np.uint8); e.ens_add(fr, (128, 128), (64, 64), corr_min=0.2, s2n_min=3.0)
+        u, v, cnt = e.ens_finish(0.2); print("rows128 ensemble", float(np.nanmean(u)))
+    if which in ("all", "rows128", "pad128"):
+        out = e.pairs(frames(4, 160, 224), (50, 50), (25, 25)); print("pad128 50x50", float(torch.nanmean(out[0])))
+        out = e.pairs(frames(3, 130, 176), (36, 20), (18, 10)); print("pad128 36x20", float(torch.nanmean(out[0])))
+    if which in ("all", "push"):
+        res = e.pairs(frames(4, 200, 304), (64, 64), (32, 32))
+        buf = torch.zeros((4, 5, res[0].shape[1], res[0].shape[2]), device=dev)
+        from pyorc_b200.parallel import _result_block
+        e.peer_push(_result_block(res), [buf.data_ptr()], 5, 2); torch.cuda.synchronize(); print("peer push", float(torch.nanmean(buf[0, 2:])))
+    if which in ("all", "generic"):
+        e.set_option("kernel_variant", 1.0)
+        out = e.pairs(frames(3, 130, 170), (50, 50), (25, 25)); print("shared-memory kernel, padded 50x50", float(torch.nanmean(out[0])))
+        e.set_option("kernel_variant", 0.0)
     if which in ("all", "pad"):
         out = e.pairs(frames(3, 120, 176), (26, 26), (12, 12)); print("pad26", float(torch.nanmean(out[0])))
     if which in ("all", "twopass"):

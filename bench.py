@@ -244,7 +244,8 @@ def other_configs(eng, dev, fp32_peak):
              ("configs[2] single pass: 1080p, 32x32 / 75 %", 1080, 1920, (32, 32), (24, 24), 21, None),
              ("configs[2] two-pass, discrete window offset (64x64 / 75 % -> 32x32 / 75 %; round 1's row)", 1080, 1920, (32, 32), (24, 24), 21, (c75, "offset")),
              ("configs[2] two-pass, discrete window offset (64x64 / 50 % -> 32x32 / 75 %)", 1080, 1920, (32, 32), (24, 24), 21, (c50, "offset")),
-             ("configs[2] two-pass DEFORM: bilinear window deformation (64x64 / 50 % -> 32x32 / 75 %)", 1080, 1920, (32, 32), (24, 24), 21, (c50, "deform"))]
+             ("configs[2] two-pass DEFORM: bilinear window deformation (64x64 / 50 % -> 32x32 / 75 %)", 1080, 1920, (32, 32), (24, 24), 21, (c50, "deform")),
+             ("f-2: 1080p, 50x50 / 50 % (windows of 34 .. 64 px: padded mode of the 128-plane polyphase kernel)", 1080, 1920, (50, 50), (25, 25), 21, None)]
     for name, h, w, ws, ov, n, two_pass in cases:
         try:
             fr = synth.particle_frames_torch(n, h, w, dev, dtype="uint8")

@@ -119,9 +119,9 @@ static bool rows_shift_eligible(const b2piv_engine* e, const void* d_frames, lon
 
 // 128 x 128 uint8 windows on the polyphase row-per-thread kernel (piv_rows128.cuh)
 static bool rows128_eligible(const b2piv_engine* e, const void* d_frames, long long frame_stride, int pitch) {
-    if (e->wy != 128 || e->wx != 128 || e->dtype != B2PIV_U8) return false;
+    if (e->wy != 128 || e->wx != 128) return false;   // uint8 and float32 frames both qualify
     if ((pitch & 15) || (frame_stride & 15) || (((uintptr_t)d_frames) & 15)) return false;
-    if ((e->wx - e->ox) & 15) return false;   // swizzled boxes start on 16-byte boundaries
+    if ((e->wx - e->ox) & (e->dtype == B2PIV_F32 ? 3 : 15)) return false;   // swizzled boxes start on 16-byte boundaries
     return tma_available();
 }
 
@@ -158,7 +158,7 @@ int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
     if (e->variant == 2 && !can_rows && e->wy != 128)
         return fail(e, B2PIV_ERR_UNSUPPORTED, "rows kernel needs a square 32/64 window, 16-byte aligned base/pitch and an x stride that is a multiple of 4");
     if (e->variant == 2 && e->wy == 128 && !rows128_eligible(e, p.frames, p.frame_stride, p.pitch))
-        return fail(e, B2PIV_ERR_UNSUPPORTED, "128x128 rows kernel needs uint8 frames, 16-byte aligned base/pitch and an x stride that is a multiple of 16");
+        return fail(e, B2PIV_ERR_UNSUPPORTED, "128x128 rows kernel needs 16-byte aligned base/pitch and an x stride of a multiple of 16 bytes");
     if (rows128_eligible(e, p.frames, p.frame_stride, p.pitch) && (e->variant == 0 || e->variant == 2)) {
         e->last_variant = 2;
         return launch_rows128(e, p, st);

@@ -6,7 +6,7 @@
 // phase (piv_rows128.cuh).  One CTA = one group of 256 threads = one pair of adjacent windows followed through a run of
 // frames; 213 KB of shared memory (4 x transpose blocks + exchange of the new spectra), the parked spectra in Tensor Memory,
 // one CTA per SM.
-template <bool ENS, bool PAD>
+template <bool ENS, bool PAD, bool F32>
 __global__ void __launch_bounds__(256, 1) piv_rows128_kernel(const __grid_constant__ CUtensorMap tmap, RParams p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -41,7 +41,17 @@ __global__ void __launch_bounds__(256, 1) piv_rows128_kernel(const __grid_consta
         const int xoff0 = un.x0[0] - xa0, xoff1 = un.x0[1] - xa1;
         auto issue_frame = [&](int frame) {
             fence_proxy_async();
-            if constexpr (PAD) {
+            if constexpr (F32) {
+                static_assert(!(F32 && PAD), "float32 frames: native 128 x 128 windows only");
+                mbar_expect_tx(&s.mbar, 2 * 128 * 128 * 4);
+#pragma unroll
+                for (int w = 0; w < 2; ++w)
+#pragma unroll
+                    for (int hb = 0; hb < 2; ++hb)
+#pragma unroll
+                        for (int h = 0; h < 4; ++h)
+                            tma_load_3d(r128_ftile(s, 2 * w + hb) + h * 8192, &tmap, &s.mbar, un.x0[w] + 32 * h, un.y0[w] + 64 * hb, frame);
+            } else if constexpr (PAD) {
                 mbar_expect_tx(&s.mbar, 2 * R128_PWIN);
                 tma_load_3d(s.sub[0].tile(), &tmap, &s.mbar, xa0, un.y0[0], frame);
                 tma_load_3d(s.sub[0].tile() + R128_PWIN, &tmap, &s.mbar, xa1, un.y0[1], frame);
@@ -60,9 +70,19 @@ __global__ void __launch_bounds__(256, 1) piv_rows128_kernel(const __grid_consta
             const int f = un.f0 + k;
             while (!mbar_try_wait(&s.mbar, parity)) {}
             parity ^= 1u;
-            if constexpr (PAD) r128_p1_pad(s, r, sub, t, p, xoff0, xoff1); else r128_p1(s, r, sub, t);
-            __syncthreads();  // A: integer moments visible, tile (aliased on the transpose blocks) fully consumed
-            if constexpr (PAD) r128_p2_pad(s, r, t, p); else r128_p2(s, r, p.clip_norm);
+            if constexpr (F32) {
+                r128_f1(s, r, sub, t, 0);
+                r128_f1(s, r, sub, t, 1);
+                __syncthreads();  // A: row sums visible, tile (in the spectrum blocks) fully consumed
+                r128_f2(s, r, sub, t, 0);
+                r128_f2(s, r, sub, t, 1);
+                __syncthreads();  // A2: centred second moments visible
+                r128_f3(s, r, p.clip_norm);
+            } else {
+                if constexpr (PAD) r128_p1_pad(s, r, sub, t, p, xoff0, xoff1); else r128_p1(s, r, sub, t);
+                __syncthreads();  // A: integer moments visible, tile (aliased on the transpose blocks) fully consumed
+                if constexpr (PAD) r128_p2_pad(s, r, t, p); else r128_p2(s, r, p.clip_norm);
+            }
             // forward: FFT(rows) T FFT(cols) per component; cross spectra across components; inverse: FFT(cols) T FFT(rows)
             // (one copy of the unrolled FFT: the loop body is far beyond the instruction caches, every KB counts)
 #pragma unroll 1
@@ -75,9 +95,13 @@ __global__ void __launch_bounds__(256, 1) piv_rows128_kernel(const __grid_consta
             const bool dead1 = (r.half_alpha_prev[1] == 0.f) || (r.half_alpha_new[1] == 0.f);
             rows_p5_post<R6, PAD>(ss, r, t, dead0, dead1, &p);
             __syncthreads();  // E1: block max / sum of all components; the transpose blocks are free again
-            if (tid == 0 && k + 1 < nfr) issue_frame(f + 1);
+            if (!(ENS && F32) && tid == 0 && k + 1 < nfr) issue_frame(f + 1);
             if constexpr (ENS) {
                 r128_ens(s, r, sub, t, tid, p, un, f - 1, have_prev);   // thresholds + accumulate; no peak search per pair
+                if constexpr (F32) {   // the float32 tile lands where the planes were staged
+                    __syncthreads();
+                    if (tid == 0 && k + 1 < nfr) issue_frame(f + 1);
+                }
             } else {
                 if constexpr (PAD) r128_p6_pad(s, r, sub, t, p); else r128_p6(s, r, sub, t);
                 __syncthreads();  // E2: first-argmax keys
@@ -102,9 +126,11 @@ int launch_rows128(b2piv_engine* e, const Params& gp, cudaStream_t st, const Ens
     CUtensorMap tmap;
     const cuuint64_t dims[3] = {(cuuint64_t)e->W, (cuuint64_t)e->H, (cuuint64_t)n_frames};
     const cuuint64_t strides[2] = {(cuuint64_t)gp.pitch, (cuuint64_t)gp.frame_stride};
-    const cuuint32_t box[3] = {(cuuint32_t)(pad ? R128_PWB : 128), (cuuint32_t)(pad ? 64 : 32), 1};
+    const bool f32 = e->dtype == B2PIV_F32;
+    if (f32 && pad) return fail(e, B2PIV_ERR_UNSUPPORTED, "padded 128-plane rows kernel needs uint8 frames");
+    const cuuint32_t box[3] = {(cuuint32_t)(f32 ? 32 : (pad ? R128_PWB : 128)), (cuuint32_t)((pad || f32) ? 64 : 32), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult cr = get_encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(gp.frames), dims, strides, box, estr,
+    const CUresult cr = get_encode_tiled()(&tmap, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(gp.frames), dims, strides, box, estr,
                                            CU_TENSOR_MAP_INTERLEAVE_NONE, pad ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(e, B2PIV_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)cr));
@@ -125,7 +151,9 @@ int launch_rows128(b2piv_engine* e, const Params& gp, cudaStream_t st, const Ens
         for (int x = 0; x < 64; ++x) p.pad_cm[x] = x < p.nx ? 1.f : 0.f;
     }
     if (ep) { p.corr_min = ep->corr_min; p.s2n_min = ep->s2n_min; p.ens_sum = ep->plane_sum; p.ens_count = ep->count; }
-    auto kern = pad ? piv_rows128_kernel<false, true> : (ep ? piv_rows128_kernel<true, false> : piv_rows128_kernel<false, false>);
+    auto kern = pad ? piv_rows128_kernel<false, true, false>
+                    : (f32 ? (ep ? piv_rows128_kernel<true, false, true> : piv_rows128_kernel<false, false, true>)
+                           : (ep ? piv_rows128_kernel<true, false, false> : piv_rows128_kernel<false, false, false>));
     const size_t smem = sizeof(R128Smem) + 1024;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;

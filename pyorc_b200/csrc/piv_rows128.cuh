@@ -215,6 +215,69 @@ __device__ __forceinline__ void r128_p2_pad(R128Smem& s, RRegs<R6>& r, int t, co
     r.tx = p.pad_tx[column_of<64>(t)];
 }
 
+// ---- float32 frames (pyorc's time_diff / smooth / edge_detect output) ------------------------------------------------------
+// Tile: window w, rows [64 hb, 64 hb + 64) in the spectrum block of sub-group 2 w + hb (idle between the cross phases):
+// [4 column blocks][64 rows][128 B] from 32-float x 64-row TMA boxes, SWIZZLE_128B.  F1(w): the thread's row of window w, the
+// floats of its column parity -> component w of r.v, row sum; F2(w): mean over all four components, centre, centred second
+// moment; F3: 0.5 / std of both windows, optional clip.  Two-pass moments like numpy's float path (rows_f1 .. f3 of piv_rows.cuh).
+__device__ __forceinline__ unsigned char* r128_ftile(R128Smem& s, int g) {
+    unsigned char* b = reinterpret_cast<unsigned char*>(&s.sub[g].park[0][0]);
+    return b + ((1024u - (smem_u32(b) & 1023u)) & 1023u);
+}
+static_assert(sizeof(RSmem<R6>::park) >= 4 * 64 * 128 + 1024, "half a float32 window (plus alignment slack) must fit in a spectrum block");
+__device__ __forceinline__ void r128_f1(R128Smem& s, RRegs<R6>& r, int sub, int t, int w) {
+    const int p1 = sub >> 1, p2 = sub & 1;
+    const int row = 2 * column_of<64>(t) + p1;
+    const int rr = row & 63;
+    const unsigned char* tile = r128_ftile(s, 2 * w + (row >> 6));
+    float sum = 0.f;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 q = *reinterpret_cast<const float4*>(tile + h * 8192 + rr * 128 + ((j ^ (rr & 7)) << 4));
+            const float a = p2 ? q.y : q.x, b = p2 ? q.w : q.z;
+            const int x = 16 * h + 2 * j;
+            if (w == 0) { r.v[x].x = a; r.v[x + 1].x = b; } else { r.v[x].y = a; r.v[x + 1].y = b; }
+            sum += a + b;
+        }
+    }
+    red_put_f32(&s.sub[sub].red[t >> 5][2 * w], sum, t);
+}
+__device__ __forceinline__ void r128_f2(R128Smem& s, RRegs<R6>& r, int sub, int t, int w) {
+    float S = 0.f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) S += bits_f32(s.sub[g].red[k][2 * w]);
+    }
+    const float mean = S * (1.0f / (float)R128_NPX);
+    float q = 0.f;
+#pragma unroll
+    for (int x = 0; x < 64; ++x) {
+        if (w == 0) { r.v[x].x -= mean; q = fmaf(r.v[x].x, r.v[x].x, q); }
+        else        { r.v[x].y -= mean; q = fmaf(r.v[x].y, r.v[x].y, q); }
+    }
+    red_put_f32(&s.sub[sub].red[t >> 5][2 * w + 1], q, t);
+}
+__device__ __forceinline__ void r128_f3(R128Smem& s, RRegs<R6>& r, int clip_norm) {
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        float Q = 0.f;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) Q += bits_f32(s.sub[g].red[k][2 * w + 1]);
+        }
+        r.half_alpha_new[w] = Q > 0.f ? 0.5f * 128.0f * (1.0f / sqrtf(Q)) : 0.f;   // 0.5 / sqrt(Q / N), N = 128 * 128
+    }
+    r.dc_fix[0] = r.dc_fix[1] = 0.f;
+    if (clip_norm) {
+#pragma unroll
+        for (int x = 0; x < 64; ++x) r.v[x] = make_float2(fmaxf(r.v[x].x, 0.f), fmaxf(r.v[x].y, 0.f));
+    }
+}
+
 // packed fp32 forms (piv_core.cuh): two instructions each
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return ctw<1>(a, b.x, b.y); }
 __device__ __forceinline__ float2 cmulc(float2 p, float2 a) { return ctw<0>(a, p.x, p.y); }   // conj(p) * a

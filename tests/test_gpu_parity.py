@@ -157,6 +157,22 @@ def test_rows128_and_generic_kernels_agree_and_signal_threshold(engine):
     engine.set_option("kernel_variant", 0.0)
 
 
+@pytest.mark.parametrize("shape,run_len", [((4, 300, 420), 0), ((6, 280, 432), 2)])
+def test_rows128_kernel_float32_frames(engine, shape, run_len):
+    """float32 frames (pyorc's time_diff / smooth / edge_detect output) at 128x128 on the polyphase kernel: 32-float swizzled TMA
+    boxes into the spectrum blocks, two-pass float moments - against the oracle (planes included) and the shared-memory kernel."""
+    imgs = synth.particle_frames(*shape, dtype=np.float32)
+    imgs[:, :128, :140] = 0
+    imgs[1:] -= 0.25 * imgs[:-1]
+    compare(engine, imgs, (128, 128), (64, 64), 0, variant=2, run_len=run_len)
+    a = engine.pairs(imgs, (128, 128), (64, 64))
+    engine.set_option("kernel_variant", 1.0)
+    b = engine.pairs(imgs, (128, 128), (64, 64))
+    engine.set_option("kernel_variant", 0.0)
+    engine.set_option("run_len", 0.0)
+    assert np.nanmax(np.abs(a[2] - b[2])) <= 1e-5
+
+
 def test_rows128_kernel_needs_16_byte_strides(engine):
     imgs = synth.particle_frames(3, 300, 420, dtype=np.uint8)
     engine.set_option("kernel_variant", 2.0)
@@ -164,7 +180,8 @@ def test_rows128_kernel_needs_16_byte_strides(engine):
         engine.pairs(imgs, (128, 128), (60, 60))          # stride 68
     engine.set_option("kernel_variant", 0.0)
     compare(engine, imgs, (128, 128), (60, 60), 0)      # auto: shared-memory kernel
-    compare(engine, imgs.astype(np.float32), (128, 128), (64, 64), 0)   # float32 frames: shared-memory kernel
+    compare(engine, imgs.astype(np.float32), (128, 128), (64, 64), 0)   # float32 frames: polyphase kernel as well (round 2)
+    compare(engine, imgs.astype(np.float32), (128, 128), (62, 62), 0)   # float32, stride 66 floats (not 16-byte aligned): shared-memory kernel
 
 
 def test_rows_kernel_refuses_stride_not_multiple_of_4(engine):
@@ -436,7 +453,8 @@ def test_ensemble_mode_matches_oracle(engine, ws, ov, shape, corr_min, s2n_min, 
 
 @pytest.mark.parametrize("ws,ov,shape,dtype", [((64, 64), (32, 32), (7, 270, 400), np.float32), ((32, 32), (24, 24), (6, 100, 144), np.uint8),
                                                ((32, 32), (16, 16), (9, 150, 208), np.float32), ((64, 64), (40, 40), (5, 160, 208), np.uint8),
-                                               ((128, 128), (64, 64), (5, 300, 432), np.uint8)])     # polyphase kernel, ensemble epilogue
+                                               ((128, 128), (64, 64), (5, 300, 432), np.uint8),      # polyphase kernel, ensemble epilogue
+                                               ((128, 128), (64, 64), (4, 300, 432), np.float32)])   # ... with float32 frames
 def test_ensemble_rows_kernel_device_frames(engine, ws, ov, shape, dtype):
     """Device-resident chunk in ONE launch (a unit walks all frames and adds its planes to the HBM accumulators): float32
     frames and window starts that are not 16-byte aligned, against the oracle's plane sums (no thresholds, so no pair can

@@ -7,3 +7,5 @@ if __name__ == "__main__":
         for variant in (0, 1):
             run(1080, 1920, ws, ov, 21, variant=variant)
     run(2160, 3840, (50, 50), (25, 25), 21, variant=0)
+    for variant in (0, 1):   # float32 frames at 128x128: polyphase kernel against the shared-memory kernel
+        run(2160, 3840, (128, 128), (64, 64), 11, dtype="float32", variant=variant)

@@ -21,6 +21,11 @@ if __name__ == "__main__":
         fr = frames(4, 300, 432)            # device tensors are used in place: the TMA kernels need a 16-byte pitch
         e.ens_begin((300, 432), (128, 128), (64, 64), np.uint8); e.ens_add(fr, (128, 128), (64, 64), corr_min=0.2, s2n_min=3.0)
         u, v, cnt = e.ens_finish(0.2); print("rows128 ensemble", float(np.nanmean(u)))
+    if which in ("all", "rows128", "rows128f32"):
+        out = e.pairs(frames(3, 300, 432, "float32"), (128, 128), (64, 64)); print("rows128 f32", float(torch.nanmean(out[0])))
+        fr = frames(3, 300, 432, "float32")
+        e.ens_begin((300, 432), (128, 128), (64, 64), np.float32); e.ens_add(fr, (128, 128), (64, 64), corr_min=0.2, s2n_min=3.0)
+        u, v, cnt = e.ens_finish(0.2); print("rows128 f32 ensemble", float(np.nanmean(u)))
     if which in ("all", "rows128", "pad128"):
         out = e.pairs(frames(4, 160, 224), (50, 50), (25, 25)); print("pad128 50x50", float(torch.nanmean(out[0])))
         out = e.pairs(frames(3, 130, 176), (36, 20), (18, 10)); print("pad128 36x20", float(torch.nanmean(out[0])))

@@ -207,6 +207,10 @@ int dispatch_ens(b2piv_engine* e, const Params& p, const EnsParams& ep, cudaStre
         e->last_variant = 2;
         return launch_rows128(e, p, st, &ep);     // polyphase kernel, ensemble epilogue
     }
+    if (pad128_eligible(e, p.frames, p.frame_stride, p.pitch) && (e->variant == 0 || e->variant == 4)) {
+        e->last_variant = 4;
+        return launch_rows128(e, p, st, &ep, true);
+    }
     const bool tiny = !fft_config(e->wy, e->wx) && e->wy * e->wx <= 144;
     if (e->variant == 4 && !pad_eligible(e, p.frames, p.frame_stride, p.pitch))
         return fail(e, B2PIV_ERR_UNSUPPORTED, "padded rows kernel needs uint8 frames, a window of at most 32 px and 16-byte aligned base/pitch");

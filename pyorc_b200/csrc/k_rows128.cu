@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(256, 1) piv_rows128_kernel(const __grid_consta
             __syncthreads();  // E1: block max / sum of all components; the transpose blocks are free again
             if (!(ENS && F32) && tid == 0 && k + 1 < nfr) issue_frame(f + 1);
             if constexpr (ENS) {
-                r128_ens(s, r, sub, t, tid, p, un, f - 1, have_prev);   // thresholds + accumulate; no peak search per pair
+                if constexpr (PAD) r128_ens_pad(s, r, sub, t, tid, p, un, f - 1, have_prev);
+                else r128_ens(s, r, sub, t, tid, p, un, f - 1, have_prev);   // thresholds + accumulate; no peak search per pair
                 if constexpr (F32) {   // the float32 tile lands where the planes were staged
                     __syncthreads();
                     if (tid == 0 && k + 1 < nfr) issue_frame(f + 1);
@@ -121,7 +122,6 @@ __global__ void __launch_bounds__(256, 1) piv_rows128_kernel(const __grid_consta
 }
 
 int launch_rows128(b2piv_engine* e, const Params& gp, cudaStream_t st, const EnsParams* ep, bool pad) {
-    if (pad && ep) return fail(e, B2PIV_ERR_UNSUPPORTED, "padded 128-plane rows kernel has no ensemble epilogue");
     const int n_frames = gp.n_pairs + 1;
     CUtensorMap tmap;
     const cuuint64_t dims[3] = {(cuuint64_t)e->W, (cuuint64_t)e->H, (cuuint64_t)n_frames};
@@ -151,7 +151,7 @@ int launch_rows128(b2piv_engine* e, const Params& gp, cudaStream_t st, const Ens
         for (int x = 0; x < 64; ++x) p.pad_cm[x] = x < p.nx ? 1.f : 0.f;
     }
     if (ep) { p.corr_min = ep->corr_min; p.s2n_min = ep->s2n_min; p.ens_sum = ep->plane_sum; p.ens_count = ep->count; }
-    auto kern = pad ? piv_rows128_kernel<false, true, false>
+    auto kern = pad ? (ep ? piv_rows128_kernel<true, true, false> : piv_rows128_kernel<false, true, false>)
                     : (f32 ? (ep ? piv_rows128_kernel<true, false, true> : piv_rows128_kernel<false, false, true>)
                            : (ep ? piv_rows128_kernel<true, false, false> : piv_rows128_kernel<false, false, false>));
     const size_t smem = sizeof(R128Smem) + 1024;

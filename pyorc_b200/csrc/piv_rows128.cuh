@@ -657,6 +657,60 @@ __device__ __forceinline__ void r128_ens(R128Smem& s, RRegs<R6>& r, int sub, int
     }
 }
 
+// Ensemble mode of the padded kernel: the same staging, for a plane of the window's own size [2 ny][2 nx] (reference order, the
+// layout of the accumulators).  A staged plane (pitch 2 nx + 1 floats, at most 64 x 65) fits in one spectrum block.
+__device__ __forceinline__ void r128_ens_pad(R128Smem& s, RRegs<R6>& r, int sub, int t, int tid, const RParams& p, const RUnit& un, int pair, bool store) {
+    const int q1 = sub >> 1, q2 = sub & 1;
+    const int hy = p.ny, hx = p.nx, ny = 2 * p.ny, nx = 2 * p.nx, pitch = nx + 1;
+    const bool rowok = column_of<64>(t) < hy;
+    const int si = rowok ? shifted_index(2 * column_of<64>(t) + q1, ny) : 0;
+    const long long nw = (long long)p.n_rows * p.n_cols;
+    bool okw[2];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        float M = 0.f, S = 0.f;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) { M = fmaxf(M, bits_f(s.sub[g].red[k][4 + w])); S += bits_f(s.sub[g].red[k][6 + w]); }
+        }
+        const float ratio = M / (S / (float)(ny * nx));
+        const int widx = w == 0 ? un.w[0] : un.w[1];
+        bool ok = (M >= p.corr_min) && (ratio >= p.s2n_min) && !r.dead[w];   // dead: 0 / 0 = NaN fails the test in the reference
+        if (p.keep && !p.keep[widx]) ok = false;                             // NaN plane in the reference -> masked out
+        const bool wr = store && !(w == 1 && !un.valid1);
+        okw[w] = ok && wr;                                                   // the same for every thread of the CTA
+        if (okw[w] && rowok) {
+            // lag l = 2 x + q2 goes to column l + hx (l < hx) or l - hx: two base pointers, static offsets
+            float* row = reinterpret_cast<float*>(&s.sub[w].park[0][0]) + si * pitch;
+            float* base_lo = row + hx + q2;
+            float* base_hi = row - hx + q2;
+#pragma unroll
+            for (int x = 0; x < 32; ++x) {
+                if (x < hx) (2 * x + q2 < hx ? base_lo : base_hi)[2 * x] = w == 0 ? r.v[x].x : r.v[x].y;
+            }
+        }
+        if (wr && tid == 0) {
+            const long long o = (long long)pair * nw + widx;
+            p.cmax[o] = ok ? M : 0.f;
+            p.s2n[o] = ok ? ratio : 0.f;
+            if (ok && M > 1e-6f) p.ens_count[widx] += 1.f;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        if (!okw[w]) continue;
+        float* dst = p.ens_sum + (long long)(w == 0 ? un.w[0] : un.w[1]) * (ny * nx);
+        const float* src = reinterpret_cast<const float*>(&s.sub[w].park[0][0]);
+        for (int e = tid; e < ny * nx; e += 256) {
+            const int row = e / nx, col = e - row * nx;
+            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + e), "f"(src[row * pitch + col]) : "memory");
+        }
+    }
+}
+static_assert(sizeof(RSmem<R6>::park) >= 64 * 65 * sizeof(float), "a staged padded plane must fit in a spectrum block");
+
 // optional triage dump of the full planes (fftshifted, clipped): every thread writes its 64 elements of one reference row
 __device__ __forceinline__ void r128_dump_planes(RRegs<R6>& r, int sub, int t, const RParams& p, const RUnit& un, int pair) {
     if (!p.planes) return;

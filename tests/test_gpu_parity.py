@@ -396,6 +396,8 @@ ENS_CASES = [
     ((10, 10), (5, 5), (5, 60, 80), 0.0, 0.0),
     ((26, 26), (12, 12), (5, 90, 120), 0.2, 1.5),
     ((128, 128), (64, 64), (4, 300, 420), 0.2, 3.0),
+    ((50, 50), (25, 25), (5, 160, 224), 0.2, 2.0),       # padded mode of the 128-plane kernel
+    ((36, 44), (18, 22), (5, 120, 150), 0.2, 2.0),
 ]
 
 
@@ -454,7 +456,8 @@ def test_ensemble_mode_matches_oracle(engine, ws, ov, shape, corr_min, s2n_min, 
 @pytest.mark.parametrize("ws,ov,shape,dtype", [((64, 64), (32, 32), (7, 270, 400), np.float32), ((32, 32), (24, 24), (6, 100, 144), np.uint8),
                                                ((32, 32), (16, 16), (9, 150, 208), np.float32), ((64, 64), (40, 40), (5, 160, 208), np.uint8),
                                                ((128, 128), (64, 64), (5, 300, 432), np.uint8),      # polyphase kernel, ensemble epilogue
-                                               ((128, 128), (64, 64), (4, 300, 432), np.float32)])   # ... with float32 frames
+                                               ((128, 128), (64, 64), (4, 300, 432), np.float32),    # ... with float32 frames
+                                               ((50, 50), (25, 25), (5, 160, 224), np.uint8)])       # ... and in padded mode
 def test_ensemble_rows_kernel_device_frames(engine, ws, ov, shape, dtype):
     """Device-resident chunk in ONE launch (a unit walks all frames and adds its planes to the HBM accumulators): float32
     frames and window starts that are not 16-byte aligned, against the oracle's plane sums (no thresholds, so no pair can

@@ -29,6 +29,9 @@ if __name__ == "__main__":
     if which in ("all", "rows128", "pad128"):
         out = e.pairs(frames(4, 160, 224), (50, 50), (25, 25)); print("pad128 50x50", float(torch.nanmean(out[0])))
         out = e.pairs(frames(3, 130, 176), (36, 20), (18, 10)); print("pad128 36x20", float(torch.nanmean(out[0])))
+        fr = frames(4, 160, 224)
+        e.ens_begin((160, 224), (50, 50), (25, 25), np.uint8); e.ens_add(fr, (50, 50), (25, 25), corr_min=0.2, s2n_min=3.0)
+        u, v, cnt = e.ens_finish(0.2); print("pad128 ensemble", float(np.nanmean(u)))
     if which in ("all", "push"):
         res = e.pairs(frames(4, 200, 304), (64, 64), (32, 32))
         buf = torch.zeros((4, 5, res[0].shape[1], res[0].shape[2]), device=dev)

@@ -39,7 +39,9 @@ const char* b2piv_last_error(const b2piv_engine* e);
 /* Numerical switches for the details that live in ffpiv rather than pyorc (see oracle/ffpiv_oracle.py):
  *   "clip_normalized" (0/1, default 0 = ffpiv), "border_nan" (0/1), "gauss_eps" (float), "copy_chunks" (H2D
  *   pipeline depth of the *_host calls; 0 = auto, about 10 MB of frames per chunk), "stage_threads" (threads that copy
- *   ordinary pageable host frames into the engine's page-locked staging ring; 0 = auto, min(8, hardware threads)), "kernel_variant" (0 auto, 1 shared-memory FFT,
+ *   ordinary pageable host frames into the engine's page-locked staging ring; 0 = auto, min(8, hardware threads)),
+ *   "stage_mode" (1: slices of "stage_slice_kb" KB per thread, one H2D per group of slices, "stage_groups" groups in flight in a
+ *   ring small enough for the host's caches, plain stores or - "stage_nt" - non-temporal ones; 0: round 1's three large buffers), "kernel_variant" (0 auto, 1 shared-memory FFT,
  *   2 row-per-thread TMA - 32x32 / 64x64 and the polyphase 128x128 kernel, 3 direct, 4 row-per-thread TMA in
  *   padded mode for uint8 windows up to 32 px), "run_len". */
 int b2piv_set_option(b2piv_engine* e, const char* name, double value);
@@ -48,7 +50,8 @@ int b2piv_set_option(b2piv_engine* e, const char* name, double value);
  * ffpiv.window.get_rect_coordinates (pyorc/api/frames.py:85-90): n_rows=(H-wy)/(wy-oy)+1, n_cols likewise.
  * Supported windows: any size 4..128 per axis - every even size pyorc can produce (frames.py:159-171).  32x32 / 64x64 /
  * 128x128 take the row-per-thread FFT kernels, other sizes up to 32 px - pyorc's 10, 20, 26 ... - their exact zero-padded
- * mode, 33..64 px and the rectangular powers of two a shared-memory FFT kernel, sizes with a side of 65..127 px a
+ * mode (uint8; 34..64 px: the padded mode of the 128-plane polyphase kernel), float32 frames of such sizes and the rectangular powers of two
+ * a shared-memory FFT kernel, sizes with a side of 65..127 px a
  * direct-correlation kernel (exact, O(N^2) per window: a compatibility path).  search_area_size == window_size as pyorc
  * always passes (frames.py:168). */
 int b2piv_plan(b2piv_engine* e, int height, int width, int win_y, int win_x, int ovl_y, int ovl_x, int dtype,

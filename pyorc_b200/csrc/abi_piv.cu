@@ -301,6 +301,9 @@ void b2piv_destroy(b2piv_engine* e) {
     for (auto ev : e->ev_chunk) cudaEventDestroy(ev);
     for (int i = 0; i < 3; ++i) { if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]); if (e->ev_stage[i]) cudaEventDestroy(e->ev_stage[i]); }
     delete e->pool;
+    delete e->stager;
+    if (e->h_ring) cudaFreeHost(e->h_ring);
+    for (auto ev : e->ev_ring) cudaEventDestroy(ev);
     if (e->ev_k0) cudaEventDestroy(e->ev_k0);
     if (e->ev_k1) cudaEventDestroy(e->ev_k1);
     if (e->ev_ens) cudaEventDestroy(e->ev_ens);
@@ -316,7 +319,15 @@ int b2piv_set_option(b2piv_engine* e, const char* name, double value) {
     else if (n == "border_nan") e->border_nan = value != 0.0;
     else if (n == "gauss_eps") e->gauss_eps = (float)value;
     else if (n == "copy_chunks") e->copy_chunks = value < 0 ? 0 : (int)value;
-    else if (n == "stage_threads") { e->stage_threads = value < 0 ? 0 : (int)value; delete e->pool; e->pool = nullptr; }
+    else if (n == "stage_threads") {
+        e->stage_threads = value < 0 ? 0 : (int)value;
+        delete e->pool; e->pool = nullptr;
+        delete e->stager; e->stager = nullptr;
+    }
+    else if (n == "stage_mode") e->stage_mode = value != 0.0;                           // 1: Stager (stager.h), 0: round 1's pool
+    else if (n == "stage_slice_kb") e->stage_slice_kb = value < 4 ? 4 : (int)value;     // per worker and copy
+    else if (n == "stage_groups") e->stage_groups = value < 2 ? 2 : (int)value;         // H2D copies in flight (ring depth)
+    else if (n == "stage_nt") e->stage_nt = value != 0.0;                               // non-temporal stores into the ring
     else if (n == "kernel_variant") e->variant = (int)value;
     else if (n == "run_len") e->run_len = value < 0 ? 0 : (int)value;
     else if (n == "tmem") e->tmem = value != 0.0;
@@ -444,12 +455,89 @@ static int pipeline_host(b2piv_engine* e, const void* frames, int n_frames, bool
         e->ev_chunk.push_back(ev);
     }
     const int per = (n_pairs + chunks - 1) / chunks;
-    // pageable source (plain numpy memory): stage through page-locked buffers with the copy threads, ~8 MB per stage chunk,
-    // three buffers so that the host copy of the next stage chunk overlaps the H2D of the previous ones
+    // pageable source (plain numpy memory): staged through a page-locked ring by the engine's copy threads
     cudaPointerAttributes attr;
     bool pageable = true;
     if (cudaPointerGetAttributes(&attr, frames) == cudaSuccess) pageable = (attr.type == cudaMemoryTypeUnregistered);
     else cudaGetLastError();
+    if (pageable && e->stage_mode == 1) {
+        // Stager (stager.h): slices of ~stage_slice_kb per worker, one H2D per group of slices, `stage_groups` groups in flight;
+        // this thread issues the copies, hands landed slots back and launches a chunk's kernel once its frames are under way
+        CK(cudaStreamSynchronize(e->s_copy));   // no earlier call may still be reading the ring
+        if (!e->stager) {
+            int nt = e->stage_threads;
+            if (nt <= 0) { nt = (int)std::thread::hardware_concurrency(); nt = nt > 8 ? 8 : (nt < 1 ? 1 : nt); }
+            try {
+                e->stager = new Stager(nt);
+            } catch (...) {   // no threads to be had: let the driver stage the pageable copy (nothing may throw across the ABI)
+                e->stager = nullptr;
+                pageable = false;
+            }
+        }
+    }
+    if (pageable && e->stage_mode == 1) {
+        Stager::Job job;
+        job.src = (const unsigned char*)frames;
+        job.row_bytes = row_bytes;
+        job.rows = (size_t)n_frames * e->H;
+        job.slice_rows = ((size_t)e->stage_slice_kb << 10) / row_bytes;
+        if (job.slice_rows < 1) job.slice_rows = 1;
+        job.parts = e->stager->size();
+        // a short call is not cut finer than it has to be: every worker gets one slice of the first group
+        if (job.slice_rows * (size_t)job.parts > job.rows) job.slice_rows = (job.rows + job.parts - 1) / job.parts;
+        job.ring_groups = e->stage_groups < 2 ? 2 : (e->stage_groups > 64 ? 64 : e->stage_groups);
+        job.nt = e->stage_nt != 0;
+        const size_t need_bytes = Stager::ring_bytes(job);
+        if (e->cap_ring < need_bytes) {
+            if (e->h_ring) { CK(cudaFreeHost(e->h_ring)); e->h_ring = nullptr; e->cap_ring = 0; }
+            CK(cudaHostAlloc((void**)&e->h_ring, need_bytes, cudaHostAllocDefault));
+            e->cap_ring = need_bytes;
+        }
+        job.ring = e->h_ring;
+        while ((int)e->ev_ring.size() < job.ring_groups) {
+            cudaEvent_t ev;
+            CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            e->ev_ring.push_back(ev);
+        }
+        CK(cudaEventRecord(e->ev_k0, e->s_comp));
+        int c = 0;   // next chunk to launch
+        const int G = job.ring_groups;
+        const int rc2 = e->stager->run(
+            job,
+            [&](size_t g, unsigned char* slot, size_t row0, size_t nrows) -> int {
+                if (dpitch == row_bytes)
+                    CK(cudaMemcpyAsync(e->d_frames + row0 * dpitch, slot, nrows * row_bytes, cudaMemcpyHostToDevice, e->s_copy));
+                else   // frames are contiguous on both sides, so any run of rows is one 2-D copy
+                    CK(cudaMemcpy2DAsync(e->d_frames + row0 * dpitch, dpitch, slot, row_bytes, row_bytes, nrows, cudaMemcpyHostToDevice, e->s_copy));
+                CK(cudaEventRecord(e->ev_ring[g % (size_t)G], e->s_copy));
+                return B2PIV_OK;
+            },
+            [&](size_t g) -> bool {
+                const cudaError_t q = cudaEventQuery(e->ev_ring[g % (size_t)G]);
+                if (q == cudaSuccess) return true;
+                cudaGetLastError();                       // cudaErrorNotReady is recorded as the last error: clear it
+                return q != cudaErrorNotReady;            // a real error: stop holding the slot back, the next CUDA call reports it
+            },
+            [&](size_t rows_issued) -> int {
+                while (c < chunks) {
+                    const int p0 = c * per;
+                    const int p1 = (p0 + per < n_pairs) ? p0 + per : n_pairs;
+                    if (p0 >= p1) { c = chunks; break; }
+                    if ((size_t)(p1 + 1) * e->H > rows_issued) break;      // frames [0, p1] must be under way
+                    CK(cudaEventRecord(e->ev_chunk[c], e->s_copy));
+                    CK(cudaStreamWaitEvent(e->s_comp, e->ev_chunk[c], 0));
+                    const int r3 = work(p0, p1 - p0);
+                    if (r3) return r3;
+                    ++c;
+                }
+                return B2PIV_OK;
+            });
+        if (rc2) return rc2;
+        CK(cudaEventRecord(e->ev_k1, e->s_comp));
+        return B2PIV_OK;
+    }
+    // "stage_mode" = 0, round 1's pool: ~8 MB per stage chunk, three buffers, so that the host copy of the next stage chunk
+    // overlaps the H2D of the previous ones
     size_t stage_frames = 0;
     unsigned stage_no = 0;
     if (pageable) {

@@ -27,32 +27,7 @@ struct NvtxRange {
     ~NvtxRange() { nvtxRangePop(); }
 };
 
-// Copy into a page-locked staging buffer with NON-TEMPORAL stores: the destination is only ever read by the DMA engine, so it
-// should neither be fetched into the caches first (read-for-ownership: a third of the memory traffic of a plain memcpy) nor evict
-// the source.  glibc switches to such stores only for single copies of many MB; the staging slices are ~1 MB per thread.
-#if defined(__x86_64__)
-#include <immintrin.h>
-__attribute__((target("avx2"))) static inline void stream_copy_avx2(unsigned char* d, const unsigned char* s, size_t n) {
-    size_t head = (32 - ((uintptr_t)d & 31)) & 31;
-    if (head > n) head = n;
-    if (head) { memcpy(d, s, head); d += head; s += head; n -= head; }
-    size_t i = 0;
-    for (; i + 128 <= n; i += 128) {
-        const __m256i a = _mm256_loadu_si256((const __m256i*)(s + i)), b = _mm256_loadu_si256((const __m256i*)(s + i + 32));
-        const __m256i c = _mm256_loadu_si256((const __m256i*)(s + i + 64)), e = _mm256_loadu_si256((const __m256i*)(s + i + 96));
-        _mm256_stream_si256((__m256i*)(d + i), a); _mm256_stream_si256((__m256i*)(d + i + 32), b);
-        _mm256_stream_si256((__m256i*)(d + i + 64), c); _mm256_stream_si256((__m256i*)(d + i + 96), e);
-    }
-    if (i < n) memcpy(d + i, s + i, n - i);
-    _mm_sfence();
-}
-static inline void stage_copy(unsigned char* d, const unsigned char* s, size_t n) {
-    static const bool avx2 = __builtin_cpu_supports("avx2");
-    if (avx2 && n >= 4096) stream_copy_avx2(d, s, n); else memcpy(d, s, n);
-}
-#else
-static inline void stage_copy(unsigned char* d, const unsigned char* s, size_t n) { memcpy(d, s, n); }
-#endif
+#include "stager.h"   // copy threads + cache-resident page-locked ring for pageable host frames; stage_copy_nt
 
 // Ensemble accumulate (pyorc/velocimetry/ffpiv.py:200-243 thresholds, :361-363 accumulation)
 struct EnsParams {
@@ -61,7 +36,8 @@ struct EnsParams {
     float* count;       // [n_windows]
 };
 
-// Worker threads that copy ordinary (pageable) host frames into the engine's page-locked staging buffers.  pyorc hands
+// Round 1's staging pool (option "stage_mode" = 0; the default is the Stager of stager.h): worker threads that copy ordinary
+// (pageable) host frames into three large page-locked buffers, one condition-variable round trip per buffer.  pyorc hands
 // `frame_chunk.values` - plain numpy memory - to the engine (pyorc/velocimetry/ffpiv.py:223,451); a cudaMemcpyAsync from
 // pageable memory is staged by the driver on ONE thread (measured: 11 GB/s, 18.7 ms per 100-pair 1080p step against 4.1 ms
 // from pinned memory), so the staging is done here, sliced over a few threads, one chunk ahead of the H2D copy.
@@ -103,7 +79,7 @@ private:
             const size_t dp = dpitch_, spp = spitch_, rb = row_bytes_;
             lk.unlock();
             if (dp == rb && spp == rb) {
-                if (r1 > r0) stage_copy(d + r0 * rb, sp + r0 * rb, (r1 - r0) * rb);
+                if (r1 > r0) stage_copy_nt(d + r0 * rb, sp + r0 * rb, (r1 - r0) * rb);
             } else {
                 for (size_t r = r0; r < r1; ++r) memcpy(d + r * dp, sp + r * spp, rb);
             }
@@ -151,6 +127,12 @@ struct b2piv_engine {
     cudaEvent_t ev_stage[3] = {nullptr, nullptr, nullptr};
     CopyPool* pool = nullptr;
     int stage_threads = 0;   // 0: auto (min(8, hardware threads))
+    // stage_mode 1 (default): Stager - slices of `stage_slice_kb` per worker, one H2D per group of `threads` slices, a ring of
+    // `stage_groups` groups that is small enough to stay in the host's caches; plain stores unless `stage_nt`
+    int stage_mode = 1, stage_slice_kb = 256, stage_groups = 4, stage_nt = 0;
+    Stager* stager = nullptr;
+    unsigned char* h_ring = nullptr; size_t cap_ring = 0;
+    std::vector<cudaEvent_t> ev_ring;
     float* d_out = nullptr; size_t cap_out = 0;       // 4 result fields
     float* d_planes = nullptr; size_t cap_planes = 0;
     float* d_planes_nat = nullptr; size_t cap_planes_nat = 0;   // padded rows kernel: W x W planes in natural lag order

@@ -615,12 +615,21 @@ def test_pageable_and_pinned_host_frames_give_identical_results(engine):
     engine.set_option("clip_normalized", 0.0)
     engine.set_option("kernel_variant", 0.0)
     ref = engine.pairs(pinned, (32, 32), (16, 16))
-    for threads, chunks in ((1, 0), (3, 5), (8, 1), (0, 0)):
+    # (threads, H2D chunks, stage_mode, slice KB, ring groups, non-temporal stores): the Stager of csrc/stager.h with slices from
+    # 4 KB (hundreds of groups for these 0.9 MB) to larger than the call, and round 1's three-buffer pool (stage_mode 0)
+    for threads, chunks, mode, kb, groups, nt in ((1, 0, 1, 256, 4, 0), (3, 5, 1, 4, 2, 0), (8, 1, 1, 16, 3, 1), (0, 0, 1, 64, 8, 1),
+                                                  (5, 22, 1, 8, 4, 0), (2, 3, 1, 4096, 2, 0), (1, 0, 0, 256, 4, 0), (3, 5, 0, 256, 4, 0),
+                                                  (0, 0, 1, 256, 4, 0)):
         engine.set_option("stage_threads", float(threads))
         engine.set_option("copy_chunks", float(chunks))
-        got = engine.pairs(imgs, (32, 32), (16, 16))
-        for a, b in zip(ref, got):
-            assert np.array_equal(a, b, equal_nan=True)
+        engine.set_option("stage_mode", float(mode))
+        engine.set_option("stage_slice_kb", float(kb))
+        engine.set_option("stage_groups", float(groups))
+        engine.set_option("stage_nt", float(nt))
+        for _ in range(2):                      # the second call reuses the ring while nothing of the first is in flight
+            got = engine.pairs(imgs, (32, 32), (16, 16))
+            for a, b in zip(ref, got):
+                assert np.array_equal(a, b, equal_nan=True)
     engine.set_option("copy_chunks", 0.0)
     f32 = imgs.astype(np.float32)
     a = engine.pairs(f32, (32, 32), (16, 16))

@@ -354,3 +354,29 @@ def test_result_block_of_engine_fields():
     assert got.data_ptr() != block.data_ptr() and torch.equal(got, block)
     partial = (block[0, 1:], block[1, 1:], block[2, 1:], block[3, 1:])     # views, but not of the whole block: must be copied
     assert torch.equal(parallel._result_block(partial), block[:, 1:])
+
+
+@pytest.mark.parametrize(
+    "rows,row_bytes,dpitch,slice_rows,parts,ring,threads,nt,delay_us",
+    [(4370, 203, 208, 1291, 8, 4, 8, 0, 20),      # the GPU test's 190 x 203 frames: one group, re-pitched rows
+     (3000, 1920, 1920, 136, 8, 4, 8, 0, 5),      # 1080p rows, 256 KB slices, plain stores
+     (3000, 1920, 1920, 136, 8, 2, 3, 1, 5),      # fewer workers than slices per group, non-temporal stores, the smallest ring
+     (777, 333, 336, 7, 5, 3, 2, 0, 0),           # ragged: last group and last slice short
+     (50, 100, 112, 100, 4, 2, 4, 1, 0),          # less than one slice
+     (3, 10, 16, 1, 1, 2, 1, 0, 0)],
+)
+def test_stager_delivers_every_row_once(rows, row_bytes, dpitch, slice_rows, parts, ring, threads, nt, delay_us):
+    """csrc/stager.h (the copy threads and ring behind `b2piv_pairs_host` on pageable numpy memory) with a thread playing the
+    copy engine: every row arrives once at its pitched place, groups are issued in order, a ring slot is never rewritten under
+    a copy in flight, the chunk hook sees growing row counts - and an error from the issue callback ends the call."""
+    import ctypes
+
+    import __graft_entry__ as g
+
+    lib = ctypes.CDLL(g.build_stager_emulator())
+    f = lib.stager_selftest
+    f.restype = ctypes.c_longlong
+    f.argtypes = [ctypes.c_longlong] * 4 + [ctypes.c_int] * 4 + [ctypes.c_longlong, ctypes.c_int, ctypes.c_int]
+    assert f(rows, row_bytes, dpitch, slice_rows, parts, ring, threads, nt, -1, delay_us, 3) == 0
+    n_groups = -(-rows // (slice_rows * parts))
+    assert f(rows, row_bytes, dpitch, slice_rows, parts, ring, threads, nt, n_groups // 2, delay_us, 2) == 0

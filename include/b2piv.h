@@ -247,6 +247,9 @@ void b2piv_host_free(void* p);
  * number of kernels this engine has launched since creation. */
 int b2piv_last_kernel_ms(const b2piv_engine* e, float* ms);
 long long b2piv_launch_count(const b2piv_engine* e);
+/* Kernel family that served the last PIV call: 1 shared-memory FFT kernel, 2 row-per-thread TMA kernels (32 / 64 / 128 px native),
+ * 3 direct correlation, 4 row-per-thread kernels in padded mode; 0 before the first call. */
+int b2piv_last_variant(const b2piv_engine* e);
 /* Measured fp32 FMA throughput of the engine's device in TFLOP/s (independent FFMA chains, `iters` per thread and chain,
  * best of 4 runs): the denominator of the fp32 fraction bench.py reports for the fused kernels, which are bound by fp32
  * issue rather than HBM. */

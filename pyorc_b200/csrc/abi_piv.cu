@@ -125,11 +125,11 @@ static bool rows128_eligible(const b2piv_engine* e, const void* d_frames, long l
     return tma_available();
 }
 
-// Padded mode of the row-per-thread kernel: any uint8 window (square or not, any stride) whose larger side is at most
-// 32 px, i.e. at most half of a 64 x 64 (or 32 x 32) plane.  Native 32 x 32 / 64 x 64 windows never come here.
+// Padded mode of the row-per-thread kernel: any window (uint8 or float32 frames, square or not, any stride) whose larger side is
+// at most 32 px, i.e. at most half of a 64 x 64 (or 32 x 32) plane.  Native 32 x 32 / 64 x 64 windows never come here.
 static bool pad_eligible(const b2piv_engine* e, const void* d_frames, long long frame_stride, int pitch) {
     const int m = e->wy > e->wx ? e->wy : e->wx;
-    if (e->dtype != B2PIV_U8 || 2 * m > 64 || e->wy < 2 || e->wx < 2) return false;
+    if (2 * m > 64 || e->wy < 2 || e->wx < 2) return false;
     if ((pitch & 15) || (frame_stride & 15) || (((uintptr_t)d_frames) & 15)) return false;
     return tma_available();
 }
@@ -152,6 +152,7 @@ int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
             return launch_rows_shift(e, p, st);
         }
         if (e->variant == 2) return fail(e, B2PIV_ERR_UNSUPPORTED, "displaced rows kernel needs square 32x32 uint8 windows, 16-byte aligned base/pitch and an x stride that is a multiple of 4");
+        e->last_variant = 1;
         return launch_generic(e, p, st);
     }
     const bool can_rows = rows_eligible(e, p.frames, p.frame_stride, p.pitch);
@@ -183,15 +184,16 @@ int dispatch_pairs(b2piv_engine* e, const Params& p, cudaStream_t st) {
     }
     const bool tiny = !fft_config(e->wy, e->wx) && e->wy * e->wx <= 144;
     if (e->variant == 4 && !pad_eligible(e, p.frames, p.frame_stride, p.pitch))
-        return fail(e, B2PIV_ERR_UNSUPPORTED, "padded rows kernels need uint8 frames, an even window of at most 64 px and 16-byte aligned base/pitch");
+        return fail(e, B2PIV_ERR_UNSUPPORTED, "padded rows kernels need a window of at most 32 px (uint8 frames: an even one of at most 64 px) and 16-byte aligned base/pitch");
     if (pad_eligible(e, p.frames, p.frame_stride, p.pitch) && (e->variant == 4 || (e->variant == 0 && !fft_config(e->wy, e->wx)))) {
         e->last_variant = 4;
-        return launch_rows_pad(e, p, st, nullptr);
+        return e->dtype == B2PIV_F32 ? launch_rows_pad_f32(e, p, st, nullptr) : launch_rows_pad(e, p, st, nullptr);
     }
     if ((e->variant == 3 || tiny) && e->wy <= 64 && e->wx <= 64) {
         e->last_variant = 3;
         return launch_direct(e, p, st);
     }
+    e->last_variant = 1;
     return launch_generic(e, p, st);
 }
 int dispatch_ens(b2piv_engine* e, const Params& p, const EnsParams& ep, cudaStream_t st) {
@@ -213,10 +215,10 @@ int dispatch_ens(b2piv_engine* e, const Params& p, const EnsParams& ep, cudaStre
     }
     const bool tiny = !fft_config(e->wy, e->wx) && e->wy * e->wx <= 144;
     if (e->variant == 4 && !pad_eligible(e, p.frames, p.frame_stride, p.pitch))
-        return fail(e, B2PIV_ERR_UNSUPPORTED, "padded rows kernel needs uint8 frames, a window of at most 32 px and 16-byte aligned base/pitch");
+        return fail(e, B2PIV_ERR_UNSUPPORTED, "padded rows kernel needs a window of at most 32 px and 16-byte aligned base/pitch");
     if (pad_eligible(e, p.frames, p.frame_stride, p.pitch) && (e->variant == 4 || (e->variant == 0 && !fft_config(e->wy, e->wx)))) {
         e->last_variant = 4;
-        return launch_rows_pad(e, p, st, &ep);
+        return e->dtype == B2PIV_F32 ? launch_rows_pad_f32(e, p, st, &ep) : launch_rows_pad(e, p, st, &ep);
     }
     e->last_variant = 1;
     if (big_direct(e)) return launch_direct_big_ens(e, p, ep, st);
@@ -988,5 +990,6 @@ int b2piv_last_kernel_ms(const b2piv_engine* e, float* ms) {
     return B2PIV_OK;
 }
 long long b2piv_launch_count(const b2piv_engine* e) { return e ? e->launches : 0; }
+int b2piv_last_variant(const b2piv_engine* e) { return e ? e->last_variant : 0; }
 
 }  // extern "C"

@@ -128,8 +128,9 @@ struct b2piv_engine {
     CopyPool* pool = nullptr;
     int stage_threads = 0;   // 0: auto (min(8, hardware threads))
     // stage_mode 1 (default): Stager - slices of `stage_slice_kb` per worker, one H2D per group of `threads` slices, a ring of
-    // `stage_groups` groups that is small enough to stay in the host's caches; plain stores unless `stage_nt`
-    int stage_mode = 1, stage_slice_kb = 256, stage_groups = 4, stage_nt = 0;
+    // `stage_groups` groups, non-temporal stores unless `stage_nt` = 0.  Defaults from tools/stage_sweep.py on B200 boxes
+    // (profiles/r02/stage_sweep_n*.log): large groups win (8 MB per H2D), a small cache-resident ring with plain stores does not
+    int stage_mode = 1, stage_slice_kb = 1024, stage_groups = 3, stage_nt = 1;
     Stager* stager = nullptr;
     unsigned char* h_ring = nullptr; size_t cap_ring = 0;
     std::vector<cudaEvent_t> ev_ring;
@@ -267,6 +268,7 @@ int launch_rows_u8(b2piv_engine* e, const Params& p, cudaStream_t st);          
 int launch_rows_f32(b2piv_engine* e, const Params& p, cudaStream_t st);                              // k_rows_f32.cu
 int launch_rows_ens(b2piv_engine* e, const Params& p, const EnsParams& ep, cudaStream_t st);         // k_rows_ens.cu (uint8 and float32)
 int launch_rows_pad(b2piv_engine* e, const Params& p, cudaStream_t st, const EnsParams* ep);         // k_rows_pad.cu
+int launch_rows_pad_f32(b2piv_engine* e, const Params& p, cudaStream_t st, const EnsParams* ep);     // k_rows_pad_f32.cu
 int launch_rows_shift(b2piv_engine* e, const Params& p, cudaStream_t st);                            // k_rows_shift.cu
 int launch_rows128(b2piv_engine* e, const Params& p, cudaStream_t st, const EnsParams* ep = nullptr, bool pad = false);                               // k_rows128.cu
 // dispatch (abi_piv.cu)

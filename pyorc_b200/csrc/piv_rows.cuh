@@ -76,6 +76,10 @@ struct RCfg {
     static constexpr int FBOX = W * 128;                 // bytes per box
     static constexpr int FWIN = (W / 32) * FBOX;         // bytes per window
     static constexpr int F_PHASES = (W == 64) ? 2 : 1;   // TMA round trips per frame
+    // float32 frames in padded mode (window sides <= W/2, any x stride): one un-swizzled box of PFW floats x ny rows per window
+    // from the 16-byte boundary below the window start (up to 3 floats of lead-in), window 1 at the fixed offset PFWIN
+    static constexpr int PFW = W / 2 + 4;                // floats per box row: 144 B (W = 64) / 80 B (W = 32), multiples of 16 B
+    static constexpr int PFWIN = (W / 2) * PFW * 4;      // bytes; 4608 / 1280: multiples of 128 (TMA destination alignment)
     // Transposes move 32x32 blocks: block b (pitch BP float2) is READ by warp b.  A 64x64 transpose first moves the
     // two off-diagonal blocks (one CTA barrier), then the diagonal ones (warp-synchronous), reusing the same two
     // blocks - half a plane - so a group needs ~52 KB of shared memory and FOUR groups (8 warps, two per
@@ -113,6 +117,9 @@ static_assert(sizeof(float2) * RCfg<64>::NWARP * RCfg<64>::XBLK >= RCfg<64>::TIL
 static_assert(sizeof(float2) * RCfg<64>::NWARP * RCfg<64>::XBLK >= RCfg<64>::FWIN, "float tile must fit in the transpose blocks");
 static_assert(sizeof(float2) * RCfg<32>::NWARP * RCfg<32>::XBLK >= 2 * RCfg<32>::FWIN, "float tiles must fit in the transpose blocks");
 static_assert(sizeof(float2) * RCfg<32>::NWARP * RCfg<32>::XBLK >= RCfg<32>::TILE_U, "tile must fit in the transpose blocks");
+static_assert(sizeof(float2) * RCfg<64>::NWARP * RCfg<64>::XBLK >= 2 * RCfg<64>::PFWIN && sizeof(float2) * RCfg<32>::NWARP * RCfg<32>::XBLK >= 2 * RCfg<32>::PFWIN,
+              "padded float tiles must fit in the transpose blocks");
+static_assert(RCfg<64>::PFWIN % 128 == 0 && RCfg<32>::PFWIN % 128 == 0 && (RCfg<64>::PFW * 4) % 16 == 0 && (RCfg<32>::PFW * 4) % 16 == 0, "TMA box alignment");
 
 // displaced-window variant (second pass of the two-pass scheme): dedicated tile buffers so that both tiles of the next frame
 // can be prefetched while the transposes use X
@@ -470,6 +477,69 @@ B2_HD void rows_f3(RSmem<R>& s, RRegs<R>& r, int tid, int clip_norm) {
 #pragma unroll
         for (int x = 0; x < W; ++x) r.v[x] = make_float2(fmaxf(r.v[x].x, 0.f), fmaxf(r.v[x].y, 0.f));
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// float32 frames in padded mode (round 2): what pyorc's own example recipe produces - `normalize -> edge_detect -> minmax ->
+// get_piv(window_size=25)` hands float32 frames and a 26 x 26 window to the engine (examples/ngwerere/ngwerere.yml,
+// pyorc/api/frames.py:430,456-466).  Same embedding as the uint8 padded mode: the thread that owns row < ny reads its nx floats
+// at the window's float offset `xoff` (0 .. 3) inside the box, everything else of the W x W plane is exactly 0; two-pass moments
+// over the ny * nx window pixels like rows_f1 / f2 / f3.  Downstream (spectrum factor of the 2 x 2 tiling, reductions restricted
+// to the window's lags) is the uint8 padded path unchanged.
+// ------------------------------------------------------------------------------------------------------------
+template <class R>
+B2_HD void rows_f1_pad(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p, int w, int xoff) {
+    constexpr int W = R::W;
+    const int row = column_of<W>(tid);
+    const bool rowok = row < p.ny;
+    const float* src = reinterpret_cast<const float*>(s.tile() + w * R::PFWIN) + (rowok ? row : 0) * R::PFW + xoff;
+    float sum = 0.f;
+#pragma unroll
+    for (int x = 0; x < W / 2; ++x) {
+        const float val = (rowok && x < p.nx) ? src[x] : 0.f;
+        if (w == 0) r.v[x].x = val; else r.v[x].y = val;
+        sum += val;
+    }
+#pragma unroll
+    for (int x = W / 2; x < W; ++x) {
+        if (w == 0) r.v[x].x = 0.f; else r.v[x].y = 0.f;
+    }
+    red_put_f32(&s.red[tid >> 5][2 * w], sum, tid);
+}
+template <class R>
+B2_HD void rows_f2_pad(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p, int w) {
+    constexpr int W = R::W;
+    float S = 0.f;
+#pragma unroll
+    for (int k = 0; k < R::NWARP; ++k) S += bits_f32(s.red[k][2 * w]);
+    const float mean = S / (float)(p.ny * p.nx);
+    const bool rowok = column_of<W>(tid) < p.ny;
+    float q = 0.f;
+#pragma unroll
+    for (int x = 0; x < W / 2; ++x) {
+        const float m = (rowok && x < p.nx) ? mean : 0.f;   // pixels outside the window stay exactly 0
+        if (w == 0) { r.v[x].x -= m; q = fmaf(r.v[x].x, r.v[x].x, q); }
+        else        { r.v[x].y -= m; q = fmaf(r.v[x].y, r.v[x].y, q); }
+    }
+    red_put_f32(&s.red[tid >> 5][2 * w + 1], q, tid);
+}
+template <class R>
+B2_HD void rows_f3_pad(RSmem<R>& s, RRegs<R>& r, int tid, const RParams& p) {
+    constexpr int W = R::W;
+    const float npx = (float)(p.ny * p.nx);
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        float Q = 0.f;
+#pragma unroll
+        for (int k = 0; k < R::NWARP; ++k) Q += bits_f32(s.red[k][2 * w + 1]);
+        r.half_alpha_new[w] = Q > 0.f ? 0.5f * sqrtf(npx) * (1.0f / sqrtf(Q)) : 0.f;   // 0.5 / sqrt(Q / (ny nx))
+    }
+    if (p.clip_norm) {
+#pragma unroll
+        for (int x = 0; x < W / 2; ++x) r.v[x] = make_float2(fmaxf(r.v[x].x, 0.f), fmaxf(r.v[x].y, 0.f));
+    }
+    r.dc_fix[0] = r.dc_fix[1] = 0.f;
+    r.tx = p.pad_tx[column_of<W>(tid)];
 }
 
 // ------------------------------------------------------------------------------------------------------------

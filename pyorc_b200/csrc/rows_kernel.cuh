@@ -76,7 +76,9 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
         const int nfr = has_unit ? un.f1 - un.f0 + 1 : 0;
         constexpr int TILE_BYTES = ALIGNED ? R::TILE : R::TILE_U;
         constexpr int WIN_BYTES = TILE_BYTES / 2;
-        const int xa0 = ALIGNED ? un.x0[0] : (un.x0[0] & ~15), xa1 = ALIGNED ? un.x0[1] : (un.x0[1] & ~15);
+        // box start = the 16-byte boundary below the window (bytes of uint8 frames, floats of padded float32 frames)
+        constexpr int XMASK = (PAD && F32) ? ~3 : ~15;
+        const int xa0 = ALIGNED ? un.x0[0] : (un.x0[0] & XMASK), xa1 = ALIGNED ? un.x0[1] : (un.x0[1] & XMASK);
         const int xoff0 = un.x0[0] - xa0, xoff1 = un.x0[1] - xa1;
         // TMA of the tile(s) a frame starts with: both uint8 windows, or (float32) window 0 - plus window 1 when both
         // fit the buffer; `issue_f32` loads the W/32 swizzled 128-byte-wide boxes of one float32 window
@@ -87,7 +89,11 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
         };
         auto issue_frame_start = [&](int frame) {
             fence_proxy_async();
-            if constexpr (!F32) {
+            if constexpr (PAD && F32) {   // one un-swizzled (PFW floats x ny rows) box per window
+                mbar_expect_tx(&s.mbar, 2u * (uint32_t)p.ny * (uint32_t)(R::PFW * 4));
+                tma_load_3d(s.tile(), &tmap, &s.mbar, xa0, un.y0[0], frame);
+                tma_load_3d(s.tile() + R::PFWIN, &tmap, &s.mbar, xa1, un.y0[1], frame);
+            } else if constexpr (!F32) {
                 mbar_expect_tx(&s.mbar, TILE_BYTES);
                 tma_load_3d(s.tile(), &tmap, &s.mbar, xa0, un.y0[0], frame);
                 tma_load_3d(s.tile() + WIN_BYTES, &tmap, &s.mbar, xa1, un.y0[1], frame);
@@ -106,8 +112,16 @@ __global__ void __launch_bounds__(R::NT* G) piv_rows_kernel(const __grid_constan
                 while (!mbar_try_wait(&s.mbar, parity)) {}
                 parity ^= 1u;
             }
-            if constexpr (PAD) {
-                static_assert(!PAD || (!ALIGNED && !F32), "padded mode uses the 16-byte wider uint8 boxes");
+            if constexpr (PAD && F32) {
+                rows_f1_pad<R>(s, r, tid, p, 0, xoff0);
+                rows_f1_pad<R>(s, r, tid, p, 1, xoff1);
+                __syncthreads();  // A: tile (aliased on X) consumed, row sums visible
+                rows_f2_pad<R>(s, r, tid, p, 0);
+                rows_f2_pad<R>(s, r, tid, p, 1);
+                __syncthreads();  // A3: centred second moments visible
+                rows_f3_pad<R>(s, r, tid, p);
+            } else if constexpr (PAD) {
+                static_assert(!PAD || !ALIGNED, "padded mode uses boxes from the 16-byte boundary below the window");
                 rows_p1_pad<R>(s, r, tid, p, xoff0, xoff1);
                 __syncthreads();  // A
                 rows_p2_pre_pad<R>(s, r, tid, p);
@@ -292,9 +306,10 @@ static int launch_rows(b2piv_engine* e, const Params& gp, cudaStream_t st, const
     CUtensorMap tmap;
     const cuuint64_t dims[3] = {(cuuint64_t)e->W, (cuuint64_t)e->H, (cuuint64_t)n_frames};
     const cuuint64_t strides[2] = {(cuuint64_t)gp.pitch, (cuuint64_t)gp.frame_stride};
-    const cuuint32_t box[3] = {(cuuint32_t)(F32 ? 32 : (ALIGNED ? W : R::WB)), (cuuint32_t)W, 1};
+    constexpr bool FPAD = F32 && PAD;   // padded float32 mode: (PFW floats x ny rows) un-swizzled boxes
+    const cuuint32_t box[3] = {(cuuint32_t)(FPAD ? R::PFW : (F32 ? 32 : (ALIGNED ? W : R::WB))), (cuuint32_t)(FPAD ? e->wy : W), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    const CUtensorMapSwizzle swz = F32 ? CU_TENSOR_MAP_SWIZZLE_128B
+    const CUtensorMapSwizzle swz = FPAD ? CU_TENSOR_MAP_SWIZZLE_NONE : F32 ? CU_TENSOR_MAP_SWIZZLE_128B
                                        : (!ALIGNED ? CU_TENSOR_MAP_SWIZZLE_NONE : (W == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B));
     const CUresult cr = get_encode_tiled()(&tmap, F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
                                            const_cast<void*>(gp.frames), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,

@@ -70,6 +70,7 @@ ABI_SYMBOLS = (
     "b2piv_host_free",
     "b2piv_last_kernel_ms",
     "b2piv_launch_count",
+    "b2piv_last_variant",
     "b2piv_fp32_peak",
 )
 
@@ -141,6 +142,7 @@ def load_library(path: Optional[str] = None):
     lib.b2piv_last_kernel_ms.argtypes = [vp, fp]
     lib.b2piv_launch_count.argtypes = [vp]
     lib.b2piv_launch_count.restype = cll
+    lib.b2piv_last_variant.argtypes = [vp]
     lib.b2piv_fp32_peak.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_double)]
     for name in ABI_SYMBOLS:
         getattr(lib, name)
@@ -297,6 +299,11 @@ class Engine:
     @property
     def launch_count(self) -> int:
         return int(self._lib.b2piv_launch_count(self._h))
+
+    @property
+    def last_variant(self) -> int:
+        """Kernel family of the last PIV call: 1 shared-memory FFT, 2 row-per-thread (native sizes), 3 direct, 4 row-per-thread padded."""
+        return int(self._lib.b2piv_last_variant(self._h))
 
     @property
     def last_kernel_ms(self) -> float:

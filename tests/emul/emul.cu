@@ -105,7 +105,24 @@ static int run_rows(RParams p) {
         const RUnit un = decode_unit(p, unit);
         for (int f = un.f0; f <= un.f1; ++f) {
             const bool have_prev = f > un.f0;
-            if (!F32) {
+            if (F32 && PAD) {
+                // padded float32 mode: one (PFW floats x ny rows) box per window from the 16-byte boundary below its start
+                int xoff[2];
+                const int width = p.pitch / 4;
+                for (int w = 0; w < 2; ++w) {
+                    const int xa = un.x0[w] & ~3;
+                    xoff[w] = un.x0[w] - xa;
+                    float* dst = reinterpret_cast<float*>(s.tile() + w * R::PFWIN);
+                    for (int row = 0; row < p.ny; ++row)
+                        for (int b = 0; b < R::PFW; ++b)
+                            dst[row * R::PFW + b] = xa + b < width
+                                ? reinterpret_cast<const float*>(p.frames + (long long)f * p.frame_stride + (long long)(un.y0[w] + row) * p.pitch)[xa + b] : 0.f;
+                }
+                memset(s.red, 0, sizeof(s.red));
+                for (int t = 0; t < W; ++t) { rows_f1_pad<R>(s, regs[t], t, p, 0, xoff[0]); rows_f1_pad<R>(s, regs[t], t, p, 1, xoff[1]); }
+                for (int t = 0; t < W; ++t) { rows_f2_pad<R>(s, regs[t], t, p, 0); rows_f2_pad<R>(s, regs[t], t, p, 1); }
+                for (int t = 0; t < W; ++t) rows_f3_pad<R>(s, regs[t], t, p);
+            } else if (!F32) {
             // "TMA": fill the tile from frame f (swizzled exact boxes, or 16-byte wider boxes from the boundary below)
             const bool aligned = !PAD && (p.sx % 16) == 0;
             int xoff[2] = {0, 0};
@@ -219,12 +236,12 @@ static int emul_rows_any(const unsigned char* frames, int is_f32, int n_frames, 
     return -1;
 }
 // padded mode: any uint8 window up to 32 px per side, any stride (piv_rows.cuh "Padded mode")
-extern "C" int b2piv_emul_rows_pad(const unsigned char* frames, int n_frames, int H, int W, int wy, int wx, int oy, int ox, int run_len,
-                                   int clip_norm, int border_nan, float eps, const unsigned char* keep, float* u, float* v, float* cmax,
-                                   float* s2n, float* planes) {
+static int emul_rows_pad_any(const unsigned char* frames, int is_f32, int n_frames, int H, int W, int wy, int wx, int oy, int ox, int run_len,
+                             int clip_norm, int border_nan, float eps, const unsigned char* keep, float* u, float* v, float* cmax,
+                             float* s2n, float* planes) {
     RParams p;
     memset(&p, 0, sizeof(p));
-    p.frames = frames; p.pitch = W; p.frame_stride = (long long)H * W; p.height = H;
+    p.frames = frames; p.pitch = W * (is_f32 ? 4 : 1); p.frame_stride = (long long)H * p.pitch; p.height = H;
     p.n_rows = (H - wy) / (wy - oy) + 1; p.n_cols = (W - wx) / (wx - ox) + 1;
     p.sy = wy - oy; p.sx = wx - ox; p.n_pairs = n_frames - 1;
     p.run_len = run_len > 0 && run_len < p.n_pairs ? run_len : p.n_pairs;
@@ -246,7 +263,8 @@ extern "C" int b2piv_emul_rows_pad(const unsigned char* frames, int n_frames, in
     std::vector<float> nat;
     const long long n_planes = (long long)p.n_pairs * nw;
     if (planes) { nat.assign((size_t)n_planes * P * P, 0.f); p.planes = nat.data(); }
-    const int rc = P == 32 ? run_rows<RCfg<32>, false, true>(p) : run_rows<RCfg<64>, false, true>(p);
+    const int rc = is_f32 ? (P == 32 ? run_rows<RCfg<32>, true, true>(p) : run_rows<RCfg<64>, true, true>(p))
+                          : (P == 32 ? run_rows<RCfg<32>, false, true>(p) : run_rows<RCfg<64>, false, true>(p));
     if (planes)
         for (long long pl = 0; pl < n_planes; ++pl)
             for (int iy = 0; iy < wy; ++iy)
@@ -256,6 +274,18 @@ extern "C" int b2piv_emul_rows_pad(const unsigned char* frames, int n_frames, in
                     planes[(pl * wy + iy) * wx + ix] = nat[(pl * P + qy) * P + qx];
                 }
     return rc;
+}
+extern "C" int b2piv_emul_rows_pad(const unsigned char* frames, int n_frames, int H, int W, int wy, int wx, int oy, int ox, int run_len,
+                                   int clip_norm, int border_nan, float eps, const unsigned char* keep, float* u, float* v, float* cmax,
+                                   float* s2n, float* planes) {
+    return emul_rows_pad_any(frames, 0, n_frames, H, W, wy, wx, oy, ox, run_len, clip_norm, border_nan, eps, keep, u, v, cmax, s2n, planes);
+}
+// padded mode, float32 frames (rows_f1_pad / f2_pad / f3_pad)
+extern "C" int b2piv_emul_rows_pad_f32(const float* frames, int n_frames, int H, int W, int wy, int wx, int oy, int ox, int run_len,
+                                       int clip_norm, int border_nan, float eps, const unsigned char* keep, float* u, float* v, float* cmax,
+                                       float* s2n, float* planes) {
+    return emul_rows_pad_any((const unsigned char*)frames, 1, n_frames, H, W, wy, wx, oy, ox, run_len, clip_norm, border_nan, eps, keep, u, v,
+                             cmax, s2n, planes);
 }
 extern "C" int b2piv_emul_rows(const unsigned char* frames, int n_frames, int H, int W, int win, int ovl, int run_len, int clip_norm,
                                int border_nan, float eps, const unsigned char* keep, float* u, float* v, float* cmax, float* s2n,

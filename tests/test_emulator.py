@@ -213,7 +213,8 @@ def emul_rows_pad():
         nr, nc = O.get_array_shape((H, W), ws, ov)
         outs = [np.full((n - 1, nr, nc), -7, np.float32) for _ in range(4)]
         planes = np.zeros((n - 1, nr * nc, ws[0], ws[1]), np.float32)
-        rc = lib.b2piv_emul_rows_pad(
+        fn = lib.b2piv_emul_rows_pad_f32 if imgs.dtype == np.float32 else lib.b2piv_emul_rows_pad
+        rc = fn(
             imgs.ctypes.data_as(ctypes.c_void_p), n, H, W, ws[0], ws[1], ov[0], ov[1], run_len, clip, border_nan, ctypes.c_float(1e-7), None,
             *[o.ctypes.data_as(ctypes.c_void_p) for o in outs], planes.ctypes.data_as(ctypes.c_void_p),
         )
@@ -234,6 +235,33 @@ def test_rows_padded_phases_match_oracle(emul_rows_pad, ws, ov, shape, run_len, 
     O.CLIP_NORMALIZED = bool(clip)
     imgs = synth.particle_frames(*shape, dtype=np.uint8)
     imgs[:, : ws[0], : ws[1] + 3] = 0          # a dead window (and a partly dark neighbour)
+    nr, nc = O.get_array_shape(shape[1:], ws, ov)
+    _, _, corr = O.cross_corr(imgs, ws, ov)
+    u, v, c, s = O.uv_timestep(imgs, nc, nr, ws, ov)
+    (eu, ev, ec, es), pl = emul_rows_pad(imgs, ws, ov, run_len, clip)
+    assert np.abs(pl - corr).max() < 3e-6
+    assert np.array_equal(np.isnan(eu), np.isnan(u)) and np.array_equal(np.isnan(es), np.isnan(s))
+    ok = np.isfinite(u)
+    same = np.abs(np.round(eu[ok]) - np.round(u[ok])) + np.abs(np.round(ev[ok]) - np.round(v[ok])) < 0.5
+    assert same.mean() > 0.99
+    assert np.abs(eu[ok][same] - u[ok][same]).max() < 2e-3 and np.abs(ev[ok][same] - v[ok][same]).max() < 2e-3
+    assert np.abs(ec - c).max() < 3e-6
+    assert np.nanmax(np.abs(es - s) / np.abs(s)) < 2e-5
+
+
+@pytest.mark.parametrize("ws,ov,shape,run_len", [((26, 26), (12, 12), (3, 96, 128), 0), ((20, 20), (10, 10), (4, 70, 96), 2),
+                                                  ((10, 10), (5, 5), (3, 48, 64), 0), ((30, 18), (15, 9), (3, 100, 81), 0),
+                                                  ((32, 32), (15, 15), (3, 100, 113), 1), ((16, 16), (8, 8), (3, 50, 64), 0),
+                                                  ((12, 28), (5, 13), (3, 61, 99), 0)])
+@pytest.mark.parametrize("clip", [0, 1])
+def test_rows_padded_phases_float32_frames(emul_rows_pad, ws, ov, shape, run_len, clip):
+    """Padded mode of the row-per-thread kernel on float32 frames - what pyorc's own recipe produces (normalize -> edge_detect ->
+    minmax -> get_piv(window_size=25): float32 frames, 26 x 26 windows): boxes from the 16-byte boundary below any window start,
+    two-pass moments over the window's pixels, frames with negative values, a dead window, frame widths that end inside a box."""
+    O.CLIP_NORMALIZED = bool(clip)
+    imgs = synth.particle_frames(*shape, dtype=np.float32)
+    imgs[1:] -= 0.25 * imgs[:-1]           # time_diff / edge_detect-like frames with negative values
+    imgs[:, : ws[0], : ws[1] + 3] = 0
     nr, nc = O.get_array_shape(shape[1:], ws, ov)
     _, _, corr = O.cross_corr(imgs, ws, ov)
     u, v, c, s = O.uv_timestep(imgs, nc, nr, ws, ov)

@@ -271,6 +271,30 @@ def test_rows_kernel_padded_mode(engine, ws, ov, shape, run_len, clip):
     engine.set_option("run_len", 0.0)
 
 
+@pytest.mark.parametrize("ws,ov,shape,run_len", ROWS_PAD_CASES + [((12, 28), (5, 13), (3, 61, 99), 0), ((26, 26), (12, 12), (3, 96, 127), 0)])
+@pytest.mark.parametrize("clip", [0, 1])
+def test_rows_kernel_padded_mode_float32_frames(engine, ws, ov, shape, run_len, clip):
+    """The padded mode on float32 frames - what pyorc's own recipe hands over (normalize -> edge_detect -> minmax ->
+    get_piv(window_size=25), examples/ngwerere/ngwerere.yml: float32 frames, 26 x 26 windows): un-swizzled TMA boxes from the
+    16-byte boundary below any window start, two-pass moments over the window's pixels, frames with negative values, a dead
+    window, frame widths that end inside a box - against the oracle (planes included) and against the shared-memory kernel."""
+    imgs = synth.particle_frames(*shape, dtype=np.float32)
+    imgs[1:] -= 0.25 * imgs[:-1]
+    imgs[:, : ws[0], : ws[1] + 3] = 0
+    compare(engine, imgs, ws, ov, clip, variant=4, run_len=run_len)
+    assert engine.last_variant == 4
+    a = engine.pairs(imgs, ws, ov)
+    engine.set_option("kernel_variant", 1.0)
+    b = engine.pairs(imgs, ws, ov)
+    engine.set_option("kernel_variant", 0.0)
+    engine.set_option("run_len", 0.0)
+    c = engine.pairs(imgs, ws, ov)                     # auto: the padded rows kernel unless the size is a compiled FFT shape
+    for x, y in zip(a[2:], b[2:]):
+        assert np.array_equal(np.isnan(x), np.isnan(y)) and np.nanmax(np.abs(x - y)) <= 1e-5 * max(1.0, np.nanmax(np.abs(y)))
+    if ws not in ((16, 16), (32, 32)):
+        assert engine.last_variant == 4 and all(np.array_equal(x, y, equal_nan=True) for x, y in zip(a, c))
+
+
 ROWS_PAD128_CASES = [
     ((50, 50), (25, 25), (4, 160, 224), 0),     # a 4K user's 50 px window: 128-point plane, 25 x 25 samples per polyphase component
     ((50, 50), (25, 25), (5, 130, 210), 2),     # short runs, frame width that is not a multiple of 16
@@ -457,7 +481,9 @@ def test_ensemble_mode_matches_oracle(engine, ws, ov, shape, corr_min, s2n_min, 
                                                ((32, 32), (16, 16), (9, 150, 208), np.float32), ((64, 64), (40, 40), (5, 160, 208), np.uint8),
                                                ((128, 128), (64, 64), (5, 300, 432), np.uint8),      # polyphase kernel, ensemble epilogue
                                                ((128, 128), (64, 64), (4, 300, 432), np.float32),    # ... with float32 frames
-                                               ((50, 50), (25, 25), (5, 160, 224), np.uint8)])       # ... and in padded mode
+                                               ((50, 50), (25, 25), (5, 160, 224), np.uint8),        # ... and in padded mode
+                                               ((26, 26), (12, 12), (6, 96, 127), np.float32),       # padded rows kernel, float32 frames
+                                               ((10, 14), (5, 7), (5, 60, 83), np.float32)])
 def test_ensemble_rows_kernel_device_frames(engine, ws, ov, shape, dtype):
     """Device-resident chunk in ONE launch (a unit walks all frames and adds its planes to the HBM accumulators): float32
     frames and window starts that are not 16-byte aligned, against the oracle's plane sums (no thresholds, so no pair can
@@ -619,7 +645,7 @@ def test_pageable_and_pinned_host_frames_give_identical_results(engine):
     # 4 KB (hundreds of groups for these 0.9 MB) to larger than the call, and round 1's three-buffer pool (stage_mode 0)
     for threads, chunks, mode, kb, groups, nt in ((1, 0, 1, 256, 4, 0), (3, 5, 1, 4, 2, 0), (8, 1, 1, 16, 3, 1), (0, 0, 1, 64, 8, 1),
                                                   (5, 22, 1, 8, 4, 0), (2, 3, 1, 4096, 2, 0), (1, 0, 0, 256, 4, 0), (3, 5, 0, 256, 4, 0),
-                                                  (0, 0, 1, 256, 4, 0)):
+                                                  (0, 0, 1, 1024, 3, 1)):     # the defaults again
         engine.set_option("stage_threads", float(threads))
         engine.set_option("copy_chunks", float(chunks))
         engine.set_option("stage_mode", float(mode))

@@ -129,8 +129,9 @@ struct b2piv_engine {
     int stage_threads = 0;   // 0: auto (min(8, hardware threads))
     // stage_mode 1 (default): Stager - slices of `stage_slice_kb` per worker, one H2D per group of `threads` slices, a ring of
     // `stage_groups` groups, non-temporal stores unless `stage_nt` = 0.  Defaults from tools/stage_sweep.py on B200 boxes
-    // (profiles/r02/stage_sweep_n*.log): large groups win (8 MB per H2D), a small cache-resident ring with plain stores does not
-    int stage_mode = 1, stage_slice_kb = 1024, stage_groups = 3, stage_nt = 1;
+    // (profiles/r02/stage_sweep_*.log): 4 MB per H2D and six of them in flight are the most even over the boxes of the pool; a small
+    // cache-resident ring with plain stores loses
+    int stage_mode = 1, stage_slice_kb = 512, stage_groups = 6, stage_nt = 1;
     Stager* stager = nullptr;
     unsigned char* h_ring = nullptr; size_t cap_ring = 0;
     std::vector<cudaEvent_t> ev_ring;

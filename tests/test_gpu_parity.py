@@ -645,7 +645,7 @@ def test_pageable_and_pinned_host_frames_give_identical_results(engine):
     # 4 KB (hundreds of groups for these 0.9 MB) to larger than the call, and round 1's three-buffer pool (stage_mode 0)
     for threads, chunks, mode, kb, groups, nt in ((1, 0, 1, 256, 4, 0), (3, 5, 1, 4, 2, 0), (8, 1, 1, 16, 3, 1), (0, 0, 1, 64, 8, 1),
                                                   (5, 22, 1, 8, 4, 0), (2, 3, 1, 4096, 2, 0), (1, 0, 0, 256, 4, 0), (3, 5, 0, 256, 4, 0),
-                                                  (0, 0, 1, 1024, 3, 1)):     # the defaults again
+                                                  (0, 0, 1, 512, 6, 1)):      # the defaults again
         engine.set_option("stage_threads", float(threads))
         engine.set_option("copy_chunks", float(chunks))
         engine.set_option("stage_mode", float(mode))

@@ -73,6 +73,24 @@ if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
 say(f"bare H2D of the same bytes: {float(t.item()):.3f}")
 
+if os.environ.get("AB"):
+    # same-box A/B of a few settings, alternating, three rounds: (threads, mode, slice KB, groups, non-temporal)
+    cfgs = [(8, 0, 0, 0, 1), (8, 1, 1024, 3, 1), (8, 1, 2048, 3, 1), (8, 1, 512, 6, 1), (12, 1, 1024, 3, 1), (6, 1, 1024, 3, 1), (8, 1, 1024, 3, 0)]
+    for rnd in range(3):
+        row = []
+        for th, mode, kb, groups, nt in cfgs:
+            e.set_option("stage_threads", th)
+            e.set_option("stage_mode", mode)
+            if mode:
+                e.set_option("stage_slice_kb", kb)
+                e.set_option("stage_groups", groups)
+                e.set_option("stage_nt", nt)
+            row.append(f"[t{th} m{mode} {kb}KB g{groups} nt{nt}] {run(pageable):.3f}")
+        say(f"round {rnd}: " + "  ".join(row))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    sys.exit(0)
 per_rank = max(2, min(8, (cores - world) // world))
 thread_list = sorted({per_rank, max(2, per_rank // 2)}, reverse=True)
 for th in thread_list:

@@ -245,16 +245,23 @@ def other_configs(eng, dev, fp32_peak):
              ("configs[2] two-pass, discrete window offset (64x64 / 75 % -> 32x32 / 75 %; round 1's row)", 1080, 1920, (32, 32), (24, 24), 21, (c75, "offset")),
              ("configs[2] two-pass, discrete window offset (64x64 / 50 % -> 32x32 / 75 %)", 1080, 1920, (32, 32), (24, 24), 21, (c50, "offset")),
              ("configs[2] two-pass DEFORM: bilinear window deformation (64x64 / 50 % -> 32x32 / 75 %)", 1080, 1920, (32, 32), (24, 24), 21, (c50, "deform")),
-             ("f-2: 1080p, 50x50 / 50 % (windows of 34 .. 64 px: padded mode of the 128-plane polyphase kernel)", 1080, 1920, (50, 50), (25, 25), 21, None)]
+             ("f-2: 1080p, 50x50 / 50 % (windows of 34 .. 64 px: padded mode of the 128-plane polyphase kernel)", 1080, 1920, (50, 50), (25, 25), 21, None),
+             ("f-2: 1080p, 26x26 / overlap 12, uint8 (pyorc's window_size=25 -> 26; padded mode of the row-per-thread kernel)", 1080, 1920, (26, 26), (12, 12), 21, None),
+             ("f-2: 1080p, 26x26 / overlap 12, FLOAT32 frames (pyorc's own recipe: normalize -> edge_detect -> minmax -> get_piv(window_size=25))", 1080, 1920, (26, 26), (12, 12), 21, "float32")]
     for name, h, w, ws, ov, n, two_pass in cases:
         try:
-            fr = synth.particle_frames_torch(n, h, w, dev, dtype="uint8")
+            in_dtype = "uint8"
+            if two_pass == "float32":
+                in_dtype, two_pass = "float32", None
+            fr = synth.particle_frames_torch(n, h, w, dev, dtype=in_dtype)
             if two_pass:
                 ms, out = _timed(torch, dev, lambda: eng.pairs_two_pass(fr, two_pass[0], (ws, ov), mode=two_pass[1]))
             else:
                 ms, out = _timed(torch, dev, lambda: eng.pairs(fr, ws, ov))
             nwin = int(out[0].numel())
             b_alg, f_alg = _alg(ws, ov)
+            if in_dtype == "float32":
+                b_alg = 2 * (ws[0] - ov[0]) * (ws[1] - ov[1]) * 4 + 16
             rows.append({"config": name, "pairs": n - 1, "windows": nwin, "ms": ms, "windows_per_s": nwin / (ms * 1e-3),
                          "hbm_frac": b_alg * nwin / (ms * 1e-3) / 1e9 / peak,
                          "fp32_tflops": f_alg * nwin / (ms * 1e-3) / 1e12,

@@ -128,3 +128,55 @@ def test_gpu_pipeline_stays_on_device_and_feeds_piv():
     ou, ov, oc, os_ = O.uv_timestep(ref_frames, nc, nr, (64, 64), (32, 32))
     ok = np.isfinite(ou)
     assert np.abs(u.cpu().numpy()[ok] - ou[ok]).max() <= 2e-3 and np.abs(c.cpu().numpy() - oc).max() <= 5e-6
+
+
+@pytest.mark.gpu
+def test_gpu_pyorc_recipe_float32_frames_and_26px_windows():
+    """pyorc's own example recipe (examples/ngwerere/ngwerere.yml): frames.normalize -> edge_detect(wdw_1=1, wdw_2=2) -> minmax(-5, 5)
+    -> get_piv(window_size=25) on the projected Ngwerere frames.  The filters hand FLOAT32 frames to the PIV and the camera-config
+    window becomes 26 x 26 with overlap 12 (frames.py:159-171): on the device that is the padded float32 mode of the row-per-thread
+    kernel.  Filters and PIV stay in HBM; the result equals the float64 oracle on the same filtered frames, and get_piv on the host
+    copy of those frames returns the same fields in m / s."""
+    import os
+
+    import torch
+
+    from oracle import ffpiv_oracle as O
+    from pyorc_b200 import _xr
+    from pyorc_b200 import frames as b2frames
+    from pyorc_b200 import preprocess as G
+    from pyorc_b200.engine import get_engine
+
+    O.CLIP_NORMALIZED = False
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ngwerere_proj.npz"))
+    fr, t, res = np.ascontiguousarray(g["frames"][:, :, :368]), g["time_s"], float(g["resolution"])
+    # (368 of the 371 columns: a caller-owned float32 device tensor needs a 16-byte pitch for the TMA kernels; host frames of any
+    # width are re-pitched by the engine - test_rows_kernel_padded_mode_float32_frames covers odd widths)
+    d = torch.from_numpy(fr).cuda()
+    de = G.minmax(G.edge_detect(G.normalize(d, samples=3), 1, 2), -5, 5)   # 3 frames in the fixture: every frame is a sample
+    assert de.is_cuda and de.dtype == torch.float32
+    # the oracle filters agree with the device filters (their own tests pin them); the PIV is compared on identical inputs
+    ref_f = P.minmax(P.edge_detect(P.normalize(fr, samples=3), 1, 2), -5, 5)
+    he = de.cpu().numpy()
+    assert np.abs(he - ref_f).max() <= 2e-4 * 255
+    ws, ov = (26, 26), (12, 12)
+    eng = get_engine(0)
+    eng.set_option("clip_normalized", 0.0)
+    eng.set_option("kernel_variant", 0.0)
+    u, v, c, s = (x.cpu().numpy() for x in eng.pairs(de, ws, ov))
+    assert eng.last_variant == 4                     # the padded row-per-thread kernel, not the shared-memory fallback
+    nr, nc = O.get_array_shape(fr.shape[1:], ws, ov)
+    ou, ovv, oc, os_ = O.uv_timestep(he, nc, nr, ws, ov)
+    assert np.array_equal(np.isnan(u), np.isnan(ou))
+    ok = np.isfinite(ou)
+    same = np.abs(np.round(u[ok]) - np.round(ou[ok])) + np.abs(np.round(v[ok]) - np.round(ovv[ok])) < 0.5
+    assert same.mean() >= 0.995
+    assert np.abs(u[ok][same] - ou[ok][same]).max() <= 2e-3 and np.abs(v[ok][same] - ovv[ok][same]).max() <= 2e-3
+    assert np.abs(c - oc).max() <= 5e-6
+    # the reference-shaped call: window_size=25 -> 26 x 26, overlap 12, velocities in m / s on (time, y, x)
+    da = _xr.DataArray(he, ("time", "y", "x"), {"time": t, "y": np.arange(he.shape[1]), "x": np.arange(he.shape[2])})
+    ds = b2frames.get_piv(da, window_size=25, resolution=res)
+    assert ds["v_x"].values.shape == (2, nr, nc)
+    dtp = np.diff(t)[:, None, None]
+    assert np.allclose(ds["v_x"].values, (u * np.float32(res) / dtp).astype(np.float32), rtol=0, atol=1e-6, equal_nan=True)
+    assert np.allclose(ds["corr"].values, c, rtol=0, atol=1e-6)

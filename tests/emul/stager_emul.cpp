@@ -87,3 +87,16 @@ extern "C" long long stager_selftest(long long rows, long long row_bytes, long l
     }
     return bad;
 }
+
+// ---- work partition of the row-per-thread kernels (pyorc_b200/csrc/work_partition.h) -------------------------------------
+#include "../../pyorc_b200/csrc/work_partition.h"
+
+extern "C" int emul_pick_run_len(int n_pairs, long long n_wp, long long resident) { return pick_run_len(n_pairs, n_wp, resident); }
+
+// writes at most `cap` ints of the [round][part][3] table; returns the number of units (rounds * n_parts), *cost as in the engine
+extern "C" int emul_partition_units(long long n_wp, int n_pairs, int n_parts, int* out, long long cap, long long* cost) {
+    std::vector<int> tab;
+    const int units = partition_units(n_wp, n_pairs, n_parts, tab, cost);
+    for (size_t i = 0; i < tab.size() && (long long)i < cap; ++i) out[i] = tab[i];
+    return units;
+}

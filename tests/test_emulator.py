@@ -103,6 +103,28 @@ def test_rows_phases_match_oracle(emul_rows, win, ovl, shape, run_len, clip):
     assert np.nanmax(np.abs(es - s) / np.abs(s)) < 1e-5
 
 
+def test_rows_phases_config0_ngwerere(emul_rows):
+    """BASELINE.json configs[0] on the CPU: the 32x32 row-per-thread kernel phases on the three orthorectified Ngwerere frames of
+    pyorc's own test (tests/golden/ngwerere_proj.npz, made by the reference's code), every window against the oracle - real river
+    imagery instead of synthetic particles (the GPU counterpart: tests/test_full_size.py::test_config0_ngwerere_32x32)."""
+    import os
+
+    O.CLIP_NORMALIZED = False
+    frames = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ngwerere_proj.npz"))["frames"]
+    ws, ov = (32, 32), (16, 16)
+    nr, nc = O.get_array_shape(frames.shape[-2:], ws, ov)
+    assert (nr, nc) == (28, 22)
+    _, _, corr = O.cross_corr(frames, ws, ov)
+    u, v, c, s = O.uv_timestep(frames, nc, nr, ws, ov)
+    (eu, ev, ec, es), pl = emul_rows(frames, 32, 16, 0, 0)
+    assert np.abs(pl - corr).max() < 2e-6
+    assert np.array_equal(np.isnan(eu), np.isnan(u)) and np.array_equal(np.isnan(es), np.isnan(s))
+    ok = np.isfinite(u)
+    assert np.abs(eu[ok] - u[ok]).max() < 1e-4 and np.abs(ev[ok] - v[ok]).max() < 1e-4
+    assert np.abs(ec - c).max() < 2e-6
+    assert np.nanmax(np.abs(es - s) / np.abs(s)) < 1e-5
+
+
 @pytest.fixture(scope="module")
 def emul_direct():
     import __graft_entry__ as g

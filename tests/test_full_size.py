@@ -102,6 +102,36 @@ def check_truth(res, H, W, ws, ov):
     assert np.nanmedian(np.abs(u - dx[None])) < 0.15 and np.nanmedian(np.abs(v - dy[None])) < 0.15
 
 
+def test_config0_ngwerere_32x32(engine):
+    """BASELINE.json configs[0]: the Ngwerere sample clip, 2 frame pairs, 32x32 windows, 50 % overlap - the three orthorectified
+    frames that reach ffpiv in pyorc's own test (tests/golden/ngwerere_proj.npz, made by the reference's decode / projection
+    code), EVERY window against the float64 oracle, from host memory as pyorc hands them over (475 x 371 uint8: the device copy is
+    re-pitched), whole and in two chunks with the 1-frame halo."""
+    import os
+
+    frames = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ngwerere_proj.npz"))["frames"]
+    assert frames.shape == (3, 475, 371) and frames.dtype == np.uint8
+    ws, ov = (32, 32), (16, 16)
+    nr, nc = O.get_array_shape(frames.shape[-2:], ws, ov)
+    assert (nr, nc) == (28, 22)                                     # SURVEY 8(a): 616 windows per pair
+    u, v, c, s = O.uv_timestep(frames, nc, nr, ws, ov)
+    gu, gv, gc, gs = (np.array(a) for a in engine.pairs(frames, ws, ov))
+    assert gu.shape == (2, nr, nc)
+    assert np.array_equal(np.isnan(gu), np.isnan(u)) and np.array_equal(np.isnan(gs), np.isnan(s))
+    fin = np.isfinite(u)
+    same = fin & (np.abs(np.round(gu) - np.round(u)) + np.abs(np.round(gv) - np.round(v)) < 0.5)
+    assert same.sum() >= 0.999 * fin.sum()
+    assert np.abs(gu[same] - u[same]).max() <= 2e-3 and np.abs(gv[same] - v[same]).max() <= 2e-3
+    assert np.sqrt(np.mean((gu[same] - u[same]) ** 2)) <= 2e-4 and np.sqrt(np.mean((gv[same] - v[same]) ** 2)) <= 2e-4
+    assert np.abs(gc - c).max() <= 5e-6
+    ok = np.isfinite(s) & (s != 0)
+    assert (np.abs(gs[ok] - s[ok]) / np.abs(s[ok])).max() <= 2e-5
+    a = engine.pairs(frames[:2], ws, ov)
+    b = engine.pairs(frames[1:], ws, ov)
+    for w, x, y in zip((gu, gv, gc, gs), a, b):
+        assert np.array_equal(np.concatenate([x, y]), w, equal_nan=True)
+
+
 def test_config1_1080p_100_pairs_64x64(engine):
     """BASELINE.json configs[1]: synthetic 1080p, 100 frame pairs, 64x64 windows, 50 % overlap (the bench workload)."""
     H, W, ws, ov = 1080, 1920, (64, 64), (32, 32)

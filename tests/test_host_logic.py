@@ -380,3 +380,88 @@ def test_stager_delivers_every_row_once(rows, row_bytes, dpitch, slice_rows, par
     assert f(rows, row_bytes, dpitch, slice_rows, parts, ring, threads, nt, -1, delay_us, 3) == 0
     n_groups = -(-rows // (slice_rows * parts))
     assert f(rows, row_bytes, dpitch, slice_rows, parts, ring, threads, nt, n_groups // 2, delay_us, 2) == 0
+
+
+# ---- work partition of the row-per-thread kernels (csrc/work_partition.h, compiled for the host) ----------------------------
+def _partition_lib():
+    import ctypes
+
+    import __graft_entry__ as g
+
+    lib = ctypes.CDLL(g.build_stager_emulator())
+    lib.emul_pick_run_len.argtypes = [ctypes.c_int, ctypes.c_longlong, ctypes.c_longlong]
+    lib.emul_partition_units.argtypes = [ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong,
+                                         ctypes.POINTER(ctypes.c_longlong)]
+    return lib
+
+
+def _partition(lib, n_wp, n_pairs, n_parts):
+    import ctypes
+
+    cap = 3 * (n_wp + n_parts + 2) * max(n_parts, 1) * 2
+    out = np.full(cap, -9, np.int32)
+    cost = ctypes.c_longlong()
+    units = lib.emul_partition_units(n_wp, n_pairs, n_parts, out.ctypes.data, cap, ctypes.byref(cost))
+    assert units % n_parts == 0 and 3 * units <= cap
+    return out[: 3 * units].reshape(units // n_parts, n_parts, 3), int(cost.value)
+
+
+@pytest.mark.parametrize(
+    "n_wp,n_pairs,n_parts",
+    [(944, 100, 888),      # BASELINE configs[1]: 1888 windows = 944 window pairs, 100 frame pairs, six groups on each of 148 SMs
+     (944, 100, 592),      # ... four groups per SM (shared-memory variant)
+     (3927, 125, 888),     # configs[3]: a 125-pair chunk of 4K
+     (7, 3, 5), (1, 40, 8), (13, 1, 4), (5, 2, 10), (3, 3, 1), (2, 7, 14)],
+)
+def test_unit_table_covers_every_item_once_and_evenly(n_wp, n_pairs, n_parts):
+    """Every (window pair, frame pair) belongs to exactly one segment, the parts are contiguous in window-pair-major order and
+    hold total / n_parts items up to rounding, a segment never crosses a window pair, padding entries are (-1, 0, -1), and the
+    reported cost is the longest part's frame pairs plus one transform per segment (what the engine compares with the wave
+    schedule of pick_run_len)."""
+    lib = _partition_lib()
+    tab, cost = _partition(lib, n_wp, n_pairs, n_parts)
+    total = n_wp * n_pairs
+    seen = np.zeros((n_wp, n_pairs), np.int32)
+    worst = 0
+    pos = 0
+    for part in range(n_parts):
+        items, c = 0, 0
+        padded = False
+        for rd in range(tab.shape[0]):
+            wp, f0, f1 = (int(x) for x in tab[rd, part])
+            if wp < 0:
+                assert (wp, f0, f1) == (-1, 0, -1)
+                padded = True
+                continue
+            assert not padded                                   # a part's segments come first, then only padding
+            assert 0 <= wp < n_wp and 0 <= f0 < f1 <= n_pairs
+            assert wp * n_pairs + f0 == pos                     # contiguous: the parts tile the window-pair-major list in order
+            seen[wp, f0:f1] += 1
+            pos += f1 - f0
+            items += f1 - f0
+            c += f1 - f0 + 1
+        assert items in (total // n_parts, -(-total // n_parts))
+        worst = max(worst, c)
+    assert pos == total and (seen == 1).all()
+    assert cost == worst
+
+
+def test_run_length_minimises_the_wave_cost():
+    """pick_run_len against a brute-force search of its own cost model; the 1080p example of DESIGN.md 4.1b (944 window pairs,
+    100 frame pairs, 592 resident groups: 5 chunks of 20 pairs, 7.97 waves, 168 frame times)."""
+    lib = _partition_lib()
+
+    def cost(n_pairs, n_wp, resident, run):
+        chunks = -(-n_pairs // run)
+        return -(-(n_wp * chunks) // resident) * (run + 1)
+
+    assert lib.emul_pick_run_len(100, 944, 592) == 20
+    assert cost(100, 944, 592, 20) == 168
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        n_pairs, n_wp, resident = int(rng.integers(1, 300)), int(rng.integers(1, 5000)), int(rng.integers(1, 1200))
+        run = lib.emul_pick_run_len(n_pairs, n_wp, resident)
+        assert 1 <= run <= n_pairs
+        reachable = {-(-n_pairs // c) for c in range(1, min(n_pairs, 64) + 1)}      # the run lengths the search visits
+        assert run in reachable
+        assert cost(n_pairs, n_wp, resident, run) == min(cost(n_pairs, n_wp, resident, r) for r in reachable)

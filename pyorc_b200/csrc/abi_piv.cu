@@ -134,12 +134,14 @@ static bool pad_eligible(const b2piv_engine* e, const void* d_frames, long long 
     return tma_available();
 }
 
-// Padded mode of the 128-plane polyphase kernel: even uint8 windows whose larger side is 34 .. 64 px (piv_rows128.cuh)
+// Padded mode of the 128-plane polyphase kernel: even windows (uint8 or float32 frames) whose larger side is 34 .. 64 px
+// (piv_rows128.cuh)
 static bool pad128_eligible(const b2piv_engine* e, const void* d_frames, long long frame_stride, int pitch) {
     const int m = e->wy > e->wx ? e->wy : e->wx;
-    if (e->dtype != B2PIV_U8 || m <= 32 || m > 64 || (e->wy & 1) || (e->wx & 1) || e->wy < 2 || e->wx < 2) return false;
+    if (m <= 32 || m > 64 || (e->wy & 1) || (e->wx & 1) || e->wy < 2 || e->wx < 2) return false;
     if (fft_config(e->wy, e->wx)) return false;   // compiled FFT shapes (64x64, 64x32 ...) have their own kernels
     if ((pitch & 15) || (frame_stride & 15) || (((uintptr_t)d_frames) & 15)) return false;
+    if (e->dtype == B2PIV_F32 && e->W < 68) return false;   // the float32 box is 68 floats wide (R128_PFW); narrower frames: shared-memory kernel
     return tma_available();
 }
 

@@ -1,4 +1,5 @@
-// k_rows128.cu - 128x128 uint8 windows on the polyphase row-per-thread kernel (piv_rows128.cuh).
+// k_rows128.cu - 128x128 windows (and, zero-padded, even windows of 34 .. 64 px) on the polyphase row-per-thread kernel
+// (piv_rows128.cuh), uint8 and float32 frames.
 #include "rows_kernel.cuh"
 #include "piv_rows128.cuh"
 
@@ -37,12 +38,16 @@ __global__ void __launch_bounds__(256, 1) piv_rows128_kernel(const __grid_consta
     for (long long unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
         const RUnit un = decode_unit(p, (int)unit);
         const int nfr = un.f1 - un.f0 + 1;
-        const int xa0 = un.x0[0] & ~15, xa1 = un.x0[1] & ~15;      // padded mode: boxes from the 16-byte boundary below
+        constexpr int XAL = F32 ? 3 : 15;                          // padded mode: boxes from the 16-byte boundary below (4 floats / 16 bytes)
+        const int xa0 = un.x0[0] & ~XAL, xa1 = un.x0[1] & ~XAL;
         const int xoff0 = un.x0[0] - xa0, xoff1 = un.x0[1] - xa1;
         auto issue_frame = [&](int frame) {
             fence_proxy_async();
-            if constexpr (F32) {
-                static_assert(!(F32 && PAD), "float32 frames: native 128 x 128 windows only");
+            if constexpr (F32 && PAD) {
+                mbar_expect_tx(&s.mbar, 2 * R128_PFWIN);
+                tma_load_3d(r128_ftile(s, 0), &tmap, &s.mbar, xa0, un.y0[0], frame);
+                tma_load_3d(r128_ftile(s, 1), &tmap, &s.mbar, xa1, un.y0[1], frame);
+            } else if constexpr (F32) {
                 mbar_expect_tx(&s.mbar, 2 * 128 * 128 * 4);
 #pragma unroll
                 for (int w = 0; w < 2; ++w)
@@ -70,7 +75,15 @@ __global__ void __launch_bounds__(256, 1) piv_rows128_kernel(const __grid_consta
             const int f = un.f0 + k;
             while (!mbar_try_wait(&s.mbar, parity)) {}
             parity ^= 1u;
-            if constexpr (F32) {
+            if constexpr (F32 && PAD) {
+                r128_f1_pad(s, r, sub, t, p, 0, xoff0);
+                r128_f1_pad(s, r, sub, t, p, 1, xoff1);
+                __syncthreads();  // A: row sums visible, tile (in the spectrum blocks of sub-groups 0 / 1) fully consumed
+                r128_f2_pad(s, r, sub, t, p, 0);
+                r128_f2_pad(s, r, sub, t, p, 1);
+                __syncthreads();  // A2: centred second moments visible
+                r128_f3_pad(s, r, t, p);
+            } else if constexpr (F32) {
                 r128_f1(s, r, sub, t, 0);
                 r128_f1(s, r, sub, t, 1);
                 __syncthreads();  // A: row sums visible, tile (in the spectrum blocks) fully consumed
@@ -127,8 +140,7 @@ int launch_rows128(b2piv_engine* e, const Params& gp, cudaStream_t st, const Ens
     const cuuint64_t dims[3] = {(cuuint64_t)e->W, (cuuint64_t)e->H, (cuuint64_t)n_frames};
     const cuuint64_t strides[2] = {(cuuint64_t)gp.pitch, (cuuint64_t)gp.frame_stride};
     const bool f32 = e->dtype == B2PIV_F32;
-    if (f32 && pad) return fail(e, B2PIV_ERR_UNSUPPORTED, "padded 128-plane rows kernel needs uint8 frames");
-    const cuuint32_t box[3] = {(cuuint32_t)(f32 ? 32 : (pad ? R128_PWB : 128)), (cuuint32_t)((pad || f32) ? 64 : 32), 1};
+    const cuuint32_t box[3] = {(cuuint32_t)(pad ? (f32 ? R128_PFW : R128_PWB) : (f32 ? 32 : 128)), (cuuint32_t)((pad || f32) ? 64 : 32), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult cr = get_encode_tiled()(&tmap, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(gp.frames), dims, strides, box, estr,
                                            CU_TENSOR_MAP_INTERLEAVE_NONE, pad ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -151,7 +163,8 @@ int launch_rows128(b2piv_engine* e, const Params& gp, cudaStream_t st, const Ens
         for (int x = 0; x < 64; ++x) p.pad_cm[x] = x < p.nx ? 1.f : 0.f;
     }
     if (ep) { p.corr_min = ep->corr_min; p.s2n_min = ep->s2n_min; p.ens_sum = ep->plane_sum; p.ens_count = ep->count; }
-    auto kern = pad ? (ep ? piv_rows128_kernel<true, true, false> : piv_rows128_kernel<false, true, false>)
+    auto kern = pad ? (f32 ? (ep ? piv_rows128_kernel<true, true, true> : piv_rows128_kernel<false, true, true>)
+                           : (ep ? piv_rows128_kernel<true, true, false> : piv_rows128_kernel<false, true, false>))
                     : (f32 ? (ep ? piv_rows128_kernel<true, false, true> : piv_rows128_kernel<false, false, true>)
                            : (ep ? piv_rows128_kernel<true, false, false> : piv_rows128_kernel<false, false, false>));
     const size_t smem = sizeof(R128Smem) + 1024;

@@ -40,6 +40,11 @@ constexpr int R128_BATCH = 11;     // ky rows per exchange batch (3 batches cove
 constexpr int R128_PWB = 80;                    // padded tile: bytes per row
 constexpr int R128_PWIN = 64 * R128_PWB;        // and per window
 static_assert(sizeof(float2) * R6::NWARP * R6::XBLK >= 2 * R128_PWIN, "padded tile must fit in a sub-group's transpose blocks");
+// Padded mode on float32 frames: one 68-float x 64-row unswizzled box per window from the 16-byte boundary below its start (the
+// window's 64 floats at a float offset of 0 .. 3), window w in the spectrum block of sub-group w (idle between the cross phases,
+// like the native float32 tile).
+constexpr int R128_PFW = 68;                    // padded float32 tile: floats per row
+constexpr int R128_PFWIN = 64 * R128_PFW * 4;   // bytes per window
 constexpr int R128_NPX = 128 * 128;
 // tile: window w rows [32 j, 32 j + 32) -> sub[j].tile() + w * 4096 ([32 rows][128 B], SWIZZLE_128B)
 static_assert(sizeof(float2) * R6::NWARP * R6::XBLK >= 2 * 4096, "tile quarter must fit in a sub-group's transpose blocks");
@@ -276,6 +281,69 @@ __device__ __forceinline__ void r128_f3(R128Smem& s, RRegs<R6>& r, int clip_norm
 #pragma unroll
         for (int x = 0; x < 64; ++x) r.v[x] = make_float2(fmaxf(r.v[x].x, 0.f), fmaxf(r.v[x].y, 0.f));
     }
+}
+
+// float32 frames in padded mode (even windows of 34 .. 64 px of pyorc's float32 filters, e.g. a 4K user's 50 px window behind
+// edge_detect): the embedding of r128_p1_pad / r128_p2_pad with the two-pass float moments of r128_f1 .. f3.  F1(w): the thread's row
+// 2 sigma(t) + p1 of window w (if it is a window row), the floats of its column parity at the window's float offset `xoff` in the
+// box -> component w of r.v[0 .. nx), everything else exactly 0, row sum; F2(w): mean over the (2 ny)(2 nx) window pixels, centre
+// the window's pixels only, centred second moment; F3: 0.5 / std, optional clip, spectrum factor of the own column.  p.ny / p.nx
+// are the COMPONENT size.  From the row transform on it is the uint8 padded path (r128_cross<PAD>, r128_p6_pad ...).
+static_assert(sizeof(RSmem<R6>::park) >= R128_PFWIN + 1024, "a padded float32 window (plus alignment slack) must fit in a spectrum block");
+__device__ __forceinline__ void r128_f1_pad(R128Smem& s, RRegs<R6>& r, int sub, int t, const RParams& p, int w, int xoff) {
+    const int p1 = sub >> 1, p2 = sub & 1;
+    const int row = 2 * column_of<64>(t) + p1;
+    const bool rowok = row < 2 * p.ny;
+    const float* src = reinterpret_cast<const float*>(r128_ftile(s, w)) + (rowok ? row : 0) * R128_PFW + xoff + p2;
+    float sum = 0.f;
+#pragma unroll
+    for (int x = 0; x < 32; ++x) {
+        const float val = (rowok && x < p.nx) ? src[2 * x] : 0.f;
+        if (w == 0) r.v[x].x = val; else r.v[x].y = val;
+        sum += val;
+    }
+#pragma unroll
+    for (int x = 32; x < 64; ++x) {
+        if (w == 0) r.v[x].x = 0.f; else r.v[x].y = 0.f;
+    }
+    red_put_f32(&s.sub[sub].red[t >> 5][2 * w], sum, t);
+}
+__device__ __forceinline__ void r128_f2_pad(R128Smem& s, RRegs<R6>& r, int sub, int t, const RParams& p, int w) {
+    float S = 0.f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) S += bits_f32(s.sub[g].red[k][2 * w]);
+    }
+    const float mean = S / (float)(4 * p.ny * p.nx);
+    const bool rowok = column_of<64>(t) < p.ny;
+    float q = 0.f;
+#pragma unroll
+    for (int x = 0; x < 32; ++x) {
+        const float m = (rowok && x < p.nx) ? mean : 0.f;   // pixels outside the window stay exactly 0
+        if (w == 0) { r.v[x].x -= m; q = fmaf(r.v[x].x, r.v[x].x, q); }
+        else        { r.v[x].y -= m; q = fmaf(r.v[x].y, r.v[x].y, q); }
+    }
+    red_put_f32(&s.sub[sub].red[t >> 5][2 * w + 1], q, t);
+}
+__device__ __forceinline__ void r128_f3_pad(R128Smem& s, RRegs<R6>& r, int t, const RParams& p) {
+    const float npx = (float)(4 * p.ny * p.nx);
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        float Q = 0.f;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) Q += bits_f32(s.sub[g].red[k][2 * w + 1]);
+        }
+        r.half_alpha_new[w] = Q > 0.f ? 0.5f * sqrtf(npx) * (1.0f / sqrtf(Q)) : 0.f;   // 0.5 / sqrt(Q / ((2 ny)(2 nx)))
+    }
+    r.dc_fix[0] = r.dc_fix[1] = 0.f;
+    if (p.clip_norm) {
+#pragma unroll
+        for (int x = 0; x < 32; ++x) r.v[x] = make_float2(fmaxf(r.v[x].x, 0.f), fmaxf(r.v[x].y, 0.f));
+    }
+    r.tx = p.pad_tx[column_of<64>(t)];
 }
 
 // packed fp32 forms (piv_core.cuh): two instructions each

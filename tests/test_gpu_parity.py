@@ -325,6 +325,30 @@ def test_rows128_kernel_padded_mode(engine, ws, ov, shape, run_len, clip):
         assert np.array_equal(np.isnan(x), np.isnan(y)) and np.nanmax(np.abs(x - y)) <= 1e-5 * max(1.0, np.nanmax(np.abs(y)))
 
 
+@pytest.mark.parametrize("ws,ov,shape,run_len", ROWS_PAD128_CASES + [((50, 50), (24, 24), (3, 131, 203), 0)])
+@pytest.mark.parametrize("clip", [0, 1])
+def test_rows128_kernel_padded_mode_float32_frames(engine, ws, ov, shape, run_len, clip):
+    """The padded mode of the 128-plane polyphase kernel on float32 frames (pyorc's edge_detect / smooth / time_diff output with a
+    window of 34 .. 64 px, e.g. a 4K user's 50 px window): one 68-float x 64-row un-swizzled TMA box per window from the 16-byte
+    boundary below its start, two-pass float moments over the window's pixels, frames with negative values, a dead window, odd
+    strides and frame widths - against the oracle (planes included) and against the shared-memory kernel."""
+    imgs = synth.particle_frames(*shape, dtype=np.float32)
+    imgs[1:] -= 0.25 * imgs[:-1]
+    imgs[:, : ws[0], : ws[1] + 3] = 0
+    compare(engine, imgs, ws, ov, clip, variant=4, run_len=run_len)
+    assert engine.last_variant == 4
+    a = engine.pairs(imgs, ws, ov)
+    engine.set_option("kernel_variant", 1.0)
+    b = engine.pairs(imgs, ws, ov)
+    assert engine.last_variant == 1
+    engine.set_option("kernel_variant", 0.0)
+    engine.set_option("run_len", 0.0)
+    c = engine.pairs(imgs, ws, ov)                     # auto: the padded polyphase kernel
+    assert engine.last_variant == 4 and all(np.array_equal(x, y, equal_nan=True) for x, y in zip(a, c))
+    for x, y in zip(a[2:], b[2:]):
+        assert np.array_equal(np.isnan(x), np.isnan(y)) and np.nanmax(np.abs(x - y)) <= 1e-5 * max(1.0, np.nanmax(np.abs(y)))
+
+
 def test_rows_kernels_on_device_tensors_need_an_aligned_pitch(engine):
     """Host frames are copied into a 16-byte pitched buffer by the engine (any width qualifies); a caller-owned device
     tensor is used in place, so an odd pitch is refused by the TMA kernels and taken by the shared-memory kernel."""
@@ -482,6 +506,7 @@ def test_ensemble_mode_matches_oracle(engine, ws, ov, shape, corr_min, s2n_min, 
                                                ((128, 128), (64, 64), (5, 300, 432), np.uint8),      # polyphase kernel, ensemble epilogue
                                                ((128, 128), (64, 64), (4, 300, 432), np.float32),    # ... with float32 frames
                                                ((50, 50), (25, 25), (5, 160, 224), np.uint8),        # ... and in padded mode
+                                               ((50, 46), (25, 23), (5, 160, 224), np.float32),      # ... padded mode, float32 frames (16-byte pitch: device tensor used in place)
                                                ((26, 26), (12, 12), (6, 96, 127), np.float32),       # padded rows kernel, float32 frames
                                                ((10, 14), (5, 7), (5, 60, 83), np.float32)])
 def test_ensemble_rows_kernel_device_frames(engine, ws, ov, shape, dtype):

@@ -246,6 +246,7 @@ def other_configs(eng, dev, fp32_peak):
              ("configs[2] two-pass, discrete window offset (64x64 / 50 % -> 32x32 / 75 %)", 1080, 1920, (32, 32), (24, 24), 21, (c50, "offset")),
              ("configs[2] two-pass DEFORM: bilinear window deformation (64x64 / 50 % -> 32x32 / 75 %)", 1080, 1920, (32, 32), (24, 24), 21, (c50, "deform")),
              ("f-2: 1080p, 50x50 / 50 % (windows of 34 .. 64 px: padded mode of the 128-plane polyphase kernel)", 1080, 1920, (50, 50), (25, 25), 21, None),
+             ("f-2: 1080p, 50x50 / 50 %, FLOAT32 frames (padded mode of the 128-plane polyphase kernel behind pyorc's float32 filters)", 1080, 1920, (50, 50), (25, 25), 21, "float32"),
              ("f-2: 1080p, 26x26 / overlap 12, uint8 (pyorc's window_size=25 -> 26; padded mode of the row-per-thread kernel)", 1080, 1920, (26, 26), (12, 12), 21, None),
              ("f-2: 1080p, 26x26 / overlap 12, FLOAT32 frames (pyorc's own recipe: normalize -> edge_detect -> minmax -> get_piv(window_size=25))", 1080, 1920, (26, 26), (12, 12), 21, "float32")]
     for name, h, w, ws, ov, n, two_pass in cases:

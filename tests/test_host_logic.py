@@ -465,3 +465,58 @@ def test_run_length_minimises_the_wave_cost():
         reachable = {-(-n_pairs // c) for c in range(1, min(n_pairs, 64) + 1)}      # the run lengths the search visits
         assert run in reachable
         assert cost(n_pairs, n_wp, resident, run) == min(cost(n_pairs, n_wp, resident, r) for r in reachable)
+
+
+def test_load_frame_chunk_retries_with_one_frame_less():
+    """pyorc/velocimetry/ffpiv.py:13-21: a chunk whose lazy load raises TypeError (pyorc: the last frame of a video that cannot be
+    decoded) is retried without its last frame, recursively; objects without .load() pass through; other exceptions propagate."""
+
+    class Lazy:
+        def __init__(self, n, bad_from, exc=TypeError):
+            self.n, self.bad_from, self.exc, self.loads = n, bad_from, exc, []
+
+        def __len__(self):
+            return self.n
+
+        def __getitem__(self, sl):
+            assert sl == slice(None, -1)
+            child = Lazy(self.n - 1, self.bad_from, self.exc)
+            child.loads = self.loads
+            return child
+
+        def load(self):
+            self.loads.append(self.n)
+            if self.n > self.bad_from:
+                raise self.exc("cannot decode")
+            return self
+
+    lazy = Lazy(6, 4)
+    got = velocimetry.load_frame_chunk(lazy)
+    assert len(got) == 4 and lazy.loads == [6, 5, 4]
+    arr = np.zeros((3, 4, 5), np.uint8)
+    assert velocimetry.load_frame_chunk(arr) is arr
+    with pytest.raises(ValueError):
+        velocimetry.load_frame_chunk(Lazy(3, 1, ValueError))
+
+
+def test_chunk_shortened_by_the_loader_keeps_time_and_dt_aligned(fake):
+    """A chunk that comes back one frame short (load_frame_chunk's retry) yields one time step less, with the time stamps and
+    dt of the pairs that were actually computed (ffpiv.py:402-404: `time = da.time[1:]`, `dt.sel(time=time)`)."""
+    da, res = make_frames(n=7)
+
+    frames = da
+    orig = velocimetry.load_frame_chunk
+    try:
+        velocimetry.load_frame_chunk = lambda chunk: chunk[:-1] if len(chunk) == 7 else orig(chunk)
+        ws, ov = (32, 32), (16, 16)
+        nr, nc = O.get_array_shape(frames.shape[-2:], ws, ov)
+        t = np.asarray(frames["time"].values)
+        dt = np.diff(t) * np.array([1.0, 1.1, 1.2, 1.3, 1.4, 1.5])
+        ds = velocimetry.get_b2piv(frames, np.arange(nr), np.arange(nc), dt, ws, ov, ws, res, res, chunksize=7)
+    finally:
+        velocimetry.load_frame_chunk = orig
+    assert ds["v_x"].shape == (5, nr, nc)
+    assert np.array_equal(np.asarray(ds.coords["time"]), t[1:6])
+    u, v, c, s = O.uv_timestep(np.asarray(frames.values)[:6], nc, nr, ws, ov)
+    want = (u * res / dt[:5, None, None]).astype(np.float32)
+    assert np.allclose(ds["v_x"].values, want, rtol=0, atol=1e-6, equal_nan=True)

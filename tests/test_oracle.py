@@ -172,3 +172,60 @@ def test_displaced_second_pass_needs_two_forward_transforms_per_frame():
     k1, k2 = np.meshgrid(np.fft.fftfreq(32), np.fft.fftfreq(32), indexing="ij")
     ramp = np.fft.fft2(w0) * np.exp(2j * np.pi * (3 * k1 - 2 * k2))
     assert np.abs(np.fft.ifft2(ramp).real - w_shift).max() > 0.5     # circular shift != displaced window
+
+
+@pytest.mark.parametrize("n,P", [((26, 26), 64), ((10, 14), 32), ((30, 18), 64), ((32, 32), 64)])
+def test_padded_embedding_identity_behind_the_padded_rows_kernels(n, P):
+    """piv_rows.cuh "Padded mode": the period-n circular correlation of the reference equals, at the lags 0 .. n-1, the circular
+    correlation on a P x P plane (P >= 2 n) of the zero-padded window `a` with the window `b` tiled 2 x 2 - and the tiled plane's
+    spectrum is the zero-padded one times T(k) = (1 + w^(ny k1)) (1 + w^(nx k2)), w = exp(-2 pi i / P), so ONE forward transform
+    per window and frame serves both roles.  Lag q >= n/2 is the reference's negative lag q - n: its fftshifted plane is
+    element (q + n/2) % n <- lag q.  Checked in float64 against irfft2(conj(rfft2 a) rfft2 b)."""
+    ny, nx = n
+    rng = np.random.default_rng(5)
+    a, b = rng.standard_normal(n), rng.standard_normal(n)
+    ref = np.fft.irfft2(np.conj(np.fft.rfft2(a)) * np.fft.rfft2(b), s=n)
+    za, zb = np.zeros((P, P)), np.zeros((P, P))
+    za[:ny, :nx], zb[:ny, :nx] = a, b
+    k1, k2 = np.meshgrid(np.arange(P), np.arange(P), indexing="ij")
+    T = (1 + np.exp(-2j * np.pi * ny * k1 / P)) * (1 + np.exp(-2j * np.pi * nx * k2 / P))
+    tiled = np.zeros((P, P))
+    tiled[: 2 * ny, : 2 * nx] = np.tile(b, (2, 2))
+    assert np.abs(np.fft.fft2(zb) * T - np.fft.fft2(tiled)).max() < 1e-9
+    plane = np.fft.ifft2(np.conj(np.fft.fft2(za)) * np.fft.fft2(zb) * T)
+    assert np.abs(plane.imag).max() < 1e-9
+    assert np.abs(plane.real[:ny, :nx] - ref).max() < 1e-9
+    sh = np.fft.fftshift(ref)
+    q1, q2 = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    assert np.array_equal(sh[(q1 + ny // 2) % ny, (q2 + nx // 2) % nx], ref)
+
+
+@pytest.mark.parametrize("n", [(50, 50), (34, 34), (64, 48), (36, 20), (62, 62)])
+def test_padded_polyphase_identity_behind_the_padded_128_plane_kernel(n):
+    """piv_rows128.cuh "Padded mode" (even windows of 34 .. 64 px, uint8 and float32 frames): the embedding above on the 128 x 128
+    plane, computed through the four 64 x 64 polyphase components.  A component holds (ny/2) x (nx/2) samples of the window, the
+    tiling shift n = 2 (n/2) stays inside a component, so T(k) = (1 + w64^(k1 ny/2)) (1 + w64^(k2 nx/2)) multiplies every C_q alike;
+    lag (2 m1 + q1, 2 m2 + q2) of component q is the reference's plane at that lag."""
+    ny, nx = n
+    rng = np.random.default_rng(9)
+    a, b = rng.standard_normal(n), rng.standard_normal(n)
+    ref = np.fft.irfft2(np.conj(np.fft.rfft2(a)) * np.fft.rfft2(b), s=n)
+    za, zb = np.zeros((128, 128)), np.zeros((128, 128))
+    za[:ny, :nx], zb[:ny, :nx] = a, b
+    comp = lambda x, p1, p2: x[p1::2, p2::2]
+    A = {(p1, p2): np.fft.fft2(comp(za, p1, p2)) for p1 in (0, 1) for p2 in (0, 1)}
+    B = {(p1, p2): np.fft.fft2(comp(zb, p1, p2)) for p1 in (0, 1) for p2 in (0, 1)}
+    k1, k2 = np.meshgrid(np.arange(64), np.arange(64), indexing="ij")
+    T = (1 + np.exp(-2j * np.pi * k1 * (ny // 2) / 64)) * (1 + np.exp(-2j * np.pi * k2 * (nx // 2) / 64))
+    got = np.empty((128, 128))
+    for q1 in (0, 1):
+        for q2 in (0, 1):
+            C = np.zeros((64, 64), complex)
+            for p1 in (0, 1):
+                for p2 in (0, 1):
+                    s1, s2 = p1 & q1, p2 & q2
+                    C += np.conj(A[p1, p2]) * B[p1 ^ q1, p2 ^ q2] * np.exp(2j * np.pi * (k1 * s1 + k2 * s2) / 64)
+            cq = np.fft.ifft2(C * T)
+            assert np.abs(cq.imag).max() < 1e-9
+            got[q1::2, q2::2] = cq.real
+    assert np.abs(got[:ny, :nx] - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())

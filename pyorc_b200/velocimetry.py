@@ -157,14 +157,7 @@ def get_b2piv(
         raise ValueError("dt must hold one interval per frame pair")
     # a device named k times gets k engines (slots): each engine is driven by one host thread only
     engs = [get_engine(d, devices[:i].count(d)) if devices[:i].count(d) else get_engine(d) for i, d in enumerate(devices)]
-    if len(engs) > 1:
-        # every engine stages pageable frames with its own copy threads: share the host's cores instead of oversubscribing them
-        import os
-
-        per = max(2, min(8, (os.cpu_count() or 8) // len(engs)))
-        for e in engs:
-            if hasattr(e, "set_option"):
-                e.set_option("stage_threads", per)
+    _share_host_cores(engs)
     common = (frames, bounds, times, dt_vals, y, x, res_y, res_x, n_rows, n_cols, window_size, overlap, engs)
     if coarse_pass is not None:
         if ensemble_corr:
@@ -197,6 +190,19 @@ def get_b2piv(
         "kernel_launches": int(sum(getattr(e, "launch_count", 0) for e in engs)),
     })
     return ds
+
+
+def _share_host_cores(engs):
+    """Every engine stages pageable frames with its own copy threads: several engines in one call share the host's cores instead
+    of oversubscribing them; a later single-engine call on the same (process-wide) engine gets the engine's own default back.
+    The option is only sent when it changes - setting it tears down the engine's copy threads."""
+    import os
+
+    per = 0 if len(engs) == 1 else max(2, min(8, (os.cpu_count() or 8) // len(engs)))      # 0: the engine's default
+    for e in engs:
+        if hasattr(e, "set_option") and getattr(e, "_stage_threads_shared", 0) != per:
+            e.set_option("stage_threads", per)
+            e._stage_threads_shared = per
 
 
 def _get_uv_timestep(da, n_cols, n_rows, window_size, overlap, search_area_size, engine, signal_threshold=None, coarse_pass=None, units=None):

@@ -520,3 +520,30 @@ def test_chunk_shortened_by_the_loader_keeps_time_and_dt_aligned(fake):
     u, v, c, s = O.uv_timestep(np.asarray(frames.values)[:6], nc, nr, ws, ov)
     want = (u * res / dt[:5, None, None]).astype(np.float32)
     assert np.allclose(ds["v_x"].values, want, rtol=0, atol=1e-6, equal_nan=True)
+
+
+def test_staging_threads_are_shared_between_engines_and_given_back(monkeypatch):
+    """Several engines in one get_b2piv call split the host's cores for their staging threads; the option is sent only when it
+    changes (it tears the copy threads down) and a later single-engine call on the same engine restores the engine's default."""
+    import os
+
+    class Opt:
+        def __init__(self):
+            self.sent = []
+
+        def set_option(self, name, value):
+            self.sent.append((name, value))
+
+    monkeypatch.setattr(os, "cpu_count", lambda: 32)
+    a, b, c, d = Opt(), Opt(), Opt(), Opt()
+    velocimetry._share_host_cores([a])
+    assert a.sent == []                                          # the single-engine path never touches the option
+    velocimetry._share_host_cores([a, b, c, d])
+    assert a.sent == b.sent == [("stage_threads", 8)]
+    velocimetry._share_host_cores([a, b, c, d])
+    assert a.sent == [("stage_threads", 8)]                      # unchanged: not sent again
+    velocimetry._share_host_cores([a, b, c, d, Opt(), Opt(), Opt(), Opt()])
+    assert a.sent[-1] == ("stage_threads", 4)
+    velocimetry._share_host_cores([a])
+    assert a.sent[-1] == ("stage_threads", 0) and len(a.sent) == 3
+    velocimetry._share_host_cores([FakeEngine()])                # engines without options (test doubles) are left alone

@@ -13,8 +13,18 @@ ffpiv.py:325-326,418-419,469-470):
                                                           [i - w // 2, i + w - 1 - w // 2]; NaN where it leaves the axis
   ``da.where(m)``, ``da.fillna(o)``                       np.where
 
-PARITY UNPINNED: xarray is not installed in this image and pyorc's mask tests (tests/test_mask.py) assert no values, so
-this restatement is checked against the reference's source, not against its output.  Reference quirks are kept:
+PARITY PIN STATUS: PINNED on the reference's own example output for seven of the eleven masks.  xarray is not installed in this
+image and pyorc's mask tests (tests/test_mask.py) assert no values, but the reference SHIPS the input and the output of its mask
+stack: examples/ngwerere/ngwerere_piv.nc and ngwerere_masked.nc (notebook 03, cells 10 + 16: corr, minmax, rolling, outliers,
+variance, count, window_mean(wdw=2, tolerance=0.5, reduce_time=True), each in place, then set_encoding + to_netcdf).  Read with a
+minimal HDF5 parser (tests/golden/h5min.py, make_mask_golden.py), this restatement reproduces that output EXACTLY: the same
+93 824 of 486 750 values survive, not one differs, and the survivors re-encode to the file's int16 values
+(tests/test_mask.py::test_oracle_reproduces_the_reference_mask_example_exactly); float64 arithmetic instead of float32 misses it in
+a few dozen threshold ties, so the arithmetic type is pinned too.  Also pinned by the files: the CF attributes (scale_factor 0.01,
+_FillValue -9999, int16) and decode -> encode being the identity on them.  NOT covered by that example and still checked against
+the reference's source only: `angle`, `s2n`, `window_nan`, `window_replace`, `rotate_u_v`, and encoding values beyond the int16
+range (the example's s2n field shows that the reference's cast WRAPS them, -5536 for 600.0; this restatement saturates).
+Reference quirks are kept (the example confirms the first: `variance` removes nothing there):
 ``variance`` clamps the mean from BELOW with 1e30 (mask.py:273-274, `np.maximum`), and ``helpers.stack_window`` leaves
 out the last positive y stride (helpers.py:676, `range(wdw_y_min, wdw_y_max)`).
 """

@@ -92,6 +92,82 @@ def test_oracle_encoding_round_trip():
 
 
 # ---------------------------------------------------------------------------------------------------------------------------
+# CPU: THE PIN - the reference's own example output of its mask stack (tests/golden/ngwerere_masks.npz, made from the two netCDF
+# files the reference ships by tests/golden/make_mask_golden.py)
+# ---------------------------------------------------------------------------------------------------------------------------
+def _reference_example():
+    import os
+
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ngwerere_masks.npz"))
+    shape = tuple(int(v) for v in d["shape"])
+    kept = np.unpackbits(d["kept_bits"])[: int(np.prod(shape))].reshape(shape).astype(bool)
+    return d, kept
+
+
+def _notebook_03_mask_sequence(fields):
+    """examples/03_Plotting_and_masking_velocimetry_results.ipynb, cell 10: seven masks with pyorc's defaults, each applied in place
+    (`ds[var].where(mask)` on every variable, mask.py:84-88) before the next one is computed; `angle(...)` is called WITHOUT
+    inplace there and changes nothing; `window_mean(..., reduce_time=True)` decides on the time-mean fields (mask.py:51-52)."""
+    f = [np.array(a, copy=True) for a in fields]
+    steps = [lambda f: MO.corr(f[2]),
+             lambda f: MO.minmax(f[0], f[1]),
+             lambda f: MO.rolling(f[0], f[1]),
+             lambda f: MO.outliers(f[0], f[1]),
+             lambda f: MO.variance(f[0], f[1]),
+             lambda f: MO.count(f[0]),
+             lambda f: MO.window_mean(MO.time_stats(f[0])[0], MO.time_stats(f[1])[0], tolerance=0.5, wdw=2)]
+    kept_after = []
+    for fn in steps:
+        f = MO.apply_masks(f, [fn(f)])
+        kept_after.append(float(np.isfinite(f[0]).mean()))
+    return f, kept_after
+
+
+def test_oracle_reproduces_the_reference_mask_example_exactly():
+    """pyorc ships the input (ngwerere_piv.nc) AND the output (ngwerere_masked.nc) of its own mask stack - xarray + pyorc/api/mask.py
+    on 125 x 59 x 66 values.  The numpy restatement must leave exactly the same 93 824 of 486 750 values standing (80.7 % are
+    masked away, so every one of corr, minmax, rolling, outliers, count and window_mean decides thousands of values; `variance`
+    must change nothing - the reference's `np.maximum(mean, 1e30)` quirk).  This pins oracle/mask_oracle.py: the float32
+    arithmetic and comparison semantics, skipna means / std (ddof 0), the centred rolling maximum, the stack_window strides
+    (including the missing last y stride), reduce_time and the in-place sequence, and the CF decode in front of it."""
+    d, kept = _reference_example()
+    assert float(d["scale_factor"]) == MO.SCALE and int(d["fill_value"]) == MO.FILL      # const.py:80-83 as found in the files
+    fields = [MO.decode_int16(d[k]) for k in ("v_x", "v_y", "corr")]
+    assert all(a.dtype == F32 for a in fields)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", category=RuntimeWarning)
+        out, kept_after = _notebook_03_mask_sequence(fields)
+    got = np.isfinite(out[0])
+    assert got.sum() == kept.sum() == 93824
+    assert np.array_equal(got, kept)                                   # not one value differs
+    assert np.array_equal(np.isfinite(out[2]), kept)                   # the same mask on every variable
+    assert kept_after[4] == kept_after[3]                              # variance: no effect (the 1e30 quirk, mask.py:273-274)
+    assert kept_after[0] > kept_after[1] > kept_after[2] > kept_after[3] > kept_after[5] > kept_after[6]
+    # survivors keep their packed value through decode -> where -> encode (what xarray wrote into ngwerere_masked.nc)
+    for k, a in zip(("v_x", "v_y", "corr"), out):
+        q = MO.encode_int16(a)
+        assert np.array_equal(q[kept], d[k][kept]) and (q[~kept] == MO.FILL).all()
+
+
+def test_reference_mask_example_distinguishes_float32_from_float64():
+    """The same sequence in float64 arithmetic misses the reference's output in a few dozen places (values that sit exactly on a
+    threshold after the 0.01 quantisation): the pin is sharp enough to see the arithmetic type - xarray decodes the int16 fields
+    to float32 and pyorc's masks stay in float32."""
+    d, kept = _reference_example()
+    f32 = MO.F32
+    try:
+        MO.F32 = np.float64
+        fields = [np.where(d[k] == MO.FILL, np.nan, d[k].astype(np.float64) * 0.01) for k in ("v_x", "v_y", "corr")]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", category=RuntimeWarning)
+            out, _ = _notebook_03_mask_sequence(fields)
+    finally:
+        MO.F32 = f32
+    diff = int((np.isfinite(out[0]) != kept).sum())
+    assert 0 < diff < 200, diff
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
 # CPU: the accessor's wrapper rules need no device until a kernel is called
 # ---------------------------------------------------------------------------------------------------------------------------
 def make_ds(vx, vy, c, s, time=True):

@@ -22,7 +22,9 @@ PARITY PIN STATUS: PINNED against the reference's own golden vectors.  tests/gol
 the reference's Python (imported from /root/reference) up to the ffpiv call and this oracle then reproduces both
 pinned ``v_x`` vectors of pyorc's tests/test_frames.py:139-153 (window 10, per-time-step and ensemble mode) to
 < 2e-8 m/s (the pins are printed with 8 digits) - tests/test_golden.py.  ``v_y``, ``corr`` and ``s2n`` are not
-value-checked by any reference test.  The switches below mark the details that pyorc's source does not determine
+value-checked by any reference test; the SIGN convention of ``v_y`` and the units are confirmed on the result file the reference
+ships (examples/ngwerere/ngwerere_piv.nc, an older engine's output: spatial correlation +0.79 for v_y, 0.73 for v_x over 125 pairs -
+tests/test_reference_example.py).  The switches below mark the details that pyorc's source does not determine
 (they live in ffpiv); CLIP_NORMALIZED is decided by the pin, GAUSS_EPS and BORDER_RULE are not observable in it.
 
 All FFTs are pocketfft (numpy.fft / scipy.fft) in float64 - the same algorithm family rocket-fft binds.

@@ -149,6 +149,33 @@ def test_oracle_reproduces_the_reference_mask_example_exactly():
         assert np.array_equal(q[kept], d[k][kept]) and (q[~kept] == MO.FILL).all()
 
 
+def test_mask_fixture_is_what_the_reference_files_hold():
+    """Where /root/reference exists (this container), the committed fixture is re-derived from the two netCDF4 files with the
+    minimal HDF5 parser (tests/golden/h5min.py): packed fields, surviving values, CF attributes."""
+    import os
+    import sys
+
+    ref = "/root/reference/examples/ngwerere"
+    if not os.path.exists(os.path.join(ref, "ngwerere_masked.nc")):
+        pytest.skip("/root/reference is not present (GPU box)")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import h5min
+
+    d, kept = _reference_example()
+    hp, hm = h5min.H5(os.path.join(ref, "ngwerere_piv.nc")), h5min.H5(os.path.join(ref, "ngwerere_masked.nc"))
+    np_, nm = h5min.dataset_names(hp), h5min.dataset_names(hm)
+    assert {"v_x", "v_y", "corr", "s2n", "time", "y", "x"} <= set(np_) and set(np_) == set(nm)
+    for k in ("v_x", "v_y", "corr"):
+        a = hp.read(np_[k])
+        assert a.dtype == np.int16 and np.array_equal(a, d[k])
+        m = hm.read(nm[k])
+        assert np.array_equal(m != -9999, kept) and np.array_equal(m[kept], a[kept])
+    assert [float(np.asarray(v).reshape(-1)[0]) for v in h5min.dense_attributes(hm, "scale_factor")] == [0.01] * 4
+    fills = [v for v in h5min.dense_attributes(hm, "_FillValue") if np.asarray(v).dtype == np.int16]
+    assert len(fills) == 4 and all(int(np.asarray(v).reshape(-1)[0]) == -9999 for v in fills)
+    assert np.allclose(hp.read(np_["time"]), d["time"])
+
+
 def test_reference_mask_example_distinguishes_float32_from_float64():
     """The same sequence in float64 arithmetic misses the reference's output in a few dozen places (values that sit exactly on a
     threshold after the 0.01 quantisation): the pin is sharp enough to see the arithmetic type - xarray decodes the int16 fields

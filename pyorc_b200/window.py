@@ -21,7 +21,8 @@ __all__ = [
 
 
 def round_to_even(input_tuple):
-    """Round each entry to an even integer; odd values go up to the next even one (frames.py:167)."""
+    """Round each entry to an even integer; odd values go up to the next even one (frames.py:167).  ffpiv's own rule for odd
+    sizes is not observable in pyorc's source or tests; rounding up keeps the requested window covered."""
     out = []
     for x in input_tuple:
         r = int(round(x))
